@@ -1,0 +1,209 @@
+/*
+ * cdgpu.h — C ABI of libcdgpu.so, the B200 (sm_100a) drop-in for the active-set
+ * proximal coordinate-descent hot path of CoordinateDescent.jl.
+ *
+ * The reference has no FFI layer; its "operator API" is the four-function loss
+ * protocol initialize!/gradient/numCoordinates/descendCoordinate!
+ * (src/cd_differentiable_function.jl:1-35) called once per coordinate from
+ * _cdPass! (src/coordinate_descent.jl:94-110).  A per-coordinate FFI call is
+ * useless for a GPU, so this ABI sits one level up: one call == one whole
+ * coordinateDescent! / LassoPath / scaledLasso! / locpolyl1 invocation.
+ *
+ * Conventions
+ *   - every entry point returns an int status (CDGPU_OK == 0); the message for a
+ *     non-zero status is cdgpu_last_error() (thread-local).
+ *   - all matrices are column-major Float64 with an explicit leading dimension,
+ *     exactly Julia's Matrix{Float64} / StridedMatrix layout.
+ *   - the iterate crosses the boundary as ProximalBase's SparseIterate triple
+ *     (nzval, nzval2ind, nnz): nzval2ind is 1-BASED Int64, both arrays have
+ *     capacity p, entries 1..nnz are meaningful, order == visit order of an
+ *     active-set pass (test/atom_iterator.jl:13-28).
+ *   - host pointers are owned by the caller; the library copies what it needs to
+ *     the device at *_create time and owns all device memory behind the handle.
+ *   - calls are blocking; a handle is not thread-safe; no C++ exception crosses.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with CDGPU_ENODEV.
+ *
+ * The CPU oracle (oracle/cdref.c -> libcdref.so) exports the same functions with
+ * the prefix cdref_ instead of cdgpu_ so one harness can drive both.
+ */
+#ifndef CDGPU_H
+#define CDGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDGPU_VERSION 100 /* 0.1.0 */
+
+/* status codes; mapping to the reference's exceptions in parentheses */
+enum {
+  CDGPU_OK = 0,
+  CDGPU_EDIM = 1,   /* DimensionMismatch: coordinate_descent.jl:13,15; cd_differentiable_function.jl:53,129,212 */
+  CDGPU_EARG = 2,   /* ArgumentError: cd_differentiable_function.jl:306; lasso.jl:128 */
+  CDGPU_ECUDA = 3,  /* ErrorException(cdgpu_last_error()) */
+  CDGPU_ENOMEM = 4, /* ErrorException */
+  CDGPU_ENCCL = 5,  /* ErrorException */
+  CDGPU_ENODEV = 6, /* ErrorException: no CUDA device / driver (no CPU fallback) */
+  CDGPU_ECAP = 7    /* caller-provided output capacity too small */
+};
+
+/* loss kinds == the four concrete CoordinateDifferentiableFunction types */
+enum {
+  CDGPU_LOSS_LS = 0,   /* CDLeastSquaresLoss  cd_differentiable_function.jl:43-111  */
+  CDGPU_LOSS_WLS = 1,  /* CDWeightedLSLoss    cd_differentiable_function.jl:118-194 */
+  CDGPU_LOSS_SQRT = 2, /* CDSqrtLassoLoss     cd_differentiable_function.jl:202-291 */
+  CDGPU_LOSS_QUAD = 3  /* CDQuadraticLoss     cd_differentiable_function.jl:299-348 */
+};
+
+/* randomize: 0 = OrderedIterator (atom_iterator.jl:9-37)
+ *            1 = RandomIterator  (atom_iterator.jl:41-75): a fresh uniform random
+ *                permutation per pass.  Julia's global RNG stream cannot be
+ *                reproduced; the permutation is the argsort of a counter-based
+ *                hash keyed by (seed, pass counter, position), identical in the
+ *                oracle (mode 1) and on the device. */
+typedef struct cdgpu_options {
+  int64_t maxIter;   /* utils.jl:8   default 2000 */
+  double optTol;     /* utils.jl:9   default 1e-7 */
+  int32_t randomize; /* utils.jl:10  default 1 (true) */
+  int32_t warmStart; /* utils.jl:11  default 1 (true) */
+  int64_t numSteps;  /* utils.jl:12  default 50 */
+  uint64_t seed;     /* replaces Julia's global RNG; default 0 */
+} cdgpu_options;
+
+/* initProcedure of IterLassoOptions (utils.jl:24-39) */
+enum { CDGPU_INIT_SCREENING = 0, CDGPU_INIT_STD = 1, CDGPU_INIT_WARMSTART = 2 };
+
+typedef struct cdgpu_iter_options {
+  int64_t maxIter;       /* utils.jl:25 default 20   */
+  double optTol;         /* utils.jl:26 default 1e-2 */
+  int32_t initProcedure; /* utils.jl:27 default :Screening */
+  int32_t _pad;
+  int64_t sinit;         /* utils.jl:28 default 5  */
+  double sigma_init;     /* utils.jl:29 default 1. */
+  cdgpu_options optionsCD;
+} cdgpu_iter_options;
+
+/* What one solve did.  The reference keeps no such record (it is silent even on
+ * hitting maxIter, coordinate_descent.jl:74-91); the counters are what the
+ * "coordinate updates / s" metric is computed from. */
+typedef struct cdgpu_stats {
+  int64_t passes;      /* _cdPass! calls                        */
+  int64_t full_passes; /* of which over all p coordinates       */
+  int64_t visits;      /* descendCoordinate! calls              */
+  int64_t accepted;    /* visits with h != 0                    */
+  double maxH;         /* max|h| of the last pass               */
+  int32_t converged;   /* 1 iff the loop left through :89       */
+  int32_t outer_iters; /* sigma iterations (scaled lasso), else 0 */
+  double sigma;        /* scaled lasso: last sigma used; else 0 */
+  double device_ms;    /* device time of the solve, CUDA events on the library stream (oracle: host wall ms) */
+} cdgpu_stats;
+
+typedef struct cdgpu_handle_s *cdgpu_handle; /* the loss object "f" */
+
+/* smoothing kernels of varying_coefficient_lasso.jl:5-21 */
+enum { CDGPU_KERNEL_GAUSSIAN = 0, CDGPU_KERNEL_EPANECHNIKOV = 1 };
+
+/* ---------------------------------------------------------------- misc -- */
+int cdgpu_version(void);
+const char *cdgpu_last_error(void);
+int cdgpu_device_count(int *count);
+void cdgpu_default_options(cdgpu_options *o);           /* CDOptions()          utils.jl:14-20 */
+void cdgpu_default_iter_options(cdgpu_iter_options *o); /* IterLassoOptions()   utils.jl:32-39 */
+
+/* ------------------------------------------------------------- handles -- */
+/* CDLeastSquaresLoss(y,X) / CDWeightedLSLoss(y,X,w) / CDSqrtLassoLoss(y,X)
+ * (cd_differentiable_function.jl:52-55,128-131,211-214).  loss_kind in
+ * {LS,WLS,SQRT}; w must be non-NULL iff WLS.  n,p >= 1, ldx >= n else EDIM.
+ * X, y, w are HOST pointers and are copied to device `device`. */
+int cdgpu_naive_create(cdgpu_handle *h, int loss_kind, const double *X, int64_t n, int64_t p, int64_t ldx,
+                       const double *y, const double *w, int device);
+/* same, X/y/w are DEVICE pointers on `device`; X is used in place (not copied,
+ * never written) and must outlive the handle. */
+int cdgpu_naive_create_dev(cdgpu_handle *h, int loss_kind, const double *dX, int64_t n, int64_t p, int64_t ldx,
+                           const double *dy, const double *dw, int device);
+
+/* CDQuadraticLoss(A,b) (cd_differentiable_function.jl:305-308): A must be exactly
+ * symmetric and length(b)==size(A,2) else EARG. */
+int cdgpu_quad_create(cdgpu_handle *h, const double *A, int64_t p, int64_t lda, const double *b, int device);
+int cdgpu_quad_create_dev(cdgpu_handle *h, const double *dA, int64_t p, int64_t lda, const double *db, int device);
+
+/* Covariance form straight from the data: A = X'X/n, b = -X'y/n (what the
+ * reference's users write by hand, test/lasso.jl:48,88) formed on the device by
+ * the FP64 tensor-core SYRK kernel, then wrapped as a QUAD handle. */
+int cdgpu_gram_create(cdgpu_handle *h, const double *X, int64_t n, int64_t p, int64_t ldx, const double *y,
+                      int device);
+int cdgpu_gram_create_dev(cdgpu_handle *h, const double *dX, int64_t n, int64_t p, int64_t ldx, const double *dy,
+                          int device);
+/* Row-sharded variant for one-process-per-GPU jobs: every rank passes its own
+ * n_local rows; partial X'X and X'y are summed over ranks with one
+ * ncclAllReduce on the communicator made by cdgpu_comm_init (NULL comm == single
+ * rank), then scaled by 1/n_total.  Every rank ends with the same QUAD handle. */
+typedef struct cdgpu_comm_s *cdgpu_comm;
+int cdgpu_comm_unique_id(void *id128);                    /* rank 0: 128-byte ncclUniqueId */
+int cdgpu_comm_init(cdgpu_comm *c, const void *id128, int rank, int nranks, int device);
+int cdgpu_comm_destroy(cdgpu_comm c);
+int cdgpu_gram_create_sharded(cdgpu_handle *h, const double *dX_local, int64_t n_local, int64_t n_total, int64_t p,
+                              int64_t ldx, const double *dy_local, cdgpu_comm comm, int device);
+
+int cdgpu_destroy(cdgpu_handle h);
+int cdgpu_dims(cdgpu_handle h, int64_t *n, int64_t *p, int *loss_kind);
+/* device time (ms, CUDA events) of the last Gram formation behind a QUAD handle
+ * made by cdgpu_gram_create*; 0 otherwise */
+int cdgpu_gram_ms(cdgpu_handle h, double *ms);
+/* copy A (p*p, ld p) and/or b back to the host (Julia's f.A / f.b) */
+int cdgpu_quad_get(cdgpu_handle h, double *A_out, double *b_out);
+
+/* -------------------------------------------------------------- solves -- */
+/* coordinateDescent!(x, f, ProxL1(lambda0[, omega]), options)
+ * (coordinate_descent.jl:7-39).  omega == NULL is ProxL1{T,Nothing}.
+ * x in/out as the SparseIterate triple; with options->warmStart == 0 the input
+ * iterate is ignored (fill!(x,0), :25) and the internal lambda continuation of
+ * :28-36 runs.  stats may be NULL. */
+int cdgpu_solve(cdgpu_handle h, double lambda0, const double *omega, const cdgpu_options *opt, double *nzval,
+                int64_t *nzval2ind, int64_t *nnz, cdgpu_stats *stats);
+
+/* Warm-started lambda path: for i in 1..m: coordinateDescent!(x, f,
+ * ProxL1(lambda[i], omega), opt); beta_path[i] = copy(x); stop after the first i
+ * with nnz(x) > max_hat_s (lasso.jl:250-257; max_hat_s < 0 == Inf).  Starts from
+ * x = 0.  Output is CSC over the m columns: colptr[m+1] (0-based offsets),
+ * rowval (1-based), nzval, caller-allocated with `capacity` entries; *m_done is
+ * the number of columns produced.  stats: array of m or NULL. */
+int cdgpu_path(cdgpu_handle h, const double *lambda, int64_t m, const double *omega, const cdgpu_options *opt,
+               int64_t max_hat_s, int64_t capacity, int64_t *colptr, int64_t *rowval, double *nzval,
+               int64_t *m_done, cdgpu_stats *stats);
+
+/* scaledLasso!(x, X, y, lambda, omega, IterLassoOptions) (lasso.jl:107-144) on an
+ * LS handle; the sigma loop runs on the device.  *sigma_out = std(r) as returned
+ * in LassoSolution (:143); stats->sigma = the sigma of the last ProxL1. */
+int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, const cdgpu_iter_options *opt,
+                       double *nzval, int64_t *nzval2ind, int64_t *nnz, double *sigma_out, cdgpu_stats *stats);
+
+/* f.r (naive handles, length n) or f.Ax (QUAD, length p) after the last solve;
+ * LassoSolution.residuals aliases f.r (lasso.jl:37). */
+int cdgpu_state(cdgpu_handle h, double *out);
+/* _stdX!(out, X) / _stdX!(out, w, X) (utils.jl:127-151) on a naive handle; w NULL
+ * uses the unweighted form even on a WLS handle. */
+int cdgpu_stdx(cdgpu_handle h, const double *w, double *out);
+/* _findLambdaMax at x = 0 (coordinate_descent.jl:118-149) */
+int cdgpu_lambda_max(cdgpu_handle h, const double *omega, double *out);
+
+/* locpolyl1(X, z, y, zgrid, degree, kernel, lambda0, refit=false, options)
+ * (varying_coefficient_lasso.jl:30-79): one kernel-weighted local-polynomial
+ * lasso per grid point, all grid points solved concurrently on the device (one
+ * CTA per local problem).  out is dense ep x m column-major, ep = p*(degree+1),
+ * column index (j-1)(degree+1)+1+l as _expand_X! (:550-569).  The reference
+ * warm-starts each grid point from its predecessor (:56,:68); the batch starts
+ * every problem from 0 — solutions agree at convergence.  stats: array of m or
+ * NULL.  Only grid points [m_begin, m_end) are solved (sharding hook). */
+int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                   const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                   double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
+                   cdgpu_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDGPU_H */
