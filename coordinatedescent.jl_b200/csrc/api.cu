@@ -1,0 +1,810 @@
+// api.cu — the extern "C" surface of libcdgpu.so (include/cdgpu.h).  Host-side control only:
+// argument checks with the reference's error behaviour, device buffers, kernel launches, result
+// copies.  No algorithmic CPU path exists here: without a CUDA device every compute entry fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+#define API extern "C" __attribute__((visibility("default")))
+
+static thread_local char g_err[1024];
+int cdgpu_set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+API int cdgpu_version(void) { return CDGPU_VERSION; }
+API const char *cdgpu_last_error(void) { return g_err; }
+API int cdgpu_device_count(int *count) {
+  if (!count) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return cdgpu_set_error(CDGPU_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return CDGPU_OK;
+}
+API void cdgpu_default_options(cdgpu_options *o) { // CDOptions() utils.jl:14-20
+  o->maxIter = 2000;
+  o->optTol = 1e-7;
+  o->randomize = 1;
+  o->warmStart = 1;
+  o->numSteps = 50;
+  o->seed = 0;
+}
+API void cdgpu_default_iter_options(cdgpu_iter_options *o) { // IterLassoOptions() utils.jl:32-39
+  o->maxIter = 20;
+  o->optTol = 1e-2;
+  o->initProcedure = CDGPU_INIT_SCREENING;
+  o->_pad = 0;
+  o->sinit = 5;
+  o->sigma_init = 1.0;
+  cdgpu_default_options(&o->optionsCD);
+}
+
+// --------------------------------------------------------------- handles --
+static int use_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return cdgpu_set_error(CDGPU_ENODEV, "no CUDA device (%s); libcdgpu has no CPU fallback",
+                           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return cdgpu_set_error(CDGPU_EARG, "device %d out of range [0,%d)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  return CDGPU_OK;
+}
+
+template <class T>
+static int dalloc(T **p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  CUDA_TRY(cudaMalloc((void **)p, count * sizeof(T)));
+  return CDGPU_OK;
+}
+
+static int handle_common_alloc(cdgpu_handle_s *h) {
+  const size_t p = (size_t)h->p;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+  CD_TRY(dalloc(&h->dbeta, p));
+  CD_TRY(dalloc(&h->dact, p));
+  CD_TRY(dalloc(&h->dactval, p));
+  CD_TRY(dalloc(&h->dnact, 1));
+  CD_TRY(dalloc(&h->dinlist, p));
+  CD_TRY(dalloc(&h->domega, p));
+  CD_TRY(dalloc(&h->dscr, 8 * p + 8 * (size_t)h->n + 64));
+  CD_TRY(dalloc(&h->discr, 4 * p + 64));
+  CD_TRY(dalloc(&h->dflag, 8));
+  CUDA_TRY(cudaMemsetAsync(h->dbeta, 0, p * sizeof(double), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dinlist, 0, p, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dnact, 0, sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 8 * sizeof(int), h->stream));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  return CDGPU_OK;
+}
+
+API int cdgpu_destroy(cdgpu_handle h) {
+  if (!h) return CDGPU_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->ownX) cudaFree(h->dX);
+  if (h->owny) cudaFree(h->dy);
+  if (h->ownw) cudaFree(h->dw);
+  cudaFree(h->dstate);
+  cudaFree(h->daux);
+  cudaFree(h->dbeta);
+  cudaFree(h->dact);
+  cudaFree(h->dactval);
+  cudaFree(h->dnact);
+  cudaFree(h->dinlist);
+  cudaFree(h->domega);
+  cudaFree(h->dscr);
+  cudaFree(h->discr);
+  cudaFree(h->dstats);
+  cudaFree(h->dlam);
+  cudaFree(h->dcolptr);
+  cudaFree(h->drowval);
+  cudaFree(h->dnzval);
+  cudaFree(h->dflag);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CDGPU_OK;
+}
+
+struct HandleGuard { // frees a half-built handle on an error return
+  cdgpu_handle_s *h;
+  ~HandleGuard() {
+    if (h) cdgpu_destroy(h);
+  }
+  cdgpu_handle_s *release() {
+    cdgpu_handle_s *t = h;
+    h = nullptr;
+    return t;
+  }
+};
+
+static int naive_finish(cdgpu_handle_s *h) {
+  // r = copy(y) (cd_differentiable_function.jl:54); column weights a_k = sum_i [w_i] X_ik^2
+  CD_TRY(dalloc(&h->dstate, (size_t)h->n));
+  CD_TRY(dalloc(&h->daux, (size_t)h->p));
+  CUDA_TRY(cudaMemcpyAsync(h->dstate, h->dy, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CD_TRY(launch_colsq(h, h->dX, h->ld, (int)h->n, (int)h->p, h->kind == CDGPU_LOSS_WLS ? h->dw : nullptr, h->daux,
+                      false));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return CDGPU_OK;
+}
+
+static int naive_check(cdgpu_handle *out, int loss_kind, const void *X, int64_t n, int64_t p, int64_t ldx,
+                       const void *y, const void *w) {
+  if (!out || !X || !y) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (loss_kind != CDGPU_LOSS_LS && loss_kind != CDGPU_LOSS_WLS && loss_kind != CDGPU_LOSS_SQRT)
+    return cdgpu_set_error(CDGPU_EARG, "loss_kind must be LS, WLS or SQRT");
+  if ((loss_kind == CDGPU_LOSS_WLS) != (w != nullptr))
+    return cdgpu_set_error(CDGPU_EARG, "w must be given iff the loss is CDWeightedLSLoss");
+  if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (n > 0x7fffffff || p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "n and p must fit in 31 bits");
+  return CDGPU_OK;
+}
+
+API int cdgpu_naive_create(cdgpu_handle *out, int loss_kind, const double *X, int64_t n, int64_t p, int64_t ldx,
+                           const double *y, const double *w, int device) {
+  CD_TRY(naive_check(out, loss_kind, X, n, p, ldx, y, w));
+  CD_TRY(use_device(device));
+  HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
+  cdgpu_handle_s *h = g.h;
+  if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+  h->kind = loss_kind;
+  h->device = device;
+  h->n = n;
+  h->p = p;
+  h->ld = (n + 1) & ~(int64_t)1; // 16-byte aligned columns on the device
+  CD_TRY(handle_common_alloc(h));
+  CD_TRY(dalloc(&h->dX, (size_t)h->ld * (size_t)p));
+  h->ownX = true;
+  CD_TRY(dalloc(&h->dy, (size_t)n));
+  h->owny = true;
+  if (h->ld != n) CUDA_TRY(cudaMemsetAsync(h->dX, 0, (size_t)h->ld * p * sizeof(double), h->stream));
+  CUDA_TRY(cudaMemcpy2DAsync(h->dX, h->ld * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), p,
+                             cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->dy, y, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (w) {
+    CD_TRY(dalloc(&h->dw, (size_t)n));
+    h->ownw = true;
+    CUDA_TRY(cudaMemcpyAsync(h->dw, w, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  CD_TRY(naive_finish(h));
+  *out = g.release();
+  return CDGPU_OK;
+}
+
+API int cdgpu_naive_create_dev(cdgpu_handle *out, int loss_kind, const double *dX, int64_t n, int64_t p, int64_t ldx,
+                               const double *dy, const double *dw, int device) {
+  CD_TRY(naive_check(out, loss_kind, dX, n, p, ldx, dy, dw));
+  CD_TRY(use_device(device));
+  HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
+  cdgpu_handle_s *h = g.h;
+  if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+  h->kind = loss_kind;
+  h->device = device;
+  h->n = n;
+  h->p = p;
+  h->ld = ldx;
+  CD_TRY(handle_common_alloc(h));
+  h->dX = const_cast<double *>(dX);
+  h->dy = const_cast<double *>(dy);
+  h->dw = const_cast<double *>(dw);
+  CUDA_TRY(cudaDeviceSynchronize()); // the caller's stream may still be producing X / y
+  CD_TRY(naive_finish(h));
+  *out = g.release();
+  return CDGPU_OK;
+}
+
+static int quad_finish(cdgpu_handle_s *h, bool check_sym) {
+  CD_TRY(dalloc(&h->dstate, (size_t)h->p));
+  CD_TRY(dalloc(&h->daux, (size_t)h->p));
+  CUDA_TRY(cudaMemsetAsync(h->dstate, 0, (size_t)h->p * sizeof(double), h->stream)); // Ax = zeros(p) :307
+  if (check_sym) {
+    CUDA_TRY(cudaMemsetAsync(h->dflag, 0, sizeof(int), h->stream));
+    CD_TRY(launch_check_symmetric(h, h->dX, h->ld, (int)h->p, h->dflag));
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, h->dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (bad) return cdgpu_set_error(CDGPU_EARG, "ArgumentError: A is not symmetric");
+  }
+  CD_TRY(launch_extract_ainv(h, h->dX, h->ld, (int)h->p, h->daux));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return CDGPU_OK;
+}
+
+API int cdgpu_quad_create(cdgpu_handle *out, const double *A, int64_t p, int64_t lda, const double *b, int device) {
+  if (!out || !A || !b) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (p < 1 || lda < p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
+  CD_TRY(use_device(device));
+  HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
+  cdgpu_handle_s *h = g.h;
+  if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+  h->kind = CDGPU_LOSS_QUAD;
+  h->device = device;
+  h->n = p;
+  h->p = p;
+  h->ld = (p + 1) & ~(int64_t)1;
+  CD_TRY(handle_common_alloc(h));
+  CD_TRY(dalloc(&h->dX, (size_t)h->ld * (size_t)p));
+  h->ownX = true;
+  CD_TRY(dalloc(&h->dy, (size_t)p));
+  h->owny = true;
+  if (h->ld != p) CUDA_TRY(cudaMemsetAsync(h->dX, 0, (size_t)h->ld * p * sizeof(double), h->stream));
+  CUDA_TRY(cudaMemcpy2DAsync(h->dX, h->ld * sizeof(double), A, lda * sizeof(double), p * sizeof(double), p,
+                             cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->dy, b, p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CD_TRY(quad_finish(h, true));
+  *out = g.release();
+  return CDGPU_OK;
+}
+
+API int cdgpu_quad_create_dev(cdgpu_handle *out, const double *dA, int64_t p, int64_t lda, const double *db,
+                              int device) {
+  if (!out || !dA || !db) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (p < 1 || lda < p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
+  CD_TRY(use_device(device));
+  HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
+  cdgpu_handle_s *h = g.h;
+  if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+  h->kind = CDGPU_LOSS_QUAD;
+  h->device = device;
+  h->n = p;
+  h->p = p;
+  h->ld = lda;
+  CD_TRY(handle_common_alloc(h));
+  h->dX = const_cast<double *>(dA);
+  h->dy = const_cast<double *>(db);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CD_TRY(quad_finish(h, true));
+  *out = g.release();
+  return CDGPU_OK;
+}
+
+// A = X'X/n, b = -X'y/n on the device, wrapped as a QUAD handle
+static int gram_build(cdgpu_handle *out, const double *dX, int64_t n_local, int64_t n_total, int64_t p, int64_t ldx,
+                      const double *dy, int device, cdgpu_comm comm, double *pinned_unused);
+int cdgpu_comm_allreduce(cdgpu_comm c, double *buf, size_t count, cudaStream_t s); // nccl_comm.cu
+
+static int gram_build(cdgpu_handle *out, const double *dX, int64_t n_local, int64_t n_total, int64_t p, int64_t ldx,
+                      const double *dy, int device, cdgpu_comm comm, double *) {
+  HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
+  cdgpu_handle_s *h = g.h;
+  if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+  h->kind = CDGPU_LOSS_QUAD;
+  h->device = device;
+  h->n = p;
+  h->p = p;
+  h->ld = (p + 1) & ~(int64_t)1;
+  CD_TRY(handle_common_alloc(h));
+  // A and b live in ONE allocation so a single allreduce covers both
+  const size_t na = (size_t)h->ld * (size_t)p;
+  CD_TRY(dalloc(&h->dX, na + (size_t)p));
+  h->ownX = true;
+  h->dy = h->dX + na;
+  h->owny = false;
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  const bool sharded = comm != nullptr;
+  CD_TRY(launch_gram(h, dX, n_local, (int)p, ldx, dy, h->dX, h->dy, (double)n_total, !sharded));
+  if (sharded) {
+    CD_TRY(cdgpu_comm_allreduce(comm, h->dX, na + (size_t)p, h->stream));
+    CD_TRY(launch_scale_gram(h, h->dX, h->dy, (int)p, (double)n_total));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->gram_ms = ms;
+  CD_TRY(quad_finish(h, false)); // symmetric by construction (mirrored tiles)
+  *out = g.release();
+  return CDGPU_OK;
+}
+
+API int cdgpu_gram_create_dev(cdgpu_handle *out, const double *dX, int64_t n, int64_t p, int64_t ldx,
+                              const double *dy, int device) {
+  if (!out || !dX || !dy) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
+  CD_TRY(use_device(device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return gram_build(out, dX, n, n, p, ldx, dy, device, nullptr, nullptr);
+}
+
+API int cdgpu_gram_create_sharded(cdgpu_handle *out, const double *dX_local, int64_t n_local, int64_t n_total,
+                                  int64_t p, int64_t ldx, const double *dy_local, cdgpu_comm comm, int device) {
+  if (!out || !dX_local || !dy_local) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (n_local < 1 || n_total < n_local || p < 1 || ldx < n_local) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
+  CD_TRY(use_device(device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return gram_build(out, dX_local, n_local, n_total, p, ldx, dy_local, device, comm, nullptr);
+}
+
+API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t p, int64_t ldx, const double *y,
+                          int device) {
+  if (!out || !X || !y) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
+  CD_TRY(use_device(device));
+  // stage X on the device with 16-byte aligned columns, form the Gram, drop the staging copy
+  const int64_t ld = (n + 1) & ~(int64_t)1;
+  double *dX = nullptr, *dy = nullptr;
+  CD_TRY(dalloc(&dX, (size_t)ld * (size_t)p));
+  int rc = dalloc(&dy, (size_t)n);
+  if (rc) {
+    cudaFree(dX);
+    return rc;
+  }
+  auto cleanup = [&]() {
+    cudaFree(dX);
+    cudaFree(dy);
+  };
+  cudaError_t e = cudaSuccess;
+  if (ld != n) e = cudaMemset(dX, 0, (size_t)ld * p * sizeof(double));
+  if (e == cudaSuccess)
+    e = cudaMemcpy2D(dX, ld * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), p, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dy, y, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cleanup();
+    return cdgpu_set_error(CDGPU_ECUDA, "H2D copy of X failed: %s", cudaGetErrorString(e));
+  }
+  rc = gram_build(out, dX, n, n, p, ld, dy, device, nullptr, nullptr);
+  cleanup();
+  return rc;
+}
+
+API int cdgpu_dims(cdgpu_handle h, int64_t *n, int64_t *p, int *loss_kind) {
+  if (!h) return cdgpu_set_error(CDGPU_EARG, "null handle");
+  if (n) *n = h->n;
+  if (p) *p = h->p;
+  if (loss_kind) *loss_kind = h->kind;
+  return CDGPU_OK;
+}
+API int cdgpu_gram_ms(cdgpu_handle h, double *ms) {
+  if (!h || !ms) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  *ms = h->gram_ms;
+  return CDGPU_OK;
+}
+API int cdgpu_quad_get(cdgpu_handle h, double *A_out, double *b_out) {
+  if (!h || h->kind != CDGPU_LOSS_QUAD) return cdgpu_set_error(CDGPU_EARG, "not a CDQuadraticLoss handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (A_out)
+    CUDA_TRY(cudaMemcpy2D(A_out, h->p * sizeof(double), h->dX, h->ld * sizeof(double), h->p * sizeof(double), h->p,
+                          cudaMemcpyDeviceToHost));
+  if (b_out) CUDA_TRY(cudaMemcpy(b_out, h->dy, h->p * sizeof(double), cudaMemcpyDeviceToHost));
+  return CDGPU_OK;
+}
+
+// ---------------------------------------------------------------- solves --
+static int check_opts(const cdgpu_options *o) {
+  if (!o) return cdgpu_set_error(CDGPU_EARG, "null options");
+  if (o->maxIter < 0 || o->numSteps < 1) return cdgpu_set_error(CDGPU_EARG, "bad options");
+  if (o->randomize < 0 || o->randomize > 1)
+    return cdgpu_set_error(CDGPU_EARG, "randomize must be 0 (ordered) or 1 (hash-keyed random permutation)");
+  return CDGPU_OK;
+}
+
+static int grow(cdgpu_handle_s *h, size_t nlam, size_t outcap, size_t outcols) {
+  if ((int64_t)nlam > h->nlam) {
+    cudaFree(h->dlam);
+    cudaFree(h->dstats);
+    h->dlam = nullptr;
+    h->dstats = nullptr;
+    h->nlam = 0;
+    CD_TRY(dalloc(&h->dlam, nlam));
+    CD_TRY(dalloc(&h->dstats, nlam));
+    h->nlam = (int64_t)nlam;
+  }
+  if ((int64_t)outcap > h->outcap) {
+    cudaFree(h->drowval);
+    cudaFree(h->dnzval);
+    h->drowval = nullptr;
+    h->dnzval = nullptr;
+    h->outcap = 0;
+    CD_TRY(dalloc(&h->drowval, outcap));
+    CD_TRY(dalloc(&h->dnzval, outcap));
+    h->outcap = (int64_t)outcap;
+  }
+  if ((int64_t)outcols > h->outcols) {
+    cudaFree(h->dcolptr);
+    h->dcolptr = nullptr;
+    h->outcols = 0;
+    CD_TRY(dalloc(&h->dcolptr, outcols + 1));
+    h->outcols = (int64_t)outcols;
+  }
+  return CDGPU_OK;
+}
+
+// upload the SparseIterate triple (1-based) as the device list (0-based)
+static int upload_iterate(cdgpu_handle_s *h, const double *nzval, const int64_t *nzval2ind, int64_t nnz) {
+  if (nnz < 0 || nnz > h->p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch: bad iterate");
+  std::vector<int> act((size_t)nnz);
+  std::vector<unsigned char> seen((size_t)h->p, 0);
+  for (int64_t i = 0; i < nnz; ++i) {
+    int64_t k = nzval2ind[i];
+    if (k < 1 || k > h->p || seen[(size_t)k - 1]) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch: bad iterate");
+    seen[(size_t)k - 1] = 1;
+    act[(size_t)i] = (int)(k - 1);
+  }
+  int m = (int)nnz;
+  if (nnz) {
+    CUDA_TRY(cudaMemcpyAsync(h->dact, act.data(), (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->dactval, nzval, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->dnact, &m, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream)); // `act` and `m` are stack/heap temporaries
+  return CDGPU_OK;
+}
+static int download_iterate(cdgpu_handle_s *h, double *nzval, int64_t *nzval2ind, int64_t *nnz) {
+  int m = 0;
+  CUDA_TRY(cudaMemcpyAsync(&m, h->dnact, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  std::vector<int> act((size_t)m);
+  if (m) {
+    CUDA_TRY(cudaMemcpyAsync(act.data(), h->dact, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(nzval, h->dactval, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  for (int i = 0; i < m; ++i) nzval2ind[i] = (int64_t)act[(size_t)i] + 1;
+  *nnz = m;
+  return CDGPU_OK;
+}
+static int set_zero_iterate(cdgpu_handle_s *h) {
+  CUDA_TRY(cudaMemsetAsync(h->dnact, 0, sizeof(int), h->stream));
+  return CDGPU_OK;
+}
+static const double *upload_omega(cdgpu_handle_s *h, const double *omega, int *rc) {
+  *rc = CDGPU_OK;
+  if (!omega) return nullptr;
+  cudaError_t e = cudaMemcpyAsync(h->domega, omega, (size_t)h->p * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) *rc = cdgpu_set_error(CDGPU_ECUDA, "H2D omega: %s", cudaGetErrorString(e));
+  return h->domega;
+}
+static void stats_to_abi(const DevStats &d, double ms, cdgpu_stats *s) {
+  s->passes = d.passes;
+  s->full_passes = d.full_passes;
+  s->visits = d.visits;
+  s->accepted = d.accepted;
+  s->maxH = d.maxH;
+  s->converged = d.converged;
+  s->outer_iters = d.outer_iters;
+  s->sigma = d.sigma;
+  s->device_ms = ms;
+}
+static int flag_status(cdgpu_handle_s *h, int *cols_done) {
+  int f[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(f, h->dflag, sizeof f, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (cols_done) *cols_done = f[1];
+  if (f[0] == 1) return cdgpu_set_error(CDGPU_ECAP, "path output capacity too small");
+  if (f[0] == 2) return cdgpu_set_error(CDGPU_ECAP, "active set larger than the in-CTA engine holds (4096)");
+  if (f[0]) return cdgpu_set_error(CDGPU_ECUDA, "kernel reported status %d", f[0]);
+  return CDGPU_OK;
+}
+
+// log-spaced continuation of coordinate_descent.jl:32-33: numSteps+1 points from lmax to l0
+static std::vector<double> continuation(double lmax, double l0, int64_t numSteps) {
+  std::vector<double> v;
+  double l1 = log(lmax), l2 = log(l0);
+  double step = (l2 - l1) / (double)numSteps;
+  for (int64_t i = 0; i <= numSteps; ++i) v.push_back(exp(i == numSteps ? l2 : l1 + (double)i * step));
+  return v;
+}
+
+struct RunCfg {
+  const double *lambdas; // host
+  int nlambda;
+  int accumulate;
+  const cdgpu_options *opt;
+  const double *domega;
+  long long max_hat_s, capacity;
+  bool want_path;
+  // scaled lasso
+  int scaled;
+  long long outerMaxIter;
+  double outerTol, sigma0;
+};
+
+// launches the sweep kernel of the handle's loss over a list of lambdas (device iterate already set)
+static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
+  CD_TRY(grow(h, (size_t)rc.nlambda, rc.want_path ? (size_t)rc.capacity : 0, rc.want_path ? (size_t)rc.nlambda : 0));
+  CUDA_TRY(cudaMemcpyAsync(h->dlam, rc.lambdas, (size_t)rc.nlambda * sizeof(double), cudaMemcpyHostToDevice,
+                           h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 8 * sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dstats, 0, (size_t)rc.nlambda * sizeof(DevStats), h->stream));
+  if (rc.want_path) CUDA_TRY(cudaMemsetAsync(h->dcolptr, 0, ((size_t)rc.nlambda + 1) * sizeof(long long), h->stream));
+  if (h->kind == CDGPU_LOSS_QUAD) {
+    CovArgs a = {};
+    a.A = h->dX;
+    a.lda = h->ld;
+    a.p = (int)h->p;
+    a.b = h->dy;
+    a.ainv = h->daux;
+    a.omega = rc.domega;
+    a.Ax = h->dstate;
+    a.beta = h->dbeta;
+    a.act = h->dact;
+    a.actval = h->dactval;
+    a.nact = h->dnact;
+    a.inlist = h->dinlist;
+    a.scr = h->dscr;
+    a.iscr = h->discr;
+    a.lambdas = h->dlam;
+    a.nlambda = rc.nlambda;
+    a.accumulate = rc.accumulate;
+    a.maxIter = rc.opt->maxIter;
+    a.optTol = rc.opt->optTol;
+    a.randomize = rc.opt->randomize;
+    a.seed = rc.opt->seed;
+    a.max_hat_s = rc.max_hat_s;
+    a.colptr = rc.want_path ? h->dcolptr : nullptr;
+    a.rowval = h->drowval;
+    a.nzval = h->dnzval;
+    a.capacity = rc.capacity;
+    a.flag = h->dflag;
+    a.stats = h->dstats;
+    CD_TRY(launch_cov_init(h, a.A, a.lda, a.p, a.act, a.actval, a.nact, a.Ax, a.beta, a.inlist));
+    CD_TRY(launch_cov_path(h, a));
+  } else {
+    NaiveArgs a = {};
+    a.kind = h->kind;
+    a.X = h->dX;
+    a.ldx = h->ld;
+    a.n = (int)h->n;
+    a.p = (int)h->p;
+    a.y = h->dy;
+    a.w = h->dw;
+    a.colsq = h->daux;
+    a.omega = rc.domega;
+    a.r = h->dstate;
+    a.beta = h->dbeta;
+    a.act = h->dact;
+    a.actval = h->dactval;
+    a.nact = h->dnact;
+    a.inlist = h->dinlist;
+    a.scr = h->dscr;
+    a.iscr = h->discr;
+    a.lambdas = h->dlam;
+    a.nlambda = rc.nlambda;
+    a.accumulate = rc.accumulate;
+    a.maxIter = rc.opt->maxIter;
+    a.optTol = rc.opt->optTol;
+    a.randomize = rc.opt->randomize;
+    a.seed = rc.opt->seed;
+    a.max_hat_s = rc.max_hat_s;
+    a.colptr = rc.want_path ? h->dcolptr : nullptr;
+    a.rowval = h->drowval;
+    a.nzval = h->dnzval;
+    a.capacity = rc.capacity;
+    a.flag = h->dflag;
+    a.stats = h->dstats;
+    a.scaled = rc.scaled;
+    a.outerMaxIter = rc.outerMaxIter;
+    a.outerTol = rc.outerTol;
+    a.sigma0 = rc.sigma0;
+    CD_TRY(launch_naive_init(h, a));
+    CD_TRY(launch_naive_path(h, a));
+  }
+  return CDGPU_OK;
+}
+
+static int lambda_max_dev(cdgpu_handle_s *h, const double *domega, double *out_host) {
+  double *dout = h->dscr; // first slot of the scratch
+  if (h->kind == CDGPU_LOSS_QUAD) {
+    CD_TRY(launch_lambda_max_quad(h, h->dy, domega, (int)h->p, dout));
+  } else {
+    CD_TRY(launch_lambda_max_naive(h, h->kind, h->dX, h->ld, (int)h->n, (int)h->p, h->dy, h->dw, domega, h->dscr + 8,
+                                   dout));
+  }
+  CUDA_TRY(cudaMemcpyAsync(out_host, dout, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return CDGPU_OK;
+}
+
+API int cdgpu_solve(cdgpu_handle h, double lambda0, const double *omega, const cdgpu_options *opt, double *nzval,
+                    int64_t *nzval2ind, int64_t *nnz, cdgpu_stats *stats) {
+  if (!h || !nzval || !nzval2ind || !nnz) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  CD_TRY(check_opts(opt));
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc;
+  const double *domega = upload_omega(h, omega, &rc);
+  CD_TRY(rc);
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  RunCfg cfg = {};
+  cfg.opt = opt;
+  cfg.domega = domega;
+  cfg.accumulate = 1;
+  cfg.max_hat_s = -1;
+  std::vector<double> lams;
+  if (opt->warmStart) {
+    CD_TRY(upload_iterate(h, nzval, nzval2ind, *nnz));
+    lams.push_back(lambda0);
+  } else {
+    CD_TRY(set_zero_iterate(h)); // fill!(x, 0)  coordinate_descent.jl:25
+    double lmax = 0.0;
+    CD_TRY(lambda_max_dev(h, domega, &lmax));
+    lams = continuation(lmax, lambda0, opt->numSteps);
+  }
+  cfg.lambdas = lams.data();
+  cfg.nlambda = (int)lams.size();
+  CD_TRY(run_sweeps(h, cfg));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CD_TRY(flag_status(h, nullptr));
+  CD_TRY(download_iterate(h, nzval, nzval2ind, nnz));
+  if (stats) {
+    DevStats d;
+    CUDA_TRY(cudaMemcpy(&d, h->dstats, sizeof d, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    stats_to_abi(d, ms, stats);
+  }
+  return CDGPU_OK;
+}
+
+API int cdgpu_path(cdgpu_handle h, const double *lambda, int64_t m, const double *omega, const cdgpu_options *opt,
+                   int64_t max_hat_s, int64_t capacity, int64_t *colptr, int64_t *rowval, double *nzval,
+                   int64_t *m_done, cdgpu_stats *stats) {
+  if (!h || !lambda || !colptr || !rowval || !nzval || !m_done) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (m < 0 || m > 0x7fffffff || capacity < 0) return cdgpu_set_error(CDGPU_EARG, "bad path length or capacity");
+  CD_TRY(check_opts(opt));
+  CUDA_TRY(cudaSetDevice(h->device));
+  colptr[0] = 0;
+  *m_done = 0;
+  if (m == 0) return CDGPU_OK;
+  if (!opt->warmStart) {
+    // LassoPath with warmStart=false re-runs the internal continuation for every lambda
+    // (coordinate_descent.jl:23-37): run it point by point.
+    int64_t off = 0;
+    std::vector<double> nz((size_t)h->p);
+    std::vector<int64_t> ind((size_t)h->p);
+    for (int64_t i = 0; i < m; ++i) {
+      int64_t nn = 0;
+      CD_TRY(cdgpu_solve(h, lambda[i], omega, opt, nz.data(), ind.data(), &nn, stats ? stats + i : nullptr));
+      if (off + nn > capacity) return cdgpu_set_error(CDGPU_ECAP, "path output capacity too small");
+      memcpy(rowval + off, ind.data(), (size_t)nn * sizeof(int64_t));
+      memcpy(nzval + off, nz.data(), (size_t)nn * sizeof(double));
+      off += nn;
+      colptr[i + 1] = off;
+      *m_done = i + 1;
+      if (max_hat_s >= 0 && nn > max_hat_s) break;
+    }
+    return CDGPU_OK;
+  }
+  int rc;
+  const double *domega = upload_omega(h, omega, &rc);
+  CD_TRY(rc);
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  CD_TRY(set_zero_iterate(h)); // x = SparseIterate(T, p)  lasso.jl:244
+  RunCfg cfg = {};
+  cfg.opt = opt;
+  cfg.domega = domega;
+  cfg.accumulate = 0;
+  cfg.max_hat_s = max_hat_s;
+  cfg.capacity = capacity;
+  cfg.want_path = true;
+  cfg.lambdas = lambda;
+  cfg.nlambda = (int)m;
+  CD_TRY(run_sweeps(h, cfg));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  int cols = 0;
+  int st = flag_status(h, &cols);
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (cols > 0) {
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    CUDA_TRY(cudaMemcpy(colptr, h->dcolptr, ((size_t)cols + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    colptr[0] = 0;
+    const int64_t tot = colptr[cols];
+    if (tot > 0) {
+      CUDA_TRY(cudaMemcpy(rowval, h->drowval, (size_t)tot * sizeof(int64_t), cudaMemcpyDeviceToHost));
+      CUDA_TRY(cudaMemcpy(nzval, h->dnzval, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (stats) {
+      std::vector<DevStats> d((size_t)cols);
+      CUDA_TRY(cudaMemcpy(d.data(), h->dstats, (size_t)cols * sizeof(DevStats), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < cols; ++i) stats_to_abi(d[(size_t)i], i == 0 ? (double)ms : 0.0, stats + i);
+    }
+  }
+  *m_done = cols;
+  return st;
+}
+
+API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, const cdgpu_iter_options *opt,
+                           double *nzval, int64_t *nzval2ind, int64_t *nnz, double *sigma_out, cdgpu_stats *stats) {
+  if (!h || !opt || !omega || !nzval || !nzval2ind || !nnz) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (h->kind != CDGPU_LOSS_LS)
+    return cdgpu_set_error(CDGPU_EARG, "scaledLasso! needs a CDLeastSquaresLoss handle (lasso.jl:117)");
+  CD_TRY(check_opts(&opt->optionsCD));
+  if (opt->initProcedure != CDGPU_INIT_STD && opt->initProcedure != CDGPU_INIT_WARMSTART &&
+      opt->initProcedure != CDGPU_INIT_SCREENING)
+    return cdgpu_set_error(CDGPU_EARG, "ArgumentError: Incorrect initialization Symbol");
+  if (opt->initProcedure == CDGPU_INIT_SCREENING)
+    return cdgpu_set_error(CDGPU_EARG, ":Screening initialisation (utils.jl:60-124) is not on the device yet; use "
+                                       ":InitStd or :WarmStart");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc;
+  const double *domega = upload_omega(h, omega, &rc);
+  CD_TRY(rc);
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  CD_TRY(upload_iterate(h, nzval, nzval2ind, *nnz));
+  RunCfg cfg = {};
+  cfg.opt = &opt->optionsCD;
+  cfg.domega = domega;
+  cfg.accumulate = 1;
+  cfg.max_hat_s = -1;
+  cfg.lambdas = &lambda;
+  cfg.nlambda = 1;
+  cfg.scaled = opt->initProcedure == CDGPU_INIT_WARMSTART ? 2 : 1; // 2: sigma0 = std(r) computed on the device
+  cfg.outerMaxIter = opt->maxIter;
+  cfg.outerTol = opt->optTol;
+  cfg.sigma0 = opt->sigma_init;
+  CD_TRY(run_sweeps(h, cfg));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CD_TRY(flag_status(h, nullptr));
+  CD_TRY(download_iterate(h, nzval, nzval2ind, nnz));
+  DevStats d;
+  CUDA_TRY(cudaMemcpy(&d, h->dstats, sizeof d, cudaMemcpyDeviceToHost));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (stats) stats_to_abi(d, ms, stats);
+  if (sigma_out) { // std(f.r) of lasso.jl:143, written by the kernel next to the flags
+    double s[2];
+    CUDA_TRY(cudaMemcpy(s, h->dscr, sizeof s, cudaMemcpyDeviceToHost));
+    *sigma_out = s[0];
+  }
+  return CDGPU_OK;
+}
+
+API int cdgpu_state(cdgpu_handle h, double *out) {
+  if (!h || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t cnt = (size_t)(h->kind == CDGPU_LOSS_QUAD ? h->p : h->n);
+  CUDA_TRY(cudaMemcpy(out, h->dstate, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+  return CDGPU_OK;
+}
+
+API int cdgpu_stdx(cdgpu_handle h, const double *w, double *out) {
+  if (!h || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (h->kind == CDGPU_LOSS_QUAD) return cdgpu_set_error(CDGPU_EARG, "_stdX! needs a naive-form handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  double *dw = nullptr;
+  if (w) {
+    dw = h->dscr + 8;
+    CUDA_TRY(cudaMemcpyAsync(dw, w, (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  double *dout = h->dscr + 8 + h->n;
+  CD_TRY(launch_colsq(h, h->dX, h->ld, (int)h->n, (int)h->p, dw, dout, true));
+  CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return CDGPU_OK;
+}
+
+API int cdgpu_lambda_max(cdgpu_handle h, const double *omega, double *out) {
+  if (!h || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc;
+  const double *domega = upload_omega(h, omega, &rc);
+  CD_TRY(rc);
+  return lambda_max_dev(h, domega, out);
+}

@@ -1,0 +1,229 @@
+// common.cuh — shared declarations of libcdgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cdgpu.h"
+
+// ---------------------------------------------------------------- errors --
+int cdgpu_set_error(int code, const char *fmt, ...);
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return cdgpu_set_error(_e == cudaErrorMemoryAllocation ? CDGPU_ENOMEM : CDGPU_ECUDA, "%s: %s (%s:%d)", #expr, \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                                \
+  } while (0)
+#define CD_TRY(expr)       \
+  do {                     \
+    int _rc = (expr);      \
+    if (_rc) return _rc;   \
+  } while (0)
+
+// ------------------------------------------------------------ device math --
+// ProximalBase.shrink: comparison based, NaN -> 0 (oracle/cdref.c: shrink)
+__device__ __forceinline__ double cd_shrink(double v, double c) { return v > c ? v - c : (v < -c ? v + c : 0.0); }
+
+// Visit order of RandomIterator mode 1: a keyed bijection of [0, N) (4-round Feistel network on
+// 2*hb bits + cycle walking), evaluated per position — no sort, no sequential shuffle.  Same
+// definition in oracle/cdref.c:order_perm.  cd_perm maps visit position -> item, cd_perm_inv
+// maps item -> visit position.
+__host__ __device__ __forceinline__ uint64_t cd_splitmix(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t cd_mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+struct PermKey {
+  uint32_t key[4];
+  uint32_t mask;
+  int hb;
+  uint32_t N;
+};
+__host__ __device__ __forceinline__ PermKey cd_perm_key(uint32_t N, uint64_t seed, uint64_t pass) {
+  PermKey k;
+  uint64_t k0 = cd_splitmix(seed ^ (pass * 0xD1B54A32D192ED03ull)), k1 = cd_splitmix(k0);
+  k.key[0] = (uint32_t)k0;
+  k.key[1] = (uint32_t)(k0 >> 32);
+  k.key[2] = (uint32_t)k1;
+  k.key[3] = (uint32_t)(k1 >> 32);
+  int bits = 0;
+  while (N > 1 && ((N - 1) >> bits) != 0) bits++;
+  k.hb = (bits + 1) / 2;
+  if (k.hb < 1) k.hb = 1;
+  k.mask = (uint32_t)((1ull << k.hb) - 1);
+  k.N = N;
+  return k;
+}
+__host__ __device__ __forceinline__ uint32_t cd_perm(const PermKey &k, uint32_t x) {
+  do {
+    uint32_t L = x >> k.hb, R = x & k.mask;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint32_t t = L ^ (cd_mix32(R + k.key[r]) & k.mask);
+      L = R;
+      R = t;
+    }
+    x = (L << k.hb) | R;
+  } while (x >= k.N);
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t cd_perm_inv(const PermKey &k, uint32_t x) {
+  do {
+    uint32_t L = x >> k.hb, R = x & k.mask;
+#pragma unroll
+    for (int r = 3; r >= 0; --r) {
+      uint32_t t = R ^ (cd_mix32(L + k.key[r]) & k.mask);
+      R = L;
+      L = t;
+    }
+    x = (L << k.hb) | R;
+  } while (x >= k.N);
+  return x;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+
+// device-side mirror of cdgpu_stats (host fills device_ms / sigma bookkeeping)
+struct DevStats {
+  long long passes, full_passes, visits, accepted;
+  double maxH;
+  int converged, outer_iters;
+  double sigma;
+};
+
+// ---------------------------------------------------------------- handle --
+struct cdgpu_handle_s {
+  int kind = -1, device = 0;
+  int64_t n = 0, p = 0, ld = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // naive: X (n x p, ld), y, w, r=state(n), colsq (p) ; quad: A (p x p, ld), b, state=Ax(p), ainv (p)
+  double *dX = nullptr, *dy = nullptr, *dw = nullptr, *dstate = nullptr, *daux = nullptr;
+  bool ownX = false, owny = false, ownw = false;
+  // iterate
+  double *dbeta = nullptr;          // dense p
+  int *dact = nullptr;              // active list (0-based coordinates), capacity p
+  double *dactval = nullptr;        // values in list order, capacity p
+  int *dnact = nullptr;             // 1 int
+  unsigned char *dinlist = nullptr; // p flags
+  double *domega = nullptr;         // p (scratch copy of the caller's weights)
+  // scratch for the sweep kernels
+  double *dscr = nullptr;           // 8 * p doubles
+  int *discr = nullptr;             // 4 * p ints
+  DevStats *dstats = nullptr;       // path stats, grown on demand
+  int64_t nstats = 0;
+  double *dlam = nullptr;
+  int64_t nlam = 0;
+  // path output
+  long long *dcolptr = nullptr, *drowval = nullptr;
+  double *dnzval = nullptr;
+  int64_t outcap = 0, outcols = 0;
+  int *dflag = nullptr;             // device status word(s)
+  double gram_ms = 0.0;
+  int sm_count = 0, max_cluster = 0;
+};
+
+// ------------------------------------------------------------- launchers --
+struct CovArgs {
+  const double *A;
+  long long lda;
+  int p;
+  const double *b, *ainv, *omega; // omega may be null
+  double *Ax, *beta;
+  int *act;
+  double *actval;
+  int *nact;
+  unsigned char *inlist;
+  double *scr;  // >= 8p doubles
+  int *iscr;    // >= 4p ints
+  const double *lambdas;
+  int nlambda;
+  int accumulate; // 1: all lambdas are one solve (cold-start continuation): stats summed into stats[0], no path output
+  long long maxIter;
+  double optTol;
+  int randomize;
+  unsigned long long seed;
+  long long max_hat_s; // <0: none
+  long long *colptr, *rowval;
+  double *nzval;
+  long long capacity;
+  int *flag; // [0]=status (0 ok, 1 capacity, 2 active set too large), [1]=columns done
+  DevStats *stats;
+};
+int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a);
+int launch_cov_init(cdgpu_handle_s *h, const double *A, long long lda, int p, const int *act, const double *actval,
+                    const int *nact, double *Ax, double *beta, unsigned char *inlist);
+int launch_lambda_max_quad(cdgpu_handle_s *h, const double *b, const double *omega, int p, double *out);
+int launch_extract_ainv(cdgpu_handle_s *h, const double *A, long long lda, int p, double *ainv);
+int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, int p, int *flag);
+
+// Gram (gram_dmma.cu): G = X'X / n_total (lower tiles computed, mirrored), c = -X'y / n_total
+int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,
+                double *c, double inv_scale_n, bool scale);
+int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_total);
+
+// naive sweeps (naive_sweep.cu)
+struct NaiveArgs {
+  int kind;
+  const double *X;
+  long long ldx;
+  int n, p;
+  const double *y, *w, *colsq, *omega;
+  double *r, *beta;
+  int *act;
+  double *actval;
+  int *nact;
+  unsigned char *inlist;
+  double *scr;
+  int *iscr;
+  const double *lambdas;
+  int nlambda;
+  int accumulate;
+  long long maxIter;
+  double optTol;
+  int randomize;
+  unsigned long long seed;
+  long long max_hat_s;
+  long long *colptr, *rowval;
+  double *nzval;
+  long long capacity;
+  int *flag;
+  DevStats *stats;
+  // scaled lasso (sigma loop on device): lambdas[0] = lambda, sigma0 = initial sigma
+  int scaled;
+  long long outerMaxIter;
+  double outerTol, sigma0;
+};
+int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
+int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a); // r = y - X beta, beta dense, inlist
+int launch_colsq(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p, const double *w, double *out,
+                 bool sqrt_over_n);
+int launch_lambda_max_naive(cdgpu_handle_s *h, int kind, const double *X, long long ldx, int n, int p, const double *y,
+                            const double *w, const double *omega, double *scr, double *out);

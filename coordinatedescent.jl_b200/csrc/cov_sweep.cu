@@ -1,0 +1,738 @@
+// cov_sweep.cu — covariance-form (CDQuadraticLoss) active-set coordinate descent, whole
+// lambda path in ONE launch of ONE thread-block cluster.
+//
+// Reference semantics: _coordinateDescent!/_cdPass! (src/coordinate_descent.jl:65-110) driving
+// descendCoordinate!(::CDQuadraticLoss) (src/cd_differentiable_function.jl:324-348):
+//     x_k <- S(x_k - (Ax_k + b_k)/A_kk, lambda0*omega_k/A_kk);   Ax += A[:,k] * h.
+//
+// B200 design:
+//  * the p coordinates are partitioned over the C CTAs of a cluster (C = 16, non-portable size);
+//    each CTA keeps its slice of Ax, b, 1/diag(A), omega, beta in shared memory for the whole path.
+//  * FULL pass = exact Gauss-Seidel by speculation: while Ax is unchanged the test "does coordinate
+//    k move?" is independent across k, so every CTA scans its slice in parallel, the cluster takes
+//    the FIRST (in visit order) coordinate with h != 0 through a DSMEM candidate exchange and one
+//    cluster barrier, applies it (a coalesced p/C-long axpy of the column slice per CTA) and resumes
+//    behind it.  Visits with h == 0 cost 40 B of shared memory and no global traffic.
+//  * ACTIVE-SET passes only ever read Ax on the active set, so they run inside CTA 0 with one
+//    register-resident entry per thread, one named barrier per coordinate step and the needed
+//    A[act, k] gathers software-prefetched two steps ahead; the other CTAs sleep on the cluster
+//    barrier.  Afterwards the whole cluster folds the accumulated change into its Ax slices
+//    (Ax += A[:, act] * (beta - beta_at_entry), a coalesced GEMV over L2-resident columns).
+//  * no grid-wide sync, no host round trip between passes or between lambdas.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int COV_T = 512;
+constexpr int COV_RMAX = 8;
+constexpr int COV_ACT_CAP = COV_T * COV_RMAX; // entries the in-CTA engine can hold
+constexpr int COV_MAXC = 16;
+constexpr unsigned long long KEY_NONE = ~0ull;
+
+struct Cand {
+  unsigned long long key;
+  int k, pad;
+  double h, nw;
+};
+
+struct Bcast { // CTA 0 -> cluster after an active phase / at the end of a lambda
+  long long npasses, visits, accepted;
+  double maxH;
+  int m0, nact, status, conv;
+};
+
+struct Smem {
+  Cand cand[2][COV_MAXC];
+  Cand mine;
+  Bcast bc;
+  unsigned long long red[COV_T / 32];
+  double h[2];
+  int nact, flag;
+};
+
+__device__ __forceinline__ void named_bar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
+
+struct Ctx {
+  const CovArgs &a;
+  cg::cluster_group &cluster;
+  Smem *sm;
+  double *sAx, *sb, *sainv, *sw, *sbeta; // this CTA's slice (shared or global)
+  int *s_act, *s_idx;                    // CTA-0 engine scratch
+  int rank, C, L, lo, len, slice_in_smem;
+};
+
+// remote (or own) element of a slice array living at the same shared offset in every CTA
+__device__ __forceinline__ double slice_get(const Ctx &c, double *arr_local, int k) {
+  int owner = k / c.L;
+  if (c.slice_in_smem) {
+    const double *r = c.cluster.map_shared_rank(arr_local, owner);
+    return r[k - owner * c.L];
+  }
+  // global slices: arr_local == base + lo
+  return __ldcg(arr_local - c.lo + k);
+}
+
+// ------------------------------------------------------------------ full pass --
+__device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter, int &par, long long &accepted) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool ordered = a.randomize == 0;
+  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  int cur = -1;          // ordered: last coordinate that moved
+  long long curpos = -1; // random: its visit position
+  double maxH = 0.0;
+  for (;;) {
+    unsigned long long best = KEY_NONE;
+    int bk = -1;
+    double bh = 0.0, bnw = 0.0;
+    int i0 = ordered ? max(0, cur + 1 - c.lo) : 0;
+    for (int i = i0 + tid; i < c.len; i += COV_T) {
+      const int k = c.lo + i;
+      const unsigned long long key = ordered ? (unsigned long long)k : (unsigned long long)cd_perm_inv(pk, (uint32_t)k);
+      if (!ordered && (long long)key <= curpos) continue;
+      const double ainv = c.sainv[i];
+      const double g = c.sAx[i] + c.sb[i];
+      const double old = c.sbeta[i];
+      const double v = __dsub_rn(old, __dmul_rn(g, ainv));
+      const double thr = __dmul_rn(__dmul_rn(ainv, lam), c.sw[i]);
+      const double nw = cd_shrink(v, thr);
+      const double h = nw - old;
+      if (h != 0.0 && key < best) {
+        best = key;
+        bk = k;
+        bh = h;
+        bnw = nw;
+      }
+    }
+    unsigned long long wmin = warp_min_u64(best);
+    if (lane == 0) sm->red[warp] = wmin;
+    __syncthreads();
+    unsigned long long bmin = sm->red[0];
+#pragma unroll
+    for (int w = 1; w < COV_T / 32; ++w) bmin = sm->red[w] < bmin ? sm->red[w] : bmin;
+    if (bmin == KEY_NONE) {
+      if (tid == 0) sm->mine.key = KEY_NONE;
+    } else if (best == bmin) {
+      sm->mine.key = best;
+      sm->mine.k = bk;
+      sm->mine.h = bh;
+      sm->mine.nw = bnw;
+    }
+    __syncthreads();
+    if (tid < c.C) {
+      Cand *dst = c.cluster.map_shared_rank(&sm->cand[par][c.rank], tid);
+      *dst = sm->mine;
+    }
+    c.cluster.sync();
+    Cand w = sm->cand[par][0];
+    for (int q = 1; q < c.C; ++q) {
+      unsigned long long kq = sm->cand[par][q].key;
+      if (kq < w.key) w = sm->cand[par][q];
+    }
+    par ^= 1;
+    if (w.key == KEY_NONE) break;
+    const int k = w.k;
+    if (tid == 0) {
+      if (k >= c.lo && k < c.lo + c.len) c.sbeta[k - c.lo] = w.nw;
+      if (c.rank == 0 && !a.inlist[k]) { // setindex! appends on the first non-zero store
+        a.inlist[k] = 1;
+        a.act[sm->nact] = k;
+        sm->nact += 1;
+      }
+    }
+    const double *col = a.A + (long long)k * a.lda + c.lo;
+    for (int i = tid; i < c.len; i += COV_T) c.sAx[i] = __dadd_rn(c.sAx[i], __dmul_rn(__ldg(col + i), w.h));
+    maxH = fmax(maxH, fabs(w.h));
+    accepted += 1;
+    cur = k;
+    curpos = (long long)w.key;
+    __syncthreads();
+  }
+  return maxH;
+}
+
+// dropzeros! on the list kept by CTA 0 (ProximalBase semantics: last entry moves into the hole).
+// Also refreshes actval[] with the current beta of every listed coordinate.
+__device__ void list_dropzeros(Ctx &c) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x;
+  const int m = sm->nact;
+  int anyz = 0;
+  for (int i = tid; i < m; i += COV_T) {
+    double v = slice_get(c, c.sbeta, a.act[i]);
+    a.actval[i] = v;
+    anyz |= (v == 0.0);
+  }
+  anyz = __syncthreads_or(anyz);
+  if (anyz && tid == 0) {
+    int n = m, i = 0;
+    while (i < n) {
+      if (a.actval[i] == 0.0) {
+        a.inlist[a.act[i]] = 0;
+        if (i != n - 1) {
+          a.actval[i] = a.actval[n - 1];
+          a.act[i] = a.act[n - 1];
+        }
+        n -= 1;
+      } else {
+        i += 1;
+      }
+    }
+    sm->nact = n;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------ active-set engine (CTA 0) --
+// Runs consecutive active-set passes until one has maxH < optTol or `maxPasses` are used.
+template <int R>
+__device__ void active_engine(Ctx &c, double lam, long long maxPasses, unsigned long long pass_counter) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x;
+  int m = sm->nact;
+  const int m0 = m;
+  int per = (m + R - 1) / R;
+  int nthr = min(COV_T, ((per + 31) / 32) * 32);
+  if (nthr < 32) nthr = 32;
+  const bool ordered = a.randomize == 0;
+  double *scr_b0 = a.scr;              // [p] beta at entry, by snapshot index
+  double *scr_dlt = a.scr + a.p;       // [p] delta by snapshot index
+  double *scr_ax = a.scr + 2 * (long long)a.p; // [p] compaction staging
+  double *scr_be = a.scr + 3 * (long long)a.p;
+  int *act0 = a.iscr; // [p] snapshot of the list
+
+  int kk[R];
+  double Ax[R], be[R], bb[R], ai[R], th[R], acur[R], anxt[R];
+  const bool part = tid < nthr;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int i = r * nthr + tid;
+    kk[r] = -1;
+    Ax[r] = be[r] = bb[r] = ai[r] = th[r] = acur[r] = anxt[r] = 0.0;
+    if (part && i < m) {
+      int k = a.act[i];
+      kk[r] = k;
+      be[r] = a.actval[i];
+      Ax[r] = slice_get(c, c.sAx, k);
+      bb[r] = __ldg(a.b + k);
+      ai[r] = __ldg(a.ainv + k);
+      double w = a.omega ? __ldg(a.omega + k) : 1.0;
+      th[r] = __dmul_rn(__dmul_rn(ai[r], lam), w);
+      c.s_act[i] = k;
+      act0[i] = k;
+      scr_b0[i] = be[r];
+    }
+  }
+  __syncthreads();
+
+  long long npasses = 0, visits = 0, accepted = 0;
+  double maxH = 0.0;
+  int conv = 0;
+  if (part) {
+    while (npasses < maxPasses) {
+      // ---- visit order of this pass (atom_iterator.jl:53-75, see common.cuh:cd_perm)
+      const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter + npasses);
+      auto entry_at = [&](int s) -> int { return ordered ? s : (int)cd_perm(pkm, (uint32_t)s); };
+      // ---- prefetch A[act, k] for steps 0 and 1
+      {
+        int e0 = m > 0 ? c.s_act[entry_at(0)] : 0, e1 = m > 1 ? c.s_act[entry_at(1)] : 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acur[r] = (kk[r] >= 0 && m > 0) ? __ldg(a.A + (long long)e0 * a.lda + kk[r]) : 0.0;
+          anxt[r] = (kk[r] >= 0 && m > 1) ? __ldg(a.A + (long long)e1 * a.lda + kk[r]) : 0.0;
+        }
+      }
+      double pmax = 0.0;
+      for (int s = 0; s < m; ++s) {
+        const int i = entry_at(s);
+        // issue the gather for step s+2 early
+        double apre[R];
+        {
+          int e2 = (s + 2 < m) ? c.s_act[entry_at(s + 2)] : -1;
+#pragma unroll
+          for (int r = 0; r < R; ++r) apre[r] = (e2 >= 0 && kk[r] >= 0) ? __ldg(a.A + (long long)e2 * a.lda + kk[r]) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (i == r * nthr + tid) {
+            const double g = Ax[r] + bb[r];
+            const double v = __dsub_rn(be[r], __dmul_rn(g, ai[r]));
+            const double nw = cd_shrink(v, th[r]);
+            sm->h[s & 1] = nw - be[r];
+            be[r] = nw;
+          }
+        }
+        named_bar(1, nthr);
+        const double h = sm->h[s & 1];
+        if (h != 0.0) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) Ax[r] = __dadd_rn(Ax[r], __dmul_rn(acur[r], h));
+          accepted += 1;
+        }
+        pmax = fmax(pmax, fabs(h));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acur[r] = anxt[r];
+          anxt[r] = apre[r];
+        }
+      }
+      npasses += 1;
+      visits += m;
+      maxH = pmax;
+      // ---- dropzeros!
+      if (tid == 0) sm->flag = 0;
+      named_bar(1, nthr);
+      {
+        int z = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) z |= (kk[r] >= 0 && be[r] == 0.0);
+        if (z) sm->flag = 1;
+      }
+      named_bar(1, nthr);
+      if (sm->flag) { // rare: an entry left the active set
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int i = r * nthr + tid;
+          if (kk[r] >= 0) {
+            scr_ax[i] = Ax[r];
+            scr_be[i] = be[r];
+          }
+          if (i < m) c.s_idx[i] = i;
+        }
+        named_bar(1, nthr);
+        if (tid == 0) {
+          int n = m, i = 0;
+          while (i < n) {
+            if (scr_be[c.s_idx[i]] == 0.0) {
+              a.inlist[c.s_act[c.s_idx[i]]] = 0;
+              if (i != n - 1) c.s_idx[i] = c.s_idx[n - 1];
+              n -= 1;
+            } else {
+              i += 1;
+            }
+          }
+          sm->nact = n;
+        }
+        named_bar(1, nthr);
+        const int mn = sm->nact;
+        int nk[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int i = r * nthr + tid;
+          nk[r] = -1;
+          if (i < mn) {
+            int src = c.s_idx[i];
+            nk[r] = c.s_act[src];
+            Ax[r] = scr_ax[src];
+            be[r] = scr_be[src];
+          }
+        }
+        named_bar(1, nthr);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int i = r * nthr + tid;
+          kk[r] = nk[r];
+          if (i < mn) {
+            const int k = nk[r];
+            c.s_act[i] = k;
+            bb[r] = __ldg(a.b + k);
+            ai[r] = __ldg(a.ainv + k);
+            double w = a.omega ? __ldg(a.omega + k) : 1.0;
+            th[r] = __dmul_rn(__dmul_rn(ai[r], lam), w);
+          }
+        }
+        m = mn;
+        named_bar(1, nthr);
+      }
+      if (maxH < a.optTol) {
+        conv = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- publish: final list, dense beta, per-snapshot-entry delta
+  for (int i = tid; i < m0; i += COV_T) a.beta[act0[i]] = 0.0;
+  __syncthreads();
+  if (part) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int i = r * nthr + tid;
+      if (kk[r] >= 0) {
+        a.beta[kk[r]] = be[r];
+        a.act[i] = kk[r];
+        a.actval[i] = be[r];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < m0; i += COV_T) scr_dlt[i] = a.beta[act0[i]] - scr_b0[i];
+  if (tid == 0) {
+    sm->nact = m;
+    sm->bc.npasses = npasses;
+    sm->bc.visits = visits;
+    sm->bc.accepted = accepted;
+    sm->bc.maxH = maxH;
+    sm->bc.m0 = m0;
+    sm->bc.nact = m;
+    sm->bc.conv = conv;
+  }
+  __syncthreads();
+}
+
+// every CTA after the active phase: Ax[slice] += A[slice, act0] * dlt ; beta[slice] <- dense beta
+__device__ void refresh_slice(Ctx &c, int m0) {
+  const CovArgs &a = c.a;
+  const int tid = threadIdx.x;
+  const double *dlt = a.scr + a.p;
+  const int *act0 = a.iscr;
+  for (int j = tid; j < c.len; j += COV_T) {
+    const double *row = a.A + c.lo + j;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int i = 0;
+    for (; i + 4 <= m0; i += 4) {
+      const int k0 = __ldcg(act0 + i), k1 = __ldcg(act0 + i + 1), k2 = __ldcg(act0 + i + 2), k3 = __ldcg(act0 + i + 3);
+      const double d0 = __ldcg(dlt + i), d1 = __ldcg(dlt + i + 1), d2 = __ldcg(dlt + i + 2), d3 = __ldcg(dlt + i + 3);
+      const double v0 = __ldg(row + (long long)k0 * a.lda), v1 = __ldg(row + (long long)k1 * a.lda);
+      const double v2 = __ldg(row + (long long)k2 * a.lda), v3 = __ldg(row + (long long)k3 * a.lda);
+      acc0 = fma(v0, d0, acc0);
+      acc1 = fma(v1, d1, acc1);
+      acc2 = fma(v2, d2, acc2);
+      acc3 = fma(v3, d3, acc3);
+    }
+    for (; i < m0; ++i) acc0 = fma(__ldg(row + (long long)__ldcg(act0 + i) * a.lda), __ldcg(dlt + i), acc0);
+    c.sAx[j] += (acc0 + acc1) + (acc2 + acc3);
+  }
+  for (int i = tid; i < m0; i += COV_T) {
+    const int k = __ldcg(act0 + i);
+    if (k >= c.lo && k < c.lo + c.len) c.sbeta[k - c.lo] = __ldcg(a.beta + k);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int L, int slice_in_smem) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx c{a, cluster};
+  c.rank = (int)cluster.block_rank();
+  c.C = (int)cluster.num_blocks();
+  c.L = L;
+  c.slice_in_smem = slice_in_smem;
+  c.lo = min(c.rank * L, a.p);
+  c.len = min(a.p, c.lo + L) - c.lo;
+  const int tid = threadIdx.x;
+  // carve shared memory (identical layout in every CTA)
+  unsigned char *sp = smem_raw;
+  c.sm = reinterpret_cast<Smem *>(sp);
+  sp += (sizeof(Smem) + 15) / 16 * 16;
+  c.s_act = reinterpret_cast<int *>(sp);
+  sp += COV_ACT_CAP * sizeof(int);
+  c.s_idx = reinterpret_cast<int *>(sp);
+  sp += COV_ACT_CAP * sizeof(int);
+  if (slice_in_smem) {
+    double *d = reinterpret_cast<double *>(sp);
+    c.sAx = d;
+    c.sb = d + L;
+    c.sainv = d + 2 * L;
+    c.sw = d + 3 * L;
+    c.sbeta = d + 4 * L;
+    for (int i = tid; i < c.len; i += COV_T) {
+      const int k = c.lo + i;
+      c.sAx[i] = a.Ax[k];
+      c.sb[i] = a.b[k];
+      c.sainv[i] = a.ainv[k];
+      c.sw[i] = a.omega ? a.omega[k] : 1.0;
+      c.sbeta[i] = a.beta[k];
+    }
+  } else { // very large p: slices stay in global memory (each CTA touches only its own)
+    double *g = a.scr + 4 * (long long)a.p;
+    c.sAx = a.Ax + c.lo;
+    c.sbeta = g + c.lo; // private dense copy so CTA 0's writes to a.beta never race
+    c.sb = const_cast<double *>(a.b) + c.lo;
+    c.sainv = const_cast<double *>(a.ainv) + c.lo;
+    c.sw = g + a.p + c.lo;
+    for (int i = tid; i < c.len; i += COV_T) {
+      c.sbeta[i] = a.beta[c.lo + i];
+      c.sw[i] = a.omega ? a.omega[c.lo + i] : 1.0;
+    }
+  }
+  if (tid == 0) {
+    c.sm->nact = (c.rank == 0) ? *a.nact : 0;
+    c.sm->bc.status = 0;
+  }
+  __syncthreads();
+  cluster.sync();
+
+  int par = 0;
+  unsigned long long pass_counter = 0;
+  DevStats st;
+  int status = 0;
+  long long cols_done = 0, out_off = 0;
+  for (int li = 0; li < a.nlambda && status == 0; ++li) {
+    const double lam = a.lambdas[li];
+    if (li == 0 || !a.accumulate) {
+      st.passes = st.full_passes = st.visits = st.accepted = 0;
+      st.maxH = 0.0;
+      st.converged = 0;
+      st.outer_iters = 0;
+      st.sigma = 0.0;
+    }
+    st.converged = 0;
+    bool conv = true;
+    long long iter = 0;
+    while (iter < a.maxIter) {
+      if (conv) {
+        iter += 1;
+        st.passes += 1;
+        st.full_passes += 1;
+        st.visits += a.p;
+        const double maxH = full_pass(c, lam, pass_counter, par, st.accepted);
+        pass_counter += 1;
+        if (c.rank == 0) list_dropzeros(c);
+        st.maxH = maxH;
+        conv = maxH < a.optTol;
+        if (conv) {
+          st.converged = 1;
+          break;
+        }
+      } else {
+        if (c.rank == 0) {
+          const int m = c.sm->nact;
+          const long long budget = a.maxIter - iter;
+          if (m > COV_ACT_CAP) {
+            if (tid == 0) c.sm->bc.status = 2;
+            __syncthreads();
+          } else if (m <= COV_T) {
+            active_engine<1>(c, lam, budget, pass_counter);
+          } else if (m <= 2 * COV_T) {
+            active_engine<2>(c, lam, budget, pass_counter);
+          } else if (m <= 4 * COV_T) {
+            active_engine<4>(c, lam, budget, pass_counter);
+          } else {
+            active_engine<8>(c, lam, budget, pass_counter);
+          }
+        }
+        cluster.sync();
+        const Bcast *bc = cluster.map_shared_rank(&c.sm->bc, 0);
+        const Bcast b = *bc;
+        if (b.status) {
+          status = b.status;
+          break;
+        }
+        refresh_slice(c, b.m0);
+        iter += b.npasses;
+        pass_counter += b.npasses;
+        st.passes += b.npasses;
+        st.visits += b.visits;
+        st.accepted += b.accepted;
+        st.maxH = b.maxH;
+        conv = b.conv != 0;
+        // conv == 0 here means the pass budget ran out: the while condition ends the solve
+      }
+    }
+    // ---- end of this lambda: publish nnz, write the path column / stats
+    if (c.rank == 0 && tid == 0) c.sm->bc.nact = c.sm->nact;
+    cluster.sync();
+    const int nnz = cluster.map_shared_rank(&c.sm->bc, 0)->nact;
+    if (status) break;
+    if (!a.accumulate) {
+      if (c.rank == 0) {
+        if (a.colptr) {
+          if (out_off + nnz > a.capacity) {
+            status = 1;
+          } else {
+            for (int i = tid; i < nnz; i += COV_T) {
+              a.rowval[out_off + i] = (long long)a.act[i] + 1;
+              a.nzval[out_off + i] = a.actval[i];
+            }
+            if (tid == 0) a.colptr[li + 1] = out_off + nnz;
+          }
+        }
+        if (tid == 0 && a.stats) a.stats[li] = st;
+      } else if (a.colptr && out_off + nnz > a.capacity) {
+        status = 1;
+      }
+      out_off += nnz;
+      if (status == 0) cols_done = li + 1;
+      if (a.max_hat_s >= 0 && nnz > a.max_hat_s) break;
+    } else {
+      cols_done = li + 1;
+    }
+  }
+  if (a.accumulate && c.rank == 0 && tid == 0 && a.stats) a.stats[0] = st;
+  // ---- write the state back
+  cluster.sync();
+  if (slice_in_smem) {
+    for (int i = tid; i < c.len; i += COV_T) {
+      a.Ax[c.lo + i] = c.sAx[i];
+      a.beta[c.lo + i] = c.sbeta[i];
+    }
+  } else {
+    for (int i = tid; i < c.len; i += COV_T) a.beta[c.lo + i] = c.sbeta[i];
+  }
+  if (c.rank == 0 && tid == 0) {
+    *a.nact = c.sm->nact;
+    a.flag[0] = status;
+    a.flag[1] = (int)cols_done;
+  }
+  cluster.sync(); // nobody exits while a peer may still read its shared memory
+}
+
+// ------------------------------------------------------------ small kernels --
+// initialize!(f::CDQuadraticLoss, x): Ax = sum_i A[:, act_i] * val_i (cd_differentiable_function.jl:311-320),
+// plus the dense copy of the iterate and the membership flags.
+__global__ void cov_init_kernel(const double *A, long long lda, int p, const int *act, const double *actval,
+                                const int *nact, double *Ax, double *beta, unsigned char *inlist) {
+  const int m = *nact;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int i = 0; i < m; ++i) acc += A[j + (long long)act[i] * lda] * actval[i];
+    Ax[j] = acc;
+    beta[j] = 0.0;
+    inlist[j] = 0;
+  }
+}
+__global__ void scatter_iterate_kernel(const int *act, const double *actval, const int *nact, double *beta,
+                                       unsigned char *inlist) {
+  const int m = *nact;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    beta[act[i]] = actval[i];
+    inlist[act[i]] = 1;
+  }
+}
+__global__ void ainv_kernel(const double *A, long long lda, int p, double *ainv) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x)
+    ainv[j] = 1.0 / A[j + (long long)j * lda];
+}
+// max_k |b_k| [/ omega_k]  (_findLambdaMax at x = 0, coordinate_descent.jl:118-149)
+__global__ void lambda_max_quad_kernel(const double *b, const double *omega, int p, double *out) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int j = threadIdx.x; j < p; j += blockDim.x) {
+    double t = fabs(b[j]);
+    if (omega) t = t / omega[j];
+    if (t > m) m = t;
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    m = warp_max(m);
+    if (threadIdx.x == 0) *out = m;
+  }
+}
+// issymmetric(A) exactly (cd_differentiable_function.jl:306): 32x32 tiles, both reads coalesced
+__global__ void symmetric_kernel(const double *A, long long lda, int p, int *flag) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.x, bj = blockIdx.y;
+  if (bj > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += blockDim.y) {
+    int i = bj * 32 + tx, j = bi * 32 + r; // tile (bj rows, bi cols)
+    t[r][tx] = (i < p && j < p) ? A[i + (long long)j * lda] : 0.0;
+  }
+  __syncthreads();
+  int bad = 0;
+  for (int r = ty; r < 32; r += blockDim.y) {
+    int i = bi * 32 + tx, j = bj * 32 + r; // tile (bi rows, bj cols): A[i,j] vs A[j,i] = t[tx][r]
+    if (i < p && j < p && A[i + (long long)j * lda] != t[tx][r]) bad = 1;
+  }
+  if (bad) atomicExch(flag, 1);
+}
+
+} // namespace
+
+int launch_cov_init(cdgpu_handle_s *h, const double *A, long long lda, int p, const int *act, const double *actval,
+                    const int *nact, double *Ax, double *beta, unsigned char *inlist) {
+  int blocks = (p + 255) / 256;
+  cov_init_kernel<<<blocks, 256, 0, h->stream>>>(A, lda, p, act, actval, nact, Ax, beta, inlist);
+  scatter_iterate_kernel<<<32, 256, 0, h->stream>>>(act, actval, nact, beta, inlist);
+  CUDA_TRY(cudaGetLastError());
+  return CDGPU_OK;
+}
+int launch_extract_ainv(cdgpu_handle_s *h, const double *A, long long lda, int p, double *ainv) {
+  ainv_kernel<<<(p + 255) / 256, 256, 0, h->stream>>>(A, lda, p, ainv);
+  CUDA_TRY(cudaGetLastError());
+  return CDGPU_OK;
+}
+int launch_lambda_max_quad(cdgpu_handle_s *h, const double *b, const double *omega, int p, double *out) {
+  lambda_max_quad_kernel<<<1, 1024, 0, h->stream>>>(b, omega, p, out);
+  CUDA_TRY(cudaGetLastError());
+  return CDGPU_OK;
+}
+int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, int p, int *flag) {
+  int nb = (p + 31) / 32;
+  dim3 grid(nb, nb), block(32, 8);
+  symmetric_kernel<<<grid, block, 0, h->stream>>>(A, lda, p, flag);
+  CUDA_TRY(cudaGetLastError());
+  return CDGPU_OK;
+}
+
+int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
+  static bool attr_done = false;
+  const size_t fixed = (sizeof(Smem) + 15) / 16 * 16 + COV_ACT_CAP * (2 * sizeof(int));
+  const size_t max_dyn = 227 * 1024;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_done = true;
+  }
+  // largest cluster the device will co-schedule (16 on B200 with the opt-in, else 8)
+  int C = h->max_cluster;
+  if (C == 0) {
+    for (int cand : {16, 8, 4, 2, 1}) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cand);
+      cfg.blockDim = dim3(COV_T);
+      cfg.dynamicSmemBytes = fixed + 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cand;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int ncl = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, cov_path_kernel, &cfg);
+      if (e == cudaSuccess && ncl >= 1) {
+        C = cand;
+        break;
+      }
+      (void)cudaGetLastError();
+    }
+    if (C == 0) return cdgpu_set_error(CDGPU_ECUDA, "no thread-block cluster configuration can be scheduled");
+    h->max_cluster = C;
+  }
+  if (const char *env = getenv("CDGPU_CLUSTER")) {
+    int v = atoi(env);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) C = v < h->max_cluster ? v : h->max_cluster;
+  }
+  while (C > 1 && a.p < C * 32) C >>= 1; // tiny problems: fewer, fuller slices
+  int L = (a.p + C - 1) / C;
+  L = (L + 1) & ~1;
+  size_t need = fixed + (size_t)5 * L * sizeof(double);
+  int slice_in_smem = need <= max_dyn;
+  size_t dyn = slice_in_smem ? need : fixed;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C);
+  cfg.blockDim = dim3(COV_T);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel, a, L, slice_in_smem));
+  return CDGPU_OK;
+}

@@ -1,0 +1,241 @@
+// gram_dmma.cu — K1: G = X'X / n (exactly symmetric) and c = -X'y / n for the covariance form
+// (what the reference's users write by hand: test/lasso.jl:48,88), as an FP64 tensor-core SYRK.
+//
+// sm_100a has no tcgen05 kind for f64 (ptxas: "Unknown modifier .kind::f64"), so the FP64 tensor
+// path is the warp-level mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Design:
+//   * X is column-major n x p, so both operands of X'X are K-contiguous: a tile is 128 columns of X
+//     by BK = 16 rows, i.e. 128 runs of 128 contiguous bytes -> 16-byte cp.async (LDGSTS), 4 stages.
+//   * CTA tile 128 x 128, 8 warps as 2 x 4, warp tile 64 x 32 = 8 x 4 DMMA fragments (64 accumulator
+//     doubles / thread).  Shared rows are padded to 20 doubles so fragment loads are conflict free.
+//   * only tiles on or below the diagonal are computed; the epilogue writes acc/n to (i,j) and the
+//     same value to (j,i), so issymmetric(G) (cd_differentiable_function.jl:306) holds bit for bit.
+//   * persistent CTAs walk a host-built tile list ordered in 12 x 12 super-tiles so the ~148 tiles in
+//     flight share ~24 column panels of X through L2 (HBM traffic ~ 20 GB instead of ~130 GB at C2).
+//   * the row-sharded multi-GPU form runs the same kernel on n_local rows without the 1/n, sums the
+//     partial G|c buffer with one ncclAllReduce (nccl_comm.cu) and then scales.
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, LDK = 20, STAGES = 4, GT = 256;
+constexpr int STAGE_DOUBLES = (BM + BN) * LDK;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// load one stage: rows (columns of X) [col0, col0+128) x k in [k0, k0+16) into dst[128][LDK]
+template <bool ALIGNED16>
+__device__ __forceinline__ void load_tile(double *dst, const double *X, long long ldx, long long n, int p, int col0,
+                                          long long k0, int tid) {
+  if (ALIGNED16) {
+    // 128 rows x 8 chunks of 16 B; 256 threads -> 4 chunks each
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * GT;
+      const int row = idx >> 3, ch = idx & 7;
+      const int col = col0 + row;
+      const long long k = k0 + ch * 2;
+      int bytes = 0;
+      if (col < p && k < n) bytes = (k + 1 < n) ? 16 : 8;
+      const double *src = X + (bytes ? ((long long)col * ldx + k) : 0);
+      cp_async16(dst + row * LDK + ch * 2, src, bytes);
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + it * GT;
+      const int row = idx >> 4, ch = idx & 15;
+      const int col = col0 + row;
+      const long long k = k0 + ch;
+      const int bytes = (col < p && k < n) ? 8 : 0;
+      const double *src = X + (bytes ? ((long long)col * ldx + k) : 0);
+      cp_async8(dst + row * LDK + ch, src, bytes);
+    }
+  }
+}
+
+template <bool ALIGNED16>
+__global__ void __launch_bounds__(GT, 1)
+    gram_syrk_kernel(const double *__restrict__ X, long long n, int p, long long ldx, double *__restrict__ G,
+                     long long ldg, const int2 *__restrict__ tiles, int ntiles, double divisor, int do_scale) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3; // 2 x 4 warps
+  const int g = lane >> 2, q = lane & 3;
+  const long long nK = (n + BK - 1) / BK;
+
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int bi = tiles[t].x, bj = tiles[t].y; // bi >= bj
+    const int colA = bi * BM, colB = bj * BN;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // prologue
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nK) {
+        double *st = smem + s * STAGE_DOUBLES;
+        load_tile<ALIGNED16>(st, X, ldx, n, p, colA, (long long)s * BK, tid);
+        load_tile<ALIGNED16>(st + BM * LDK, X, ldx, n, p, colB, (long long)s * BK, tid);
+      }
+      cp_commit();
+    }
+    for (long long kt = 0; kt < nK; ++kt) {
+      cp_wait<STAGES - 2>();
+      __syncthreads();
+      { // prefetch stage kt + STAGES - 1 into the slot freed by iteration kt - 1
+        const long long kn = kt + STAGES - 1;
+        if (kn < nK) {
+          double *st = smem + (kn % STAGES) * STAGE_DOUBLES;
+          load_tile<ALIGNED16>(st, X, ldx, n, p, colA, kn * BK, tid);
+          load_tile<ALIGNED16>(st + BM * LDK, X, ldx, n, p, colB, kn * BK, tid);
+        }
+        cp_commit();
+      }
+      const double *As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * 64) * LDK;
+      const double *Bs = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDK + (wn * 32) * LDK;
+#pragma unroll
+      for (int kk = 0; kk < BK; kk += 4) {
+        double af[8], bf[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) af[i] = As[(i * 8 + g) * LDK + kk + q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = Bs[(j * 8 + g) * LDK + kk + q];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    cp_wait<0>();
+    __syncthreads(); // all warps done with the last stage before the next tile's prologue overwrites it
+
+    // epilogue: G[colA + m, colB + nn] and its mirror
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = colA + wm * 64 + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = colB + wn * 32 + j * 8 + 2 * q;
+        double v0 = acc[i][j][0], v1 = acc[i][j][1];
+        if (do_scale) {
+          v0 = v0 / divisor;
+          v1 = v1 / divisor;
+        }
+        if (row < p) {
+          if (bi != bj) {
+            if (col < p) {
+              G[row + (long long)col * ldg] = v0;
+              G[col + (long long)row * ldg] = v0;
+            }
+            if (col + 1 < p) {
+              G[row + (long long)(col + 1) * ldg] = v1;
+              G[col + 1 + (long long)row * ldg] = v1;
+            }
+          } else { // diagonal tile: the lower part (and the diagonal) is authoritative
+            if (col < p && row >= col) {
+              G[row + (long long)col * ldg] = v0;
+              G[col + (long long)row * ldg] = v0;
+            }
+            if (col + 1 < p && row >= col + 1) {
+              G[row + (long long)(col + 1) * ldg] = v1;
+              G[col + 1 + (long long)row * ldg] = v1;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// c_j = -(X_j'y) [/ n]; one warp per column
+__global__ void xty_kernel(const double *__restrict__ X, long long n, int p, long long ldx,
+                           const double *__restrict__ y, double *__restrict__ c, double divisor, int do_scale) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < p; k += gridDim.x * wpb) {
+    const double *col = X + (long long)k * ldx;
+    double s0 = 0.0, s1 = 0.0;
+    long long i = lane;
+    for (; i + 32 < n; i += 64) {
+      s0 = fma(__ldg(col + i), __ldg(y + i), s0);
+      s1 = fma(__ldg(col + i + 32), __ldg(y + i + 32), s1);
+    }
+    for (; i < n; i += 32) s0 = fma(__ldg(col + i), __ldg(y + i), s0);
+    double s = warp_sum(s0 + s1);
+    if (lane == 0) c[k] = do_scale ? -s / divisor : -s;
+  }
+}
+
+__global__ void scale_kernel(double *G, long long count, double divisor) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    G[i] = G[i] / divisor;
+}
+
+} // namespace
+
+int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,
+                double *c, double divisor, bool scale) {
+  const int nb = (p + BM - 1) / BM;
+  // tile list in 12 x 12 super-tiles over the lower triangle
+  const int S = 12;
+  std::vector<int2> tiles;
+  tiles.reserve((size_t)nb * (nb + 1) / 2);
+  for (int SI = 0; SI < nb; SI += S)
+    for (int SJ = 0; SJ <= SI; SJ += S)
+      for (int bi = SI; bi < min(SI + S, nb); ++bi)
+        for (int bj = SJ; bj < min(SJ + S, nb) && bj <= bi; ++bj) tiles.push_back(make_int2(bi, bj));
+  const int ntiles = (int)tiles.size();
+  int2 *dtiles = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&dtiles, (size_t)ntiles * sizeof(int2), h->stream));
+  CUDA_TRY(cudaMemcpyAsync(dtiles, tiles.data(), (size_t)ntiles * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream)); // `tiles` is a host temporary
+  const size_t dyn = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
+  const long long ldg = ((long long)p + 1) & ~1ll;
+  const int grid = min(ntiles, h->sm_count);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(gram_syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CUDA_TRY(cudaFuncSetAttribute(gram_syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_done = true;
+  }
+  if (aligned)
+    gram_syrk_kernel<true><<<grid, GT, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, scale ? 1 : 0);
+  else
+    gram_syrk_kernel<false><<<grid, GT, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, scale ? 1 : 0);
+  CUDA_TRY(cudaGetLastError());
+  xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, c, divisor, scale ? 1 : 0);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(dtiles, h->stream));
+  return CDGPU_OK;
+}
+
+int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_total) {
+  const long long ldg = ((long long)p + 1) & ~1ll;
+  (void)c; // c sits right behind G in the same allocation (api.cu: gram_build)
+  const long long count = ldg * p + p;
+  scale_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(G, count, n_total);
+  CUDA_TRY(cudaGetLastError());
+  return CDGPU_OK;
+}

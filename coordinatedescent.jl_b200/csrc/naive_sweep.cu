@@ -1,0 +1,639 @@
+// naive_sweep.cu — naive/residual-form active-set coordinate descent for CDLeastSquaresLoss,
+// CDWeightedLSLoss and CDSqrtLassoLoss (src/cd_differentiable_function.jl:43-291) driven by
+// _coordinateDescent!/_cdPass! (src/coordinate_descent.jl:65-110), with the scaledLasso! sigma loop
+// (src/lasso.jl:131-141) on the device.  One persistent cooperative kernel per solve / path.
+//
+// B200 design:
+//  * every CTA keeps a private copy of the residual r (and the weights w) in shared memory; the
+//    same updates are applied to every copy, so the copies stay bit-identical with no traffic.
+//  * FULL pass = exact Gauss-Seidel by speculation over chunks of columns: one warp per column
+//    streams X[:,k] from HBM once (8n bytes/visit, the algorithmic minimum), forms X_k'r against the
+//    shared r, evaluates the closed-form update and publishes h.  One grid barrier later every CTA
+//    finds the FIRST coordinate of the chunk that moves, applies r -= X_k h to its copy (the column
+//    is L2 resident) and only the columns behind it are re-evaluated (from L2, not HBM).
+//  * the column norms a_k = sum_i [w_i] X_ik^2, which the reference recomputes on every visit
+//    (:96-99), are formed once per handle.
+//  * ACTIVE-SET passes are a sequential chain over a few columns: CTA 0 runs them alone against its
+//    shared r (column reads are L2 hits, next column prefetched), then publishes r.
+//  * sqrt-lasso: s, ||r+||^2 of :254-266 follow from d = X_k'r, ||r||^2 and a_k
+//    (s = d + a_k x_k, ||r+||^2 = ||r||^2 + 2 x_k d + x_k^2 a_k), so a visit is still one column read.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int NV_T = 512;
+constexpr int NV_W = NV_T / 32;
+
+struct HEntry {
+  double h, nw;
+};
+
+struct NBcast {
+  long long npasses, visits, accepted;
+  double maxH;
+  int conv, nact, status, pad;
+};
+
+struct NSmem {
+  double red[2][NV_W];
+  unsigned int redu[NV_W];
+  double bval[2];
+  int nact, flag;
+};
+
+struct NCtx {
+  const NaiveArgs &a;
+  cg::grid_group &grid;
+  NSmem *sm;
+  double *r, *w; // shared
+  double rr;     // ||r||^2 (every thread of every CTA holds the same value)
+  HEntry *hbuf;  // global, 2 * CH
+  NBcast *bc;    // global
+  int CH, G, bid;
+};
+
+__device__ __forceinline__ double block_sum(NSmem *sm, double v, int slot) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm->red[slot][threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < NV_W; ++i) t += sm->red[slot][i];
+  return t;
+}
+__device__ __forceinline__ void block_sum2(NSmem *sm, double &u, double &v) {
+  u = warp_sum(u);
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) {
+    sm->red[0][threadIdx.x >> 5] = u;
+    sm->red[1][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < NV_W; ++i) {
+    t0 += sm->red[0][i];
+    t1 += sm->red[1][i];
+  }
+  u = t0;
+  v = t1;
+}
+
+// closed-form coordinate update given d = X_k' (w .* r):
+//   LS/WLS  cd_differentiable_function.jl:101-104 / :184-187;  sqrt  :271-283
+__device__ __forceinline__ void coord_update(int kind, int n, double d, double a, double old, double lam, double om,
+                                             double rr, double &nw, double &h) {
+  if (kind == CDGPU_LOSS_SQRT) {
+    const double s = d + a * old;
+    const double rsq = rr + 2.0 * old * d + old * old * a;
+    const double l = lam * om;
+    const double t = l * sqrt(rsq);
+    if (fabs(s) <= t)
+      nw = 0.0;
+    else if (s > t)
+      nw = (s - l / sqrt(1.0 - l * l / a) * sqrt(rsq - s * s / a)) / a;
+    else
+      nw = (s + l / sqrt(1.0 - l * l / a) * sqrt(rsq - s * s / a)) / a;
+  } else {
+    const double v = __dadd_rn(old, d / a);
+    const double thr = __dmul_rn(__dmul_rn((double)n / a, lam), om);
+    nw = cd_shrink(v, thr);
+  }
+  h = nw - old;
+}
+
+// one warp: d = sum_i X[i,k] r_i [w_i]
+__device__ __forceinline__ double warp_col_dot(const NCtx &c, const double *col) {
+  const int n = c.a.n, lane = threadIdx.x & 31;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = lane;
+  if (c.w) {
+    for (; i + 96 < n; i += 128) {
+      const double x0 = __ldg(col + i), x1 = __ldg(col + i + 32), x2 = __ldg(col + i + 64), x3 = __ldg(col + i + 96);
+      s0 = fma(x0 * c.w[i], c.r[i], s0);
+      s1 = fma(x1 * c.w[i + 32], c.r[i + 32], s1);
+      s2 = fma(x2 * c.w[i + 64], c.r[i + 64], s2);
+      s3 = fma(x3 * c.w[i + 96], c.r[i + 96], s3);
+    }
+    for (; i < n; i += 32) s0 = fma(__ldg(col + i) * c.w[i], c.r[i], s0);
+  } else {
+    for (; i + 96 < n; i += 128) {
+      const double x0 = __ldg(col + i), x1 = __ldg(col + i + 32), x2 = __ldg(col + i + 64), x3 = __ldg(col + i + 96);
+      s0 = fma(x0, c.r[i], s0);
+      s1 = fma(x1, c.r[i + 32], s1);
+      s2 = fma(x2, c.r[i + 64], s2);
+      s3 = fma(x3, c.r[i + 96], s3);
+    }
+    for (; i < n; i += 32) s0 = fma(__ldg(col + i), c.r[i], s0);
+  }
+  return warp_sum((s0 + s1) + (s2 + s3));
+}
+
+// r -= X_k * h on this CTA's copy; refreshes ||r||^2 when the loss needs it
+__device__ __forceinline__ void apply_step(NCtx &c, const double *col, double h) {
+  const int n = c.a.n;
+  if (c.a.kind == CDGPU_LOSS_SQRT) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += NV_T) {
+      const double v = __dsub_rn(c.r[i], __dmul_rn(__ldg(col + i), h));
+      c.r[i] = v;
+      acc = fma(v, v, acc);
+    }
+    c.rr = block_sum(c.sm, acc, 0);
+    __syncthreads();
+  } else {
+    for (int i = threadIdx.x; i < n; i += NV_T) c.r[i] = __dsub_rn(c.r[i], __dmul_rn(__ldg(col + i), h));
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ full pass --
+__device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter, int &rp, long long &accepted) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool ordered = a.randomize == 0;
+  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  double maxH = 0.0;
+  for (int q0 = 0; q0 < a.p; q0 += c.CH) {
+    const int qlen = min(c.CH, a.p - q0);
+    int start = 0;
+    for (;;) {
+      HEntry *hb = c.hbuf + (size_t)rp * c.CH;
+      // position j of the chunk belongs to CTA j % G, warp (j / G) % NV_W
+      for (int j = c.bid + c.G * warp; j < qlen; j += c.G * NV_W) {
+        if (j < start) continue;
+        const int k = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
+        const double d = warp_col_dot(c, a.X + (long long)k * a.ldx);
+        if (lane == 0) {
+          double nw, h;
+          coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
+                       c.rr, nw, h);
+          HEntry e;
+          e.h = h;
+          e.nw = nw;
+          __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(e.h, e.nw));
+        }
+      }
+      c.grid.sync();
+      // first position >= start with h != 0
+      unsigned int best = 0xffffffffu;
+      for (int j = start + tid; j < qlen; j += NV_T) {
+        const double hj = __ldcg(&hb[j].h);
+        if (hj != 0.0) {
+          best = (unsigned int)j;
+          break;
+        }
+      }
+      best = __reduce_min_sync(0xffffffffu, best);
+      if (lane == 0) sm->redu[warp] = best;
+      __syncthreads();
+      unsigned int jmin = sm->redu[0];
+#pragma unroll
+      for (int i = 1; i < NV_W; ++i) jmin = min(jmin, sm->redu[i]);
+      __syncthreads();
+      rp ^= 1;
+      if (jmin == 0xffffffffu) break;
+      const int k = ordered ? q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(q0 + jmin));
+      const double2 e = __ldcg(reinterpret_cast<const double2 *>(hb + jmin));
+      const double h = e.x, nw = e.y;
+      if (c.bid == 0 && tid == 0) {
+        __stcg(a.beta + k, nw);
+        if (!a.inlist[k]) { // setindex! appends on the first non-zero store
+          a.inlist[k] = 1;
+          a.act[sm->nact] = k;
+          sm->nact += 1;
+        }
+      }
+      apply_step(c, a.X + (long long)k * a.ldx, h);
+      maxH = fmax(maxH, fabs(h));
+      accepted += 1;
+      start = (int)jmin + 1;
+      if (start >= qlen) break;
+    }
+  }
+  return maxH;
+}
+
+// dropzeros! on CTA 0's list; refreshes actval from the dense beta
+__device__ void list_dropzeros(NCtx &c) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x;
+  const int m = sm->nact;
+  int anyz = 0;
+  for (int i = tid; i < m; i += NV_T) {
+    const double v = __ldcg(a.beta + a.act[i]);
+    a.actval[i] = v;
+    anyz |= (v == 0.0);
+  }
+  anyz = __syncthreads_or(anyz);
+  if (anyz && tid == 0) {
+    int n = m, i = 0;
+    while (i < n) {
+      if (a.actval[i] == 0.0) {
+        a.inlist[a.act[i]] = 0;
+        if (i != n - 1) {
+          a.actval[i] = a.actval[n - 1];
+          a.act[i] = a.act[n - 1];
+        }
+        n -= 1;
+      } else {
+        i += 1;
+      }
+    }
+    sm->nact = n;
+  }
+  __syncthreads();
+}
+
+// consecutive active-set passes on CTA 0 (sequential chain; one column per step)
+__device__ void active_phase(NCtx &c, double lam, long long maxPasses, unsigned long long pass_counter) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x, n = a.n;
+  const bool ordered = a.randomize == 0;
+  long long npasses = 0, visits = 0, accepted = 0;
+  double maxH = 0.0;
+  int conv = 0;
+  while (npasses < maxPasses) {
+    const int m = sm->nact;
+    const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter + npasses);
+    double pmax = 0.0;
+    for (int s = 0; s < m; ++s) {
+      const int i = ordered ? s : (int)cd_perm(pkm, (uint32_t)s);
+      const int k = a.act[i];
+      const double *col = a.X + (long long)k * a.ldx;
+      if (s + 1 < m) { // pull the next column towards the SM while this one is reduced
+        const int kn = a.act[ordered ? s + 1 : (int)cd_perm(pkm, (uint32_t)(s + 1))];
+        const char *nc = reinterpret_cast<const char *>(a.X + (long long)kn * a.ldx);
+        for (int off = tid * 128; off < n * 8; off += NV_T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nc + off));
+      }
+      double d = 0.0;
+      if (c.w) {
+        for (int t = tid; t < n; t += NV_T) d = fma(__ldg(col + t) * c.w[t], c.r[t], d);
+      } else {
+        for (int t = tid; t < n; t += NV_T) d = fma(__ldg(col + t), c.r[t], d);
+      }
+      d = block_sum(sm, d, 1);
+      double nw, h;
+      const double old = a.actval[i];
+      coord_update(a.kind, n, d, __ldg(a.colsq + k), old, lam, a.omega ? __ldg(a.omega + k) : 1.0, c.rr, nw, h);
+      __syncthreads(); // everyone has read actval[i] and red[1]
+      if (tid == 0) a.actval[i] = nw;
+      if (h != 0.0) {
+        apply_step(c, col, h);
+        accepted += 1;
+      }
+      pmax = fmax(pmax, fabs(h));
+    }
+    npasses += 1;
+    visits += m;
+    maxH = pmax;
+    // dropzeros!
+    __syncthreads();
+    int anyz = 0;
+    for (int i = tid; i < m; i += NV_T) anyz |= (a.actval[i] == 0.0);
+    anyz = __syncthreads_or(anyz);
+    if (anyz) {
+      if (tid == 0) {
+        int nn = m, i = 0;
+        while (i < nn) {
+          if (a.actval[i] == 0.0) {
+            a.inlist[a.act[i]] = 0;
+            __stcg(a.beta + a.act[i], 0.0);
+            if (i != nn - 1) {
+              a.actval[i] = a.actval[nn - 1];
+              a.act[i] = a.act[nn - 1];
+            }
+            nn -= 1;
+          } else {
+            i += 1;
+          }
+        }
+        sm->nact = nn;
+      }
+      __syncthreads();
+    }
+    if (maxH < a.optTol) {
+      conv = 1;
+      break;
+    }
+  }
+  // publish: dense beta of the listed coordinates, residual, summary
+  const int m = sm->nact;
+  for (int i = tid; i < m; i += NV_T) __stcg(a.beta + a.act[i], a.actval[i]);
+  for (int i = tid; i < n; i += NV_T) __stcg(a.r + i, c.r[i]);
+  if (tid == 0) {
+    c.bc->npasses = npasses;
+    c.bc->visits = visits;
+    c.bc->accepted = accepted;
+    c.bc->maxH = maxH;
+    c.bc->conv = conv;
+    c.bc->nact = m;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
+__device__ double shared_std(NCtx &c) { // Statistics.std(r), corrected, two-pass
+  const int n = c.a.n;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += NV_T) s += c.r[i];
+  const double mean = block_sum(c.sm, s, 0) / (double)n;
+  __syncthreads();
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += NV_T) v = fma(c.r[i] - mean, c.r[i] - mean, v);
+  v = block_sum(c.sm, v, 0);
+  __syncthreads();
+  return sqrt(v / (double)(n - 1));
+}
+__device__ double shared_sumsq(NCtx &c) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < c.a.n; i += NV_T) v = fma(c.r[i], c.r[i], v);
+  v = block_sum(c.sm, v, 0);
+  __syncthreads();
+  return v;
+}
+
+__global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, int CH, HEntry *hbuf, NBcast *bc) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NCtx c{a, grid};
+  c.sm = reinterpret_cast<NSmem *>(smem_raw);
+  double *sd = reinterpret_cast<double *>(smem_raw + (sizeof(NSmem) + 15) / 16 * 16);
+  c.r = sd;
+  c.w = a.w ? sd + a.n : nullptr;
+  c.hbuf = hbuf;
+  c.bc = bc;
+  c.CH = CH;
+  c.G = gridDim.x;
+  c.bid = blockIdx.x;
+  const int tid = threadIdx.x, n = a.n;
+  for (int i = tid; i < n; i += NV_T) {
+    c.r[i] = a.r[i];
+    if (c.w) c.w[i] = a.w[i];
+  }
+  if (tid == 0) c.sm->nact = *a.nact;
+  __syncthreads();
+  c.rr = shared_sumsq(c);
+
+  int rp = 0;
+  unsigned long long pass_counter = 0;
+  DevStats st;
+  st.passes = st.full_passes = st.visits = st.accepted = 0;
+  st.maxH = 0.0;
+  st.converged = 0;
+  st.outer_iters = 0;
+  st.sigma = 0.0;
+  int status = 0;
+  long long cols_done = 0, out_off = 0;
+  double sigma = 1.0;
+  if (a.scaled == 1) sigma = a.sigma0;
+  if (a.scaled == 2) sigma = shared_std(c); // :WarmStart  lasso.jl:124-126
+  const long long nouter = a.scaled ? a.outerMaxIter : 1;
+  for (int li = 0; li < a.nlambda && status == 0; ++li) {
+    if (li > 0 && !a.accumulate) {
+      st.passes = st.full_passes = st.visits = st.accepted = 0;
+      st.maxH = 0.0;
+    }
+    for (long long outer = 1; outer <= nouter; ++outer) {
+      const double lam = a.scaled ? a.lambdas[li] * sigma : a.lambdas[li];
+      st.converged = 0;
+      bool conv = true;
+      long long iter = 0;
+      while (iter < a.maxIter) {
+        if (conv) {
+          iter += 1;
+          st.passes += 1;
+          st.full_passes += 1;
+          st.visits += a.p;
+          const double maxH = full_pass(c, lam, pass_counter, rp, st.accepted);
+          pass_counter += 1;
+          if (c.bid == 0) list_dropzeros(c);
+          st.maxH = maxH;
+          conv = maxH < a.optTol;
+          if (conv) {
+            st.converged = 1;
+            break;
+          }
+        } else {
+          if (c.bid == 0) active_phase(c, lam, a.maxIter - iter, pass_counter);
+          grid.sync();
+          const long long np = __ldcg(&bc->npasses);
+          if (c.bid != 0) {
+            for (int i = tid; i < n; i += NV_T) c.r[i] = __ldcg(a.r + i);
+            __syncthreads();
+          }
+          if (a.kind == CDGPU_LOSS_SQRT) c.rr = shared_sumsq(c);
+          iter += np;
+          pass_counter += np;
+          st.passes += np;
+          st.visits += __ldcg(&bc->visits);
+          st.accepted += __ldcg(&bc->accepted);
+          st.maxH = __ldcg(&bc->maxH);
+          conv = __ldcg(&bc->conv) != 0;
+          grid.sync(); // bc may be rewritten only after everyone has read it
+        }
+      }
+      if (!a.scaled) break;
+      // sigma update, lasso.jl:134-140 (every CTA computes the same value from its copy of r)
+      st.outer_iters = (int)outer;
+      const double snew = sqrt(shared_sumsq(c) / (double)n);
+      if (fabs(snew - sigma) / sigma < a.outerTol) break;
+      sigma = snew;
+    }
+    if (a.scaled) st.sigma = sigma;
+    // ---- end of this lambda
+    if (c.bid == 0 && tid == 0) {
+      bc->nact = c.sm->nact;
+      __threadfence();
+    }
+    grid.sync();
+    const int nnz = __ldcg(&bc->nact);
+    if (!a.accumulate) {
+      if (a.colptr && out_off + nnz > a.capacity) status = 1;
+      if (c.bid == 0 && status == 0) {
+        if (a.colptr) {
+          for (int i = tid; i < nnz; i += NV_T) {
+            a.rowval[out_off + i] = (long long)a.act[i] + 1;
+            a.nzval[out_off + i] = a.actval[i];
+          }
+          if (tid == 0) a.colptr[li + 1] = out_off + nnz;
+        }
+        if (tid == 0 && a.stats) a.stats[li] = st;
+      }
+      out_off += nnz;
+      if (status == 0) cols_done = li + 1;
+      if (a.max_hat_s >= 0 && nnz > a.max_hat_s) break;
+    } else {
+      cols_done = li + 1;
+    }
+  }
+  if (c.bid == 0) {
+    if (a.accumulate && tid == 0 && a.stats) a.stats[0] = st;
+    for (int i = tid; i < n; i += NV_T) a.r[i] = c.r[i];
+    if (a.scaled) { // std(f.r) of the returned LassoSolution (lasso.jl:143)
+      const double sd = shared_std(c);
+      if (tid == 0) a.scr[0] = sd;
+    }
+    if (tid == 0) {
+      *a.nact = c.sm->nact;
+      a.flag[0] = status;
+      a.flag[1] = (int)cols_done;
+    }
+  }
+}
+
+// ------------------------------------------------------------ small kernels --
+// initialize!: r = y - X beta over the stored entries (cd_differentiable_function.jl:59-72)
+__global__ void naive_init_kernel(const double *X, long long ldx, int n, const double *y, const int *act,
+                                  const double *actval, const int *nact, double *r) {
+  const int m = *nact;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < m; ++s) acc += X[i + (long long)act[s] * ldx] * actval[s];
+    r[i] = y[i] - acc;
+  }
+}
+__global__ void dense_iterate_kernel(int p, const int *act, const double *actval, const int *nact, double *beta,
+                                     unsigned char *inlist, int phase) {
+  const int m = *nact;
+  if (phase == 0) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) {
+      beta[j] = 0.0;
+      inlist[j] = 0;
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+      beta[act[i]] = actval[i];
+      inlist[act[i]] = 1;
+    }
+  }
+}
+// a_k = sum_i [w_i] X_ik^2 (one warp per column); sqrt_over_n: _stdX! (utils.jl:127-151)
+__global__ void colsq_kernel(const double *X, long long ldx, int n, int p, const double *w, double *out,
+                             int sqrt_over_n) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < p; k += gridDim.x * wpb) {
+    const double *col = X + (long long)k * ldx;
+    double s = 0.0;
+    if (w)
+      for (int i = lane; i < n; i += 32) s = fma(w[i], col[i] * col[i], s);
+    else
+      for (int i = lane; i < n; i += 32) s = fma(col[i], col[i], s);
+    s = warp_sum(s);
+    if (lane == 0) out[k] = sqrt_over_n ? sqrt(s / (double)n) : s;
+  }
+}
+// |gradient_k(0)| [/ omega_k] per column, then the max (_findLambdaMax, coordinate_descent.jl:118-149)
+__global__ void grad0_kernel(int kind, const double *X, long long ldx, int n, int p, const double *y, const double *w,
+                             const double *omega, double *out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  double ynorm = 1.0;
+  if (kind == CDGPU_LOSS_SQRT) { // gradient = -X_j'r / norm(r)   :234-235
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s = fma(y[i], y[i], s);
+    ynorm = sqrt(warp_sum(s));
+  }
+  for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < p; k += gridDim.x * wpb) {
+    const double *col = X + (long long)k * ldx;
+    double s = 0.0;
+    if (w)
+      for (int i = lane; i < n; i += 32) s = fma(w[i] * col[i], y[i], s);
+    else
+      for (int i = lane; i < n; i += 32) s = fma(col[i], y[i], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      double t = fabs(kind == CDGPU_LOSS_SQRT ? s / ynorm : s / (double)n);
+      if (omega) t = t / omega[k];
+      out[k] = t;
+    }
+  }
+}
+__global__ void max_kernel(const double *v, int p, double *out) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int j = threadIdx.x; j < p; j += blockDim.x) m = fmax(m, v[j]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    m = warp_max(m);
+    if (threadIdx.x == 0) *out = m;
+  }
+}
+
+} // namespace
+
+int launch_colsq(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p, const double *w, double *out,
+                 bool sqrt_over_n) {
+  int blocks = min((p + 7) / 8, h->sm_count * 8);
+  colsq_kernel<<<max(blocks, 1), 256, 0, h->stream>>>(X, ldx, n, p, w, out, sqrt_over_n ? 1 : 0);
+  CUDA_TRY(cudaGetLastError());
+  return CDGPU_OK;
+}
+
+int launch_lambda_max_naive(cdgpu_handle_s *h, int kind, const double *X, long long ldx, int n, int p, const double *y,
+                            const double *w, const double *omega, double *scr, double *out) {
+  int blocks = min((p + 7) / 8, h->sm_count * 8);
+  grad0_kernel<<<max(blocks, 1), 256, 0, h->stream>>>(kind, X, ldx, n, p, y, w, omega, scr);
+  max_kernel<<<1, 1024, 0, h->stream>>>(scr, p, out);
+  CUDA_TRY(cudaGetLastError());
+  return CDGPU_OK;
+}
+
+int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a) {
+  naive_init_kernel<<<(a.n + 255) / 256, 256, 0, h->stream>>>(a.X, a.ldx, a.n, a.y, a.act, a.actval, a.nact, a.r);
+  dense_iterate_kernel<<<(a.p + 255) / 256, 256, 0, h->stream>>>(a.p, a.act, a.actval, a.nact, a.beta, a.inlist, 0);
+  dense_iterate_kernel<<<32, 256, 0, h->stream>>>(a.p, a.act, a.actval, a.nact, a.beta, a.inlist, 1);
+  CUDA_TRY(cudaGetLastError());
+  return CDGPU_OK;
+}
+
+int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
+  static bool attr_done = false;
+  const size_t max_dyn = 227 * 1024;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    attr_done = true;
+  }
+  const size_t dyn = (sizeof(NSmem) + 15) / 16 * 16 + (size_t)a.n * sizeof(double) * (a.w ? 2 : 1);
+  if (dyn > max_dyn)
+    return cdgpu_set_error(CDGPU_ECAP,
+                           "naive-form sweep keeps r%s in shared memory: n = %d exceeds the %zu-byte limit; use the "
+                           "covariance form (cdgpu_gram_create) for tall problems",
+                           a.w ? " and w" : "", a.n, max_dyn);
+  // grid: one CTA per SM, fewer when there are not enough columns to feed 16 warps each
+  int G = min(h->sm_count, (a.p + NV_W - 1) / NV_W);
+  if (const char *env = getenv("CDGPU_NAIVE_GRID")) {
+    int v = atoi(env);
+    if (v >= 1 && v <= h->sm_count) G = v;
+  }
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, naive_path_kernel, NV_T, dyn));
+  if (occ < 1) return cdgpu_set_error(CDGPU_ECUDA, "naive sweep kernel does not fit on an SM");
+  G = max(1, min(G, occ * h->sm_count));
+  // chunk: up to 8 columns per warp per round, at most ~48 MB of columns so a re-evaluation hits L2
+  long long cols_l2 = (48ll << 20) / ((long long)a.n * 8);
+  long long CH = min((long long)G * NV_W * 8, max((long long)G * NV_W, cols_l2));
+  CH = max(1ll, min(CH, (long long)a.p));
+  if (const char *env = getenv("CDGPU_NAIVE_CHUNK")) {
+    long long v = atoll(env);
+    if (v >= 1) CH = min(v, (long long)a.p);
+  }
+  // hbuf + broadcast block live behind the 8p+8n scratch doubles: carve from the tail of iscr/scr
+  HEntry *hbuf = reinterpret_cast<HEntry *>(a.scr + 8); // 2*CH entries = 4*CH doubles <= 4p
+  NBcast *bc = reinterpret_cast<NBcast *>(a.scr + 8 + 4 * (long long)a.p);
+  int ch = (int)CH;
+  void *args[] = {(void *)&a, (void *)&ch, (void *)&hbuf, (void *)&bc};
+  CUDA_TRY(cudaLaunchCooperativeKernel((void *)naive_path_kernel, dim3(G), dim3(NV_T), args, dyn, h->stream));
+  return CDGPU_OK;
+}

@@ -1,0 +1,376 @@
+// vc_batch.cu — K4: batched varying-coefficient lasso, locpolyl1 with refit=false
+// (src/varying_coefficient_lasso.jl:30-79): for every grid point z0 one kernel-weighted
+// local-polynomial lasso  min sum_i w_i (y_i - eX_i'b)^2/(2n) + lambda0 sum_k sd_k |b_k|,
+//   w_i = K_h(z_i, z0) (:17-21),  eX[i,(j,l)] = X[i,j] (z_i - z0)^l (:550-569),
+//   sd_k = sqrt(sum_i w_i eX_ik^2 / n) (utils.jl:140-151),
+// solved by the reference's CD loop on CDWeightedLSLoss (cd_differentiable_function.jl:165-194).
+//
+// B200 design: ONE CTA PER GRID POINT, everything per-problem (w, z - z0, r, column norms, iterate,
+// active list) in shared memory; the expanded n x p(d+1) design is never materialised — a column
+// is X[:,j] (shared by all problems, L1/L2 resident: 8np bytes total) times a power of (z - z0).
+// Full passes are speculative (one warp per coordinate, first mover wins, exact Gauss-Seidel
+// order); active-set passes are a short sequential chain with block-wide dots.  No inter-CTA
+// communication at all; grid points are sharded over GPUs by [m_begin, m_end).
+#include <math.h>
+
+#include "common.cuh"
+
+#define API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+constexpr int VC_T = 256;
+constexpr int VC_W = VC_T / 32;
+
+struct VcArgs {
+  const double *X;
+  long long ldx;
+  int n, p, degree;
+  const double *z, *y, *zgrid;
+  int g0, g1; // grid points [g0, g1)
+  int kernel_kind;
+  double bandwidth, lambda0;
+  long long maxIter;
+  double optTol;
+  int randomize;
+  unsigned long long seed;
+  double *out; // ep x m, column g at out + g*ep
+  DevStats *stats;
+};
+
+struct VSm {
+  double red[VC_W];
+  double cand_h[VC_W], cand_nw[VC_W];
+  int nact, flag;
+};
+
+__device__ __forceinline__ double ipow(double x, int l) {
+  double v = 1.0;
+  for (int i = 0; i < l; ++i) v *= x;
+  return v;
+}
+
+__device__ __forceinline__ double vblock_sum(VSm *sm, double v) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm->red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < VC_W; ++i) t += sm->red[i];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  const int n = a.n, dg = a.degree + 1, ep = a.p * dg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  VSm *sm = reinterpret_cast<VSm *>(raw);
+  double *sw = reinterpret_cast<double *>(raw + (sizeof(VSm) + 15) / 16 * 16);
+  double *sdz = sw + n, *sr = sdz + n;
+  double *sa = sr + n;       // a_k = sum w eX_k^2
+  double *sbeta = sa + ep;   // dense iterate
+  double *sval = sbeta + ep; // values in list order
+  int *sact = reinterpret_cast<int *>(sval + ep);
+  unsigned char *sin = reinterpret_cast<unsigned char *>(sact + ep);
+
+  for (int g = a.g0 + blockIdx.x; g < a.g1; g += gridDim.x) {
+    const double z0 = a.zgrid[g];
+    __syncthreads();
+    for (int i = tid; i < n; i += VC_T) {
+      const double zi = a.z[i];
+      double w;
+      if (a.kernel_kind == CDGPU_KERNEL_GAUSSIAN) {
+        const double d = zi - z0;
+        w = exp(-(d * d) / a.bandwidth) / a.bandwidth;
+      } else {
+        const double u = (zi - z0) / a.bandwidth;
+        w = fabs(u) >= 1.0 ? 0.0 : 0.75 * (1.0 - u * u) / a.bandwidth;
+      }
+      sw[i] = w;
+      sdz[i] = zi - z0;
+      sr[i] = a.y[i]; // r = y - eX*0
+    }
+    for (int k = tid; k < ep; k += VC_T) {
+      sbeta[k] = 0.0;
+      sin[k] = 0;
+    }
+    if (tid == 0) sm->nact = 0;
+    __syncthreads();
+    // column norms, one warp per expanded column
+    for (int k = warp; k < ep; k += VC_W) {
+      const int j = k / dg, l = k - j * dg;
+      const double *col = a.X + (long long)j * a.ldx;
+      double s = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const double e = __ldg(col + i) * ipow(sdz[i], l);
+        s = fma(sw[i], e * e, s);
+      }
+      s = warp_sum(s);
+      if (lane == 0) sa[k] = s;
+    }
+    __syncthreads();
+
+    DevStats st;
+    st.passes = st.full_passes = st.visits = st.accepted = 0;
+    st.maxH = 0.0;
+    st.converged = 0;
+    st.outer_iters = 0;
+    st.sigma = 0.0;
+    const bool ordered = a.randomize == 0;
+    unsigned long long pass_counter = 0;
+    bool conv = true;
+    long long iter = 0;
+    while (iter < a.maxIter) {
+      double maxH = 0.0;
+      iter += 1;
+      st.passes += 1;
+      if (conv) { // ---- full pass, speculative in rounds of VC_W coordinates
+        st.full_passes += 1;
+        st.visits += ep;
+        const PermKey pk = cd_perm_key((uint32_t)ep, a.seed, pass_counter);
+        int pos = 0;
+        while (pos < ep) {
+          const int myq = pos + warp;
+          double h = 0.0, nw = 0.0;
+          int k = -1;
+          if (myq < ep) {
+            k = ordered ? myq : (int)cd_perm(pk, (uint32_t)myq);
+            const int j = k / dg, l = k - j * dg;
+            const double *col = a.X + (long long)j * a.ldx;
+            double d = 0.0;
+            for (int i = lane; i < n; i += 32) d = fma(sr[i] * (__ldg(col + i) * ipow(sdz[i], l)), sw[i], d);
+            d = warp_sum(d);
+            const double ak = sa[k], old = sbeta[k];
+            const double v = __dadd_rn(old, d / ak);
+            const double thr = __dmul_rn(__dmul_rn((double)n / ak, a.lambda0), sqrt(ak / (double)n));
+            nw = cd_shrink(v, thr);
+            h = nw - old;
+          }
+          if (lane == 0) {
+            sm->cand_h[warp] = h;
+            sm->cand_nw[warp] = nw;
+          }
+          __syncthreads();
+          int first = -1;
+#pragma unroll
+          for (int q = VC_W - 1; q >= 0; --q)
+            if (sm->cand_h[q] != 0.0) first = q;
+          if (first < 0) {
+            pos += VC_W;
+            __syncthreads();
+            continue;
+          }
+          const double hh = sm->cand_h[first], nn = sm->cand_nw[first];
+          const int kq = pos + first;
+          const int kk = ordered ? kq : (int)cd_perm(pk, (uint32_t)kq);
+          __syncthreads();
+          if (tid == 0) {
+            sbeta[kk] = nn;
+            if (!sin[kk]) {
+              sin[kk] = 1;
+              sact[sm->nact] = kk;
+              sm->nact += 1;
+            }
+          }
+          {
+            const int j = kk / dg, l = kk - j * dg;
+            const double *col = a.X + (long long)j * a.ldx;
+            for (int i = tid; i < n; i += VC_T) sr[i] = __dsub_rn(sr[i], __dmul_rn(__ldg(col + i) * ipow(sdz[i], l), hh));
+          }
+          maxH = fmax(maxH, fabs(hh));
+          st.accepted += 1;
+          pos = kq + 1;
+          __syncthreads();
+        }
+        // refresh list values
+        for (int i = tid; i < sm->nact; i += VC_T) sval[i] = sbeta[sact[i]];
+        __syncthreads();
+      } else { // ---- active-set pass: sequential chain, block-wide dot per step
+        const int m = sm->nact;
+        st.visits += m;
+        const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter);
+        for (int s = 0; s < m; ++s) {
+          const int i_ = ordered ? s : (int)cd_perm(pkm, (uint32_t)s);
+          const int k = sact[i_];
+          const int j = k / dg, l = k - j * dg;
+          const double *col = a.X + (long long)j * a.ldx;
+          double d = 0.0;
+          for (int i = tid; i < n; i += VC_T) d = fma(sr[i] * (__ldg(col + i) * ipow(sdz[i], l)), sw[i], d);
+          d = vblock_sum(sm, d);
+          const double ak = sa[k], old = sval[i_];
+          const double v = __dadd_rn(old, d / ak);
+          const double thr = __dmul_rn(__dmul_rn((double)n / ak, a.lambda0), sqrt(ak / (double)n));
+          const double nw = cd_shrink(v, thr);
+          const double h = nw - old;
+          __syncthreads();
+          if (tid == 0) {
+            sval[i_] = nw;
+            sbeta[k] = nw;
+          }
+          if (h != 0.0) {
+            for (int i = tid; i < n; i += VC_T) sr[i] = __dsub_rn(sr[i], __dmul_rn(__ldg(col + i) * ipow(sdz[i], l), h));
+            st.accepted += 1;
+          }
+          maxH = fmax(maxH, fabs(h));
+          __syncthreads();
+        }
+      }
+      pass_counter += 1;
+      // ---- dropzeros!
+      if (tid == 0) {
+        int nn = sm->nact, i = 0;
+        while (i < nn) {
+          if (sval[i] == 0.0) {
+            sin[sact[i]] = 0;
+            if (i != nn - 1) {
+              sval[i] = sval[nn - 1];
+              sact[i] = sact[nn - 1];
+            }
+            nn -= 1;
+          } else {
+            i += 1;
+          }
+        }
+        sm->nact = nn;
+      }
+      __syncthreads();
+      st.maxH = maxH;
+      const bool prev = conv;
+      conv = maxH < a.optTol;
+      if (prev && conv) {
+        st.converged = 1;
+        break;
+      }
+    }
+    double *col = a.out + (long long)g * ep;
+    for (int k = tid; k < ep; k += VC_T) col[k] = sbeta[k];
+    if (tid == 0 && a.stats) a.stats[g] = st;
+  }
+}
+
+} // namespace
+
+API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                       const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                       double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
+                       cdgpu_stats *stats) {
+  if (!X || !z || !y || !zgrid || !opt || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (n < 1 || p < 1 || ldx < n || degree < 0 || m < 0 || m_begin < 0 || m_end > m || m_begin > m_end)
+    return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (kernel_kind != CDGPU_KERNEL_GAUSSIAN && kernel_kind != CDGPU_KERNEL_EPANECHNIKOV)
+    return cdgpu_set_error(CDGPU_EARG, "unknown smoothing kernel");
+  if (opt->maxIter < 0 || opt->randomize < 0 || opt->randomize > 1) return cdgpu_set_error(CDGPU_EARG, "bad options");
+  const int64_t ep = p * (degree + 1);
+  if (n > 0x7fffffff || ep > 0x7fffffff || m > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "sizes must fit in 31 bits");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return cdgpu_set_error(CDGPU_ENODEV, "no CUDA device (%s); libcdgpu has no CPU fallback",
+                           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return cdgpu_set_error(CDGPU_EARG, "device out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  const int64_t mloc = m_end - m_begin;
+  if (mloc == 0) return CDGPU_OK;
+  const size_t dyn = (sizeof(VSm) + 15) / 16 * 16 + (size_t)(3 * n + 3 * ep) * sizeof(double) + (size_t)ep * 5 + 16;
+  if (dyn > 227 * 1024)
+    return cdgpu_set_error(CDGPU_ECAP, "local problem does not fit in shared memory (n=%lld, ep=%lld)", (long long)n,
+                           (long long)ep);
+  double *dX = nullptr, *dz = nullptr, *dy = nullptr, *dgz = nullptr, *dout = nullptr;
+  DevStats *dst = nullptr;
+  cudaStream_t s = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = CDGPU_OK;
+  auto cleanup = [&]() {
+    cudaFree(dX);
+    cudaFree(dz);
+    cudaFree(dy);
+    cudaFree(dgz);
+    cudaFree(dout);
+    cudaFree(dst);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (s) cudaStreamDestroy(s);
+  };
+#define VC_TRY(expr)                                                                                        \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) {                                                                                \
+      rc = cdgpu_set_error(_e == cudaErrorMemoryAllocation ? CDGPU_ENOMEM : CDGPU_ECUDA, "%s: %s", #expr,   \
+                           cudaGetErrorString(_e));                                                         \
+      cleanup();                                                                                            \
+      return rc;                                                                                            \
+    }                                                                                                       \
+  } while (0)
+  VC_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  VC_TRY(cudaEventCreate(&e0));
+  VC_TRY(cudaEventCreate(&e1));
+  VC_TRY(cudaMalloc((void **)&dX, (size_t)n * p * sizeof(double)));
+  VC_TRY(cudaMalloc((void **)&dz, (size_t)n * sizeof(double)));
+  VC_TRY(cudaMalloc((void **)&dy, (size_t)n * sizeof(double)));
+  VC_TRY(cudaMalloc((void **)&dgz, (size_t)m * sizeof(double)));
+  VC_TRY(cudaMalloc((void **)&dout, (size_t)ep * m * sizeof(double)));
+  VC_TRY(cudaMalloc((void **)&dst, (size_t)m * sizeof(DevStats)));
+  VC_TRY(cudaMemcpy2DAsync(dX, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), p,
+                           cudaMemcpyHostToDevice, s));
+  VC_TRY(cudaMemcpyAsync(dz, z, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  VC_TRY(cudaMemcpyAsync(dy, y, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  VC_TRY(cudaMemcpyAsync(dgz, zgrid, m * sizeof(double), cudaMemcpyHostToDevice, s));
+  VcArgs a = {};
+  a.X = dX;
+  a.ldx = n;
+  a.n = (int)n;
+  a.p = (int)p;
+  a.degree = degree;
+  a.z = dz;
+  a.y = dy;
+  a.zgrid = dgz;
+  a.g0 = (int)m_begin;
+  a.g1 = (int)m_end;
+  a.kernel_kind = kernel_kind;
+  a.bandwidth = bandwidth;
+  a.lambda0 = lambda0;
+  a.maxIter = opt->maxIter;
+  a.optTol = opt->optTol;
+  a.randomize = opt->randomize;
+  a.seed = opt->seed;
+  a.out = dout;
+  a.stats = dst;
+  VC_TRY(cudaFuncSetAttribute(vc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int occ = 0, sms = 0;
+  VC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vc_kernel, VC_T, dyn));
+  VC_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (occ < 1) occ = 1;
+  const int grid = (int)(mloc < (int64_t)occ * sms ? mloc : (int64_t)occ * sms);
+  VC_TRY(cudaEventRecord(e0, s));
+  vc_kernel<<<grid, VC_T, dyn, s>>>(a);
+  VC_TRY(cudaGetLastError());
+  VC_TRY(cudaEventRecord(e1, s));
+  VC_TRY(cudaMemcpyAsync(out + m_begin * ep, dout + m_begin * ep, (size_t)mloc * ep * sizeof(double),
+                         cudaMemcpyDeviceToHost, s));
+  VC_TRY(cudaStreamSynchronize(s));
+  if (stats) {
+    float ms = 0.f;
+    VC_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    DevStats *hst = new DevStats[(size_t)mloc];
+    cudaError_t e2 = cudaMemcpy(hst, dst + m_begin, (size_t)mloc * sizeof(DevStats), cudaMemcpyDeviceToHost);
+    if (e2 == cudaSuccess)
+      for (int64_t g = 0; g < mloc; ++g) {
+        cdgpu_stats *o = stats + m_begin + g;
+        o->passes = hst[g].passes;
+        o->full_passes = hst[g].full_passes;
+        o->visits = hst[g].visits;
+        o->accepted = hst[g].accepted;
+        o->maxH = hst[g].maxH;
+        o->converged = hst[g].converged;
+        o->outer_iters = 0;
+        o->sigma = 0.0;
+        o->device_ms = g == 0 ? (double)ms : 0.0;
+      }
+    delete[] hst;
+    VC_TRY(e2);
+  }
+#undef VC_TRY
+  cleanup();
+  return CDGPU_OK;
+}

@@ -328,8 +328,35 @@ static inline uint64_t splitmix(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
-static inline uint64_t order_key(uint64_t seed, uint64_t pass, uint64_t i /*0-based position*/) {
-  return splitmix(splitmix(seed ^ (pass * 0xD1B54A32D192ED03ull)) + i);
+/* Mode-1 visit order: a keyed bijection of [0, N) — 4-round Feistel network on
+ * 2*hb bits with cycle walking — evaluated per position, so neither side needs a
+ * sort or a sequential shuffle.  Same definition on the device (csrc/common.cuh). */
+static inline uint32_t mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+static inline uint64_t order_perm(uint64_t N, uint64_t seed, uint64_t pass, uint64_t x) {
+  uint64_t k0 = splitmix(seed ^ (pass * 0xD1B54A32D192ED03ull)), k1 = splitmix(k0);
+  uint32_t key[4] = {(uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32)};
+  int bits = 0;
+  while (((N - 1) >> bits) != 0) bits++;
+  int hb = (bits + 1) / 2;
+  if (hb < 1) hb = 1;
+  uint32_t mask = (uint32_t)((1ull << hb) - 1);
+  do {
+    uint32_t L = (uint32_t)(x >> hb), R = (uint32_t)x & mask;
+    for (int r = 0; r < 4; ++r) {
+      uint32_t t = L ^ (mix32(R + key[r]) & mask);
+      L = R;
+      R = t;
+    }
+    x = ((uint64_t)L << hb) | R;
+  } while (x >= N);
+  return x;
 }
 static uint64_t xo_s[4];
 static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
@@ -351,26 +378,12 @@ static int64_t rand_range(int64_t lo, int64_t hi) { /* rand(lo:hi) */
   do v = xo_next(); while (v >= lim);
   return lo + (int64_t)(v % span);
 }
-typedef struct {
-  const uint64_t *keys;
-} keycmp_ctx;
-static const uint64_t *g_sort_keys;
-static int cmp_by_key(const void *a, const void *b) {
-  int64_t ia = *(const int64_t *)a, ib = *(const int64_t *)b;
-  uint64_t ka = g_sort_keys[ia - 1], kb = g_sort_keys[ib - 1];
-  if (ka != kb) return ka < kb ? -1 : 1;
-  return ia < ib ? -1 : (ia > ib);
-}
 /* reset!(it, fullPass): :34-37 (ordered), :53-64 (random) */
 static void iterator_reset(H *f, const sparse_iterate *x, int fullPass, int randomize, uint64_t seed) {
   int64_t len = fullPass ? f->p : x->nnz;
   if (randomize == 1) {
-    for (int64_t i = 0; i < len; ++i) {
-      f->order[i] = i + 1;
-      f->keys[i] = order_key(seed, f->pass_counter, (uint64_t)i);
-    }
-    g_sort_keys = f->keys;
-    qsort(f->order, (size_t)len, sizeof(int64_t), cmp_by_key);
+    for (int64_t i = 0; i < len; ++i)
+      f->order[i] = (int64_t)order_perm((uint64_t)len, seed, f->pass_counter, (uint64_t)i) + 1;
   } else if (randomize == 2) {
     for (int64_t i = 1; i <= len; ++i) f->order[i - 1] = i;
     for (int64_t i = 1; i <= len - 1; ++i) {
@@ -953,4 +966,4 @@ API int cdref_iterator_collect(int64_t p, const int64_t *nzval2ind, int64_t nnz,
   return CDGPU_OK;
 }
 API double cdref_shrink(double v, double c) { return shrink(v, c); }
-API uint64_t cdref_order_key(uint64_t seed, uint64_t pass, uint64_t i) { return order_key(seed, pass, i); }
+API uint64_t cdref_order_perm(uint64_t N, uint64_t seed, uint64_t pass, uint64_t x) { return order_perm(N, seed, pass, x); }

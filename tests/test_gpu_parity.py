@@ -1,0 +1,243 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerances are north_star's: identical supports, coefficients within 1e-6 relative, objective
+within 1e-8 — at a convergence tolerance tight enough for two correct solvers to agree
+(SURVEY.md §7 hard part 3)."""
+import numpy as np
+import pytest
+
+import cdgpu
+from cdgpu import CDOptions, IterLassoOptions, ProxL1, SparseIterate, GaussianKernel, EpanechnikovKernel
+from helpers import (assert_parity, gauss_problem, lasso_objective, quad_objective, sprand_iterate, sqrt_objective)
+
+pytestmark = pytest.mark.gpu
+TIGHT = dict(maxIter=20000, optTol=1e-12)
+
+
+def test_kat_small_proxl1(gpu):
+    # test/coordinate_descent.jl:13-25
+    f = gpu.CDQuadraticLoss(np.eye(2), -np.array([1.0, 1.5]))
+    x = SparseIterate(2)
+    gpu.coordinateDescent_(x, f, ProxL1(1.2), CDOptions(maxIter=100, optTol=1e-8, warmStart=True, randomize=False))
+    assert np.allclose(x.toarray(), [0.0, 0.3], rtol=1e-12)
+
+
+def test_quad_rejects_nonsymmetric(gpu):
+    A = np.eye(40)
+    A[3, 17] = 1e-9
+    with pytest.raises(cdgpu.ArgumentError):
+        gpu.CDQuadraticLoss(A, np.zeros(40))
+
+
+@pytest.mark.parametrize("n,p,s,lam,weighted", [(200, 50, 10, 0.2, False), (500, 300, 20, 0.05, True),
+                                                (300, 1000, 15, 0.1, True)])
+@pytest.mark.parametrize("randomize", [0, 1])
+def test_cov_form_solve_parity(gpu, ref, n, p, s, lam, weighted, randomize):
+    X, y, _ = gauss_problem(n, p, s, seed=100 + p)
+    A, b = X.T @ X / n, -X.T @ y / n
+    A = (A + A.T) / 2
+    om = 0.5 + np.random.default_rng(p).random(p) if weighted else None
+    o = CDOptions(randomize=randomize, seed=3, **TIGHT)
+    xs = []
+    for be in (gpu, ref):
+        f = be.CDQuadraticLoss(A, b)
+        x = SparseIterate(p)
+        be.coordinateDescent_(x, f, ProxL1(lam, om), o)
+        assert f.last_stats["converged"] == 1
+        xs.append((x.toarray(), f.last_stats, f.Ax))
+    (bg, sg, axg), (br, sr, axr) = xs
+    assert_parity(bg, br, quad_objective(A, b, bg, lam, om), quad_objective(A, b, br, lam, om))
+    assert np.allclose(axg, A @ bg, rtol=1e-9, atol=1e-12)  # f.Ax is the state of the final iterate
+    assert abs(sg["passes"] - sr["passes"]) <= 2 and sg["full_passes"] >= 2
+
+
+def test_cov_form_warm_cold_agree(gpu, ref):
+    # test/coordinate_descent.jl:29-63 on the covariance form; warm start from a random sprand iterate
+    rng = np.random.default_rng(5)
+    n, p, s = 500, 50, 5
+    X, y, _ = gauss_problem(n, p, s, seed=6)
+    A, b = X.T @ X / n, -X.T @ y / n
+    A = (A + A.T) / 2
+    start = sprand_iterate(p, 0.6, rng)
+    sols = []
+    for be in (gpu, ref):
+        f = be.CDQuadraticLoss(A, b)
+        for warm in (True, False):
+            x = SparseIterate(start)
+            be.coordinateDescent_(x, f, ProxL1(0.02), CDOptions(warmStart=warm, randomize=False, numSteps=50, **TIGHT))
+            sols.append(x.toarray())
+    for s_ in sols[1:]:
+        assert_parity(s_, sols[0])
+
+
+def test_cov_path_parity(gpu, ref):
+    n, p, s = 400, 600, 12
+    X, y, _ = gauss_problem(n, p, s, seed=21)
+    A, b = X.T @ X / n, -X.T @ y / n
+    A = (A + A.T) / 2
+    om = np.sqrt((X ** 2).sum(0) / n)
+    lmax = np.max(np.abs(b) / om)
+    lams = np.exp(np.linspace(np.log(lmax), np.log(0.05 * lmax), 30))
+    o = CDOptions(randomize=False, **TIGHT)
+    paths = []
+    for be in (gpu, ref):
+        f = be.CDQuadraticLoss(A, b)
+        assert be.findLambdaMax(f, om) == pytest.approx(lmax, rel=1e-14)
+        paths.append(be.LassoPath(None, None, lams, o, standardizeX=om, loss=f))
+    pg, pr = paths
+    assert len(pg.βpath) == len(pr.βpath) == 30
+    for i in range(30):
+        bg, br = pg.βpath[i].toarray(), pr.βpath[i].toarray()
+        assert_parity(bg, br, quad_objective(A, b, bg, lams[i], om), quad_objective(A, b, br, lams[i], om))
+    assert pg.βpath[0].nnz == 0 and pg.βpath[-1].nnz > s
+    # max_hat_s stops the path early (lasso.jl:253-256)
+    f = gpu.CDQuadraticLoss(A, b)
+    short = gpu.LassoPath(None, None, lams, o, standardizeX=om, loss=f, max_hat_s=3)
+    fr = ref.CDQuadraticLoss(A, b)
+    short_r = ref.LassoPath(None, None, lams, o, standardizeX=om, loss=fr, max_hat_s=3)
+    assert len(short.βpath) == len(short_r.βpath) < 30 and short.βpath[-1].nnz > 3
+
+
+@pytest.mark.parametrize("kind", ["ls", "wls", "sqrt"])
+@pytest.mark.parametrize("randomize", [0, 1])
+def test_naive_solve_parity(gpu, ref, kind, randomize):
+    rng = np.random.default_rng(31)
+    n, p, s = 300, 700, 10
+    X, y, _ = gauss_problem(n, p, s, seed=32)
+    om = 0.5 + rng.random(p)
+    w = rng.random(n) + 0.1
+    lam = {"ls": 0.1, "wls": 0.06, "sqrt": 3.2 / 1.0}[kind]
+    o = CDOptions(randomize=randomize, seed=9, **TIGHT)
+    outs = []
+    for be in (gpu, ref):
+        f = {"ls": lambda: be.CDLeastSquaresLoss(y, X), "wls": lambda: be.CDWeightedLSLoss(y, X, w),
+             "sqrt": lambda: be.CDSqrtLassoLoss(y, X)}[kind]()
+        x = SparseIterate(p)
+        be.coordinateDescent_(x, f, ProxL1(lam, om), o)
+        assert f.last_stats["converged"] == 1
+        outs.append((x.toarray(), f.r, f.last_stats))
+    (bg, rg, sg), (br, rr, sr) = outs
+    assert np.count_nonzero(br) >= 3
+    if kind == "sqrt":
+        og, orf = sqrt_objective(X, y, bg, lam, om), sqrt_objective(X, y, br, lam, om)
+    elif kind == "ls":
+        og, orf = lasso_objective(X, y, bg, lam, om), lasso_objective(X, y, br, lam, om)
+    else:
+        sw = np.sqrt(w)
+        og = lasso_objective(sw[:, None] * X, sw * y, bg, lam, om)
+        orf = lasso_objective(sw[:, None] * X, sw * y, br, lam, om)
+    assert_parity(bg, br, og, orf)
+    assert np.allclose(rg, y - X @ bg, atol=1e-10)  # f.r aliases LassoSolution.residuals (lasso.jl:37)
+
+
+def test_naive_warm_and_cold(gpu, ref):
+    rng = np.random.default_rng(41)
+    n, p, s = 500, 50, 5
+    X, y, _ = gauss_problem(n, p, s, seed=42)
+    start = sprand_iterate(p, 0.6, rng)
+    sols = []
+    for be in (gpu, ref):
+        f = be.CDLeastSquaresLoss(y, X)
+        for warm in (True, False):
+            for rand in (0, 1):
+                x = SparseIterate(start)
+                be.coordinateDescent_(x, f, ProxL1(0.02), CDOptions(warmStart=warm, randomize=rand, seed=1, **TIGHT))
+                sols.append(x.toarray())
+    for s_ in sols[1:]:
+        assert_parity(s_, sols[0])
+
+
+def test_front_ends(gpu, ref):
+    n, p, s = 400, 300, 12
+    X, y, _ = gauss_problem(n, p, s, seed=51)
+    o = CDOptions(randomize=False, **TIGHT)
+    a, b = gpu.lasso(X, y, 0.1, o), ref.lasso(X, y, 0.1, o)
+    assert_parity(a.x.toarray(), b.x.toarray())
+    assert a.σ == pytest.approx(b.σ, rel=1e-9) and np.allclose(a.residuals, b.residuals, atol=1e-9)
+    om = np.sqrt((X ** 2).sum(0) / n)
+    f = gpu.CDLeastSquaresLoss(y, X)
+    assert np.allclose(f.stdX(), om, rtol=1e-13)
+    wts = np.random.default_rng(1).random(n)
+    assert np.allclose(f.stdX(wts), np.sqrt((wts[:, None] * X ** 2).sum(0) / n), rtol=1e-13)
+    a, b = gpu.sqrtLasso(X, y, 3.0, o, standardizeX=False), ref.sqrtLasso(X, y, 3.0, o, standardizeX=False)
+    assert_parity(a.x.toarray(), b.x.toarray())
+    pa = gpu.LassoPath(X, y, [0.3, 0.1, 0.05], o)
+    pb = ref.LassoPath(X, y, [0.3, 0.1, 0.05], o)
+    for i in range(3):
+        assert_parity(pa.βpath[i].toarray(), pb.βpath[i].toarray())
+    # zero solution above lambda_max (test/lasso.jl:23-34)
+    lam = np.max(np.abs(X.T @ y / n)) + 0.1
+    assert gpu.lasso(X, y, lam).x.nnz == 0
+
+
+@pytest.mark.parametrize("init", ["InitStd", "WarmStart"])
+def test_scaled_lasso_parity(gpu, ref, init):
+    n, p, s = 600, 400, 15
+    X, y, _ = gauss_problem(n, p, s, seed=61)
+    lam = 0.12
+    o = IterLassoOptions(maxIter=100, optTol=1e-10, initProcedure=init, σinit=2.0,
+                         optionsCD=CDOptions(randomize=False, **TIGHT))
+    outs = []
+    for be in (gpu, ref):
+        x = SparseIterate(p)
+        sol = be.scaledLasso_(x, X, y, lam, np.ones(p), o)
+        outs.append((x.toarray(), sol))
+    (bg, sg), (br, sr) = outs
+    assert_parity(bg, br)
+    assert sg.σ == pytest.approx(sr.σ, rel=1e-8)
+    assert sg.stats["sigma"] == pytest.approx(sr.stats["sigma"], rel=1e-8)
+    assert sg.stats["outer_iters"] == sr.stats["outer_iters"]
+    kkt = np.max(np.abs(X.T @ (y - X @ bg) / n))
+    assert abs(kkt - lam * sg.stats["sigma"]) / (lam * sg.stats["sigma"]) < 1e-6  # test/lasso.jl:211-212
+
+
+def test_gram_matches_and_is_symmetric(gpu, ref):
+    for n, p in [(257, 130), (1000, 515), (64, 33)]:
+        X, y, _ = gauss_problem(n, p, 5, seed=n)
+        f = gpu.CDQuadraticLoss_from_data(X, y)
+        A, b = f.get()
+        assert np.array_equal(A, A.T)  # issymmetric must hold exactly (cd_differentiable_function.jl:306)
+        assert np.allclose(A, X.T @ X / n, rtol=1e-12, atol=1e-13)
+        assert np.allclose(b, -X.T @ y / n, rtol=1e-12, atol=1e-13)
+        assert f.gram_ms > 0
+    # ... and drives the same solution as the naive form (test/lasso.jl:76-101)
+    X, y, _ = gauss_problem(500, 260, 10, seed=71)
+    o = CDOptions(randomize=False, **TIGHT)
+    f = gpu.CDQuadraticLoss_from_data(X, y)
+    x1 = SparseIterate(260)
+    gpu.coordinateDescent_(x1, f, ProxL1(0.1), o)
+    x2 = ref.lasso(X, y, 0.1, o).x
+    assert_parity(x1.toarray(), x2.toarray())
+
+
+@pytest.mark.parametrize("kernel,degree", [(GaussianKernel(0.2), 1), (GaussianKernel(0.2), 2),
+                                           (EpanechnikovKernel(0.4), 1), (GaussianKernel(0.3), 0)])
+def test_locpolyl1_parity(gpu, ref, kernel, degree):
+    rng = np.random.default_rng(81)
+    n, p = 300, 12
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    c = rng.choice([2, 4, 6, 8], size=p)
+    Y = np.array([np.sin(c * Z[i])[:2] @ X[i, :2] for i in range(n)]) + 0.1 * rng.standard_normal(n)
+    zgrid = np.linspace(0.05, 0.95, 24)
+    o = CDOptions(randomize=False, **TIGHT)
+    og, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, kernel, 0.02, False, o)
+    orf, _ = ref.locpolyl1(X, Z, Y, zgrid, degree, kernel, 0.02, False, o)
+    assert np.count_nonzero(orf) > 24
+    for g in range(24):
+        assert_parity(og[:, g], orf[:, g])
+    assert all(s["converged"] == 1 for s in gpu.last_vc_stats)
+    # sharding hook: two halves == whole
+    a, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, kernel, 0.02, False, o, shard=(0, 12))
+    b, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, kernel, 0.02, False, o, shard=(12, 24))
+    assert np.array_equal(a[:, :12], og[:, :12]) and np.array_equal(b[:, 12:], og[:, 12:])
+
+
+def test_errors_match_reference(gpu):
+    X, y, _ = gauss_problem(20, 5, 2, seed=16)
+    f = gpu.CDLeastSquaresLoss(y, X)
+    with pytest.raises(cdgpu.DimensionMismatch):
+        gpu.coordinateDescent_(SparseIterate(4), f, ProxL1(0.1))
+    with pytest.raises(cdgpu.DimensionMismatch):
+        gpu.coordinateDescent_(SparseIterate(5), f, ProxL1(0.1, np.ones(4)))
+    with pytest.raises(cdgpu.ArgumentError):
+        gpu.scaledLasso_(SparseIterate(5), X, y, 0.1, np.ones(5), IterLassoOptions(initProcedure="Nope"))
