@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 coordinate-descent path (BASELINE.json configs[1], "C2").
+
+One STEP = one pass of the hot path over one synthetic problem:
+    (X, y)  ->  covariance form  A = X'X/n, b = -X'y/n  (FP64 tensor-core SYRK)
+            ->  omega = _stdX!(X), lambda_max, 100 log-spaced lambdas down to 0.05*lambda_max
+            ->  warm-started weighted-L1 lasso path by active-set coordinate descent (cluster kernel)
+metric  = coordinate updates / s  = descendCoordinate! visits of the whole path / step time
+value   = inputs (X, y) already resident in HBM, device pointers through the C ABI
+e2e     = the same step through the C ABI with HOST buffers (pinned): H2D of X,y and D2H of the
+          CSC path inside the timed region
+N > 1   = one process per GPU, every rank solves its own replica (another seed: a CV fold /
+          bootstrap replicate); a warm-started path is a sequential chain, so there is no
+          data-path collective ("replicas only"); value = sum of visits / max time.
+--impl reference = the reference's CPU implementation of the same step on the host cores: Gram by
+          OpenBLAS (what Julia's X'X/n calls) with all threads + the C port of the reference's
+          single-threaded CD loop (oracle/libcdref_fast.so), on a bounded sample (fewer columns).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "coordinatedescent.jl_b200"))
+
+C2 = dict(n=10000, p=20000, s=50, nlambda=100, ratio=0.05, optTol=1e-7, maxIter=2000)
+REF_SAMPLE_P = 4000  # columns of the reference arm's bounded sample
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=C2["n"])
+    ap.add_argument("--p", type=int, default=C2["p"])
+    ap.add_argument("--nlambda", type=int, default=C2["nlambda"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-p", type=int, default=REF_SAMPLE_P)
+    return ap.parse_args()
+
+
+def make_problem(n, p, s, seed):
+    """X ~ N(0,1) (n x p, column-major), y = X[:, :s] beta + N(0,1).  numpy PCG64, fixed seed."""
+    rng = np.random.default_rng(seed)
+    Xt = rng.standard_normal((p, n))  # C-order (p, n) == F-order (n, p)
+    X = Xt.T
+    beta = rng.standard_normal(s) * (1.0 + rng.random(s))  # benchmark/cd_bench.jl:14
+    y = X[:, :s] @ beta + rng.standard_normal(n)
+    return X, np.ascontiguousarray(y)
+
+
+def lambda_grid(lmax, ratio, m):
+    return np.exp(np.linspace(np.log(lmax), np.log(ratio * lmax), m))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_step(lib, be, make_handle, cfg, opts):
+    """One step against an already chosen input location; returns (visits, accepted, gram_ms, cd_ms, nnz_last, bytes_out)."""
+    import cdgpu
+    f = make_handle()
+    om = f.stdX()
+    lmax = be.findLambdaMax(f, om)
+    lams = lambda_grid(lmax, cfg["ratio"], cfg["nlambda"])
+    path = be.LassoPath(None, None, lams, opts, standardizeX=om, loss=f)
+    gram_ms = f.gram_ms
+    f.close()
+    visits = sum(s["visits"] for s in path.stats)
+    accepted = sum(s["accepted"] for s in path.stats)
+    cd_ms = path.stats[0]["device_ms"]
+    nnz_tot = sum(x.nnz for x in path.βpath)
+    return dict(visits=visits, accepted=accepted, gram_ms=gram_ms, cd_ms=cd_ms, nnz_last=path.βpath[-1].nnz,
+                passes=sum(s["passes"] for s in path.stats), full_passes=sum(s["full_passes"] for s in path.stats),
+                converged=all(s["converged"] for s in path.stats), d2h=16 * nnz_tot + 8 * (len(lams) + 1) + 8 * f.p + 8)
+
+
+def reference_arm(args, cfg):
+    """CPU: OpenBLAS Gram (all threads) + C port of the reference CD loop (1 thread) on a bounded sample."""
+    import cdgpu
+    from cdgpu import CDOptions
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    ref = cdgpu.Backend(cdgpu.Lib(os.path.join(ROOT, "oracle", "libcdref_fast.so"), "cdref"))
+    ps = min(args.cpu_sample_p, cfg["p"])
+    X, y = make_problem(cfg["n"], ps, cfg["s"], seed=123)
+    n = cfg["n"]
+    opts = CDOptions(maxIter=cfg["maxIter"], optTol=cfg["optTol"], randomize=False, warmStart=True)
+    cores = os.cpu_count()
+
+    def step():
+        t0 = time.perf_counter()
+        A = X.T @ X
+        A /= n
+        A = np.asfortranarray((A + A.T) * 0.5) if not np.array_equal(A, A.T) else np.asfortranarray(A)
+        b = -(X.T @ y) / n
+        t1 = time.perf_counter()
+        f = ref.CDQuadraticLoss(A, b)
+        om = f.stdX()
+        lmax = ref.findLambdaMax(f, om)
+        lams = lambda_grid(lmax, cfg["ratio"], cfg["nlambda"])
+        path = ref.LassoPath(None, None, lams, opts, standardizeX=om, loss=f)
+        f.close()
+        t2 = time.perf_counter()
+        return sum(s["visits"] for s in path.stats), t1 - t0, t2 - t1
+
+    return step, cores, ps
+
+
+def main():
+    args = parse()
+    cfg = dict(C2, n=args.n, p=args.p, nlambda=args.nlambda)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"C2: weighted-L1 lasso lambda-path, covariance form, n={cfg['n']} p={cfg['p']}, "
+                f"{cfg['nlambda']} lambdas (lambda_max -> {cfg['ratio']} lambda_max) warm-started, Gram formed in the step")
+    base = {"metric": "coordinate_updates_per_sec", "unit": "visits/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        step, cores, ps = reference_arm(args, cfg)
+        for _ in range(min(args.warmup, 1)):
+            step()
+        tot_v, tg, tc = 0, 0.0, 0.0
+        for _ in range(args.steps):
+            v, a, b = step()
+            tot_v += v
+            tg += a
+            tc += b
+        secs = tg + tc
+        val = tot_v / secs
+        sample = (f"same generator (seed 123), first {ps} of {cfg['p']} columns, n={cfg['n']}, {cfg['nlambda']} lambdas; "
+                  f"Gram by numpy/OpenBLAS on {cores} threads ({tg / args.steps:.2f} s/step) + C port of the reference's "
+                  f"single-threaded CD loop incl. its unconditional O(p) axpy per visit ({tc / args.steps:.2f} s/step). "
+                  f"The reference moves 8p bytes per visit, so its rate at the full p={cfg['p']} is ~{cfg['p'] // ps}x lower.")
+        out = dict(base, impl="reference", value=val, ms_per_step=1e3 * secs / args.steps,
+                   config={"workload": workload, "sample_p": ps, "optTol": cfg["optTol"], "randomize": False},
+                   cpu_baseline={"value": val, "unit": "visits/s", "cores": cores, "kind": "port", "sample": sample},
+                   e2e={"value": val, "unit": "visits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(out))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+
+    import cdgpu
+    from cdgpu import CDOptions
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; libcdgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    be = cdgpu.Backend(cdgpu.load_product(), device=local)
+    lib = be.lib
+    opts = CDOptions(maxIter=cfg["maxIter"], optTol=cfg["optTol"], randomize=False, warmStart=True)
+    n, p = cfg["n"], cfg["p"]
+    X, y = make_problem(n, p, cfg["s"], seed=123 + rank)
+    # pinned host copies for the e2e leg, resident device copies for the value leg
+    Xp = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory()  # (p, n) C-order == (n, p) F-order
+    yp = torch.from_numpy(y).pin_memory()
+    Xd, yd = Xp.cuda(non_blocking=False), yp.cuda(non_blocking=False)
+    torch.cuda.synchronize()
+
+    def handle_dev():
+        f = cdgpu.CDQuadraticLoss.__new__(cdgpu.CDQuadraticLoss)
+        cdgpu.api._Loss.__init__(f, lib)
+        f.p = p
+        lib.check(lib.gram_create_dev(C.byref(f._h), C.c_void_p(Xd.data_ptr()), n, p, n, C.c_void_p(yd.data_ptr()), local))
+        return f
+
+    def handle_host():
+        f = cdgpu.CDQuadraticLoss.__new__(cdgpu.CDQuadraticLoss)
+        cdgpu.api._Loss.__init__(f, lib)
+        f.p = p
+        lib.check(lib.gram_create(C.byref(f._h), C.c_void_p(Xp.data_ptr()), n, p, n, C.c_void_p(yp.data_ptr()), local))
+        return f
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def launches():
+        c = C.c_int64()
+        lib.launch_count(C.byref(c))
+        return c.value
+
+    def timed(make_handle, steps, warmup):
+        for _ in range(warmup):
+            run_step(lib, be, make_handle, cfg, opts)
+        barrier()
+        l0 = launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        res = [run_step(lib, be, make_handle, cfg, opts) for _ in range(steps)]
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        dev = e0.elapsed_time(e1) * 1e-3
+        secs = max(wall, dev)
+        if world > 1:
+            t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        return res, secs, launches() - l0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    res, secs, nlaunch = timed(handle_dev, args.steps, args.warmup)
+    clocks = sampler.stop()
+    res_e, secs_e, _ = timed(handle_host, max(1, min(args.steps, 3)), 1)
+
+    visits = sum(r["visits"] for r in res)
+    visits_e = sum(r["visits"] for r in res_e)
+    if world > 1:
+        t = torch.tensor([visits, visits_e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        visits, visits_e = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    r0 = res[-1]
+    gram_ms = float(np.mean([r["gram_ms"] for r in res]))
+    cd_ms = float(np.mean([r["cd_ms"] for r in res]))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    # FP64 tensor ceiling: MEASURED_PEAKS.json has no FP64 entry -> cuBLAS Dgemm measured here, outside the timed region
+    a64 = torch.randn(8192, 8192, device="cuda", dtype=torch.float64)
+    b64 = torch.randn(8192, 8192, device="cuda", dtype=torch.float64)
+    best = 1e9
+    for i in range(6):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        torch.mm(a64, b64)
+        s1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = min(best, s0.elapsed_time(s1))
+    dgemm_tf = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    del a64, b64
+    gram_flops = n * p * (p + 1) + 2 * n * p  # SYRK (lower triangle) + X'y, algorithmic
+    gram_tf = gram_flops / (gram_ms * 1e-3) / 1e12
+    sweep_bytes = 24 * r0["visits"] + 8 * p * r0["accepted"]  # 24 B/visit + 8p B/accepted step
+    out = dict(base, value=visits / secs, ms_per_step=1e3 * secs / args.steps,
+               config={"workload": workload, "optTol": cfg["optTol"], "randomize": False, "replicas": world,
+                       "l2": "inputs exceed L2: X %.1f GB, G %.1f GB per replica" % (8 * n * p / 1e9, 8 * p * p / 1e9)},
+               clocks=clocks,
+               e2e={"value": visits_e / secs_e, "unit": "visits/s", "ms_per_step": 1e3 * secs_e / len(res_e),
+                    "h2d_bytes_per_step": 8 * n * p + 8 * n + 8 * p * 2 + 8 * cfg["nlambda"],
+                    "d2h_bytes_per_step": int(res_e[-1]["d2h"])},
+               gpu_launches=int(nlaunch),
+               roofline={"kernel": "gram_syrk_kernel (FP64 DMMA SYRK)", "bound": "tensor", "achieved": gram_tf,
+                         "peak": dgemm_tf, "unit": "TFLOP/s", "frac": gram_tf / dgemm_tf, "traffic": None,
+                         "flops_per_launch": gram_flops, "launch_ms": gram_ms,
+                         "peak_source": "cuBLAS Dgemm 8192^3 FP64 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},
+               roofline_sweep={"kernel": "cov_path_kernel (cluster CD sweep, whole path)", "bound": "hbm",
+                               "achieved": sweep_bytes / (cd_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                               "frac": sweep_bytes / (cd_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                               "bytes_per_launch": sweep_bytes, "launch_ms": cd_ms, "peak_source": hbm_src,
+                               "note": "latency-bound sequential chain: one cluster, 24 B/visit + 8p B/accepted step"},
+               breakdown={"gram_ms": gram_ms, "cd_path_ms": cd_ms, "visits_per_step": r0["visits"],
+                          "accepted_per_step": r0["accepted"], "passes": r0["passes"], "full_passes": r0["full_passes"],
+                          "nnz_at_last_lambda": r0["nnz_last"], "all_converged": bool(r0["converged"]),
+                          "cd_only_visits_per_sec": r0["visits"] / (cd_ms * 1e-3)})
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        step, cores, ps = reference_arm(args, cfg)
+        v, tg, tc = step()
+        out["cpu_baseline"] = {"value": v / (tg + tc), "unit": "visits/s", "cores": cores, "kind": "port",
+                               "sample": f"same generator, first {ps} of {p} columns, n={n}, {cfg['nlambda']} lambdas; "
+                                         f"Gram numpy/OpenBLAS {cores} threads {tg:.2f} s + C port of the reference CD loop "
+                                         f"(1 thread, literal always-axpy) {tc:.2f} s"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,7 @@ _SIGS = {
 
 # only libcdgpu.so has these (the oracle is single-process, single-device)
 _SIGS_GPU_ONLY = {
+    "launch_count": (C.c_int, [c_int64_p]),
     "comm_unique_id": (C.c_int, [C.c_void_p]),
     "comm_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "comm_destroy": (C.c_int, [C.c_void_p]),

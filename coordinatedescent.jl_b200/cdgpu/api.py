@@ -278,6 +278,12 @@ class CDQuadraticLoss(_Loss):
         lib.check(lib.gram_create(C.byref(self._h), ptr(X), X.shape[0], self.p, X.shape[0], ptr(y), device))
         return self
 
+    def stdX(self) -> np.ndarray:
+        """sqrt(diag(A)) == _stdX!(X) when A = X'X/n (utils.jl:127-138)."""
+        out = np.empty(self.p)
+        self.lib.check(self.lib.stdx(self._h, None, ptr(out)))
+        return out
+
     @property
     def Ax(self) -> np.ndarray:
         return self._state(self.p)

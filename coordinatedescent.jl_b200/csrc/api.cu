@@ -22,6 +22,12 @@ int cdgpu_set_error(int code, const char *fmt, ...) {
   return code;
 }
 
+long long g_cdgpu_launches = 0;
+API int cdgpu_launch_count(int64_t *count) {
+  if (!count) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  *count = g_cdgpu_launches;
+  return CDGPU_OK;
+}
 API int cdgpu_version(void) { return CDGPU_VERSION; }
 API const char *cdgpu_last_error(void) { return g_err; }
 API int cdgpu_device_count(int *count) {
@@ -786,8 +792,15 @@ API int cdgpu_state(cdgpu_handle h, double *out) {
 
 API int cdgpu_stdx(cdgpu_handle h, const double *w, double *out) {
   if (!h || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
-  if (h->kind == CDGPU_LOSS_QUAD) return cdgpu_set_error(CDGPU_EARG, "_stdX! needs a naive-form handle");
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->kind == CDGPU_LOSS_QUAD) { // A = X'X/n  =>  _stdX!(X)_j = sqrt(A_jj)
+    if (w) return cdgpu_set_error(CDGPU_EARG, "weighted _stdX! needs a naive-form handle");
+    double *dout = h->dscr + 8;
+    CD_TRY(launch_diag_sqrt(h, h->dX, h->ld, (int)h->p, dout));
+    CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CDGPU_OK;
+  }
   double *dw = nullptr;
   if (w) {
     dw = h->dscr + 8;

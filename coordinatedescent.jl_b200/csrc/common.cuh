@@ -118,6 +118,10 @@ struct DevStats {
   double sigma;
 };
 
+// number of kernels this library has launched (diagnostic; bench.py's gpu_launches)
+extern long long g_cdgpu_launches;
+#define CD_COUNT_LAUNCH(k) (g_cdgpu_launches += (k))
+
 // ---------------------------------------------------------------- handle --
 struct cdgpu_handle_s {
   int kind = -1, device = 0;
@@ -183,6 +187,7 @@ int launch_cov_init(cdgpu_handle_s *h, const double *A, long long lda, int p, co
 int launch_lambda_max_quad(cdgpu_handle_s *h, const double *b, const double *omega, int p, double *out);
 int launch_extract_ainv(cdgpu_handle_s *h, const double *A, long long lda, int p, double *ainv);
 int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, int p, int *flag);
+int launch_diag_sqrt(cdgpu_handle_s *h, const double *A, long long lda, int p, double *out);
 
 // Gram (gram_dmma.cu): G = X'X / n_total (lower tiles computed, mirrored), c = -X'y / n_total
 int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,

@@ -607,6 +607,10 @@ __global__ void scatter_iterate_kernel(const int *act, const double *actval, con
     inlist[act[i]] = 1;
   }
 }
+__global__ void diag_sqrt_kernel(const double *A, long long lda, int p, double *out) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x)
+    out[j] = sqrt(A[j + (long long)j * lda]);
+}
 __global__ void ainv_kernel(const double *A, long long lda, int p, double *ainv) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x)
     ainv[j] = 1.0 / A[j + (long long)j * lda];
@@ -656,16 +660,25 @@ int launch_cov_init(cdgpu_handle_s *h, const double *A, long long lda, int p, co
   cov_init_kernel<<<blocks, 256, 0, h->stream>>>(A, lda, p, act, actval, nact, Ax, beta, inlist);
   scatter_iterate_kernel<<<32, 256, 0, h->stream>>>(act, actval, nact, beta, inlist);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(2);
+  return CDGPU_OK;
+}
+int launch_diag_sqrt(cdgpu_handle_s *h, const double *A, long long lda, int p, double *out) {
+  diag_sqrt_kernel<<<(p + 255) / 256, 256, 0, h->stream>>>(A, lda, p, out);
+  CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
 int launch_extract_ainv(cdgpu_handle_s *h, const double *A, long long lda, int p, double *ainv) {
   ainv_kernel<<<(p + 255) / 256, 256, 0, h->stream>>>(A, lda, p, ainv);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
 int launch_lambda_max_quad(cdgpu_handle_s *h, const double *b, const double *omega, int p, double *out) {
   lambda_max_quad_kernel<<<1, 1024, 0, h->stream>>>(b, omega, p, out);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
 int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, int p, int *flag) {
@@ -673,6 +686,7 @@ int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, in
   dim3 grid(nb, nb), block(32, 8);
   symmetric_kernel<<<grid, block, 0, h->stream>>>(A, lda, p, flag);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
 
@@ -734,5 +748,6 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel, a, L, slice_in_smem));
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }

@@ -227,6 +227,7 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
   CUDA_TRY(cudaGetLastError());
   xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, c, divisor, scale ? 1 : 0);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(2);
   CUDA_TRY(cudaFreeAsync(dtiles, h->stream));
   return CDGPU_OK;
 }
@@ -237,5 +238,6 @@ int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_t
   const long long count = ldg * p + p;
   scale_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(G, count, n_total);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }

@@ -578,6 +578,7 @@ int launch_colsq(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p
   int blocks = min((p + 7) / 8, h->sm_count * 8);
   colsq_kernel<<<max(blocks, 1), 256, 0, h->stream>>>(X, ldx, n, p, w, out, sqrt_over_n ? 1 : 0);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
 
@@ -587,6 +588,7 @@ int launch_lambda_max_naive(cdgpu_handle_s *h, int kind, const double *X, long l
   grad0_kernel<<<max(blocks, 1), 256, 0, h->stream>>>(kind, X, ldx, n, p, y, w, omega, scr);
   max_kernel<<<1, 1024, 0, h->stream>>>(scr, p, out);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(2);
   return CDGPU_OK;
 }
 
@@ -595,6 +597,7 @@ int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a) {
   dense_iterate_kernel<<<(a.p + 255) / 256, 256, 0, h->stream>>>(a.p, a.act, a.actval, a.nact, a.beta, a.inlist, 0);
   dense_iterate_kernel<<<32, 256, 0, h->stream>>>(a.p, a.act, a.actval, a.nact, a.beta, a.inlist, 1);
   CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(3);
   return CDGPU_OK;
 }
 
@@ -635,5 +638,6 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
   int ch = (int)CH;
   void *args[] = {(void *)&a, (void *)&ch, (void *)&hbuf, (void *)&bc};
   CUDA_TRY(cudaLaunchCooperativeKernel((void *)naive_path_kernel, dim3(G), dim3(NV_T), args, dyn, h->stream));
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }

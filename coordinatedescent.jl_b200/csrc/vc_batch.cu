@@ -344,6 +344,7 @@ API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
   const int grid = (int)(mloc < (int64_t)occ * sms ? mloc : (int64_t)occ * sms);
   VC_TRY(cudaEventRecord(e0, s));
   vc_kernel<<<grid, VC_T, dyn, s>>>(a);
+  CD_COUNT_LAUNCH(1);
   VC_TRY(cudaGetLastError());
   VC_TRY(cudaEventRecord(e1, s));
   VC_TRY(cudaMemcpyAsync(out + m_begin * ep, dout + m_begin * ep, (size_t)mloc * ep * sizeof(double),

@@ -110,6 +110,7 @@ enum { CDGPU_KERNEL_GAUSSIAN = 0, CDGPU_KERNEL_EPANECHNIKOV = 1 };
 int cdgpu_version(void);
 const char *cdgpu_last_error(void);
 int cdgpu_device_count(int *count);
+int cdgpu_launch_count(int64_t *count); /* kernels launched by this library so far (diagnostic) */
 void cdgpu_default_options(cdgpu_options *o);           /* CDOptions()          utils.jl:14-20 */
 void cdgpu_default_iter_options(cdgpu_iter_options *o); /* IterLassoOptions()   utils.jl:32-39 */
 
@@ -185,7 +186,8 @@ int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, const
  * LassoSolution.residuals aliases f.r (lasso.jl:37). */
 int cdgpu_state(cdgpu_handle h, double *out);
 /* _stdX!(out, X) / _stdX!(out, w, X) (utils.jl:127-151) on a naive handle; w NULL
- * uses the unweighted form even on a WLS handle. */
+ * uses the unweighted form even on a WLS handle.  On a QUAD handle (w must be
+ * NULL) it returns sqrt(A_jj), which is _stdX!(X) when A = X'X/n. */
 int cdgpu_stdx(cdgpu_handle h, const double *w, double *out);
 /* _findLambdaMax at x = 0 (coordinate_descent.jl:118-149) */
 int cdgpu_lambda_max(cdgpu_handle h, const double *omega, double *out);

@@ -830,7 +830,11 @@ API int cdref_state(cdgpu_handle f, double *out) {
 }
 API int cdref_stdx(cdgpu_handle f, const double *w, double *out) {
   if (!f || !out) return fail(CDGPU_EARG, "null pointer");
-  if (f->kind == CDGPU_LOSS_QUAD) return fail(CDGPU_EARG, "stdx needs a naive handle");
+  if (f->kind == CDGPU_LOSS_QUAD) { /* A = X'X/n  =>  _stdX!(X)_j = sqrt(A_jj) */
+    if (w) return fail(CDGPU_EARG, "weighted stdx needs a naive handle");
+    for (int64_t j = 0; j < f->p; ++j) out[j] = sqrt(f->X[j + j * f->ld]);
+    return CDGPU_OK;
+  }
   stdx(f->X, f->n, f->p, f->ld, w, out);
   return CDGPU_OK;
 }

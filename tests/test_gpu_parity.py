@@ -47,7 +47,32 @@ def test_cov_form_solve_parity(gpu, ref, n, p, s, lam, weighted, randomize):
     (bg, sg, axg), (br, sr, axr) = xs
     assert_parity(bg, br, quad_objective(A, b, bg, lam, om), quad_objective(A, b, br, lam, om))
     assert np.allclose(axg, A @ bg, rtol=1e-9, atol=1e-12)  # f.Ax is the state of the final iterate
-    assert abs(sg["passes"] - sr["passes"]) <= 2 and sg["full_passes"] >= 2
+    assert sg["full_passes"] >= 2
+
+
+@pytest.mark.parametrize("form", ["quad", "ls", "sqrt"])
+@pytest.mark.parametrize("randomize", [0, 1])
+def test_visit_sequence_matches_oracle(gpu, ref, form, randomize):
+    """At a tolerance far above rounding noise the device must retrace the oracle's Gauss-Seidel
+    sequence: same number of passes, visits and accepted steps (ordered AND keyed-random order)."""
+    n, p, s = 400, 500, 10
+    X, y, _ = gauss_problem(n, p, s, seed=77)
+    A, b = X.T @ X / n, -X.T @ y / n
+    A = (A + A.T) / 2
+    o = CDOptions(randomize=randomize, seed=5, maxIter=5000, optTol=1e-6)
+    lam = 3.0 if form == "sqrt" else 0.08
+    st = []
+    for be in (gpu, ref):
+        f = {"quad": lambda: be.CDQuadraticLoss(A, b), "ls": lambda: be.CDLeastSquaresLoss(y, X),
+             "sqrt": lambda: be.CDSqrtLassoLoss(y, X)}[form]()
+        x = SparseIterate(p)
+        be.coordinateDescent_(x, f, ProxL1(lam), o)
+        st.append((f.last_stats, x))
+    (sg, xg), (sr, xr) = st
+    for key in ("passes", "full_passes", "visits", "accepted", "converged"):
+        assert sg[key] == sr[key], (key, sg, sr)
+    assert list(xg.nzval2ind[: xg.nnz]) == list(xr.nzval2ind[: xr.nnz])  # same SparseIterate order
+    assert np.allclose(xg.toarray(), xr.toarray(), rtol=1e-9, atol=1e-12)
 
 
 def test_cov_form_warm_cold_agree(gpu, ref):
