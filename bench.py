@@ -107,14 +107,22 @@ class ClockSampler:
 
 def run_step(lib, be, make_handle, cfg, opts):
     """One step against an already chosen input location; returns (visits, accepted, gram_ms, cd_ms, nnz_last, bytes_out)."""
-    import cdgpu
+    t0 = time.perf_counter()
     f = make_handle()
+    t1 = time.perf_counter()
     om = f.stdX()
     lmax = be.findLambdaMax(f, om)
     lams = lambda_grid(lmax, cfg["ratio"], cfg["nlambda"])
+    t2 = time.perf_counter()
     path = be.LassoPath(None, None, lams, opts, standardizeX=om, loss=f)
+    t3 = time.perf_counter()
     gram_ms = f.gram_ms
     f.close()
+    t4 = time.perf_counter()
+    if os.environ.get("CDGPU_BENCH_VERBOSE"):
+        print("step: create %.1f ms (gram kernel %.1f) stdx+lmax %.1f path %.1f (device %.1f) close %.1f" % (
+            1e3 * (t1 - t0), gram_ms, 1e3 * (t2 - t1), 1e3 * (t3 - t2), path.stats[0]["device_ms"], 1e3 * (t4 - t3)),
+            file=sys.stderr)
     visits = sum(s["visits"] for s in path.stats)
     accepted = sum(s["accepted"] for s in path.stats)
     cd_ms = path.stats[0]["device_ms"]

@@ -60,6 +60,7 @@ API void cdgpu_default_iter_options(cdgpu_iter_options *o) { // IterLassoOptions
 }
 
 // --------------------------------------------------------------- handles --
+static int pool_init(int device);
 static int use_device(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -68,15 +69,33 @@ static int use_device(int device) {
                            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   if (device < 0 || device >= n) return cdgpu_set_error(CDGPU_EARG, "device %d out of range [0,%d)", device, n);
   CUDA_TRY(cudaSetDevice(device));
+  CD_TRY(pool_init(device));
   return CDGPU_OK;
 }
 
+// Device memory comes from the device's default stream-ordered pool with the release threshold
+// lifted, so the multi-GB Gram / staging buffers of consecutive solves are recycled instead of
+// being mapped and unmapped by cudaMalloc/cudaFree on every call (tens of ms each at C2 size).
+static int pool_init(int device) {
+  static bool done[64] = {false};
+  if (device < 64 && done[device]) return CDGPU_OK;
+  cudaMemPool_t pool;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  if (device < 64) done[device] = true;
+  return CDGPU_OK;
+}
 template <class T>
 static int dalloc(T **p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  CUDA_TRY(cudaMalloc((void **)p, count * sizeof(T)));
+  CUDA_TRY(cudaMallocAsync((void **)p, count * sizeof(T), (cudaStream_t)0));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0)); // usable from any stream from here on
   return CDGPU_OK;
+}
+static void dfree(void *p) {
+  if (p) cudaFreeAsync(p, (cudaStream_t)0);
 }
 
 static int handle_common_alloc(cdgpu_handle_s *h) {
@@ -90,8 +109,9 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   CD_TRY(dalloc(&h->dnact, 1));
   CD_TRY(dalloc(&h->dinlist, p));
   CD_TRY(dalloc(&h->domega, p));
-  CD_TRY(dalloc(&h->dscr, 8 * p + 8 * (size_t)h->n + 64));
-  CD_TRY(dalloc(&h->discr, 4 * p + 64));
+  CD_TRY(dalloc(&h->dscr, 12 * p + 8 * (size_t)h->n + 64));
+  CD_TRY(dalloc(&h->discr, 8 * p + 64));
+  CD_TRY(dalloc(&h->dbscr, 2 * p + 64));
   CD_TRY(dalloc(&h->dflag, 8));
   CUDA_TRY(cudaMemsetAsync(h->dbeta, 0, p * sizeof(double), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dinlist, 0, p, h->stream));
@@ -107,25 +127,26 @@ API int cdgpu_destroy(cdgpu_handle h) {
   if (!h) return CDGPU_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->ownX) cudaFree(h->dX);
-  if (h->owny) cudaFree(h->dy);
-  if (h->ownw) cudaFree(h->dw);
-  cudaFree(h->dstate);
-  cudaFree(h->daux);
-  cudaFree(h->dbeta);
-  cudaFree(h->dact);
-  cudaFree(h->dactval);
-  cudaFree(h->dnact);
-  cudaFree(h->dinlist);
-  cudaFree(h->domega);
-  cudaFree(h->dscr);
-  cudaFree(h->discr);
-  cudaFree(h->dstats);
-  cudaFree(h->dlam);
-  cudaFree(h->dcolptr);
-  cudaFree(h->drowval);
-  cudaFree(h->dnzval);
-  cudaFree(h->dflag);
+  if (h->ownX) dfree(h->dX);
+  if (h->owny) dfree(h->dy);
+  if (h->ownw) dfree(h->dw);
+  dfree(h->dstate);
+  dfree(h->daux);
+  dfree(h->dbeta);
+  dfree(h->dact);
+  dfree(h->dactval);
+  dfree(h->dnact);
+  dfree(h->dinlist);
+  dfree(h->domega);
+  dfree(h->dscr);
+  dfree(h->discr);
+  dfree(h->dbscr);
+  dfree(h->dstats);
+  dfree(h->dlam);
+  dfree(h->dcolptr);
+  dfree(h->drowval);
+  dfree(h->dnzval);
+  dfree(h->dflag);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -359,17 +380,21 @@ API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t
   CD_TRY(dalloc(&dX, (size_t)ld * (size_t)p));
   int rc = dalloc(&dy, (size_t)n);
   if (rc) {
-    cudaFree(dX);
+    dfree(dX);
     return rc;
   }
   auto cleanup = [&]() {
-    cudaFree(dX);
-    cudaFree(dy);
+    dfree(dX);
+    dfree(dy);
   };
   cudaError_t e = cudaSuccess;
   if (ld != n) e = cudaMemset(dX, 0, (size_t)ld * p * sizeof(double));
-  if (e == cudaSuccess)
-    e = cudaMemcpy2D(dX, ld * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), p, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    if (ld == n && ldx == n)
+      e = cudaMemcpy(dX, X, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice);
+    else
+      e = cudaMemcpy2D(dX, ld * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), p, cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaMemcpy(dy, y, n * sizeof(double), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cleanup();
@@ -413,8 +438,8 @@ static int check_opts(const cdgpu_options *o) {
 
 static int grow(cdgpu_handle_s *h, size_t nlam, size_t outcap, size_t outcols) {
   if ((int64_t)nlam > h->nlam) {
-    cudaFree(h->dlam);
-    cudaFree(h->dstats);
+    dfree(h->dlam);
+    dfree(h->dstats);
     h->dlam = nullptr;
     h->dstats = nullptr;
     h->nlam = 0;
@@ -423,8 +448,8 @@ static int grow(cdgpu_handle_s *h, size_t nlam, size_t outcap, size_t outcols) {
     h->nlam = (int64_t)nlam;
   }
   if ((int64_t)outcap > h->outcap) {
-    cudaFree(h->drowval);
-    cudaFree(h->dnzval);
+    dfree(h->drowval);
+    dfree(h->dnzval);
     h->drowval = nullptr;
     h->dnzval = nullptr;
     h->outcap = 0;
@@ -433,7 +458,7 @@ static int grow(cdgpu_handle_s *h, size_t nlam, size_t outcap, size_t outcols) {
     h->outcap = (int64_t)outcap;
   }
   if ((int64_t)outcols > h->outcols) {
-    cudaFree(h->dcolptr);
+    dfree(h->dcolptr);
     h->dcolptr = nullptr;
     h->outcols = 0;
     CD_TRY(dalloc(&h->dcolptr, outcols + 1));
@@ -556,6 +581,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.inlist = h->dinlist;
     a.scr = h->dscr;
     a.iscr = h->discr;
+    a.bscr = h->dbscr;
     a.lambdas = h->dlam;
     a.nlambda = rc.nlambda;
     a.accumulate = rc.accumulate;
@@ -570,8 +596,19 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.capacity = rc.capacity;
     a.flag = h->dflag;
     a.stats = h->dstats;
+    const bool prof = getenv("CDGPU_PROFILE") != nullptr;
+    a.prof = prof ? reinterpret_cast<long long *>(h->dscr + 11 * (size_t)h->p) : nullptr;
     CD_TRY(launch_cov_init(h, a.A, a.lda, a.p, a.act, a.actval, a.nact, a.Ax, a.beta, a.inlist));
     CD_TRY(launch_cov_path(h, a));
+    if (prof) {
+      long long pf[8];
+      CUDA_TRY(cudaMemcpyAsync(pf, a.prof, sizeof pf, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      fprintf(stderr,
+              "[cdgpu profile] cov path: total %.3f Mcyc | full passes %.3f (events %lld) | list update %.3f | "
+              "active engine %.3f (steps %lld) | refresh %.3f\n",
+              pf[6] * 1e-6, pf[0] * 1e-6, pf[4], pf[1] * 1e-6, pf[2] * 1e-6, pf[5], pf[3] * 1e-6);
+    }
   } else {
     NaiveArgs a = {};
     a.kind = h->kind;
@@ -591,6 +628,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.inlist = h->dinlist;
     a.scr = h->dscr;
     a.iscr = h->discr;
+    a.bscr = h->dbscr;
     a.lambdas = h->dlam;
     a.nlambda = rc.nlambda;
     a.accumulate = rc.accumulate;

@@ -110,6 +110,83 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return v;
 }
 
+// List order after a pass == closed form of ProximalBase.dropzeros! (the LAST stored entry moves into
+// the hole) applied to the reference's pre-compaction list L.  During a full pass the reference's
+// `x[k] += b/a` (cd_differentiable_function.jl:102,185,335) APPENDS every visited non-member whose
+// tentative value is non-zero, the prox then stores an explicit zero for most of them, and
+// dropzeros! at the end of the pass (coordinate_descent.jl:108) removes those again — which
+// permutes the survivors: with K survivors, a survivor at position < K stays, and the holes among
+// the first K positions are filled, in increasing hole order, by the survivors at positions >= K
+// taken in DEcreasing position order.  (Verified against the sequential algorithm, tests/.)
+//
+// Block-collective over T threads.  Entries e < m_now: coordinate act[e], value val[e], position
+// in L = e for e < m_old, newpos[e - m_old] otherwise; an entry survives iff val[e] != 0.
+// tmp_i: >= 5*m_now ints, tmp_d: >= m_now doubles, s2: two shared ints.  Result: act/val[0..K),
+// K in s2[0]; inlist (nullable) is cleared for dropped coordinates.
+template <int T>
+__device__ void cd_compact_list(int *act, double *val, int m_old, int m_now, const int *newpos, unsigned char *inlist,
+                                int *tmp_i, double *tmp_d, int *s2) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s2[0] = 0;
+    s2[1] = 0;
+  }
+  __syncthreads();
+  int cnt = 0;
+  for (int e = tid; e < m_now; e += T) cnt += (val[e] != 0.0);
+  if (cnt) atomicAdd(&s2[0], cnt);
+  __syncthreads();
+  const int K = s2[0];
+  if (K == m_now && m_now == m_old) return; // nothing dropped, nothing new: order unchanged
+  int *F = tmp_i, *tailE = tmp_i + m_now, *tailP = tmp_i + 2 * m_now, *tailS = tmp_i + 3 * m_now, *ti = tmp_i + 4 * m_now;
+  for (int i = tid; i < K; i += T) F[i] = -1;
+  __syncthreads();
+  for (int e = tid; e < m_now; e += T) {
+    if (val[e] != 0.0) {
+      const int pos = e < m_old ? e : newpos[e - m_old];
+      if (pos < K) {
+        F[pos] = e;
+      } else {
+        const int t = atomicAdd(&s2[1], 1);
+        tailE[t] = e;
+        tailP[t] = pos;
+      }
+    } else if (inlist) {
+      inlist[act[e]] = 0;
+    }
+  }
+  __syncthreads();
+  const int Tn = s2[1];
+  for (int t = tid; t < Tn; t += T) {
+    const int pt = tailP[t];
+    int r = 0;
+    for (int u = 0; u < Tn; ++u) r += tailP[u] > pt;
+    tailS[r] = tailE[t];
+  }
+  __syncthreads();
+  if (tid < 32) {
+    int filled = 0;
+    for (int base = 0; base < K; base += 32) {
+      const int i = base + tid;
+      const bool hole = i < K && F[i] < 0;
+      const unsigned b = __ballot_sync(0xffffffffu, hole);
+      if (hole) F[i] = tailS[filled + __popc(b & ((1u << tid) - 1u))];
+      filled += __popc(b);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < K; i += T) {
+    ti[i] = act[F[i]];
+    tmp_d[i] = val[F[i]];
+  }
+  __syncthreads();
+  for (int i = tid; i < K; i += T) {
+    act[i] = ti[i];
+    val[i] = tmp_d[i];
+  }
+  __syncthreads();
+}
+
 // device-side mirror of cdgpu_stats (host fills device_ms / sigma bookkeeping)
 struct DevStats {
   long long passes, full_passes, visits, accepted;
@@ -139,8 +216,9 @@ struct cdgpu_handle_s {
   unsigned char *dinlist = nullptr; // p flags
   double *domega = nullptr;         // p (scratch copy of the caller's weights)
   // scratch for the sweep kernels
-  double *dscr = nullptr;           // 8 * p doubles
-  int *discr = nullptr;             // 4 * p ints
+  double *dscr = nullptr;           // 12 * p + 8 * n doubles
+  int *discr = nullptr;             // 8 * p ints
+  unsigned char *dbscr = nullptr;   // 2 * p bytes
   DevStats *dstats = nullptr;       // path stats, grown on demand
   int64_t nstats = 0;
   double *dlam = nullptr;
@@ -166,7 +244,8 @@ struct CovArgs {
   int *nact;
   unsigned char *inlist;
   double *scr;  // >= 8p doubles
-  int *iscr;    // >= 4p ints
+  int *iscr;    // >= 8p ints
+  unsigned char *bscr; // >= 2p bytes
   const double *lambdas;
   int nlambda;
   int accumulate; // 1: all lambdas are one solve (cold-start continuation): stats summed into stats[0], no path output
@@ -180,6 +259,7 @@ struct CovArgs {
   long long capacity;
   int *flag; // [0]=status (0 ok, 1 capacity, 2 active set too large), [1]=columns done
   DevStats *stats;
+  long long *prof; // optional [8]: SM cycles spent per phase by CTA 0 (CDGPU_PROFILE=1)
 };
 int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a);
 int launch_cov_init(cdgpu_handle_s *h, const double *A, long long lda, int p, const int *act, const double *actval,
@@ -208,6 +288,7 @@ struct NaiveArgs {
   unsigned char *inlist;
   double *scr;
   int *iscr;
+  unsigned char *bscr;
   const double *lambdas;
   int nlambda;
   int accumulate;

@@ -51,7 +51,8 @@ struct Smem {
   Bcast bc;
   unsigned long long red[COV_T / 32];
   double h[2];
-  int nact, flag;
+  int nact, flag, nonapp;
+  int s2[2];
 };
 
 __device__ __forceinline__ void named_bar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
@@ -62,6 +63,7 @@ struct Ctx {
   Smem *sm;
   double *sAx, *sb, *sainv, *sw, *sbeta; // this CTA's slice (shared or global)
   int *s_act, *s_idx;                    // CTA-0 engine scratch
+  unsigned char *s_in, *s_vnz;           // per slice: member at pass start / tentative value non-zero
   int rank, C, L, lo, len, slice_in_smem;
 };
 
@@ -77,7 +79,11 @@ __device__ __forceinline__ double slice_get(const Ctx &c, double *arr_local, int
 }
 
 // ------------------------------------------------------------------ full pass --
-__device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter, int &par, long long &accepted) {
+// Returns max|h|.  On return CTA 0 holds the new entries appended (in visit order) behind the
+// m_old old ones in a.act; `nonapp_total` is the number of visited non-members whose tentative value
+// was exactly zero (they are NOT appended by the reference's setindex!; practically always 0).
+__device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter, int &par, long long &accepted,
+                            bool first_pass_of_kernel, int &nonapp_total) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,6 +92,13 @@ __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter,
   int cur = -1;          // ordered: last coordinate that moved
   long long curpos = -1; // random: its visit position
   double maxH = 0.0;
+  // membership at the start of the pass (beta != 0, or an explicit zero handed in by the caller)
+  for (int i = tid; i < c.len; i += COV_T) {
+    c.s_in[i] = first_pass_of_kernel ? a.inlist[c.lo + i] : (unsigned char)(c.sbeta[i] != 0.0);
+    c.s_vnz[i] = 1;
+  }
+  if (tid == 0) sm->nonapp = 0;
+  __syncthreads();
   for (;;) {
     unsigned long long best = KEY_NONE;
     int bk = -1;
@@ -102,6 +115,11 @@ __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter,
       const double thr = __dmul_rn(__dmul_rn(ainv, lam), c.sw[i]);
       const double nw = cd_shrink(v, thr);
       const double h = nw - old;
+      const unsigned char nz = (unsigned char)(v != 0.0); // `x[k] -= b*a` appends iff the value is non-zero
+      if (nz != c.s_vnz[i]) {
+        c.s_vnz[i] = nz;
+        if (!c.s_in[i]) atomicAdd(&sm->nonapp, nz ? -1 : 1);
+      }
       if (h != 0.0 && key < best) {
         best = key;
         bk = k;
@@ -116,12 +134,16 @@ __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter,
 #pragma unroll
     for (int w = 1; w < COV_T / 32; ++w) bmin = sm->red[w] < bmin ? sm->red[w] : bmin;
     if (bmin == KEY_NONE) {
-      if (tid == 0) sm->mine.key = KEY_NONE;
+      if (tid == 0) {
+        sm->mine.key = KEY_NONE;
+        sm->mine.pad = sm->nonapp;
+      }
     } else if (best == bmin) {
       sm->mine.key = best;
       sm->mine.k = bk;
       sm->mine.h = bh;
       sm->mine.nw = bnw;
+      sm->mine.pad = sm->nonapp;
     }
     __syncthreads();
     if (tid < c.C) {
@@ -130,12 +152,17 @@ __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter,
     }
     c.cluster.sync();
     Cand w = sm->cand[par][0];
+    int napp = w.pad;
     for (int q = 1; q < c.C; ++q) {
       unsigned long long kq = sm->cand[par][q].key;
+      napp += sm->cand[par][q].pad;
       if (kq < w.key) w = sm->cand[par][q];
     }
     par ^= 1;
-    if (w.key == KEY_NONE) break;
+    if (w.key == KEY_NONE) {
+      nonapp_total = napp; // every slice's scan was final
+      break;
+    }
     const int k = w.k;
     if (tid == 0) {
       if (k >= c.lo && k < c.lo + c.len) c.sbeta[k - c.lo] = w.nw;
@@ -156,36 +183,44 @@ __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter,
   return maxH;
 }
 
-// dropzeros! on the list kept by CTA 0 (ProximalBase semantics: last entry moves into the hole).
-// Also refreshes actval[] with the current beta of every listed coordinate.
-__device__ void list_dropzeros(Ctx &c) {
+// rare: publish the visited non-members that were not appended (tentative value exactly zero)
+__device__ void publish_nonapp(Ctx &c) {
+  int *cnt = c.a.flag + 2, *list = c.a.iscr + 6 * (long long)c.a.p;
+  for (int i = threadIdx.x; i < c.len; i += COV_T)
+    if (!c.s_in[i] && !c.s_vnz[i]) list[atomicAdd(cnt, 1)] = c.lo + i;
+  __threadfence();
+}
+
+// dropzeros! after a full pass, CTA 0.  Gathers the final values of all listed coordinates, places
+// the new entries where the reference's temporary appends put them (see cd_compact_list) and compacts.
+__device__ void list_update_full(Ctx &c, int m_old, int nonapp_total, unsigned long long pass_counter) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
   const int tid = threadIdx.x;
   const int m = sm->nact;
-  int anyz = 0;
-  for (int i = tid; i < m; i += COV_T) {
-    double v = slice_get(c, c.sbeta, a.act[i]);
-    a.actval[i] = v;
-    anyz |= (v == 0.0);
-  }
-  anyz = __syncthreads_or(anyz);
-  if (anyz && tid == 0) {
-    int n = m, i = 0;
-    while (i < n) {
-      if (a.actval[i] == 0.0) {
-        a.inlist[a.act[i]] = 0;
-        if (i != n - 1) {
-          a.actval[i] = a.actval[n - 1];
-          a.act[i] = a.act[n - 1];
-        }
-        n -= 1;
-      } else {
-        i += 1;
-      }
+  for (int i = tid; i < m; i += COV_T) a.actval[i] = slice_get(c, c.sbeta, a.act[i]);
+  int *newpos = a.iscr + 7 * (long long)a.p;
+  const bool ordered = a.randomize == 0;
+  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  const int *nonapp = a.iscr + 6 * (long long)a.p;
+  for (int e = m_old + tid; e < m; e += COV_T) {
+    const int k = a.act[e];
+    const long long vis = ordered ? k : (long long)cd_perm_inv(pk, (uint32_t)k);
+    int before = 0; // old members and non-appended non-members visited before k
+    for (int j = 0; j < m_old; ++j) {
+      const int kj = a.act[j];
+      before += (ordered ? kj : (long long)cd_perm_inv(pk, (uint32_t)kj)) < vis;
     }
-    sm->nact = n;
+    for (int j = 0; j < nonapp_total; ++j) {
+      const int kj = __ldcg(nonapp + j);
+      before += (ordered ? kj : (long long)cd_perm_inv(pk, (uint32_t)kj)) < vis;
+    }
+    newpos[e - m_old] = m_old + (int)vis - before;
   }
+  __syncthreads();
+  cd_compact_list<COV_T>(a.act, a.actval, m_old, m, newpos, a.inlist, a.iscr + (long long)a.p, a.scr + 2 * (long long)a.p,
+                         sm->s2);
+  if (tid == 0) sm->nact = sm->s2[0];
   __syncthreads();
 }
 
@@ -443,6 +478,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
     c.sainv = d + 2 * L;
     c.sw = d + 3 * L;
     c.sbeta = d + 4 * L;
+    c.s_in = reinterpret_cast<unsigned char *>(d + 5 * L);
+    c.s_vnz = c.s_in + L;
     for (int i = tid; i < c.len; i += COV_T) {
       const int k = c.lo + i;
       c.sAx[i] = a.Ax[k];
@@ -458,6 +495,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
     c.sb = const_cast<double *>(a.b) + c.lo;
     c.sainv = const_cast<double *>(a.ainv) + c.lo;
     c.sw = g + a.p + c.lo;
+    c.s_in = a.bscr + c.lo;
+    c.s_vnz = a.bscr + a.p + c.lo;
     for (int i = tid; i < c.len; i += COV_T) {
       c.sbeta[i] = a.beta[c.lo + i];
       c.sw[i] = a.omega ? a.omega[c.lo + i] : 1.0;
@@ -470,7 +509,10 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   __syncthreads();
   cluster.sync();
 
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = clock64();
   int par = 0;
+  bool first_pass = true;
   unsigned long long pass_counter = 0;
   DevStats st;
   int status = 0;
@@ -493,9 +535,24 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         st.passes += 1;
         st.full_passes += 1;
         st.visits += a.p;
-        const double maxH = full_pass(c, lam, pass_counter, par, st.accepted);
+        int nonapp_total = 0;
+        const int m_old = c.sm->nact; // only meaningful on CTA 0
+        const long long t0 = clock64();
+        const long long acc0 = st.accepted;
+        const double maxH = full_pass(c, lam, pass_counter, par, st.accepted, first_pass, nonapp_total);
+        const long long t1 = clock64();
+        pf[0] += t1 - t0;
+        pf[4] += st.accepted - acc0;
+        first_pass = false;
+        if (nonapp_total > 0) { // rare slow path: collect the non-appended coordinates for CTA 0
+          if (c.rank == 0 && tid == 0) a.flag[2] = 0;
+          cluster.sync();
+          publish_nonapp(c);
+          cluster.sync();
+        }
+        if (c.rank == 0) list_update_full(c, m_old, nonapp_total, pass_counter);
+        pf[1] += clock64() - t1;
         pass_counter += 1;
-        if (c.rank == 0) list_dropzeros(c);
         st.maxH = maxH;
         conv = maxH < a.optTol;
         if (conv) {
@@ -503,6 +560,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           break;
         }
       } else {
+        const long long t0 = clock64();
         if (c.rank == 0) {
           const int m = c.sm->nact;
           const long long budget = a.maxIter - iter;
@@ -520,6 +578,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           }
         }
         cluster.sync();
+        const long long t1 = clock64();
+        pf[2] += t1 - t0;
         const Bcast *bc = cluster.map_shared_rank(&c.sm->bc, 0);
         const Bcast b = *bc;
         if (b.status) {
@@ -527,6 +587,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           break;
         }
         refresh_slice(c, b.m0);
+        pf[3] += clock64() - t1;
+        pf[5] += b.visits;
         iter += b.npasses;
         pass_counter += b.npasses;
         st.passes += b.npasses;
@@ -578,6 +640,10 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
     for (int i = tid; i < c.len; i += COV_T) a.beta[c.lo + i] = c.sbeta[i];
   }
   if (c.rank == 0 && tid == 0) {
+    if (a.prof) {
+      pf[6] = clock64() - t_start;
+      for (int i = 0; i < 8; ++i) a.prof[i] = pf[i];
+    }
     *a.nact = c.sm->nact;
     a.flag[0] = status;
     a.flag[1] = (int)cols_done;
@@ -732,7 +798,7 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   while (C > 1 && a.p < C * 32) C >>= 1; // tiny problems: fewer, fuller slices
   int L = (a.p + C - 1) / C;
   L = (L + 1) & ~1;
-  size_t need = fixed + (size_t)5 * L * sizeof(double);
+  size_t need = fixed + (size_t)5 * L * sizeof(double) + 2 * (size_t)L + 16;
   int slice_in_smem = need <= max_dyn;
   size_t dyn = slice_in_smem ? need : fixed;
   cudaLaunchConfig_t cfg = {};

@@ -28,9 +28,11 @@ namespace {
 constexpr int NV_T = 512;
 constexpr int NV_W = NV_T / 32;
 
-struct HEntry {
+struct __align__(16) HEntry {
   double h, nw;
+  int app, pad[3]; // app == 0: a non-member whose tentative value was exactly zero (not appended by setindex!)
 };
+static_assert(sizeof(HEntry) == 32, "HEntry");
 
 struct NBcast {
   long long npasses, visits, accepted;
@@ -42,7 +44,8 @@ struct NSmem {
   double red[2][NV_W];
   unsigned int redu[NV_W];
   double bval[2];
-  int nact, flag;
+  int nact, flag, nonapp;
+  int s2[2];
 };
 
 struct NCtx {
@@ -86,7 +89,7 @@ __device__ __forceinline__ void block_sum2(NSmem *sm, double &u, double &v) {
 // closed-form coordinate update given d = X_k' (w .* r):
 //   LS/WLS  cd_differentiable_function.jl:101-104 / :184-187;  sqrt  :271-283
 __device__ __forceinline__ void coord_update(int kind, int n, double d, double a, double old, double lam, double om,
-                                             double rr, double &nw, double &h) {
+                                             double rr, double &nw, double &h, bool &tentative_nz) {
   if (kind == CDGPU_LOSS_SQRT) {
     const double s = d + a * old;
     const double rsq = rr + 2.0 * old * d + old * old * a;
@@ -98,8 +101,10 @@ __device__ __forceinline__ void coord_update(int kind, int n, double d, double a
       nw = (s - l / sqrt(1.0 - l * l / a) * sqrt(rsq - s * s / a)) / a;
     else
       nw = (s + l / sqrt(1.0 - l * l / a) * sqrt(rsq - s * s / a)) / a;
+    tentative_nz = nw != 0.0; // x[k] = newVal: appended only when non-zero (:278-283)
   } else {
     const double v = __dadd_rn(old, d / a);
+    tentative_nz = v != 0.0; // x[k] += b/a appends whenever the sum is non-zero (:102,:185)
     const double thr = __dmul_rn(__dmul_rn((double)n / a, lam), om);
     nw = cd_shrink(v, thr);
   }
@@ -158,7 +163,13 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool ordered = a.randomize == 0;
   const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  int *nonapp_flag = a.flag + 2;              // set by any warp that produced a non-appended entry
+  int *nonapp_list = a.iscr + 6 * (long long)a.p; // CTA 0
   double maxH = 0.0;
+  if (c.bid == 0 && tid == 0) {
+    sm->nonapp = 0;
+    __stcg(nonapp_flag, 0);
+  }
   for (int q0 = 0; q0 < a.p; q0 += c.CH) {
     const int qlen = min(c.CH, a.p - q0);
     int start = 0;
@@ -171,12 +182,13 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
         const double d = warp_col_dot(c, a.X + (long long)k * a.ldx);
         if (lane == 0) {
           double nw, h;
+          bool tnz;
           coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
-                       c.rr, nw, h);
-          HEntry e;
-          e.h = h;
-          e.nw = nw;
-          __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(e.h, e.nw));
+                       c.rr, nw, h, tnz);
+          const int app = (tnz || __ldcg(a.inlist + k)) ? 1 : 0;
+          __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
+          __stcg(&hb[j].app, app);
+          if (!app) __stcg(nonapp_flag, 1);
         }
       }
       c.grid.sync();
@@ -197,6 +209,13 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
       for (int i = 1; i < NV_W; ++i) jmin = min(jmin, sm->redu[i]);
       __syncthreads();
       rp ^= 1;
+      if (c.bid == 0 && __ldcg(nonapp_flag)) { // rare: remember the finalised non-appended coordinates
+        const int jend = jmin == 0xffffffffu ? qlen : (int)jmin;
+        for (int j = start + tid; j < jend; j += NV_T)
+          if (__ldcg(&hb[j].app) == 0)
+            nonapp_list[atomicAdd(&sm->nonapp, 1)] = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
+        __syncthreads();
+      }
       if (jmin == 0xffffffffu) break;
       const int k = ordered ? q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(q0 + jmin));
       const double2 e = __ldcg(reinterpret_cast<const double2 *>(hb + jmin));
@@ -204,7 +223,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
       if (c.bid == 0 && tid == 0) {
         __stcg(a.beta + k, nw);
         if (!a.inlist[k]) { // setindex! appends on the first non-zero store
-          a.inlist[k] = 1;
+          __stcg(a.inlist + k, (unsigned char)1);
           a.act[sm->nact] = k;
           sm->nact += 1;
         }
@@ -219,35 +238,41 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
   return maxH;
 }
 
-// dropzeros! on CTA 0's list; refreshes actval from the dense beta
-__device__ void list_dropzeros(NCtx &c) {
+// dropzeros! after a full pass on CTA 0: new entries go where the reference's temporary appends put
+// them (common.cuh: cd_compact_list); sqrt-lasso never appends temporarily (:278-283).
+__device__ void list_update_full(NCtx &c, int m_old, unsigned long long pass_counter) {
   const NaiveArgs &a = c.a;
   NSmem *sm = c.sm;
   const int tid = threadIdx.x;
   const int m = sm->nact;
-  int anyz = 0;
-  for (int i = tid; i < m; i += NV_T) {
-    const double v = __ldcg(a.beta + a.act[i]);
-    a.actval[i] = v;
-    anyz |= (v == 0.0);
-  }
-  anyz = __syncthreads_or(anyz);
-  if (anyz && tid == 0) {
-    int n = m, i = 0;
-    while (i < n) {
-      if (a.actval[i] == 0.0) {
-        a.inlist[a.act[i]] = 0;
-        if (i != n - 1) {
-          a.actval[i] = a.actval[n - 1];
-          a.act[i] = a.act[n - 1];
-        }
-        n -= 1;
-      } else {
-        i += 1;
-      }
+  for (int i = tid; i < m; i += NV_T) a.actval[i] = __ldcg(a.beta + a.act[i]);
+  int *newpos = a.iscr + 7 * (long long)a.p;
+  const int *nonapp = a.iscr + 6 * (long long)a.p;
+  const int nna = sm->nonapp;
+  const bool ordered = a.randomize == 0;
+  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  for (int e = m_old + tid; e < m; e += NV_T) {
+    if (a.kind == CDGPU_LOSS_SQRT) {
+      newpos[e - m_old] = e;
+      continue;
     }
-    sm->nact = n;
+    const int k = a.act[e];
+    const long long vis = ordered ? k : (long long)cd_perm_inv(pk, (uint32_t)k);
+    int before = 0;
+    for (int j = 0; j < m_old; ++j) {
+      const int kj = a.act[j];
+      before += (ordered ? kj : (long long)cd_perm_inv(pk, (uint32_t)kj)) < vis;
+    }
+    for (int j = 0; j < nna; ++j) {
+      const int kj = nonapp[j];
+      before += (ordered ? kj : (long long)cd_perm_inv(pk, (uint32_t)kj)) < vis;
+    }
+    newpos[e - m_old] = m_old + (int)vis - before;
   }
+  __syncthreads();
+  cd_compact_list<NV_T>(a.act, a.actval, m_old, m, newpos, a.inlist, a.iscr + (long long)a.p, a.scr + 8 + 8 * (long long)a.p + 16,
+                        sm->s2);
+  if (tid == 0) sm->nact = sm->s2[0];
   __syncthreads();
 }
 
@@ -281,8 +306,9 @@ __device__ void active_phase(NCtx &c, double lam, long long maxPasses, unsigned 
       }
       d = block_sum(sm, d, 1);
       double nw, h;
+      bool tnz;
       const double old = a.actval[i];
-      coord_update(a.kind, n, d, __ldg(a.colsq + k), old, lam, a.omega ? __ldg(a.omega + k) : 1.0, c.rr, nw, h);
+      coord_update(a.kind, n, d, __ldg(a.colsq + k), old, lam, a.omega ? __ldg(a.omega + k) : 1.0, c.rr, nw, h, tnz);
       __syncthreads(); // everyone has read actval[i] and red[1]
       if (tid == 0) a.actval[i] = nw;
       if (h != 0.0) {
@@ -412,9 +438,10 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           st.passes += 1;
           st.full_passes += 1;
           st.visits += a.p;
+          const int m_old = c.sm->nact; // CTA 0
           const double maxH = full_pass(c, lam, pass_counter, rp, st.accepted);
+          if (c.bid == 0) list_update_full(c, m_old, pass_counter);
           pass_counter += 1;
-          if (c.bid == 0) list_dropzeros(c);
           st.maxH = maxH;
           conv = maxH < a.optTol;
           if (conv) {
@@ -633,8 +660,9 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
     if (v >= 1) CH = min(v, (long long)a.p);
   }
   // hbuf + broadcast block live behind the 8p+8n scratch doubles: carve from the tail of iscr/scr
-  HEntry *hbuf = reinterpret_cast<HEntry *>(a.scr + 8); // 2*CH entries = 4*CH doubles <= 4p
-  NBcast *bc = reinterpret_cast<NBcast *>(a.scr + 8 + 4 * (long long)a.p);
+  // scratch doubles: [0,8) misc | hbuf 2*CH entries of 32 B <= 8p | bc 16 | compaction staging p
+  HEntry *hbuf = reinterpret_cast<HEntry *>(a.scr + 8);
+  NBcast *bc = reinterpret_cast<NBcast *>(a.scr + 8 + 8 * (long long)a.p);
   int ch = (int)CH;
   void *args[] = {(void *)&a, (void *)&ch, (void *)&hbuf, (void *)&bc};
   CUDA_TRY(cudaLaunchCooperativeKernel((void *)naive_path_kernel, dim3(G), dim3(NV_T), args, dyn, h->stream));

@@ -41,7 +41,9 @@ struct VcArgs {
 struct VSm {
   double red[VC_W];
   double cand_h[VC_W], cand_nw[VC_W];
-  int nact, flag;
+  int cand_app[VC_W];
+  int nact, flag, nonapp;
+  int s2[2];
 };
 
 __device__ __forceinline__ double ipow(double x, int l) {
@@ -71,8 +73,10 @@ __global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
   double *sa = sr + n;       // a_k = sum w eX_k^2
   double *sbeta = sa + ep;   // dense iterate
   double *sval = sbeta + ep; // values in list order
-  int *sact = reinterpret_cast<int *>(sval + ep);
-  unsigned char *sin = reinterpret_cast<unsigned char *>(sact + ep);
+  double *stmpd = sval + ep; // compaction staging
+  int *sact = reinterpret_cast<int *>(stmpd + ep);
+  int *snewpos = sact + ep, *snonapp = snewpos + ep, *stmpi = snonapp + ep; // stmpi: 5*ep
+  unsigned char *sin = reinterpret_cast<unsigned char *>(stmpi + 5 * ep);
 
   for (int g = a.g0 + blockIdx.x; g < a.g1; g += gridDim.x) {
     const double z0 = a.zgrid[g];
@@ -129,11 +133,13 @@ __global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
         st.full_passes += 1;
         st.visits += ep;
         const PermKey pk = cd_perm_key((uint32_t)ep, a.seed, pass_counter);
+        const int m_old = sm->nact;
+        if (tid == 0) sm->nonapp = 0;
         int pos = 0;
         while (pos < ep) {
           const int myq = pos + warp;
           double h = 0.0, nw = 0.0;
-          int k = -1;
+          int k = -1, app = 1;
           if (myq < ep) {
             k = ordered ? myq : (int)cd_perm(pk, (uint32_t)myq);
             const int j = k / dg, l = k - j * dg;
@@ -146,16 +152,23 @@ __global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
             const double thr = __dmul_rn(__dmul_rn((double)n / ak, a.lambda0), sqrt(ak / (double)n));
             nw = cd_shrink(v, thr);
             h = nw - old;
+            app = (v != 0.0 || sin[k]) ? 1 : 0; // `x[k] += b/a` appends a non-member iff the sum is non-zero
           }
           if (lane == 0) {
             sm->cand_h[warp] = h;
             sm->cand_nw[warp] = nw;
+            sm->cand_app[warp] = app;
           }
           __syncthreads();
           int first = -1;
 #pragma unroll
           for (int q = VC_W - 1; q >= 0; --q)
             if (sm->cand_h[q] != 0.0) first = q;
+          if (tid == 0) { // finalised visits of this round that the reference would not have appended (rare)
+            const int qend = first < 0 ? VC_W : first;
+            for (int q = 0; q < qend; ++q)
+              if (!sm->cand_app[q] && pos + q < ep) snonapp[sm->nonapp++] = ordered ? pos + q : (int)cd_perm(pk, (uint32_t)(pos + q));
+          }
           if (first < 0) {
             pos += VC_W;
             __syncthreads();
@@ -183,8 +196,20 @@ __global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
           pos = kq + 1;
           __syncthreads();
         }
-        // refresh list values
-        for (int i = tid; i < sm->nact; i += VC_T) sval[i] = sbeta[sact[i]];
+        // list update: values, then the reference's post-dropzeros! order (common.cuh: cd_compact_list)
+        const int mnow = sm->nact, nna = sm->nonapp;
+        for (int i = tid; i < mnow; i += VC_T) sval[i] = sbeta[sact[i]];
+        for (int e = m_old + tid; e < mnow; e += VC_T) {
+          const int k = sact[e];
+          const int vis = ordered ? k : (int)cd_perm_inv(pk, (uint32_t)k);
+          int before = 0;
+          for (int j = 0; j < m_old; ++j) before += (ordered ? sact[j] : (int)cd_perm_inv(pk, (uint32_t)sact[j])) < vis;
+          for (int j = 0; j < nna; ++j) before += (ordered ? snonapp[j] : (int)cd_perm_inv(pk, (uint32_t)snonapp[j])) < vis;
+          snewpos[e - m_old] = m_old + vis - before;
+        }
+        __syncthreads();
+        cd_compact_list<VC_T>(sact, sval, m_old, mnow, snewpos, sin, stmpi, stmpd, sm->s2);
+        if (tid == 0) sm->nact = sm->s2[0];
         __syncthreads();
       } else { // ---- active-set pass: sequential chain, block-wide dot per step
         const int m = sm->nact;
@@ -217,7 +242,7 @@ __global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
         }
       }
       pass_counter += 1;
-      // ---- dropzeros!
+      // ---- dropzeros! (after a full pass the list was already compacted above)
       if (tid == 0) {
         int nn = sm->nact, i = 0;
         while (i < nn) {
@@ -272,7 +297,7 @@ API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
   CUDA_TRY(cudaSetDevice(device));
   const int64_t mloc = m_end - m_begin;
   if (mloc == 0) return CDGPU_OK;
-  const size_t dyn = (sizeof(VSm) + 15) / 16 * 16 + (size_t)(3 * n + 3 * ep) * sizeof(double) + (size_t)ep * 5 + 16;
+  const size_t dyn = (sizeof(VSm) + 15) / 16 * 16 + (size_t)(3 * n + 4 * ep) * sizeof(double) + (size_t)ep * (8 * 4 + 1) + 16;
   if (dyn > 227 * 1024)
     return cdgpu_set_error(CDGPU_ECAP, "local problem does not fit in shared memory (n=%lld, ep=%lld)", (long long)n,
                            (long long)ep);
