@@ -78,8 +78,12 @@ class SparseIterate:
     `x[k]` and `nonzero()` are 0-based.
     """
 
-    def __init__(self, p_or_vec):
-        if np.isscalar(p_or_vec):
+    def __init__(self, p_or_vec, _triple=None):
+        if _triple is not None:  # (nzval, nzval2ind) of exactly nnz entries: a read-only snapshot (path column)
+            self.p = int(p_or_vec)
+            self.nzval, self.nzval2ind = _triple
+            self._nnz = C.c_int64(len(self.nzval))
+        elif np.isscalar(p_or_vec):
             self.p = int(p_or_vec)
             self.nzval = np.zeros(self.p)
             self.nzval2ind = np.zeros(self.p, dtype=np.int64)
@@ -105,9 +109,17 @@ class SparseIterate:
         hit = np.flatnonzero(self.nzval2ind[: self.nnz] == k + 1)
         return float(self.nzval[hit[0]]) if hit.size else 0.0
 
+    def _grow(self):
+        if self.nzval.size < self.p:  # snapshot made by LassoPath: give it ProximalBase's dense capacity
+            n = self.nnz
+            nz, ind = np.zeros(self.p), np.zeros(self.p, dtype=np.int64)
+            nz[:n], ind[:n] = self.nzval[:n], self.nzval2ind[:n]
+            self.nzval, self.nzval2ind = nz, ind
+
     def __setitem__(self, k: int, v: float):
         if not 0 <= k < self.p:
             raise IndexError(k)
+        self._grow()
         hit = np.flatnonzero(self.nzval2ind[: self.nnz] == k + 1)
         if hit.size:
             self.nzval[hit[0]] = v
@@ -128,7 +140,8 @@ class SparseIterate:
 
     def copy(self) -> "SparseIterate":
         o = SparseIterate(self.p)
-        o.nzval[:], o.nzval2ind[:], o._nnz.value = self.nzval, self.nzval2ind, self.nnz
+        n = self.nnz
+        o.nzval[:n], o.nzval2ind[:n], o._nnz.value = self.nzval[:n], self.nzval2ind[:n], n
         return o
 
     def __eq__(self, other):
@@ -332,6 +345,7 @@ class Backend:
         if g.λ is not None and g.λ.shape != (p,):
             raise DimensionMismatch()  # :15
         o, st = options.c(), _ffi.Stats()
+        x._grow()
         self.lib.check(self.lib.solve(f._h, float(g.λ0), ptr(g.λ), C.byref(o), ptr(x.nzval), ptr(x.nzval2ind),
                                       C.byref(x._nnz), C.byref(st)))
         f.last_stats = st.as_dict()
@@ -379,6 +393,7 @@ class Backend:
         if x.p != X.shape[1] or ω.shape != (X.shape[1],):
             raise DimensionMismatch()
         o = options.c()
+        x._grow()
         f = self.CDLeastSquaresLoss(y, X)
         st, sig = _ffi.Stats(), C.c_double()
         self.lib.check(self.lib.scaled_solve(f._h, float(λ), ptr(ω), C.byref(o), ptr(x.nzval), ptr(x.nzval2ind),
@@ -415,10 +430,8 @@ class Backend:
                                      ptr(nzval), C.byref(done), C.cast(stats, C.c_void_p)))
         βpath = []
         for i in range(done.value):
-            xi = SparseIterate(p)
             a, b = colptr[i], colptr[i + 1]
-            xi.nzval[: b - a], xi.nzval2ind[: b - a], xi._nnz.value = nzval[a:b], rowval[a:b], b - a
-            βpath.append(xi)
+            βpath.append(SparseIterate(p, _triple=(nzval[a:b].copy(), rowval[a:b].copy())))
         if own:
             f.close()
         return LassoPath(lam[: done.value].copy(), βpath, [stats[i].as_dict() for i in range(done.value)])

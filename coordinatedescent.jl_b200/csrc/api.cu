@@ -601,13 +601,15 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     CD_TRY(launch_cov_init(h, a.A, a.lda, a.p, a.act, a.actval, a.nact, a.Ax, a.beta, a.inlist));
     CD_TRY(launch_cov_path(h, a));
     if (prof) {
-      long long pf[8];
+      long long pf[10];
       CUDA_TRY(cudaMemcpyAsync(pf, a.prof, sizeof pf, cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream));
       fprintf(stderr,
               "[cdgpu profile] cov path: total %.3f Mcyc | full passes %.3f (events %lld) | list update %.3f | "
-              "active engine %.3f (steps %lld) | refresh %.3f\n",
-              pf[6] * 1e-6, pf[0] * 1e-6, pf[4], pf[1] * 1e-6, pf[2] * 1e-6, pf[5], pf[3] * 1e-6);
+              "active engine %.3f (steps %lld) | refresh %.3f || full-pass rounds: scan+publish %.3f, cluster.sync %.3f, "
+              "apply %.3f\n",
+              pf[6] * 1e-6, pf[0] * 1e-6, pf[4], pf[1] * 1e-6, pf[2] * 1e-6, pf[5], pf[3] * 1e-6, pf[7] * 1e-6, pf[8] * 1e-6,
+              pf[9] * 1e-6);
     }
   } else {
     NaiveArgs a = {};

@@ -83,7 +83,7 @@ __device__ __forceinline__ double slice_get(const Ctx &c, double *arr_local, int
 // m_old old ones in a.act; `nonapp_total` is the number of visited non-members whose tentative value
 // was exactly zero (they are NOT appended by the reference's setindex!; practically always 0).
 __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter, int &par, long long &accepted,
-                            bool first_pass_of_kernel, int &nonapp_total) {
+                            bool first_pass_of_kernel, int &nonapp_total, long long *pf) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -100,6 +100,7 @@ __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter,
   if (tid == 0) sm->nonapp = 0;
   __syncthreads();
   for (;;) {
+    const long long ta = clock64();
     unsigned long long best = KEY_NONE;
     int bk = -1;
     double bh = 0.0, bnw = 0.0;
@@ -150,7 +151,11 @@ __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter,
       Cand *dst = c.cluster.map_shared_rank(&sm->cand[par][c.rank], tid);
       *dst = sm->mine;
     }
+    const long long tb = clock64();
     c.cluster.sync();
+    const long long tc = clock64();
+    pf[7] += tb - ta;
+    pf[8] += tc - tb;
     Cand w = sm->cand[par][0];
     int napp = w.pad;
     for (int q = 1; q < c.C; ++q) {
@@ -179,6 +184,7 @@ __device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter,
     cur = k;
     curpos = (long long)w.key;
     __syncthreads();
+    pf[9] += clock64() - tc;
   }
   return maxH;
 }
@@ -509,7 +515,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   __syncthreads();
   cluster.sync();
 
-  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_start = clock64();
   int par = 0;
   bool first_pass = true;
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         const int m_old = c.sm->nact; // only meaningful on CTA 0
         const long long t0 = clock64();
         const long long acc0 = st.accepted;
-        const double maxH = full_pass(c, lam, pass_counter, par, st.accepted, first_pass, nonapp_total);
+        const double maxH = full_pass(c, lam, pass_counter, par, st.accepted, first_pass, nonapp_total, pf);
         const long long t1 = clock64();
         pf[0] += t1 - t0;
         pf[4] += st.accepted - acc0;
@@ -642,7 +648,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   if (c.rank == 0 && tid == 0) {
     if (a.prof) {
       pf[6] = clock64() - t_start;
-      for (int i = 0; i < 8; ++i) a.prof[i] = pf[i];
+      for (int i = 0; i < 10; ++i) a.prof[i] = pf[i];
     }
     *a.nact = c.sm->nact;
     a.flag[0] = status;
