@@ -562,7 +562,8 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
   CD_TRY(grow(h, (size_t)rc.nlambda, rc.want_path ? (size_t)rc.capacity : 0, rc.want_path ? (size_t)rc.nlambda : 0));
   CUDA_TRY(cudaMemcpyAsync(h->dlam, rc.lambdas, (size_t)rc.nlambda * sizeof(double), cudaMemcpyHostToDevice,
                            h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 8 * sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 4 * sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dflag + 4, 0xff, 4 * sizeof(int), h->stream)); // first-mover words
   CUDA_TRY(cudaMemsetAsync(h->dstats, 0, (size_t)rc.nlambda * sizeof(DevStats), h->stream));
   if (rc.want_path) CUDA_TRY(cudaMemsetAsync(h->dcolptr, 0, ((size_t)rc.nlambda + 1) * sizeof(long long), h->stream));
   if (h->kind == CDGPU_LOSS_QUAD) {
@@ -649,8 +650,19 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.outerMaxIter = rc.outerMaxIter;
     a.outerTol = rc.outerTol;
     a.sigma0 = rc.sigma0;
+    const bool prof = getenv("CDGPU_PROFILE") != nullptr;
+    a.prof = prof ? reinterpret_cast<long long *>(h->dscr + 11 * (size_t)h->p) : nullptr;
     CD_TRY(launch_naive_init(h, a));
     CD_TRY(launch_naive_path(h, a));
+    if (prof) {
+      long long pf[10];
+      CUDA_TRY(cudaMemcpyAsync(pf, a.prof, sizeof pf, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      fprintf(stderr,
+              "[cdgpu profile] naive path (CTA 0): total %.3f Mcyc | full-pass rounds %lld: column dots %.3f, grid.sync "
+              "%.3f, scan %.3f, apply %.3f | list update %.3f | active phase %.3f\n",
+              pf[6] * 1e-6, pf[7], pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6);
+    }
   }
   return CDGPU_OK;
 }

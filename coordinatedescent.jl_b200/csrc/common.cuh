@@ -306,6 +306,7 @@ struct NaiveArgs {
   int scaled;
   long long outerMaxIter;
   double outerTol, sigma0;
+  long long *prof; // optional [10]: SM cycles per phase on CTA 0 (CDGPU_PROFILE=1)
 };
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
 int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a); // r = y - X beta, beta dense, inlist

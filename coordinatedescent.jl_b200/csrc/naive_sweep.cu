@@ -111,31 +111,64 @@ __device__ __forceinline__ void coord_update(int kind, int n, double d, double a
   h = nw - old;
 }
 
-// one warp: d = sum_i X[i,k] r_i [w_i]
-__device__ __forceinline__ double warp_col_dot(const NCtx &c, const double *col) {
+// streaming 16-byte load that does not pollute L1 (each column is read once per visit)
+__device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// one warp: d = sum_i X[i,k] r_i [w_i].  16-byte loads, 8 independent loads (4 KB) in flight per
+// warp so 16 warps keep ~64 KB per SM outstanding (HBM latency x bandwidth / 148 SMs ~ 35 KB).
+template <bool HASW>
+__device__ __forceinline__ double warp_col_dot_t(const NCtx &c, const double *col) {
   const int n = c.a.n, lane = threadIdx.x & 31;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int i = lane;
-  if (c.w) {
-    for (; i + 96 < n; i += 128) {
-      const double x0 = __ldg(col + i), x1 = __ldg(col + i + 32), x2 = __ldg(col + i + 64), x3 = __ldg(col + i + 96);
-      s0 = fma(x0 * c.w[i], c.r[i], s0);
-      s1 = fma(x1 * c.w[i + 32], c.r[i + 32], s1);
-      s2 = fma(x2 * c.w[i + 64], c.r[i + 64], s2);
-      s3 = fma(x3 * c.w[i + 96], c.r[i + 96], s3);
+  if ((reinterpret_cast<uintptr_t>(col) & 15) == 0) {
+    const double2 *c2 = reinterpret_cast<const double2 *>(col);
+    const double2 *r2 = reinterpret_cast<const double2 *>(c.r);
+    const double2 *w2 = reinterpret_cast<const double2 *>(c.w);
+    const int np = n >> 1;
+    int i = lane;
+    for (; i + 7 * 32 < np; i += 8 * 32) {
+      double2 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = ldg_stream2(c2 + i + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double2 rv = r2[i + 32 * u];
+        if (HASW) {
+          const double2 wv = w2[i + 32 * u];
+          x[u].x *= wv.x;
+          x[u].y *= wv.y;
+        }
+        if (u & 1) {
+          s2 = fma(x[u].x, rv.x, s2);
+          s3 = fma(x[u].y, rv.y, s3);
+        } else {
+          s0 = fma(x[u].x, rv.x, s0);
+          s1 = fma(x[u].y, rv.y, s1);
+        }
+      }
     }
-    for (; i < n; i += 32) s0 = fma(__ldg(col + i) * c.w[i], c.r[i], s0);
+    for (; i < np; i += 32) {
+      double2 xv = ldg_stream2(c2 + i);
+      const double2 rv = r2[i];
+      if (HASW) {
+        xv.x *= w2[i].x;
+        xv.y *= w2[i].y;
+      }
+      s0 = fma(xv.x, rv.x, s0);
+      s1 = fma(xv.y, rv.y, s1);
+    }
+    if ((n & 1) && lane == 0) s2 = fma(HASW ? col[n - 1] * c.w[n - 1] : col[n - 1], c.r[n - 1], s2);
   } else {
-    for (; i + 96 < n; i += 128) {
-      const double x0 = __ldg(col + i), x1 = __ldg(col + i + 32), x2 = __ldg(col + i + 64), x3 = __ldg(col + i + 96);
-      s0 = fma(x0, c.r[i], s0);
-      s1 = fma(x1, c.r[i + 32], s1);
-      s2 = fma(x2, c.r[i + 64], s2);
-      s3 = fma(x3, c.r[i + 96], s3);
-    }
-    for (; i < n; i += 32) s0 = fma(__ldg(col + i), c.r[i], s0);
+    for (int i = lane; i < n; i += 32) s0 = fma(HASW ? __ldg(col + i) * c.w[i] : __ldg(col + i), c.r[i], s0);
   }
   return warp_sum((s0 + s1) + (s2 + s3));
+}
+__device__ __forceinline__ double warp_col_dot(const NCtx &c, const double *col) {
+  return c.w ? warp_col_dot_t<true>(c, col) : warp_col_dot_t<false>(c, col);
 }
 
 // r -= X_k * h on this CTA's copy; refreshes ||r||^2 when the loss needs it
@@ -143,27 +176,47 @@ __device__ __forceinline__ void apply_step(NCtx &c, const double *col, double h)
   const int n = c.a.n;
   if (c.a.kind == CDGPU_LOSS_SQRT) {
     double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += NV_T) {
-      const double v = __dsub_rn(c.r[i], __dmul_rn(__ldg(col + i), h));
-      c.r[i] = v;
-      acc = fma(v, v, acc);
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * NV_T) {
+      double xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xv[u] = (i0 + u * NV_T < n) ? __ldg(col + i0 + u * NV_T) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NV_T;
+        if (i < n) {
+          const double v = __dsub_rn(c.r[i], __dmul_rn(xv[u], h));
+          c.r[i] = v;
+          acc = fma(v, v, acc);
+        }
+      }
     }
     c.rr = block_sum(c.sm, acc, 0);
     __syncthreads();
   } else {
-    for (int i = threadIdx.x; i < n; i += NV_T) c.r[i] = __dsub_rn(c.r[i], __dmul_rn(__ldg(col + i), h));
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * NV_T) {
+      double xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xv[u] = (i0 + u * NV_T < n) ? __ldg(col + i0 + u * NV_T) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NV_T;
+        if (i < n) c.r[i] = __dsub_rn(c.r[i], __dmul_rn(xv[u], h));
+      }
+    }
     __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------ full pass --
-__device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter, int &rp, long long &accepted) {
+__device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter, int &rp, int &round3,
+                            long long &accepted, long long *pf) {
   const NaiveArgs &a = c.a;
   NSmem *sm = c.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool ordered = a.randomize == 0;
   const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
   int *nonapp_flag = a.flag + 2;              // set by any warp that produced a non-appended entry
+  unsigned int *gmin = reinterpret_cast<unsigned int *>(a.flag + 4); // 3 rotating words: first mover of a round
   int *nonapp_list = a.iscr + 6 * (long long)a.p; // CTA 0
   double maxH = 0.0;
   if (c.bid == 0 && tid == 0) {
@@ -175,6 +228,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     int start = 0;
     for (;;) {
       HEntry *hb = c.hbuf + (size_t)rp * c.CH;
+      const long long ta = clock64();
       // position j of the chunk belongs to CTA j % G, warp (j / G) % NV_W
       for (int j = c.bid + c.G * warp; j < qlen; j += c.G * NV_W) {
         if (j < start) continue;
@@ -189,25 +243,19 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
           __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
           __stcg(&hb[j].app, app);
           if (!app) __stcg(nonapp_flag, 1);
+          if (h != 0.0) atomicMin(gmin + round3, (unsigned int)j); // first position of the round that moves
         }
       }
+      const long long tb = clock64();
       c.grid.sync();
-      // first position >= start with h != 0
-      unsigned int best = 0xffffffffu;
-      for (int j = start + tid; j < qlen; j += NV_T) {
-        const double hj = __ldcg(&hb[j].h);
-        if (hj != 0.0) {
-          best = (unsigned int)j;
-          break;
-        }
-      }
-      best = __reduce_min_sync(0xffffffffu, best);
-      if (lane == 0) sm->redu[warp] = best;
-      __syncthreads();
-      unsigned int jmin = sm->redu[0];
-#pragma unroll
-      for (int i = 1; i < NV_W; ++i) jmin = min(jmin, sm->redu[i]);
-      __syncthreads();
+      const long long tc = clock64();
+      pf[0] += tb - ta;
+      pf[1] += tc - tb;
+      pf[7] += 1;
+      const unsigned int jmin = __ldcg(gmin + round3);
+      // the word used two rounds from now was last read before this barrier: reset it
+      if (c.bid == 0 && tid == 0) __stcg(gmin + (round3 + 2) % 3, 0xffffffffu);
+      round3 = (round3 + 1) % 3;
       rp ^= 1;
       if (c.bid == 0 && __ldcg(nonapp_flag)) { // rare: remember the finalised non-appended coordinates
         const int jend = jmin == 0xffffffffu ? qlen : (int)jmin;
@@ -216,6 +264,8 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
             nonapp_list[atomicAdd(&sm->nonapp, 1)] = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
         __syncthreads();
       }
+      const long long td = clock64();
+      pf[2] += td - tc;
       if (jmin == 0xffffffffu) break;
       const int k = ordered ? q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(q0 + jmin));
       const double2 e = __ldcg(reinterpret_cast<const double2 *>(hb + jmin));
@@ -232,6 +282,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
       maxH = fmax(maxH, fabs(h));
       accepted += 1;
       start = (int)jmin + 1;
+      pf[3] += clock64() - td;
       if (start >= qlen) break;
     }
   }
@@ -299,10 +350,15 @@ __device__ void active_phase(NCtx &c, double lam, long long maxPasses, unsigned 
         for (int off = tid * 128; off < n * 8; off += NV_T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nc + off));
       }
       double d = 0.0;
-      if (c.w) {
-        for (int t = tid; t < n; t += NV_T) d = fma(__ldg(col + t) * c.w[t], c.r[t], d);
-      } else {
-        for (int t = tid; t < n; t += NV_T) d = fma(__ldg(col + t), c.r[t], d);
+      for (int t0 = tid; t0 < n; t0 += 8 * NV_T) { // 8 independent loads in flight per thread
+        double xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = (t0 + u * NV_T < n) ? __ldg(col + t0 + u * NV_T) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + u * NV_T;
+          if (t < n) d = fma(c.w ? xv[u] * c.w[t] : xv[u], c.r[t], d);
+        }
       }
       d = block_sum(sm, d, 1);
       double nw, h;
@@ -393,7 +449,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   c.sm = reinterpret_cast<NSmem *>(smem_raw);
   double *sd = reinterpret_cast<double *>(smem_raw + (sizeof(NSmem) + 15) / 16 * 16);
   c.r = sd;
-  c.w = a.w ? sd + a.n : nullptr;
+  c.w = a.w ? sd + ((a.n + 1) & ~1) : nullptr; // keep w 16-byte aligned
   c.hbuf = hbuf;
   c.bc = bc;
   c.CH = CH;
@@ -408,7 +464,9 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   __syncthreads();
   c.rr = shared_sumsq(c);
 
-  int rp = 0;
+  long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = clock64();
+  int rp = 0, round3 = 0;
   unsigned long long pass_counter = 0;
   DevStats st;
   st.passes = st.full_passes = st.visits = st.accepted = 0;
@@ -439,8 +497,10 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           st.full_passes += 1;
           st.visits += a.p;
           const int m_old = c.sm->nact; // CTA 0
-          const double maxH = full_pass(c, lam, pass_counter, rp, st.accepted);
+          const double maxH = full_pass(c, lam, pass_counter, rp, round3, st.accepted, pf);
+          const long long t1 = clock64();
           if (c.bid == 0) list_update_full(c, m_old, pass_counter);
+          pf[4] += clock64() - t1;
           pass_counter += 1;
           st.maxH = maxH;
           conv = maxH < a.optTol;
@@ -449,7 +509,9 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
             break;
           }
         } else {
+          const long long t0 = clock64();
           if (c.bid == 0) active_phase(c, lam, a.maxIter - iter, pass_counter);
+          pf[5] += clock64() - t0;
           grid.sync();
           const long long np = __ldcg(&bc->npasses);
           if (c.bid != 0) {
@@ -509,6 +571,10 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
       if (tid == 0) a.scr[0] = sd;
     }
     if (tid == 0) {
+      if (a.prof) {
+        pf[6] = clock64() - t_start;
+        for (int i = 0; i < 10; ++i) a.prof[i] = pf[i];
+      }
       *a.nact = c.sm->nact;
       a.flag[0] = status;
       a.flag[1] = (int)cols_done;
@@ -635,7 +701,7 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
     CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
     attr_done = true;
   }
-  const size_t dyn = (sizeof(NSmem) + 15) / 16 * 16 + (size_t)a.n * sizeof(double) * (a.w ? 2 : 1);
+  const size_t dyn = (sizeof(NSmem) + 15) / 16 * 16 + (size_t)((a.n + 1) & ~1) * sizeof(double) * (a.w ? 2 : 1);
   if (dyn > max_dyn)
     return cdgpu_set_error(CDGPU_ECAP,
                            "naive-form sweep keeps r%s in shared memory: n = %d exceeds the %zu-byte limit; use the "

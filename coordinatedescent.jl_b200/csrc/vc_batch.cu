@@ -19,8 +19,8 @@
 
 namespace {
 
-constexpr int VC_T = 256;
-constexpr int VC_W = VC_T / 32;
+// threads per local problem: a single warp when n is small (no block-wide barriers on the per-step
+// chain, ~14 problems resident per SM), more warps for longer columns
 
 struct VcArgs {
   const double *X;
@@ -38,10 +38,11 @@ struct VcArgs {
   DevStats *stats;
 };
 
+constexpr int VC_WMAX = 8;
 struct VSm {
-  double red[VC_W];
-  double cand_h[VC_W], cand_nw[VC_W];
-  int cand_app[VC_W];
+  double red[VC_WMAX];
+  double cand_h[VC_WMAX], cand_nw[VC_WMAX];
+  int cand_app[VC_WMAX];
   int nact, flag, nonapp;
   int s2[2];
 };
@@ -52,8 +53,10 @@ __device__ __forceinline__ double ipow(double x, int l) {
   return v;
 }
 
+template <int VC_W>
 __device__ __forceinline__ double vblock_sum(VSm *sm, double v) {
   v = warp_sum(v);
+  if (VC_W == 1) return v;
   if ((threadIdx.x & 31) == 0) sm->red[threadIdx.x >> 5] = v;
   __syncthreads();
   double t = 0.0;
@@ -63,7 +66,9 @@ __device__ __forceinline__ double vblock_sum(VSm *sm, double v) {
   return t;
 }
 
+template <int VC_T>
 __global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
+  constexpr int VC_W = VC_T / 32;
   extern __shared__ __align__(16) unsigned char raw[];
   const int n = a.n, dg = a.degree + 1, ep = a.p * dg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
           const double *col = a.X + (long long)j * a.ldx;
           double d = 0.0;
           for (int i = tid; i < n; i += VC_T) d = fma(sr[i] * (__ldg(col + i) * ipow(sdz[i], l)), sw[i], d);
-          d = vblock_sum(sm, d);
+          d = vblock_sum<VC_W>(sm, d);
           const double ak = sa[k], old = sval[i_];
           const double v = __dadd_rn(old, d / ak);
           const double thr = __dmul_rn(__dmul_rn((double)n / ak, a.lambda0), sqrt(ak / (double)n));
@@ -274,6 +279,193 @@ __global__ void __launch_bounds__(VC_T) vc_kernel(const VcArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// One WARP per local problem, for n <= 32*NR: w, z - z0 and the residual live in REGISTERS (NR
+// values per lane), a visit is NR independent loads of the shared X column (L1/L2 resident), a
+// shuffle reduction and, when the coordinate moves, NR register FMAs.  No block barrier on the
+// per-step chain, ~10 KB of shared memory per problem (only the ep-sized iterate/list state), so
+// ~12 problems are resident per SM and X keeps most of L1.
+template <int NR>
+__global__ void __launch_bounds__(32) vc_warp_kernel(const VcArgs a) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  const int n = a.n, dg = a.degree + 1, ep = a.p * dg, lane = threadIdx.x;
+  double *sa = reinterpret_cast<double *>(raw);
+  double *sbeta = sa + ep, *sval = sbeta + ep, *stmpd = sval + ep;
+  int *sact = reinterpret_cast<int *>(stmpd + ep);
+  int *snewpos = sact + ep, *snonapp = snewpos + ep, *stmpi = snonapp + ep, *s2 = stmpi + 5 * ep;
+  unsigned char *sin = reinterpret_cast<unsigned char *>(s2 + 4);
+  const bool ordered = a.randomize == 0;
+
+  for (int g = a.g0 + blockIdx.x; g < a.g1; g += gridDim.x) {
+    const double z0 = a.zgrid[g];
+    double w[NR], dz[NR], r[NR];
+#pragma unroll
+    for (int t = 0; t < NR; ++t) {
+      const int i = lane + 32 * t;
+      w[t] = dz[t] = r[t] = 0.0;
+      if (i < n) {
+        const double zi = a.z[i];
+        if (a.kernel_kind == CDGPU_KERNEL_GAUSSIAN) {
+          const double d = zi - z0;
+          w[t] = exp(-(d * d) / a.bandwidth) / a.bandwidth;
+        } else {
+          const double u = (zi - z0) / a.bandwidth;
+          w[t] = fabs(u) >= 1.0 ? 0.0 : 0.75 * (1.0 - u * u) / a.bandwidth;
+        }
+        dz[t] = zi - z0;
+        r[t] = a.y[i];
+      }
+    }
+    __syncwarp();
+    for (int k = lane; k < ep; k += 32) {
+      sbeta[k] = 0.0;
+      sin[k] = 0;
+    }
+    // expanded column k = (j, l): e_t = X[i, j] * dz^l; returns sum_t w e r (dot) or sum_t w e^2 (norm)
+    auto column = [&](int k, double (&e)[NR]) {
+      const int j = k / dg, l = k - j * dg;
+      const double *col = a.X + (long long)j * a.ldx;
+#pragma unroll
+      for (int t = 0; t < NR; ++t) {
+        const int i = lane + 32 * t;
+        e[t] = i < n ? __ldg(col + i) : 0.0;
+      }
+      for (int q = 0; q < l; ++q) {
+#pragma unroll
+        for (int t = 0; t < NR; ++t) e[t] *= dz[t];
+      }
+    };
+    for (int k = 0; k < ep; ++k) {
+      double e[NR];
+      column(k, e);
+      double s = 0.0;
+#pragma unroll
+      for (int t = 0; t < NR; ++t) s = fma(w[t], e[t] * e[t], s);
+      s = warp_sum(s);
+      if (lane == 0) sa[k] = s;
+    }
+    int nact = 0;
+    __syncwarp();
+
+    DevStats st;
+    st.passes = st.full_passes = st.visits = st.accepted = 0;
+    st.maxH = 0.0;
+    st.converged = 0;
+    st.outer_iters = 0;
+    st.sigma = 0.0;
+    unsigned long long pass_counter = 0;
+    bool conv = true;
+    long long iter = 0;
+    // one visit of coordinate k whose current value is `old`; returns h (uniform across the warp)
+    auto visit = [&](int k, double old, double &nw, bool &tnz) -> double {
+      double e[NR];
+      column(k, e);
+      double d = 0.0;
+#pragma unroll
+      for (int t = 0; t < NR; ++t) d = fma(r[t] * e[t], w[t], d);
+      d = warp_sum(d);
+      const double ak = sa[k];
+      const double v = __dadd_rn(old, d / ak);
+      const double thr = __dmul_rn(__dmul_rn((double)n / ak, a.lambda0), sqrt(ak / (double)n));
+      nw = cd_shrink(v, thr);
+      tnz = v != 0.0;
+      const double h = nw - old;
+      if (h != 0.0) {
+#pragma unroll
+        for (int t = 0; t < NR; ++t) r[t] = __dsub_rn(r[t], __dmul_rn(e[t], h));
+      }
+      return h;
+    };
+    while (iter < a.maxIter) {
+      double maxH = 0.0;
+      iter += 1;
+      st.passes += 1;
+      if (conv) { // ---- full pass
+        st.full_passes += 1;
+        st.visits += ep;
+        const PermKey pk = cd_perm_key((uint32_t)ep, a.seed, pass_counter);
+        const int m_old = nact;
+        int nna = 0;
+        for (int q = 0; q < ep; ++q) {
+          const int k = ordered ? q : (int)cd_perm(pk, (uint32_t)q);
+          const double old = sbeta[k];
+          double nw;
+          bool tnz;
+          const double h = visit(k, old, nw, tnz);
+          const bool member = sin[k] != 0;
+          __syncwarp();
+          if (!tnz && !member) { // not appended by `x[k] += b/a` (rare)
+            if (lane == 0) snonapp[nna] = k;
+            nna += 1;
+          }
+          if (h != 0.0) {
+            if (lane == 0) {
+              sbeta[k] = nw;
+              if (!member) {
+                sin[k] = 1;
+                sact[nact] = k;
+              }
+            }
+            if (!member) nact += 1;
+            maxH = fmax(maxH, fabs(h));
+            st.accepted += 1;
+          }
+          __syncwarp();
+        }
+        for (int i = lane; i < nact; i += 32) sval[i] = sbeta[sact[i]];
+        for (int e = m_old + lane; e < nact; e += 32) {
+          const int k = sact[e];
+          const int vis = ordered ? k : (int)cd_perm_inv(pk, (uint32_t)k);
+          int before = 0;
+          for (int j = 0; j < m_old; ++j) before += (ordered ? sact[j] : (int)cd_perm_inv(pk, (uint32_t)sact[j])) < vis;
+          for (int j = 0; j < nna; ++j) before += (ordered ? snonapp[j] : (int)cd_perm_inv(pk, (uint32_t)snonapp[j])) < vis;
+          snewpos[e - m_old] = m_old + vis - before;
+        }
+        __syncwarp();
+        cd_compact_list<32>(sact, sval, m_old, nact, snewpos, sin, stmpi, stmpd, s2);
+        nact = s2[0];
+        __syncwarp();
+      } else { // ---- active-set pass
+        const int m = nact;
+        st.visits += m;
+        const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter);
+        for (int s = 0; s < m; ++s) {
+          const int i_ = ordered ? s : (int)cd_perm(pkm, (uint32_t)s);
+          const int k = sact[i_];
+          const double old = sval[i_];
+          double nw;
+          bool tnz;
+          const double h = visit(k, old, nw, tnz);
+          __syncwarp();
+          if (lane == 0) {
+            sval[i_] = nw;
+            sbeta[k] = nw;
+          }
+          if (h != 0.0) st.accepted += 1;
+          maxH = fmax(maxH, fabs(h));
+          __syncwarp();
+        }
+        cd_compact_list<32>(sact, sval, m, m, snewpos, sin, stmpi, stmpd, s2); // dropzeros!
+        nact = s2[0];
+        __syncwarp();
+      }
+      pass_counter += 1;
+      st.maxH = maxH;
+      const bool prev = conv;
+      conv = maxH < a.optTol;
+      if (prev && conv) {
+        st.converged = 1;
+        break;
+      }
+    }
+    double *col = a.out + (long long)g * ep;
+    for (int k = lane; k < ep; k += 32) col[k] = sbeta[k];
+    if (lane == 0 && a.stats) a.stats[g] = st;
+    __syncwarp();
+  }
+}
+
 } // namespace
 
 API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
@@ -297,7 +489,12 @@ API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
   CUDA_TRY(cudaSetDevice(device));
   const int64_t mloc = m_end - m_begin;
   if (mloc == 0) return CDGPU_OK;
-  const size_t dyn = (sizeof(VSm) + 15) / 16 * 16 + (size_t)(3 * n + 4 * ep) * sizeof(double) + (size_t)ep * (8 * 4 + 1) + 16;
+  int nr = n <= 128 ? 4 : (n <= 256 ? 8 : (n <= 512 ? 16 : 0)); // 0: CTA-per-problem kernel
+  if (const char *env = getenv("CDGPU_VC_THREADS")) nr = atoi(env) == 32 ? nr : 0;
+  const size_t dyn_cta = (sizeof(VSm) + 15) / 16 * 16 + (size_t)(3 * n + 4 * ep) * sizeof(double) + (size_t)ep * (8 * 4 + 1) + 16;
+  const size_t dyn_warp = (size_t)4 * ep * sizeof(double) + (size_t)(8 * ep + 4) * sizeof(int) + (size_t)ep + 16;
+  if (nr && dyn_warp > 227 * 1024) nr = 0;
+  const size_t dyn = nr ? dyn_warp : dyn_cta;
   if (dyn > 227 * 1024)
     return cdgpu_set_error(CDGPU_ECAP, "local problem does not fit in shared memory (n=%lld, ep=%lld)", (long long)n,
                            (long long)ep);
@@ -361,14 +558,27 @@ API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
   a.seed = opt->seed;
   a.out = dout;
   a.stats = dst;
-  VC_TRY(cudaFuncSetAttribute(vc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int VC_T = nr ? 32 : (n <= 1024 ? 64 : (n <= 4096 ? 128 : 256));
+  if (const char *env = getenv("CDGPU_VC_THREADS")) {
+    int v = atoi(env);
+    if (!nr && (v == 64 || v == 128 || v == 256)) VC_T = v;
+  }
+  const void *kfn = nr == 4    ? (const void *)vc_warp_kernel<4>
+                    : nr == 8  ? (const void *)vc_warp_kernel<8>
+                    : nr == 16 ? (const void *)vc_warp_kernel<16>
+                    : VC_T == 64 ? (const void *)vc_kernel<64>
+                    : VC_T == 128 ? (const void *)vc_kernel<128> : (const void *)vc_kernel<256>;
+  VC_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   int occ = 0, sms = 0;
-  VC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vc_kernel, VC_T, dyn));
+  VC_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, VC_T, dyn));
   VC_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   if (occ < 1) occ = 1;
   const int grid = (int)(mloc < (int64_t)occ * sms ? mloc : (int64_t)occ * sms);
   VC_TRY(cudaEventRecord(e0, s));
-  vc_kernel<<<grid, VC_T, dyn, s>>>(a);
+  {
+    void *kargs[] = {(void *)&a};
+    VC_TRY(cudaLaunchKernel(kfn, dim3(grid), dim3(VC_T), kargs, dyn, s));
+  }
   CD_COUNT_LAUNCH(1);
   VC_TRY(cudaGetLastError());
   VC_TRY(cudaEventRecord(e1, s));

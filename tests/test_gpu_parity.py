@@ -238,7 +238,9 @@ def test_gram_matches_and_is_symmetric(gpu, ref):
 
 @pytest.mark.parametrize("kernel,degree", [(GaussianKernel(0.2), 1), (GaussianKernel(0.2), 2),
                                            (EpanechnikovKernel(0.4), 1), (GaussianKernel(0.3), 0)])
-def test_locpolyl1_parity(gpu, ref, kernel, degree):
+def test_locpolyl1_parity(gpu, ref, kernel, degree, monkeypatch):
+    if degree == 2:  # exercise the CTA-per-problem kernel as well as the warp-per-problem one
+        monkeypatch.setenv("CDGPU_VC_THREADS", "128")
     rng = np.random.default_rng(81)
     n, p = 300, 12
     X = np.asfortranarray(rng.standard_normal((n, p)))
