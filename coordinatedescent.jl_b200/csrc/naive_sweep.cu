@@ -239,7 +239,8 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
           bool tnz;
           coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
                        c.rr, nw, h, tnz);
-          const int app = (tnz || __ldcg(a.inlist + k)) ? 1 : 0;
+          // sqrt-lasso never appends temporarily (x[k] = newVal, :278-283), so nothing to track there
+          const int app = (a.kind == CDGPU_LOSS_SQRT || tnz || __ldcg(a.inlist + k)) ? 1 : 0;
           __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
           __stcg(&hb[j].app, app);
           if (!app) __stcg(nonapp_flag, 1);
