@@ -421,8 +421,8 @@ class Backend:
         lam = np.ascontiguousarray(λpath, dtype=np.float64)
         m = lam.size
         cap = int(min(m * p, max(1 << 22, 4 * p)))
-        colptr, rowval = np.zeros(m + 1, dtype=np.int64), np.zeros(cap, dtype=np.int64)
-        nzval, done = np.zeros(cap), C.c_int64()
+        colptr, rowval = np.zeros(m + 1, dtype=np.int64), np.empty(cap, dtype=np.int64)
+        nzval, done = np.empty(cap), C.c_int64()
         stats = (_ffi.Stats * m)()
         mhs = -1 if math.isinf(max_hat_s) else int(max_hat_s)
         o = options.c()
@@ -436,10 +436,21 @@ class Backend:
             f.close()
         return LassoPath(lam[: done.value].copy(), βpath, [stats[i].as_dict() for i in range(done.value)])
 
+    # refitLassoPath(path, X, Y)                        lasso.jl:208-225
+    @staticmethod
+    def refitLassoPath(path: LassoPath, X, Y):
+        """OLS refit on each distinct support of the path: `X[:, S] \\ Y` (LAPACK on the host, as in the
+        reference — post-processing, not part of the CD hot path).  Keys are 0-based index tuples."""
+        X, Y = np.asarray(X), np.asarray(Y)
+        out = {}
+        for β in path.βpath:
+            S = tuple(int(k) for k in β.nonzero())
+            if S not in out:
+                out[S] = np.linalg.lstsq(X[:, list(S)], Y, rcond=None)[0] if S else np.zeros(0)
+        return out
+
     # locpolyl1(X, z, y, zgrid, degree, kernel, λ0, refit, options)  varying_coefficient_lasso.jl:30-79
     def locpolyl1(self, X, z, y, zgrid, degree, kernel, λ0, refit=False, options: CDOptions = None, shard=None):
-        if refit:
-            raise NotImplementedError("refit=true (varying_coefficient_lasso.jl:71-76) is not on the device yet")
         options = options or CDOptions()
         X, z, y, zgrid = f64(X), f64(z), f64(y), f64(zgrid)
         n, p = X.shape
@@ -454,7 +465,24 @@ class Backend:
                                          kernel.kind, float(kernel.h), float(λ0), C.byref(o), self.device, ptr(out),
                                          C.cast(stats, C.c_void_p)))
         self.last_vc_stats = [stats[i].as_dict() for i in range(lo, hi)]
-        return out, None
+        if not refit:
+            return out, None
+        # refit on the selected groups (varying_coefficient_lasso.jl:71-76, get_nonzero_coordinates! :488-512):
+        # weighted normal equations on the host (LAPACK `\`, as in the reference) — post-processing
+        outR = np.zeros_like(out)
+        dg = degree + 1
+        for g in range(lo, hi):
+            grp = np.flatnonzero(np.any(out[:, g].reshape(p, dg) != 0, axis=1))
+            if grp.size == 0:
+                continue
+            S = (grp[:, None] * dg + np.arange(dg)[None, :]).ravel()
+            d = z - zgrid[g]
+            w = np.exp(-d ** 2 / kernel.h) / kernel.h if kernel.kind == _ffi.KERNEL_GAUSSIAN else \
+                np.where(np.abs(d / kernel.h) >= 1, 0.0, 0.75 * (1 - (d / kernel.h) ** 2) / kernel.h)
+            Xs = np.stack([X[:, k // dg] * d ** (k % dg) for k in S], axis=1)
+            tmp = Xs.T * w
+            outR[S, g] = np.linalg.solve(tmp @ Xs, tmp @ y)
+        return out, outR
 
     def findLambdaMax(self, f: _Loss, ω=None) -> float:  # coordinate_descent.jl:118-149 at x = 0
         out = C.c_double()

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -788,6 +789,71 @@ API int cdgpu_path(cdgpu_handle h, const double *lambda, int64_t m, const double
   return st;
 }
 
+// _findInitSigma! (utils.jl:60-77): the s columns most correlated with y (device: |X'y|), a tiny
+// least-squares fit of y on them (host: Householder QR on n x s, as LAPACK's `\` does) and the
+// corrected standard deviation of its residuals.  One host round trip at initialisation only.
+static int screening_sigma(cdgpu_handle_s *h, int64_t sinit, double *sigma) {
+  const int64_t n = h->n, p = h->p;
+  int64_t s = sinit < 1 ? 1 : (sinit > p ? p : sinit);
+  double *dcorr = h->dscr + 8;
+  CD_TRY(launch_abs_xty(h, h->dX, h->ld, (int)n, (int)p, h->dy, dcorr));
+  std::vector<double> corr((size_t)p), y((size_t)n);
+  CUDA_TRY(cudaMemcpyAsync(corr.data(), dcorr, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(y.data(), h->dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  std::vector<double> sorted(corr);
+  std::nth_element(sorted.begin(), sorted.begin() + (s - 1), sorted.end(), [](double a, double b) { return a > b; });
+  const double thr = sorted[(size_t)s - 1]; // nlargest(s, storage)[end]
+  std::vector<int64_t> S;
+  for (int64_t j = 0; j < p; ++j)
+    if (corr[(size_t)j] >= thr) S.push_back(j); // storage .>= thr (ties may select more than s)
+  const int64_t cnt = (int64_t)S.size();
+  std::vector<double> Xs((size_t)(n * cnt)), Q, rhs(y), beta((size_t)cnt, 0.0);
+  for (int64_t q = 0; q < cnt; ++q)
+    CUDA_TRY(cudaMemcpyAsync(Xs.data() + q * n, h->dX + S[(size_t)q] * h->ld, (size_t)n * sizeof(double),
+                             cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  Q = Xs;
+  for (int64_t j = 0; j < cnt; ++j) { // Householder QR applied to [Q | rhs]
+    double *c = Q.data() + j * n;
+    double nrm = 0.0;
+    for (int64_t i = j; i < n; ++i) nrm += c[i] * c[i];
+    nrm = sqrt(nrm);
+    if (nrm == 0.0) continue;
+    const double alpha = c[j] > 0 ? -nrm : nrm;
+    const double v0 = c[j] - alpha;
+    double vn2 = v0 * v0;
+    for (int64_t i = j + 1; i < n; ++i) vn2 += c[i] * c[i];
+    c[j] = v0;
+    for (int64_t jj = j + 1; jj <= cnt; ++jj) {
+      double *t = jj < cnt ? Q.data() + jj * n : rhs.data();
+      double d = 0.0;
+      for (int64_t i = j; i < n; ++i) d += c[i] * t[i];
+      d = 2.0 * d / vn2;
+      for (int64_t i = j; i < n; ++i) t[i] -= d * c[i];
+    }
+    c[j] = alpha;
+  }
+  for (int64_t j = cnt - 1; j >= 0; --j) {
+    double v = rhs[(size_t)j];
+    for (int64_t jj = j + 1; jj < cnt; ++jj) v -= Q[(size_t)(j + jj * n)] * beta[(size_t)jj];
+    beta[(size_t)j] = v / Q[(size_t)(j + j * n)];
+  }
+  double mean = 0.0;
+  std::vector<double> r((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    double v = 0.0;
+    for (int64_t q = 0; q < cnt; ++q) v += Xs[(size_t)(i + q * n)] * beta[(size_t)q];
+    r[(size_t)i] = y[(size_t)i] - v;
+    mean += r[(size_t)i];
+  }
+  mean /= (double)n;
+  double var = 0.0;
+  for (int64_t i = 0; i < n; ++i) var += (r[(size_t)i] - mean) * (r[(size_t)i] - mean);
+  *sigma = sqrt(var / (double)(n - 1)); // Statistics.std
+  return CDGPU_OK;
+}
+
 API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, const cdgpu_iter_options *opt,
                            double *nzval, int64_t *nzval2ind, int64_t *nnz, double *sigma_out, cdgpu_stats *stats) {
   if (!h || !opt || !omega || !nzval || !nzval2ind || !nnz) return cdgpu_set_error(CDGPU_EARG, "null pointer");
@@ -797,10 +863,9 @@ API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, c
   if (opt->initProcedure != CDGPU_INIT_STD && opt->initProcedure != CDGPU_INIT_WARMSTART &&
       opt->initProcedure != CDGPU_INIT_SCREENING)
     return cdgpu_set_error(CDGPU_EARG, "ArgumentError: Incorrect initialization Symbol");
-  if (opt->initProcedure == CDGPU_INIT_SCREENING)
-    return cdgpu_set_error(CDGPU_EARG, ":Screening initialisation (utils.jl:60-124) is not on the device yet; use "
-                                       ":InitStd or :WarmStart");
   CUDA_TRY(cudaSetDevice(h->device));
+  double sigma0 = opt->sigma_init;
+  if (opt->initProcedure == CDGPU_INIT_SCREENING) CD_TRY(screening_sigma(h, opt->sinit, &sigma0));
   int rc;
   const double *domega = upload_omega(h, omega, &rc);
   CD_TRY(rc);
@@ -816,7 +881,7 @@ API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, c
   cfg.scaled = opt->initProcedure == CDGPU_INIT_WARMSTART ? 2 : 1; // 2: sigma0 = std(r) computed on the device
   cfg.outerMaxIter = opt->maxIter;
   cfg.outerTol = opt->optTol;
-  cfg.sigma0 = opt->sigma_init;
+  cfg.sigma0 = sigma0;
   CD_TRY(run_sweeps(h, cfg));
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   CD_TRY(flag_status(h, nullptr));

@@ -312,5 +312,6 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
 int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a); // r = y - X beta, beta dense, inlist
 int launch_colsq(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p, const double *w, double *out,
                  bool sqrt_over_n);
+int launch_abs_xty(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p, const double *y, double *out);
 int launch_lambda_max_naive(cdgpu_handle_s *h, int kind, const double *X, long long ldx, int n, int p, const double *y,
                             const double *w, const double *omega, double *scr, double *out);

@@ -31,11 +31,13 @@ constexpr int COV_T = 512;
 constexpr int COV_RMAX = 8;
 constexpr int COV_ACT_CAP = COV_T * COV_RMAX; // entries the in-CTA engine can hold
 constexpr int COV_MAXC = 16;
-constexpr unsigned long long KEY_NONE = ~0ull;
+constexpr unsigned KEY_NONE = 0xffffffffu;
 
-struct Cand {
-  unsigned long long key;
-  int k, pad;
+struct __align__(16) Cand { // 32 bytes = two st.async.v2.b64
+  unsigned key; // visit position of the coordinate (KEY_NONE: this slice has no mover)
+  int k;        // coordinate | member flag in bit 31
+  int pad;      // sender's count of visited-but-not-appended non-members (see full_pass)
+  int unused;
   double h, nw;
 };
 
@@ -47,12 +49,12 @@ struct Bcast { // CTA 0 -> cluster after an active phase / at the end of a lambd
 
 struct Smem {
   Cand cand[2][COV_MAXC];
-  Cand mine;
+  Cand wcand[COV_T / 32]; // per-warp best of the current scan
   Bcast bc;
-  unsigned long long red[COV_T / 32];
   double h[2];
   int nact, flag, nonapp;
   int s2[2];
+  unsigned long long mbar[2]; // candidate-exchange barriers (one per round parity)
 };
 
 __device__ __forceinline__ void named_bar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
@@ -78,113 +80,177 @@ __device__ __forceinline__ double slice_get(const Ctx &c, double *arr_local, int
   return __ldcg(arr_local - c.lo + k);
 }
 
+// ---------------------------------------------------------- DSMEM message passing --
+// The per-step candidate exchange of a full pass does not go through a cluster barrier (whose
+// release semantics cost a GPU-scope MEMBAR per round): every CTA pushes its 32-byte candidate into
+// each peer's shared memory with st.async, which also signals the peer's mbarrier (complete_tx);
+// a CTA only waits on its OWN mbarrier until all C candidates of the round have landed.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_16(uint32_t raddr, unsigned long long a, unsigned long long b, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+               "l"(a), "l"(b), "r"(rbar)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ full pass --
 // Returns max|h|.  On return CTA 0 holds the new entries appended (in visit order) behind the
 // m_old old ones in a.act; `nonapp_total` is the number of visited non-members whose tentative value
 // was exactly zero (they are NOT appended by the reference's setindex!; practically always 0).
-__device__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter, int &par, long long &accepted,
-                            bool first_pass_of_kernel, int &nonapp_total, long long *pf) {
+template <bool PROF>
+__device__ __forceinline__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter, unsigned &round,
+                                            long long &accepted, bool first_pass_of_kernel, int &nonapp_total,
+                                            long long *pf) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool ordered = a.randomize == 0;
   const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  // hot-loop state in registers
+  double *__restrict__ sAx = c.sAx;
+  const double *__restrict__ sb = c.sb, *__restrict__ sainv = c.sainv, *__restrict__ sw = c.sw;
+  double *__restrict__ sbeta = c.sbeta;
+  unsigned char *__restrict__ s_in = c.s_in, *__restrict__ s_vnz = c.s_vnz;
+  const int lo = c.lo, len = c.len, C = c.C, rank = c.rank;
+  const double *__restrict__ A = a.A;
+  const long long lda = a.lda;
   int cur = -1;          // ordered: last coordinate that moved
   long long curpos = -1; // random: its visit position
   double maxH = 0.0;
   // membership at the start of the pass (beta != 0, or an explicit zero handed in by the caller)
-  for (int i = tid; i < c.len; i += COV_T) {
-    c.s_in[i] = first_pass_of_kernel ? a.inlist[c.lo + i] : (unsigned char)(c.sbeta[i] != 0.0);
-    c.s_vnz[i] = 1;
+  for (int i = tid; i < len; i += COV_T) {
+    s_in[i] = first_pass_of_kernel ? a.inlist[lo + i] : (unsigned char)(sbeta[i] != 0.0);
+    s_vnz[i] = 1;
   }
   if (tid == 0) sm->nonapp = 0;
   __syncthreads();
   for (;;) {
-    const long long ta = clock64();
-    unsigned long long best = KEY_NONE;
-    int bk = -1;
+    const long long ta = PROF ? clock64() : 0;
+    const unsigned par = round & 1u, phase = (round >> 1) & 1u;
+    if (tid == 0) mbar_arrive_expect_tx(&sm->mbar[par], (uint32_t)(C * sizeof(Cand)));
+    unsigned best = KEY_NONE;
+    int bk = 0;
     double bh = 0.0, bnw = 0.0;
-    int i0 = ordered ? max(0, cur + 1 - c.lo) : 0;
-    for (int i = i0 + tid; i < c.len; i += COV_T) {
-      const int k = c.lo + i;
-      const unsigned long long key = ordered ? (unsigned long long)k : (unsigned long long)cd_perm_inv(pk, (uint32_t)k);
+    const int i0 = ordered ? max(0, cur + 1 - lo) : 0;
+    // every thread owns the slice elements tid, tid+T, ... in BOTH the scan and the update below, so no
+    // barrier is needed between a step and the next scan
+#pragma unroll 2
+    for (int i = tid; i < len; i += COV_T) {
+      if (i < i0) continue;
+      const unsigned key = ordered ? (unsigned)(lo + i) : cd_perm_inv(pk, (uint32_t)(lo + i));
       if (!ordered && (long long)key <= curpos) continue;
-      const double ainv = c.sainv[i];
-      const double g = c.sAx[i] + c.sb[i];
-      const double old = c.sbeta[i];
-      const double v = __dsub_rn(old, __dmul_rn(g, ainv));
-      const double thr = __dmul_rn(__dmul_rn(ainv, lam), c.sw[i]);
+      const double ainv = sainv[i];
+      const double g = sAx[i] + sb[i];
+      const double old = sbeta[i];
+      const double t = __dmul_rn(g, ainv);
+      const double thr = __dmul_rn(__dmul_rn(ainv, lam), sw[i]);
+      const bool member = s_in[i] != 0;
+      // short dependent chain for the common case (x_k == 0 stays 0): v = -t, and S(v, thr) != 0 <=> |t| > thr;
+      // t == 0 is the (practically impossible) "not appended" case tracked below
+      if (old == 0.0 && !(fabs(t) > thr) && t != 0.0 && s_vnz[i]) continue;
+      const double v = __dsub_rn(old, t);
       const double nw = cd_shrink(v, thr);
       const double h = nw - old;
       const unsigned char nz = (unsigned char)(v != 0.0); // `x[k] -= b*a` appends iff the value is non-zero
-      if (nz != c.s_vnz[i]) {
-        c.s_vnz[i] = nz;
-        if (!c.s_in[i]) atomicAdd(&sm->nonapp, nz ? -1 : 1);
+      if (nz != s_vnz[i]) {
+        s_vnz[i] = nz;
+        if (!member) atomicAdd(&sm->nonapp, nz ? -1 : 1);
       }
       if (h != 0.0 && key < best) {
         best = key;
-        bk = k;
+        bk = (lo + i) | (member ? (int)0x80000000 : 0);
         bh = h;
         bnw = nw;
       }
     }
-    unsigned long long wmin = warp_min_u64(best);
-    if (lane == 0) sm->red[warp] = wmin;
+    // block argmin with ONE barrier: every warp leaves its best candidate in shared memory, then warp 0
+    // alone picks the block's and pushes it to the peers; the other warps go straight to the wait.
+    const unsigned wmin = __reduce_min_sync(0xffffffffu, best);
+    if (best == wmin && (best != KEY_NONE || lane == 0)) { // positions are unique: one lane per warp
+      Cand &wc = sm->wcand[warp];
+      wc.key = best;
+      wc.k = bk;
+      wc.h = bh;
+      wc.nw = bnw;
+    }
     __syncthreads();
-    unsigned long long bmin = sm->red[0];
-#pragma unroll
-    for (int w = 1; w < COV_T / 32; ++w) bmin = sm->red[w] < bmin ? sm->red[w] : bmin;
-    if (bmin == KEY_NONE) {
-      if (tid == 0) {
-        sm->mine.key = KEY_NONE;
-        sm->mine.pad = sm->nonapp;
+    if (warp == 0) {
+      const unsigned mykey = lane < COV_T / 32 ? sm->wcand[lane].key : KEY_NONE;
+      const unsigned bmin = __reduce_min_sync(0xffffffffu, mykey);
+      const unsigned src = __ffs(__ballot_sync(0xffffffffu, mykey == bmin && lane < COV_T / 32)) - 1; // winning warp
+      if (lane < C) { // push the block's candidate into peer `lane`'s slot [par][rank] and signal its mbarrier
+        const Cand &bc = sm->wcand[src];
+        const unsigned long long w0 = (unsigned long long)bmin | ((unsigned long long)(unsigned)bc.k << 32);
+        const unsigned long long w1 = (unsigned long long)(unsigned)sm->nonapp;
+        const uint32_t slot = map_to_rank(smem_u32(&sm->cand[par][rank]), (uint32_t)lane);
+        const uint32_t rbar = map_to_rank(smem_u32(&sm->mbar[par]), (uint32_t)lane);
+        st_async_16(slot, w0, w1, rbar);
+        st_async_16(slot + 16, (unsigned long long)__double_as_longlong(bc.h), (unsigned long long)__double_as_longlong(bc.nw), rbar);
       }
-    } else if (best == bmin) {
-      sm->mine.key = best;
-      sm->mine.k = bk;
-      sm->mine.h = bh;
-      sm->mine.nw = bnw;
-      sm->mine.pad = sm->nonapp;
     }
-    __syncthreads();
-    if (tid < c.C) {
-      Cand *dst = c.cluster.map_shared_rank(&sm->cand[par][c.rank], tid);
-      *dst = sm->mine;
-    }
-    const long long tb = clock64();
-    c.cluster.sync();
-    const long long tc = clock64();
-    pf[7] += tb - ta;
-    pf[8] += tc - tb;
-    Cand w = sm->cand[par][0];
-    int napp = w.pad;
-    for (int q = 1; q < c.C; ++q) {
-      unsigned long long kq = sm->cand[par][q].key;
-      napp += sm->cand[par][q].pad;
-      if (kq < w.key) w = sm->cand[par][q];
-    }
-    par ^= 1;
+    const long long tb = PROF ? clock64() : 0;
+    mbar_wait(&sm->mbar[par], phase);
+    const long long tc = PROF ? clock64() : 0;
+    if (PROF) pf[7] += tb - ta;
+    if (PROF) pf[8] += tc - tb;
+    // every warp picks the cluster's winner lane-parallel: lane q looks at CTA q's candidate
+    const unsigned ckey = lane < C ? sm->cand[par][lane].key : KEY_NONE;
+    int napp = lane < C ? sm->cand[par][lane].pad : 0;
+    const unsigned wkey = __reduce_min_sync(0xffffffffu, ckey);
+    napp = __reduce_add_sync(0xffffffffu, napp);
+    const unsigned wsrc = __ffs(__ballot_sync(0xffffffffu, ckey == wkey && lane < C)) - 1;
+    Cand w = sm->cand[par][wsrc];
+    w.key = wkey;
+    round += 1;
     if (w.key == KEY_NONE) {
       nonapp_total = napp; // every slice's scan was final
       break;
     }
-    const int k = w.k;
-    if (tid == 0) {
-      if (k >= c.lo && k < c.lo + c.len) c.sbeta[k - c.lo] = w.nw;
-      if (c.rank == 0 && !a.inlist[k]) { // setindex! appends on the first non-zero store
-        a.inlist[k] = 1;
-        a.act[sm->nact] = k;
-        sm->nact += 1;
-      }
+    const int k = w.k & 0x7fffffff;
+    const bool wmember = w.k < 0;
+    // column slice first (independent loads in flight), then the shared-memory update
+    const double *col = A + (long long)k * lda + lo;
+    for (int i = tid; i < len; i += 4 * COV_T) {
+      double x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = (i + u * COV_T < len) ? __ldg(col + i + u * COV_T) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * COV_T < len) sAx[i + u * COV_T] = __dadd_rn(sAx[i + u * COV_T], __dmul_rn(x[u], w.h));
     }
-    const double *col = a.A + (long long)k * a.lda + c.lo;
-    for (int i = tid; i < c.len; i += COV_T) c.sAx[i] = __dadd_rn(c.sAx[i], __dmul_rn(__ldg(col + i), w.h));
+    if (k >= lo && k < lo + len && ((k - lo) % COV_T) == tid) { // the thread that scans this element
+      sbeta[k - lo] = w.nw;
+      s_in[k - lo] = 1;
+    }
+    if (rank == 0 && tid == 0 && !wmember) { // setindex! appends on the first non-zero store
+      a.act[sm->nact] = k;
+      sm->nact += 1;
+    }
     maxH = fmax(maxH, fabs(w.h));
     accepted += 1;
     cur = k;
     curpos = (long long)w.key;
-    __syncthreads();
-    pf[9] += clock64() - tc;
+    if (PROF) pf[9] += clock64() - tc;
   }
   return maxH;
 }
@@ -458,6 +524,7 @@ __device__ void refresh_slice(Ctx &c, int m0) {
   __syncthreads();
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int L, int slice_in_smem) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -511,13 +578,16 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   if (tid == 0) {
     c.sm->nact = (c.rank == 0) ? *a.nact : 0;
     c.sm->bc.status = 0;
+    mbar_init(&c.sm->mbar[0], 1);
+    mbar_init(&c.sm->mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   cluster.sync();
 
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const long long t_start = clock64();
-  int par = 0;
+  const long long t_start = PROF ? clock64() : 0;
+  unsigned round = 0; // candidate-exchange rounds so far (selects slot parity and mbarrier phase)
   bool first_pass = true;
   unsigned long long pass_counter = 0;
   DevStats st;
@@ -543,12 +613,12 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         st.visits += a.p;
         int nonapp_total = 0;
         const int m_old = c.sm->nact; // only meaningful on CTA 0
-        const long long t0 = clock64();
+        const long long t0 = PROF ? clock64() : 0;
         const long long acc0 = st.accepted;
-        const double maxH = full_pass(c, lam, pass_counter, par, st.accepted, first_pass, nonapp_total, pf);
-        const long long t1 = clock64();
-        pf[0] += t1 - t0;
-        pf[4] += st.accepted - acc0;
+        const double maxH = full_pass<PROF>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf);
+        const long long t1 = PROF ? clock64() : 0;
+        if (PROF) pf[0] += t1 - t0;
+        if (PROF) pf[4] += st.accepted - acc0;
         first_pass = false;
         if (nonapp_total > 0) { // rare slow path: collect the non-appended coordinates for CTA 0
           if (c.rank == 0 && tid == 0) a.flag[2] = 0;
@@ -557,7 +627,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           cluster.sync();
         }
         if (c.rank == 0) list_update_full(c, m_old, nonapp_total, pass_counter);
-        pf[1] += clock64() - t1;
+        if (PROF) pf[1] += clock64() - t1;
         pass_counter += 1;
         st.maxH = maxH;
         conv = maxH < a.optTol;
@@ -566,7 +636,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           break;
         }
       } else {
-        const long long t0 = clock64();
+        const long long t0 = PROF ? clock64() : 0;
         if (c.rank == 0) {
           const int m = c.sm->nact;
           const long long budget = a.maxIter - iter;
@@ -584,8 +654,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           }
         }
         cluster.sync();
-        const long long t1 = clock64();
-        pf[2] += t1 - t0;
+        const long long t1 = PROF ? clock64() : 0;
+        if (PROF) pf[2] += t1 - t0;
         const Bcast *bc = cluster.map_shared_rank(&c.sm->bc, 0);
         const Bcast b = *bc;
         if (b.status) {
@@ -593,8 +663,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           break;
         }
         refresh_slice(c, b.m0);
-        pf[3] += clock64() - t1;
-        pf[5] += b.visits;
+        if (PROF) pf[3] += clock64() - t1;
+        if (PROF) pf[5] += b.visits;
         iter += b.npasses;
         pass_counter += b.npasses;
         st.passes += b.npasses;
@@ -767,8 +837,10 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   const size_t fixed = (sizeof(Smem) + 15) / 16 * 16 + COV_ACT_CAP * (2 * sizeof(int));
   const size_t max_dyn = 227 * 1024;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
-    CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_done = true;
   }
   // largest cluster the device will co-schedule (16 on B200 with the opt-in, else 8)
@@ -787,7 +859,7 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
       cfg.attrs = at;
       cfg.numAttrs = 1;
       int ncl = 0;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, cov_path_kernel, &cfg);
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, cov_path_kernel<false>, &cfg);
       if (e == cudaSuccess && ncl >= 1) {
         C = cand;
         break;
@@ -819,7 +891,10 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel, a, L, slice_in_smem));
+  if (a.prof)
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<true>, a, L, slice_in_smem));
+  else
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<false>, a, L, slice_in_smem));
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }

@@ -7,6 +7,9 @@
 //     by BK = 16 rows, i.e. 128 runs of 128 contiguous bytes -> 16-byte cp.async (LDGSTS), 4 stages.
 //   * CTA tile 128 x 128, 8 warps as 2 x 4, warp tile 64 x 32 = 8 x 4 DMMA fragments (64 accumulator
 //     doubles / thread).  Shared rows are padded to 20 doubles so fragment loads are conflict free.
+//   * operand fragments are double-buffered in registers ACROSS the k-tile barrier (the wait covers two
+//     stages), so the DMMA pipe does not drain at each __syncthreads: 128.6 ms -> 113.4 ms at C2
+//     (85 % -> ~99 % of the cuBLAS Dgemm rate).  CDGPU_GRAM_VARIANT selects the other tilings tried.
 //   * only tiles on or below the diagonal are computed; the epilogue writes acc/n to (i,j) and the
 //     same value to (j,i), so issymmetric(G) (cd_differentiable_function.jl:306) holds bit for bit.
 //   * persistent CTAs walk a host-built tile list ordered in 12 x 12 super-tiles so the ~148 tiles in
@@ -19,8 +22,7 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, LDK = 20, STAGES = 4, GT = 256;
-constexpr int STAGE_DOUBLES = (BM + BN) * LDK;
+constexpr int BM = 128, BN = 128;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -41,16 +43,17 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-// load one stage: rows (columns of X) [col0, col0+128) x k in [k0, k0+16) into dst[128][LDK]
-template <bool ALIGNED16>
+// load one stage: rows (columns of X) [col0, col0+128) x k in [k0, k0+BK) into dst[128][LDK]
+template <bool ALIGNED16, int BK, int LDK, int GT>
 __device__ __forceinline__ void load_tile(double *dst, const double *X, long long ldx, long long n, int p, int col0,
                                           long long k0, int tid) {
   if (ALIGNED16) {
-    // 128 rows x 8 chunks of 16 B; 256 threads -> 4 chunks each
+    constexpr int CPR = BK / 2; // 16-byte chunks per row
+    constexpr int ITERS = (128 * CPR) / GT;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const int idx = tid + it * GT;
-      const int row = idx >> 3, ch = idx & 7;
+      const int row = idx / CPR, ch = idx % CPR;
       const int col = col0 + row;
       const long long k = k0 + ch * 2;
       int bytes = 0;
@@ -59,10 +62,11 @@ __device__ __forceinline__ void load_tile(double *dst, const double *X, long lon
       cp_async16(dst + row * LDK + ch * 2, src, bytes);
     }
   } else {
+    constexpr int ITERS = (128 * BK) / GT;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const int idx = tid + it * GT;
-      const int row = idx >> 4, ch = idx & 15;
+      const int row = idx / BK, ch = idx % BK;
       const int col = col0 + row;
       const long long k = k0 + ch;
       const int bytes = (col < p && k < n) ? 8 : 0;
@@ -72,60 +76,106 @@ __device__ __forceinline__ void load_tile(double *dst, const double *X, long lon
   }
 }
 
-template <bool ALIGNED16>
-__global__ void __launch_bounds__(GT, 1)
+// WM x WN warps; warp tile (128/WM) x (128/WN) = MI x NI fragments of 8 x 8
+template <bool ALIGNED16, int WM, int WN, int BK, int STAGES, bool PIPE>
+__global__ void __launch_bounds__(WM *WN * 32, 1)
     gram_syrk_kernel(const double *__restrict__ X, long long n, int p, long long ldx, double *__restrict__ G,
                      long long ldg, const int2 *__restrict__ tiles, int ntiles, double divisor, int do_scale) {
+  constexpr int GT = WM * WN * 32, LDK = BK + 4, STAGE_DOUBLES = (BM + BN) * LDK;
+  constexpr int MI = BM / (WM * 8), NI = BN / (WN * 8);
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3; // 2 x 4 warps
+  const int wm = warp / WN, wn = warp % WN;
   const int g = lane >> 2, q = lane & 3;
   const long long nK = (n + BK - 1) / BK;
 
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int bi = tiles[t].x, bj = tiles[t].y; // bi >= bj
     const int colA = bi * BM, colB = bj * BN;
-    double acc[8][4][2];
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // prologue
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       if (s < nK) {
         double *st = smem + s * STAGE_DOUBLES;
-        load_tile<ALIGNED16>(st, X, ldx, n, p, colA, (long long)s * BK, tid);
-        load_tile<ALIGNED16>(st + BM * LDK, X, ldx, n, p, colB, (long long)s * BK, tid);
+        load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, (long long)s * BK, tid);
+        load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, X, ldx, n, p, colB, (long long)s * BK, tid);
       }
       cp_commit();
     }
-    for (long long kt = 0; kt < nK; ++kt) {
+    if (!PIPE) {
+      for (long long kt = 0; kt < nK; ++kt) {
+        cp_wait<STAGES - 2>();
+        __syncthreads();
+        { // prefetch stage kt + STAGES - 1 into the slot freed by iteration kt - 1
+          const long long kn = kt + STAGES - 1;
+          if (kn < nK) {
+            double *st = smem + (kn % STAGES) * STAGE_DOUBLES;
+            load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, kn * BK, tid);
+            load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, X, ldx, n, p, colB, kn * BK, tid);
+          }
+          cp_commit();
+        }
+        const double *As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * MI * 8) * LDK;
+        const double *Bs = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDK + (wn * NI * 8) * LDK;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+          double af[MI], bf[NI];
+#pragma unroll
+          for (int i = 0; i < MI; ++i) af[i] = As[(i * 8 + g) * LDK + kk + q];
+#pragma unroll
+          for (int j = 0; j < NI; ++j) bf[j] = Bs[(j * 8 + g) * LDK + kk + q];
+#pragma unroll
+          for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      }
+    } else {
+      // Register double-buffered fragments carried ACROSS the k-tile barrier: the wait at the top of
+      // iteration kt covers stages kt and kt+1, so the first fragments of tile kt+1 are loaded while the
+      // last DMMAs of tile kt issue, and the tensor pipe does not drain at every __syncthreads.
+      double af[2][MI], bf[2][NI];
+      auto load_frag = [&](int buf, long long kt, int kk) {
+        const double *As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * MI * 8) * LDK;
+        const double *Bs = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDK + (wn * NI * 8) * LDK;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) af[buf][i] = As[(i * 8 + g) * LDK + kk + q];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) bf[buf][j] = Bs[(j * 8 + g) * LDK + kk + q];
+      };
       cp_wait<STAGES - 2>();
       __syncthreads();
-      { // prefetch stage kt + STAGES - 1 into the slot freed by iteration kt - 1
-        const long long kn = kt + STAGES - 1;
-        if (kn < nK) {
-          double *st = smem + (kn % STAGES) * STAGE_DOUBLES;
-          load_tile<ALIGNED16>(st, X, ldx, n, p, colA, kn * BK, tid);
-          load_tile<ALIGNED16>(st + BM * LDK, X, ldx, n, p, colB, kn * BK, tid);
+      load_frag(0, 0, 0);
+      for (long long kt = 0; kt < nK; ++kt) {
+        cp_wait<(STAGES >= 3 ? STAGES - 3 : 0)>(); // stages kt and kt+1 have landed (this thread's part)
+        __syncthreads();                           // ... and everyone's; slot of tile kt-1 is free
+        {
+          const long long kn = kt + STAGES - 1;
+          if (kn < nK) {
+            double *st = smem + (kn % STAGES) * STAGE_DOUBLES;
+            load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, kn * BK, tid);
+            load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, X, ldx, n, p, colB, kn * BK, tid);
+          }
+          cp_commit();
         }
-        cp_commit();
-      }
-      const double *As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * 64) * LDK;
-      const double *Bs = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDK + (wn * 32) * LDK;
 #pragma unroll
-      for (int kk = 0; kk < BK; kk += 4) {
-        double af[8], bf[4];
+        for (int ks = 0; ks < BK / 4; ++ks) {
+          const int cur = ks & 1;
+          if (ks + 1 < BK / 4)
+            load_frag(cur ^ 1, kt, (ks + 1) * 4);
+          else if (kt + 1 < nK)
+            load_frag(cur ^ 1, kt + 1, 0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) af[i] = As[(i * 8 + g) * LDK + kk + q];
+          for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = Bs[(j * 8 + g) * LDK + kk + q];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            for (int j = 0; j < NI; ++j) dmma(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+        }
       }
     }
     cp_wait<0>();
@@ -133,11 +183,11 @@ __global__ void __launch_bounds__(GT, 1)
 
     // epilogue: G[colA + m, colB + nn] and its mirror
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = colA + wm * 64 + i * 8 + g;
+    for (int i = 0; i < MI; ++i) {
+      const int row = colA + wm * MI * 8 + i * 8 + g;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = colB + wn * 32 + j * 8 + 2 * q;
+      for (int j = 0; j < NI; ++j) {
+        const int col = colB + wn * NI * 8 + j * 8 + 2 * q;
         double v0 = acc[i][j][0], v1 = acc[i][j][1];
         if (do_scale) {
           v0 = v0 / divisor;
@@ -210,21 +260,41 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
   CUDA_TRY(cudaMallocAsync((void **)&dtiles, (size_t)ntiles * sizeof(int2), h->stream));
   CUDA_TRY(cudaMemcpyAsync(dtiles, tiles.data(), (size_t)ntiles * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream)); // `tiles` is a host temporary
-  const size_t dyn = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
   const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
   const long long ldg = ((long long)p + 1) & ~1ll;
   const int grid = min(ntiles, h->sm_count);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(gram_syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    CUDA_TRY(cudaFuncSetAttribute(gram_syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    attr_done = true;
-  }
-  if (aligned)
-    gram_syrk_kernel<true><<<grid, GT, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, scale ? 1 : 0);
+  int variant = 5; // 2x4 warps, BK 16, 4 stages, fragments double-buffered across the k-tile barrier
+  if (const char *env = getenv("CDGPU_GRAM_VARIANT")) variant = atoi(env);
+  auto launch = [&](auto kern, int threads, size_t dyn) -> int {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<grid, threads, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, scale ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return CDGPU_OK;
+  };
+#define GRAM_DYN(BK, ST) ((size_t)(ST) * (BM + BN) * ((BK) + 4) * sizeof(double))
+  int rc;
+  if (!aligned)
+    rc = launch(gram_syrk_kernel<false, 2, 4, 16, 4, false>, 256, GRAM_DYN(16, 4));
+  else if (variant == 1)
+    rc = launch(gram_syrk_kernel<true, 4, 4, 16, 4, false>, 512, GRAM_DYN(16, 4));
+  else if (variant == 2)
+    rc = launch(gram_syrk_kernel<true, 4, 4, 32, 3, false>, 512, GRAM_DYN(32, 3));
+  else if (variant == 3)
+    rc = launch(gram_syrk_kernel<true, 2, 4, 32, 3, false>, 256, GRAM_DYN(32, 3));
+  else if (variant == 5)
+    rc = launch(gram_syrk_kernel<true, 2, 4, 16, 4, true>, 256, GRAM_DYN(16, 4));
+  else if (variant == 6)
+    rc = launch(gram_syrk_kernel<true, 2, 4, 32, 3, true>, 256, GRAM_DYN(32, 3));
+  else if (variant == 7)
+    rc = launch(gram_syrk_kernel<true, 2, 4, 16, 5, true>, 256, GRAM_DYN(16, 5));
+  else if (variant == 4)
+    rc = launch(gram_syrk_kernel<true, 4, 2, 16, 4, false>, 256, GRAM_DYN(16, 4));
+  else if (variant == 0)
+    rc = launch(gram_syrk_kernel<true, 2, 4, 16, 4, false>, 256, GRAM_DYN(16, 4));
   else
-    gram_syrk_kernel<false><<<grid, GT, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, scale ? 1 : 0);
-  CUDA_TRY(cudaGetLastError());
+    rc = launch(gram_syrk_kernel<true, 2, 4, 16, 4, true>, 256, GRAM_DYN(16, 4));
+#undef GRAM_DYN
+  CD_TRY(rc);
   xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, c, divisor, scale ? 1 : 0);
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(2);

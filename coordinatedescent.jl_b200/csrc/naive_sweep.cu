@@ -645,7 +645,7 @@ __global__ void grad0_kernel(int kind, const double *X, long long ldx, int n, in
       for (int i = lane; i < n; i += 32) s = fma(col[i], y[i], s);
     s = warp_sum(s);
     if (lane == 0) {
-      double t = fabs(kind == CDGPU_LOSS_SQRT ? s / ynorm : s / (double)n);
+      double t = kind < 0 ? fabs(s) : fabs(kind == CDGPU_LOSS_SQRT ? s / ynorm : s / (double)n);
       if (omega) t = t / omega[k];
       out[k] = t;
     }
@@ -671,6 +671,15 @@ int launch_colsq(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p
                  bool sqrt_over_n) {
   int blocks = min((p + 7) / 8, h->sm_count * 8);
   colsq_kernel<<<max(blocks, 1), 256, 0, h->stream>>>(X, ldx, n, p, w, out, sqrt_over_n ? 1 : 0);
+  CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
+  return CDGPU_OK;
+}
+
+// |X_j'y| for every column (the screening statistic of _findLargestCorrelations, utils.jl:96-107)
+int launch_abs_xty(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p, const double *y, double *out) {
+  int blocks = min((p + 7) / 8, h->sm_count * 8);
+  grad0_kernel<<<max(blocks, 1), 256, 0, h->stream>>>(-1, X, ldx, n, p, y, nullptr, nullptr, out);
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;

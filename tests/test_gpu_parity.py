@@ -196,7 +196,7 @@ def test_front_ends(gpu, ref):
     assert gpu.lasso(X, y, lam).x.nnz == 0
 
 
-@pytest.mark.parametrize("init", ["InitStd", "WarmStart"])
+@pytest.mark.parametrize("init", ["InitStd", "WarmStart", "Screening"])
 def test_scaled_lasso_parity(gpu, ref, init):
     n, p, s = 600, 400, 15
     X, y, _ = gauss_problem(n, p, s, seed=61)
@@ -259,6 +259,26 @@ def test_locpolyl1_parity(gpu, ref, kernel, degree, monkeypatch):
     a, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, kernel, 0.02, False, o, shard=(0, 12))
     b, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, kernel, 0.02, False, o, shard=(12, 24))
     assert np.array_equal(a[:, :12], og[:, :12]) and np.array_equal(b[:, 12:], og[:, 12:])
+
+
+def test_refit_next_tier(gpu, ref):
+    # test/lasso.jl:236-241: refitLassoPath == X[:, S] \\ Y on every distinct support
+    n, p, s = 400, 120, 8
+    X, y, _ = gauss_problem(n, p, s, seed=91)
+    o = CDOptions(randomize=False, **TIGHT)
+    path = gpu.LassoPath(X, y, [0.3, 0.1], o, standardizeX=False)
+    rf = gpu.refitLassoPath(path, X, y)
+    for β in path.βpath:
+        S = tuple(β.nonzero())
+        assert np.allclose(rf[S], np.linalg.lstsq(X[:, list(S)], y, rcond=None)[0], atol=1e-10)
+    # locpolyl1(refit=true): refitted coefficients solve the weighted normal equations on the selected groups
+    rng = np.random.default_rng(92)
+    Xs = np.asfortranarray(rng.standard_normal((200, 6)))
+    Z = rng.random(200)
+    Y = np.sin(4 * Z) * Xs[:, 0] + 0.1 * rng.standard_normal(200)
+    out, outR = gpu.locpolyl1(Xs, Z, Y, np.array([0.3, 0.6]), 1, GaussianKernel(0.2), 0.05, True, o)
+    assert outR.shape == out.shape and np.count_nonzero(outR) >= np.count_nonzero(out) > 0
+    assert np.array_equal(np.any(outR.reshape(6, 2, 2) != 0, axis=1), np.any(out.reshape(6, 2, 2) != 0, axis=1))
 
 
 def test_errors_match_reference(gpu):
