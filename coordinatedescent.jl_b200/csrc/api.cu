@@ -110,7 +110,7 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   CD_TRY(dalloc(&h->dnact, 1));
   CD_TRY(dalloc(&h->dinlist, p));
   CD_TRY(dalloc(&h->domega, p));
-  CD_TRY(dalloc(&h->dscr, 12 * p + 8 * (size_t)h->n + 64));
+  CD_TRY(dalloc(&h->dscr, 12 * p + 8 * (size_t)h->n + 64 + 4 * 2048 + 64));
   CD_TRY(dalloc(&h->discr, 8 * p + 64));
   CD_TRY(dalloc(&h->dbscr, 2 * p + 64));
   CD_TRY(dalloc(&h->dflag, 8));
@@ -142,6 +142,7 @@ API int cdgpu_destroy(cdgpu_handle h) {
   dfree(h->dscr);
   dfree(h->discr);
   dfree(h->dbscr);
+  dfree(h->dgram);
   dfree(h->dstats);
   dfree(h->dlam);
   dfree(h->dcolptr);
@@ -647,6 +648,8 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.capacity = rc.capacity;
     a.flag = h->dflag;
     a.stats = h->dstats;
+    if (!h->dgram && !getenv("CDGPU_NAIVE_NO_GRAM_ENGINE")) CD_TRY(dalloc(&h->dgram, (size_t)2048 * 2048 + 2048));
+    a.gram = getenv("CDGPU_NAIVE_NO_GRAM_ENGINE") ? nullptr : h->dgram;
     a.scaled = rc.scaled;
     a.outerMaxIter = rc.outerMaxIter;
     a.outerTol = rc.outerTol;

@@ -219,6 +219,7 @@ struct cdgpu_handle_s {
   double *dscr = nullptr;           // 12 * p + 8 * n doubles
   int *discr = nullptr;             // 8 * p ints
   unsigned char *dbscr = nullptr;   // 2 * p bytes
+  double *dgram = nullptr;          // naive handles: active-set Gram scratch (allocated at first solve)
   DevStats *dstats = nullptr;       // path stats, grown on demand
   int64_t nstats = 0;
   double *dlam = nullptr;
@@ -307,6 +308,7 @@ struct NaiveArgs {
   long long outerMaxIter;
   double outerTol, sigma0;
   long long *prof; // optional [10]: SM cycles per phase on CTA 0 (CDGPU_PROFILE=1)
+  double *gram;    // scratch for the covariance-form active engine: 2048*2048 + 2048 doubles (or null)
 };
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
 int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a); // r = y - X beta, beta dense, inlist

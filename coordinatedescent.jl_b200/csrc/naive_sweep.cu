@@ -27,6 +27,7 @@ namespace {
 
 constexpr int NV_T = 512;
 constexpr int NV_W = NV_T / 32;
+constexpr int NV_GCAP_ = 2048; // == NV_GCAP below
 
 struct __align__(16) HEntry {
   double h, nw;
@@ -43,7 +44,7 @@ struct NBcast {
 struct NSmem {
   double red[2][NV_W];
   unsigned int redu[NV_W];
-  double bval[2];
+  double bval[2], bval2[2];
   int nact, flag, nonapp;
   int s2[2];
 };
@@ -56,6 +57,7 @@ struct NCtx {
   double rr;     // ||r||^2 (every thread of every CTA holds the same value)
   HEntry *hbuf;  // global, 2 * CH
   NBcast *bc;    // global
+  int *s_act, *s_g, *s_idx; // shared, NV_GCAP ints each: scratch of the covariance-form active engine
   int CH, G, bid;
 };
 
@@ -209,7 +211,7 @@ __device__ __forceinline__ void apply_step(NCtx &c, const double *col, double h)
 
 // ------------------------------------------------------------------ full pass --
 __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter, int &rp, int &round3,
-                            long long &accepted, long long *pf) {
+                            long long &accepted, long long *pf, int nact_hint) {
   const NaiveArgs &a = c.a;
   NSmem *sm = c.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -223,8 +225,13 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     sm->nonapp = 0;
     __stcg(nonapp_flag, 0);
   }
-  for (int q0 = 0; q0 < a.p; q0 += c.CH) {
-    const int qlen = min(c.CH, a.p - q0);
+  // chunk length: every mover costs a re-evaluation of the rest of its chunk (~CH/2 columns) and every chunk
+  // a grid barrier, so CH ~ sqrt(2 p T_sync / (E T_col)) with E ~ current active-set size movers per pass,
+  // T_sync ~ 2.5 us, T_col ~ 8n B / 4 TB/s
+  int CHp = (int)sqrt(2.5e6 * (double)a.p / ((double)(nact_hint + 4) * (double)a.n));
+  CHp = max(min(CHp, c.CH), min(c.CH, 64));
+  for (int q0 = 0; q0 < a.p; q0 += CHp) {
+    const int qlen = min(CHp, a.p - q0);
     int start = 0;
     for (;;) {
       HEntry *hb = c.hbuf + (size_t)rp * c.CH;
@@ -423,6 +430,293 @@ __device__ void active_phase(NCtx &c, double lam, long long maxPasses, unsigned 
   __syncthreads();
 }
 
+// ------------------------------------------------- active-set passes in covariance form --
+// An active-set pass only touches the m active columns, and X_k'(w.r) for k in the set obeys
+// d_t -= G_tk h with G = X_A' diag(w) X_A.  So the whole grid forms G (m x m) and d = X_A'(w.r) once per
+// active phase (m(m+1)/2 + m dot products, one warp each, columns are L2 hot), CTA 0 then runs the
+// sequential chain with one register-resident entry per thread, one named barrier per coordinate
+// step and the G column gathers prefetched two steps ahead (no O(n) work per step at all), and
+// finally r -= X_A (beta - beta_at_entry) is applied once.  Same iterates as the reference up to
+// rounding (d maintained incrementally instead of re-reduced); same visit order and list semantics.
+constexpr int NV_GCAP = NV_GCAP_; // largest active set handled this way (G scratch = 32 MB)
+constexpr int NV_RMAX = NV_GCAP / NV_T;
+
+__device__ __forceinline__ void nbar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
+
+// all CTAs: G[i + j*m] = sum_t w_t X[t,act_i] X[t,act_j] (both triangles), d[i] = sum_t w_t r_t X[t,act_i]
+__device__ void build_active_gram(NCtx &c, int m, double *G, double *d) {
+  const NaiveArgs &a = c.a;
+  const int lane = threadIdx.x & 31, n = a.n;
+  const long long gw = (long long)c.bid * NV_W + (threadIdx.x >> 5), nw = (long long)c.G * NV_W;
+  const long long npair = (long long)m * (m + 1) / 2;
+  for (long long idx = gw; idx < npair + m; idx += nw) {
+    if (idx >= npair) { // d entry
+      const int i = (int)(idx - npair);
+      const double v = warp_col_dot(c, a.X + (long long)__ldcg(a.act + i) * a.ldx);
+      if (lane == 0) __stcg(d + i, v);
+      continue;
+    }
+    // idx -> (i, j), j <= i, row-major over the lower triangle
+    int i = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while ((long long)i * (i + 1) / 2 > idx) --i;
+    while ((long long)(i + 1) * (i + 2) / 2 <= idx) ++i;
+    const int j = (int)(idx - (long long)i * (i + 1) / 2);
+    const double *ci = a.X + (long long)__ldcg(a.act + i) * a.ldx, *cj = a.X + (long long)__ldcg(a.act + j) * a.ldx;
+    double s0 = 0.0, s1 = 0.0;
+    if (c.w) {
+      int t = lane;
+      for (; t + 32 < n; t += 64) {
+        s0 = fma(__ldg(ci + t) * c.w[t], __ldg(cj + t), s0);
+        s1 = fma(__ldg(ci + t + 32) * c.w[t + 32], __ldg(cj + t + 32), s1);
+      }
+      for (; t < n; t += 32) s0 = fma(__ldg(ci + t) * c.w[t], __ldg(cj + t), s0);
+    } else {
+      int t = lane;
+      for (; t + 32 < n; t += 64) {
+        s0 = fma(__ldg(ci + t), __ldg(cj + t), s0);
+        s1 = fma(__ldg(ci + t + 32), __ldg(cj + t + 32), s1);
+      }
+      for (; t < n; t += 32) s0 = fma(__ldg(ci + t), __ldg(cj + t), s0);
+    }
+    const double v = warp_sum(s0 + s1);
+    if (lane == 0) {
+      __stcg(G + i + (long long)j * m, v);
+      __stcg(G + j + (long long)i * m, v);
+    }
+  }
+}
+
+template <int R>
+__device__ void gram_engine(NCtx &c, double lam, long long maxPasses, unsigned long long pass_counter, int m0,
+                            const double *G, const double *d0, int *s_act, int *s_g, int *s_idx) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x, n = a.n;
+  const bool ordered = a.randomize == 0, is_sqrt = a.kind == CDGPU_LOSS_SQRT;
+  int m = m0;
+  int per = (m + R - 1) / R;
+  int nthr = min(NV_T, ((per + 31) / 32) * 32);
+  if (nthr < 32) nthr = 32;
+  double *scr_b0 = a.scr + 8 + 9 * (long long)a.p + 32; // [<= NV_GCAP] each, behind the compaction staging
+  double *scr_dlt = scr_b0 + NV_GCAP, *scr_d = scr_dlt + NV_GCAP, *scr_be = scr_d + NV_GCAP;
+  int *act0 = a.iscr; // snapshot of the list
+
+  int kk[R], gi[R];
+  double dd[R], be[R], aa[R], th[R], gcur[R], gnxt[R];
+  const bool part = tid < nthr;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = r * nthr + tid;
+    kk[r] = -1;
+    gi[r] = 0;
+    dd[r] = be[r] = aa[r] = th[r] = gcur[r] = gnxt[r] = 0.0;
+    if (part && i < m) {
+      const int k = a.act[i];
+      kk[r] = k;
+      gi[r] = i;
+      be[r] = a.actval[i];
+      dd[r] = __ldcg(d0 + i);
+      aa[r] = __ldg(a.colsq + k);
+      const double om = a.omega ? __ldg(a.omega + k) : 1.0;
+      th[r] = is_sqrt ? lam * om : __dmul_rn(__dmul_rn((double)n / aa[r], lam), om);
+      s_act[i] = k;
+      s_g[i] = i;
+      act0[i] = k;
+      scr_b0[i] = be[r];
+    }
+  }
+  double rr = c.rr; // sqrt-lasso: ||r||^2, tracked by every participating thread
+  __syncthreads();
+
+  long long npasses = 0, visits = 0, accepted = 0;
+  double maxH = 0.0;
+  int conv = 0;
+  if (part) {
+    while (npasses < maxPasses) {
+      const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter + npasses);
+      auto entry_at = [&](int s) -> int { return ordered ? s : (int)cd_perm(pkm, (uint32_t)s); };
+      {
+        const int e0 = m > 0 ? s_g[entry_at(0)] : 0, e1 = m > 1 ? s_g[entry_at(1)] : 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          gcur[r] = (kk[r] >= 0 && m > 0) ? __ldcg(G + gi[r] + (long long)e0 * m0) : 0.0;
+          gnxt[r] = (kk[r] >= 0 && m > 1) ? __ldcg(G + gi[r] + (long long)e1 * m0) : 0.0;
+        }
+      }
+      double pmax = 0.0;
+      for (int s = 0; s < m; ++s) {
+        const int i = entry_at(s);
+        double gpre[R];
+        {
+          const int e2 = (s + 2 < m) ? s_g[entry_at(s + 2)] : -1;
+#pragma unroll
+          for (int r = 0; r < R; ++r) gpre[r] = (e2 >= 0 && kk[r] >= 0) ? __ldcg(G + gi[r] + (long long)e2 * m0) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (i == r * nthr + tid) {
+            double nw, h;
+            if (is_sqrt) { // :259-283 with s, ||r+||^2 from d, ||r||^2, a
+              const double old = be[r], sv = dd[r] + aa[r] * old;
+              const double rsq = rr + 2.0 * old * dd[r] + old * old * aa[r];
+              const double l = th[r], t = l * sqrt(rsq);
+              if (fabs(sv) <= t)
+                nw = 0.0;
+              else if (sv > t)
+                nw = (sv - l / sqrt(1.0 - l * l / aa[r]) * sqrt(rsq - sv * sv / aa[r])) / aa[r];
+              else
+                nw = (sv + l / sqrt(1.0 - l * l / aa[r]) * sqrt(rsq - sv * sv / aa[r])) / aa[r];
+            } else {
+              const double v = __dadd_rn(be[r], dd[r] / aa[r]);
+              nw = cd_shrink(v, th[r]);
+            }
+            h = nw - be[r];
+            sm->bval[s & 1] = h;
+            if (is_sqrt) sm->bval2[s & 1] = h * (h * aa[r] - 2.0 * dd[r]); // change of ||r||^2
+            be[r] = nw;
+          }
+        }
+        nbar(1, nthr);
+        const double h = sm->bval[s & 1];
+        if (h != 0.0) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) dd[r] = __dsub_rn(dd[r], __dmul_rn(gcur[r], h));
+          if (is_sqrt) rr += sm->bval2[s & 1];
+          accepted += 1;
+        }
+        pmax = fmax(pmax, fabs(h));
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          gcur[r] = gnxt[r];
+          gnxt[r] = gpre[r];
+        }
+      }
+      npasses += 1;
+      visits += m;
+      maxH = pmax;
+      // ---- dropzeros!
+      if (tid == 0) sm->flag = 0;
+      nbar(1, nthr);
+      {
+        int z = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) z |= (kk[r] >= 0 && be[r] == 0.0);
+        if (z) sm->flag = 1;
+      }
+      nbar(1, nthr);
+      if (sm->flag) { // rare: an entry left the active set
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = r * nthr + tid;
+          if (kk[r] >= 0) {
+            scr_d[i] = dd[r];
+            scr_be[i] = be[r];
+          }
+          if (i < m) s_idx[i] = i;
+        }
+        nbar(1, nthr);
+        if (tid == 0) {
+          int nn = m, i = 0;
+          while (i < nn) {
+            if (scr_be[s_idx[i]] == 0.0) {
+              a.inlist[s_act[s_idx[i]]] = 0;
+              if (i != nn - 1) s_idx[i] = s_idx[nn - 1];
+              nn -= 1;
+            } else {
+              i += 1;
+            }
+          }
+          sm->nact = nn;
+        }
+        nbar(1, nthr);
+        const int mn = sm->nact;
+        int nk[R], ng[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = r * nthr + tid;
+          nk[r] = -1;
+          ng[r] = 0;
+          if (i < mn) {
+            const int src = s_idx[i];
+            nk[r] = s_act[src];
+            ng[r] = s_g[src];
+            dd[r] = scr_d[src];
+            be[r] = scr_be[src];
+          }
+        }
+        nbar(1, nthr);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = r * nthr + tid;
+          kk[r] = nk[r];
+          gi[r] = ng[r];
+          if (i < mn) {
+            const int k = nk[r];
+            s_act[i] = k;
+            s_g[i] = ng[r];
+            aa[r] = __ldg(a.colsq + k);
+            const double om = a.omega ? __ldg(a.omega + k) : 1.0;
+            th[r] = is_sqrt ? lam * om : __dmul_rn(__dmul_rn((double)n / aa[r], lam), om);
+          }
+        }
+        m = mn;
+        nbar(1, nthr);
+      }
+      if (maxH < a.optTol) {
+        conv = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- publish the new iterate and fold the change into r: r -= X[:, act0] (beta - beta_at_entry)
+  for (int i = tid; i < m0; i += NV_T) __stcg(a.beta + act0[i], 0.0);
+  __syncthreads();
+  if (part) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = r * nthr + tid;
+      if (kk[r] >= 0) {
+        __stcg(a.beta + kk[r], be[r]);
+        a.act[i] = kk[r];
+        a.actval[i] = be[r];
+        __stcg(a.inlist + kk[r], (unsigned char)1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < m0; i += NV_T) scr_dlt[i] = __ldcg(a.beta + act0[i]) - scr_b0[i];
+  __syncthreads();
+  for (int t0 = tid; t0 < n; t0 += NV_T) {
+    const double *row = a.X + t0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int i = 0;
+    for (; i + 4 <= m0; i += 4) {
+      const double v0 = __ldg(row + (long long)act0[i] * a.ldx), v1 = __ldg(row + (long long)act0[i + 1] * a.ldx);
+      const double v2 = __ldg(row + (long long)act0[i + 2] * a.ldx), v3 = __ldg(row + (long long)act0[i + 3] * a.ldx);
+      acc0 = fma(v0, scr_dlt[i], acc0);
+      acc1 = fma(v1, scr_dlt[i + 1], acc1);
+      acc2 = fma(v2, scr_dlt[i + 2], acc2);
+      acc3 = fma(v3, scr_dlt[i + 3], acc3);
+    }
+    for (; i < m0; ++i) acc0 = fma(__ldg(row + (long long)act0[i] * a.ldx), scr_dlt[i], acc0);
+    const double v = c.r[t0] - ((acc0 + acc1) + (acc2 + acc3));
+    c.r[t0] = v;
+    __stcg(a.r + t0, v);
+  }
+  if (tid == 0) {
+    sm->nact = m;
+    c.bc->npasses = npasses;
+    c.bc->visits = visits;
+    c.bc->accepted = accepted;
+    c.bc->maxH = maxH;
+    c.bc->conv = conv;
+    c.bc->nact = m;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
 __device__ double shared_std(NCtx &c) { // Statistics.std(r), corrected, two-pass
   const int n = c.a.n;
   double s = 0.0;
@@ -448,7 +742,10 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NCtx c{a, grid};
   c.sm = reinterpret_cast<NSmem *>(smem_raw);
-  double *sd = reinterpret_cast<double *>(smem_raw + (sizeof(NSmem) + 15) / 16 * 16);
+  c.s_act = reinterpret_cast<int *>(smem_raw + (sizeof(NSmem) + 15) / 16 * 16);
+  c.s_g = c.s_act + NV_GCAP_;
+  c.s_idx = c.s_g + NV_GCAP_;
+  double *sd = reinterpret_cast<double *>(c.s_idx + NV_GCAP_);
   c.r = sd;
   c.w = a.w ? sd + ((a.n + 1) & ~1) : nullptr; // keep w 16-byte aligned
   c.hbuf = hbuf;
@@ -468,6 +765,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_start = clock64();
   int rp = 0, round3 = 0;
+  int nact_hint = *a.nact; // every CTA's view of the list length (refreshed whenever CTA 0 publishes it)
   unsigned long long pass_counter = 0;
   DevStats st;
   st.passes = st.full_passes = st.visits = st.accepted = 0;
@@ -498,9 +796,15 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           st.full_passes += 1;
           st.visits += a.p;
           const int m_old = c.sm->nact; // CTA 0
-          const double maxH = full_pass(c, lam, pass_counter, rp, round3, st.accepted, pf);
+          const double maxH = full_pass(c, lam, pass_counter, rp, round3, st.accepted, pf, nact_hint);
           const long long t1 = clock64();
-          if (c.bid == 0) list_update_full(c, m_old, pass_counter);
+          if (c.bid == 0) {
+            list_update_full(c, m_old, pass_counter);
+            if (tid == 0) {
+              __stcg(&bc->nact, c.sm->nact);
+              __threadfence();
+            }
+          }
           pf[4] += clock64() - t1;
           pass_counter += 1;
           st.maxH = maxH;
@@ -511,7 +815,25 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           }
         } else {
           const long long t0 = clock64();
-          if (c.bid == 0) active_phase(c, lam, a.maxIter - iter, pass_counter);
+          grid.sync(); // CTA 0 has published the list length
+          const int m_act = __ldcg(&bc->nact);
+          nact_hint = m_act;
+          if (m_act >= 1 && m_act <= NV_GCAP && a.gram) {
+            double *Gs = a.gram, *ds = a.gram + (long long)NV_GCAP * NV_GCAP;
+            build_active_gram(c, m_act, Gs, ds);
+            grid.sync();
+            if (c.bid == 0) {
+              const long long budget = a.maxIter - iter;
+              if (m_act <= NV_T)
+                gram_engine<1>(c, lam, budget, pass_counter, m_act, Gs, ds, c.s_act, c.s_g, c.s_idx);
+              else if (m_act <= 2 * NV_T)
+                gram_engine<2>(c, lam, budget, pass_counter, m_act, Gs, ds, c.s_act, c.s_g, c.s_idx);
+              else
+                gram_engine<NV_RMAX>(c, lam, budget, pass_counter, m_act, Gs, ds, c.s_act, c.s_g, c.s_idx);
+            }
+          } else if (c.bid == 0) {
+            active_phase(c, lam, a.maxIter - iter, pass_counter);
+          }
           pf[5] += clock64() - t0;
           grid.sync();
           const long long np = __ldcg(&bc->npasses);
@@ -527,6 +849,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           st.accepted += __ldcg(&bc->accepted);
           st.maxH = __ldcg(&bc->maxH);
           conv = __ldcg(&bc->conv) != 0;
+          nact_hint = __ldcg(&bc->nact);
           grid.sync(); // bc may be rewritten only after everyone has read it
         }
       }
@@ -545,6 +868,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
     }
     grid.sync();
     const int nnz = __ldcg(&bc->nact);
+    nact_hint = nnz;
     if (!a.accumulate) {
       if (a.colptr && out_off + nnz > a.capacity) status = 1;
       if (c.bid == 0 && status == 0) {
@@ -711,7 +1035,8 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
     CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
     attr_done = true;
   }
-  const size_t dyn = (sizeof(NSmem) + 15) / 16 * 16 + (size_t)((a.n + 1) & ~1) * sizeof(double) * (a.w ? 2 : 1);
+  const size_t dyn = (sizeof(NSmem) + 15) / 16 * 16 + 3 * NV_GCAP * sizeof(int) +
+                     (size_t)((a.n + 1) & ~1) * sizeof(double) * (a.w ? 2 : 1);
   if (dyn > max_dyn)
     return cdgpu_set_error(CDGPU_ECAP,
                            "naive-form sweep keeps r%s in shared memory: n = %d exceeds the %zu-byte limit; use the "
