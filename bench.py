@@ -97,7 +97,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.05)
+            time.sleep(0.2)  # NVML queries take driver locks: a tighter loop was seen to stall cudaMallocAsync/launches
 
     def stop(self):
         if not self.nv:
@@ -225,6 +225,13 @@ def main():
     yp = torch.from_numpy(y).pin_memory()
     Xd, yd = Xp.cuda(non_blocking=False), yp.cuda(non_blocking=False)
     torch.cuda.synchronize()
+    # the box's pinned H2D rate, for reading the e2e number (outside the timed region)
+    hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hb0.record()
+    Xd.copy_(Xp, non_blocking=True)
+    hb1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 8 * n * p / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
 
     def handle_dev():
         f = cdgpu.CDQuadraticLoss.__new__(cdgpu.CDQuadraticLoss)
@@ -323,6 +330,7 @@ def main():
                clocks=clocks,
                e2e={"value": visits_e / secs_e, "unit": "visits/s", "ms_per_step": 1e3 * secs_e / len(res_e),
                     "h2d_bytes_per_step": 8 * n * p + 8 * n + 8 * p * 2 + 8 * cfg["nlambda"],
+                    "h2d_gbs_pinned_measured": h2d_gbs,
                     "d2h_bytes_per_step": int(res_e[-1]["d2h"])},
                gpu_launches=int(nlaunch),
                roofline={"kernel": "gram_syrk_kernel (FP64 DMMA SYRK)", "bound": "tensor", "achieved": gram_tf,

@@ -143,6 +143,7 @@ API int cdgpu_destroy(cdgpu_handle h) {
   dfree(h->discr);
   dfree(h->dbscr);
   dfree(h->dgram);
+  dfree(h->dtiles);
   dfree(h->dstats);
   dfree(h->dlam);
   dfree(h->dcolptr);
@@ -335,7 +336,7 @@ static int gram_build(cdgpu_handle *out, const double *dX, int64_t n_local, int6
   h->owny = false;
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   const bool sharded = comm != nullptr;
-  CD_TRY(launch_gram(h, dX, n_local, (int)p, ldx, dy, h->dX, h->dy, (double)n_total, !sharded));
+  CD_TRY(launch_gram(h, dX, n_local, (int)p, ldx, dy, h->dX, h->dy, (double)n_total, sharded ? 0 : 1));
   if (sharded) {
     CD_TRY(cdgpu_comm_allreduce(comm, h->dX, na + (size_t)p, h->stream));
     CD_TRY(launch_scale_gram(h, h->dX, h->dy, (int)p, (double)n_total));
@@ -376,35 +377,90 @@ API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t
   if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
   CD_TRY(use_device(device));
-  // stage X on the device with 16-byte aligned columns, form the Gram, drop the staging copy
+  // Host X: the rows are staged in chunks on a copy stream while the SYRK of the previous chunk runs
+  // (G accumulates over row chunks, then one scale pass), so the H2D transfer hides behind the DMMA
+  // work when the host memory is pinned.  The staging copy is dropped afterwards.
+  HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
+  cdgpu_handle_s *h = g.h;
+  if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+  h->kind = CDGPU_LOSS_QUAD;
+  h->device = device;
+  h->n = p;
+  h->p = p;
+  h->ld = (p + 1) & ~(int64_t)1;
+  CD_TRY(handle_common_alloc(h));
+  const size_t na = (size_t)h->ld * (size_t)p;
+  CD_TRY(dalloc(&h->dX, na + (size_t)p));
+  h->ownX = true;
+  h->dy = h->dX + na;
+  h->owny = false;
   const int64_t ld = (n + 1) & ~(int64_t)1;
-  double *dX = nullptr, *dy = nullptr;
-  CD_TRY(dalloc(&dX, (size_t)ld * (size_t)p));
-  int rc = dalloc(&dy, (size_t)n);
+  double *dXs = nullptr, *dys = nullptr;
+  CD_TRY(dalloc(&dXs, (size_t)ld * (size_t)p));
+  int rc = dalloc(&dys, (size_t)n);
+  cudaStream_t cs = nullptr;
+  const int NCH = 8;
+  cudaEvent_t ev[NCH] = {nullptr};
+  auto cleanup = [&]() {
+    if (cs) {
+      cudaStreamSynchronize(cs);
+      cudaStreamDestroy(cs);
+    }
+    for (int i = 0; i < NCH; ++i)
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    dfree(dXs);
+    dfree(dys);
+  };
+#define G_TRY(expr)                                                                                                  \
+  do {                                                                                                               \
+    cudaError_t _e = (expr);                                                                                         \
+    if (_e != cudaSuccess) {                                                                                         \
+      cleanup();                                                                                                     \
+      return cdgpu_set_error(_e == cudaErrorMemoryAllocation ? CDGPU_ENOMEM : CDGPU_ECUDA, "%s: %s", #expr,          \
+                             cudaGetErrorString(_e));                                                                \
+    }                                                                                                                \
+  } while (0)
   if (rc) {
-    dfree(dX);
+    cleanup();
     return rc;
   }
-  auto cleanup = [&]() {
-    dfree(dX);
-    dfree(dy);
-  };
-  cudaError_t e = cudaSuccess;
-  if (ld != n) e = cudaMemset(dX, 0, (size_t)ld * p * sizeof(double));
-  if (e == cudaSuccess) {
-    if (ld == n && ldx == n)
-      e = cudaMemcpy(dX, X, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice);
-    else
-      e = cudaMemcpy2D(dX, ld * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), p, cudaMemcpyHostToDevice);
+  G_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  G_TRY(cudaEventRecord(h->ev0, h->stream));
+  G_TRY(cudaMemcpyAsync(dys, y, n * sizeof(double), cudaMemcpyHostToDevice, cs));
+  if (ld != n) G_TRY(cudaMemsetAsync(dXs, 0, (size_t)ld * p * sizeof(double), cs));
+  int nch = NCH;
+  if (const char *env = getenv("CDGPU_GRAM_CHUNKS")) nch = std::max(1, std::min(NCH, atoi(env)));
+  int64_t chunk = ((n + nch - 1) / nch + 15) & ~(int64_t)15; // multiple of 16 rows: 16-byte aligned, whole k-tiles
+  if (chunk < 1024) chunk = n;                                // small problems: one piece
+  int ci = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk, ++ci) {
+    const int64_t rows = (r0 + chunk < n) ? chunk : n - r0;
+    G_TRY(cudaMemcpy2DAsync(dXs + r0, ld * sizeof(double), X + r0, ldx * sizeof(double), rows * sizeof(double), p,
+                            cudaMemcpyHostToDevice, cs));
+    G_TRY(cudaEventCreateWithFlags(&ev[ci], cudaEventDisableTiming));
+    G_TRY(cudaEventRecord(ev[ci], cs));
+    G_TRY(cudaStreamWaitEvent(h->stream, ev[ci], 0));
+    rc = launch_gram(h, dXs + r0, rows, (int)p, ld, dys + r0, h->dX, h->dy, (double)n, ci == 0 ? 0 : 2);
+    if (rc) {
+      cleanup();
+      return rc;
+    }
   }
-  if (e == cudaSuccess) e = cudaMemcpy(dy, y, n * sizeof(double), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
+  rc = launch_scale_gram(h, h->dX, h->dy, (int)p, (double)n);
+  if (rc) {
     cleanup();
-    return cdgpu_set_error(CDGPU_ECUDA, "H2D copy of X failed: %s", cudaGetErrorString(e));
+    return rc;
   }
-  rc = gram_build(out, dX, n, n, p, ld, dy, device, nullptr, nullptr);
+  G_TRY(cudaEventRecord(h->ev1, h->stream));
+  G_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  G_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+#undef G_TRY
+  h->gram_ms = ms; // includes the overlapped H2D staging
   cleanup();
-  return rc;
+  CD_TRY(quad_finish(h, false));
+  *out = g.release();
+  return CDGPU_OK;
 }
 
 API int cdgpu_dims(cdgpu_handle h, int64_t *n, int64_t *p, int *loss_kind) {

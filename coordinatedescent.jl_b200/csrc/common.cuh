@@ -220,6 +220,8 @@ struct cdgpu_handle_s {
   int *discr = nullptr;             // 8 * p ints
   unsigned char *dbscr = nullptr;   // 2 * p bytes
   double *dgram = nullptr;          // naive handles: active-set Gram scratch (allocated at first solve)
+  void *dtiles = nullptr;           // Gram tile schedule (int2[ntiles])
+  int ntiles = 0;
   DevStats *dstats = nullptr;       // path stats, grown on demand
   int64_t nstats = 0;
   double *dlam = nullptr;
@@ -271,8 +273,9 @@ int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, in
 int launch_diag_sqrt(cdgpu_handle_s *h, const double *A, long long lda, int p, double *out);
 
 // Gram (gram_dmma.cu): G = X'X / n_total (lower tiles computed, mirrored), c = -X'y / n_total
+// mode 0: raw sums, 1: sums / divisor, 2: accumulate raw sums into G | c
 int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,
-                double *c, double inv_scale_n, bool scale);
+                double *c, double divisor, int mode);
 int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_total);
 
 // naive sweeps (naive_sweep.cu)

@@ -79,8 +79,8 @@ __device__ __forceinline__ void load_tile(double *dst, const double *X, long lon
 // WM x WN warps; warp tile (128/WM) x (128/WN) = MI x NI fragments of 8 x 8
 template <bool ALIGNED16, int WM, int WN, int BK, int STAGES, bool PIPE>
 __global__ void __launch_bounds__(WM *WN * 32, 1)
-    gram_syrk_kernel(const double *__restrict__ X, long long n, int p, long long ldx, double *__restrict__ G,
-                     long long ldg, const int2 *__restrict__ tiles, int ntiles, double divisor, int do_scale) {
+    gram_syrk_kernel(const double *__restrict__ X, long long n, int p, long long ldx, double *G,
+                     long long ldg, const int2 *__restrict__ tiles, int ntiles, double divisor, int mode) {
   constexpr int GT = WM * WN * 32, LDK = BK + 4, STAGE_DOUBLES = (BM + BN) * LDK;
   constexpr int MI = BM / (WM * 8), NI = BN / (WN * 8);
   extern __shared__ __align__(16) double smem[];
@@ -181,7 +181,13 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
     cp_wait<0>();
     __syncthreads(); // all warps done with the last stage before the next tile's prologue overwrites it
 
-    // epilogue: G[colA + m, colB + nn] and its mirror
+    // epilogue: G[colA + m, colB + nn] and its mirror.  mode 0: store raw sums, 1: store sums / divisor,
+    // 2: add the raw sums to what is there (row-chunked accumulation; both triangles hold the same value)
+    auto put = [&](int r, int cidx, double v) {
+      if (mode == 2) v += G[r + (long long)cidx * ldg];
+      G[r + (long long)cidx * ldg] = v;
+      G[cidx + (long long)r * ldg] = v;
+    };
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
       const int row = colA + wm * MI * 8 + i * 8 + g;
@@ -189,30 +195,14 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
       for (int j = 0; j < NI; ++j) {
         const int col = colB + wn * NI * 8 + j * 8 + 2 * q;
         double v0 = acc[i][j][0], v1 = acc[i][j][1];
-        if (do_scale) {
+        if (mode == 1) {
           v0 = v0 / divisor;
           v1 = v1 / divisor;
         }
         if (row < p) {
-          if (bi != bj) {
-            if (col < p) {
-              G[row + (long long)col * ldg] = v0;
-              G[col + (long long)row * ldg] = v0;
-            }
-            if (col + 1 < p) {
-              G[row + (long long)(col + 1) * ldg] = v1;
-              G[col + 1 + (long long)row * ldg] = v1;
-            }
-          } else { // diagonal tile: the lower part (and the diagonal) is authoritative
-            if (col < p && row >= col) {
-              G[row + (long long)col * ldg] = v0;
-              G[col + (long long)row * ldg] = v0;
-            }
-            if (col + 1 < p && row >= col + 1) {
-              G[row + (long long)(col + 1) * ldg] = v1;
-              G[col + 1 + (long long)row * ldg] = v1;
-            }
-          }
+          // diagonal tiles: the lower part (and the diagonal) is authoritative
+          if (col < p && (bi != bj || row >= col)) put(row, col, v0);
+          if (col + 1 < p && (bi != bj || row >= col + 1)) put(row, col + 1, v1);
         }
       }
     }
@@ -221,7 +211,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
 
 // c_j = -(X_j'y) [/ n]; one warp per column
 __global__ void xty_kernel(const double *__restrict__ X, long long n, int p, long long ldx,
-                           const double *__restrict__ y, double *__restrict__ c, double divisor, int do_scale) {
+                           const double *__restrict__ y, double *c, double divisor, int mode) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < p; k += gridDim.x * wpb) {
     const double *col = X + (long long)k * ldx;
@@ -233,7 +223,7 @@ __global__ void xty_kernel(const double *__restrict__ X, long long n, int p, lon
     }
     for (; i < n; i += 32) s0 = fma(__ldg(col + i), __ldg(y + i), s0);
     double s = warp_sum(s0 + s1);
-    if (lane == 0) c[k] = do_scale ? -s / divisor : -s;
+    if (lane == 0) c[k] = mode == 1 ? -s / divisor : (mode == 2 ? c[k] - s : -s);
   }
 }
 
@@ -245,21 +235,28 @@ __global__ void scale_kernel(double *G, long long count, double divisor) {
 } // namespace
 
 int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,
-                double *c, double divisor, bool scale) {
+                double *c, double divisor, int mode) {
   const int nb = (p + BM - 1) / BM;
   // tile list in 12 x 12 super-tiles over the lower triangle
   const int S = 12;
   std::vector<int2> tiles;
-  tiles.reserve((size_t)nb * (nb + 1) / 2);
-  for (int SI = 0; SI < nb; SI += S)
-    for (int SJ = 0; SJ <= SI; SJ += S)
-      for (int bi = SI; bi < min(SI + S, nb); ++bi)
-        for (int bj = SJ; bj < min(SJ + S, nb) && bj <= bi; ++bj) tiles.push_back(make_int2(bi, bj));
-  const int ntiles = (int)tiles.size();
-  int2 *dtiles = nullptr;
-  CUDA_TRY(cudaMallocAsync((void **)&dtiles, (size_t)ntiles * sizeof(int2), h->stream));
-  CUDA_TRY(cudaMemcpyAsync(dtiles, tiles.data(), (size_t)ntiles * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream)); // `tiles` is a host temporary
+  if (!h->dtiles) {
+    tiles.reserve((size_t)nb * (nb + 1) / 2);
+    for (int SI = 0; SI < nb; SI += S)
+      for (int SJ = 0; SJ <= SI; SJ += S)
+        for (int bi = SI; bi < min(SI + S, nb); ++bi)
+          for (int bj = SJ; bj < min(SJ + S, nb) && bj <= bi; ++bj) tiles.push_back(make_int2(bi, bj));
+    h->ntiles = (int)tiles.size();
+  }
+  const int ntiles = h->ntiles;
+  if (!h->dtiles) { // built once per handle (depends only on p)
+    // NB: stream-ordered copy + sync.  A plain cudaMemcpy from pageable memory may return before the DMA has
+    // landed, and the kernel below runs on a non-blocking stream that does not order against it.
+    CUDA_TRY(cudaMallocAsync((void **)&h->dtiles, (size_t)ntiles * sizeof(int2), h->stream)); // pool: no device sync
+    CUDA_TRY(cudaMemcpyAsync(h->dtiles, tiles.data(), (size_t)ntiles * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream)); // `tiles` is a host temporary
+  }
+  const int2 *dtiles = static_cast<const int2 *>(h->dtiles);
   const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
   const long long ldg = ((long long)p + 1) & ~1ll;
   const int grid = min(ntiles, h->sm_count);
@@ -267,7 +264,7 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
   if (const char *env = getenv("CDGPU_GRAM_VARIANT")) variant = atoi(env);
   auto launch = [&](auto kern, int threads, size_t dyn) -> int {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    kern<<<grid, threads, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, scale ? 1 : 0);
+    kern<<<grid, threads, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, mode);
     CUDA_TRY(cudaGetLastError());
     return CDGPU_OK;
   };
@@ -295,10 +292,9 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
     rc = launch(gram_syrk_kernel<true, 2, 4, 16, 4, true>, 256, GRAM_DYN(16, 4));
 #undef GRAM_DYN
   CD_TRY(rc);
-  xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, c, divisor, scale ? 1 : 0);
+  xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, c, divisor, mode);
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(2);
-  CUDA_TRY(cudaFreeAsync(dtiles, h->stream));
   return CDGPU_OK;
 }
 

@@ -218,7 +218,7 @@ def test_scaled_lasso_parity(gpu, ref, init):
 
 
 def test_gram_matches_and_is_symmetric(gpu, ref):
-    for n, p in [(257, 130), (1000, 515), (64, 33)]:
+    for n, p in [(257, 130), (1000, 515), (64, 33), (9001, 140)]:  # the last one takes the row-chunked H2D/accumulate path
         X, y, _ = gauss_problem(n, p, 5, seed=n)
         f = gpu.CDQuadraticLoss_from_data(X, y)
         A, b = f.get()
