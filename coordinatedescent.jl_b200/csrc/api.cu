@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -60,6 +61,22 @@ API void cdgpu_default_iter_options(cdgpu_iter_options *o) { // IterLassoOptions
   cdgpu_default_options(&o->optionsCD);
 }
 
+// CDGPU_TRACE=1: host-side wall-clock trace of the handle constructors (where do create() stalls come from?)
+#include <chrono>
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  Trace() : on(getenv("CDGPU_TRACE") != nullptr) { t0 = last = std::chrono::steady_clock::now(); }
+  void mark(const char *what) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cdgpu trace] %-28s +%8.3f ms (t=%8.3f)\n", what,
+            std::chrono::duration<double, std::milli>(now - last).count(),
+            std::chrono::duration<double, std::milli>(now - t0).count());
+    last = now;
+  }
+};
+
 // --------------------------------------------------------------- handles --
 static int pool_init(int device);
 static int use_device(int device) {
@@ -99,28 +116,88 @@ static void dfree(void *p) {
   if (p) cudaFreeAsync(p, (cudaStream_t)0);
 }
 
+// Streams and events come from a per-device free list: cudaStreamCreate / cudaEventCreate go through
+// the resource manager and were seen to stall for up to 300 ms when an NVML client (nvidia-smi, a
+// clock sampler) polls the same device, so a handle takes a recycled set and returns it on destroy.
+struct StreamSet {
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+};
+static std::mutex g_res_mu;
+static std::vector<StreamSet> g_free_sets[64];
+static int g_sm_count[64] = {0};
+
+static int stream_set_acquire(int device, StreamSet *out) {
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    if (device < 64 && !g_free_sets[device].empty()) {
+      *out = g_free_sets[device].back();
+      g_free_sets[device].pop_back();
+      return CDGPU_OK;
+    }
+  }
+  CUDA_TRY(cudaStreamCreateWithFlags(&out->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&out->ev0));
+  CUDA_TRY(cudaEventCreate(&out->ev1));
+  return CDGPU_OK;
+}
+static void stream_set_release(int device, const StreamSet &s) {
+  std::lock_guard<std::mutex> lk(g_res_mu);
+  if (device < 64 && g_free_sets[device].size() < 16) {
+    g_free_sets[device].push_back(s);
+    return;
+  }
+  cudaEventDestroy(s.ev0);
+  cudaEventDestroy(s.ev1);
+  cudaStreamDestroy(s.stream);
+}
+static int device_sm_count(int device, int *out) {
+  if (device < 64 && g_sm_count[device] > 0) {
+    *out = g_sm_count[device];
+    return CDGPU_OK;
+  }
+  int v = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+  if (device < 64) g_sm_count[device] = v;
+  *out = v;
+  return CDGPU_OK;
+}
+
+// iterate + sweep scratch of a handle: ONE pool allocation carved into 256-byte aligned pieces
 static int handle_common_alloc(cdgpu_handle_s *h) {
   const size_t p = (size_t)h->p;
-  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreate(&h->ev0));
-  CUDA_TRY(cudaEventCreate(&h->ev1));
-  CD_TRY(dalloc(&h->dbeta, p));
-  CD_TRY(dalloc(&h->dact, p));
-  CD_TRY(dalloc(&h->dactval, p));
-  CD_TRY(dalloc(&h->dnact, 1));
-  CD_TRY(dalloc(&h->dinlist, p));
-  CD_TRY(dalloc(&h->domega, p));
-  CD_TRY(dalloc(&h->dscr, 12 * p + 8 * (size_t)h->n + 64 + 4 * 2048 + 64));
-  CD_TRY(dalloc(&h->discr, 8 * p + 64));
-  CD_TRY(dalloc(&h->dbscr, 2 * p + 64));
-  CD_TRY(dalloc(&h->dflag, 8));
+  StreamSet ss;
+  CD_TRY(stream_set_acquire(h->device, &ss));
+  h->stream = ss.stream;
+  h->ev0 = ss.ev0;
+  h->ev1 = ss.ev1;
+  size_t off = 0;
+  auto take = [&off](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  const size_t o_beta = take(p * sizeof(double)), o_act = take(p * sizeof(int)), o_actval = take(p * sizeof(double)),
+               o_nact = take(sizeof(int)), o_inlist = take(p), o_omega = take(p * sizeof(double)),
+               o_scr = take((12 * p + 8 * (size_t)h->n + 64 + 4 * 2048 + 64) * sizeof(double)),
+               o_iscr = take((8 * p + 64) * sizeof(int)), o_bscr = take(2 * p + 64), o_flag = take(8 * sizeof(int));
+  CD_TRY(dalloc(&h->dcommon, off));
+  unsigned char *base = h->dcommon;
+  h->dbeta = (double *)(base + o_beta);
+  h->dact = (int *)(base + o_act);
+  h->dactval = (double *)(base + o_actval);
+  h->dnact = (int *)(base + o_nact);
+  h->dinlist = base + o_inlist;
+  h->domega = (double *)(base + o_omega);
+  h->dscr = (double *)(base + o_scr);
+  h->discr = (int *)(base + o_iscr);
+  h->dbscr = base + o_bscr;
+  h->dflag = (int *)(base + o_flag);
   CUDA_TRY(cudaMemsetAsync(h->dbeta, 0, p * sizeof(double), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dinlist, 0, p, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dnact, 0, sizeof(int), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 8 * sizeof(int), h->stream));
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
-  h->sm_count = prop.multiProcessorCount;
+  CD_TRY(device_sm_count(h->device, &h->sm_count));
   return CDGPU_OK;
 }
 
@@ -133,15 +210,7 @@ API int cdgpu_destroy(cdgpu_handle h) {
   if (h->ownw) dfree(h->dw);
   dfree(h->dstate);
   dfree(h->daux);
-  dfree(h->dbeta);
-  dfree(h->dact);
-  dfree(h->dactval);
-  dfree(h->dnact);
-  dfree(h->dinlist);
-  dfree(h->domega);
-  dfree(h->dscr);
-  dfree(h->discr);
-  dfree(h->dbscr);
+  dfree(h->dcommon);
   dfree(h->dgram);
   dfree(h->dtiles);
   dfree(h->dstats);
@@ -149,10 +218,7 @@ API int cdgpu_destroy(cdgpu_handle h) {
   dfree(h->dcolptr);
   dfree(h->drowval);
   dfree(h->dnzval);
-  dfree(h->dflag);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream) stream_set_release(h->device, StreamSet{h->stream, h->ev0, h->ev1});
   delete h;
   return CDGPU_OK;
 }
@@ -319,6 +385,7 @@ int cdgpu_comm_allreduce(cdgpu_comm c, double *buf, size_t count, cudaStream_t s
 
 static int gram_build(cdgpu_handle *out, const double *dX, int64_t n_local, int64_t n_total, int64_t p, int64_t ldx,
                       const double *dy, int device, cdgpu_comm comm, double *) {
+  Trace tr;
   HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
   cdgpu_handle_s *h = g.h;
   if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
@@ -328,9 +395,11 @@ static int gram_build(cdgpu_handle *out, const double *dX, int64_t n_local, int6
   h->p = p;
   h->ld = (p + 1) & ~(int64_t)1;
   CD_TRY(handle_common_alloc(h));
+  tr.mark("handle_common_alloc");
   // A and b live in ONE allocation so a single allreduce covers both
   const size_t na = (size_t)h->ld * (size_t)p;
   CD_TRY(dalloc(&h->dX, na + (size_t)p));
+  tr.mark("alloc G");
   h->ownX = true;
   h->dy = h->dX + na;
   h->owny = false;
@@ -342,11 +411,14 @@ static int gram_build(cdgpu_handle *out, const double *dX, int64_t n_local, int6
     CD_TRY(launch_scale_gram(h, h->dX, h->dy, (int)p, (double)n_total));
   }
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  tr.mark("launches");
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  tr.mark("gram kernels done");
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->gram_ms = ms;
   CD_TRY(quad_finish(h, false)); // symmetric by construction (mirrored tiles)
+  tr.mark("quad_finish");
   *out = g.release();
   return CDGPU_OK;
 }
@@ -356,8 +428,10 @@ API int cdgpu_gram_create_dev(cdgpu_handle *out, const double *dX, int64_t n, in
   if (!out || !dX || !dy) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
+  Trace tr;
   CD_TRY(use_device(device));
   CUDA_TRY(cudaDeviceSynchronize());
+  tr.mark("use_device + device sync");
   return gram_build(out, dX, n, n, p, ldx, dy, device, nullptr, nullptr);
 }
 

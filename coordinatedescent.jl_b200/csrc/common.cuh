@@ -208,6 +208,7 @@ struct cdgpu_handle_s {
   // naive: X (n x p, ld), y, w, r=state(n), colsq (p) ; quad: A (p x p, ld), b, state=Ax(p), ainv (p)
   double *dX = nullptr, *dy = nullptr, *dw = nullptr, *dstate = nullptr, *daux = nullptr;
   bool ownX = false, owny = false, ownw = false;
+  unsigned char *dcommon = nullptr; // one allocation behind the iterate + scratch pointers below
   // iterate
   double *dbeta = nullptr;          // dense p
   int *dact = nullptr;              // active list (0-based coordinates), capacity p

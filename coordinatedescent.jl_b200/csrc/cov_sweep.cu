@@ -844,6 +844,8 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
     attr_done = true;
   }
   // largest cluster the device will co-schedule (16 on B200 with the opt-in, else 8)
+  static int dev_max_cluster[64] = {0}; // per device: the occupancy query is not free
+  if (h->max_cluster == 0 && h->device < 64) h->max_cluster = dev_max_cluster[h->device];
   int C = h->max_cluster;
   if (C == 0) {
     for (int cand : {16, 8, 4, 2, 1}) {
@@ -868,6 +870,7 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
     }
     if (C == 0) return cdgpu_set_error(CDGPU_ECUDA, "no thread-block cluster configuration can be scheduled");
     h->max_cluster = C;
+    if (h->device < 64) dev_max_cluster[h->device] = C;
   }
   if (const char *env = getenv("CDGPU_CLUSTER")) {
     int v = atoi(env);
