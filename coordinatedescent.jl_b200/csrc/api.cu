@@ -734,7 +734,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     CD_TRY(launch_cov_init(h, a.A, a.lda, a.p, a.act, a.actval, a.nact, a.Ax, a.beta, a.inlist));
     CD_TRY(launch_cov_path(h, a));
     if (prof) {
-      long long pf[10];
+      long long pf[24];
       CUDA_TRY(cudaMemcpyAsync(pf, a.prof, sizeof pf, cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream));
       fprintf(stderr,
@@ -743,6 +743,10 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
               "apply %.3f\n",
               pf[6] * 1e-6, pf[0] * 1e-6, pf[4], pf[1] * 1e-6, pf[2] * 1e-6, pf[5], pf[3] * 1e-6, pf[7] * 1e-6, pf[8] * 1e-6,
               pf[9] * 1e-6);
+      fprintf(stderr,
+              "[cdgpu profile]   chain engine: warp0 panel %.3f chain %.3f barrier %.3f pass-ends %.3f | workers stage %.3f apply "
+              "%.3f barrier %.3f Mcyc\n",
+              pf[16] * 1e-6, pf[17] * 1e-6, pf[18] * 1e-6, pf[19] * 1e-6, pf[20] * 1e-6, pf[21] * 1e-6, pf[22] * 1e-6);
     }
   } else {
     NaiveArgs a = {};
@@ -789,13 +793,17 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     CD_TRY(launch_naive_init(h, a));
     CD_TRY(launch_naive_path(h, a));
     if (prof) {
-      long long pf[10];
+      long long pf[24];
       CUDA_TRY(cudaMemcpyAsync(pf, a.prof, sizeof pf, cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream));
       fprintf(stderr,
               "[cdgpu profile] naive path (CTA 0): total %.3f Mcyc | full-pass rounds %lld: column dots %.3f, grid.sync "
               "%.3f, scan %.3f, apply %.3f | list update %.3f | active phase %.3f\n",
               pf[6] * 1e-6, pf[7], pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6);
+      fprintf(stderr,
+              "[cdgpu profile]   chain engine: warp0 panel %.3f chain %.3f barrier %.3f pass-ends %.3f | workers stage %.3f apply "
+              "%.3f barrier %.3f Mcyc\n",
+              pf[16] * 1e-6, pf[17] * 1e-6, pf[18] * 1e-6, pf[19] * 1e-6, pf[20] * 1e-6, pf[21] * 1e-6, pf[22] * 1e-6);
     }
   }
   return CDGPU_OK;

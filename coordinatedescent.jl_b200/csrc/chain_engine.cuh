@@ -1,0 +1,302 @@
+// chain_engine.cuh — the sequential Gauss-Seidel chain of ACTIVE-SET passes (_cdPass! over the stored
+// entries, src/coordinate_descent.jl:94-110 with the sparse iterators of src/atom_iterator.jl:18-37,
+// 53-75) as a blocked, software-pipelined CTA-level engine.  Shared by the covariance-form kernel
+// (cov_sweep.cu) and by the naive kernels once they have formed the active Gram (naive_sweep.cu).
+//
+// State per stored entry t (list position): g_t (cov: (A x)_t; naive: X_t'(w.r)), beta_t.  A step on
+// entry i changes every g_t by G[t,i]*h, so a pass is a length-m dependent chain.  Layout of the work:
+//   * visit positions are cut into blocks of 32.  WARP 0 runs the chain of one block entirely in
+//     registers: lane j owns entry j of the block, a step is "all lanes evaluate their closed-form
+//     update, lane i's h is broadcast by one shuffle, every lane applies G[j,i]*h" — no barrier and
+//     no memory access on the dependent path (the 32x32 diagonal block D sits in shared memory and
+//     its next row is fetched ahead of the shuffle).
+//   * before the chain of block b, warp 0 applies the 32 steps of block b-1 to its new entries (the
+//     "panel" P = G[block b, block b-1], also staged in shared memory).
+//   * WARPS 1..15 meanwhile (a) gather D, P and the per-entry constants of block b+1 from L2 into the
+//     other stage buffer and (b) apply the steps of block b-1 to every entry outside blocks b-1 and b.
+//     One __syncthreads per block hands the results over.
+//   * every entry receives the steps in visit order, each as the same non-fused multiply-add the
+//     sequential algorithm performs, so iterates are bit-identical to the one-step-at-a-time chain.
+//   * dropzeros! (swap-with-last compaction, ProximalBase) runs at the end of a pass, only when an
+//     entry became exactly zero.
+#pragma once
+#include "common.cuh"
+
+namespace chain {
+
+#ifdef CHAIN_PROBE
+__device__ int probe_mode; // benchmarks/micro/chain_probe.cu: bit 0 skip worker apply, bit 1 skip worker stage, bit 2 skip chain
+#define CHAIN_PROBE_BIT(b) ((probe_mode >> (b)) & 1)
+#else
+#define CHAIN_PROBE_BIT(b) 0
+#endif
+
+constexpr int BUF_DOUBLES = 2 * 32 * 32 + 3 * 32; // D, P, three per-entry constants
+constexpr int STAGE_DOUBLES = 2 * BUF_DOUBLES;
+
+struct Shared { // small block-shared scalars
+  double hb[2][32];
+  double pmax;
+  int newm, flag;
+};
+
+struct State {
+  int m;                       // stored entries
+  int *row;                    // [cap] row/column id of the entry inside G
+  int *coord;                  // [cap] coordinate (0-based) of the entry (may alias row)
+  double *g, *be;              // [cap]
+  unsigned short *ord, *pos;   // [cap] visit position -> entry, entry -> visit position
+  double *stage;               // [STAGE_DOUBLES]
+  Shared *sh;
+  const double *G;             // symmetric; G(t,i) = G[row[t] + row[i]*ldg]
+  long long ldg;
+  long long *prof; // optional [8]: cycles of thread 0 (panel, chain, barrier wait, pass ends) and thread 32 (stage, apply, barrier wait), blocks
+};
+
+struct Result {
+  long long npasses, visits, accepted;
+  double maxH;
+  int conv, m;
+};
+
+__device__ __forceinline__ double ld_l2(const double *p) { return __ldcg(p); }
+
+// gather block `bb` (diagonal block, panel against block bb-1, constants) into `buf`; threads t0, t0+nthr, ...
+template <class Policy>
+__device__ __forceinline__ void stage_block(const State &S, const Policy &P, int m, int bb, double *buf, int t0, int nthr) {
+  const int cnt = min(32, m - 32 * bb);
+  const int total = bb > 0 ? 2048 : 1024;
+  for (int base = t0; base < total; base += 5 * nthr) {
+    double v[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int idx = base + u * nthr;
+      v[u] = 0.0;
+      if (idx < total) {
+        const int i = (idx >> 5) & 31, j = idx & 31;
+        const bool panel = idx >= 1024;
+        if (j < cnt && (panel || i < cnt)) {
+          const int rj = S.row[S.ord[32 * bb + j]];
+          const int ri = S.row[S.ord[32 * (panel ? bb - 1 : bb) + i]];
+          v[u] = ld_l2(S.G + rj + (long long)ri * S.ldg);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int idx = base + u * nthr;
+      if (idx < total) buf[idx] = v[u];
+    }
+  }
+  for (int j = t0; j < cnt; j += nthr) {
+    double c0, c1, c2;
+    P.load_consts(S.coord[S.ord[32 * bb + j]], c0, c1, c2);
+    buf[2048 + j] = c0;
+    buf[2048 + 32 + j] = c1;
+    buf[2048 + 64 + j] = c2;
+  }
+}
+
+// apply the steps of block `hbk` (h values in hv[0..cnt)) to every entry whose block is neither ex0 nor ex1
+template <class Policy>
+__device__ __forceinline__ void apply_block(const State &S, int m, int hbk, const double *hv, int ex0, int ex1, int t0, int nthr) {
+  const int cnt = min(32, m - 32 * hbk);
+  bool any = false;
+  for (int i = 0; i < cnt; ++i) any |= hv[i] != 0.0;
+  if (!any) return;
+  for (int t = t0; t < m; t += nthr) {
+    const int blk = S.pos[t] >> 5;
+    if (blk == ex0 || blk == ex1) continue;
+    const double *Gt = S.G + S.row[t];
+    double gt = S.g[t];
+#pragma unroll 1
+    for (int i0 = 0; i0 < cnt; i0 += 16) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        v[u] = (i0 + u < cnt) ? ld_l2(Gt + (long long)S.row[S.ord[32 * hbk + i0 + u]] * S.ldg) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const double h = (i0 + u < cnt) ? hv[i0 + u] : 0.0;
+        if (h != 0.0) gt = Policy::apply(gt, v[u], h);
+      }
+    }
+    S.g[t] = gt;
+  }
+}
+
+// Runs consecutive active-set passes until one has max|h| < optTol or maxPasses are used.
+// Block-collective over T threads (T >= 64, multiple of 32); S.m entries are loaded in S.g/be/row/coord.
+template <int T, class Policy>
+__device__ Result run(State &S, const Policy &P, double rr, long long maxPasses, unsigned long long pass_counter,
+                      bool ordered, unsigned long long seed, double optTol, unsigned char *inlist) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWORK = T - 32;
+  int m = S.m;
+  Result R{0, 0, 0, 0.0, 0, m};
+  Shared *sh = S.sh;
+  long long pc[4] = {0, 0, 0, 0};
+  const bool prof = S.prof != nullptr && (tid == 0 || tid == 32);
+  long long tp = prof ? clock64() : 0;
+  auto lap = [&](int slot) {
+    if (prof) {
+      const long long t = clock64();
+      pc[slot] += t - tp;
+      tp = t;
+    }
+  };
+  bool staged_ok = false; // ordered, <= 2 blocks: both stage buffers still hold this list's blocks
+  while (R.npasses < maxPasses) {
+    const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), seed, pass_counter + R.npasses);
+    for (int s = tid; s < m; s += T) {
+      const int e = ordered ? s : (int)cd_perm(pkm, (uint32_t)s);
+      S.ord[s] = (unsigned short)e;
+      S.pos[e] = (unsigned short)s;
+    }
+    __syncthreads();
+    const int nb = (m + 31) >> 5;
+    if (!staged_ok && nb > 0) {
+      stage_block(S, P, m, 0, S.stage, tid, T);
+      __syncthreads();
+    }
+    double pmax = 0.0;
+    long long acc = 0;
+    lap(3);
+    for (int b = 0; b < nb; ++b) {
+      double *buf = S.stage + (b & 1) * BUF_DOUBLES;
+      if (warp == 0) {
+        const int cnt = min(32, m - 32 * b);
+        const bool valid = lane < cnt;
+        const int e = valid ? S.ord[32 * b + lane] : 0;
+        double gj = valid ? S.g[e] : 0.0, bej = valid ? S.be[e] : 0.0;
+        const double c0 = buf[2048 + lane], c1 = buf[2048 + 32 + lane], c2 = buf[2048 + 64 + lane];
+        if (b > 0) { // steps of the previous block, in order
+          const double *hp = sh->hb[(b - 1) & 1], *Pb = buf + 1024;
+#pragma unroll 1
+          for (int i0 = 0; i0 < 32; i0 += 16) { // loads first, then the dependent adds
+            double pv[16], hv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              pv[u] = Pb[(i0 + u) * 32 + lane];
+              hv[u] = hp[i0 + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+              if (hv[u] != 0.0) gj = Policy::apply(gj, pv[u], hv[u]);
+          }
+        }
+        lap(0);
+        double myh = 0.0;
+        double drow = buf[lane];
+        for (int i = 0; i < (CHAIN_PROBE_BIT(2) ? 0 : cnt); ++i) {
+          const double dnext = buf[((i + 1) & 31) * 32 + lane];
+          double nw, hi, dr;
+          P.step(gj, bej, c0, c1, c2, rr, nw, hi, dr);
+          const double h = __shfl_sync(0xffffffffu, hi, i);
+          if (lane == i) {
+            bej = nw;
+            myh = hi;
+          }
+          if (h != 0.0) {
+            gj = Policy::apply(gj, drow, h);
+            if (Policy::HAS_RR) rr += __shfl_sync(0xffffffffu, dr, i);
+            acc += 1;
+          }
+          drow = dnext;
+        }
+        if (valid) {
+          S.g[e] = gj;
+          S.be[e] = bej;
+        }
+        sh->hb[b & 1][lane] = valid ? myh : 0.0;
+        pmax = fmax(pmax, fabs(myh));
+        lap(1);
+      } else {
+        const int wt = tid - 32;
+        if (b + 1 < nb && !staged_ok && !CHAIN_PROBE_BIT(1)) stage_block(S, P, m, b + 1, S.stage + ((b + 1) & 1) * BUF_DOUBLES, wt, NWORK);
+        lap(0);
+        if (b >= 1 && !CHAIN_PROBE_BIT(0)) apply_block<Policy>(S, m, b - 1, sh->hb[(b - 1) & 1], b - 1, b, wt, NWORK);
+        lap(1);
+      }
+      __syncthreads();
+      lap(2);
+    }
+    if (nb >= 2) { // drain: the last block's steps reach the rest of the list
+      apply_block<Policy>(S, m, nb - 1, sh->hb[(nb - 1) & 1], nb - 1, -1, tid, T);
+    }
+    if (warp == 0) {
+      pmax = warp_max(pmax);
+      if (lane == 0) sh->pmax = pmax;
+    }
+    // ---- dropzeros!
+    int z = 0;
+    for (int i = tid; i < m; i += T) z |= (S.be[i] == 0.0);
+    z = __syncthreads_or(z);
+    R.npasses += 1;
+    R.visits += m;
+    R.accepted += __shfl_sync(0xffffffffu, acc, 0); // only meaningful on warp 0; fixed up below
+    R.maxH = sh->pmax;
+    staged_ok = ordered && nb <= 2 && !z;
+    if (z) { // rare: an entry left the active set — swap-with-last in list order
+      unsigned short *idx = S.ord;
+      for (int i = tid; i < m; i += T) idx[i] = (unsigned short)i;
+      __syncthreads();
+      if (tid == 0) {
+        int n = m, i = 0;
+        while (i < n) {
+          if (S.be[idx[i]] == 0.0) {
+            inlist[S.coord[idx[i]]] = 0;
+            if (i != n - 1) idx[i] = idx[n - 1];
+            n -= 1;
+          } else {
+            i += 1;
+          }
+        }
+        sh->newm = n;
+      }
+      __syncthreads();
+      const int mn = sh->newm;
+      double *tmpd = S.stage;
+      int *tmpi = reinterpret_cast<int *>(S.stage);
+      // permute the four per-entry arrays through the stage area (>= 4096 doubles)
+      for (int i = tid; i < mn; i += T) tmpd[i] = S.g[idx[i]];
+      __syncthreads();
+      for (int i = tid; i < mn; i += T) S.g[i] = tmpd[i];
+      __syncthreads();
+      for (int i = tid; i < mn; i += T) tmpd[i] = S.be[idx[i]];
+      __syncthreads();
+      for (int i = tid; i < mn; i += T) S.be[i] = tmpd[i];
+      __syncthreads();
+      for (int i = tid; i < mn; i += T) tmpi[i] = S.row[idx[i]];
+      __syncthreads();
+      for (int i = tid; i < mn; i += T) S.row[i] = tmpi[i];
+      __syncthreads();
+      if (S.coord != S.row) {
+        for (int i = tid; i < mn; i += T) tmpi[i] = S.coord[idx[i]];
+        __syncthreads();
+        for (int i = tid; i < mn; i += T) S.coord[i] = tmpi[i];
+        __syncthreads();
+      }
+      m = mn;
+    }
+    if (R.maxH < optTol) {
+      R.conv = 1;
+      break;
+    }
+  }
+  lap(3);
+  if (prof) {
+    const int o = tid == 0 ? 0 : 4;
+    for (int i = 0; i < 4; ++i) S.prof[o + i] += pc[i];
+  }
+  // the accepted-step count lives in warp 0: publish it to the block
+  __syncthreads();
+  if (tid == 0) sh->hb[0][0] = (double)R.accepted;
+  __syncthreads();
+  R.accepted = (long long)sh->hb[0][0];
+  R.m = m;
+  S.m = m;
+  return R;
+}
+
+} // namespace chain

@@ -21,6 +21,9 @@
 //  * no grid-wide sync, no host round trip between passes or between lambdas.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
+#include "chain_engine.cuh"
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -28,8 +31,7 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int COV_T = 512;
-constexpr int COV_RMAX = 8;
-constexpr int COV_ACT_CAP = COV_T * COV_RMAX; // entries the in-CTA engine can hold
+constexpr int COV_ACT_CAP = 4096; // most entries the in-CTA engine is ever given (launcher may pick less)
 constexpr int COV_MAXC = 16;
 constexpr unsigned KEY_NONE = 0xffffffffu;
 
@@ -55,6 +57,7 @@ struct Smem {
   int nact, flag, nonapp;
   int s2[2];
   unsigned long long mbar[2]; // candidate-exchange barriers (one per round parity)
+  chain::Shared ch;
 };
 
 __device__ __forceinline__ void named_bar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
@@ -64,7 +67,10 @@ struct Ctx {
   cg::cluster_group &cluster;
   Smem *sm;
   double *sAx, *sb, *sainv, *sw, *sbeta; // this CTA's slice (shared or global)
-  int *s_act, *s_idx;                    // CTA-0 engine scratch
+  int *s_act;                            // CTA-0 engine: coordinates of the stored entries
+  double *e_g, *e_be, *e_stage;          // CTA-0 engine state (chain_engine.cuh)
+  unsigned short *e_ord, *e_pos;
+  int ecap;                              // entries the engine can hold in this launch
   unsigned char *s_in, *s_vnz;           // per slice: member at pass start / tentative value non-zero
   int rank, C, L, lo, len, slice_in_smem;
 };
@@ -297,199 +303,85 @@ __device__ void list_update_full(Ctx &c, int m_old, int nonapp_total, unsigned l
 }
 
 // ------------------------------------------------------ active-set engine (CTA 0) --
-// Runs consecutive active-set passes until one has maxH < optTol or `maxPasses` are used.
-template <int R>
+// Consecutive active-set passes until one has maxH < optTol or `maxPasses` are used: the blocked
+// warp-level chain of chain_engine.cuh on (Ax_t, beta_t) of the stored entries, G = A[act, act]
+// gathered from the L2-resident columns of A.
+struct CovPolicy {
+  static constexpr bool HAS_RR = false;
+  const double *b, *ainv, *omega;
+  double lam;
+  __device__ __forceinline__ void load_consts(int k, double &c0, double &c1, double &c2) const {
+    c0 = __ldg(b + k);
+    c1 = __ldg(ainv + k);
+    const double w = omega ? __ldg(omega + k) : 1.0;
+    c2 = __dmul_rn(__dmul_rn(c1, lam), w);
+  }
+  // cd_differentiable_function.jl:330-337
+  __device__ __forceinline__ void step(double g, double be, double c0, double c1, double c2, double, double &nw, double &h,
+                                       double &dr) const {
+    const double gg = g + c0;
+    const double v = __dsub_rn(be, __dmul_rn(gg, c1));
+    nw = cd_shrink(v, c2);
+    h = nw - be;
+    dr = 0.0;
+  }
+  static __device__ __forceinline__ double apply(double g, double Gv, double h) { return __dadd_rn(g, __dmul_rn(Gv, h)); } // :343-345
+};
+
 __device__ void active_engine(Ctx &c, double lam, long long maxPasses, unsigned long long pass_counter) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
   const int tid = threadIdx.x;
-  int m = sm->nact;
-  const int m0 = m;
-  int per = (m + R - 1) / R;
-  int nthr = min(COV_T, ((per + 31) / 32) * 32);
-  if (nthr < 32) nthr = 32;
-  const bool ordered = a.randomize == 0;
-  double *scr_b0 = a.scr;              // [p] beta at entry, by snapshot index
-  double *scr_dlt = a.scr + a.p;       // [p] delta by snapshot index
-  double *scr_ax = a.scr + 2 * (long long)a.p; // [p] compaction staging
-  double *scr_be = a.scr + 3 * (long long)a.p;
-  int *act0 = a.iscr; // [p] snapshot of the list
-
-  int kk[R];
-  double Ax[R], be[R], bb[R], ai[R], th[R], acur[R], anxt[R];
-  const bool part = tid < nthr;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    int i = r * nthr + tid;
-    kk[r] = -1;
-    Ax[r] = be[r] = bb[r] = ai[r] = th[r] = acur[r] = anxt[r] = 0.0;
-    if (part && i < m) {
-      int k = a.act[i];
-      kk[r] = k;
-      be[r] = a.actval[i];
-      Ax[r] = slice_get(c, c.sAx, k);
-      bb[r] = __ldg(a.b + k);
-      ai[r] = __ldg(a.ainv + k);
-      double w = a.omega ? __ldg(a.omega + k) : 1.0;
-      th[r] = __dmul_rn(__dmul_rn(ai[r], lam), w);
-      c.s_act[i] = k;
-      act0[i] = k;
-      scr_b0[i] = be[r];
-    }
+  const int m0 = sm->nact;
+  double *scr_b0 = a.scr;        // [p] beta at entry, by snapshot index
+  double *scr_dlt = a.scr + a.p; // [p] delta by snapshot index
+  int *act0 = a.iscr;            // [p] snapshot of the list
+  for (int i = tid; i < m0; i += COV_T) {
+    const int k = a.act[i];
+    const double be = a.actval[i];
+    c.s_act[i] = k;
+    act0[i] = k;
+    c.e_be[i] = be;
+    scr_b0[i] = be;
+    c.e_g[i] = slice_get(c, c.sAx, k);
   }
   __syncthreads();
-
-  long long npasses = 0, visits = 0, accepted = 0;
-  double maxH = 0.0;
-  int conv = 0;
-  if (part) {
-    while (npasses < maxPasses) {
-      // ---- visit order of this pass (atom_iterator.jl:53-75, see common.cuh:cd_perm)
-      const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter + npasses);
-      auto entry_at = [&](int s) -> int { return ordered ? s : (int)cd_perm(pkm, (uint32_t)s); };
-      // ---- prefetch A[act, k] for steps 0 and 1
-      {
-        int e0 = m > 0 ? c.s_act[entry_at(0)] : 0, e1 = m > 1 ? c.s_act[entry_at(1)] : 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          acur[r] = (kk[r] >= 0 && m > 0) ? __ldg(a.A + (long long)e0 * a.lda + kk[r]) : 0.0;
-          anxt[r] = (kk[r] >= 0 && m > 1) ? __ldg(a.A + (long long)e1 * a.lda + kk[r]) : 0.0;
-        }
-      }
-      double pmax = 0.0;
-      for (int s = 0; s < m; ++s) {
-        const int i = entry_at(s);
-        // issue the gather for step s+2 early
-        double apre[R];
-        {
-          int e2 = (s + 2 < m) ? c.s_act[entry_at(s + 2)] : -1;
-#pragma unroll
-          for (int r = 0; r < R; ++r) apre[r] = (e2 >= 0 && kk[r] >= 0) ? __ldg(a.A + (long long)e2 * a.lda + kk[r]) : 0.0;
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (i == r * nthr + tid) {
-            const double g = Ax[r] + bb[r];
-            const double v = __dsub_rn(be[r], __dmul_rn(g, ai[r]));
-            const double nw = cd_shrink(v, th[r]);
-            sm->h[s & 1] = nw - be[r];
-            be[r] = nw;
-          }
-        }
-        named_bar(1, nthr);
-        const double h = sm->h[s & 1];
-        if (h != 0.0) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) Ax[r] = __dadd_rn(Ax[r], __dmul_rn(acur[r], h));
-          accepted += 1;
-        }
-        pmax = fmax(pmax, fabs(h));
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          acur[r] = anxt[r];
-          anxt[r] = apre[r];
-        }
-      }
-      npasses += 1;
-      visits += m;
-      maxH = pmax;
-      // ---- dropzeros!
-      if (tid == 0) sm->flag = 0;
-      named_bar(1, nthr);
-      {
-        int z = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) z |= (kk[r] >= 0 && be[r] == 0.0);
-        if (z) sm->flag = 1;
-      }
-      named_bar(1, nthr);
-      if (sm->flag) { // rare: an entry left the active set
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          int i = r * nthr + tid;
-          if (kk[r] >= 0) {
-            scr_ax[i] = Ax[r];
-            scr_be[i] = be[r];
-          }
-          if (i < m) c.s_idx[i] = i;
-        }
-        named_bar(1, nthr);
-        if (tid == 0) {
-          int n = m, i = 0;
-          while (i < n) {
-            if (scr_be[c.s_idx[i]] == 0.0) {
-              a.inlist[c.s_act[c.s_idx[i]]] = 0;
-              if (i != n - 1) c.s_idx[i] = c.s_idx[n - 1];
-              n -= 1;
-            } else {
-              i += 1;
-            }
-          }
-          sm->nact = n;
-        }
-        named_bar(1, nthr);
-        const int mn = sm->nact;
-        int nk[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          int i = r * nthr + tid;
-          nk[r] = -1;
-          if (i < mn) {
-            int src = c.s_idx[i];
-            nk[r] = c.s_act[src];
-            Ax[r] = scr_ax[src];
-            be[r] = scr_be[src];
-          }
-        }
-        named_bar(1, nthr);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          int i = r * nthr + tid;
-          kk[r] = nk[r];
-          if (i < mn) {
-            const int k = nk[r];
-            c.s_act[i] = k;
-            bb[r] = __ldg(a.b + k);
-            ai[r] = __ldg(a.ainv + k);
-            double w = a.omega ? __ldg(a.omega + k) : 1.0;
-            th[r] = __dmul_rn(__dmul_rn(ai[r], lam), w);
-          }
-        }
-        m = mn;
-        named_bar(1, nthr);
-      }
-      if (maxH < a.optTol) {
-        conv = 1;
-        break;
-      }
-    }
-  }
-  __syncthreads();
+  chain::State S;
+  S.m = m0;
+  S.row = c.s_act;
+  S.coord = c.s_act;
+  S.g = c.e_g;
+  S.be = c.e_be;
+  S.ord = c.e_ord;
+  S.pos = c.e_pos;
+  S.stage = c.e_stage;
+  S.sh = &sm->ch;
+  S.G = a.A;
+  S.ldg = a.lda;
+  S.prof = a.prof ? a.prof + 16 : nullptr;
+  const CovPolicy P{a.b, a.ainv, a.omega, lam};
+  const chain::Result r = chain::run<COV_T>(S, P, 0.0, maxPasses, pass_counter, a.randomize == 0, a.seed, a.optTol, a.inlist);
   // ---- publish: final list, dense beta, per-snapshot-entry delta
   for (int i = tid; i < m0; i += COV_T) a.beta[act0[i]] = 0.0;
   __syncthreads();
-  if (part) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int i = r * nthr + tid;
-      if (kk[r] >= 0) {
-        a.beta[kk[r]] = be[r];
-        a.act[i] = kk[r];
-        a.actval[i] = be[r];
-      }
-    }
+  for (int i = tid; i < r.m; i += COV_T) {
+    const int k = c.s_act[i];
+    const double be = c.e_be[i];
+    a.beta[k] = be;
+    a.act[i] = k;
+    a.actval[i] = be;
   }
   __syncthreads();
   for (int i = tid; i < m0; i += COV_T) scr_dlt[i] = a.beta[act0[i]] - scr_b0[i];
   if (tid == 0) {
-    sm->nact = m;
-    sm->bc.npasses = npasses;
-    sm->bc.visits = visits;
-    sm->bc.accepted = accepted;
-    sm->bc.maxH = maxH;
+    sm->nact = r.m;
+    sm->bc.npasses = r.npasses;
+    sm->bc.visits = r.visits;
+    sm->bc.accepted = r.accepted;
+    sm->bc.maxH = r.maxH;
     sm->bc.m0 = m0;
-    sm->bc.nact = m;
-    sm->bc.conv = conv;
+    sm->bc.nact = r.m;
+    sm->bc.conv = r.conv;
   }
   __syncthreads();
 }
@@ -525,7 +417,7 @@ __device__ void refresh_slice(Ctx &c, int m0) {
 }
 
 template <bool PROF>
-__global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int L, int slice_in_smem) {
+__global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int L, int slice_in_smem, int ecap) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx c{a, cluster};
@@ -540,10 +432,19 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   unsigned char *sp = smem_raw;
   c.sm = reinterpret_cast<Smem *>(sp);
   sp += (sizeof(Smem) + 15) / 16 * 16;
+  c.ecap = ecap;
+  c.e_stage = reinterpret_cast<double *>(sp);
+  sp += chain::STAGE_DOUBLES * sizeof(double);
+  c.e_g = reinterpret_cast<double *>(sp);
+  sp += (size_t)ecap * sizeof(double);
+  c.e_be = reinterpret_cast<double *>(sp);
+  sp += (size_t)ecap * sizeof(double);
   c.s_act = reinterpret_cast<int *>(sp);
-  sp += COV_ACT_CAP * sizeof(int);
-  c.s_idx = reinterpret_cast<int *>(sp);
-  sp += COV_ACT_CAP * sizeof(int);
+  sp += (size_t)ecap * sizeof(int);
+  c.e_ord = reinterpret_cast<unsigned short *>(sp);
+  sp += (size_t)ecap * sizeof(unsigned short);
+  c.e_pos = reinterpret_cast<unsigned short *>(sp);
+  sp += (size_t)ecap * sizeof(unsigned short);
   if (slice_in_smem) {
     double *d = reinterpret_cast<double *>(sp);
     c.sAx = d;
@@ -586,6 +487,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   cluster.sync();
 
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (PROF && c.rank == 0 && tid < 8) a.prof[16 + tid] = 0;
   const long long t_start = PROF ? clock64() : 0;
   unsigned round = 0; // candidate-exchange rounds so far (selects slot parity and mbarrier phase)
   bool first_pass = true;
@@ -640,17 +542,11 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         if (c.rank == 0) {
           const int m = c.sm->nact;
           const long long budget = a.maxIter - iter;
-          if (m > COV_ACT_CAP) {
+          if (m > c.ecap) {
             if (tid == 0) c.sm->bc.status = 2;
             __syncthreads();
-          } else if (m <= COV_T) {
-            active_engine<1>(c, lam, budget, pass_counter);
-          } else if (m <= 2 * COV_T) {
-            active_engine<2>(c, lam, budget, pass_counter);
-          } else if (m <= 4 * COV_T) {
-            active_engine<4>(c, lam, budget, pass_counter);
           } else {
-            active_engine<8>(c, lam, budget, pass_counter);
+            active_engine(c, lam, budget, pass_counter);
           }
         }
         cluster.sync();
@@ -834,7 +730,10 @@ int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, in
 
 int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   static bool attr_done = false;
-  const size_t fixed = (sizeof(Smem) + 15) / 16 * 16 + COV_ACT_CAP * (2 * sizeof(int));
+  auto fixed_for = [](int ecap) {
+    return (sizeof(Smem) + 15) / 16 * 16 + chain::STAGE_DOUBLES * sizeof(double) + (size_t)ecap * (2 * sizeof(double) + sizeof(int) + 2 * sizeof(unsigned short));
+  };
+  const size_t fixed = fixed_for(COV_ACT_CAP);
   const size_t max_dyn = 227 * 1024;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
@@ -879,9 +778,14 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   while (C > 1 && a.p < C * 32) C >>= 1; // tiny problems: fewer, fuller slices
   int L = (a.p + C - 1) / C;
   L = (L + 1) & ~1;
-  size_t need = fixed + (size_t)5 * L * sizeof(double) + 2 * (size_t)L + 16;
-  int slice_in_smem = need <= max_dyn;
-  size_t dyn = slice_in_smem ? need : fixed;
+  // engine capacity: as large as still leaves room for the slices in shared memory
+  const size_t slices = (size_t)5 * L * sizeof(double) + 2 * (size_t)L + 16;
+  int ecap = COV_ACT_CAP;
+  if (const char *env = getenv("CDGPU_ECAP_MAX")) ecap = std::max(512, std::min(COV_ACT_CAP, atoi(env) / 512 * 512));
+  while (ecap > 1024 && fixed_for(ecap) + slices > max_dyn) ecap >>= 1;
+  int slice_in_smem = fixed_for(ecap) + slices <= max_dyn;
+  if (!slice_in_smem) ecap = COV_ACT_CAP;
+  size_t dyn = slice_in_smem ? fixed_for(ecap) + slices : fixed_for(ecap);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C);
   cfg.blockDim = dim3(COV_T);
@@ -895,9 +799,9 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (a.prof)
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<true>, a, L, slice_in_smem));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<true>, a, L, slice_in_smem, ecap));
   else
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<false>, a, L, slice_in_smem));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<false>, a, L, slice_in_smem, ecap));
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }

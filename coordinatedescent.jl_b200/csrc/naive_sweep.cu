@@ -19,6 +19,7 @@
 //    (s = d + a_k x_k, ||r+||^2 = ||r||^2 + 2 x_k d + x_k^2 a_k), so a visit is still one column read.
 #include <cooperative_groups.h>
 
+#include "chain_engine.cuh"
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -47,6 +48,7 @@ struct NSmem {
   double bval[2], bval2[2];
   int nact, flag, nonapp;
   int s2[2];
+  chain::Shared ch;
 };
 
 struct NCtx {
@@ -57,7 +59,11 @@ struct NCtx {
   double rr;     // ||r||^2 (every thread of every CTA holds the same value)
   HEntry *hbuf;  // global, 2 * CH
   NBcast *bc;    // global
-  int *s_act, *s_g, *s_idx; // shared, NV_GCAP ints each: scratch of the covariance-form active engine
+  // shared state of the covariance-form active engine (chain_engine.cuh), gcap entries (0: engine disabled)
+  int *e_row, *e_coord;
+  double *e_g, *e_be, *e_stage;
+  unsigned short *e_ord, *e_pos;
+  int gcap;
   int CH, G, bid;
 };
 
@@ -225,74 +231,108 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     sm->nonapp = 0;
     __stcg(nonapp_flag, 0);
   }
-  // chunk length: every mover costs a re-evaluation of the rest of its chunk (~CH/2 columns) and every chunk
-  // a grid barrier, so CH ~ sqrt(2 p T_sync / (E T_col)) with E ~ current active-set size movers per pass,
-  // T_sync ~ 2.5 us, T_col ~ 8n B / 4 TB/s
-  int CHp = (int)sqrt(2.5e6 * (double)a.p / ((double)(nact_hint + 4) * (double)a.n));
-  CHp = max(min(CHp, c.CH), min(c.CH, 64));
-  for (int q0 = 0; q0 < a.p; q0 += CHp) {
-    const int qlen = min(CHp, a.p - q0);
-    int start = 0;
-    for (;;) {
-      HEntry *hb = c.hbuf + (size_t)rp * c.CH;
-      const long long ta = clock64();
-      // position j of the chunk belongs to CTA j % G, warp (j / G) % NV_W
-      for (int j = c.bid + c.G * warp; j < qlen; j += c.G * NV_W) {
-        if (j < start) continue;
+  // Window of columns evaluated in parallel against the same r.  A mover invalidates everything behind it,
+  // so the window restarts small right behind a mover (those columns are L2-hot: a cheap re-evaluation)
+  // and doubles after every clean round up to CH (streaming regime: one barrier per CH columns).
+  // Right behind a mover the window is G columns, ONE PER CTA (16 warps share a column: lowest latency,
+  // movers tend to cluster); a clean round then widens it to one column per warp, 2 per warp, ...
+  const int Wwarp = min(c.CH, c.G * NV_W);
+  int W = nact_hint > 0 ? min(c.CH, c.G) : Wwarp;
+  int q0 = 0;
+  while (q0 < a.p) {
+    const int qlen = min(W, a.p - q0);
+    HEntry *hb = c.hbuf + (size_t)rp * c.CH;
+    const long long ta = clock64();
+    if (W <= c.G) { // CTA-per-column mode
+      const int j = c.bid;
+      if (j < qlen) {
         const int k = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
-        const double d = warp_col_dot(c, a.X + (long long)k * a.ldx);
-        if (lane == 0) {
+        const double *col = a.X + (long long)k * a.ldx;
+        double s = 0.0;
+        for (int t0 = tid; t0 < a.n; t0 += 8 * NV_T) {
+          double xv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) xv[u] = (t0 + u * NV_T < a.n) ? __ldg(col + t0 + u * NV_T) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int t = t0 + u * NV_T;
+            if (t < a.n) s = fma(c.w ? xv[u] * c.w[t] : xv[u], c.r[t], s);
+          }
+        }
+        const double d = block_sum(sm, s, 1);
+        if (tid == 0) {
           double nw, h;
           bool tnz;
           coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
                        c.rr, nw, h, tnz);
-          // sqrt-lasso never appends temporarily (x[k] = newVal, :278-283), so nothing to track there
           const int app = (a.kind == CDGPU_LOSS_SQRT || tnz || __ldcg(a.inlist + k)) ? 1 : 0;
           __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
           __stcg(&hb[j].app, app);
           if (!app) __stcg(nonapp_flag, 1);
-          if (h != 0.0) atomicMin(gmin + round3, (unsigned int)j); // first position of the round that moves
+          if (h != 0.0) atomicMin(gmin + round3, (unsigned int)j);
         }
       }
-      const long long tb = clock64();
-      c.grid.sync();
-      const long long tc = clock64();
-      pf[0] += tb - ta;
-      pf[1] += tc - tb;
-      pf[7] += 1;
-      const unsigned int jmin = __ldcg(gmin + round3);
-      // the word used two rounds from now was last read before this barrier: reset it
-      if (c.bid == 0 && tid == 0) __stcg(gmin + (round3 + 2) % 3, 0xffffffffu);
-      round3 = (round3 + 1) % 3;
-      rp ^= 1;
-      if (c.bid == 0 && __ldcg(nonapp_flag)) { // rare: remember the finalised non-appended coordinates
-        const int jend = jmin == 0xffffffffu ? qlen : (int)jmin;
-        for (int j = start + tid; j < jend; j += NV_T)
-          if (__ldcg(&hb[j].app) == 0)
-            nonapp_list[atomicAdd(&sm->nonapp, 1)] = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
-        __syncthreads();
+    } else {
+    // position j of the window belongs to CTA j % G, warp (j / G) % NV_W
+    for (int j = c.bid + c.G * warp; j < qlen; j += c.G * NV_W) {
+      const int k = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
+      const double d = warp_col_dot(c, a.X + (long long)k * a.ldx);
+      if (lane == 0) {
+        double nw, h;
+        bool tnz;
+        coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
+                     c.rr, nw, h, tnz);
+        // sqrt-lasso never appends temporarily (x[k] = newVal, :278-283), so nothing to track there
+        const int app = (a.kind == CDGPU_LOSS_SQRT || tnz || __ldcg(a.inlist + k)) ? 1 : 0;
+        __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
+        __stcg(&hb[j].app, app);
+        if (!app) __stcg(nonapp_flag, 1);
+        if (h != 0.0) atomicMin(gmin + round3, (unsigned int)j); // first position of the round that moves
       }
-      const long long td = clock64();
-      pf[2] += td - tc;
-      if (jmin == 0xffffffffu) break;
-      const int k = ordered ? q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(q0 + jmin));
-      const double2 e = __ldcg(reinterpret_cast<const double2 *>(hb + jmin));
-      const double h = e.x, nw = e.y;
-      if (c.bid == 0 && tid == 0) {
-        __stcg(a.beta + k, nw);
-        if (!a.inlist[k]) { // setindex! appends on the first non-zero store
-          __stcg(a.inlist + k, (unsigned char)1);
-          a.act[sm->nact] = k;
-          sm->nact += 1;
-        }
-      }
-      apply_step(c, a.X + (long long)k * a.ldx, h);
-      maxH = fmax(maxH, fabs(h));
-      accepted += 1;
-      start = (int)jmin + 1;
-      pf[3] += clock64() - td;
-      if (start >= qlen) break;
     }
+    }
+    const long long tb = clock64();
+    c.grid.sync();
+    const long long tc = clock64();
+    pf[0] += tb - ta;
+    pf[1] += tc - tb;
+    pf[7] += 1;
+    const unsigned int jmin = __ldcg(gmin + round3);
+    // the word used two rounds from now was last read before this barrier: reset it
+    if (c.bid == 0 && tid == 0) __stcg(gmin + (round3 + 2) % 3, 0xffffffffu);
+    round3 = (round3 + 1) % 3;
+    rp ^= 1;
+    if (c.bid == 0 && __ldcg(nonapp_flag)) { // rare: remember the finalised non-appended coordinates
+      const int jend = jmin == 0xffffffffu ? qlen : (int)jmin;
+      for (int j = tid; j < jend; j += NV_T)
+        if (__ldcg(&hb[j].app) == 0)
+          nonapp_list[atomicAdd(&sm->nonapp, 1)] = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
+      __syncthreads();
+    }
+    const long long td = clock64();
+    pf[2] += td - tc;
+    if (jmin == 0xffffffffu) { // clean round: every position of the window is final
+      q0 += qlen;
+      W = W <= c.G ? Wwarp : min(c.CH, 2 * W);
+      continue;
+    }
+    const int k = ordered ? q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(q0 + jmin));
+    const double2 e = __ldcg(reinterpret_cast<const double2 *>(hb + jmin));
+    const double h = e.x, nw = e.y;
+    if (c.bid == 0 && tid == 0) {
+      __stcg(a.beta + k, nw);
+      if (!a.inlist[k]) { // setindex! appends on the first non-zero store
+        __stcg(a.inlist + k, (unsigned char)1);
+        a.act[sm->nact] = k;
+        sm->nact += 1;
+      }
+    }
+    apply_step(c, a.X + (long long)k * a.ldx, h);
+    maxH = fmax(maxH, fabs(h));
+    accepted += 1;
+    q0 += (int)jmin + 1;
+    W = min(c.CH, c.G);
+    pf[3] += clock64() - td;
   }
   return maxH;
 }
@@ -439,7 +479,6 @@ __device__ void active_phase(NCtx &c, double lam, long long maxPasses, unsigned 
 // finally r -= X_A (beta - beta_at_entry) is applied once.  Same iterates as the reference up to
 // rounding (d maintained incrementally instead of re-reduced); same visit order and list semantics.
 constexpr int NV_GCAP = NV_GCAP_; // largest active set handled this way (G scratch = 32 MB)
-constexpr int NV_RMAX = NV_GCAP / NV_T;
 
 __device__ __forceinline__ void nbar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
 
@@ -486,203 +525,104 @@ __device__ void build_active_gram(NCtx &c, int m, double *G, double *d) {
   }
 }
 
-template <int R>
+// closed-form updates on d_t = X_t'(w.r) for the chain engine (chain_engine.cuh)
+struct LsPolicy { // cd_differentiable_function.jl:101-104 / :184-187
+  static constexpr bool HAS_RR = false;
+  const double *colsq, *omega;
+  double lam, nd;
+  __device__ __forceinline__ void load_consts(int k, double &c0, double &c1, double &c2) const {
+    c0 = __ldg(colsq + k);
+    c1 = 0.0;
+    c2 = __dmul_rn(__dmul_rn(nd / c0, lam), omega ? __ldg(omega + k) : 1.0);
+  }
+  __device__ __forceinline__ void step(double d, double be, double aa, double, double th, double, double &nw, double &h,
+                                       double &dr) const {
+    const double v = __dadd_rn(be, d / aa);
+    nw = cd_shrink(v, th);
+    h = nw - be;
+    dr = 0.0;
+  }
+  static __device__ __forceinline__ double apply(double d, double Gv, double h) { return __dsub_rn(d, __dmul_rn(Gv, h)); }
+};
+struct SqrtPolicy { // :259-283 with s, ||r+||^2 from d, ||r||^2, a
+  static constexpr bool HAS_RR = true;
+  const double *colsq, *omega;
+  double lam;
+  __device__ __forceinline__ void load_consts(int k, double &c0, double &c1, double &c2) const {
+    c0 = __ldg(colsq + k);
+    c2 = lam * (omega ? __ldg(omega + k) : 1.0);
+    c1 = c2 / sqrt(1.0 - c2 * c2 / c0); // the state-independent factor of :280-283, same operation order
+  }
+  __device__ __forceinline__ void step(double d, double old, double aa, double lq, double l, double rr, double &nw, double &h,
+                                       double &dr) const {
+    const double sv = d + aa * old;
+    const double rsq = rr + 2.0 * old * d + old * old * aa;
+    const double t = l * sqrt(rsq);
+    if (fabs(sv) <= t)
+      nw = 0.0;
+    else if (sv > t)
+      nw = (sv - lq * sqrt(rsq - sv * sv / aa)) / aa;
+    else
+      nw = (sv + lq * sqrt(rsq - sv * sv / aa)) / aa;
+    h = nw - old;
+    dr = h * (h * aa - 2.0 * d); // change of ||r||^2
+  }
+  static __device__ __forceinline__ double apply(double d, double Gv, double h) { return __dsub_rn(d, __dmul_rn(Gv, h)); }
+};
+
+// CTA 0: the active-set passes as the blocked warp-level chain over (d, beta) of the m0 stored entries
 __device__ void gram_engine(NCtx &c, double lam, long long maxPasses, unsigned long long pass_counter, int m0,
-                            const double *G, const double *d0, int *s_act, int *s_g, int *s_idx) {
+                            const double *G, const double *d0) {
   const NaiveArgs &a = c.a;
   NSmem *sm = c.sm;
   const int tid = threadIdx.x, n = a.n;
-  const bool ordered = a.randomize == 0, is_sqrt = a.kind == CDGPU_LOSS_SQRT;
-  int m = m0;
-  int per = (m + R - 1) / R;
-  int nthr = min(NV_T, ((per + 31) / 32) * 32);
-  if (nthr < 32) nthr = 32;
   double *scr_b0 = a.scr + 8 + 9 * (long long)a.p + 32; // [<= NV_GCAP] each, behind the compaction staging
-  double *scr_dlt = scr_b0 + NV_GCAP, *scr_d = scr_dlt + NV_GCAP, *scr_be = scr_d + NV_GCAP;
+  double *scr_dlt = scr_b0 + NV_GCAP;
   int *act0 = a.iscr; // snapshot of the list
-
-  int kk[R], gi[R];
-  double dd[R], be[R], aa[R], th[R], gcur[R], gnxt[R];
-  const bool part = tid < nthr;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i = r * nthr + tid;
-    kk[r] = -1;
-    gi[r] = 0;
-    dd[r] = be[r] = aa[r] = th[r] = gcur[r] = gnxt[r] = 0.0;
-    if (part && i < m) {
-      const int k = a.act[i];
-      kk[r] = k;
-      gi[r] = i;
-      be[r] = a.actval[i];
-      dd[r] = __ldcg(d0 + i);
-      aa[r] = __ldg(a.colsq + k);
-      const double om = a.omega ? __ldg(a.omega + k) : 1.0;
-      th[r] = is_sqrt ? lam * om : __dmul_rn(__dmul_rn((double)n / aa[r], lam), om);
-      s_act[i] = k;
-      s_g[i] = i;
-      act0[i] = k;
-      scr_b0[i] = be[r];
-    }
-  }
-  double rr = c.rr; // sqrt-lasso: ||r||^2, tracked by every participating thread
-  __syncthreads();
-
-  long long npasses = 0, visits = 0, accepted = 0;
-  double maxH = 0.0;
-  int conv = 0;
-  if (part) {
-    while (npasses < maxPasses) {
-      const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter + npasses);
-      auto entry_at = [&](int s) -> int { return ordered ? s : (int)cd_perm(pkm, (uint32_t)s); };
-      {
-        const int e0 = m > 0 ? s_g[entry_at(0)] : 0, e1 = m > 1 ? s_g[entry_at(1)] : 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          gcur[r] = (kk[r] >= 0 && m > 0) ? __ldcg(G + gi[r] + (long long)e0 * m0) : 0.0;
-          gnxt[r] = (kk[r] >= 0 && m > 1) ? __ldcg(G + gi[r] + (long long)e1 * m0) : 0.0;
-        }
-      }
-      double pmax = 0.0;
-      for (int s = 0; s < m; ++s) {
-        const int i = entry_at(s);
-        double gpre[R];
-        {
-          const int e2 = (s + 2 < m) ? s_g[entry_at(s + 2)] : -1;
-#pragma unroll
-          for (int r = 0; r < R; ++r) gpre[r] = (e2 >= 0 && kk[r] >= 0) ? __ldcg(G + gi[r] + (long long)e2 * m0) : 0.0;
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (i == r * nthr + tid) {
-            double nw, h;
-            if (is_sqrt) { // :259-283 with s, ||r+||^2 from d, ||r||^2, a
-              const double old = be[r], sv = dd[r] + aa[r] * old;
-              const double rsq = rr + 2.0 * old * dd[r] + old * old * aa[r];
-              const double l = th[r], t = l * sqrt(rsq);
-              if (fabs(sv) <= t)
-                nw = 0.0;
-              else if (sv > t)
-                nw = (sv - l / sqrt(1.0 - l * l / aa[r]) * sqrt(rsq - sv * sv / aa[r])) / aa[r];
-              else
-                nw = (sv + l / sqrt(1.0 - l * l / aa[r]) * sqrt(rsq - sv * sv / aa[r])) / aa[r];
-            } else {
-              const double v = __dadd_rn(be[r], dd[r] / aa[r]);
-              nw = cd_shrink(v, th[r]);
-            }
-            h = nw - be[r];
-            sm->bval[s & 1] = h;
-            if (is_sqrt) sm->bval2[s & 1] = h * (h * aa[r] - 2.0 * dd[r]); // change of ||r||^2
-            be[r] = nw;
-          }
-        }
-        nbar(1, nthr);
-        const double h = sm->bval[s & 1];
-        if (h != 0.0) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) dd[r] = __dsub_rn(dd[r], __dmul_rn(gcur[r], h));
-          if (is_sqrt) rr += sm->bval2[s & 1];
-          accepted += 1;
-        }
-        pmax = fmax(pmax, fabs(h));
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          gcur[r] = gnxt[r];
-          gnxt[r] = gpre[r];
-        }
-      }
-      npasses += 1;
-      visits += m;
-      maxH = pmax;
-      // ---- dropzeros!
-      if (tid == 0) sm->flag = 0;
-      nbar(1, nthr);
-      {
-        int z = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) z |= (kk[r] >= 0 && be[r] == 0.0);
-        if (z) sm->flag = 1;
-      }
-      nbar(1, nthr);
-      if (sm->flag) { // rare: an entry left the active set
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int i = r * nthr + tid;
-          if (kk[r] >= 0) {
-            scr_d[i] = dd[r];
-            scr_be[i] = be[r];
-          }
-          if (i < m) s_idx[i] = i;
-        }
-        nbar(1, nthr);
-        if (tid == 0) {
-          int nn = m, i = 0;
-          while (i < nn) {
-            if (scr_be[s_idx[i]] == 0.0) {
-              a.inlist[s_act[s_idx[i]]] = 0;
-              if (i != nn - 1) s_idx[i] = s_idx[nn - 1];
-              nn -= 1;
-            } else {
-              i += 1;
-            }
-          }
-          sm->nact = nn;
-        }
-        nbar(1, nthr);
-        const int mn = sm->nact;
-        int nk[R], ng[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int i = r * nthr + tid;
-          nk[r] = -1;
-          ng[r] = 0;
-          if (i < mn) {
-            const int src = s_idx[i];
-            nk[r] = s_act[src];
-            ng[r] = s_g[src];
-            dd[r] = scr_d[src];
-            be[r] = scr_be[src];
-          }
-        }
-        nbar(1, nthr);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int i = r * nthr + tid;
-          kk[r] = nk[r];
-          gi[r] = ng[r];
-          if (i < mn) {
-            const int k = nk[r];
-            s_act[i] = k;
-            s_g[i] = ng[r];
-            aa[r] = __ldg(a.colsq + k);
-            const double om = a.omega ? __ldg(a.omega + k) : 1.0;
-            th[r] = is_sqrt ? lam * om : __dmul_rn(__dmul_rn((double)n / aa[r], lam), om);
-          }
-        }
-        m = mn;
-        nbar(1, nthr);
-      }
-      if (maxH < a.optTol) {
-        conv = 1;
-        break;
-      }
-    }
+  for (int i = tid; i < m0; i += NV_T) {
+    const int k = a.act[i];
+    const double be = a.actval[i];
+    c.e_coord[i] = k;
+    c.e_row[i] = i;
+    act0[i] = k;
+    c.e_be[i] = be;
+    scr_b0[i] = be;
+    c.e_g[i] = __ldcg(d0 + i);
   }
   __syncthreads();
+  chain::State S;
+  S.m = m0;
+  S.row = c.e_row;
+  S.coord = c.e_coord;
+  S.g = c.e_g;
+  S.be = c.e_be;
+  S.ord = c.e_ord;
+  S.pos = c.e_pos;
+  S.stage = c.e_stage;
+  S.sh = &sm->ch;
+  S.G = G;
+  S.ldg = m0;
+  S.prof = a.prof ? a.prof + 16 : nullptr;
+  chain::Result r;
+  const bool ordered = a.randomize == 0;
+  if (a.kind == CDGPU_LOSS_SQRT) {
+    const SqrtPolicy P{a.colsq, a.omega, lam};
+    r = chain::run<NV_T>(S, P, c.rr, maxPasses, pass_counter, ordered, a.seed, a.optTol, a.inlist);
+  } else {
+    const LsPolicy P{a.colsq, a.omega, lam, (double)n};
+    r = chain::run<NV_T>(S, P, 0.0, maxPasses, pass_counter, ordered, a.seed, a.optTol, a.inlist);
+  }
+  const int m = r.m;
   // ---- publish the new iterate and fold the change into r: r -= X[:, act0] (beta - beta_at_entry)
   for (int i = tid; i < m0; i += NV_T) __stcg(a.beta + act0[i], 0.0);
   __syncthreads();
-  if (part) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = r * nthr + tid;
-      if (kk[r] >= 0) {
-        __stcg(a.beta + kk[r], be[r]);
-        a.act[i] = kk[r];
-        a.actval[i] = be[r];
-        __stcg(a.inlist + kk[r], (unsigned char)1);
-      }
-    }
+  for (int i = tid; i < m; i += NV_T) {
+    const int k = c.e_coord[i];
+    const double be = c.e_be[i];
+    __stcg(a.beta + k, be);
+    a.act[i] = k;
+    a.actval[i] = be;
+    __stcg(a.inlist + k, (unsigned char)1);
   }
   __syncthreads();
   for (int i = tid; i < m0; i += NV_T) scr_dlt[i] = __ldcg(a.beta + act0[i]) - scr_b0[i];
@@ -706,11 +646,11 @@ __device__ void gram_engine(NCtx &c, double lam, long long maxPasses, unsigned l
   }
   if (tid == 0) {
     sm->nact = m;
-    c.bc->npasses = npasses;
-    c.bc->visits = visits;
-    c.bc->accepted = accepted;
-    c.bc->maxH = maxH;
-    c.bc->conv = conv;
+    c.bc->npasses = r.npasses;
+    c.bc->visits = r.visits;
+    c.bc->accepted = r.accepted;
+    c.bc->maxH = r.maxH;
+    c.bc->conv = r.conv;
     c.bc->nact = m;
   }
   __threadfence();
@@ -737,15 +677,28 @@ __device__ double shared_sumsq(NCtx &c) {
   return v;
 }
 
-__global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, int CH, HEntry *hbuf, NBcast *bc) {
+__global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, int CH, HEntry *hbuf, NBcast *bc, int gcap) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NCtx c{a, grid};
   c.sm = reinterpret_cast<NSmem *>(smem_raw);
-  c.s_act = reinterpret_cast<int *>(smem_raw + (sizeof(NSmem) + 15) / 16 * 16);
-  c.s_g = c.s_act + NV_GCAP_;
-  c.s_idx = c.s_g + NV_GCAP_;
-  double *sd = reinterpret_cast<double *>(c.s_idx + NV_GCAP_);
+  unsigned char *sp = smem_raw + (sizeof(NSmem) + 15) / 16 * 16;
+  c.gcap = gcap;
+  c.e_stage = reinterpret_cast<double *>(sp);
+  sp += gcap ? chain::STAGE_DOUBLES * sizeof(double) : 0;
+  c.e_g = reinterpret_cast<double *>(sp);
+  sp += (size_t)gcap * sizeof(double);
+  c.e_be = reinterpret_cast<double *>(sp);
+  sp += (size_t)gcap * sizeof(double);
+  c.e_row = reinterpret_cast<int *>(sp);
+  sp += (size_t)gcap * sizeof(int);
+  c.e_coord = reinterpret_cast<int *>(sp);
+  sp += (size_t)gcap * sizeof(int);
+  c.e_ord = reinterpret_cast<unsigned short *>(sp);
+  sp += (size_t)gcap * sizeof(unsigned short);
+  c.e_pos = reinterpret_cast<unsigned short *>(sp);
+  sp += (size_t)gcap * sizeof(unsigned short);
+  double *sd = reinterpret_cast<double *>(sp);
   c.r = sd;
   c.w = a.w ? sd + ((a.n + 1) & ~1) : nullptr; // keep w 16-byte aligned
   c.hbuf = hbuf;
@@ -763,6 +716,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   c.rr = shared_sumsq(c);
 
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (a.prof && c.bid == 0 && tid < 8) a.prof[16 + tid] = 0;
   const long long t_start = clock64();
   int rp = 0, round3 = 0;
   int nact_hint = *a.nact; // every CTA's view of the list length (refreshed whenever CTA 0 publishes it)
@@ -818,18 +772,12 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           grid.sync(); // CTA 0 has published the list length
           const int m_act = __ldcg(&bc->nact);
           nact_hint = m_act;
-          if (m_act >= 1 && m_act <= NV_GCAP && a.gram) {
+          if (m_act >= 1 && m_act <= c.gcap && a.gram) {
             double *Gs = a.gram, *ds = a.gram + (long long)NV_GCAP * NV_GCAP;
             build_active_gram(c, m_act, Gs, ds);
             grid.sync();
             if (c.bid == 0) {
-              const long long budget = a.maxIter - iter;
-              if (m_act <= NV_T)
-                gram_engine<1>(c, lam, budget, pass_counter, m_act, Gs, ds, c.s_act, c.s_g, c.s_idx);
-              else if (m_act <= 2 * NV_T)
-                gram_engine<2>(c, lam, budget, pass_counter, m_act, Gs, ds, c.s_act, c.s_g, c.s_idx);
-              else
-                gram_engine<NV_RMAX>(c, lam, budget, pass_counter, m_act, Gs, ds, c.s_act, c.s_g, c.s_idx);
+              gram_engine(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);
             }
           } else if (c.bid == 0) {
             active_phase(c, lam, a.maxIter - iter, pass_counter);
@@ -1035,8 +983,17 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
     CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
     attr_done = true;
   }
-  const size_t dyn = (sizeof(NSmem) + 15) / 16 * 16 + 3 * NV_GCAP * sizeof(int) +
-                     (size_t)((a.n + 1) & ~1) * sizeof(double) * (a.w ? 2 : 1);
+  // shared memory: r (and w) + the state of the covariance-form active engine, whose capacity shrinks
+  // (down to 0 = disabled, CTA 0 then runs active passes column by column) as n grows
+  const size_t rbytes = (size_t)((a.n + 1) & ~1) * sizeof(double) * (a.w ? 2 : 1) + (sizeof(NSmem) + 15) / 16 * 16;
+  auto engine_bytes = [](int gcap) {
+    return gcap ? chain::STAGE_DOUBLES * sizeof(double) + (size_t)gcap * (2 * sizeof(double) + 2 * sizeof(int) + 2 * sizeof(unsigned short))
+                : (size_t)0;
+  };
+  int gcap = a.gram ? NV_GCAP : 0;
+  while (gcap >= 256 && rbytes + engine_bytes(gcap) > max_dyn) gcap >>= 1;
+  if (gcap < 256) gcap = 0;
+  const size_t dyn = rbytes + engine_bytes(gcap);
   if (dyn > max_dyn)
     return cdgpu_set_error(CDGPU_ECAP,
                            "naive-form sweep keeps r%s in shared memory: n = %d exceeds the %zu-byte limit; use the "
@@ -1054,7 +1011,7 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
   G = max(1, min(G, occ * h->sm_count));
   // chunk: up to 8 columns per warp per round, at most ~48 MB of columns so a re-evaluation hits L2
   long long cols_l2 = (48ll << 20) / ((long long)a.n * 8);
-  long long CH = min((long long)G * NV_W * 8, max((long long)G * NV_W, cols_l2));
+  long long CH = min((long long)G * NV_W * 8, max((long long)G * NV_W * 4, cols_l2));
   CH = max(1ll, min(CH, (long long)a.p));
   if (const char *env = getenv("CDGPU_NAIVE_CHUNK")) {
     long long v = atoll(env);
@@ -1065,7 +1022,7 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
   HEntry *hbuf = reinterpret_cast<HEntry *>(a.scr + 8);
   NBcast *bc = reinterpret_cast<NBcast *>(a.scr + 8 + 8 * (long long)a.p);
   int ch = (int)CH;
-  void *args[] = {(void *)&a, (void *)&ch, (void *)&hbuf, (void *)&bc};
+  void *args[] = {(void *)&a, (void *)&ch, (void *)&hbuf, (void *)&bc, (void *)&gcap};
   CUDA_TRY(cudaLaunchCooperativeKernel((void *)naive_path_kernel, dim3(G), dim3(NV_T), args, dyn, h->stream));
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
