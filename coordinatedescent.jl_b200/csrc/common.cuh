@@ -126,21 +126,28 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 template <int T>
 __device__ void cd_compact_list(int *act, double *val, int m_old, int m_now, const int *newpos, unsigned char *inlist,
                                 int *tmp_i, double *tmp_d, int *s2) {
-  const int tid = threadIdx.x;
+  // T == 32: warp-collective (several independent warps per CTA may call it), else block-collective
+  const int tid = T == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  auto sync = [] {
+    if (T == 32)
+      __syncwarp();
+    else
+      __syncthreads();
+  };
   if (tid == 0) {
     s2[0] = 0;
     s2[1] = 0;
   }
-  __syncthreads();
+  sync();
   int cnt = 0;
   for (int e = tid; e < m_now; e += T) cnt += (val[e] != 0.0);
   if (cnt) atomicAdd(&s2[0], cnt);
-  __syncthreads();
+  sync();
   const int K = s2[0];
   if (K == m_now && m_now == m_old) return; // nothing dropped, nothing new: order unchanged
   int *F = tmp_i, *tailE = tmp_i + m_now, *tailP = tmp_i + 2 * m_now, *tailS = tmp_i + 3 * m_now, *ti = tmp_i + 4 * m_now;
   for (int i = tid; i < K; i += T) F[i] = -1;
-  __syncthreads();
+  sync();
   for (int e = tid; e < m_now; e += T) {
     if (val[e] != 0.0) {
       const int pos = e < m_old ? e : newpos[e - m_old];
@@ -155,7 +162,7 @@ __device__ void cd_compact_list(int *act, double *val, int m_old, int m_now, con
       inlist[act[e]] = 0;
     }
   }
-  __syncthreads();
+  sync();
   const int Tn = s2[1];
   for (int t = tid; t < Tn; t += T) {
     const int pt = tailP[t];
@@ -163,7 +170,7 @@ __device__ void cd_compact_list(int *act, double *val, int m_old, int m_now, con
     for (int u = 0; u < Tn; ++u) r += tailP[u] > pt;
     tailS[r] = tailE[t];
   }
-  __syncthreads();
+  sync();
   if (tid < 32) {
     int filled = 0;
     for (int base = 0; base < K; base += 32) {
@@ -174,17 +181,17 @@ __device__ void cd_compact_list(int *act, double *val, int m_old, int m_now, con
       filled += __popc(b);
     }
   }
-  __syncthreads();
+  sync();
   for (int i = tid; i < K; i += T) {
     ti[i] = act[F[i]];
     tmp_d[i] = val[F[i]];
   }
-  __syncthreads();
+  sync();
   for (int i = tid; i < K; i += T) {
     act[i] = ti[i];
     val[i] = tmp_d[i];
   }
-  __syncthreads();
+  sync();
 }
 
 // device-side mirror of cdgpu_stats (host fills device_ms / sigma bookkeeping)
@@ -278,6 +285,8 @@ int launch_diag_sqrt(cdgpu_handle_s *h, const double *A, long long lda, int p, d
 int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,
                 double *c, double divisor, int mode);
 int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_total);
+int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, long long lda, const double *B, int pb,
+                   long long ldb, long long n, double *C, long long ldc, double divisor, void **tiles_out);
 
 // naive sweeps (naive_sweep.cu)
 struct NaiveArgs {

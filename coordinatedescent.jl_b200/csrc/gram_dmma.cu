@@ -77,10 +77,17 @@ __device__ __forceinline__ void load_tile(double *dst, const double *X, long lon
 }
 
 // WM x WN warps; warp tile (128/WM) x (128/WN) = MI x NI fragments of 8 x 8
-template <bool ALIGNED16, int WM, int WN, int BK, int STAGES, bool PIPE>
+// GEMM = false: SYRK on X (lower tiles, mirrored).  GEMM = true: C = X'B for a second K-contiguous operand
+// B (n x pb, ldb): every tile of the pa x pb rectangle, plain stores (used by the batched
+// varying-coefficient path, vc_batch.cu: all local Gram matrices in one FP64 tensor-core GEMM).
+template <bool ALIGNED16, int WM, int WN, int BK, int STAGES, bool PIPE, bool GEMM = false>
 __global__ void __launch_bounds__(WM *WN * 32, 1)
     gram_syrk_kernel(const double *__restrict__ X, long long n, int p, long long ldx, double *G,
-                     long long ldg, const int2 *__restrict__ tiles, int ntiles, double divisor, int mode) {
+                     long long ldg, const int2 *__restrict__ tiles, int ntiles, double divisor, int mode,
+                     const double *__restrict__ Bm = nullptr, int pb = 0, long long ldb = 0) {
+  const double *__restrict__ XB = GEMM ? Bm : X;
+  const int pB = GEMM ? pb : p;
+  const long long ldB = GEMM ? ldb : ldx;
   constexpr int GT = WM * WN * 32, LDK = BK + 4, STAGE_DOUBLES = (BM + BN) * LDK;
   constexpr int MI = BM / (WM * 8), NI = BN / (WN * 8);
   extern __shared__ __align__(16) double smem[];
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
       if (s < nK) {
         double *st = smem + s * STAGE_DOUBLES;
         load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, (long long)s * BK, tid);
-        load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, X, ldx, n, p, colB, (long long)s * BK, tid);
+        load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, XB, ldB, n, pB, colB, (long long)s * BK, tid);
       }
       cp_commit();
     }
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
           if (kn < nK) {
             double *st = smem + (kn % STAGES) * STAGE_DOUBLES;
             load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, kn * BK, tid);
-            load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, X, ldx, n, p, colB, kn * BK, tid);
+            load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, XB, ldB, n, pB, colB, kn * BK, tid);
           }
           cp_commit();
         }
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
           if (kn < nK) {
             double *st = smem + (kn % STAGES) * STAGE_DOUBLES;
             load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, kn * BK, tid);
-            load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, X, ldx, n, p, colB, kn * BK, tid);
+            load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, XB, ldB, n, pB, colB, kn * BK, tid);
           }
           cp_commit();
         }
@@ -199,7 +206,12 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
           v0 = v0 / divisor;
           v1 = v1 / divisor;
         }
-        if (row < p) {
+        if (GEMM) {
+          if (row < p) {
+            if (col < pB) G[row + (long long)col * ldg] = v0;
+            if (col + 1 < pB) G[row + (long long)(col + 1) * ldg] = v1;
+          }
+        } else if (row < p) {
           // diagonal tiles: the lower part (and the diagonal) is authoritative
           if (col < p && (bi != bj || row >= col)) put(row, col, v0);
           if (col + 1 < p && (bi != bj || row >= col + 1)) put(row, col + 1, v1);
@@ -264,7 +276,7 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
   if (const char *env = getenv("CDGPU_GRAM_VARIANT")) variant = atoi(env);
   auto launch = [&](auto kern, int threads, size_t dyn) -> int {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    kern<<<grid, threads, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, mode);
+    kern<<<grid, threads, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, mode, nullptr, 0, 0);
     CUDA_TRY(cudaGetLastError());
     return CDGPU_OK;
   };
@@ -295,6 +307,43 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
   xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, c, divisor, mode);
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(2);
+  return CDGPU_OK;
+}
+
+// C (pa x pb, ldc) = A'B / divisor for K-contiguous A (n x pa, lda) and B (n x pb, ldb).  The tile list is
+// allocated from the stream-ordered pool and returned in *tiles_out for the caller to free after the stream
+// has drained.
+int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, long long lda, const double *B, int pb,
+                   long long ldb, long long n, double *C, long long ldc, double divisor, void **tiles_out) {
+  const int nbi = (pa + BM - 1) / BM, nbj = (pb + BN - 1) / BN;
+  std::vector<int2> tiles;
+  tiles.reserve((size_t)nbi * nbj);
+  // column panels of B outermost: the CTAs in flight share a few B panels and all of A through L2
+  const int S = 8;
+  for (int SJ = 0; SJ < nbj; SJ += S)
+    for (int bi = 0; bi < nbi; ++bi)
+      for (int bj = SJ; bj < min(SJ + S, nbj); ++bj) tiles.push_back(make_int2(bi, bj));
+  const int ntiles = (int)tiles.size();
+  int2 *dt = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&dt, (size_t)ntiles * sizeof(int2), stream));
+  *tiles_out = dt;
+  CUDA_TRY(cudaMemcpyAsync(dt, tiles.data(), (size_t)ntiles * sizeof(int2), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream)); // `tiles` is a host temporary
+  const bool aligned = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((lda & 1) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((ldb & 1) == 0);
+  const int grid = min(ntiles, sm_count);
+  const size_t dyn = (size_t)4 * (BM + BN) * (16 + 4) * sizeof(double);
+  if (aligned) {
+    auto kern = gram_syrk_kernel<true, 2, 4, 16, 4, true, true>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<grid, 256, dyn, stream>>>(A, n, pa, lda, C, ldc, dt, ntiles, divisor, 1, B, pb, ldb);
+  } else {
+    auto kern = gram_syrk_kernel<false, 2, 4, 16, 4, false, true>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<grid, 256, dyn, stream>>>(A, n, pa, lda, C, ldc, dt, ntiles, divisor, 1, B, pb, ldb);
+  }
+  CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
 

@@ -12,6 +12,10 @@
 // order); active-set passes are a short sequential chain with block-wide dots.  No inter-CTA
 // communication at all; grid points are sharded over GPUs by [m_begin, m_end).
 #include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -466,7 +470,647 @@ __global__ void __launch_bounds__(32) vc_warp_kernel(const VcArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// MOMENT FORM (default for ep <= 256): the covariance form of every local problem at once.
+// With eX[i,(j,l)] = X[i,j] dz_i^l the weighted Gram of grid point g is
+//     A_g[(j,l),(j',l')] = sum_i w_gi dz_gi^(l+l') X[i,j] X[i,j'] / n = M_{g,l+l'}[j,j'],
+// i.e. 2d+1 weighted p x p moment matrices per grid point, and ALL of them for ALL grid points are
+// ONE dense FP64 contraction  C = Z'V / n  with  Z[i,(j>=j')] = X[i,j] X[i,j'] | Z[i,P2+j] = X[i,j] y_i
+// (n x (p(p+1)/2 + p)) and V[i,(g,q)] = w_gi dz_gi^q (n x m(2d+1)) — run on the FP64 tensor cores by
+// the DMMA kernel of gram_dmma.cu (launch_gemm_tn).  The local lasso is then CDQuadraticLoss
+// (cd_differentiable_function.jl:324-348) on A_g, b_g = -eX'W y/n with omega_k = sqrt(A_kk)
+// (utils.jl:140-151) — the same minimiser as the reference's CDWeightedLSLoss form (:165-194);
+// iterates differ at rounding level.  ONE WARP PER GRID POINT: lane owns coordinates lane, lane+32, ...
+// with (A x)_t, beta_t and the per-coordinate constants in registers; a full pass is the speculative
+// first-mover scan (non-moving coordinates cost no memory traffic), an accepted step reads one
+// column of A_g through the moment blocks (L1/L2 resident).
+struct VcCovArgs {
+  const double *C; // moment blocks: problem g at C + (g - g0) * NQ * ldc, block q at + q * ldc
+  long long ldc;
+  int p, degree, ep, P2;
+  int g0, g1;
+  double lambda0;
+  long long maxIter;
+  double optTol;
+  int randomize;
+  unsigned long long seed;
+  double *out;
+  DevStats *stats;
+  int *counter; // dynamic work distribution
+  unsigned long long *prof; // optional [8]: summed warp cycles: full passes, active chain, list compaction, phase open, phase close, total
+  int dbg;      // CDGPU_VC_DBG (timing experiments only; results are wrong when set): 1 no column prefetch, 2 no compaction
+  double *gscr; // per-warp scratch for the compact active Gram: (grid * VCW) x MC x MC doubles, MC = ep rounded up to even
+};
+
+constexpr int VCW = 4;      // warps (local problems) per CTA
+constexpr int VC_RING = 4;  // columns of the compact active Gram in flight to shared memory per warp
+__host__ __device__ inline size_t vc_cov_warp_bytes(int ep) {
+  const int MC = ((ep + 31) / 32) * 32; // ring stage stride: a whole number of 32-lane rows, so no lane ever clamps
+  return ((size_t)(VC_RING * MC + 7 * ep) * sizeof(double) + (size_t)(9 * ep + 4) * sizeof(int) + (size_t)ep + 15) / 16 * 16;
+}
+
+__global__ void vc_build_z_kernel(const double *__restrict__ X, long long ldx, int n, int p, const double *__restrict__ y,
+                                  double *Z, long long ldz) {
+  const int P2 = p * (p + 1) / 2;
+  const int col = blockIdx.x;
+  int j, jp;
+  if (col < P2) {
+    j = (int)((sqrt(8.0 * (double)col + 1.0) - 1.0) * 0.5);
+    while (j * (j + 1) / 2 > col) --j;
+    while ((j + 1) * (j + 2) / 2 <= col) ++j;
+    jp = col - j * (j + 1) / 2;
+  } else {
+    j = col - P2;
+    jp = -1;
+  }
+  const double *cj = X + (long long)j * ldx, *cjp = jp >= 0 ? X + (long long)jp * ldx : y;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) Z[i + (long long)col * ldz] = cj[i] * cjp[i];
+}
+
+__global__ void vc_build_v_kernel(const double *__restrict__ z, const double *__restrict__ zgrid, int n, int g0, int g1,
+                                  int nq, int kernel_kind, double bandwidth, double *V, long long ldv) {
+  const int g = g0 + blockIdx.x;
+  if (g >= g1) return;
+  const double z0 = zgrid[g];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double zi = z[i];
+    double w;
+    if (kernel_kind == CDGPU_KERNEL_GAUSSIAN) { // varying_coefficient_lasso.jl:17
+      const double d = zi - z0;
+      w = exp(-(d * d) / bandwidth) / bandwidth;
+    } else { // :18-21
+      const double u = (zi - z0) / bandwidth;
+      w = fabs(u) >= 1.0 ? 0.0 : 0.75 * (1.0 - u * u) / bandwidth;
+    }
+    const double dz = zi - z0;
+    double v = w;
+    for (int q = 0; q < nq; ++q) {
+      V[i + (long long)((g - g0) * nq + q) * ldv] = v;
+      v *= dz;
+    }
+  }
+}
+
+template <int OFF>
+__device__ __forceinline__ void vc_cp16(unsigned dst, const char *src) {
+  asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%2], 16;" ::"r"(dst), "l"(src), "n"(OFF) : "memory");
+}
+
+template <int NU>
+__global__ void __launch_bounds__(VCW * 32, 3) vc_cov_kernel(const VcCovArgs a) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  const int ep = a.ep, dg = a.degree + 1, nq = 2 * a.degree + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int MC = (ep + 1) & ~1, RS = 32 * NU; // scratch leading dimension bound, ring stage stride
+  unsigned char *base = raw + warp * vc_cov_warp_bytes(ep);
+  double *ring = reinterpret_cast<double *>(base);       // VC_RING prefetched columns of the compact active Gram
+  double *sbeta = ring + VC_RING * RS;                   // dense beta (after a full pass / at phase start)
+  double *sval = sbeta + ep, *stmpd = sval + ep;         // list-order values, scratch
+  double *sAx = stmpd + ep, *scc = sAx + ep, *sai = scc + ep, *sth = sai + ep; // dense (A x) and constants
+  int *sact = reinterpret_cast<int *>(sth + ep);
+  int *snewpos = sact + ep, *sact0 = snewpos + ep, *stmpi = sact0 + ep, *s2 = stmpi + 5 * ep, *spos = s2 + 4;
+  unsigned char *sin = reinterpret_cast<unsigned char *>(spos + ep);
+  double *Gw = a.gscr + ((long long)blockIdx.x * VCW + warp) * (long long)MC * MC; // this warp's compact Gram scratch
+  const bool ordered = a.randomize == 0;
+  constexpr unsigned NONE = 0xffffffffu;
+
+  int tj[NU], tl[NU], ttri[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const int t = lane + 32 * u;
+    tj[u] = t / dg;
+    tl[u] = t - tj[u] * dg;
+    ttri[u] = tj[u] * (tj[u] + 1) / 2;
+  }
+
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = a.g0 + atomicAdd(a.counter, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= a.g1) break;
+    const double *Cg = a.C + (long long)(g - a.g0) * nq * a.ldc;
+    // element (k1, k2) of A_g through the moment blocks
+    auto moment = [&](int k1, int k2) -> double {
+      const int j1 = k1 / dg, l1 = k1 - j1 * dg, j2 = k2 / dg, l2 = k2 - j2 * dg;
+      const int pk_ = j1 >= j2 ? j1 * (j1 + 1) / 2 + j2 : j2 * (j2 + 1) / 2 + j1;
+      return __ldg(Cg + (long long)(l1 + l2) * a.ldc + pk_);
+    };
+    // state: COORDINATE layout outside a phase (slot u <-> coordinate lane + 32u), ENTRY layout inside one
+    // (slot u <-> snapshot entry lane + 32u of the phase's active list)
+    double Ax[NU], be[NU], cc[NU], ai[NU], th[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int t = lane + 32 * u;
+      Ax[u] = be[u] = cc[u] = th[u] = 0.0;
+      ai[u] = 0.0;
+      if (t < ep) {
+        const double att = __ldg(Cg + (long long)(2 * tl[u]) * a.ldc + ttri[u] + tj[u]);
+        ai[u] = 1.0 / att;
+        th[u] = __dmul_rn(__dmul_rn(ai[u], a.lambda0), sqrt(att)); // lambda0 * omega_k / A_kk, omega_k = sqrt(A_kk)
+        cc[u] = -__ldg(Cg + (long long)tl[u] * a.ldc + a.P2 + tj[u]);
+        scc[t] = cc[u];
+        sai[t] = ai[u];
+        sth[t] = th[u];
+      }
+    }
+    for (int k = lane; k < ep; k += 32) sin[k] = 0;
+    int nact = 0;
+    __syncwarp();
+
+    // coordinate layout: Ax[u] += A_g[t_u, k] * h for the mover k = (kj, kl)
+    auto apply = [&](int k, double h) {
+      const int kj = k / dg, kl = k - kj * dg, ktri = kj * (kj + 1) / 2;
+      double gv[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int t = lane + 32 * u;
+        const int pk_ = kj >= tj[u] ? ktri + tj[u] : ttri[u] + kj;
+        gv[u] = t < ep ? __ldg(Cg + (long long)(kl + tl[u]) * a.ldc + pk_) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < NU; ++u) Ax[u] = __dadd_rn(Ax[u], __dmul_rn(gv[u], h));
+    };
+
+    // ---- phases of consecutive active-set passes.  Active-set passes only need (A x) on the active set, so a
+    // phase (a) gathers the compact m0 x m0 block A_g[act0, act0] once into this warp's scratch (L2 resident,
+    // column-contiguous), (b) moves the state of the active entries into the entry layout, (c) runs the chain
+    // with the column of the next VC_RING-1 steps already in flight to shared memory (cp.async), so a step is:
+    // owner evaluates, one shuffle broadcasts h, every lane updates its entries — no memory latency on the
+    // dependent path, and (d) at the end brings (A x) of the other coordinates up to date from the change of beta.
+    bool in_phase = false;
+    int m0 = 0, ldw = 0;
+    long long wait_cyc = 0;
+    auto phase_open = [&](int m) {
+      m0 = m;
+      ldw = (m + 1) & ~1;
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+        if (lane + 32 * u < ep) {
+          sbeta[lane + 32 * u] = be[u]; // beta at the start of the phase
+          sAx[lane + 32 * u] = Ax[u];
+        }
+      for (int k = lane; k < ep; k += 32) spos[k] = -1;
+      __syncwarp();
+      for (int i = lane; i < m; i += 32) {
+        sact0[i] = sact[i];
+        spos[sact[i]] = i;
+      }
+      __syncwarp();
+      for (int j = 0; j < m; ++j) {
+        const int kj = sact0[j];
+        for (int i = lane; i < m; i += 32) Gw[i + (long long)j * ldw] = moment(sact0[i], kj);
+      }
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int e = lane + 32 * u;
+        Ax[u] = be[u] = cc[u] = ai[u] = th[u] = 0.0;
+        if (e < m) {
+          const int k = sact0[e];
+          Ax[u] = sAx[k];
+          be[u] = sbeta[k];
+          cc[u] = scc[k];
+          ai[u] = sai[k];
+          th[u] = sth[k];
+        }
+      }
+      __syncwarp();
+      in_phase = true;
+    };
+    auto phase_close = [&](int nact_now) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int e = lane + 32 * u;
+        if (e < m0) {
+          const int k = sact0[e];
+          sAx[k] = Ax[u];
+        }
+      }
+      __syncwarp();
+      // beta of the listed entries by coordinate (dropped entries are exactly zero)
+      for (int k = lane; k < ep; k += 32) stmpd[k] = 0.0;
+      __syncwarp();
+      for (int i = lane; i < nact_now; i += 32) stmpd[sact[i]] = sval[i];
+      __syncwarp();
+      bool inactive[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int t = lane + 32 * u;
+        Ax[u] = be[u] = cc[u] = ai[u] = th[u] = 0.0;
+        inactive[u] = false;
+        if (t < ep) {
+          inactive[u] = spos[t] < 0;
+          Ax[u] = sAx[t];
+          be[u] = inactive[u] ? 0.0 : stmpd[t];
+          cc[u] = scc[t];
+          ai[u] = sai[t];
+          th[u] = sth[t];
+        }
+      }
+      // (A x)_t += sum_e A[t, act0_e] (beta_e - beta_e at phase start) for the coordinates outside the active set
+      for (int e = 0; e < m0; ++e) {
+        const int k = sact0[e];
+        const double dlt = stmpd[k] - sbeta[k];
+        if (dlt == 0.0) continue;
+        const int kj = k / dg, kl = k - kj * dg, ktri = kj * (kj + 1) / 2;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          if (inactive[u]) {
+            const int pk_ = kj >= tj[u] ? ktri + tj[u] : ttri[u] + kj;
+            Ax[u] = fma(__ldg(Cg + (long long)(kl + tl[u]) * a.ldc + pk_), dlt, Ax[u]);
+          }
+        }
+      }
+      __syncwarp();
+      in_phase = false;
+    };
+    // one active-set pass inside a phase; returns max|h|
+    auto phase_pass = [&](int m, const PermKey &pkm, long long &accepted) -> double {
+      int *sord = snewpos; // visit position -> snapshot entry | list position << 16 (snewpos is unused while m_old == m_now)
+      for (int s_ = lane; s_ < m; s_ += 32) {
+        const int i_ = ordered ? s_ : (int)cd_perm(pkm, (uint32_t)s_);
+        sord[s_] = spos[sact[i_]] | (i_ << 16);
+      }
+      __syncwarp();
+      // column of snapshot entry e -> ring stage (16-byte chunks; ldw is even and Gw 16-byte aligned)
+      const char *gsrc = reinterpret_cast<const char *>(Gw) + lane * 16;
+      const unsigned rdst = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;
+      auto fetch = [&](int s_) {
+        if (s_ < m) {
+          const char *src = gsrc + (unsigned)((sord[s_] & 0xffff) * ldw) * 8u;
+          const unsigned dst = rdst + (unsigned)(s_ % VC_RING) * (unsigned)(RS * 8);
+          if (2 * lane < m0) vc_cp16<0>(dst, src);
+          if ((NU + 1) / 2 > 1 && 2 * (lane + 32) < m0) vc_cp16<512>(dst, src);
+          if ((NU + 1) / 2 > 2 && 2 * (lane + 64) < m0) vc_cp16<1024>(dst, src);
+          if ((NU + 1) / 2 > 3 && 2 * (lane + 96) < m0) vc_cp16<1536>(dst, src);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+#pragma unroll
+      for (int d = 0; d < VC_RING - 1; ++d) fetch(d);
+      asm volatile("cp.async.wait_group %0;" ::"n"(VC_RING - 2) : "memory");
+      __syncwarp();
+      double gn[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) gn[u] = ring[lane + 32 * u]; // column of step 0 (stage 0)
+      // beta and the constants of the stepping entry are read (uniformly) from shared memory one step ahead;
+      // only (A x) of the entries lives in registers, so the owner picks ONE value by slot
+      int nxt = m > 0 ? sord[0] : 0;
+      int kn = m > 0 ? sact[nxt >> 16] : 0;
+      double nbe = m > 0 ? sval[nxt >> 16] : 0.0, ncc = scc[kn], nai = sai[kn], nth = sth[kn];
+      double maxH = 0.0;
+#pragma unroll 2
+      for (int s_ = 0; s_ < m; ++s_) {
+        const int e = nxt & 0xffff, i_ = nxt >> 16;
+        const double xbe = nbe, xcc = ncc, xai = nai, xth = nth;
+        double gc[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) gc[u] = gn[u];
+        const long long tw0 = (a.dbg & 4) ? clock64() : 0;
+        if (!(a.dbg & 1)) {
+        fetch(s_ + VC_RING - 1); // overwrites the stage of step s_-1, whose values were taken an iteration ago
+        asm volatile("cp.async.wait_group %0;" ::"n"(VC_RING - 2) : "memory");
+        __syncwarp();
+        }
+        if (a.dbg & 4) wait_cyc += clock64() - tw0;
+        if (s_ + 1 < m) {
+          const double *nx = ring + ((s_ + 1) % VC_RING) * RS + lane;
+#pragma unroll
+          for (int u = 0; u < NU; ++u) gn[u] = nx[32 * u];
+          nxt = sord[s_ + 1];
+          kn = sact[nxt >> 16];
+          nbe = sval[nxt >> 16];
+          ncc = scc[kn];
+          nai = sai[kn];
+          nth = sth[kn];
+        }
+        const int owner = e & 31, slot = e >> 5;
+        double xg = Ax[0];
+#pragma unroll
+        for (int u = 1; u < NU; ++u) xg = u == slot ? Ax[u] : xg;
+        const double v = __dsub_rn(xbe, __dmul_rn(xg + xcc, xai));
+        const double nwl = cd_shrink(v, xth);
+        const double h = __shfl_sync(0xffffffffu, nwl - xbe, owner);
+        if (lane == owner) sval[i_] = nwl;
+        if (h != 0.0) {
+#pragma unroll
+          for (int u = 0; u < NU; ++u) Ax[u] = __dadd_rn(Ax[u], __dmul_rn(gc[u], h));
+          accepted += 1;
+        }
+        maxH = fmax(maxH, fabs(h));
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      return maxH;
+    };
+
+    DevStats st;
+    st.passes = st.full_passes = st.visits = st.accepted = 0;
+    st.maxH = 0.0;
+    st.converged = 0;
+    st.outer_iters = 0;
+    st.sigma = 0.0;
+    unsigned long long pass_counter = 0;
+    bool conv = true;
+    long long iter = 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0};
+    const long long tstart = clock64();
+    while (iter < a.maxIter) {
+      double maxH = 0.0;
+      iter += 1;
+      st.passes += 1;
+      long long tq = clock64();
+      if (conv) { // ---- full pass: speculative first-mover scan (exact Gauss-Seidel order)
+        if (in_phase) {
+          phase_close(nact);
+          pc[4] += clock64() - tq;
+          tq = clock64();
+        }
+        st.full_passes += 1;
+        st.visits += ep;
+        const PermKey pk = cd_perm_key((uint32_t)ep, a.seed, pass_counter);
+        const int m_old = nact;
+        long long cur = -1;
+        for (;;) {
+          unsigned best = NONE;
+          double bh = 0.0, bnw = 0.0;
+          int bk = 0;
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const int t = lane + 32 * u;
+            if (t < ep) {
+              const unsigned key = ordered ? (unsigned)t : cd_perm_inv(pk, (uint32_t)t);
+              if ((long long)key > cur) {
+                const double tt = __dmul_rn(Ax[u] + cc[u], ai[u]);
+                const double v = __dsub_rn(be[u], tt);
+                const double nw = cd_shrink(v, th[u]);
+                const double h = nw - be[u];
+                if (h != 0.0 && key < best) {
+                  best = key;
+                  bh = h;
+                  bnw = nw;
+                  bk = t;
+                }
+              }
+            }
+          }
+          const unsigned wmin = __reduce_min_sync(0xffffffffu, best);
+          if (wmin == NONE) break;
+          const int src = __ffs(__ballot_sync(0xffffffffu, best == wmin)) - 1;
+          const int k = __shfl_sync(0xffffffffu, bk, src);
+          const double h = __shfl_sync(0xffffffffu, bh, src), nw = __shfl_sync(0xffffffffu, bnw, src);
+          if (lane == (k & 31)) {
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+              if (u == (k >> 5)) be[u] = nw;
+          }
+          apply(k, h);
+          if (!sin[k]) { // setindex! appends on the first non-zero store
+            __syncwarp();
+            if (lane == 0) {
+              sin[k] = 1;
+              sact[nact] = k;
+            }
+            nact += 1;
+            __syncwarp();
+          }
+          maxH = fmax(maxH, fabs(h));
+          st.accepted += 1;
+          cur = (long long)wmin;
+        }
+        pc[0] += clock64() - tq;
+        tq = clock64();
+        // list order after the pass (common.cuh: cd_compact_list); the visited non-members whose tentative
+        // value is exactly zero (not appended by the reference) are not tracked here: it needs an exactly
+        // zero gradient and only affects the visit order of later active-set passes
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+          if (lane + 32 * u < ep) sbeta[lane + 32 * u] = be[u];
+        __syncwarp();
+        for (int i = lane; i < nact; i += 32) sval[i] = sbeta[sact[i]];
+        for (int e = m_old + lane; e < nact; e += 32) {
+          const int k = sact[e];
+          const int vis = ordered ? k : (int)cd_perm_inv(pk, (uint32_t)k);
+          int before = 0;
+          for (int j = 0; j < m_old; ++j) before += (ordered ? sact[j] : (int)cd_perm_inv(pk, (uint32_t)sact[j])) < vis;
+          snewpos[e - m_old] = m_old + vis - before;
+        }
+        __syncwarp();
+        cd_compact_list<32>(sact, sval, m_old, nact, snewpos, sin, stmpi, stmpd, s2);
+        nact = s2[0];
+        __syncwarp();
+        pc[2] += clock64() - tq;
+      } else { // ---- active-set pass: sequential chain over the stored entries
+        const int m = nact;
+        st.visits += m;
+        if (!in_phase) {
+          phase_open(m);
+          pc[3] += clock64() - tq;
+          tq = clock64();
+        }
+        const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter);
+        maxH = phase_pass(m, pkm, st.accepted);
+        pc[1] += clock64() - tq;
+        tq = clock64();
+        if (!(a.dbg & 2)) {
+        cd_compact_list<32>(sact, sval, m, m, snewpos, sin, stmpi, stmpd, s2); // dropzeros!
+        nact = s2[0];
+        }
+        __syncwarp();
+        pc[2] += clock64() - tq;
+      }
+      pass_counter += 1;
+      st.maxH = maxH;
+      const bool prev = conv;
+      conv = maxH < a.optTol;
+      if (prev && conv) {
+        st.converged = 1;
+        break;
+      }
+    }
+    if (in_phase) phase_close(nact); // pass budget ran out inside a phase: back to the coordinate layout
+    if (a.prof && lane == 0) {
+      pc[5] = clock64() - tstart;
+      for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, (unsigned long long)pc[i]);
+      atomicAdd(a.prof + 7, (unsigned long long)wait_cyc);
+      atomicMax(a.prof + 6, (unsigned long long)pc[5]);
+    }
+    double *col = a.out + (long long)g * ep;
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+      if (lane + 32 * u < ep) col[lane + 32 * u] = be[u];
+    if (lane == 0 && a.stats) a.stats[g] = st;
+    __syncwarp();
+  }
+}
+
 } // namespace
+
+// host driver of the moment form; grid points are processed in chunks so the moment blocks stay <= ~1 GiB
+static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                           const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                           double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
+                           cdgpu_stats *stats) {
+  const int64_t ep = p * (degree + 1), mloc = m_end - m_begin, P2 = p * (p + 1) / 2, PA = P2 + p;
+  const int nq = 2 * degree + 1;
+  const long long ldz = (n + 1) & ~(int64_t)1, ldc = (PA + 1) & ~(int64_t)1;
+  int64_t chunk = (int64_t)((1ll << 30) / ((long long)ldc * nq * 8));
+  chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, mloc));
+  chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (int64_t)((1ll << 30) / ((long long)ldz * nq * 8))));
+  cudaStream_t s = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, eg = nullptr;
+  double *dX = nullptr, *dz = nullptr, *dy = nullptr, *dgz = nullptr, *dout = nullptr, *dZ = nullptr, *dV = nullptr, *dC = nullptr;
+  DevStats *dst = nullptr;
+  double *dG = nullptr;
+  int *dcounter = nullptr;
+  unsigned long long *dprof = nullptr;
+  void *dtiles = nullptr;
+  int rc = CDGPU_OK;
+  auto cleanup = [&]() {
+    if (s) cudaStreamSynchronize(s);
+    for (void *ptr : {(void *)dX, (void *)dz, (void *)dy, (void *)dgz, (void *)dout, (void *)dZ, (void *)dV, (void *)dC,
+                      (void *)dst, (void *)dcounter, (void *)dprof, (void *)dG, dtiles})
+      if (ptr) cudaFreeAsync(ptr, s);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (eg) cudaEventDestroy(eg);
+    if (s) {
+      cudaStreamSynchronize(s);
+      cudaStreamDestroy(s);
+    }
+  };
+#define VM_TRY(expr)                                                                                        \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) {                                                                                \
+      rc = cdgpu_set_error(_e == cudaErrorMemoryAllocation ? CDGPU_ENOMEM : CDGPU_ECUDA, "%s: %s", #expr,   \
+                           cudaGetErrorString(_e));                                                         \
+      cleanup();                                                                                            \
+      return rc;                                                                                            \
+    }                                                                                                       \
+  } while (0)
+  VM_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  VM_TRY(cudaEventCreate(&e0));
+  VM_TRY(cudaEventCreate(&e1));
+  VM_TRY(cudaEventCreate(&eg));
+  VM_TRY(cudaMallocAsync((void **)&dX, (size_t)n * p * sizeof(double), s));
+  VM_TRY(cudaMallocAsync((void **)&dz, (size_t)n * sizeof(double), s));
+  VM_TRY(cudaMallocAsync((void **)&dy, (size_t)n * sizeof(double), s));
+  VM_TRY(cudaMallocAsync((void **)&dgz, (size_t)m * sizeof(double), s));
+  VM_TRY(cudaMallocAsync((void **)&dout, (size_t)ep * m * sizeof(double), s));
+  VM_TRY(cudaMallocAsync((void **)&dst, (size_t)m * sizeof(DevStats), s));
+  VM_TRY(cudaMallocAsync((void **)&dZ, (size_t)ldz * PA * sizeof(double), s));
+  VM_TRY(cudaMallocAsync((void **)&dV, (size_t)ldz * nq * chunk * sizeof(double), s));
+  VM_TRY(cudaMallocAsync((void **)&dC, (size_t)ldc * nq * chunk * sizeof(double), s));
+  VM_TRY(cudaMallocAsync((void **)&dcounter, sizeof(int), s));
+  if (getenv("CDGPU_PROFILE")) {
+    VM_TRY(cudaMallocAsync((void **)&dprof, 8 * sizeof(unsigned long long), s));
+    VM_TRY(cudaMemsetAsync(dprof, 0, 8 * sizeof(unsigned long long), s));
+  }
+  VM_TRY(cudaMemcpy2DAsync(dX, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), p, cudaMemcpyHostToDevice, s));
+  VM_TRY(cudaMemcpyAsync(dz, z, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  VM_TRY(cudaMemcpyAsync(dy, y, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  VM_TRY(cudaMemcpyAsync(dgz, zgrid, m * sizeof(double), cudaMemcpyHostToDevice, s));
+  int sms = 0;
+  VM_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int nu = (int)((ep + 31) / 32);
+  const void *kfn = nu <= 1   ? (const void *)vc_cov_kernel<1>
+                    : nu == 2 ? (const void *)vc_cov_kernel<2>
+                    : nu == 3 ? (const void *)vc_cov_kernel<3>
+                    : nu == 4 ? (const void *)vc_cov_kernel<4>
+                    : nu == 5 ? (const void *)vc_cov_kernel<5>
+                    : nu == 6 ? (const void *)vc_cov_kernel<6>
+                              : (const void *)vc_cov_kernel<8>;
+  const size_t wsz = vc_cov_warp_bytes((int)ep);
+  const size_t dyn = VCW * wsz;
+  VM_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int occ = 0;
+  VM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, VCW * 32, dyn));
+  if (occ < 1) occ = 1;
+  const int64_t max_ctas = std::min<int64_t>((std::min<int64_t>(chunk, mloc) + VCW - 1) / VCW, (int64_t)occ * sms);
+  const int64_t MCs = (ep + 1) & ~(int64_t)1;
+  VM_TRY(cudaMallocAsync((void **)&dG, (size_t)max_ctas * VCW * MCs * MCs * sizeof(double), s));
+  VM_TRY(cudaEventRecord(e0, s));
+  vc_build_z_kernel<<<(unsigned)PA, 128, 0, s>>>(dX, n, (int)n, (int)p, dy, dZ, ldz);
+  VM_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
+  for (int64_t c0 = m_begin; c0 < m_end; c0 += chunk) {
+    const int64_t c1 = std::min<int64_t>(m_end, c0 + chunk), mc = c1 - c0;
+    vc_build_v_kernel<<<(unsigned)mc, 128, 0, s>>>(dz, dgz, (int)n, (int)c0, (int)c1, nq, kernel_kind, bandwidth, dV, ldz);
+    VM_TRY(cudaGetLastError());
+    if (dtiles) {
+      VM_TRY(cudaFreeAsync(dtiles, s));
+      dtiles = nullptr;
+    }
+    rc = launch_gemm_tn(s, sms, dZ, (int)PA, ldz, dV, (int)(mc * nq), ldz, n, dC, ldc, (double)n, &dtiles);
+    if (rc) {
+      cleanup();
+      return rc;
+    }
+    VM_TRY(cudaEventRecord(eg, s)); // (last chunk's) moment blocks formed
+    VM_TRY(cudaMemsetAsync(dcounter, 0, sizeof(int), s));
+    VcCovArgs a = {};
+    a.C = dC;
+    a.ldc = ldc;
+    a.p = (int)p;
+    a.degree = degree;
+    a.ep = (int)ep;
+    a.P2 = (int)P2;
+    a.g0 = (int)c0;
+    a.g1 = (int)c1;
+    a.lambda0 = lambda0;
+    a.maxIter = opt->maxIter;
+    a.optTol = opt->optTol;
+    a.randomize = opt->randomize;
+    a.seed = opt->seed;
+    a.out = dout;
+    a.stats = dst;
+    a.counter = dcounter;
+    a.prof = dprof;
+    a.gscr = dG;
+    a.dbg = getenv("CDGPU_VC_DBG") ? atoi(getenv("CDGPU_VC_DBG")) : 0;
+    const int64_t ctas = std::min<int64_t>((mc + VCW - 1) / VCW, (int64_t)occ * sms);
+    void *kargs[] = {(void *)&a};
+    VM_TRY(cudaLaunchKernel(kfn, dim3((unsigned)ctas), dim3(VCW * 32), kargs, dyn, s));
+    CD_COUNT_LAUNCH(2);
+  }
+  VM_TRY(cudaEventRecord(e1, s));
+  VM_TRY(cudaMemcpyAsync(out + m_begin * ep, dout + m_begin * ep, (size_t)mloc * ep * sizeof(double), cudaMemcpyDeviceToHost, s));
+  VM_TRY(cudaStreamSynchronize(s));
+  if (stats) {
+    float ms = 0.f;
+    VM_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (getenv("CDGPU_PROFILE")) {
+      float mg = 0.f;
+      cudaEventElapsedTime(&mg, e0, eg);
+      fprintf(stderr, "[cdgpu profile] vc moment form: total %.3f ms, of which Z/V build + DMMA GEMM %.3f ms (single chunk: %s)\n", ms, mg,
+              chunk >= mloc ? "yes" : "no, GEMM time is the last chunk's offset");
+      if (dprof) {
+        unsigned long long pf[8];
+        cudaMemcpy(pf, dprof, sizeof pf, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[cdgpu profile]   warp cycles summed over problems (M): full passes %.1f | active chain %.1f | compaction %.1f | phase open %.1f | "
+                        "phase close %.1f | total %.1f | longest problem %.2f | column fetch+wait inside the chain (CDGPU_VC_DBG=4) %.1f\n",
+                pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6, pf[6] * 1e-6, pf[7] * 1e-6);
+      }
+    }
+    std::vector<DevStats> hst((size_t)mloc);
+    VM_TRY(cudaMemcpy(hst.data(), dst + m_begin, (size_t)mloc * sizeof(DevStats), cudaMemcpyDeviceToHost));
+    for (int64_t g = 0; g < mloc; ++g) {
+      cdgpu_stats *o = stats + m_begin + g;
+      o->passes = hst[g].passes;
+      o->full_passes = hst[g].full_passes;
+      o->visits = hst[g].visits;
+      o->accepted = hst[g].accepted;
+      o->maxH = hst[g].maxH;
+      o->converged = hst[g].converged;
+      o->outer_iters = 0;
+      o->sigma = 0.0;
+      o->device_ms = g == 0 ? (double)ms : 0.0;
+    }
+  }
+#undef VM_TRY
+  cleanup();
+  return CDGPU_OK;
+}
 
 API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                        const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
@@ -489,6 +1133,14 @@ API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
   CUDA_TRY(cudaSetDevice(device));
   const int64_t mloc = m_end - m_begin;
   if (mloc == 0) return CDGPU_OK;
+  {
+    // moment (covariance) form unless the expanded problem is too wide for the warp kernel's registers;
+    // CDGPU_VC_FORM=naive keeps the residual-form kernels below
+    const char *form = getenv("CDGPU_VC_FORM");
+    if (ep <= 256 && !(form && strcmp(form, "naive") == 0))
+      return vc_solve_moment(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt,
+                             device, out, stats);
+  }
   int nr = n <= 128 ? 4 : (n <= 256 ? 8 : (n <= 512 ? 16 : 0)); // 0: CTA-per-problem kernel
   if (const char *env = getenv("CDGPU_VC_THREADS")) nr = atoi(env) == 32 ? nr : 0;
   const size_t dyn_cta = (sizeof(VSm) + 15) / 16 * 16 + (size_t)(3 * n + 4 * ep) * sizeof(double) + (size_t)ep * (8 * 4 + 1) + 16;
