@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--nlambda", type=int, default=C2["nlambda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-p", type=int, default=REF_SAMPLE_P)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 side measurements")
     return ap.parse_args()
 
 
@@ -133,6 +134,74 @@ def run_step(lib, be, make_handle, cfg, opts):
     return dict(visits=visits, accepted=accepted, gram_ms=gram_ms, cd_ms=cd_ms, nnz_last=path.βpath[-1].nnz,
                 passes=sum(s["passes"] for s in path.stats), full_passes=sum(s["full_passes"] for s in path.stats),
                 converged=all(s["converged"] for s in path.stats), d2h=16 * nnz_tot + 8 * (len(lams) + 1) + 8 * f.p + 8)
+
+
+def secondary_metrics(be, local, hbm):
+    """The other two numbers BASELINE.json's metric names, outside the timed region of the headline:
+    C3 (configs[2]): sqrt-lasso n=5000 p=50000 in naive form — the HBM-bound sweep kernel, X resident in HBM;
+    C4 (configs[3]): 4096 kernel-weighted local problems of the varying-coefficient lasso, problems/s."""
+    import math
+
+    import torch
+
+    import cdgpu
+    from cdgpu import CDOptions, GaussianKernel, ProxL1, SparseIterate
+    lib, out = be.lib, {}
+    # ---- C3
+    n, p, s = 5000, 50000, 20
+    g = torch.Generator(device="cuda")
+    g.manual_seed(124)
+    Xd = torch.empty((p, n), device="cuda", dtype=torch.float64)  # (p, n) C-order == (n, p) column-major
+    for j0 in range(0, p, 5000):
+        Xd[j0:j0 + 5000].normal_(generator=g)
+    beta = torch.randn(s, device="cuda", dtype=torch.float64, generator=g) * (1.0 + torch.rand(s, device="cuda", dtype=torch.float64, generator=g))
+    yd = Xd[:s].T @ beta + torch.randn(n, device="cuda", dtype=torch.float64, generator=g)
+    torch.cuda.synchronize()
+    f = cdgpu.CDSqrtLassoLoss.__new__(cdgpu.CDSqrtLassoLoss)
+    cdgpu.api._Loss.__init__(f, lib)
+    f.n, f.p = n, p
+    lib.check(lib.naive_create_dev(C.byref(f._h), cdgpu._ffi.LOSS_SQRT, C.c_void_p(Xd.data_ptr()), n, p, n,
+                                   C.c_void_p(yd.data_ptr()), None, local))
+    lam = 1.1 * math.sqrt(2 * math.log(p))
+    best = None
+    for _ in range(3):
+        x = SparseIterate(p)
+        be.coordinateDescent_(x, f, ProxL1(lam), CDOptions(randomize=False))
+        st = dict(f.last_stats, nnz=x.nnz)
+        if best is None or st["device_ms"] < best["device_ms"]:
+            best = st
+    f.close()
+    del Xd, yd
+    gbs = 8 * n * best["visits"] / (best["device_ms"] * 1e-3) / 1e9
+    out["c3_sqrt_lasso"] = {"workload": f"sqrt-lasso n={n} p={p} lambda={lam:.3f}, naive form, X 2.0 GB resident in HBM, one launch",
+                            "kernel": "naive_path_kernel", "device_ms": best["device_ms"], "visits": best["visits"],
+                            "passes": best["passes"], "full_passes": best["full_passes"], "nnz": best["nnz"],
+                            "converged": bool(best["converged"]), "visits_per_sec": best["visits"] / (best["device_ms"] * 1e-3),
+                            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                         "bytes_per_visit": 8 * n}}
+    # ---- C4
+    n, p, degree, m = 500, 50, 2, 4096
+    rng = np.random.default_rng(125)
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    cj = rng.choice([2, 4, 6, 8], size=p)
+    Y = np.array([np.sin(cj * Z[i])[:2] @ X[i, :2] for i in range(n)]) + 0.1 * rng.standard_normal(n)
+    zgrid = np.linspace(0.01, 0.99, m)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        be.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.01, False, CDOptions(randomize=False))
+        wall = time.perf_counter() - t0
+        dev = be.last_vc_stats[0]["device_ms"]
+        if best is None or dev < best[0]:
+            best = (dev, wall, be.last_vc_stats)
+    dev, wall, stats = best
+    out["c4_vc_lasso"] = {"workload": f"locpolyl1: {m} grid points, n={n} p={p} degree={degree} (ep={p * (degree + 1)}), Gaussian h=0.2, lambda0=0.01",
+                          "kernels": "vc_build_z/v + gram_syrk_kernel<GEMM> (all local Grams as one DMMA GEMM) + vc_cov_kernel",
+                          "device_ms": dev, "wall_ms_incl_h2d_d2h": 1e3 * wall, "problems_per_sec": m / (dev * 1e-3),
+                          "problems_per_sec_e2e": m / wall, "visits": int(sum(s["visits"] for s in stats)),
+                          "all_converged": all(s["converged"] for s in stats)}
+    return out
 
 
 def reference_arm(args, cfg):
@@ -353,6 +422,11 @@ def main():
                                "sample": f"same generator, first {ps} of {p} columns, n={n}, {cfg['nlambda']} lambdas; "
                                          f"Gram numpy/OpenBLAS {cores} threads {tg:.2f} s + C port of the reference CD loop "
                                          f"(1 thread, literal always-axpy) {tc:.2f} s"}
+    if args.gpus == 1 and not args.no_secondary:
+        try:
+            out["secondary"] = secondary_metrics(be, local, hbm)
+        except Exception as e:  # noqa: BLE001  (side measurements must never cost the headline line)
+            out["secondary"] = {"error": repr(e)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

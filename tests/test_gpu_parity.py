@@ -238,9 +238,12 @@ def test_gram_matches_and_is_symmetric(gpu, ref):
 
 @pytest.mark.parametrize("kernel,degree", [(GaussianKernel(0.2), 1), (GaussianKernel(0.2), 2),
                                            (EpanechnikovKernel(0.4), 1), (GaussianKernel(0.3), 0)])
-def test_locpolyl1_parity(gpu, ref, kernel, degree, monkeypatch):
-    if degree == 2:  # exercise the CTA-per-problem kernel as well as the warp-per-problem one
-        monkeypatch.setenv("CDGPU_VC_THREADS", "128")
+@pytest.mark.parametrize("form", ["moment", "naive"])
+def test_locpolyl1_parity(gpu, ref, kernel, degree, form, monkeypatch):
+    if form == "naive":  # the residual-form kernels (default is the moment / covariance form)
+        monkeypatch.setenv("CDGPU_VC_FORM", "naive")
+        if degree == 2:  # exercise the CTA-per-problem kernel as well as the warp-per-problem one
+            monkeypatch.setenv("CDGPU_VC_THREADS", "128")
     rng = np.random.default_rng(81)
     n, p = 300, 12
     X = np.asfortranarray(rng.standard_normal((n, p)))
@@ -259,6 +262,51 @@ def test_locpolyl1_parity(gpu, ref, kernel, degree, monkeypatch):
     a, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, kernel, 0.02, False, o, shard=(0, 12))
     b, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, kernel, 0.02, False, o, shard=(12, 24))
     assert np.array_equal(a[:, :12], og[:, :12]) and np.array_equal(b[:, 12:], og[:, 12:])
+
+
+@pytest.mark.parametrize("randomize", [0, 1])
+@pytest.mark.parametrize("form", ["moment", "naive"])
+def test_locpolyl1_wide_dense_active_sets(gpu, ref, form, randomize, monkeypatch):
+    """ep = 120 (4 coordinates per lane), a weak penalty: active sets above 64 entries, many phases, dropzeros."""
+    if form == "naive":
+        monkeypatch.setenv("CDGPU_VC_FORM", "naive")
+    rng = np.random.default_rng(83)
+    n, p, degree = 260, 40, 2
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    Y = X[:, 0] * np.sin(2 * Z) + X[:, 1] * np.sin(4 * Z) + 0.1 * rng.standard_normal(n)
+    zgrid = np.linspace(0.1, 0.9, 6)
+    o = CDOptions(randomize=randomize, seed=3, maxIter=200000, optTol=1e-11)
+    og, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.25), 0.004, False, o)
+    orf, _ = ref.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.25), 0.004, False, o)
+    assert (orf != 0).sum(0).max() > 64
+    for g in range(6):
+        assert_parity(og[:, g], orf[:, g])
+    assert all(s["converged"] == 1 for s in gpu.last_vc_stats)
+
+
+@pytest.mark.parametrize("form", ["quad", "ls"])
+@pytest.mark.parametrize("randomize", [0, 1])
+def test_dense_active_set_retraces_oracle(gpu, ref, form, randomize):
+    """Active sets of several 32-entry blocks (the blocked chain engine: panel updates, worker warps, drain,
+    a ragged last block): same passes / visits / list order as the oracle and the same iterate."""
+    n, p, s = 300, 420, 30
+    X, y, _ = gauss_problem(n, p, s, seed=91)
+    A, b = X.T @ X / n, -X.T @ y / n
+    A = (A + A.T) / 2
+    o = CDOptions(randomize=randomize, seed=11, maxIter=20000, optTol=1e-7)
+    st = []
+    for be in (gpu, ref):
+        f = be.CDQuadraticLoss(A, b) if form == "quad" else be.CDLeastSquaresLoss(y, X)
+        x = SparseIterate(p)
+        be.coordinateDescent_(x, f, ProxL1(0.012), o)
+        st.append((f.last_stats, x))
+    (sg, xg), (sr, xr) = st
+    assert xr.nnz > 100
+    for key in ("passes", "full_passes", "visits", "converged"):
+        assert sg[key] == sr[key], (key, sg, sr)
+    assert list(xg.nzval2ind[: xg.nnz]) == list(xr.nzval2ind[: xr.nnz])
+    assert_parity(xg.toarray(), xr.toarray())
 
 
 def test_refit_next_tier(gpu, ref):
