@@ -502,28 +502,39 @@ API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t
   G_TRY(cudaEventRecord(h->ev0, h->stream));
   G_TRY(cudaMemcpyAsync(dys, y, n * sizeof(double), cudaMemcpyHostToDevice, cs));
   if (ld != n) G_TRY(cudaMemsetAsync(dXs, 0, (size_t)ld * p * sizeof(double), cs));
-  int nch = NCH;
-  if (const char *env = getenv("CDGPU_GRAM_CHUNKS")) nch = std::max(1, std::min(NCH, atoi(env)));
-  int64_t chunk = ((n + nch - 1) / nch + 15) & ~(int64_t)15; // multiple of 16 rows: 16-byte aligned, whole k-tiles
-  if (chunk < 1024) chunk = n;                                // small problems: one piece
-  int ci = 0;
-  for (int64_t r0 = 0; r0 < n; r0 += chunk, ++ci) {
-    const int64_t rows = (r0 + chunk < n) ? chunk : n - r0;
+  // Row chunks grow geometrically: the first one is small (its H2D is the only exposed transfer), and since
+  // PCIe/C2C moves rows ~3x faster than the DMMA SYRK consumes them, each next chunk may be 3x larger and still
+  // land before the previous chunk's SYRK ends.  Few launches also means few read-modify-write passes over G.
+  // The last launch divides by n in its epilogue (mode 3), so there is no separate scale pass.
+  int64_t bounds[NCH + 1];
+  int nch = 0;
+  bounds[0] = 0;
+  {
+    int64_t first = 512, grow = 3;
+    if (const char *env = getenv("CDGPU_GRAM_FIRST_CHUNK")) first = std::max<int64_t>(16, atoll(env) & ~15ll);
+    if (n < 4096) first = n;
+    int64_t r0 = 0, len = first;
+    while (r0 < n && nch < NCH - 1) {
+      const int64_t r1 = std::min<int64_t>(n, r0 + len);
+      bounds[++nch] = r1;
+      r0 = r1;
+      len *= grow;
+    }
+    if (r0 < n) bounds[++nch] = n;
+  }
+  for (int ci = 0; ci < nch; ++ci) {
+    const int64_t r0 = bounds[ci], rows = bounds[ci + 1] - r0;
     G_TRY(cudaMemcpy2DAsync(dXs + r0, ld * sizeof(double), X + r0, ldx * sizeof(double), rows * sizeof(double), p,
                             cudaMemcpyHostToDevice, cs));
     G_TRY(cudaEventCreateWithFlags(&ev[ci], cudaEventDisableTiming));
     G_TRY(cudaEventRecord(ev[ci], cs));
     G_TRY(cudaStreamWaitEvent(h->stream, ev[ci], 0));
-    rc = launch_gram(h, dXs + r0, rows, (int)p, ld, dys + r0, h->dX, h->dy, (double)n, ci == 0 ? 0 : 2);
+    const int mode = nch == 1 ? 1 : (ci == 0 ? 0 : (ci == nch - 1 ? 3 : 2));
+    rc = launch_gram(h, dXs + r0, rows, (int)p, ld, dys + r0, h->dX, h->dy, (double)n, mode);
     if (rc) {
       cleanup();
       return rc;
     }
-  }
-  rc = launch_scale_gram(h, h->dX, h->dy, (int)p, (double)n);
-  if (rc) {
-    cleanup();
-    return rc;
   }
   G_TRY(cudaEventRecord(h->ev1, h->stream));
   G_TRY(cudaStreamSynchronize(h->stream));

@@ -281,7 +281,7 @@ int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, in
 int launch_diag_sqrt(cdgpu_handle_s *h, const double *A, long long lda, int p, double *out);
 
 // Gram (gram_dmma.cu): G = X'X / n_total (lower tiles computed, mirrored), c = -X'y / n_total
-// mode 0: raw sums, 1: sums / divisor, 2: accumulate raw sums into G | c
+// mode 0: raw sums, 1: sums / divisor, 2: accumulate raw sums into G | c, 3: accumulate, then divide
 int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,
                 double *c, double divisor, int mode);
 int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_total);

@@ -189,9 +189,11 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
     __syncthreads(); // all warps done with the last stage before the next tile's prologue overwrites it
 
     // epilogue: G[colA + m, colB + nn] and its mirror.  mode 0: store raw sums, 1: store sums / divisor,
-    // 2: add the raw sums to what is there (row-chunked accumulation; both triangles hold the same value)
+    // 2: add the raw sums to what is there (row-chunked accumulation; both triangles hold the same value),
+    // 3: as 2, then divide by divisor (last row chunk)
     auto put = [&](int r, int cidx, double v) {
-      if (mode == 2) v += G[r + (long long)cidx * ldg];
+      if (mode >= 2) v += G[r + (long long)cidx * ldg];
+      if (mode == 3) v = v / divisor;
       G[r + (long long)cidx * ldg] = v;
       G[cidx + (long long)r * ldg] = v;
     };
@@ -235,7 +237,7 @@ __global__ void xty_kernel(const double *__restrict__ X, long long n, int p, lon
     }
     for (; i < n; i += 32) s0 = fma(__ldg(col + i), __ldg(y + i), s0);
     double s = warp_sum(s0 + s1);
-    if (lane == 0) c[k] = mode == 1 ? -s / divisor : (mode == 2 ? c[k] - s : -s);
+    if (lane == 0) c[k] = mode == 1 ? -s / divisor : (mode == 2 ? c[k] - s : (mode == 3 ? (c[k] - s) / divisor : -s));
   }
 }
 
