@@ -23,22 +23,31 @@ def shard_range(m: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def locpolyl1_sharded(be: Backend, X, z, y, zgrid, degree, kernel, λ0, options=None, group=None):
+def locpolyl1_sharded(be: Backend, X, z, y, zgrid, degree, kernel, λ0, options=None, group=None, interleave=True):
     """locpolyl1 with the grid points split over the ranks of `group`; every rank returns the full
-    ep x m matrix (all_gather of the owned column blocks)."""
+    ep x m matrix (all_gather of the owned columns).  No data-path collective: the local problems are
+    independent.  `interleave=True` deals the grid points round-robin (rank r owns zgrid[r::world]):
+    neighbouring grid points cost about the same number of passes, so the ranks finish together;
+    `interleave=False` gives every rank one contiguous block ([m_begin, m_end) of the C ABI)."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     zgrid = f64(zgrid)
     m = zgrid.size
-    lo, hi = shard_range(m, rank, world)
-    out, _ = be.locpolyl1(X, z, y, zgrid, degree, kernel, λ0, False, options, shard=(lo, hi))
+    if interleave:
+        mine_idx = np.arange(rank, m, world)
+        out, _ = be.locpolyl1(X, z, y, np.ascontiguousarray(zgrid[mine_idx]), degree, kernel, λ0, False, options)
+        cols = out
+    else:
+        lo, hi = shard_range(m, rank, world)
+        out, _ = be.locpolyl1(X, z, y, zgrid, degree, kernel, λ0, False, options, shard=(lo, hi))
+        cols = out[:, lo:hi]
     ep = out.shape[0]
     # gather variable-sized column blocks: pad to the largest block
     width = -(-m // world)
     mine = torch.zeros(width * ep, dtype=torch.float64)
-    mine[: (hi - lo) * ep] = torch.from_numpy(np.ascontiguousarray(out[:, lo:hi].T).ravel())
+    mine[: cols.shape[1] * ep] = torch.from_numpy(np.ascontiguousarray(cols.T).ravel())
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     mine = mine.to(dev)
@@ -46,8 +55,12 @@ def locpolyl1_sharded(be: Backend, X, z, y, zgrid, degree, kernel, λ0, options=
     dist.all_gather(parts, mine, group=group)
     full = np.zeros((ep, m), order="F")
     for r, t in enumerate(parts):
-        a, b = shard_range(m, r, world)
-        full[:, a:b] = t.cpu().numpy()[: (b - a) * ep].reshape(b - a, ep).T
+        if interleave:
+            idx = np.arange(r, m, world)
+            full[:, idx] = t.cpu().numpy()[: idx.size * ep].reshape(idx.size, ep).T
+        else:
+            a, b = shard_range(m, r, world)
+            full[:, a:b] = t.cpu().numpy()[: (b - a) * ep].reshape(b - a, ep).T
     return full
 
 

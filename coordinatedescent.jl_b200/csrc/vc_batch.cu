@@ -503,11 +503,11 @@ struct VcCovArgs {
   double *gscr; // per-warp scratch for the compact active Gram: (grid * VCW) x MC x MC doubles, MC = ep rounded up to even
 };
 
-constexpr int VCW = 4;      // warps (local problems) per CTA
+constexpr int VCW = 1;      // warps (local problems) per CTA (one: shared memory then packs 11 problems per SM)
 constexpr int VC_RING = 4;  // columns of the compact active Gram in flight to shared memory per warp
 __host__ __device__ inline size_t vc_cov_warp_bytes(int ep) {
   const int MC = ((ep + 31) / 32) * 32; // ring stage stride: a whole number of 32-lane rows, so no lane ever clamps
-  return ((size_t)(VC_RING * MC + 7 * ep) * sizeof(double) + (size_t)(9 * ep + 4) * sizeof(int) + (size_t)ep + 15) / 16 * 16;
+  return ((size_t)(VC_RING * MC + 8 * ep) * sizeof(double) + (size_t)(9 * ep + 4) * sizeof(int) + (size_t)ep + 15) / 16 * 16;
 }
 
 __global__ void vc_build_z_kernel(const double *__restrict__ X, long long ldx, int n, int p, const double *__restrict__ y,
@@ -558,7 +558,7 @@ __device__ __forceinline__ void vc_cp16(unsigned dst, const char *src) {
 }
 
 template <int NU>
-__global__ void __launch_bounds__(VCW * 32, 3) vc_cov_kernel(const VcCovArgs a) {
+__global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int ep = a.ep, dg = a.degree + 1, nq = 2 * a.degree + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int MC = (ep + 1) & ~1, RS = 32 * NU; // scratch leading dimension bound, ring stage stride
@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(VCW * 32, 3) vc_cov_kernel(const VcCovArgs a) 
   double *sbeta = ring + VC_RING * RS;                   // dense beta (after a full pass / at phase start)
   double *sval = sbeta + ep, *stmpd = sval + ep;         // list-order values, scratch
   double *sAx = stmpd + ep, *scc = sAx + ep, *sai = scc + ep, *sth = sai + ep; // dense (A x) and constants
-  int *sact = reinterpret_cast<int *>(sth + ep);
+  double *sAxE = sth + ep;                               // (A x) of the active entries of a phase, by snapshot entry
+  int *sact = reinterpret_cast<int *>(sAxE + ep);
   int *snewpos = sact + ep, *sact0 = snewpos + ep, *stmpi = sact0 + ep, *s2 = stmpi + 5 * ep, *spos = s2 + 4;
   unsigned char *sin = reinterpret_cast<unsigned char *>(spos + ep);
   double *Gw = a.gscr + ((long long)blockIdx.x * VCW + warp) * (long long)MC * MC; // this warp's compact Gram scratch
@@ -647,49 +648,35 @@ __global__ void __launch_bounds__(VCW * 32, 3) vc_cov_kernel(const VcCovArgs a) 
       for (int u = 0; u < NU; ++u)
         if (lane + 32 * u < ep) {
           sbeta[lane + 32 * u] = be[u]; // beta at the start of the phase
-          sAx[lane + 32 * u] = Ax[u];
+          sAx[lane + 32 * u] = Ax[u];   // (A x) at the start of the phase, by coordinate
         }
       for (int k = lane; k < ep; k += 32) spos[k] = -1;
       __syncwarp();
       for (int i = lane; i < m; i += 32) {
-        sact0[i] = sact[i];
-        spos[sact[i]] = i;
+        const int k = sact[i];
+        sact0[i] = k;
+        spos[k] = i;
+        sAxE[i] = sAx[k]; // (A x) of the active entries, by snapshot entry, carried from pass to pass
       }
       __syncwarp();
       for (int j = 0; j < m; ++j) {
         const int kj = sact0[j];
         for (int i = lane; i < m; i += 32) Gw[i + (long long)j * ldw] = moment(sact0[i], kj);
       }
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int e = lane + 32 * u;
-        Ax[u] = be[u] = cc[u] = ai[u] = th[u] = 0.0;
-        if (e < m) {
-          const int k = sact0[e];
-          Ax[u] = sAx[k];
-          be[u] = sbeta[k];
-          cc[u] = scc[k];
-          ai[u] = sai[k];
-          th[u] = sth[k];
-        }
-      }
       __syncwarp();
       in_phase = true;
     };
+    // back to the coordinate layout.  Coordinates in the list take their tracked (A x); every other coordinate
+    // (never active in this phase, or dropped during it) gets (A x) at phase start + sum_e A[t, act0_e] (beta_e -
+    // beta_e at phase start).
     auto phase_close = [&](int nact_now) {
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int e = lane + 32 * u;
-        if (e < m0) {
-          const int k = sact0[e];
-          sAx[k] = Ax[u];
-        }
+      for (int k = lane; k < ep; k += 32) stmpd[k] = 0.0; // dense beta now (dropped entries are exactly zero)
+      __syncwarp();
+      for (int i = lane; i < nact_now; i += 32) {
+        const int k = sact[i];
+        stmpd[k] = sval[i];
+        sAx[k] = sAxE[spos[k]];
       }
-      __syncwarp();
-      // beta of the listed entries by coordinate (dropped entries are exactly zero)
-      for (int k = lane; k < ep; k += 32) stmpd[k] = 0.0;
-      __syncwarp();
-      for (int i = lane; i < nact_now; i += 32) stmpd[sact[i]] = sval[i];
       __syncwarp();
       bool inactive[NU];
 #pragma unroll
@@ -698,15 +685,14 @@ __global__ void __launch_bounds__(VCW * 32, 3) vc_cov_kernel(const VcCovArgs a) 
         Ax[u] = be[u] = cc[u] = ai[u] = th[u] = 0.0;
         inactive[u] = false;
         if (t < ep) {
-          inactive[u] = spos[t] < 0;
+          inactive[u] = sin[t] == 0;
           Ax[u] = sAx[t];
-          be[u] = inactive[u] ? 0.0 : stmpd[t];
+          be[u] = stmpd[t];
           cc[u] = scc[t];
           ai[u] = sai[t];
           th[u] = sth[t];
         }
       }
-      // (A x)_t += sum_e A[t, act0_e] (beta_e - beta_e at phase start) for the coordinates outside the active set
       for (int e = 0; e < m0; ++e) {
         const int k = sact0[e];
         const double dlt = stmpd[k] - sbeta[k];
@@ -723,20 +709,42 @@ __global__ void __launch_bounds__(VCW * 32, 3) vc_cov_kernel(const VcCovArgs a) 
       __syncwarp();
       in_phase = false;
     };
-    // one active-set pass inside a phase; returns max|h|
-    auto phase_pass = [&](int m, const PermKey &pkm, long long &accepted) -> double {
-      int *sord = snewpos; // visit position -> snapshot entry | list position << 16 (snewpos is unused while m_old == m_now)
+    // One active-set pass inside a phase; returns max|h|.  The m listed entries are laid out IN VISIT ORDER for the
+    // pass: visit position s <-> (lane s & 31, slot s >> 5), so the stepping slot is a compile-time index and the
+    // owner is the loop counter: no selects, no uniform loads on the chain.  A step: every lane evaluates its own
+    // slot-u entry, lane i's h is broadcast by one shuffle, every lane updates all its entries with the column of
+    // the compact Gram that the cp.async ring brought to shared memory VC_RING-1 steps earlier (rows are read
+    // through the lane's position -> snapshot-entry map).
+    auto phase_pass = [&](int m, const PermKey &pkm, int &accepted) -> double {
+      unsigned *soff = reinterpret_cast<unsigned *>(stmpi); // byte offset of the column of visit position s in Gw
+      int *slist = stmpi + ep;                              // list position i_ of visit position s
       for (int s_ = lane; s_ < m; s_ += 32) {
         const int i_ = ordered ? s_ : (int)cd_perm(pkm, (uint32_t)s_);
-        sord[s_] = spos[sact[i_]] | (i_ << 16);
+        slist[s_] = i_;
+        soff[s_] = (unsigned)(spos[sact[i_]] * ldw) * 8u;
       }
       __syncwarp();
-      // column of snapshot entry e -> ring stage (16-byte chunks; ldw is even and Gw 16-byte aligned)
+      int row[NU]; // snapshot entry (= row of the compact Gram) of this lane's visit positions
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int s_ = lane + 32 * u;
+        Ax[u] = be[u] = cc[u] = ai[u] = th[u] = 0.0;
+        row[u] = 0;
+        if (s_ < m) {
+          const int i_ = slist[s_], k = sact[i_];
+          row[u] = spos[k];
+          Ax[u] = sAxE[row[u]];
+          be[u] = sval[i_];
+          cc[u] = scc[k];
+          ai[u] = sai[k];
+          th[u] = sth[k];
+        }
+      }
       const char *gsrc = reinterpret_cast<const char *>(Gw) + lane * 16;
       const unsigned rdst = (unsigned)__cvta_generic_to_shared(ring) + lane * 16;
-      auto fetch = [&](int s_) {
+      auto fetch = [&](int s_) { // column of visit position s_ -> ring stage s_ % VC_RING (16-byte chunks)
         if (s_ < m) {
-          const char *src = gsrc + (unsigned)((sord[s_] & 0xffff) * ldw) * 8u;
+          const char *src = gsrc + soff[s_];
           const unsigned dst = rdst + (unsigned)(s_ % VC_RING) * (unsigned)(RS * 8);
           if (2 * lane < m0) vc_cp16<0>(dst, src);
           if ((NU + 1) / 2 > 1 && 2 * (lane + 32) < m0) vc_cp16<512>(dst, src);
@@ -747,58 +755,41 @@ __global__ void __launch_bounds__(VCW * 32, 3) vc_cov_kernel(const VcCovArgs a) 
       };
 #pragma unroll
       for (int d = 0; d < VC_RING - 1; ++d) fetch(d);
-      asm volatile("cp.async.wait_group %0;" ::"n"(VC_RING - 2) : "memory");
-      __syncwarp();
-      double gn[NU];
-#pragma unroll
-      for (int u = 0; u < NU; ++u) gn[u] = ring[lane + 32 * u]; // column of step 0 (stage 0)
-      // beta and the constants of the stepping entry are read (uniformly) from shared memory one step ahead;
-      // only (A x) of the entries lives in registers, so the owner picks ONE value by slot
-      int nxt = m > 0 ? sord[0] : 0;
-      int kn = m > 0 ? sact[nxt >> 16] : 0;
-      double nbe = m > 0 ? sval[nxt >> 16] : 0.0, ncc = scc[kn], nai = sai[kn], nth = sth[kn];
       double maxH = 0.0;
-#pragma unroll 2
-      for (int s_ = 0; s_ < m; ++s_) {
-        const int e = nxt & 0xffff, i_ = nxt >> 16;
-        const double xbe = nbe, xcc = ncc, xai = nai, xth = nth;
-        double gc[NU];
 #pragma unroll
-        for (int u = 0; u < NU; ++u) gc[u] = gn[u];
-        const long long tw0 = (a.dbg & 4) ? clock64() : 0;
-        if (!(a.dbg & 1)) {
-        fetch(s_ + VC_RING - 1); // overwrites the stage of step s_-1, whose values were taken an iteration ago
-        asm volatile("cp.async.wait_group %0;" ::"n"(VC_RING - 2) : "memory");
-        __syncwarp();
+      for (int u = 0; u < NU; ++u) {
+        const int cnt = min(32, m - 32 * u);
+        for (int i = 0; i < cnt; ++i) { // visit position s_ = 32 u + i, ring stage i % VC_RING (32 % VC_RING == 0)
+          const int s_ = 32 * u + i;
+          asm volatile("cp.async.wait_group %0;" ::"n"(VC_RING - 2) : "memory"); // column of position s_ has landed
+          __syncwarp();
+          const double *col = ring + (i % VC_RING) * RS;
+          double gc[NU];
+#pragma unroll
+          for (int q = 0; q < NU; ++q) gc[q] = col[row[q]];
+          fetch(s_ + VC_RING - 1); // into the stage of position s_-1, which every lane read before the barrier above
+          const double v = __dsub_rn(be[u], __dmul_rn(Ax[u] + cc[u], ai[u]));
+          const double nwl = cd_shrink(v, th[u]);
+          const double h = __shfl_sync(0xffffffffu, nwl - be[u], i);
+          if (lane == i) be[u] = nwl;
+          if (h != 0.0) {
+#pragma unroll
+            for (int q = 0; q < NU; ++q) Ax[q] = __dadd_rn(Ax[q], __dmul_rn(gc[q], h));
+            accepted += 1;
+          }
+          maxH = fmax(maxH, fabs(h));
         }
-        if (a.dbg & 4) wait_cyc += clock64() - tw0;
-        if (s_ + 1 < m) {
-          const double *nx = ring + ((s_ + 1) % VC_RING) * RS + lane;
-#pragma unroll
-          for (int u = 0; u < NU; ++u) gn[u] = nx[32 * u];
-          nxt = sord[s_ + 1];
-          kn = sact[nxt >> 16];
-          nbe = sval[nxt >> 16];
-          ncc = scc[kn];
-          nai = sai[kn];
-          nth = sth[kn];
-        }
-        const int owner = e & 31, slot = e >> 5;
-        double xg = Ax[0];
-#pragma unroll
-        for (int u = 1; u < NU; ++u) xg = u == slot ? Ax[u] : xg;
-        const double v = __dsub_rn(xbe, __dmul_rn(xg + xcc, xai));
-        const double nwl = cd_shrink(v, xth);
-        const double h = __shfl_sync(0xffffffffu, nwl - xbe, owner);
-        if (lane == owner) sval[i_] = nwl;
-        if (h != 0.0) {
-#pragma unroll
-          for (int u = 0; u < NU; ++u) Ax[u] = __dadd_rn(Ax[u], __dmul_rn(gc[u], h));
-          accepted += 1;
-        }
-        maxH = fmax(maxH, fabs(h));
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int s_ = lane + 32 * u;
+        if (s_ < m) {
+          sAxE[row[u]] = Ax[u];
+          sval[slist[s_]] = be[u];
+        }
+      }
       __syncwarp();
       return maxH;
     };
@@ -908,7 +899,9 @@ __global__ void __launch_bounds__(VCW * 32, 3) vc_cov_kernel(const VcCovArgs a) 
           tq = clock64();
         }
         const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter);
-        maxH = phase_pass(m, pkm, st.accepted);
+        int acc_pass = 0;
+        maxH = phase_pass(m, pkm, acc_pass);
+        st.accepted += acc_pass;
         pc[1] += clock64() - tq;
         tq = clock64();
         if (!(a.dbg & 2)) {
