@@ -3,7 +3,7 @@
 grid points dealt round-robin over the ranks, no data-path collective (final all_gather of the coefficients).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29541 \
-        benchmarks/c4_sharded.py [--m 4096]
+        benchmarks/c4_sharded.py [--grid-points 4096]
 
 Strong scaling: the same 4096 problems whatever N.  Device time = max over ranks of the library's CUDA-event time;
 wall = barrier-to-barrier around the sharded call including H2D, D2H and the gather.  One JSON line from rank 0."""
@@ -26,7 +26,7 @@ from cdgpu.distributed import locpolyl1_sharded  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--m", type=int, default=4096)
+    ap.add_argument("--grid-points", dest="m", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

@@ -772,11 +772,10 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
           const double nwl = cd_shrink(v, th[u]);
           const double h = __shfl_sync(0xffffffffu, nwl - be[u], i);
           if (lane == i) be[u] = nwl;
-          if (h != 0.0) {
+          // h == 0 adds an exact zero (the Gram entries are finite): no data-dependent branch on the chain
 #pragma unroll
-            for (int q = 0; q < NU; ++q) Ax[q] = __dadd_rn(Ax[q], __dmul_rn(gc[q], h));
-            accepted += 1;
-          }
+          for (int q = 0; q < NU; ++q) Ax[q] = __dadd_rn(Ax[q], __dmul_rn(gc[q], h));
+          accepted += h != 0.0;
           maxH = fmax(maxH, fabs(h));
         }
       }
