@@ -461,27 +461,19 @@ class Backend:
         out = np.zeros((ep, m), order="F")
         stats = (_ffi.Stats * m)()
         o = options.c()
-        self.lib.check(self.lib.vc_solve(ptr(X), n, p, n, ptr(z), ptr(y), ptr(zgrid), m, lo, hi, int(degree),
-                                         kernel.kind, float(kernel.h), float(λ0), C.byref(o), self.device, ptr(out),
-                                         C.cast(stats, C.c_void_p)))
-        self.last_vc_stats = [stats[i].as_dict() for i in range(lo, hi)]
         if not refit:
+            self.lib.check(self.lib.vc_solve(ptr(X), n, p, n, ptr(z), ptr(y), ptr(zgrid), m, lo, hi, int(degree),
+                                             kernel.kind, float(kernel.h), float(λ0), C.byref(o), self.device, ptr(out),
+                                             C.cast(stats, C.c_void_p)))
+            self.last_vc_stats = [stats[i].as_dict() for i in range(lo, hi)]
             return out, None
-        # refit on the selected groups (varying_coefficient_lasso.jl:71-76, get_nonzero_coordinates! :488-512):
-        # weighted normal equations on the host (LAPACK `\`, as in the reference) — post-processing
-        outR = np.zeros_like(out)
-        dg = degree + 1
-        for g in range(lo, hi):
-            grp = np.flatnonzero(np.any(out[:, g].reshape(p, dg) != 0, axis=1))
-            if grp.size == 0:
-                continue
-            S = (grp[:, None] * dg + np.arange(dg)[None, :]).ravel()
-            d = z - zgrid[g]
-            w = np.exp(-d ** 2 / kernel.h) / kernel.h if kernel.kind == _ffi.KERNEL_GAUSSIAN else \
-                np.where(np.abs(d / kernel.h) >= 1, 0.0, 0.75 * (1 - (d / kernel.h) ** 2) / kernel.h)
-            Xs = np.stack([X[:, k // dg] * d ** (k % dg) for k in S], axis=1)
-            tmp = Xs.T * w
-            outR[S, g] = np.linalg.solve(tmp @ Xs, tmp @ y)
+        # refit on the selected groups (varying_coefficient_lasso.jl:71-76, get_nonzero_coordinates! :488-512) inside the
+        # same library call: the normal equations come from the moment blocks already on the device
+        outR = np.zeros((ep, m), order="F")
+        self.lib.check(self.lib.vc_solve_refit(ptr(X), n, p, n, ptr(z), ptr(y), ptr(zgrid), m, lo, hi, int(degree),
+                                               kernel.kind, float(kernel.h), float(λ0), C.byref(o), self.device, ptr(out),
+                                               ptr(outR), C.cast(stats, C.c_void_p)))
+        self.last_vc_stats = [stats[i].as_dict() for i in range(lo, hi)]
         return out, outR
 
     def findLambdaMax(self, f: _Loss, ω=None) -> float:  # coordinate_descent.jl:118-149 at x = 0

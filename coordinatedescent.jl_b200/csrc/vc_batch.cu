@@ -495,7 +495,7 @@ struct VcCovArgs {
   double optTol;
   int randomize;
   unsigned long long seed;
-  double *out;
+  double *out, *outR; // outR: refitted coefficients (null: no refit)
   DevStats *stats;
   int *counter; // dynamic work distribution
   unsigned long long *prof; // optional [8]: summed warp cycles: full passes, active chain, list compaction, phase open, phase close, total
@@ -932,6 +932,87 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
       if (lane + 32 * u < ep) col[lane + 32 * u] = be[u];
     if (lane == 0 && a.stats) a.stats[g] = st;
     __syncwarp();
+    if (a.outR) {
+      // ---- refit (varying_coefficient_lasso.jl:71-76): A_g[S,S] x = -b_g[S] on the expanded coordinates S of every
+      // group with a non-zero coefficient (get_nonzero_coordinates!, :488-512).  Both sides come from the moment
+      // blocks; left-looking Cholesky in this warp's scratch (columns are contiguous: coalesced, and all loads of
+      // a column's update are independent), then the two triangular solves.
+      double *colR = a.outR + (long long)g * ep;
+      for (int k = lane; k < ep; k += 32) {
+        colR[k] = 0.0;
+        sin[k] = 0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+        if (lane + 32 * u < ep && be[u] != 0.0) {
+          const int j0 = tj[u] * dg;
+          for (int l = 0; l < dg; ++l) sin[j0 + l] = 1; // the whole group (same byte value from every writer)
+        }
+      __syncwarp();
+      int ms = 0; // ordered list S (ascending coordinates) in sact
+      for (int k0 = 0; k0 < ep; k0 += 32) {
+        const int k = k0 + lane;
+        const bool inS = k < ep && sin[k] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, inS);
+        if (inS) sact[ms + __popc(bal & ((1u << lane) - 1u))] = k;
+        ms += __popc(bal);
+      }
+      __syncwarp();
+      if (ms > 0) {
+        const int ldm = (ms + 1) & ~1;
+        double *rhs = stmpd, *lrow = sval; // right-hand side / solution, L[j, 0..j) of the column being formed
+        for (int i = lane; i < ms; i += 32) rhs[i] = -scc[sact[i]];
+        bool ok = true;
+        for (int j = 0; j < ms; ++j) {
+          const int kj = sact[j];
+          // row j of L computed so far -> shared memory (uniform operands of the column update)
+          for (int k = lane; k < j; k += 32) lrow[k] = Gw[j + (long long)k * ldm];
+          __syncwarp();
+          double acc[NU];
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const int i = j + lane + 32 * u;
+            acc[u] = i < ms ? moment(sact[i], kj) : 0.0;
+          }
+          for (int k = 0; k < j; ++k) {
+            const double ljk = lrow[k];
+            const double *ck = Gw + (long long)k * ldm + j + lane;
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+              if (j + lane + 32 * u < ms) acc[u] = fma(-__ldcg(ck + 32 * u), ljk, acc[u]);
+          }
+          const double djj = __shfl_sync(0xffffffffu, acc[0], 0);
+          if (!(djj > 0.0)) ok = false; // not positive definite (collinear selected columns): NaN, as a SingularException
+          const double d = sqrt(djj);
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const int i = j + lane + 32 * u;
+            if (i < ms) Gw[i + (long long)j * ldm] = i == j ? d : acc[u] / d;
+          }
+          __syncwarp();
+        }
+        // L y = rhs (column sweep), then L' x = y (dot products)
+        for (int j = 0; j < ms; ++j) {
+          const double yj = rhs[j] / __ldcg(Gw + j + (long long)j * ldm);
+          __syncwarp();
+          if (lane == 0) rhs[j] = yj;
+          for (int i = j + 1 + lane; i < ms; i += 32) rhs[i] = fma(-__ldcg(Gw + i + (long long)j * ldm), yj, rhs[i]);
+          __syncwarp();
+        }
+        for (int j = ms - 1; j >= 0; --j) {
+          double sacc = 0.0;
+          for (int i = j + 1 + lane; i < ms; i += 32) sacc = fma(__ldcg(Gw + i + (long long)j * ldm), rhs[i], sacc);
+          sacc = warp_sum(sacc);
+          const double xj = (rhs[j] - sacc) / __ldcg(Gw + j + (long long)j * ldm);
+          __syncwarp();
+          if (lane == 0) rhs[j] = xj;
+          __syncwarp();
+        }
+        for (int i = lane; i < ms; i += 32) colR[sact[i]] = ok ? rhs[i] : nan("");
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -941,7 +1022,7 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
 static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                            const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                            double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
-                           cdgpu_stats *stats) {
+                           double *outR, cdgpu_stats *stats) {
   const int64_t ep = p * (degree + 1), mloc = m_end - m_begin, P2 = p * (p + 1) / 2, PA = P2 + p;
   const int nq = 2 * degree + 1;
   const long long ldz = (n + 1) & ~(int64_t)1, ldc = (PA + 1) & ~(int64_t)1;
@@ -952,7 +1033,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   cudaEvent_t e0 = nullptr, e1 = nullptr, eg = nullptr;
   double *dX = nullptr, *dz = nullptr, *dy = nullptr, *dgz = nullptr, *dout = nullptr, *dZ = nullptr, *dV = nullptr, *dC = nullptr;
   DevStats *dst = nullptr;
-  double *dG = nullptr;
+  double *dG = nullptr, *doutR = nullptr;
   int *dcounter = nullptr;
   unsigned long long *dprof = nullptr;
   void *dtiles = nullptr;
@@ -960,7 +1041,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   auto cleanup = [&]() {
     if (s) cudaStreamSynchronize(s);
     for (void *ptr : {(void *)dX, (void *)dz, (void *)dy, (void *)dgz, (void *)dout, (void *)dZ, (void *)dV, (void *)dC,
-                      (void *)dst, (void *)dcounter, (void *)dprof, (void *)dG, dtiles})
+                      (void *)dst, (void *)dcounter, (void *)dprof, (void *)dG, (void *)doutR, dtiles})
       if (ptr) cudaFreeAsync(ptr, s);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
@@ -990,6 +1071,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   VM_TRY(cudaMallocAsync((void **)&dgz, (size_t)m * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dout, (size_t)ep * m * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dst, (size_t)m * sizeof(DevStats), s));
+  if (outR) VM_TRY(cudaMallocAsync((void **)&doutR, (size_t)ep * m * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dZ, (size_t)ldz * PA * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dV, (size_t)ldz * nq * chunk * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dC, (size_t)ldc * nq * chunk * sizeof(double), s));
@@ -1055,6 +1137,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
     a.randomize = opt->randomize;
     a.seed = opt->seed;
     a.out = dout;
+    a.outR = doutR;
     a.stats = dst;
     a.counter = dcounter;
     a.prof = dprof;
@@ -1067,6 +1150,8 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   }
   VM_TRY(cudaEventRecord(e1, s));
   VM_TRY(cudaMemcpyAsync(out + m_begin * ep, dout + m_begin * ep, (size_t)mloc * ep * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (outR)
+    VM_TRY(cudaMemcpyAsync(outR + m_begin * ep, doutR + m_begin * ep, (size_t)mloc * ep * sizeof(double), cudaMemcpyDeviceToHost, s));
   VM_TRY(cudaStreamSynchronize(s));
   if (stats) {
     float ms = 0.f;
@@ -1104,10 +1189,29 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   return CDGPU_OK;
 }
 
+static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                         const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                         double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out, double *outR,
+                         cdgpu_stats *stats);
 API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                        const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                        double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
                        cdgpu_stats *stats) {
+  return vc_solve_impl(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt, device, out,
+                       nullptr, stats);
+}
+API int cdgpu_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                             const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                             double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
+                             double *outR, cdgpu_stats *stats) {
+  if (!outR) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  return vc_solve_impl(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt, device, out,
+                       outR, stats);
+}
+static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                         const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                         double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out, double *outR,
+                         cdgpu_stats *stats) {
   if (!X || !z || !y || !zgrid || !opt || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (n < 1 || p < 1 || ldx < n || degree < 0 || m < 0 || m_begin < 0 || m_end > m || m_begin > m_end)
     return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
@@ -1129,9 +1233,12 @@ API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
     // moment (covariance) form unless the expanded problem is too wide for the warp kernel's registers;
     // CDGPU_VC_FORM=naive keeps the residual-form kernels below
     const char *form = getenv("CDGPU_VC_FORM");
-    if (ep <= 256 && !(form && strcmp(form, "naive") == 0))
+    if (ep <= 256 && (outR || !(form && strcmp(form, "naive") == 0)))
       return vc_solve_moment(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt,
-                             device, out, stats);
+                             device, out, outR, stats);
+    if (outR)
+      return cdgpu_set_error(CDGPU_ECAP, "refit on the device needs the moment form: p*(degree+1) = %lld exceeds 256",
+                             (long long)ep);
   }
   int nr = n <= 128 ? 4 : (n <= 256 ? 8 : (n <= 512 ? 16 : 0)); // 0: CTA-per-problem kernel
   if (const char *env = getenv("CDGPU_VC_THREADS")) nr = atoi(env) == 32 ? nr : 0;

@@ -273,17 +273,25 @@ end
 kernel_kind(::GaussianKernel) = Cint(0)
 kernel_kind(::EpanechnikovKernel) = Cint(1)
 
-# locpolyl1 (varying_coefficient_lasso.jl:30-79), refit=false: all grid points in one batched launch
+# locpolyl1 (varying_coefficient_lasso.jl:30-79): all grid points in one batched call; with refit=true the weighted
+# normal equations on the selected groups (:71-76) are formed from the same moment blocks and solved on the device
 function locpolyl1(X::Matrix{Float64}, z::Vector{Float64}, y::Vector{Float64}, zgrid::Vector{Float64}, degree::Int64,
                    kernel::SmoothingKernel{Float64}, λ0::Float64, refit::Bool, options::CDOptions=CDOptions(); device::Integer=0)
-    refit && error("refit=true is not on the device yet")
     n, p = size(X); ep = p * (degree + 1); m = length(zgrid)
     out = zeros(Float64, ep, m)
-    GC.@preserve X z y zgrid out check(ccall((:cdgpu_vc_solve, libcdgpu), Cint,
+    if !refit
+        GC.@preserve X z y zgrid out check(ccall((:cdgpu_vc_solve, libcdgpu), Cint,
+            (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint, Cint, Float64, Float64,
+             Ref{cdgpu_options}, Cint, Ptr{Float64}, Ptr{Cvoid}),
+            X, n, p, n, z, y, zgrid, m, 0, m, degree, kernel_kind(kernel), kernel.h, λ0, Ref(c_opts(options)), device, out, C_NULL))
+        return sparse(out), spzeros(Float64, ep, m)
+    end
+    outR = zeros(Float64, ep, m)
+    GC.@preserve X z y zgrid out outR check(ccall((:cdgpu_vc_solve_refit, libcdgpu), Cint,
         (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint, Cint, Float64, Float64,
-         Ref{cdgpu_options}, Cint, Ptr{Float64}, Ptr{Cvoid}),
-        X, n, p, n, z, y, zgrid, m, 0, m, degree, kernel_kind(kernel), kernel.h, λ0, Ref(c_opts(options)), device, out, C_NULL))
-    sparse(out), spzeros(Float64, ep, m)
+         Ref{cdgpu_options}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+        X, n, p, n, z, y, zgrid, m, 0, m, degree, kernel_kind(kernel), kernel.h, λ0, Ref(c_opts(options)), device, out, outR, C_NULL))
+    sparse(out), sparse(outR)
 end
 
 end # module

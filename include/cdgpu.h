@@ -204,6 +204,14 @@ int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const dou
                    const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                    double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
                    cdgpu_stats *stats);
+/* locpolyl1(...; refit=true) (:71-76): as cdgpu_vc_solve, and outR[S, g] = (Xs' W Xs) \ (Xs' W y) on the expanded
+ * coordinates S of every group with a non-zero coefficient (get_nonzero_coordinates!, :488-512), zero elsewhere.
+ * On the device the normal equations come from the same moment blocks as the lasso (no pass over the data) and
+ * are solved by one warp per grid point (Cholesky).  outR: dense ep x m like out. */
+int cdgpu_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                         const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                         double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
+                         double *outR, cdgpu_stats *stats);
 
 #ifdef __cplusplus
 }

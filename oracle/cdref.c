@@ -871,12 +871,47 @@ API void cdref_expand_X(double *tX, const double *X, int64_t n, int64_t p, int64
       }
     }
 }
-/* locpolyl1 with refit=false: :30-79.  The iterate is carried from one grid
- * point to the next exactly as in the reference (:56,:68). */
-API int cdref_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
-                       const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
-                       double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
-                       cdgpu_stats *stats) {
+/* The iterate is carried from one grid point to the next exactly as in the reference (:56,:68). */
+/* A x = rhs for a dense k x k system by LU with partial pivoting (what Julia's `\` does for a general square
+ * matrix); A (column-major, ld k) and rhs are overwritten.  Returns 1 on a zero pivot. */
+static int lu_solve(double *A, double *rhs, int64_t k) {
+  for (int64_t c = 0; c < k; ++c) {
+    int64_t piv = c;
+    for (int64_t i = c + 1; i < k; ++i)
+      if (fabs(A[i + c * k]) > fabs(A[piv + c * k])) piv = i;
+    if (A[piv + c * k] == 0.0) return 1;
+    if (piv != c) {
+      for (int64_t j = 0; j < k; ++j) {
+        double t = A[c + j * k];
+        A[c + j * k] = A[piv + j * k];
+        A[piv + j * k] = t;
+      }
+      double t = rhs[c];
+      rhs[c] = rhs[piv];
+      rhs[piv] = t;
+    }
+    for (int64_t i = c + 1; i < k; ++i) {
+      double l = A[i + c * k] / A[c + c * k];
+      A[i + c * k] = l;
+      for (int64_t j = c + 1; j < k; ++j) A[i + j * k] -= l * A[c + j * k];
+      rhs[i] -= l * rhs[c];
+    }
+  }
+  for (int64_t c = k - 1; c >= 0; --c) {
+    double v = rhs[c];
+    for (int64_t j = c + 1; j < k; ++j) v -= A[c + j * k] * rhs[j];
+    rhs[c] = v / A[c + c * k];
+  }
+  return 0;
+}
+
+/* locpolyl1 (:30-79) with the optional refit (:71-76): outR[S, g] = (Xs' W Xs) \ (Xs' W y) on the expanded
+ * coordinates S of every group with a non-zero coefficient (get_nonzero_coordinates!, :488-512).  outR may be
+ * NULL (refit = false). */
+API int cdref_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                             const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                             double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
+                             double *outR, cdgpu_stats *stats) {
   (void)device;
   if (!X || !z || !y || !zgrid || !opt || !out) return fail(CDGPU_EARG, "null pointer");
   if (n < 1 || p < 1 || ldx < n || degree < 0 || m < 0 || m_begin < 0 || m_end > m || m_begin > m_end)
@@ -913,12 +948,51 @@ API int cdref_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
     for (int64_t s = 0; s < f->x.nnz; ++s) col[f->x.nzval2ind[s] - 1] = f->x.nzval[s];
     st.device_ms = now_ms() - t0;
     if (stats) stats[g] = st;
+    if (outR) {
+      double *colR = outR + g * ep;
+      int64_t *S = (int64_t *)malloc((size_t)ep * sizeof(int64_t)), ns = 0, dgp = degree + 1;
+      for (int64_t k = 0; k < ep; ++k) colR[k] = 0.0;
+      for (int64_t j = 0; j < p; ++j) {
+        int nz = 0;
+        for (int64_t k = j * dgp; k < (j + 1) * dgp; ++k) nz |= col[k] != 0.0;
+        if (nz)
+          for (int64_t k = j * dgp; k < (j + 1) * dgp; ++k) S[ns++] = k;
+      }
+      if (ns > 0) {
+        double *M = (double *)malloc((size_t)(ns * ns) * sizeof(double)), *rhs = (double *)malloc((size_t)ns * sizeof(double));
+        for (int64_t a = 0; a < ns; ++a) {
+          const double *ca = eX + S[a] * n;
+          double r = 0.0;
+          for (int64_t i = 0; i < n; ++i) r += ca[i] * w[i] * y[i];
+          rhs[a] = r;
+          for (int64_t b = 0; b < ns; ++b) {
+            const double *cb = eX + S[b] * n;
+            double v = 0.0;
+            for (int64_t i = 0; i < n; ++i) v += ca[i] * w[i] * cb[i];
+            M[a + b * ns] = v;
+          }
+        }
+        if (lu_solve(M, rhs, ns))
+          for (int64_t a = 0; a < ns; ++a) rhs[a] = NAN; /* SingularException in the reference */
+        for (int64_t a = 0; a < ns; ++a) colR[S[a]] = rhs[a];
+        free(M);
+        free(rhs);
+      }
+      free(S);
+    }
   }
   cdref_destroy(f);
   free(w);
   free(eX);
   free(sd);
   return CDGPU_OK;
+}
+API int cdref_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                       const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                       double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
+                       cdgpu_stats *stats) {
+  return cdref_vc_solve_refit(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt,
+                              device, out, NULL, stats);
 }
 
 /* ---------------------------------------------------------------------- */

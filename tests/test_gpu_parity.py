@@ -327,6 +327,19 @@ def test_refit_next_tier(gpu, ref):
     out, outR = gpu.locpolyl1(Xs, Z, Y, np.array([0.3, 0.6]), 1, GaussianKernel(0.2), 0.05, True, o)
     assert outR.shape == out.shape and np.count_nonzero(outR) >= np.count_nonzero(out) > 0
     assert np.array_equal(np.any(outR.reshape(6, 2, 2) != 0, axis=1), np.any(out.reshape(6, 2, 2) != 0, axis=1))
+    # device refit (Cholesky on the moment blocks) == oracle refit (LU on X_S' W X_S), also on wide groups
+    outr, outRr = ref.locpolyl1(Xs, Z, Y, np.array([0.3, 0.6]), 1, GaussianKernel(0.2), 0.05, True, o)
+    assert np.array_equal(outR != 0, outRr != 0) and np.allclose(outR, outRr, rtol=1e-8, atol=1e-11)
+    rng = np.random.default_rng(93)
+    n, p = 260, 40
+    Xw = np.asfortranarray(rng.standard_normal((n, p)))
+    Zw = rng.random(n)
+    Yw = Xw[:, 0] * np.sin(2 * Zw) + Xw[:, 1] * np.sin(4 * Zw) + 0.1 * rng.standard_normal(n)
+    zg = np.linspace(0.1, 0.9, 5)
+    og, ogR = gpu.locpolyl1(Xw, Zw, Yw, zg, 2, GaussianKernel(0.25), 0.02, True, o)
+    orf, orR = ref.locpolyl1(Xw, Zw, Yw, zg, 2, GaussianKernel(0.25), 0.02, True, o)
+    assert (orR != 0).sum(0).max() > 32  # more selected coordinates than one lane row
+    assert np.array_equal(ogR != 0, orR != 0) and np.allclose(ogR, orR, rtol=1e-7, atol=1e-10)
 
 
 def test_errors_match_reference(gpu):
