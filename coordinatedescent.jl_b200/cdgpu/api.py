@@ -476,6 +476,28 @@ class Backend:
         self.last_vc_stats = [stats[i].as_dict() for i in range(lo, hi)]
         return out, outR
 
+    # lvocv_locpolyl1(X, z, y, degree, hArr, kernelType, λ0, options)   varying_coefficient_lasso.jl:81-137
+    def lvocv_locpolyl1(self, X, z, y, degree, hArr, kernelType, λ0, options: CDOptions = None, shard=None):
+        """Leave-one-out MSE per bandwidth.  `kernelType` is GaussianKernel or EpanechnikovKernel (the class, as in the
+        reference's `createKernel(kernelType, h)`).  All numH*n local problems run as one batch; `shard=(q0, q1)`
+        restricts the call to a slice of the (bandwidth-major) problem list and returns the partial sums."""
+        options = options or CDOptions()
+        X, z, y, hArr = f64(X), f64(z), f64(y), f64(hArr)
+        n, p = X.shape
+        if z.shape != (n,) or y.shape != (n,):
+            raise DimensionMismatch()
+        numH = hArr.size
+        m = numH * n
+        lo, hi = shard if shard is not None else (0, m)
+        sq = np.zeros(m)
+        stats = (_ffi.Stats * m)()
+        o = options.c()
+        self.lib.check(self.lib.vc_lvocv(ptr(X), n, p, n, ptr(z), ptr(y), int(degree), ptr(hArr), numH, kernelType(1.0).kind,
+                                         float(λ0), C.byref(o), lo, hi, self.device, ptr(sq), C.cast(stats, C.c_void_p)))
+        self.last_vc_stats = [stats[i].as_dict() for i in range(lo, hi)]
+        self.last_lvocv_sqerr = sq
+        return sq.reshape(numH, n).sum(axis=1)  # MSE[indH] += (Yh - y[i])^2, :131
+
     def findLambdaMax(self, f: _Loss, ω=None) -> float:  # coordinate_descent.jl:118-149 at x = 0
         out = C.c_double()
         ω = None if ω is None else f64(ω)

@@ -498,6 +498,11 @@ struct VcCovArgs {
   double *out, *outR; // outR: refitted coefficients (null: no refit)
   DevStats *stats;
   int *counter; // dynamic work distribution
+  // lvocv_locpolyl1: problem g = (bandwidth g / n, left-out observation g % n)
+  int lvo, n;
+  const double *X, *y; // device copies (n x p, ldx) for the prediction of the left-out response
+  long long ldx;
+  double *lvo_err;     // squared prediction error per problem
   unsigned long long *prof; // optional [8]: summed warp cycles: full passes, active chain, list compaction, phase open, phase close, total
   int dbg;      // CDGPU_VC_DBG (timing experiments only; results are wrong when set): 1 no column prefetch, 2 no compaction
   double *gscr; // per-warp scratch for the compact active Gram: (grid * VCW) x MC x MC doubles, MC = ep rounded up to even
@@ -514,6 +519,10 @@ __global__ void vc_build_z_kernel(const double *__restrict__ X, long long ldx, i
                                   double *Z, long long ldz) {
   const int P2 = p * (p + 1) / 2;
   const int col = blockIdx.x;
+  if (col >= P2 + p) { // y.^2 and the constant 1: sum w y^2 and sum w for the sigma of the scaled-lasso loops
+    for (int i = threadIdx.x; i < n; i += blockDim.x) Z[i + (long long)col * ldz] = col == P2 + p ? y[i] * y[i] : 1.0;
+    return;
+  }
   int j, jp;
   if (col < P2) {
     j = (int)((sqrt(8.0 * (double)col + 1.0) - 1.0) * 0.5);
@@ -528,11 +537,14 @@ __global__ void vc_build_z_kernel(const double *__restrict__ X, long long ldx, i
   for (int i = threadIdx.x; i < n; i += blockDim.x) Z[i + (long long)col * ldz] = cj[i] * cjp[i];
 }
 
+// lvo (harr != null): problem g = (bandwidth harr[g / n], z0 = z[g % n]) with the weight of observation g % n zeroed
 __global__ void vc_build_v_kernel(const double *__restrict__ z, const double *__restrict__ zgrid, int n, int g0, int g1,
-                                  int nq, int kernel_kind, double bandwidth, double *V, long long ldv) {
+                                  int nq, int kernel_kind, double bandwidth, double *V, long long ldv,
+                                  const double *__restrict__ harr) {
   const int g = g0 + blockIdx.x;
   if (g >= g1) return;
-  const double z0 = zgrid[g];
+  const double z0 = harr ? z[g % n] : zgrid[g];
+  if (harr) bandwidth = harr[g / n];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double zi = z[i];
     double w;
@@ -543,6 +555,7 @@ __global__ void vc_build_v_kernel(const double *__restrict__ z, const double *__
       const double u = (zi - z0) / bandwidth;
       w = fabs(u) >= 1.0 ? 0.0 : 0.75 * (1.0 - u * u) / bandwidth;
     }
+    if (harr && i == g % n) w = 0.0; // w[i] = zero(T), varying_coefficient_lasso.jl:108
     const double dz = zi - z0;
     double v = w;
     for (int q = 0; q < nq; ++q) {
@@ -557,7 +570,7 @@ __device__ __forceinline__ void vc_cp16(unsigned dst, const char *src) {
   asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%2], 16;" ::"r"(dst), "l"(src), "n"(OFF) : "memory");
 }
 
-template <int NU>
+template <int NU, bool LVO>
 __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int ep = a.ep, dg = a.degree + 1, nq = 2 * a.degree + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -800,10 +813,14 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
     st.outer_iters = 0;
     st.sigma = 0.0;
     unsigned long long pass_counter = 0;
-    bool conv = true;
-    long long iter = 0;
     long long pc[6] = {0, 0, 0, 0, 0, 0};
     const long long tstart = clock64();
+    // _coordinateDescent! (coordinate_descent.jl:65-92) from the current iterate: full pass first, active-set passes
+    // until one converges, exit when a full pass has max|h| < optTol
+    auto run_solve = [&]() {
+    bool conv = true;
+    long long iter = 0;
+    st.converged = 0;
     while (iter < a.maxIter) {
       double maxH = 0.0;
       iter += 1;
@@ -920,28 +937,64 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
       }
     }
     if (in_phase) phase_close(nact); // pass budget ran out inside a phase: back to the coordinate layout
-    if (a.prof && lane == 0) {
-      pc[5] = clock64() - tstart;
-      for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, (unsigned long long)pc[i]);
-      atomicAdd(a.prof + 7, (unsigned long long)wait_cyc);
-      atomicMax(a.prof + 6, (unsigned long long)pc[5]);
-    }
-    double *col = a.out + (long long)g * ep;
+    };
+
+    // A_g[S,S] x = rhs for the ms coordinates listed (ascending) in sact; rhs and the solution live in stmpd.
+    // Left-looking Cholesky in this warp's scratch (columns contiguous: coalesced; all loads of a column's update
+    // are independent), then the two triangular solves.  false: not positive definite.
+    auto spd_solve = [&](int ms) -> bool {
+      const int ldm = (ms + 1) & ~1;
+      double *rhs = stmpd, *lrow = sval; // lrow: L[j, 0..j) of the column being formed
+      bool ok = true;
+      for (int j = 0; j < ms; ++j) {
+        const int kj = sact[j];
+        for (int k2 = lane; k2 < j; k2 += 32) lrow[k2] = Gw[j + (long long)k2 * ldm];
+        __syncwarp();
+        double acc[NU];
 #pragma unroll
-    for (int u = 0; u < NU; ++u)
-      if (lane + 32 * u < ep) col[lane + 32 * u] = be[u];
-    if (lane == 0 && a.stats) a.stats[g] = st;
-    __syncwarp();
-    if (a.outR) {
-      // ---- refit (varying_coefficient_lasso.jl:71-76): A_g[S,S] x = -b_g[S] on the expanded coordinates S of every
-      // group with a non-zero coefficient (get_nonzero_coordinates!, :488-512).  Both sides come from the moment
-      // blocks; left-looking Cholesky in this warp's scratch (columns are contiguous: coalesced, and all loads of
-      // a column's update are independent), then the two triangular solves.
-      double *colR = a.outR + (long long)g * ep;
-      for (int k = lane; k < ep; k += 32) {
-        colR[k] = 0.0;
-        sin[k] = 0;
+        for (int u = 0; u < NU; ++u) {
+          const int i = j + lane + 32 * u;
+          acc[u] = i < ms ? moment(sact[i], kj) : 0.0;
+        }
+        for (int k2 = 0; k2 < j; ++k2) {
+          const double ljk = lrow[k2];
+          const double *ck = Gw + (long long)k2 * ldm + j + lane;
+#pragma unroll
+          for (int u = 0; u < NU; ++u)
+            if (j + lane + 32 * u < ms) acc[u] = fma(-__ldcg(ck + 32 * u), ljk, acc[u]);
+        }
+        const double djj = __shfl_sync(0xffffffffu, acc[0], 0);
+        if (!(djj > 0.0)) ok = false;
+        const double d = sqrt(djj);
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int i = j + lane + 32 * u;
+          if (i < ms) Gw[i + (long long)j * ldm] = i == j ? d : acc[u] / d;
+        }
+        __syncwarp();
       }
+      for (int j = 0; j < ms; ++j) { // L y = rhs (column sweep)
+        const double yj = rhs[j] / __ldcg(Gw + j + (long long)j * ldm);
+        __syncwarp();
+        if (lane == 0) rhs[j] = yj;
+        for (int i = j + 1 + lane; i < ms; i += 32) rhs[i] = fma(-__ldcg(Gw + i + (long long)j * ldm), yj, rhs[i]);
+        __syncwarp();
+      }
+      for (int j = ms - 1; j >= 0; --j) { // L' x = y (dot products)
+        double sacc = 0.0;
+        for (int i = j + 1 + lane; i < ms; i += 32) sacc = fma(__ldcg(Gw + i + (long long)j * ldm), rhs[i], sacc);
+        sacc = warp_sum(sacc);
+        const double xj = (rhs[j] - sacc) / __ldcg(Gw + j + (long long)j * ldm);
+        __syncwarp();
+        if (lane == 0) rhs[j] = xj;
+        __syncwarp();
+      }
+      return ok;
+    };
+    // the expanded coordinates of every group with a non-zero coefficient, ascending, into sact
+    // (get_nonzero_coordinates!(S, beta, p, degree, true), varying_coefficient_lasso.jl:488-512); returns |S|
+    auto selected_groups = [&]() -> int {
+      for (int k2 = lane; k2 < ep; k2 += 32) sin[k2] = 0;
       __syncwarp();
 #pragma unroll
       for (int u = 0; u < NU; ++u)
@@ -950,66 +1003,133 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
           for (int l = 0; l < dg; ++l) sin[j0 + l] = 1; // the whole group (same byte value from every writer)
         }
       __syncwarp();
-      int ms = 0; // ordered list S (ascending coordinates) in sact
+      int ms = 0;
       for (int k0 = 0; k0 < ep; k0 += 32) {
-        const int k = k0 + lane;
-        const bool inS = k < ep && sin[k] != 0;
+        const int k2 = k0 + lane;
+        const bool inS = k2 < ep && sin[k2] != 0;
         const unsigned bal = __ballot_sync(0xffffffffu, inS);
-        if (inS) sact[ms + __popc(bal & ((1u << lane) - 1u))] = k;
+        if (inS) sact[ms + __popc(bal & ((1u << lane) - 1u))] = k2;
         ms += __popc(bal);
       }
       __syncwarp();
-      if (ms > 0) {
-        const int ldm = (ms + 1) & ~1;
-        double *rhs = stmpd, *lrow = sval; // right-hand side / solution, L[j, 0..j) of the column being formed
-        for (int i = lane; i < ms; i += 32) rhs[i] = -scc[sact[i]];
-        bool ok = true;
-        for (int j = 0; j < ms; ++j) {
-          const int kj = sact[j];
-          // row j of L computed so far -> shared memory (uniform operands of the column update)
-          for (int k = lane; k < j; k += 32) lrow[k] = Gw[j + (long long)k * ldm];
-          __syncwarp();
-          double acc[NU];
+      return ms;
+    };
+
+    if constexpr (!LVO) {
+      run_solve();
+    } else {
+      // ---- one problem of lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): scaled-lasso sigma loop on the
+      // leave-one-out local problem, refit, prediction of the left-out response.  Everything about the residual
+      // comes from the moment blocks: r'Wr/n = y'Wy/n + 2 b'beta + beta'(A beta), sum(w)/n.
+      const double yWy = __ldg(Cg + a.P2 + a.p), Sw = __ldg(Cg + a.P2 + a.p + 1);
+      auto sigma_now = [&]() -> double { // _getSigma(w, f.r), utils.jl:167-175
+        double t = 0.0;
 #pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            const int i = j + lane + 32 * u;
-            acc[u] = i < ms ? moment(sact[i], kj) : 0.0;
-          }
-          for (int k = 0; k < j; ++k) {
-            const double ljk = lrow[k];
-            const double *ck = Gw + (long long)k * ldm + j + lane;
+        for (int u = 0; u < NU; ++u) t += be[u] * (2.0 * cc[u] + Ax[u]);
+        t = warp_sum(t);
+        return sqrt(fmax(yWy + t, 0.0) / Sw);
+      };
+      // _findInitResiduals!(w, wX, y, min(10, ep), f.r) (utils.jl:79-92): the s columns with the largest |X_k'Wy|,
+      // weighted least squares on them, sigma from those residuals
+      const int s_init = min(10, ep);
+      double thr = 0.0;
+      {
+        double cv[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) cv[u] = lane + 32 * u < ep ? fabs(cc[u]) : -1.0;
+        for (int r = 0; r < s_init; ++r) { // r-th largest by repeated arg-max
+          double best = -1.0;
+#pragma unroll
+          for (int u = 0; u < NU; ++u) best = fmax(best, cv[u]);
+          const double wbest = warp_max(best);
+          thr = wbest;
+          const unsigned bal = __ballot_sync(0xffffffffu, best == wbest);
+          if (lane == __ffs(bal) - 1) {
+            bool done = false;
 #pragma unroll
             for (int u = 0; u < NU; ++u)
-              if (j + lane + 32 * u < ms) acc[u] = fma(-__ldcg(ck + 32 * u), ljk, acc[u]);
+              if (!done && cv[u] == wbest) {
+                cv[u] = -1.0;
+                done = true;
+              }
           }
-          const double djj = __shfl_sync(0xffffffffu, acc[0], 0);
-          if (!(djj > 0.0)) ok = false; // not positive definite (collinear selected columns): NaN, as a SingularException
-          const double d = sqrt(djj);
+        }
+      }
+      int ms0 = 0;
+      for (int k0 = 0; k0 < ep; k0 += 32) { // S = storage .>= nlargest(s, storage)[end] (ties included)
+        const int k2 = k0 + lane;
+        const bool inS = k2 < ep && fabs(scc[k2]) >= thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, inS);
+        if (inS) sact[ms0 + __popc(bal & ((1u << lane) - 1u))] = k2;
+        ms0 += __popc(bal);
+      }
+      __syncwarp();
+      for (int i = lane; i < ms0; i += 32) stmpd[i] = -scc[sact[i]];
+      __syncwarp();
+      spd_solve(ms0);
+      double t0 = 0.0;
+      for (int i = lane; i < ms0; i += 32) t0 = fma(scc[sact[i]], stmpd[i], t0); // at the LS solution r'Wr/n = y'Wy/n + b_S'gamma
+      t0 = warp_sum(t0);
+      double sigma = sqrt(fmax(yWy + t0, 0.0) / Sw);
+      __syncwarp();
+      for (int outer = 1; outer <= 10; ++outer) { // :115-124
+        const double lam = a.lambda0 * sigma;
 #pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            const int i = j + lane + 32 * u;
-            if (i < ms) Gw[i + (long long)j * ldm] = i == j ? d : acc[u] / d;
+        for (int u = 0; u < NU; ++u)
+          if (lane + 32 * u < ep) {
+            th[u] = __dmul_rn(__dmul_rn(ai[u], lam), sqrt(1.0 / ai[u])); // lambda0 sigma omega_k / A_kk
+            sth[lane + 32 * u] = th[u];
           }
-          __syncwarp();
+        __syncwarp();
+        run_solve();
+        st.outer_iters = outer;
+        const double snew = sigma_now();
+        if (fabs(snew - sigma) / sigma < 1e-2) break;
+        sigma = snew;
+      }
+      st.sigma = sigma;
+    }
+    if (a.prof && lane == 0) {
+      pc[5] = clock64() - tstart;
+      for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, (unsigned long long)pc[i]);
+      atomicAdd(a.prof + 7, (unsigned long long)wait_cyc);
+      atomicMax(a.prof + 6, (unsigned long long)pc[5]);
+    }
+    if (a.out) {
+      double *col = a.out + (long long)g * ep;
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+        if (lane + 32 * u < ep) col[lane + 32 * u] = be[u];
+    }
+    if (lane == 0 && a.stats) a.stats[g] = st;
+    __syncwarp();
+    if (LVO || a.outR) {
+      // ---- refit (varying_coefficient_lasso.jl:71-76): A_g[S,S] x = -b_g[S] on the expanded coordinates S of every
+      // group with a non-zero coefficient; both sides come from the moment blocks
+      const int ms = selected_groups();
+      for (int i = lane; i < ms; i += 32) stmpd[i] = -scc[sact[i]];
+      __syncwarp();
+      const bool ok = ms > 0 ? spd_solve(ms) : true;
+      if (a.outR) {
+        double *colR = a.outR + (long long)g * ep;
+        for (int k2 = lane; k2 < ep; k2 += 32) colR[k2] = 0.0;
+        __syncwarp();
+        for (int i = lane; i < ms; i += 32) colR[sact[i]] = ok ? stmpd[i] : nan("");
+      }
+      if constexpr (LVO) {
+        // prediction of the left-out response (:129-131): z0 = z_i, so only the degree-0 columns of row i are
+        // non-zero: Yh = sum_{(j,0) in S} X[i,j] x_(j,0)
+        const int i_obs = g % a.n;
+        double yh = 0.0;
+        for (int i = lane; i < ms; i += 32) {
+          const int k2 = sact[i], j = k2 / dg;
+          if (k2 - j * dg == 0) yh = fma(__ldg(a.X + i_obs + (long long)j * a.ldx), stmpd[i], yh);
         }
-        // L y = rhs (column sweep), then L' x = y (dot products)
-        for (int j = 0; j < ms; ++j) {
-          const double yj = rhs[j] / __ldcg(Gw + j + (long long)j * ldm);
-          __syncwarp();
-          if (lane == 0) rhs[j] = yj;
-          for (int i = j + 1 + lane; i < ms; i += 32) rhs[i] = fma(-__ldcg(Gw + i + (long long)j * ldm), yj, rhs[i]);
-          __syncwarp();
+        yh = warp_sum(yh);
+        if (lane == 0) {
+          const double e = yh - __ldg(a.y + i_obs);
+          a.lvo_err[g] = ok ? e * e : nan("");
         }
-        for (int j = ms - 1; j >= 0; --j) {
-          double sacc = 0.0;
-          for (int i = j + 1 + lane; i < ms; i += 32) sacc = fma(__ldcg(Gw + i + (long long)j * ldm), rhs[i], sacc);
-          sacc = warp_sum(sacc);
-          const double xj = (rhs[j] - sacc) / __ldcg(Gw + j + (long long)j * ldm);
-          __syncwarp();
-          if (lane == 0) rhs[j] = xj;
-          __syncwarp();
-        }
-        for (int i = lane; i < ms; i += 32) colR[sact[i]] = ok ? rhs[i] : nan("");
       }
       __syncwarp();
     }
@@ -1022,8 +1142,10 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
 static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                            const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                            double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
-                           double *outR, cdgpu_stats *stats) {
-  const int64_t ep = p * (degree + 1), mloc = m_end - m_begin, P2 = p * (p + 1) / 2, PA = P2 + p;
+                           double *outR, cdgpu_stats *stats, const double *harr = nullptr, double *lvo_err = nullptr) {
+  // harr != null: the problems are those of lvocv_locpolyl1 (m = numH * n, zgrid unused, out/outR null, one squared
+  // prediction error per problem into lvo_err)
+  const int64_t ep = p * (degree + 1), mloc = m_end - m_begin, P2 = p * (p + 1) / 2, PA = P2 + p + 2;
   const int nq = 2 * degree + 1;
   const long long ldz = (n + 1) & ~(int64_t)1, ldc = (PA + 1) & ~(int64_t)1;
   int64_t chunk = (int64_t)((1ll << 30) / ((long long)ldc * nq * 8));
@@ -1033,7 +1155,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   cudaEvent_t e0 = nullptr, e1 = nullptr, eg = nullptr;
   double *dX = nullptr, *dz = nullptr, *dy = nullptr, *dgz = nullptr, *dout = nullptr, *dZ = nullptr, *dV = nullptr, *dC = nullptr;
   DevStats *dst = nullptr;
-  double *dG = nullptr, *doutR = nullptr;
+  double *dG = nullptr, *doutR = nullptr, *dharr = nullptr, *derr = nullptr;
   int *dcounter = nullptr;
   unsigned long long *dprof = nullptr;
   void *dtiles = nullptr;
@@ -1041,7 +1163,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   auto cleanup = [&]() {
     if (s) cudaStreamSynchronize(s);
     for (void *ptr : {(void *)dX, (void *)dz, (void *)dy, (void *)dgz, (void *)dout, (void *)dZ, (void *)dV, (void *)dC,
-                      (void *)dst, (void *)dcounter, (void *)dprof, (void *)dG, (void *)doutR, dtiles})
+                      (void *)dst, (void *)dcounter, (void *)dprof, (void *)dG, (void *)doutR, (void *)dharr, (void *)derr, dtiles})
       if (ptr) cudaFreeAsync(ptr, s);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
@@ -1068,8 +1190,14 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   VM_TRY(cudaMallocAsync((void **)&dX, (size_t)n * p * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dz, (size_t)n * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dy, (size_t)n * sizeof(double), s));
-  VM_TRY(cudaMallocAsync((void **)&dgz, (size_t)m * sizeof(double), s));
-  VM_TRY(cudaMallocAsync((void **)&dout, (size_t)ep * m * sizeof(double), s));
+  if (!harr) VM_TRY(cudaMallocAsync((void **)&dgz, (size_t)m * sizeof(double), s));
+  if (out) VM_TRY(cudaMallocAsync((void **)&dout, (size_t)ep * m * sizeof(double), s));
+  if (harr) {
+    const int64_t numH = m / n;
+    VM_TRY(cudaMallocAsync((void **)&dharr, (size_t)numH * sizeof(double), s));
+    VM_TRY(cudaMallocAsync((void **)&derr, (size_t)m * sizeof(double), s));
+    VM_TRY(cudaMemcpyAsync(dharr, harr, (size_t)numH * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
   VM_TRY(cudaMallocAsync((void **)&dst, (size_t)m * sizeof(DevStats), s));
   if (outR) VM_TRY(cudaMallocAsync((void **)&doutR, (size_t)ep * m * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dZ, (size_t)ldz * PA * sizeof(double), s));
@@ -1083,17 +1211,25 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   VM_TRY(cudaMemcpy2DAsync(dX, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), p, cudaMemcpyHostToDevice, s));
   VM_TRY(cudaMemcpyAsync(dz, z, n * sizeof(double), cudaMemcpyHostToDevice, s));
   VM_TRY(cudaMemcpyAsync(dy, y, n * sizeof(double), cudaMemcpyHostToDevice, s));
-  VM_TRY(cudaMemcpyAsync(dgz, zgrid, m * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (!harr) VM_TRY(cudaMemcpyAsync(dgz, zgrid, m * sizeof(double), cudaMemcpyHostToDevice, s));
   int sms = 0;
   VM_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int nu = (int)((ep + 31) / 32);
-  const void *kfn = nu <= 1   ? (const void *)vc_cov_kernel<1>
-                    : nu == 2 ? (const void *)vc_cov_kernel<2>
-                    : nu == 3 ? (const void *)vc_cov_kernel<3>
-                    : nu == 4 ? (const void *)vc_cov_kernel<4>
-                    : nu == 5 ? (const void *)vc_cov_kernel<5>
-                    : nu == 6 ? (const void *)vc_cov_kernel<6>
-                              : (const void *)vc_cov_kernel<8>;
+  const void *kfn_std = nu <= 1   ? (const void *)vc_cov_kernel<1, false>
+                        : nu == 2 ? (const void *)vc_cov_kernel<2, false>
+                        : nu == 3 ? (const void *)vc_cov_kernel<3, false>
+                        : nu == 4 ? (const void *)vc_cov_kernel<4, false>
+                        : nu == 5 ? (const void *)vc_cov_kernel<5, false>
+                        : nu == 6 ? (const void *)vc_cov_kernel<6, false>
+                                  : (const void *)vc_cov_kernel<8, false>;
+  const void *kfn_lvo = nu <= 1   ? (const void *)vc_cov_kernel<1, true>
+                        : nu == 2 ? (const void *)vc_cov_kernel<2, true>
+                        : nu == 3 ? (const void *)vc_cov_kernel<3, true>
+                        : nu == 4 ? (const void *)vc_cov_kernel<4, true>
+                        : nu == 5 ? (const void *)vc_cov_kernel<5, true>
+                        : nu == 6 ? (const void *)vc_cov_kernel<6, true>
+                                  : (const void *)vc_cov_kernel<8, true>;
+  const void *kfn = harr ? kfn_lvo : kfn_std;
   const size_t wsz = vc_cov_warp_bytes((int)ep);
   const size_t dyn = VCW * wsz;
   VM_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -1109,7 +1245,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   CD_COUNT_LAUNCH(1);
   for (int64_t c0 = m_begin; c0 < m_end; c0 += chunk) {
     const int64_t c1 = std::min<int64_t>(m_end, c0 + chunk), mc = c1 - c0;
-    vc_build_v_kernel<<<(unsigned)mc, 128, 0, s>>>(dz, dgz, (int)n, (int)c0, (int)c1, nq, kernel_kind, bandwidth, dV, ldz);
+    vc_build_v_kernel<<<(unsigned)mc, 128, 0, s>>>(dz, dgz, (int)n, (int)c0, (int)c1, nq, kernel_kind, bandwidth, dV, ldz, dharr);
     VM_TRY(cudaGetLastError());
     if (dtiles) {
       VM_TRY(cudaFreeAsync(dtiles, s));
@@ -1140,6 +1276,12 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
     a.outR = doutR;
     a.stats = dst;
     a.counter = dcounter;
+    a.lvo = harr ? 1 : 0;
+    a.n = (int)n;
+    a.X = dX;
+    a.y = dy;
+    a.ldx = n;
+    a.lvo_err = derr;
     a.prof = dprof;
     a.gscr = dG;
     a.dbg = getenv("CDGPU_VC_DBG") ? atoi(getenv("CDGPU_VC_DBG")) : 0;
@@ -1149,7 +1291,10 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
     CD_COUNT_LAUNCH(2);
   }
   VM_TRY(cudaEventRecord(e1, s));
-  VM_TRY(cudaMemcpyAsync(out + m_begin * ep, dout + m_begin * ep, (size_t)mloc * ep * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (out)
+    VM_TRY(cudaMemcpyAsync(out + m_begin * ep, dout + m_begin * ep, (size_t)mloc * ep * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (lvo_err)
+    VM_TRY(cudaMemcpyAsync(lvo_err + m_begin, derr + m_begin, (size_t)mloc * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (outR)
     VM_TRY(cudaMemcpyAsync(outR + m_begin * ep, doutR + m_begin * ep, (size_t)mloc * ep * sizeof(double), cudaMemcpyDeviceToHost, s));
   VM_TRY(cudaStreamSynchronize(s));
@@ -1179,8 +1324,8 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
       o->accepted = hst[g].accepted;
       o->maxH = hst[g].maxH;
       o->converged = hst[g].converged;
-      o->outer_iters = 0;
-      o->sigma = 0.0;
+      o->outer_iters = hst[g].outer_iters;
+      o->sigma = hst[g].sigma;
       o->device_ms = g == 0 ? (double)ms : 0.0;
     }
   }
@@ -1193,6 +1338,33 @@ static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, con
                          const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                          double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out, double *outR,
                          cdgpu_stats *stats);
+// lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): numH * n leave-one-out local scaled-lasso problems, all in
+// one batch; problems [q_begin, q_end) of the (bandwidth-major) list are solved (sharding hook), MSE[h] is summed on
+// the host in observation order from the per-problem squared errors.
+API int cdgpu_vc_lvocv(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y, int degree,
+                       const double *hArr, int64_t numH, int kernel_kind, double lambda0, const cdgpu_options *opt,
+                       int64_t q_begin, int64_t q_end, int device, double *sqerr, cdgpu_stats *stats) {
+  if (!X || !z || !y || !hArr || !opt || !sqerr) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  const int64_t m = numH * n;
+  if (n < 2 || p < 1 || ldx < n || degree < 0 || numH < 0 || q_begin < 0 || q_end > m || q_begin > q_end)
+    return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (kernel_kind != CDGPU_KERNEL_GAUSSIAN && kernel_kind != CDGPU_KERNEL_EPANECHNIKOV)
+    return cdgpu_set_error(CDGPU_EARG, "unknown smoothing kernel");
+  if (opt->maxIter < 0 || opt->randomize < 0 || opt->randomize > 1) return cdgpu_set_error(CDGPU_EARG, "bad options");
+  const int64_t ep = p * (degree + 1);
+  if (n > 0x7fffffff || ep > 0x7fffffff || m > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "sizes must fit in 31 bits");
+  if (ep > 256) return cdgpu_set_error(CDGPU_ECAP, "lvocv needs the moment form: p*(degree+1) = %lld exceeds 256", (long long)ep);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return cdgpu_set_error(CDGPU_ENODEV, "no CUDA device (%s); libcdgpu has no CPU fallback",
+                           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return cdgpu_set_error(CDGPU_EARG, "device out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  if (q_begin == q_end) return CDGPU_OK;
+  return vc_solve_moment(X, n, p, ldx, z, y, nullptr, m, q_begin, q_end, degree, kernel_kind, 0.0, lambda0, opt, device, nullptr,
+                         nullptr, stats, hArr, sqerr);
+}
 API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                        const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                        double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,

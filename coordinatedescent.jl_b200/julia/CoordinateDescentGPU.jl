@@ -294,4 +294,18 @@ function locpolyl1(X::Matrix{Float64}, z::Vector{Float64}, y::Vector{Float64}, z
     sparse(out), sparse(outR)
 end
 
+# lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): every (bandwidth, left-out observation) pair is one local
+# scaled-lasso problem of a single batched call; MSE[indH] is the sum of the squared prediction errors over i
+function lvocv_locpolyl1(X::Matrix{Float64}, z::Vector{Float64}, y::Vector{Float64}, degree::Int64, hArr::Vector{Float64},
+                         kernelType::Type{<:SmoothingKernel}, λ0::Float64, options::CDOptions=CDOptions(); device::Integer=0)
+    n, p = size(X); numH = length(hArr)
+    sqerr = zeros(Float64, n * numH)
+    kind = kernel_kind(createKernel(kernelType{Float64}, 1.0))
+    GC.@preserve X z y hArr sqerr check(ccall((:cdgpu_vc_lvocv, libcdgpu), Cint,
+        (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Int64, Cint, Float64,
+         Ref{cdgpu_options}, Int64, Int64, Cint, Ptr{Float64}, Ptr{Cvoid}),
+        X, n, p, n, z, y, degree, hArr, numH, kind, λ0, Ref(c_opts(options)), 0, n * numH, device, sqerr, C_NULL))
+    vec(sum(reshape(sqerr, n, numH), dims=1))
+end
+
 end # module

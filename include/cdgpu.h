@@ -213,6 +213,17 @@ int cdgpu_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx, con
                          double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
                          double *outR, cdgpu_stats *stats);
 
+/* lvocv_locpolyl1(X, z, y, degree, hArr, kernelType, lambda0, options) (varying_coefficient_lasso.jl:81-137):
+ * leave-one-out choice of the bandwidth.  For every bandwidth hArr[ih] and observation i: the local problem at
+ * z0 = z_i with w_i = 0, sigma initialised by screening (utils.jl:79-92), <= 10 rounds of CD at lambda0*sigma with
+ * sigma re-estimated on the device between rounds (:112-124), refit on the selected groups and the squared error of
+ * the prediction of y_i (:127-131).  All numH*n problems are independent units of one batch (one warp each); the
+ * reference's warm start from the previous observation (:99) is cut.  sqerr[q], q = ih*n + i, is written for
+ * q in [q_begin, q_end) (sharding hook); MSE[ih] = sum_i sqerr[ih*n + i].  stats: numH*n entries or NULL. */
+int cdgpu_vc_lvocv(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y, int degree,
+                   const double *hArr, int64_t numH, int kernel_kind, double lambda0, const cdgpu_options *opt,
+                   int64_t q_begin, int64_t q_end, int device, double *sqerr, cdgpu_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

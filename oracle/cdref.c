@@ -920,7 +920,7 @@ API int cdref_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx,
     return fail(CDGPU_EARG, "unknown kernel");
   const int64_t ep = p * (degree + 1);
   double *w = (double *)malloc((size_t)n * sizeof(double));
-  double *eX = (double *)malloc((size_t)(n * ep) * sizeof(double));
+  double *eX = (double *)calloc((size_t)(n * ep), sizeof(double));
   double *sd = (double *)malloc((size_t)ep * sizeof(double));
   if (!w || !eX || !sd) return fail(CDGPU_ENOMEM, "out of memory");
   cdgpu_handle f;
@@ -993,6 +993,134 @@ API int cdref_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
                        cdgpu_stats *stats) {
   return cdref_vc_solve_refit(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt,
                               device, out, NULL, stats);
+}
+
+/* lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): for every bandwidth and every observation i the
+ * leave-one-out local problem at z0 = z_i (w_i = 0), sigma initialised from the residuals of a weighted LS on the
+ * min(10, ep) most correlated columns (utils.jl:79-92, 107-122), <= 10 rounds of CD at lambda0*sigma with
+ * sigma = _getSigma(w, r) until it moves by < 1e-2 (:112-124), refit on the selected groups and the squared error
+ * of the prediction of y_i (:127-131).  sqerr[q] for problem q = ih * n + i, q in [q_begin, q_end); the caller sums
+ * MSE[ih] over i.  opt->warmStart != 0: beta is carried from problem to problem as in the reference (:99,:116);
+ * opt->warmStart == 0: every problem starts from beta = 0 (what the batched device path does). */
+API int cdref_vc_lvocv(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y, int degree,
+                       const double *hArr, int64_t numH, int kernel_kind, double lambda0, const cdgpu_options *opt,
+                       int64_t q_begin, int64_t q_end, int device, double *sqerr, cdgpu_stats *stats) {
+  (void)device;
+  if (!X || !z || !y || !hArr || !opt || !sqerr) return fail(CDGPU_EARG, "null pointer");
+  const int64_t m = numH * n;
+  if (n < 2 || p < 1 || ldx < n || degree < 0 || numH < 0 || q_begin < 0 || q_end > m || q_begin > q_end)
+    return fail(CDGPU_EDIM, "DimensionMismatch");
+  if (kernel_kind != CDGPU_KERNEL_GAUSSIAN && kernel_kind != CDGPU_KERNEL_EPANECHNIKOV)
+    return fail(CDGPU_EARG, "unknown kernel");
+  const int64_t ep = p * (degree + 1), dgp = degree + 1;
+  double *w = (double *)malloc((size_t)n * sizeof(double));
+  double *eX = (double *)calloc((size_t)(n * ep), sizeof(double));
+  double *sd = (double *)malloc((size_t)ep * sizeof(double)), *cor = (double *)malloc((size_t)ep * sizeof(double));
+  double *srt = (double *)malloc((size_t)ep * sizeof(double)), *M = (double *)malloc((size_t)(ep * ep) * sizeof(double));
+  double *rhs = (double *)malloc((size_t)ep * sizeof(double)), *beta = (double *)malloc((size_t)ep * sizeof(double));
+  int64_t *S = (int64_t *)malloc((size_t)ep * sizeof(int64_t));
+  if (!w || !eX || !sd || !cor || !srt || !M || !rhs || !beta || !S) return fail(CDGPU_ENOMEM, "out of memory");
+  for (int64_t i = 0; i < n; ++i) w[i] = 1.0;
+  cdgpu_handle f;
+  int rc = cdref_naive_create(&f, CDGPU_LOSS_WLS, eX, n, ep, n, y, w, 0);
+  if (rc) return rc;
+  cdgpu_options o = *opt;
+  o.warmStart = 1; /* :92 */
+  if (o.randomize == 2) xo_seed(o.seed);
+  si_fill_zero(&f->x);
+  /* weighted normal equations on the ns columns S of eX: solution into rhs; returns 1 when singular */
+#define NORMAL_EQ_SOLVE(ns)                                              \
+  do {                                                                   \
+    for (int64_t a_ = 0; a_ < (ns); ++a_) {                              \
+      const double *ca = eX + S[a_] * n;                                 \
+      double r_ = 0.0;                                                   \
+      for (int64_t i_ = 0; i_ < n; ++i_) r_ += ca[i_] * w[i_] * y[i_];   \
+      rhs[a_] = r_;                                                      \
+      for (int64_t b_ = 0; b_ < (ns); ++b_) {                            \
+        const double *cb = eX + S[b_] * n;                               \
+        double v_ = 0.0;                                                 \
+        for (int64_t i_ = 0; i_ < n; ++i_) v_ += ca[i_] * w[i_] * cb[i_]; \
+        M[a_ + b_ * (ns)] = v_;                                          \
+      }                                                                  \
+    }                                                                    \
+    singular = lu_solve(M, rhs, (ns));                                   \
+  } while (0)
+  for (int64_t q = q_begin; q < q_end; ++q) {
+    const int64_t ih = q / n, io = q % n;
+    const double z0 = z[io], bw = hArr[ih];
+    cdgpu_stats st;
+    memset(&st, 0, sizeof st);
+    double t0 = now_ms();
+    int singular = 0;
+    if (!opt->warmStart) si_fill_zero(&f->x);
+    for (int64_t i = 0; i < n; ++i) w[i] = cdref_kernel_evaluate(kernel_kind, bw, z[i], z0);
+    w[io] = 0.0; /* :108 */
+    cdref_expand_X(eX, X, n, p, ldx, z, z0, degree);
+    stdx(eX, n, ep, n, w, sd);
+    /* _findLargestCorrelations(w, X, y, s), utils.jl:107-122: S = storage .>= nlargest(s, storage)[end] */
+    const int64_t s_init = ep < 10 ? ep : 10;
+    for (int64_t k = 0; k < ep; ++k) {
+      const double *ck = eX + k * n;
+      double v = 0.0;
+      for (int64_t i = 0; i < n; ++i) v += ck[i] * w[i] * y[i];
+      cor[k] = srt[k] = fabs(v);
+    }
+    for (int64_t a_ = 0; a_ < s_init; ++a_) { /* partial selection sort, descending */
+      int64_t best = a_;
+      for (int64_t b_ = a_ + 1; b_ < ep; ++b_)
+        if (srt[b_] > srt[best]) best = b_;
+      double t = srt[a_];
+      srt[a_] = srt[best];
+      srt[best] = t;
+    }
+    int64_t ns = 0;
+    for (int64_t k = 0; k < ep; ++k)
+      if (cor[k] >= srt[s_init - 1]) S[ns++] = k;
+    NORMAL_EQ_SOLVE(ns);
+    double swr = 0.0, sw = 0.0;
+    for (int64_t i = 0; i < n; ++i) { /* residuals of that fit, _getSigma (utils.jl:167-175) */
+      double fit = 0.0;
+      for (int64_t a_ = 0; a_ < ns; ++a_) fit += eX[i + S[a_] * n] * rhs[a_];
+      const double r = y[i] - fit;
+      swr += r * r * w[i];
+      sw += w[i];
+    }
+    double sigma = sqrt(swr / sw);
+    for (int outer = 1; outer <= 10; ++outer) { /* :114-124 */
+      prox_l1 pen = {lambda0 * sigma, sd};
+      f->pass_counter = 0;
+      coordinate_descent(f, &pen, &f->x, &o, &st);
+      st.outer_iters = outer;
+      swr = 0.0;
+      for (int64_t i = 0; i < n; ++i) swr += f->state[i] * f->state[i] * w[i];
+      const double snew = sqrt(swr / sw);
+      if (fabs(snew - sigma) / sigma < 1e-2) break;
+      sigma = snew;
+    }
+    st.sigma = sigma;
+    /* refit on the selected groups and prediction of the left-out response, :127-131 */
+    for (int64_t k = 0; k < ep; ++k) beta[k] = 0.0;
+    for (int64_t s_ = 0; s_ < f->x.nnz; ++s_) beta[f->x.nzval2ind[s_] - 1] = f->x.nzval[s_];
+    ns = 0;
+    for (int64_t j = 0; j < p; ++j) {
+      int nz = 0;
+      for (int64_t k = j * dgp; k < (j + 1) * dgp; ++k) nz |= beta[k] != 0.0;
+      if (nz)
+        for (int64_t k = j * dgp; k < (j + 1) * dgp; ++k) S[ns++] = k;
+    }
+    double yh = 0.0;
+    if (ns > 0) {
+      NORMAL_EQ_SOLVE(ns);
+      for (int64_t a_ = 0; a_ < ns; ++a_) yh += eX[io + S[a_] * n] * rhs[a_];
+    }
+    sqerr[q] = singular ? NAN : (yh - y[io]) * (yh - y[io]);
+    st.device_ms = now_ms() - t0;
+    if (stats) stats[q] = st;
+  }
+#undef NORMAL_EQ_SOLVE
+  cdref_destroy(f);
+  free(w); free(eX); free(sd); free(cor); free(srt); free(M); free(rhs); free(beta); free(S);
+  return CDGPU_OK;
 }
 
 /* ---------------------------------------------------------------------- */

@@ -342,6 +342,31 @@ def test_refit_next_tier(gpu, ref):
     assert np.array_equal(ogR != 0, orR != 0) and np.allclose(ogR, orR, rtol=1e-7, atol=1e-10)
 
 
+@pytest.mark.parametrize("kernel_type,degree", [(GaussianKernel, 1), (EpanechnikovKernel, 0), (GaussianKernel, 2)])
+def test_lvocv_locpolyl1_parity(gpu, ref, kernel_type, degree):
+    """lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): numH*n leave-one-out scaled-lasso local problems as one
+    batch; per-problem sigma, outer iterations and squared prediction errors against the oracle (chain cut on both)."""
+    rng = np.random.default_rng(95)
+    n, p = 90, 7
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    Y = X[:, 0] * np.sin(3 * Z) + X[:, 1] * np.cos(2 * Z) + 0.2 * rng.standard_normal(n)
+    h = np.array([0.2, 0.5]) if kernel_type is EpanechnikovKernel else np.array([0.05, 0.2])
+    o = CDOptions(randomize=False, warmStart=False, **TIGHT)
+    mg = gpu.lvocv_locpolyl1(X, Z, Y, degree, h, kernel_type, 0.3, o)
+    sg, stg = gpu.last_lvocv_sqerr.copy(), gpu.last_vc_stats
+    mr = ref.lvocv_locpolyl1(X, Z, Y, degree, h, kernel_type, 0.3, o)
+    sr, str_ = ref.last_lvocv_sqerr.copy(), ref.last_vc_stats
+    assert [s["outer_iters"] for s in stg] == [s["outer_iters"] for s in str_]
+    assert np.allclose([s["sigma"] for s in stg], [s["sigma"] for s in str_], rtol=1e-8)
+    assert np.allclose(sg, sr, rtol=1e-6, atol=1e-12) and np.allclose(mg, mr, rtol=1e-8)
+    # sharding hook: two halves of the problem list add up to the whole
+    m = h.size * n
+    a = gpu.lvocv_locpolyl1(X, Z, Y, degree, h, kernel_type, 0.3, o, shard=(0, m // 3))
+    b = gpu.lvocv_locpolyl1(X, Z, Y, degree, h, kernel_type, 0.3, o, shard=(m // 3, m))
+    assert np.allclose(a + b, mg, rtol=1e-12)
+
+
 def test_errors_match_reference(gpu):
     X, y, _ = gauss_problem(20, 5, 2, seed=16)
     f = gpu.CDLeastSquaresLoss(y, X)

@@ -225,3 +225,22 @@ def test_locpolyl1_matches_alt_formulation(ref):
         alt = ref.lasso(np.asfortranarray(sw[:, None] * eX), sw * Y, 0.05, sd, o)
         assert np.allclose(out[:, gi], alt.x.toarray(), atol=1e-8)
     assert np.count_nonzero(out) > 0
+
+
+def test_lvocv_oracle_prefers_the_true_bandwidth_and_chain_cut_agree(ref):
+    """lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137) in the oracle: the warm-start chain across observations
+    (reference) and independent problems (what the device batches) give the same leave-one-out MSE, and an absurdly
+    wide bandwidth loses against a reasonable one on a strongly varying coefficient."""
+    import cdgpu
+    from cdgpu import CDOptions, GaussianKernel
+    rng = np.random.default_rng(96)
+    n, p = 80, 5
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    Y = X[:, 0] * np.sin(6 * Z) + 0.1 * rng.standard_normal(n)
+    h = np.array([0.02, 5.0])
+    o = dict(randomize=False, maxIter=20000, optTol=1e-10)
+    chain = ref.lvocv_locpolyl1(X, Z, Y, 1, h, GaussianKernel, 0.2, CDOptions(warmStart=True, **o))
+    cut = ref.lvocv_locpolyl1(X, Z, Y, 1, h, GaussianKernel, 0.2, CDOptions(warmStart=False, **o))
+    assert np.allclose(chain, cut, rtol=1e-3)
+    assert cut[0] < 0.5 * cut[1]
