@@ -79,7 +79,7 @@ struct Trace {
 
 // --------------------------------------------------------------- handles --
 static int pool_init(int device);
-static int use_device(int device) {
+int cd_use_device(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
@@ -119,15 +119,11 @@ static void dfree(void *p) {
 // Streams and events come from a per-device free list: cudaStreamCreate / cudaEventCreate go through
 // the resource manager and were seen to stall for up to 300 ms when an NVML client (nvidia-smi, a
 // clock sampler) polls the same device, so a handle takes a recycled set and returns it on destroy.
-struct StreamSet {
-  cudaStream_t stream;
-  cudaEvent_t ev0, ev1;
-};
 static std::mutex g_res_mu;
 static std::vector<StreamSet> g_free_sets[64];
 static int g_sm_count[64] = {0};
 
-static int stream_set_acquire(int device, StreamSet *out) {
+int stream_set_acquire(int device, StreamSet *out) {
   {
     std::lock_guard<std::mutex> lk(g_res_mu);
     if (device < 64 && !g_free_sets[device].empty()) {
@@ -141,7 +137,7 @@ static int stream_set_acquire(int device, StreamSet *out) {
   CUDA_TRY(cudaEventCreate(&out->ev1));
   return CDGPU_OK;
 }
-static void stream_set_release(int device, const StreamSet &s) {
+void stream_set_release(int device, const StreamSet &s) {
   std::lock_guard<std::mutex> lk(g_res_mu);
   if (device < 64 && g_free_sets[device].size() < 16) {
     g_free_sets[device].push_back(s);
@@ -261,7 +257,7 @@ static int naive_check(cdgpu_handle *out, int loss_kind, const void *X, int64_t 
 API int cdgpu_naive_create(cdgpu_handle *out, int loss_kind, const double *X, int64_t n, int64_t p, int64_t ldx,
                            const double *y, const double *w, int device) {
   CD_TRY(naive_check(out, loss_kind, X, n, p, ldx, y, w));
-  CD_TRY(use_device(device));
+  CD_TRY(cd_use_device(device));
   HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
   cdgpu_handle_s *h = g.h;
   if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
@@ -292,7 +288,7 @@ API int cdgpu_naive_create(cdgpu_handle *out, int loss_kind, const double *X, in
 API int cdgpu_naive_create_dev(cdgpu_handle *out, int loss_kind, const double *dX, int64_t n, int64_t p, int64_t ldx,
                                const double *dy, const double *dw, int device) {
   CD_TRY(naive_check(out, loss_kind, dX, n, p, ldx, dy, dw));
-  CD_TRY(use_device(device));
+  CD_TRY(cd_use_device(device));
   HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
   cdgpu_handle_s *h = g.h;
   if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
@@ -332,7 +328,7 @@ API int cdgpu_quad_create(cdgpu_handle *out, const double *A, int64_t p, int64_t
   if (!out || !A || !b) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (p < 1 || lda < p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
-  CD_TRY(use_device(device));
+  CD_TRY(cd_use_device(device));
   HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
   cdgpu_handle_s *h = g.h;
   if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
@@ -360,7 +356,7 @@ API int cdgpu_quad_create_dev(cdgpu_handle *out, const double *dA, int64_t p, in
   if (!out || !dA || !db) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (p < 1 || lda < p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
-  CD_TRY(use_device(device));
+  CD_TRY(cd_use_device(device));
   HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
   cdgpu_handle_s *h = g.h;
   if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
@@ -429,7 +425,7 @@ API int cdgpu_gram_create_dev(cdgpu_handle *out, const double *dX, int64_t n, in
   if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
   Trace tr;
-  CD_TRY(use_device(device));
+  CD_TRY(cd_use_device(device));
   CUDA_TRY(cudaDeviceSynchronize());
   tr.mark("use_device + device sync");
   return gram_build(out, dX, n, n, p, ldx, dy, device, nullptr, nullptr);
@@ -440,7 +436,7 @@ API int cdgpu_gram_create_sharded(cdgpu_handle *out, const double *dX_local, int
   if (!out || !dX_local || !dy_local) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (n_local < 1 || n_total < n_local || p < 1 || ldx < n_local) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
-  CD_TRY(use_device(device));
+  CD_TRY(cd_use_device(device));
   CUDA_TRY(cudaDeviceSynchronize());
   return gram_build(out, dX_local, n_local, n_total, p, ldx, dy_local, device, comm, nullptr);
 }
@@ -450,7 +446,7 @@ API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t
   if (!out || !X || !y) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
-  CD_TRY(use_device(device));
+  CD_TRY(cd_use_device(device));
   // Host X: the rows are staged in chunks on a copy stream while the SYRK of the previous chunk runs
   // (G accumulates over row chunks, then one scale pass), so the H2D transfer hides behind the DMMA
   // work when the host memory is pinned.  The staging copy is dropped afterwards.

@@ -243,6 +243,15 @@ struct cdgpu_handle_s {
   int sm_count = 0, max_cluster = 0;
 };
 
+// device selection (+ memory-pool release threshold) and the per-device free list of stream/event sets (api.cu)
+int cd_use_device(int device);
+struct StreamSet {
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+};
+int stream_set_acquire(int device, StreamSet *out);
+void stream_set_release(int device, const StreamSet &s);
+
 // ------------------------------------------------------------- launchers --
 struct CovArgs {
   const double *A;

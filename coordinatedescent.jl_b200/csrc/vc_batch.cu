@@ -1165,12 +1165,10 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
     for (void *ptr : {(void *)dX, (void *)dz, (void *)dy, (void *)dgz, (void *)dout, (void *)dZ, (void *)dV, (void *)dC,
                       (void *)dst, (void *)dcounter, (void *)dprof, (void *)dG, (void *)doutR, (void *)dharr, (void *)derr, dtiles})
       if (ptr) cudaFreeAsync(ptr, s);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
     if (eg) cudaEventDestroy(eg);
     if (s) {
       cudaStreamSynchronize(s);
-      cudaStreamDestroy(s);
+      stream_set_release(device, StreamSet{s, e0, e1});
     }
   };
 #define VM_TRY(expr)                                                                                        \
@@ -1183,10 +1181,15 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
       return rc;                                                                                            \
     }                                                                                                       \
   } while (0)
-  VM_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  VM_TRY(cudaEventCreate(&e0));
-  VM_TRY(cudaEventCreate(&e1));
-  VM_TRY(cudaEventCreate(&eg));
+  {
+    StreamSet ss;
+    rc = stream_set_acquire(device, &ss); // recycled: creating streams/events goes through the resource manager
+    if (rc) return rc;
+    s = ss.stream;
+    e0 = ss.ev0;
+    e1 = ss.ev1;
+  }
+  VM_TRY(cudaEventCreateWithFlags(&eg, cudaEventDefault));
   VM_TRY(cudaMallocAsync((void **)&dX, (size_t)n * p * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dz, (size_t)n * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dy, (size_t)n * sizeof(double), s));
@@ -1360,7 +1363,7 @@ API int cdgpu_vc_lvocv(const double *X, int64_t n, int64_t p, int64_t ldx, const
     return cdgpu_set_error(CDGPU_ENODEV, "no CUDA device (%s); libcdgpu has no CPU fallback",
                            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return cdgpu_set_error(CDGPU_EARG, "device out of range");
-  CUDA_TRY(cudaSetDevice(device));
+  CD_TRY(cd_use_device(device));
   if (q_begin == q_end) return CDGPU_OK;
   return vc_solve_moment(X, n, p, ldx, z, y, nullptr, m, q_begin, q_end, degree, kernel_kind, 0.0, lambda0, opt, device, nullptr,
                          nullptr, stats, hArr, sqerr);
@@ -1398,7 +1401,7 @@ static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, con
     return cdgpu_set_error(CDGPU_ENODEV, "no CUDA device (%s); libcdgpu has no CPU fallback",
                            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return cdgpu_set_error(CDGPU_EARG, "device out of range");
-  CUDA_TRY(cudaSetDevice(device));
+  CD_TRY(cd_use_device(device));
   const int64_t mloc = m_end - m_begin;
   if (mloc == 0) return CDGPU_OK;
   {
