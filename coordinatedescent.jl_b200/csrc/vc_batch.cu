@@ -672,9 +672,20 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
         sAxE[i] = sAx[k]; // (A x) of the active entries, by snapshot entry, carried from pass to pass
       }
       __syncwarp();
-      for (int j = 0; j < m; ++j) {
-        const int kj = sact0[j];
-        for (int i = lane; i < m; i += 32) Gw[i + (long long)j * ldw] = moment(sact0[i], kj);
+      // compact Gram: 4 columns per iteration so that 4 * ceil(m/32) independent gathers are in flight per lane
+      for (int j = 0; j < m; j += 4) {
+        int kj[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kj[c] = sact0[min(j + c, m - 1)];
+        for (int i = lane; i < m; i += 32) {
+          const int ki = sact0[i];
+          double v[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = moment(ki, kj[c]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (j + c < m) Gw[i + (long long)(j + c) * ldw] = v[c];
+        }
       }
       __syncwarp();
       in_phase = true;
@@ -706,18 +717,24 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
           th[u] = sth[t];
         }
       }
-      for (int e = 0; e < m0; ++e) {
-        const int k = sact0[e];
-        const double dlt = stmpd[k] - sbeta[k];
-        if (dlt == 0.0) continue;
-        const int kj = k / dg, kl = k - kj * dg, ktri = kj * (kj + 1) / 2;
+      for (int e0 = 0; e0 < m0; e0 += 2) { // two entries per iteration: twice the loads in flight
+        double gv[2][NU], dl[2];
 #pragma unroll
-        for (int u = 0; u < NU; ++u) {
-          if (inactive[u]) {
+        for (int c = 0; c < 2; ++c) {
+          const int k = sact0[min(e0 + c, m0 - 1)];
+          dl[c] = e0 + c < m0 ? stmpd[k] - sbeta[k] : 0.0;
+          const int kj = k / dg, kl = k - kj * dg, ktri = kj * (kj + 1) / 2;
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
             const int pk_ = kj >= tj[u] ? ktri + tj[u] : ttri[u] + kj;
-            Ax[u] = fma(__ldg(Cg + (long long)(kl + tl[u]) * a.ldc + pk_), dlt, Ax[u]);
+            gv[c][u] = inactive[u] && dl[c] != 0.0 ? __ldg(Cg + (long long)(kl + tl[u]) * a.ldc + pk_) : 0.0;
           }
         }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int u = 0; u < NU; ++u)
+            if (inactive[u]) Ax[u] = fma(gv[c][u], dl[c], Ax[u]);
       }
       __syncwarp();
       in_phase = false;
