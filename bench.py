@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-p", type=int, default=REF_SAMPLE_P)
     ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 side measurements")
+    ap.add_argument("--other-configs", default="", help="comma list of c1,c3,c4,lvocv: run benchmarks/other_configs.py instead")
+    ap.add_argument("--other-cpu", action="store_true", help="with --other-configs: add the CPU-port columns (cpu_baseline leg)")
     return ap.parse_args()
 
 
@@ -249,6 +251,18 @@ def main():
     base = {"metric": "coordinate_updates_per_sec", "unit": "visits/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic"}
+
+    # ------------------------------------------------------------------ the other BASELINE configs (one JSON line each)
+    if args.other_configs:
+        import cdgpu
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        import other_configs
+        ref = None
+        if args.other_cpu:  # cpu_baseline leg: the only place outside tests/ and smoke() that executes oracle/
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+            ref = cdgpu.Backend(cdgpu.Lib(os.path.join(ROOT, "oracle", "libcdref_fast.so"), "cdref"))
+        other_configs.main(args.other_configs.split(","), ref)
+        return
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":

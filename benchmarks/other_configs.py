@@ -2,8 +2,10 @@
 """Measurements of the BASELINE.json configs that are not the headline bench line:
 C1 (lasso n=1000 p=5000), C3 (sqrt-/scaled-lasso n=5000 p=50000, naive form), C4 (4096 local
 varying-coefficient problems).  Prints one JSON object per config.  GPU timings are the library's
-CUDA-event device_ms; the CPU column is the oracle port (-O3, 1 thread, literal reference loops).
-Usage: python benchmarks/other_configs.py [c1] [c3] [c4] [lvocv] [--no-cpu]
+CUDA-event device_ms; the CPU columns (only through bench.py's cpu_baseline leg) are the oracle port
+(-O3, 1 thread, literal reference loops).
+Usage: python benchmarks/other_configs.py [c1] [c3] [c4] [lvocv]            (GPU columns only)
+       python bench.py --other-configs c1,c3,c4,lvocv [--other-cpu]         (adds the CPU-port columns)
 """
 import json
 import math
@@ -69,11 +71,12 @@ def compare(xg, xr):
     return bool(np.array_equal(a != 0, b != 0)), float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
-def main():
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c3", "c4", "lvocv"]
-    cpu_on = "--no-cpu" not in sys.argv
+def main(which=None, ref=None):
+    """`ref`: a Backend bound to the CPU port, handed in by bench.py's cpu_baseline leg (`bench.py --other-configs ...
+    --other-cpu`); this script itself never loads anything from oracle/ — run directly it measures the GPU only."""
+    which = which or [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c3", "c4", "lvocv"]
+    cpu_on = ref is not None
     gpu = cdgpu.default()
-    ref = cdgpu.Backend(cdgpu.Lib(os.path.join(ROOT, "oracle", "libcdref_fast.so"), "cdref")) if cpu_on else None
     opt = CDOptions(randomize=False)  # defaults: optTol 1e-7, maxIter 2000
 
     if "c1" in which:
