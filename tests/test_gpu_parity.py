@@ -367,6 +367,19 @@ def test_lvocv_locpolyl1_parity(gpu, ref, kernel_type, degree):
     assert np.allclose(a + b, mg, rtol=1e-12)
 
 
+@pytest.mark.parametrize("n", [20000, 26000])
+def test_tall_naive_problem_shrinks_or_disables_the_active_engine(gpu, ref, n):
+    """r lives in shared memory, so the covariance-form active engine gets less room as n grows (capacity 1024 at
+    n = 20000) and is switched off near the limit (n = 26000: CTA 0 runs active passes column by column)."""
+    p, s = 48, 6
+    X, y, _ = gauss_problem(n, p, s, seed=97)
+    o = CDOptions(randomize=False, **TIGHT)
+    xg = gpu.lasso(X, y, 0.004, None, o).x.toarray()
+    xr = ref.lasso(X, y, 0.004, None, o).x.toarray()
+    assert np.count_nonzero(xr) >= 8
+    assert_parity(xg, xr)
+
+
 def test_errors_match_reference(gpu):
     X, y, _ = gauss_problem(20, 5, 2, seed=16)
     f = gpu.CDLeastSquaresLoss(y, X)
