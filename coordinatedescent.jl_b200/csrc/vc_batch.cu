@@ -510,9 +510,9 @@ struct VcCovArgs {
 
 constexpr int VCW = 1;      // warps (local problems) per CTA (one: shared memory then packs 11 problems per SM)
 constexpr int VC_RING = 4;  // columns of the compact active Gram in flight to shared memory per warp
-__host__ __device__ inline size_t vc_cov_warp_bytes(int ep) {
-  const int MC = ((ep + 31) / 32) * 32; // ring stage stride: a whole number of 32-lane rows, so no lane ever clamps
-  return ((size_t)(VC_RING * MC + 8 * ep) * sizeof(double) + (size_t)(9 * ep + 4) * sizeof(int) + (size_t)ep + 15) / 16 * 16;
+__host__ __device__ inline size_t vc_cov_warp_bytes(int ep, int nu) { // nu: the kernel instance's slots per lane
+  const int RS = 32 * nu; // ring stage stride: a whole number of 32-lane rows, so no lane ever clamps
+  return ((size_t)(VC_RING * RS + 8 * ep) * sizeof(double) + (size_t)(9 * ep + 4) * sizeof(int) + (size_t)ep + 15) / 16 * 16;
 }
 
 __global__ void vc_build_z_kernel(const double *__restrict__ X, long long ldx, int n, int p, const double *__restrict__ y,
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
   extern __shared__ __align__(16) unsigned char raw[];
   const int ep = a.ep, dg = a.degree + 1, nq = 2 * a.degree + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int MC = (ep + 1) & ~1, RS = 32 * NU; // scratch leading dimension bound, ring stage stride
-  unsigned char *base = raw + warp * vc_cov_warp_bytes(ep);
+  unsigned char *base = raw + warp * vc_cov_warp_bytes(ep, NU);
   double *ring = reinterpret_cast<double *>(base);       // VC_RING prefetched columns of the compact active Gram
   double *sbeta = ring + VC_RING * RS;                   // dense beta (after a full pass / at phase start)
   double *sval = sbeta + ep, *stmpd = sval + ep;         // list-order values, scratch
@@ -1168,6 +1168,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   int64_t chunk = (int64_t)((1ll << 30) / ((long long)ldc * nq * 8));
   chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, mloc));
   chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (int64_t)((1ll << 30) / ((long long)ldz * nq * 8))));
+  if (const char *env = getenv("CDGPU_VC_CHUNK")) chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, atoll(env))); // tests: force several chunks
   cudaStream_t s = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr, eg = nullptr;
   double *dX = nullptr, *dz = nullptr, *dy = nullptr, *dgz = nullptr, *dout = nullptr, *dZ = nullptr, *dV = nullptr, *dC = nullptr;
@@ -1250,7 +1251,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
                         : nu == 6 ? (const void *)vc_cov_kernel<6, true>
                                   : (const void *)vc_cov_kernel<8, true>;
   const void *kfn = harr ? kfn_lvo : kfn_std;
-  const size_t wsz = vc_cov_warp_bytes((int)ep);
+  const size_t wsz = vc_cov_warp_bytes((int)ep, nu <= 6 ? std::max(nu, 1) : 8);
   const size_t dyn = VCW * wsz;
   VM_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   int occ = 0;

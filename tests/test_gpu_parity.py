@@ -264,6 +264,26 @@ def test_locpolyl1_parity(gpu, ref, kernel, degree, form, monkeypatch):
     assert np.array_equal(a[:, :12], og[:, :12]) and np.array_equal(b[:, 12:], og[:, 12:])
 
 
+@pytest.mark.parametrize("p,degree", [(28, 2), (100, 1), (64, 3)])
+def test_locpolyl1_moment_form_lane_slot_counts(gpu, ref, p, degree, monkeypatch):
+    """ep = 84, 200, 256: three, seven (kernel instance 8) and eight coordinates per lane; the grid is also cut into
+    chunks of two problems (CDGPU_VC_CHUNK) to cover the chunked driver."""
+    monkeypatch.setenv("CDGPU_VC_CHUNK", "2")
+    rng = np.random.default_rng(84)
+    n = 300
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    Y = X[:, 0] * np.sin(2 * Z) + X[:, 1] * np.sin(4 * Z) + 0.1 * rng.standard_normal(n)
+    zgrid = np.linspace(0.15, 0.85, 5)
+    o = CDOptions(randomize=False, maxIter=200000, optTol=1e-11)
+    og, ogR = gpu.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.3), 0.03, True, o)
+    orf, orR = ref.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.3), 0.03, True, o)
+    assert np.count_nonzero(orf) > 10
+    for g in range(5):
+        assert_parity(og[:, g], orf[:, g])
+    assert np.array_equal(ogR != 0, orR != 0) and np.allclose(ogR, orR, rtol=1e-6, atol=1e-9)
+
+
 @pytest.mark.parametrize("randomize", [0, 1])
 @pytest.mark.parametrize("form", ["moment", "naive"])
 def test_locpolyl1_wide_dense_active_sets(gpu, ref, form, randomize, monkeypatch):
@@ -342,8 +362,9 @@ def test_refit_next_tier(gpu, ref):
     assert np.array_equal(ogR != 0, orR != 0) and np.allclose(ogR, orR, rtol=1e-7, atol=1e-10)
 
 
-@pytest.mark.parametrize("kernel_type,degree", [(GaussianKernel, 1), (EpanechnikovKernel, 0), (GaussianKernel, 2)])
-def test_lvocv_locpolyl1_parity(gpu, ref, kernel_type, degree):
+@pytest.mark.parametrize("kernel_type,degree,randomize", [(GaussianKernel, 1, 0), (EpanechnikovKernel, 0, 0),
+                                                          (GaussianKernel, 2, 0), (GaussianKernel, 1, 1)])
+def test_lvocv_locpolyl1_parity(gpu, ref, kernel_type, degree, randomize):
     """lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): numH*n leave-one-out scaled-lasso local problems as one
     batch; per-problem sigma, outer iterations and squared prediction errors against the oracle (chain cut on both)."""
     rng = np.random.default_rng(95)
@@ -352,7 +373,7 @@ def test_lvocv_locpolyl1_parity(gpu, ref, kernel_type, degree):
     Z = rng.random(n)
     Y = X[:, 0] * np.sin(3 * Z) + X[:, 1] * np.cos(2 * Z) + 0.2 * rng.standard_normal(n)
     h = np.array([0.2, 0.5]) if kernel_type is EpanechnikovKernel else np.array([0.05, 0.2])
-    o = CDOptions(randomize=False, warmStart=False, **TIGHT)
+    o = CDOptions(randomize=randomize, seed=17, warmStart=False, **TIGHT)
     mg = gpu.lvocv_locpolyl1(X, Z, Y, degree, h, kernel_type, 0.3, o)
     sg, stg = gpu.last_lvocv_sqerr.copy(), gpu.last_vc_stats
     mr = ref.lvocv_locpolyl1(X, Z, Y, degree, h, kernel_type, 0.3, o)
