@@ -299,4 +299,225 @@ __device__ Result run(State &S, const Policy &P, double rr, long long maxPasses,
   return R;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The same engine spread over W CTAs (a thread-block cluster, or the cooperative grid), for active sets of many
+// blocks: with ONE CTA the 32 steps of a block reach the other m - 64 entries through a single SM's L2 port
+// (~12 k cycles per block at m = 800, measured), which is what bounds dense active sets.  Here g lives in global
+// memory (L2), CTA 0 keeps the chain (warp 0) and the staging (warps 1..15), and EVERY CTA applies the previous
+// block's steps to the 32-entry groups it owns (group % W); one barrier of the whole team per block hands over g
+// of the next block and h of the finished one.  Same step order per entry as run(): bit-identical iterates.
+struct Multi {
+  int W, me;      // CTAs in the team, this CTA's index (0 runs the chain)
+  double *gG;     // [m] g by entry (global)
+  double *hG;     // [2][32] steps of the last two blocks (global)
+  double *pmaxG;  // [1]
+  int *flagsG;    // [0] new m, [1] list changed
+  int *rowG;      // [m] row ids of the list (global; rewritten by CTA 0 when the list is compacted)
+};
+
+// apply block hbk's steps to the entries of the 32-entry groups owned by this CTA, skipping blocks ex0 / ex1.
+// Warps wfirst.. of the CTA take the owned groups round-robin; lane = entry within the group.
+template <int T, class Policy>
+__device__ __forceinline__ void apply_owned(const State &S, const Multi &X, int m, int hbk, const double *hsrc, int ex0,
+                                            int ex1, int wfirst) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T / 32 - wfirst;
+  if (warp < wfirst) return;
+  const int cnt = min(32, m - 32 * hbk);
+  const double hl = lane < cnt ? __ldcg(hsrc + lane) : 0.0; // lane i holds h_i
+  if (!__any_sync(0xffffffffu, hl != 0.0)) return;
+  const int ri = lane < cnt ? S.row[S.ord[32 * hbk + lane]] : 0; // ... and the row id of entry i of the block
+  const int ngroups = (m + 31) >> 5;
+  for (int gi = X.me + X.W * (warp - wfirst); gi < ngroups; gi += X.W * nw) {
+    const int t = 32 * gi + lane;
+    const bool live = t < m;
+    const int blk = live ? (S.pos[t] >> 5) : ex0;
+    const bool skip = !live || blk == ex0 || blk == ex1;
+    const double *Gt = S.G + (live ? S.row[t] : 0);
+    double gt = skip ? 0.0 : __ldcg(X.gG + t);
+#pragma unroll 1
+    for (int i0 = 0; i0 < cnt; i0 += 16) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int rr_ = __shfl_sync(0xffffffffu, ri, (i0 + u) & 31);
+        v[u] = (!skip && i0 + u < cnt) ? ld_l2(Gt + (long long)rr_ * S.ldg) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const double h = __shfl_sync(0xffffffffu, hl, (i0 + u) & 31);
+        if (i0 + u < cnt && h != 0.0) gt = Policy::apply(gt, v[u], h);
+      }
+    }
+    if (!skip) __stcg(X.gG + t, gt);
+  }
+}
+
+// Team-collective: every thread of every CTA of the team calls it with the same arguments (S.row/ord/pos are
+// per-CTA shared-memory copies; S.g is unused, S.be/S.stage/S.sh only matter on CTA 0).  `sync` is the team barrier
+// (cluster.sync / grid.sync) with release-acquire semantics on global memory.  Only CTA 0's Result is meaningful.
+template <int T, class Policy, class Sync>
+__device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync, double rr, long long maxPasses,
+                            unsigned long long pass_counter, bool ordered, unsigned long long seed, double optTol,
+                            unsigned char *inlist) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool chainCTA = X.me == 0;
+  int m = S.m;
+  Result R{0, 0, 0, 0.0, 0, m};
+  Shared *sh = S.sh;
+  for (long long pass = 0; pass < maxPasses; ++pass) {
+    const int m_pass = m;
+    const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), seed, pass_counter + pass);
+    for (int s = tid; s < m; s += T) {
+      const int e = ordered ? s : (int)cd_perm(pkm, (uint32_t)s);
+      S.ord[s] = (unsigned short)e;
+      S.pos[e] = (unsigned short)s;
+    }
+    __syncthreads();
+    const int nb = (m + 31) >> 5;
+    if (chainCTA) {
+      stage_block(S, P, m, 0, S.stage, tid, T);
+      __syncthreads();
+    }
+    double pmax = 0.0;
+    long long acc = 0;
+    for (int b = 0; b < nb; ++b) {
+      if (chainCTA && warp == 0) {
+        double *buf = S.stage + (b & 1) * BUF_DOUBLES;
+        const int cnt = min(32, m - 32 * b);
+        const bool valid = lane < cnt;
+        const int e = valid ? S.ord[32 * b + lane] : 0;
+        double gj = valid ? __ldcg(X.gG + e) : 0.0, bej = valid ? S.be[e] : 0.0;
+        const double c0 = buf[2048 + lane], c1 = buf[2048 + 32 + lane], c2 = buf[2048 + 64 + lane];
+        if (b > 0) { // steps of the previous block, in order
+          const double *hp = sh->hb[(b - 1) & 1], *Pb = buf + 1024;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const double h = hp[i];
+            if (h != 0.0) gj = Policy::apply(gj, Pb[i * 32 + lane], h);
+          }
+        }
+        double myh = 0.0;
+        double drow = buf[lane];
+        for (int i = 0; i < cnt; ++i) {
+          const double dnext = buf[((i + 1) & 31) * 32 + lane];
+          double nw, hi, dr;
+          P.step(gj, bej, c0, c1, c2, rr, nw, hi, dr);
+          const double h = __shfl_sync(0xffffffffu, hi, i);
+          if (lane == i) {
+            bej = nw;
+            myh = hi;
+          }
+          if (h != 0.0) {
+            gj = Policy::apply(gj, drow, h);
+            if (Policy::HAS_RR) rr += __shfl_sync(0xffffffffu, dr, i);
+            acc += 1;
+          }
+          drow = dnext;
+        }
+        if (valid) {
+          __stcg(X.gG + e, gj);
+          S.be[e] = bej;
+        }
+        const double hv = valid ? myh : 0.0;
+        sh->hb[b & 1][lane] = hv;
+        __stcg(X.hG + (b & 1) * 32 + lane, hv);
+        pmax = fmax(pmax, fabs(myh));
+      } else {
+        if (chainCTA && b + 1 < nb) stage_block(S, P, m, b + 1, S.stage + ((b + 1) & 1) * BUF_DOUBLES, tid - 32, T - 32);
+        if (b >= 1) apply_owned<T, Policy>(S, X, m, b - 1, X.hG + ((b - 1) & 1) * 32, b - 1, b, chainCTA ? 1 : 0);
+      }
+      sync();
+    }
+    // drain: the last block's steps reach the rest of the list (CTA 0's warp 0 joins in)
+    if (nb >= 2) apply_owned<T, Policy>(S, X, m, nb - 1, X.hG + ((nb - 1) & 1) * 32, nb - 1, -1, 0);
+    // ---- end of the pass on CTA 0: max|h|, dropzeros!
+    if (chainCTA) {
+      if (warp == 0) {
+        pmax = warp_max(pmax);
+        if (lane == 0) sh->pmax = pmax;
+      }
+      int z = 0;
+      for (int i = tid; i < m; i += T) z |= (S.be[i] == 0.0);
+      z = __syncthreads_or(z);
+      R.accepted += __shfl_sync(0xffffffffu, acc, 0);
+      if (tid == 0) {
+        __stcg(X.pmaxG, sh->pmax);
+        __stcg(X.flagsG + 1, z ? 1 : 0);
+        if (!z) __stcg(X.flagsG, m);
+      }
+    }
+    sync(); // drain complete everywhere, pass summary published
+    const bool changed = __ldcg(X.flagsG + 1) != 0;
+    if (changed) { // rare: an entry left the active set — CTA 0 compacts (swap-with-last in list order)
+      if (chainCTA) {
+        unsigned short *idx = S.ord;
+        for (int i = tid; i < m; i += T) idx[i] = (unsigned short)i;
+        __syncthreads();
+        if (tid == 0) {
+          int n = m, i = 0;
+          while (i < n) {
+            if (S.be[idx[i]] == 0.0) {
+              inlist[S.coord[idx[i]]] = 0;
+              if (i != n - 1) idx[i] = idx[n - 1];
+              n -= 1;
+            } else {
+              i += 1;
+            }
+          }
+          sh->newm = n;
+        }
+        __syncthreads();
+        const int mn = sh->newm;
+        double *tmpd = S.stage;
+        int *tmpi = reinterpret_cast<int *>(S.stage);
+        for (int i = tid; i < mn; i += T) tmpd[i] = __ldcg(X.gG + idx[i]);
+        __syncthreads();
+        for (int i = tid; i < mn; i += T) __stcg(X.gG + i, tmpd[i]);
+        __syncthreads();
+        for (int i = tid; i < mn; i += T) tmpd[i] = S.be[idx[i]];
+        __syncthreads();
+        for (int i = tid; i < mn; i += T) S.be[i] = tmpd[i];
+        __syncthreads();
+        for (int i = tid; i < mn; i += T) tmpi[i] = S.row[idx[i]];
+        __syncthreads();
+        for (int i = tid; i < mn; i += T) {
+          S.row[i] = tmpi[i];
+          __stcg(X.rowG + i, tmpi[i]);
+        }
+        __syncthreads();
+        if (S.coord != S.row) {
+          for (int i = tid; i < mn; i += T) tmpi[i] = S.coord[idx[i]];
+          __syncthreads();
+          for (int i = tid; i < mn; i += T) S.coord[i] = tmpi[i];
+          __syncthreads();
+        }
+        if (tid == 0) __stcg(X.flagsG, mn);
+      }
+      sync(); // the compacted list is published
+      m = __ldcg(X.flagsG);
+      if (!chainCTA) {
+        for (int i = tid; i < m; i += T) S.row[i] = __ldcg(X.rowG + i);
+        __syncthreads();
+      }
+    }
+    R.npasses += 1;
+    R.visits += m_pass;
+    const double pm = __ldcg(X.pmaxG);
+    R.maxH = pm;
+    if (pm < optTol) {
+      R.conv = 1;
+      break;
+    }
+  }
+  if (chainCTA) {
+    __syncthreads();
+    if (tid == 0) sh->hb[0][0] = (double)R.accepted;
+    __syncthreads();
+    R.accepted = (long long)sh->hb[0][0];
+  }
+  R.m = m;
+  S.m = m;
+  return R;
+}
+
 } // namespace chain

@@ -71,6 +71,7 @@ struct Ctx {
   double *e_g, *e_be, *e_stage;          // CTA-0 engine state (chain_engine.cuh)
   unsigned short *e_ord, *e_pos;
   int ecap;                              // entries the engine can hold in this launch
+  int multi_ok;                          // the cluster-distributed engine may be used (CDGPU_COV_MULTI=0 disables)
   unsigned char *s_in, *s_vnz;           // per slice: member at pass start / tentative value non-zero
   int rank, C, L, lo, len, slice_in_smem;
 };
@@ -386,6 +387,75 @@ __device__ void active_engine(Ctx &c, double lam, long long maxPasses, unsigned 
   __syncthreads();
 }
 
+// The same phase with the chain engine spread over the whole cluster (chain_engine.cuh: run_multi), for active
+// sets of many 32-entry blocks: every CTA applies each block's steps to the entries it owns, one cluster barrier per
+// block.  Called by ALL CTAs; m is the list length read from CTA 0.
+constexpr int COV_MULTI_MIN = 160; // below this the single-CTA engine (no cluster barrier per block) is faster
+__device__ void active_engine_multi(Ctx &c, double lam, long long maxPasses, unsigned long long pass_counter, int m0) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x;
+  double *scr_b0 = a.scr, *scr_dlt = a.scr + a.p;
+  int *act0 = a.iscr;
+  double *gG = a.scr + 6 * (long long)a.p, *hG = a.scr + 8 * (long long)a.p, *pmaxG = hG + 64;
+  int *flagsG = reinterpret_cast<int *>(hG + 72);
+  for (int i = tid; i < m0; i += COV_T) c.s_act[i] = a.act[i]; // every CTA: its own copy of the list
+  if (c.rank == 0) {
+    for (int i = tid; i < m0; i += COV_T) {
+      const int k = a.act[i];
+      const double be = a.actval[i];
+      act0[i] = k;
+      c.e_be[i] = be;
+      scr_b0[i] = be;
+      gG[i] = slice_get(c, c.sAx, k);
+    }
+  }
+  __syncthreads();
+  c.cluster.sync(); // g published
+  chain::State S;
+  S.m = m0;
+  S.row = c.s_act;
+  S.coord = c.s_act;
+  S.g = nullptr;
+  S.be = c.e_be;
+  S.ord = c.e_ord;
+  S.pos = c.e_pos;
+  S.stage = c.e_stage;
+  S.sh = &sm->ch;
+  S.G = a.A;
+  S.ldg = a.lda;
+  S.prof = nullptr;
+  chain::Multi X{c.C, c.rank, gG, hG, pmaxG, flagsG, a.act};
+  const CovPolicy P{a.b, a.ainv, a.omega, lam};
+  cg::cluster_group &cl = c.cluster;
+  const chain::Result r = chain::run_multi<COV_T>(S, X, P, [&cl]() { cl.sync(); }, 0.0, maxPasses, pass_counter,
+                                                  a.randomize == 0, a.seed, a.optTol, a.inlist);
+  if (c.rank == 0) { // publish: final list, dense beta, per-snapshot-entry delta
+    for (int i = tid; i < m0; i += COV_T) a.beta[act0[i]] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < r.m; i += COV_T) {
+      const int k = c.s_act[i];
+      const double be = c.e_be[i];
+      a.beta[k] = be;
+      a.act[i] = k;
+      a.actval[i] = be;
+    }
+    __syncthreads();
+    for (int i = tid; i < m0; i += COV_T) scr_dlt[i] = a.beta[act0[i]] - scr_b0[i];
+    if (tid == 0) {
+      sm->nact = r.m;
+      sm->bc.npasses = r.npasses;
+      sm->bc.visits = r.visits;
+      sm->bc.accepted = r.accepted;
+      sm->bc.maxH = r.maxH;
+      sm->bc.m0 = m0;
+      sm->bc.nact = r.m;
+      sm->bc.conv = r.conv;
+    }
+    __syncthreads();
+  }
+}
+
 // every CTA after the active phase: Ax[slice] += A[slice, act0] * dlt ; beta[slice] <- dense beta
 __device__ void refresh_slice(Ctx &c, int m0) {
   const CovArgs &a = c.a;
@@ -417,7 +487,7 @@ __device__ void refresh_slice(Ctx &c, int m0) {
 }
 
 template <bool PROF>
-__global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int L, int slice_in_smem, int ecap) {
+__global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int L, int slice_in_smem, int ecap, int multi_ok) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx c{a, cluster};
@@ -433,6 +503,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   c.sm = reinterpret_cast<Smem *>(sp);
   sp += (sizeof(Smem) + 15) / 16 * 16;
   c.ecap = ecap;
+  c.multi_ok = multi_ok;
   c.e_stage = reinterpret_cast<double *>(sp);
   sp += chain::STAGE_DOUBLES * sizeof(double);
   c.e_g = reinterpret_cast<double *>(sp);
@@ -539,7 +610,14 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         }
       } else {
         const long long t0 = PROF ? clock64() : 0;
-        if (c.rank == 0) {
+        int m_all = 0; // list length, known to every CTA only when the distributed engine may be used
+        if (c.C > 1 && c.multi_ok) {
+          cluster.sync(); // CTA 0 has finished the list update
+          m_all = *cluster.map_shared_rank(&c.sm->nact, 0);
+        }
+        if (m_all >= COV_MULTI_MIN && m_all <= c.ecap) {
+          active_engine_multi(c, lam, a.maxIter - iter, pass_counter, m_all);
+        } else if (c.rank == 0) {
           const int m = c.sm->nact;
           const long long budget = a.maxIter - iter;
           if (m > c.ecap) {
@@ -786,6 +864,9 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   int slice_in_smem = fixed_for(ecap) + slices <= max_dyn;
   if (!slice_in_smem) ecap = COV_ACT_CAP;
   size_t dyn = slice_in_smem ? fixed_for(ecap) + slices : fixed_for(ecap);
+  // the distributed engine needs 8p + 80 scratch doubles behind the slices; CDGPU_COV_MULTI=0 switches it off
+  int multi_ok = a.p >= 64;
+  if (const char *env = getenv("CDGPU_COV_MULTI")) multi_ok = multi_ok && atoi(env) != 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C);
   cfg.blockDim = dim3(COV_T);
@@ -799,9 +880,9 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (a.prof)
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<true>, a, L, slice_in_smem, ecap));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<true>, a, L, slice_in_smem, ecap, multi_ok));
   else
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<false>, a, L, slice_in_smem, ecap));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<false>, a, L, slice_in_smem, ecap, multi_ok));
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
