@@ -791,6 +791,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.stats = h->dstats;
     if (!h->dgram && !getenv("CDGPU_NAIVE_NO_GRAM_ENGINE")) CD_TRY(dalloc(&h->dgram, (size_t)2048 * 2048 + 2048));
     a.gram = getenv("CDGPU_NAIVE_NO_GRAM_ENGINE") ? nullptr : h->dgram;
+    a.multi_ok = getenv("CDGPU_NAIVE_MULTI") ? atoi(getenv("CDGPU_NAIVE_MULTI")) != 0 : 1;
     a.scaled = rc.scaled;
     a.outerMaxIter = rc.outerMaxIter;
     a.outerTol = rc.outerTol;

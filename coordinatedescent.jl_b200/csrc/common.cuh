@@ -331,6 +331,7 @@ struct NaiveArgs {
   double outerTol, sigma0;
   long long *prof; // optional [10]: SM cycles per phase on CTA 0 (CDGPU_PROFILE=1)
   double *gram;    // scratch for the covariance-form active engine: 2048*2048 + 2048 doubles (or null)
+  int multi_ok;    // grid-distributed chain engine for large active sets (CDGPU_NAIVE_MULTI=0 disables)
 };
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
 int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a); // r = y - X beta, beta dense, inlist

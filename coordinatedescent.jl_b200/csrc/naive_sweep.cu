@@ -657,6 +657,120 @@ __device__ void gram_engine(NCtx &c, double lam, long long maxPasses, unsigned l
   __syncthreads();
 }
 
+// The same phase with the chain engine spread over the whole cooperative grid (chain_engine.cuh: run_multi), for
+// active sets of many 32-entry blocks; called by ALL CTAs after the active Gram has been formed.
+constexpr int NV_MULTI_MIN = 160;
+constexpr int NV_MULTI_TEAM = 16; // CTAs that share the engine
+__device__ void gram_engine_multi(NCtx &c, double lam, long long maxPasses, unsigned long long pass_counter, int m0,
+                                  const double *G, double *d0) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x, n = a.n;
+  double *scr_b0 = a.scr + 8 + 9 * (long long)a.p + 32;
+  double *scr_dlt = scr_b0 + NV_GCAP;
+  double *hG = scr_b0 + 4 * NV_GCAP + 8, *pmaxG = hG + 64;
+  int *flagsG = reinterpret_cast<int *>(hG + 72);
+  int *act0 = a.iscr, *rowG = a.iscr + a.p;
+  for (int i = tid; i < m0; i += NV_T) c.e_row[i] = i; // every CTA: row ids of the compact Gram
+  if (c.bid == 0) {
+    for (int i = tid; i < m0; i += NV_T) {
+      const int k = a.act[i];
+      const double be = a.actval[i];
+      c.e_coord[i] = k;
+      act0[i] = k;
+      c.e_be[i] = be;
+      scr_b0[i] = be;
+      rowG[i] = i;
+    }
+  }
+  __syncthreads();
+  chain::State S;
+  S.m = m0;
+  S.row = c.e_row;
+  S.coord = c.e_coord;
+  S.g = nullptr;
+  S.be = c.e_be;
+  S.ord = c.e_ord;
+  S.pos = c.e_pos;
+  S.stage = c.e_stage;
+  S.sh = &sm->ch;
+  S.G = G;
+  S.ldg = m0;
+  S.prof = nullptr;
+  // team = the first W CTAs of the cooperative grid (all co-resident), with its own barrier: one atomic arrive and
+  // an acquire-poll on a counter in global memory — a 16-CTA barrier costs a fraction of grid.sync() over 148
+  const int W = min(c.G, NV_MULTI_TEAM);
+  chain::Multi X{W, c.bid, d0, hG, pmaxG, flagsG, rowG}; // g = X_A'(w.r), already in global memory
+  unsigned *ctr = reinterpret_cast<unsigned *>(flagsG + 2);
+  unsigned target = 0;
+  auto sync = [ctr, &target, W]() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      target += (unsigned)W;
+      __threadfence();
+      atomicAdd(ctr, 1u);
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      } while (v < target);
+    }
+    __syncthreads();
+  };
+  chain::Result r;
+  const bool ordered = a.randomize == 0;
+  if (a.kind == CDGPU_LOSS_SQRT) {
+    const SqrtPolicy P{a.colsq, a.omega, lam};
+    r = chain::run_multi<NV_T>(S, X, P, sync, c.rr, maxPasses, pass_counter, ordered, a.seed, a.optTol, a.inlist);
+  } else {
+    const LsPolicy P{a.colsq, a.omega, lam, (double)n};
+    r = chain::run_multi<NV_T>(S, X, P, sync, 0.0, maxPasses, pass_counter, ordered, a.seed, a.optTol, a.inlist);
+  }
+  if (c.bid != 0) return;
+  const int m = r.m;
+  // ---- publish the new iterate and fold the change into r: r -= X[:, act0] (beta - beta_at_entry)
+  for (int i = tid; i < m0; i += NV_T) __stcg(a.beta + act0[i], 0.0);
+  __syncthreads();
+  for (int i = tid; i < m; i += NV_T) {
+    const int k = c.e_coord[i];
+    const double be = c.e_be[i];
+    __stcg(a.beta + k, be);
+    a.act[i] = k;
+    a.actval[i] = be;
+    __stcg(a.inlist + k, (unsigned char)1);
+  }
+  __syncthreads();
+  for (int i = tid; i < m0; i += NV_T) scr_dlt[i] = __ldcg(a.beta + act0[i]) - scr_b0[i];
+  __syncthreads();
+  for (int t0 = tid; t0 < n; t0 += NV_T) {
+    const double *row = a.X + t0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int i = 0;
+    for (; i + 4 <= m0; i += 4) {
+      const double v0 = __ldg(row + (long long)act0[i] * a.ldx), v1 = __ldg(row + (long long)act0[i + 1] * a.ldx);
+      const double v2 = __ldg(row + (long long)act0[i + 2] * a.ldx), v3 = __ldg(row + (long long)act0[i + 3] * a.ldx);
+      acc0 = fma(v0, scr_dlt[i], acc0);
+      acc1 = fma(v1, scr_dlt[i + 1], acc1);
+      acc2 = fma(v2, scr_dlt[i + 2], acc2);
+      acc3 = fma(v3, scr_dlt[i + 3], acc3);
+    }
+    for (; i < m0; ++i) acc0 = fma(__ldg(row + (long long)act0[i] * a.ldx), scr_dlt[i], acc0);
+    const double v = c.r[t0] - ((acc0 + acc1) + (acc2 + acc3));
+    c.r[t0] = v;
+    __stcg(a.r + t0, v);
+  }
+  if (tid == 0) {
+    sm->nact = m;
+    c.bc->npasses = r.npasses;
+    c.bc->visits = r.visits;
+    c.bc->accepted = r.accepted;
+    c.bc->maxH = r.maxH;
+    c.bc->conv = r.conv;
+    c.bc->nact = m;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
 __device__ double shared_std(NCtx &c) { // Statistics.std(r), corrected, two-pass
   const int n = c.a.n;
   double s = 0.0;
@@ -775,8 +889,14 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           if (m_act >= 1 && m_act <= c.gcap && a.gram) {
             double *Gs = a.gram, *ds = a.gram + (long long)NV_GCAP * NV_GCAP;
             build_active_gram(c, m_act, Gs, ds);
+            if (c.bid == 0 && tid == 0) { // team-barrier counter of gram_engine_multi (behind hG, pmaxG, 2 flags)
+              double *hG0 = a.scr + 8 + 9 * (long long)a.p + 32 + 4 * NV_GCAP + 8;
+              __stcg(reinterpret_cast<unsigned *>(reinterpret_cast<int *>(hG0 + 72) + 2), 0u);
+            }
             grid.sync();
-            if (c.bid == 0) {
+            if (m_act >= NV_MULTI_MIN && a.multi_ok) {
+              if (c.bid < NV_MULTI_TEAM) gram_engine_multi(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);
+            } else if (c.bid == 0) {
               gram_engine(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);
             }
           } else if (c.bid == 0) {
