@@ -329,6 +329,30 @@ def test_dense_active_set_retraces_oracle(gpu, ref, form, randomize):
     assert_parity(xg.toarray(), xr.toarray())
 
 
+@pytest.mark.parametrize("randomize", [0, 1])
+def test_gram_handle_path_retraces_oracle(gpu, ref, randomize):
+    """A path on a handle whose A was formed by the library (DMMA Gram) retraces the oracle run on the same A, b:
+    same passes / visits per lambda, same list order, same iterates (p = 2500: 16 slices of the cluster)."""
+    n, p, s = 300, 2500, 12
+    X, y, _ = gauss_problem(n, p, s, seed=98)
+    o = CDOptions(randomize=randomize, seed=23, maxIter=5000, optTol=1e-7)
+    f = gpu.CDQuadraticLoss_from_data(X, y)
+    A, b = f.get()
+    om = f.stdX()
+    lmax = gpu.findLambdaMax(f, om)
+    lams = np.exp(np.linspace(np.log(lmax), np.log(0.08 * lmax), 15))
+    pg = gpu.LassoPath(None, None, lams, o, standardizeX=om, loss=f)
+    fr = ref.CDQuadraticLoss(A, b)
+    pr = ref.LassoPath(None, None, lams, o, standardizeX=om, loss=fr)
+    assert pr.βpath[-1].nnz > 10
+    for sg, sr in zip(pg.stats, pr.stats):
+        for key in ("passes", "full_passes", "visits", "converged"):
+            assert sg[key] == sr[key], (key, sg, sr)
+    for xg, xr in zip(pg.βpath, pr.βpath):
+        assert list(xg.nzval2ind[: xg.nnz]) == list(xr.nzval2ind[: xr.nnz])
+        assert np.allclose(xg.toarray(), xr.toarray(), rtol=1e-9, atol=1e-12)
+
+
 def test_refit_next_tier(gpu, ref):
     # test/lasso.jl:236-241: refitLassoPath == X[:, S] \\ Y on every distinct support
     n, p, s = 400, 120, 8
