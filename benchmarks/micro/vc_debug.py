@@ -1,3 +1,5 @@
+"""Moment (covariance) form of the varying-coefficient path against the residual-form kernels on mid-size problems:
+per-problem pass counts and the largest coefficient difference.  Diagnostic, not a test."""
 import os, sys, subprocess, json
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,12 +21,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
 else:
     for cfg in (["200", "20", "2", "64", "0.01"], ["500", "50", "2", "64", "0.01"], ["500", "50", "2", "64", "0.002"]):
         res = {}
-        for name, env in (("naive", {"CDGPU_VC_FORM": "naive"}), ("cov", {}), ("cov_nophase", {"CDGPU_VC_NOPHASE": "1"})):
+        for name, env in (("naive", {"CDGPU_VC_FORM": "naive"}), ("cov", {})):
             f = f"/tmp/vc_{name}.npy"
             r = subprocess.run([sys.executable, __file__, "child", *cfg, f], env=dict(os.environ, **env), capture_output=True, text=True)
             print(cfg, name, r.stdout.strip()[-300:], r.stderr.strip()[-300:])
             res[name] = np.load(f)
-        for name in ("cov", "cov_nophase"):
+        for name in ("cov",):
             d = np.abs(res[name] - res["naive"]).max(axis=0)
             print(cfg, name, "max abs diff vs naive %.3e" % d.max(), "problems off by >1e-6:", int((d > 1e-6).sum()),
                   "support equal:", bool(np.array_equal(res[name] != 0, res["naive"] != 0)))
