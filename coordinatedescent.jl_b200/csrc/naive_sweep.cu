@@ -180,6 +180,27 @@ __device__ __forceinline__ double warp_col_dot(const NCtx &c, const double *col)
   return c.w ? warp_col_dot_t<true>(c, col) : warp_col_dot_t<false>(c, col);
 }
 
+// Barrier of the whole cooperative grid: one atomic arrive + acquire-poll on a counter in global memory (the
+// cooperative launch guarantees co-residency).  Every CTA must call it the same number of times; cheaper than
+// cg::grid_group::sync() over 148 CTAs.  The counter is zeroed at kernel start.
+__device__ __forceinline__ void fast_grid_sync(NCtx &c) {
+  unsigned *ctr = reinterpret_cast<unsigned *>(c.a.flag + 7);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c.bar_target += (unsigned)c.G;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned v;
+    int spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= c.bar_target) break;
+      if (++spins > 64) __nanosleep(256); // a long wait (e.g. CTAs outside the 16-CTA engine team): stop hammering L2
+    }
+  }
+  __syncthreads();
+}
+
 // r -= X_k * h on this CTA's copy; refreshes ||r||^2 when the loss needs it
 __device__ __forceinline__ void apply_step(NCtx &c, const double *col, double h) {
   const int n = c.a.n;
@@ -293,21 +314,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     }
     }
     const long long tb = clock64();
-    { // barrier of the whole grid for this round: one atomic arrive + acquire-poll on a counter (the cooperative
-      // launch guarantees co-residency); cheaper than cg::grid_group::sync() for 148 CTAs
-      unsigned *ctr = reinterpret_cast<unsigned *>(a.flag + 7);
-      __syncthreads();
-      if (tid == 0) {
-        c.bar_target += (unsigned)c.G;
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        unsigned v;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        } while (v < c.bar_target);
-      }
-      __syncthreads();
-    }
+    fast_grid_sync(c);
     const long long tc = clock64();
     pf[0] += tb - ta;
     pf[1] += tc - tb;
@@ -901,7 +908,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           }
         } else {
           const long long t0 = clock64();
-          grid.sync(); // CTA 0 has published the list length
+          fast_grid_sync(c); // CTA 0 has published the list length
           const int m_act = __ldcg(&bc->nact);
           nact_hint = m_act;
           if (m_act >= 1 && m_act <= c.gcap && a.gram) {
@@ -911,7 +918,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
               double *hG0 = a.scr + 8 + 9 * (long long)a.p + 32 + 4 * NV_GCAP + 8;
               __stcg(reinterpret_cast<unsigned *>(reinterpret_cast<int *>(hG0 + 72) + 2), 0u);
             }
-            grid.sync();
+            fast_grid_sync(c);
             if (m_act >= NV_MULTI_MIN && a.multi_ok) {
               if (c.bid < NV_MULTI_TEAM) gram_engine_multi(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);
             } else if (c.bid == 0) {
@@ -921,7 +928,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
             active_phase(c, lam, a.maxIter - iter, pass_counter);
           }
           pf[5] += clock64() - t0;
-          grid.sync();
+          fast_grid_sync(c);
           const long long np = __ldcg(&bc->npasses);
           if (c.bid != 0) {
             for (int i = tid; i < n; i += NV_T) c.r[i] = __ldcg(a.r + i);
@@ -936,7 +943,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           st.maxH = __ldcg(&bc->maxH);
           conv = __ldcg(&bc->conv) != 0;
           nact_hint = __ldcg(&bc->nact);
-          grid.sync(); // bc may be rewritten only after everyone has read it
+          fast_grid_sync(c); // bc may be rewritten only after everyone has read it
         }
       }
       if (!a.scaled) break;
@@ -952,7 +959,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
       bc->nact = c.sm->nact;
       __threadfence();
     }
-    grid.sync();
+    fast_grid_sync(c);
     const int nnz = __ldcg(&bc->nact);
     nact_hint = nnz;
     if (!a.accumulate) {
