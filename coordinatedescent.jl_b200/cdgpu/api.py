@@ -437,16 +437,24 @@ class Backend:
         return LassoPath(lam[: done.value].copy(), βpath, [stats[i].as_dict() for i in range(done.value)])
 
     # refitLassoPath(path, X, Y)                        lasso.jl:208-225
-    @staticmethod
-    def refitLassoPath(path: LassoPath, X, Y):
-        """OLS refit on each distinct support of the path: `X[:, S] \\ Y` (LAPACK on the host, as in the
-        reference — post-processing, not part of the CD hot path).  Keys are 0-based index tuples."""
-        X, Y = np.asarray(X), np.asarray(Y)
+    def refitLassoPath(self, path: LassoPath, X, Y, loss=None):
+        """Least-squares refit on each distinct support of the path (`X[:, S] \\ Y`), through the library
+        (`cdgpu_refit`: normal equations on the support + Cholesky on the device).  Keys are 0-based index tuples
+        in increasing order.  `loss`: an existing handle on (X, Y) to reuse."""
+        own = loss is None
+        f = self.CDLeastSquaresLoss(Y, f64(X)) if own else loss
         out = {}
         for β in path.βpath:
-            S = tuple(int(k) for k in β.nonzero())
-            if S not in out:
-                out[S] = np.linalg.lstsq(X[:, list(S)], Y, rcond=None)[0] if S else np.zeros(0)
+            S = tuple(sorted(int(k) for k in β.nonzero()))
+            if S in out:
+                continue
+            coef = np.zeros(len(S))
+            if S:
+                idx = np.asarray(S, dtype=np.int64) + 1
+                self.lib.check(self.lib.refit(f._h, ptr(idx), len(S), ptr(coef)))
+            out[S] = coef
+        if own:
+            f.close()
         return out
 
     # locpolyl1(X, z, y, zgrid, degree, kernel, λ0, refit, options)  varying_coefficient_lasso.jl:30-79

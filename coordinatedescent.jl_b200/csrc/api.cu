@@ -1079,6 +1079,35 @@ API int cdgpu_stdx(cdgpu_handle h, const double *w, double *out) {
   return CDGPU_OK;
 }
 
+// refitLassoPath (lasso.jl:208-225): coefficients of the least-squares fit on the columns `support` (1-based, ns of
+// them) of the handle's design: X[:, S] \ y for a naive-form handle ([W]-weighted for CDWeightedLSLoss), the
+// equivalent A[S,S] \ (-b[S]) for a covariance-form handle.  Normal equations + Cholesky on the device.
+API int cdgpu_refit(cdgpu_handle h, const int64_t *support, int64_t ns, double *coef_out) {
+  if (!h || (ns > 0 && (!support || !coef_out))) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (ns < 0 || ns > h->p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+  if (ns == 0) return CDGPU_OK;
+  if (ns > 2048) return cdgpu_set_error(CDGPU_ECAP, "refit handles supports of at most 2048 columns");
+  CUDA_TRY(cudaSetDevice(h->device));
+  std::vector<int> s0((size_t)ns);
+  for (int64_t i = 0; i < ns; ++i) {
+    if (support[i] < 1 || support[i] > h->p) return cdgpu_set_error(CDGPU_EDIM, "BoundsError: support index out of range");
+    s0[(size_t)i] = (int)(support[i] - 1);
+  }
+  if (!h->dgram) CD_TRY(dalloc(&h->dgram, (size_t)2048 * 2048 + 2048));
+  int *dS = h->discr; // 8p ints of scratch
+  CUDA_TRY(cudaMemcpyAsync(dS, s0.data(), (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream)); // s0 is a host temporary
+  CD_TRY(launch_refit(h, dS, (int)ns, h->dgram, h->dflag));
+  const int ld = ((int)ns + 1) & ~1;
+  int flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(coef_out, h->dgram + (size_t)ld * ns, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(&flag, h->dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dflag, 0, sizeof(int), h->stream));
+  if (flag) return cdgpu_set_error(CDGPU_EARG, "SingularException: the selected columns are not linearly independent");
+  return CDGPU_OK;
+}
+
 API int cdgpu_lambda_max(cdgpu_handle h, const double *omega, double *out) {
   if (!h || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   CUDA_TRY(cudaSetDevice(h->device));

@@ -294,6 +294,8 @@ int launch_diag_sqrt(cdgpu_handle_s *h, const double *A, long long lda, int p, d
 int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,
                 double *c, double divisor, int mode);
 int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_total);
+// refit.cu: least squares on a support (refitLassoPath); scratch >= ld*ns + ns doubles, ld = ns rounded up to even
+int launch_refit(cdgpu_handle_s *h, const int *dS, int ns, double *scratch, int *flag);
 int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, long long lda, const double *B, int pb,
                    long long ldb, long long n, double *C, long long ldc, double divisor, void **tiles_out);
 

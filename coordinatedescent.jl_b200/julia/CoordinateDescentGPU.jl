@@ -294,6 +294,21 @@ function locpolyl1(X::Matrix{Float64}, z::Vector{Float64}, y::Vector{Float64}, z
     sparse(out), sparse(outR)
 end
 
+# refitLassoPath (lasso.jl:208-225): least squares on each distinct support of the path, on the device
+function refitLassoPath(path::LassoPath{Float64}, X::Matrix{Float64}, Y::Vector{Float64}; device::Integer=0)
+    f = CDLeastSquaresLoss(Y, X; device=device)
+    out = Dict{Vector{Int64},Vector{Float64}}()
+    for β in path.βpath
+        S = sort(β.nzval2ind[1:β.nnz])
+        haskey(out, S) && continue
+        coef = zeros(Float64, length(S))
+        isempty(S) || GC.@preserve S coef check(ccall((:cdgpu_refit, libcdgpu), Cint,
+            (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}), f.h.ptr, S, length(S), coef))
+        out[S] = coef
+    end
+    out
+end
+
 # lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): every (bandwidth, left-out observation) pair is one local
 # scaled-lasso problem of a single batched call; MSE[indH] is the sum of the squared prediction errors over i
 function lvocv_locpolyl1(X::Matrix{Float64}, z::Vector{Float64}, y::Vector{Float64}, degree::Int64, hArr::Vector{Float64},

@@ -213,6 +213,12 @@ int cdgpu_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx, con
                          double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
                          double *outR, cdgpu_stats *stats);
 
+/* refitLassoPath(path, X, Y) (lasso.jl:208-225), one support at a time: the least-squares coefficients on the
+ * columns `support` (1-based indices, ns of them) of the handle's design — X[:, S] \ y for a naive-form handle
+ * (w-weighted for CDWeightedLSLoss), A[S,S] \ (-b[S]) for a covariance-form handle.  Normal equations and Cholesky
+ * on the device; CDGPU_EARG ("SingularException") when the selected columns are linearly dependent. */
+int cdgpu_refit(cdgpu_handle h, const int64_t *support, int64_t ns, double *coef_out);
+
 /* lvocv_locpolyl1(X, z, y, degree, hArr, kernelType, lambda0, options) (varying_coefficient_lasso.jl:81-137):
  * leave-one-out choice of the bandwidth.  For every bandwidth hArr[ih] and observation i: the local problem at
  * z0 = z_i with w_i = 0, sigma initialised by screening (utils.jl:79-92), <= 10 rounds of CD at lambda0*sigma with

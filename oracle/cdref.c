@@ -995,6 +995,41 @@ API int cdref_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
                               device, out, NULL, stats);
 }
 
+/* refitLassoPath (lasso.jl:208-225) for one support: X[:, S] \ y by the normal equations and LU (the reference's
+ * `\` on a tall matrix is a QR least squares: same solution up to conditioning). */
+API int cdref_refit(cdgpu_handle f, const int64_t *support, int64_t ns, double *coef_out) {
+  if (!f || (ns > 0 && (!support || !coef_out))) return fail(CDGPU_EARG, "null pointer");
+  if (ns < 0 || ns > f->p) return fail(CDGPU_EDIM, "DimensionMismatch");
+  if (ns == 0) return CDGPU_OK;
+  for (int64_t a = 0; a < ns; ++a)
+    if (support[a] < 1 || support[a] > f->p) return fail(CDGPU_EDIM, "BoundsError: support index out of range");
+  double *M = (double *)malloc((size_t)(ns * ns) * sizeof(double));
+  if (!M) return fail(CDGPU_ENOMEM, "out of memory");
+  if (f->kind == CDGPU_LOSS_QUAD) {
+    for (int64_t a = 0; a < ns; ++a) {
+      coef_out[a] = -f->y[support[a] - 1];
+      for (int64_t b = 0; b < ns; ++b) M[a + b * ns] = f->X[(support[a] - 1) + (support[b] - 1) * f->ld];
+    }
+  } else {
+    for (int64_t a = 0; a < ns; ++a) {
+      const double *ca = f->X + (support[a] - 1) * f->ld;
+      double r = 0.0;
+      for (int64_t i = 0; i < f->n; ++i) r += ca[i] * (f->kind == CDGPU_LOSS_WLS ? f->w[i] : 1.0) * f->y[i];
+      coef_out[a] = r;
+      for (int64_t b = 0; b < ns; ++b) {
+        const double *cb = f->X + (support[b] - 1) * f->ld;
+        double v = 0.0;
+        for (int64_t i = 0; i < f->n; ++i) v += ca[i] * (f->kind == CDGPU_LOSS_WLS ? f->w[i] : 1.0) * cb[i];
+        M[a + b * ns] = v;
+      }
+    }
+  }
+  int singular = lu_solve(M, coef_out, ns);
+  free(M);
+  if (singular) return fail(CDGPU_EARG, "SingularException: the selected columns are not linearly independent");
+  return CDGPU_OK;
+}
+
 /* lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): for every bandwidth and every observation i the
  * leave-one-out local problem at z0 = z_i (w_i = 0), sigma initialised from the residuals of a weighted LS on the
  * min(10, ep) most correlated columns (utils.jl:79-92, 107-122), <= 10 rounds of CD at lambda0*sigma with

@@ -359,10 +359,24 @@ def test_refit_next_tier(gpu, ref):
     X, y, _ = gauss_problem(n, p, s, seed=91)
     o = CDOptions(randomize=False, **TIGHT)
     path = gpu.LassoPath(X, y, [0.3, 0.1], o, standardizeX=False)
-    rf = gpu.refitLassoPath(path, X, y)
+    rf = gpu.refitLassoPath(path, X, y)  # cdgpu_refit: normal equations + Cholesky on the device
+    rr = ref.refitLassoPath(path, X, y)
+    assert len(rf) == len(rr) >= 2
     for β in path.βpath:
-        S = tuple(β.nonzero())
+        S = tuple(sorted(β.nonzero()))
         assert np.allclose(rf[S], np.linalg.lstsq(X[:, list(S)], y, rcond=None)[0], atol=1e-10)
+        assert np.allclose(rf[S], rr[S], rtol=1e-9, atol=1e-12)
+    # the same supports through a covariance-form handle: A[S,S] \\ (-b[S])
+    fq = gpu.CDQuadraticLoss_from_data(X, y)
+    rq = gpu.refitLassoPath(path, None, None, loss=fq)
+    for S, coef in rf.items():
+        assert np.allclose(rq[S], coef, rtol=1e-8, atol=1e-11)
+    fq.close()
+    with pytest.raises(cdgpu.ArgumentError):  # SingularException: duplicated column in the support
+        Xd = np.asfortranarray(np.hstack([X[:, :3], X[:, :1]]))
+        fd = gpu.CDLeastSquaresLoss(y, Xd)
+        coef = np.zeros(4)
+        gpu.lib.check(gpu.lib.refit(fd._h, cdgpu._ffi.ptr(np.array([1, 2, 3, 4], dtype=np.int64)), 4, cdgpu._ffi.ptr(coef)))
     # locpolyl1(refit=true): refitted coefficients solve the weighted normal equations on the selected groups
     rng = np.random.default_rng(92)
     Xs = np.asfortranarray(rng.standard_normal((200, 6)))
