@@ -32,8 +32,8 @@ sys.path.insert(0, os.path.join(ROOT, "coordinatedescent.jl_b200"))
 
 C2 = dict(n=10000, p=20000, s=50, nlambda=100, ratio=0.05, optTol=1e-7, maxIter=2000)
 REF_SAMPLE_P = 4000  # columns of the reference arm's bounded sample
-NCU_GRAM_DRAM_BYTES = 30.516891e9 + 3.203871e9  # profiles/r1b_kernels_ncu.txt: gram_syrk_kernel at C2, per launch
-NCU_C3_DRAM_BYTES = 6.059927e9 + 0.009213e9     # profiles/r1b_kernels_ncu.txt: naive_path_kernel at C3, per launch
+NCU_GRAM_DRAM_BYTES = 30.228562e9 + 3.203871e9  # profiles/r1d_kernels_ncu.txt: gram_syrk_kernel at C2, per launch
+NCU_C3_DRAM_BYTES = 6.059584e9 + 0.009213e9     # profiles/r1d_kernels_ncu.txt: naive_path_kernel at C3, per launch
 
 
 def parse():
@@ -183,7 +183,7 @@ def secondary_metrics(be, local, hbm):
                             "converged": bool(best["converged"]), "visits_per_sec": best["visits"] / (best["device_ms"] * 1e-3),
                             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                          "bytes_per_visit": 8 * n, "traffic": NCU_C3_DRAM_BYTES,
-                                         "traffic_source": "profiles/r1b_kernels_ncu.txt (ncu --set full, one launch)"}}
+                                         "traffic_source": "profiles/r1d_kernels_ncu.txt (ncu --set full, one launch)"}}
     # ---- C4
     n, p, degree, m = 500, 50, 2, 4096
     rng = np.random.default_rng(125)
@@ -422,9 +422,9 @@ def main():
                roofline={"kernel": "gram_syrk_kernel (FP64 DMMA SYRK)", "bound": "tensor", "achieved": gram_tf,
                          "peak": dgemm_tf, "unit": "TFLOP/s", "frac": gram_tf / dgemm_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default size, from the
-                         # ncu --set full capture in profiles/r1b_kernels_ncu.txt (X is 1.6 GB, G 3.2 GB)
+                         # ncu --set full capture in profiles/r1d_kernels_ncu.txt (X is 1.6 GB, G 3.2 GB)
                          "traffic": NCU_GRAM_DRAM_BYTES if (n, p) == (C2["n"], C2["p"]) else None,
-                         "traffic_source": "profiles/r1b_kernels_ncu.txt (ncu --set full, one launch)",
+                         "traffic_source": "profiles/r1d_kernels_ncu.txt (ncu --set full, one launch)",
                          "flops_per_launch": gram_flops, "launch_ms": gram_ms,
                          "peak_source": "cuBLAS Dgemm 8192^3 FP64 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},
                roofline_sweep={"kernel": "cov_path_kernel (cluster CD sweep, whole path)", "bound": "hbm",
