@@ -64,6 +64,25 @@ def locpolyl1_sharded(be: Backend, X, z, y, zgrid, degree, kernel, λ0, options=
     return full
 
 
+def lvocv_locpolyl1_sharded(be: Backend, X, z, y, degree, hArr, kernelType, λ0, options=None, group=None):
+    """lvocv_locpolyl1 with the numH*n leave-one-out problems split over the ranks of `group` (contiguous slices of
+    the bandwidth-major problem list; every problem is independent).  The only communication is one all_reduce of the
+    numH partial sums; every rank returns the full MSE vector."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    hArr = f64(hArr)
+    m = hArr.size * np.asarray(X).shape[0]
+    lo, hi = shard_range(m, rank, world)
+    part = be.lvocv_locpolyl1(X, z, y, degree, hArr, kernelType, λ0, options, shard=(lo, hi))
+    t = torch.from_numpy(np.ascontiguousarray(part))
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, group=group)
+    return t.cpu().numpy()
+
+
 class Comm:
     """NCCL communicator owned by libcdgpu (cdgpu_comm_*), bootstrapped over torch.distributed."""
 

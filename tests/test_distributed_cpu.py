@@ -41,7 +41,16 @@ def _worker(rank, world, port, q):
     o = CDOptions(randomize=False, optTol=1e-12, maxIter=20000)
     full = locpolyl1_sharded(ref, X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.02, o)
     whole, _ = ref.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.02, False, o)
-    q.put((rank, float(np.max(np.abs(full - whole))), int(np.count_nonzero(whole))))
+    # both sharding modes of the grid, and the leave-one-out problems of lvocv_locpolyl1 (one all_reduce of the sums)
+    blocks = locpolyl1_sharded(ref, X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.02, o, interleave=False)
+    from cdgpu.distributed import lvocv_locpolyl1_sharded
+    hs = np.array([0.1, 0.3])
+    oc = CDOptions(randomize=False, warmStart=False, optTol=1e-10, maxIter=20000)
+    mse_sharded = lvocv_locpolyl1_sharded(ref, X[:60], Z[:60], Y[:60], degree, hs, GaussianKernel, 0.3, oc)
+    mse_whole = ref.lvocv_locpolyl1(X[:60], Z[:60], Y[:60], degree, hs, GaussianKernel, 0.3, oc)
+    err = max(float(np.max(np.abs(full - whole))), float(np.max(np.abs(blocks - whole))),
+              float(np.max(np.abs(mse_sharded - mse_whole) / mse_whole)))
+    q.put((rank, err, int(np.count_nonzero(whole))))
     dist.destroy_process_group()
 
 
