@@ -82,10 +82,11 @@ __device__ __forceinline__ void load_tile(double *dst, const double *X, long lon
 // varying-coefficient path, vc_batch.cu: all local Gram matrices in one FP64 tensor-core GEMM).
 template <bool ALIGNED16, int WM, int WN, int BK, int STAGES, bool PIPE, bool GEMM = false>
 __global__ void __launch_bounds__(WM *WN * 32, 1)
-    gram_syrk_kernel(const double *__restrict__ X, long long n, int p, long long ldx, double *G,
+    gram_syrk_kernel(const double *X, long long n, int p, long long ldx, double *G,
                      long long ldg, const int2 *__restrict__ tiles, int ntiles, double divisor, int mode,
-                     const double *__restrict__ Bm = nullptr, int pb = 0, long long ldb = 0) {
-  const double *__restrict__ XB = GEMM ? Bm : X;
+                     const double *__restrict__ Bm = nullptr, int pb = 0, long long ldb = 0, long long kchunk = 0,
+                     double *__restrict__ slab = nullptr, int slab_tiles = 0) {
+  const double *XB = GEMM ? Bm : X;
   const int pB = GEMM ? pb : p;
   const long long ldB = GEMM ? ldb : ldx;
   constexpr int GT = WM * WN * 32, LDK = BK + 4, STAGE_DOUBLES = (BM + BN) * LDK;
@@ -94,10 +95,17 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / WN, wn = warp % WN;
   const int g = lane >> 2, q = lane & 3;
-  const long long nK = (n + BK - 1) / BK;
+  const long long n_all = n;
 
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int bi = tiles[t].x, bj = tiles[t].y; // bi >= bj
+    // work item: tile (bi >= bj) and, in the row-split form (kchunk > 0, tall-skinny X), the chunk of rows it covers;
+    // its partial sums go to slab[chunk][tile index] and are reduced in a fixed order afterwards
+    const int bi = tiles[t].x & 0xffff, chunk = tiles[t].x >> 16, bj = tiles[t].y & 0xffff, tidx = tiles[t].y >> 16;
+    const long long kbeg = kchunk > 0 ? (long long)chunk * kchunk : 0;
+    X += kbeg;   // rows [kbeg, kend) of both operands
+    XB += kbeg;
+    n = kchunk > 0 ? min(n_all - kbeg, kchunk) : n_all;
+    const long long nK = (n + BK - 1) / BK;
     const int colA = bi * BM, colB = bj * BN;
     double acc[MI][NI][2];
 #pragma unroll
@@ -191,6 +199,19 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
     // epilogue: G[colA + m, colB + nn] and its mirror.  mode 0: store raw sums, 1: store sums / divisor,
     // 2: add the raw sums to what is there (row-chunked accumulation; both triangles hold the same value),
     // 3: as 2, then divide by divisor (last row chunk)
+    if (kchunk > 0) { // row-split: raw partial tile to the slab (the reduction applies scale / mirror / diagonal rule)
+      double *st = slab + ((size_t)chunk * slab_tiles + tidx) * (size_t)(BM * BN);
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          const int r = wm * MI * 8 + i * 8 + g, cc = wn * NI * 8 + j * 8 + 2 * q;
+          *reinterpret_cast<double2 *>(st + (size_t)r * BN + cc) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+      X -= kbeg;
+      XB -= kbeg;
+      continue;
+    }
     auto put = [&](int r, int cidx, double v) {
       if (mode >= 2) v += G[r + (long long)cidx * ldg];
       if (mode == 3) v = v / divisor;
@@ -220,6 +241,24 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
         }
       }
     }
+  }
+}
+
+// row-split form: G tile = sum over row chunks of the slab partials (fixed order: deterministic), then the same
+// store rule as the direct epilogue (mode 0 raw / 1 divided; lower part authoritative on diagonal tiles; mirrored)
+__global__ void gram_reduce_slabs_kernel(const double *__restrict__ slab, int nchunks, int slab_tiles, const int2 *__restrict__ base_tiles,
+                                         int p, double *G, long long ldg, double divisor, int mode) {
+  const int tidx = blockIdx.x;
+  const int bi = base_tiles[tidx].x, bj = base_tiles[tidx].y;
+  for (int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
+    const int r = e / BN, cc = e % BN;
+    const int row = bi * BM + r, col = bj * BN + cc;
+    if (row >= p || col >= p || (bi == bj && row < col)) continue;
+    double v = 0.0;
+    for (int c = 0; c < nchunks; ++c) v += slab[((size_t)c * slab_tiles + tidx) * (size_t)(BM * BN) + e];
+    if (mode == 1) v = v / divisor;
+    G[row + (long long)col * ldg] = v;
+    G[col + (long long)row * ldg] = v;
   }
 }
 
@@ -273,12 +312,66 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
   const int2 *dtiles = static_cast<const int2 *>(h->dtiles);
   const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((ldx & 1) == 0);
   const long long ldg = ((long long)p + 1) & ~1ll;
+  // Tall-skinny X (few tiles, many rows): with one work item per tile the last wave is mostly idle and there are
+  // fewer tiles than SMs times two; split the ROWS as well: items = tiles x row chunks with nchunks chosen so that
+  // the item count is a multiple of the SM count, partial tiles to a slab, one deterministic reduction.
+  if (aligned && (mode == 0 || mode == 1) && ntiles < 2 * h->sm_count && n >= 65536 && !getenv("CDGPU_GRAM_NO_ROWSPLIT")) {
+    auto gcd = [](int a_, int b_) {
+      while (b_) {
+        const int t_ = a_ % b_;
+        a_ = b_;
+        b_ = t_;
+      }
+      return a_;
+    };
+    int nchunks = h->sm_count / gcd(ntiles, h->sm_count);
+    while ((long long)nchunks * ntiles < 6ll * h->sm_count) nchunks *= 2; // at least ~6 waves
+    long long kchunk = ((n + nchunks - 1) / nchunks + 15) & ~15ll;
+    if (kchunk < 4096) kchunk = 4096;
+    nchunks = (int)((n + kchunk - 1) / kchunk);
+    std::vector<int2> base((size_t)ntiles), items;
+    {
+      std::vector<int2> all;
+      for (int SI = 0; SI < nb; SI += S)
+        for (int SJ = 0; SJ <= SI; SJ += S)
+          for (int bi = SI; bi < min(SI + S, nb); ++bi)
+            for (int bj = SJ; bj < min(SJ + S, nb) && bj <= bi; ++bj) all.push_back(make_int2(bi, bj));
+      base = all;
+    }
+    items.reserve((size_t)ntiles * nchunks);
+    for (int ch = 0; ch < nchunks; ++ch)
+      for (int t = 0; t < ntiles; ++t) items.push_back(make_int2(base[t].x | (ch << 16), base[t].y | (t << 16)));
+    int2 *ditems = nullptr, *dbase = nullptr;
+    double *slab = nullptr;
+    const size_t slab_doubles = (size_t)nchunks * ntiles * BM * BN;
+    CUDA_TRY(cudaMallocAsync((void **)&ditems, items.size() * sizeof(int2), h->stream));
+    CUDA_TRY(cudaMallocAsync((void **)&dbase, base.size() * sizeof(int2), h->stream));
+    CUDA_TRY(cudaMallocAsync((void **)&slab, slab_doubles * sizeof(double), h->stream));
+    CUDA_TRY(cudaMemcpyAsync(ditems, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dbase, base.data(), base.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream)); // host temporaries
+    auto kern = gram_syrk_kernel<true, 2, 4, 16, 4, true>;
+    const size_t dyn = (size_t)4 * (BM + BN) * (16 + 4) * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<min((int)items.size(), h->sm_count), 256, dyn, h->stream>>>(X, n, p, ldx, G, ldg, ditems, (int)items.size(), divisor, mode,
+                                                                      nullptr, 0, 0, kchunk, slab, ntiles);
+    CUDA_TRY(cudaGetLastError());
+    gram_reduce_slabs_kernel<<<ntiles, 512, 0, h->stream>>>(slab, nchunks, ntiles, dbase, p, G, ldg, divisor, mode);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(slab, h->stream));
+    CUDA_TRY(cudaFreeAsync(ditems, h->stream));
+    CUDA_TRY(cudaFreeAsync(dbase, h->stream));
+    xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, c, divisor, mode);
+    CUDA_TRY(cudaGetLastError());
+    CD_COUNT_LAUNCH(3);
+    return CDGPU_OK;
+  }
   const int grid = min(ntiles, h->sm_count);
   int variant = 5; // 2x4 warps, BK 16, 4 stages, fragments double-buffered across the k-tile barrier
   if (const char *env = getenv("CDGPU_GRAM_VARIANT")) variant = atoi(env);
   auto launch = [&](auto kern, int threads, size_t dyn) -> int {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    kern<<<grid, threads, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, mode, nullptr, 0, 0);
+    kern<<<grid, threads, dyn, h->stream>>>(X, n, p, ldx, G, ldg, dtiles, ntiles, divisor, mode, nullptr, 0, 0, 0, nullptr, 0);
     CUDA_TRY(cudaGetLastError());
     return CDGPU_OK;
   };
@@ -338,11 +431,11 @@ int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, l
   if (aligned) {
     auto kern = gram_syrk_kernel<true, 2, 4, 16, 4, true, true>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    kern<<<grid, 256, dyn, stream>>>(A, n, pa, lda, C, ldc, dt, ntiles, divisor, 1, B, pb, ldb);
+    kern<<<grid, 256, dyn, stream>>>(A, n, pa, lda, C, ldc, dt, ntiles, divisor, 1, B, pb, ldb, 0, nullptr, 0);
   } else {
     auto kern = gram_syrk_kernel<false, 2, 4, 16, 4, false, true>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    kern<<<grid, 256, dyn, stream>>>(A, n, pa, lda, C, ldc, dt, ntiles, divisor, 1, B, pb, ldb);
+    kern<<<grid, 256, dyn, stream>>>(A, n, pa, lda, C, ldc, dt, ntiles, divisor, 1, B, pb, ldb, 0, nullptr, 0);
   }
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(1);

@@ -353,6 +353,37 @@ def test_gram_handle_path_retraces_oracle(gpu, ref, randomize):
         assert np.allclose(xg.toarray(), xr.toarray(), rtol=1e-9, atol=1e-12)
 
 
+def test_tall_gram_row_split_form(gpu, monkeypatch):
+    """Tall-skinny X resident on the device (few 128-column tiles, many rows): the SYRK splits the rows over the CTAs
+    as well and reduces the partial tiles in a fixed order.  Same Gram as the direct form to rounding, exactly
+    symmetric, deterministic."""
+    import ctypes as C
+
+    import torch
+    rng = np.random.default_rng(99)
+    n, p = 70001, 300
+    X = rng.standard_normal((p, n))  # (p, n) C-order == (n, p) column-major
+    y = X[:5].T @ rng.standard_normal(5) + rng.standard_normal(n)
+    Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
+
+    def gram():
+        f = cdgpu.CDQuadraticLoss.__new__(cdgpu.CDQuadraticLoss)
+        cdgpu.api._Loss.__init__(f, gpu.lib)
+        f.p = p
+        gpu.lib.check(gpu.lib.gram_create_dev(C.byref(f._h), C.c_void_p(Xd.data_ptr()), n, p, n, C.c_void_p(yd.data_ptr()), 0))
+        A, b = f.get()
+        f.close()
+        return A, b
+
+    A, b = gram()
+    A2, _ = gram()
+    monkeypatch.setenv("CDGPU_GRAM_NO_ROWSPLIT", "1")
+    A3, b3 = gram()
+    assert np.array_equal(A, A.T) and np.array_equal(A, A2)
+    assert np.allclose(A, X @ X.T / n, rtol=1e-12, atol=1e-13) and np.allclose(b, -X @ y / n, rtol=1e-12, atol=1e-13)
+    assert np.allclose(A, A3, rtol=1e-13, atol=1e-14) and np.array_equal(b, b3)
+
+
 def test_refit_next_tier(gpu, ref):
     # test/lasso.jl:236-241: refitLassoPath == X[:, S] \\ Y on every distinct support
     n, p, s = 400, 120, 8
