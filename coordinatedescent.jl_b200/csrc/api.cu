@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -62,7 +63,6 @@ API void cdgpu_default_iter_options(cdgpu_iter_options *o) { // IterLassoOptions
 }
 
 // CDGPU_TRACE=1: host-side wall-clock trace of the handle constructors (where do create() stalls come from?)
-#include <chrono>
 struct Trace {
   bool on;
   std::chrono::steady_clock::time_point t0, last;

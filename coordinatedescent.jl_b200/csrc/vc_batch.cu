@@ -504,7 +504,6 @@ struct VcCovArgs {
   long long ldx;
   double *lvo_err;     // squared prediction error per problem
   unsigned long long *prof; // optional [8]: summed warp cycles: full passes, active chain, list compaction, phase open, phase close, total
-  int dbg;      // CDGPU_VC_DBG (timing experiments only; results are wrong when set): 1 no column prefetch, 2 no compaction
   double *gscr; // per-warp scratch for the compact active Gram: (grid * VCW) x MC x MC doubles, MC = ep rounded up to even
 };
 
@@ -653,7 +652,6 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
     // dependent path, and (d) at the end brings (A x) of the other coordinates up to date from the change of beta.
     bool in_phase = false;
     int m0 = 0, ldw = 0;
-    long long wait_cyc = 0;
     auto phase_open = [&](int m) {
       m0 = m;
       ldw = (m + 1) & ~1;
@@ -937,10 +935,8 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
         st.accepted += acc_pass;
         pc[1] += clock64() - tq;
         tq = clock64();
-        if (!(a.dbg & 2)) {
         cd_compact_list<32>(sact, sval, m, m, snewpos, sin, stmpi, stmpd, s2); // dropzeros!
         nact = s2[0];
-        }
         __syncwarp();
         pc[2] += clock64() - tq;
       }
@@ -1109,7 +1105,6 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
     if (a.prof && lane == 0) {
       pc[5] = clock64() - tstart;
       for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, (unsigned long long)pc[i]);
-      atomicAdd(a.prof + 7, (unsigned long long)wait_cyc);
       atomicMax(a.prof + 6, (unsigned long long)pc[5]);
     }
     if (a.out) {
@@ -1305,7 +1300,6 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
     a.lvo_err = derr;
     a.prof = dprof;
     a.gscr = dG;
-    a.dbg = getenv("CDGPU_VC_DBG") ? atoi(getenv("CDGPU_VC_DBG")) : 0;
     const int64_t ctas = std::min<int64_t>((mc + VCW - 1) / VCW, (int64_t)occ * sms);
     void *kargs[] = {(void *)&a};
     VM_TRY(cudaLaunchKernel(kfn, dim3((unsigned)ctas), dim3(VCW * 32), kargs, dyn, s));
@@ -1331,8 +1325,8 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
         unsigned long long pf[8];
         cudaMemcpy(pf, dprof, sizeof pf, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[cdgpu profile]   warp cycles summed over problems (M): full passes %.1f | active chain %.1f | compaction %.1f | phase open %.1f | "
-                        "phase close %.1f | total %.1f | longest problem %.2f | column fetch+wait inside the chain (CDGPU_VC_DBG=4) %.1f\n",
-                pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6, pf[6] * 1e-6, pf[7] * 1e-6);
+                        "phase close %.1f | total %.1f | longest problem %.2f\n",
+                pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6, pf[6] * 1e-6);
       }
     }
     std::vector<DevStats> hst((size_t)mloc);
