@@ -5,12 +5,14 @@
 //   sd_k = sqrt(sum_i w_i eX_ik^2 / n) (utils.jl:140-151),
 // solved by the reference's CD loop on CDWeightedLSLoss (cd_differentiable_function.jl:165-194).
 //
-// B200 design: ONE CTA PER GRID POINT, everything per-problem (w, z - z0, r, column norms, iterate,
-// active list) in shared memory; the expanded n x p(d+1) design is never materialised — a column
-// is X[:,j] (shared by all problems, L1/L2 resident: 8np bytes total) times a power of (z - z0).
-// Full passes are speculative (one warp per coordinate, first mover wins, exact Gauss-Seidel
-// order); active-set passes are a short sequential chain with block-wide dots.  No inter-CTA
-// communication at all; grid points are sharded over GPUs by [m_begin, m_end).
+// B200 design.  DEFAULT (ep <= 256): the MOMENT FORM further down — all local Gram matrices of all grid points are
+// one FP64 tensor-core GEMM (Z'V, gram_dmma.cu) and each local lasso is a covariance-form CD solved by ONE WARP
+// (vc_cov_kernel), with the refit (cdgpu_vc_solve_refit) and the leave-one-out scaled-lasso problems of
+// lvocv_locpolyl1 (cdgpu_vc_lvocv) in the same kernel.  RESIDUAL FORM (CDGPU_VC_FORM=naive, or ep > 256), first
+// in this file: ONE WARP (n <= 512) or ONE CTA PER GRID POINT, everything per-problem (w, z - z0, r, column
+// norms, iterate, active list) in registers / shared memory; the expanded n x p(d+1) design is never
+// materialised — a column is X[:,j] (shared by all problems, L1/L2 resident: 8np bytes total) times a power of
+// (z - z0).  No inter-CTA communication at all; grid points are sharded over GPUs by [m_begin, m_end).
 #include <math.h>
 #include <string.h>
 
