@@ -244,3 +244,31 @@ def test_lvocv_oracle_prefers_the_true_bandwidth_and_chain_cut_agree(ref):
     cut = ref.lvocv_locpolyl1(X, Z, Y, 1, h, GaussianKernel, 0.2, CDOptions(warmStart=False, **o))
     assert np.allclose(chain, cut, rtol=1e-3)
     assert cut[0] < 0.5 * cut[1]
+
+
+def test_oracle_refits_match_numpy(ref):
+    """refitLassoPath (lasso.jl:208-225, test/lasso.jl:236-241) and locpolyl1(refit=true)
+    (varying_coefficient_lasso.jl:71-76) in the oracle against numpy's own least squares."""
+    from cdgpu import CDOptions, GaussianKernel
+    X, y, _ = gauss_problem(200, 60, 6, seed=51)
+    o = CDOptions(randomize=False, maxIter=20000, optTol=1e-12)
+    path = ref.LassoPath(X, y, [0.3, 0.1, 0.03], o, standardizeX=False)
+    rf = ref.refitLassoPath(path, X, y)
+    assert len(rf) >= 2
+    for S, coef in rf.items():
+        assert np.allclose(coef, np.linalg.lstsq(X[:, list(S)], y, rcond=None)[0], rtol=1e-9, atol=1e-12)
+    rng = np.random.default_rng(52)
+    Xs = np.asfortranarray(rng.standard_normal((150, 5)))
+    Z = rng.random(150)
+    Y = np.sin(4 * Z) * Xs[:, 0] + 0.1 * rng.standard_normal(150)
+    zg = np.array([0.25, 0.5, 0.75])
+    out, outR = ref.locpolyl1(Xs, Z, Y, zg, 2, GaussianKernel(0.2), 0.05, True, o)
+    for g in range(3):
+        grp = np.flatnonzero(np.any(out[:, g].reshape(5, 3) != 0, axis=1))
+        S = (grp[:, None] * 3 + np.arange(3)).ravel()
+        d = Z - zg[g]
+        w = np.exp(-d ** 2 / 0.2) / 0.2
+        E = np.stack([Xs[:, k // 3] * d ** (k % 3) for k in S], axis=1)
+        t = E.T * w
+        assert np.allclose(outR[S, g], np.linalg.solve(t @ E, t @ Y), rtol=1e-9, atol=1e-12)
+        assert np.count_nonzero(outR[:, g]) == S.size
