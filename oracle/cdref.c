@@ -37,7 +37,7 @@
  * convergence do not depend on either.
  *
  * Build: see oracle/Makefile.  libcdref.so      = -O2 -ffp-contract=off (parity)
- *                              libcdref_fast.so = -O3 -march=native      (timing)
+ *                              libcdref_fast.so = -O3 -march=x86-64-v3   (timing)
  */
 #include "../include/cdgpu.h"
 
