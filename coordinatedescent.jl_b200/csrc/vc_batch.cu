@@ -513,7 +513,7 @@ constexpr int VCW = 1;      // warps (local problems) per CTA (one: shared memor
 constexpr int VC_RING = 4;  // columns of the compact active Gram in flight to shared memory per warp
 __host__ __device__ inline size_t vc_cov_warp_bytes(int ep, int nu) { // nu: the kernel instance's slots per lane
   const int RS = 32 * nu; // ring stage stride: a whole number of 32-lane rows, so no lane ever clamps
-  return ((size_t)(VC_RING * RS + 8 * ep) * sizeof(double) + (size_t)(9 * ep + 4) * sizeof(int) + (size_t)ep + 15) / 16 * 16;
+  return ((size_t)(VC_RING * RS + 8 * ep) * sizeof(double) + (size_t)(6 * ep + 4) * sizeof(int) + (size_t)ep + 15) / 16 * 16;
 }
 
 __global__ void vc_build_z_kernel(const double *__restrict__ X, long long ldx, int n, int p, const double *__restrict__ y,
@@ -572,7 +572,7 @@ __device__ __forceinline__ void vc_cp16(unsigned dst, const char *src) {
 }
 
 template <int NU, bool LVO>
-__global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a) {
+__global__ void __launch_bounds__(VCW * 32, 11) vc_cov_kernel(const VcCovArgs a) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int ep = a.ep, dg = a.degree + 1, nq = 2 * a.degree + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int MC = (ep + 1) & ~1, RS = 32 * NU; // scratch leading dimension bound, ring stage stride
@@ -583,7 +583,8 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
   double *sAx = stmpd + ep, *scc = sAx + ep, *sai = scc + ep, *sth = sai + ep; // dense (A x) and constants
   double *sAxE = sth + ep;                               // (A x) of the active entries of a phase, by snapshot entry
   int *sact = reinterpret_cast<int *>(sAxE + ep);
-  int *snewpos = sact + ep, *sact0 = snewpos + ep, *stmpi = sact0 + ep, *s2 = stmpi + 5 * ep, *spos = s2 + 4;
+  int *snewpos = sact + ep, *sact0 = snewpos + ep, *stmpi = sact0 + ep, *s2 = stmpi + 2 * ep, *spos = s2 + 4;
+  int *scmp = reinterpret_cast<int *>(ring); // cd_compact_list's 5*m ints: the column ring is idle whenever a list is compacted
   unsigned char *sin = reinterpret_cast<unsigned char *>(spos + ep);
   double *Gw = a.gscr + ((long long)blockIdx.x * VCW + warp) * (long long)MC * MC; // this warp's compact Gram scratch
   const bool ordered = a.randomize == 0;
@@ -919,7 +920,7 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
           snewpos[e - m_old] = m_old + vis - before;
         }
         __syncwarp();
-        cd_compact_list<32>(sact, sval, m_old, nact, snewpos, sin, stmpi, stmpd, s2);
+        cd_compact_list<32>(sact, sval, m_old, nact, snewpos, sin, scmp, stmpd, s2);
         nact = s2[0];
         __syncwarp();
         pc[2] += clock64() - tq;
@@ -937,7 +938,7 @@ __global__ void __launch_bounds__(VCW * 32, 10) vc_cov_kernel(const VcCovArgs a)
         st.accepted += acc_pass;
         pc[1] += clock64() - tq;
         tq = clock64();
-        cd_compact_list<32>(sact, sval, m, m, snewpos, sin, stmpi, stmpd, s2); // dropzeros!
+        cd_compact_list<32>(sact, sval, m, m, snewpos, sin, scmp, stmpd, s2); // dropzeros!
         nact = s2[0];
         __syncwarp();
         pc[2] += clock64() - tq;
