@@ -547,6 +547,56 @@ __device__ void build_active_gram(NCtx &c, int m, double *G, double *d) {
   }
 }
 
+// CTA 0 after an active phase on the Gram: publish the new iterate (list, dense beta, membership) and fold the change
+// into the residual once, r -= X[:, act0] (beta - beta_at_entry); summary to the broadcast block.
+__device__ void gram_publish(NCtx &c, const chain::Result &r, int m0, const int *act0, const double *scr_b0, double *scr_dlt) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x, n = a.n;
+  const int m = r.m;
+  for (int i = tid; i < m0; i += NV_T) __stcg(a.beta + act0[i], 0.0);
+  __syncthreads();
+  for (int i = tid; i < m; i += NV_T) {
+    const int k = c.e_coord[i];
+    const double be = c.e_be[i];
+    __stcg(a.beta + k, be);
+    a.act[i] = k;
+    a.actval[i] = be;
+    __stcg(a.inlist + k, (unsigned char)1);
+  }
+  __syncthreads();
+  for (int i = tid; i < m0; i += NV_T) scr_dlt[i] = __ldcg(a.beta + act0[i]) - scr_b0[i];
+  __syncthreads();
+  for (int t0 = tid; t0 < n; t0 += NV_T) {
+    const double *row = a.X + t0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int i = 0;
+    for (; i + 4 <= m0; i += 4) {
+      const double v0 = __ldg(row + (long long)act0[i] * a.ldx), v1 = __ldg(row + (long long)act0[i + 1] * a.ldx);
+      const double v2 = __ldg(row + (long long)act0[i + 2] * a.ldx), v3 = __ldg(row + (long long)act0[i + 3] * a.ldx);
+      acc0 = fma(v0, scr_dlt[i], acc0);
+      acc1 = fma(v1, scr_dlt[i + 1], acc1);
+      acc2 = fma(v2, scr_dlt[i + 2], acc2);
+      acc3 = fma(v3, scr_dlt[i + 3], acc3);
+    }
+    for (; i < m0; ++i) acc0 = fma(__ldg(row + (long long)act0[i] * a.ldx), scr_dlt[i], acc0);
+    const double v = c.r[t0] - ((acc0 + acc1) + (acc2 + acc3));
+    c.r[t0] = v;
+    __stcg(a.r + t0, v);
+  }
+  if (tid == 0) {
+    sm->nact = m;
+    c.bc->npasses = r.npasses;
+    c.bc->visits = r.visits;
+    c.bc->accepted = r.accepted;
+    c.bc->maxH = r.maxH;
+    c.bc->conv = r.conv;
+    c.bc->nact = m;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
 // closed-form updates on d_t = X_t'(w.r) for the chain engine (chain_engine.cuh)
 struct LsPolicy { // cd_differentiable_function.jl:101-104 / :184-187
   static constexpr bool HAS_RR = false;
@@ -634,49 +684,7 @@ __device__ void gram_engine(NCtx &c, double lam, long long maxPasses, unsigned l
     const LsPolicy P{a.colsq, a.omega, lam, (double)n};
     r = chain::run<NV_T>(S, P, 0.0, maxPasses, pass_counter, ordered, a.seed, a.optTol, a.inlist);
   }
-  const int m = r.m;
-  // ---- publish the new iterate and fold the change into r: r -= X[:, act0] (beta - beta_at_entry)
-  for (int i = tid; i < m0; i += NV_T) __stcg(a.beta + act0[i], 0.0);
-  __syncthreads();
-  for (int i = tid; i < m; i += NV_T) {
-    const int k = c.e_coord[i];
-    const double be = c.e_be[i];
-    __stcg(a.beta + k, be);
-    a.act[i] = k;
-    a.actval[i] = be;
-    __stcg(a.inlist + k, (unsigned char)1);
-  }
-  __syncthreads();
-  for (int i = tid; i < m0; i += NV_T) scr_dlt[i] = __ldcg(a.beta + act0[i]) - scr_b0[i];
-  __syncthreads();
-  for (int t0 = tid; t0 < n; t0 += NV_T) {
-    const double *row = a.X + t0;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-    int i = 0;
-    for (; i + 4 <= m0; i += 4) {
-      const double v0 = __ldg(row + (long long)act0[i] * a.ldx), v1 = __ldg(row + (long long)act0[i + 1] * a.ldx);
-      const double v2 = __ldg(row + (long long)act0[i + 2] * a.ldx), v3 = __ldg(row + (long long)act0[i + 3] * a.ldx);
-      acc0 = fma(v0, scr_dlt[i], acc0);
-      acc1 = fma(v1, scr_dlt[i + 1], acc1);
-      acc2 = fma(v2, scr_dlt[i + 2], acc2);
-      acc3 = fma(v3, scr_dlt[i + 3], acc3);
-    }
-    for (; i < m0; ++i) acc0 = fma(__ldg(row + (long long)act0[i] * a.ldx), scr_dlt[i], acc0);
-    const double v = c.r[t0] - ((acc0 + acc1) + (acc2 + acc3));
-    c.r[t0] = v;
-    __stcg(a.r + t0, v);
-  }
-  if (tid == 0) {
-    sm->nact = m;
-    c.bc->npasses = r.npasses;
-    c.bc->visits = r.visits;
-    c.bc->accepted = r.accepted;
-    c.bc->maxH = r.maxH;
-    c.bc->conv = r.conv;
-    c.bc->nact = m;
-  }
-  __threadfence();
-  __syncthreads();
+  gram_publish(c, r, m0, act0, scr_b0, scr_dlt);
 }
 
 // The same phase with the chain engine spread over the whole cooperative grid (chain_engine.cuh: run_multi), for
@@ -748,49 +756,7 @@ __device__ void gram_engine_multi(NCtx &c, double lam, long long maxPasses, unsi
     r = chain::run_multi<NV_T>(S, X, P, sync, 0.0, maxPasses, pass_counter, ordered, a.seed, a.optTol, a.inlist);
   }
   if (c.bid != 0) return;
-  const int m = r.m;
-  // ---- publish the new iterate and fold the change into r: r -= X[:, act0] (beta - beta_at_entry)
-  for (int i = tid; i < m0; i += NV_T) __stcg(a.beta + act0[i], 0.0);
-  __syncthreads();
-  for (int i = tid; i < m; i += NV_T) {
-    const int k = c.e_coord[i];
-    const double be = c.e_be[i];
-    __stcg(a.beta + k, be);
-    a.act[i] = k;
-    a.actval[i] = be;
-    __stcg(a.inlist + k, (unsigned char)1);
-  }
-  __syncthreads();
-  for (int i = tid; i < m0; i += NV_T) scr_dlt[i] = __ldcg(a.beta + act0[i]) - scr_b0[i];
-  __syncthreads();
-  for (int t0 = tid; t0 < n; t0 += NV_T) {
-    const double *row = a.X + t0;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-    int i = 0;
-    for (; i + 4 <= m0; i += 4) {
-      const double v0 = __ldg(row + (long long)act0[i] * a.ldx), v1 = __ldg(row + (long long)act0[i + 1] * a.ldx);
-      const double v2 = __ldg(row + (long long)act0[i + 2] * a.ldx), v3 = __ldg(row + (long long)act0[i + 3] * a.ldx);
-      acc0 = fma(v0, scr_dlt[i], acc0);
-      acc1 = fma(v1, scr_dlt[i + 1], acc1);
-      acc2 = fma(v2, scr_dlt[i + 2], acc2);
-      acc3 = fma(v3, scr_dlt[i + 3], acc3);
-    }
-    for (; i < m0; ++i) acc0 = fma(__ldg(row + (long long)act0[i] * a.ldx), scr_dlt[i], acc0);
-    const double v = c.r[t0] - ((acc0 + acc1) + (acc2 + acc3));
-    c.r[t0] = v;
-    __stcg(a.r + t0, v);
-  }
-  if (tid == 0) {
-    sm->nact = m;
-    c.bc->npasses = r.npasses;
-    c.bc->visits = r.visits;
-    c.bc->accepted = r.accepted;
-    c.bc->maxH = r.maxH;
-    c.bc->conv = r.conv;
-    c.bc->nact = m;
-  }
-  __threadfence();
-  __syncthreads();
+  gram_publish(c, r, m0, act0, scr_b0, scr_dlt);
 }
 
 __device__ double shared_std(NCtx &c) { // Statistics.std(r), corrected, two-pass
