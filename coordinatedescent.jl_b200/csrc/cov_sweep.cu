@@ -329,6 +329,35 @@ struct CovPolicy {
   static __device__ __forceinline__ double apply(double g, double Gv, double h) { return __dadd_rn(g, __dmul_rn(Gv, h)); } // :343-345
 };
 
+// CTA 0 after an active phase: final list, dense beta, per-snapshot-entry delta (for refresh_slice), summary
+__device__ void engine_publish(Ctx &c, const chain::Result &r, int m0, const int *act0, const double *scr_b0, double *scr_dlt) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < m0; i += COV_T) a.beta[act0[i]] = 0.0;
+  __syncthreads();
+  for (int i = tid; i < r.m; i += COV_T) {
+    const int k = c.s_act[i];
+    const double be = c.e_be[i];
+    a.beta[k] = be;
+    a.act[i] = k;
+    a.actval[i] = be;
+  }
+  __syncthreads();
+  for (int i = tid; i < m0; i += COV_T) scr_dlt[i] = a.beta[act0[i]] - scr_b0[i];
+  if (tid == 0) {
+    sm->nact = r.m;
+    sm->bc.npasses = r.npasses;
+    sm->bc.visits = r.visits;
+    sm->bc.accepted = r.accepted;
+    sm->bc.maxH = r.maxH;
+    sm->bc.m0 = m0;
+    sm->bc.nact = r.m;
+    sm->bc.conv = r.conv;
+  }
+  __syncthreads();
+}
+
 __device__ void active_engine(Ctx &c, double lam, long long maxPasses, unsigned long long pass_counter) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
@@ -362,29 +391,7 @@ __device__ void active_engine(Ctx &c, double lam, long long maxPasses, unsigned 
   S.prof = a.prof ? a.prof + 16 : nullptr;
   const CovPolicy P{a.b, a.ainv, a.omega, lam};
   const chain::Result r = chain::run<COV_T>(S, P, 0.0, maxPasses, pass_counter, a.randomize == 0, a.seed, a.optTol, a.inlist);
-  // ---- publish: final list, dense beta, per-snapshot-entry delta
-  for (int i = tid; i < m0; i += COV_T) a.beta[act0[i]] = 0.0;
-  __syncthreads();
-  for (int i = tid; i < r.m; i += COV_T) {
-    const int k = c.s_act[i];
-    const double be = c.e_be[i];
-    a.beta[k] = be;
-    a.act[i] = k;
-    a.actval[i] = be;
-  }
-  __syncthreads();
-  for (int i = tid; i < m0; i += COV_T) scr_dlt[i] = a.beta[act0[i]] - scr_b0[i];
-  if (tid == 0) {
-    sm->nact = r.m;
-    sm->bc.npasses = r.npasses;
-    sm->bc.visits = r.visits;
-    sm->bc.accepted = r.accepted;
-    sm->bc.maxH = r.maxH;
-    sm->bc.m0 = m0;
-    sm->bc.nact = r.m;
-    sm->bc.conv = r.conv;
-  }
-  __syncthreads();
+  engine_publish(c, r, m0, act0, scr_b0, scr_dlt);
 }
 
 // The same phase with the chain engine spread over the whole cluster (chain_engine.cuh: run_multi), for active
@@ -430,30 +437,7 @@ __device__ void active_engine_multi(Ctx &c, double lam, long long maxPasses, uns
   cg::cluster_group &cl = c.cluster;
   const chain::Result r = chain::run_multi<COV_T>(S, X, P, [&cl]() { cl.sync(); }, 0.0, maxPasses, pass_counter,
                                                   a.randomize == 0, a.seed, a.optTol, a.inlist);
-  if (c.rank == 0) { // publish: final list, dense beta, per-snapshot-entry delta
-    for (int i = tid; i < m0; i += COV_T) a.beta[act0[i]] = 0.0;
-    __syncthreads();
-    for (int i = tid; i < r.m; i += COV_T) {
-      const int k = c.s_act[i];
-      const double be = c.e_be[i];
-      a.beta[k] = be;
-      a.act[i] = k;
-      a.actval[i] = be;
-    }
-    __syncthreads();
-    for (int i = tid; i < m0; i += COV_T) scr_dlt[i] = a.beta[act0[i]] - scr_b0[i];
-    if (tid == 0) {
-      sm->nact = r.m;
-      sm->bc.npasses = r.npasses;
-      sm->bc.visits = r.visits;
-      sm->bc.accepted = r.accepted;
-      sm->bc.maxH = r.maxH;
-      sm->bc.m0 = m0;
-      sm->bc.nact = r.m;
-      sm->bc.conv = r.conv;
-    }
-    __syncthreads();
-  }
+  if (c.rank == 0) engine_publish(c, r, m0, act0, scr_b0, scr_dlt);
 }
 
 // every CTA after the active phase: Ax[slice] += A[slice, act0] * dlt ; beta[slice] <- dense beta
