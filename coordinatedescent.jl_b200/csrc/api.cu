@@ -791,7 +791,9 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.stats = h->dstats;
     if (!h->dgram && !getenv("CDGPU_NAIVE_NO_GRAM_ENGINE")) CD_TRY(dalloc(&h->dgram, (size_t)2048 * 2048 + 2048));
     a.gram = getenv("CDGPU_NAIVE_NO_GRAM_ENGINE") ? nullptr : h->dgram;
-    a.multi_ok = getenv("CDGPU_NAIVE_MULTI") ? atoi(getenv("CDGPU_NAIVE_MULTI")) != 0 : 1;
+    a.multi_ok = 384; // smallest active set handed to the 16-CTA team engine (below: chain-bound on one CTA anyway)
+    if (const char *env = getenv("CDGPU_MULTI_MIN")) a.multi_ok = std::max(64, atoi(env));
+    if (const char *env = getenv("CDGPU_NAIVE_MULTI")) a.multi_ok = atoi(env) != 0 ? a.multi_ok : 0;
     a.scaled = rc.scaled;
     a.outerMaxIter = rc.outerMaxIter;
     a.outerTol = rc.outerTol;

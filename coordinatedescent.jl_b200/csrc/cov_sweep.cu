@@ -397,7 +397,8 @@ __device__ void active_engine(Ctx &c, double lam, long long maxPasses, unsigned 
 // The same phase with the chain engine spread over the whole cluster (chain_engine.cuh: run_multi), for active
 // sets of many 32-entry blocks: every CTA applies each block's steps to the entries it owns, one cluster barrier per
 // block.  Called by ALL CTAs; m is the list length read from CTA 0.
-constexpr int COV_MULTI_MIN = 160; // below this the single-CTA engine (no cluster barrier per block) is faster
+// c.multi_ok carries the smallest list length handed to the distributed engine (0: never).  Default 384: below that
+// the single-CTA engine is chain-bound anyway and saves the cluster barrier + L2 round trip per block.
 __device__ void active_engine_multi(Ctx &c, double lam, long long maxPasses, unsigned long long pass_counter, int m0) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           cluster.sync(); // CTA 0 has finished the list update
           m_all = *cluster.map_shared_rank(&c.sm->nact, 0);
         }
-        if (m_all >= COV_MULTI_MIN && m_all <= c.ecap) {
+        if (c.multi_ok > 0 && m_all >= c.multi_ok && m_all <= c.ecap) {
           active_engine_multi(c, lam, a.maxIter - iter, pass_counter, m_all);
         } else if (c.rank == 0) {
           const int m = c.sm->nact;
@@ -849,8 +850,9 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   if (!slice_in_smem) ecap = COV_ACT_CAP;
   size_t dyn = slice_in_smem ? fixed_for(ecap) + slices : fixed_for(ecap);
   // the distributed engine needs 8p + 80 scratch doubles behind the slices; CDGPU_COV_MULTI=0 switches it off
-  int multi_ok = a.p >= 64;
-  if (const char *env = getenv("CDGPU_COV_MULTI")) multi_ok = multi_ok && atoi(env) != 0;
+  int multi_ok = a.p >= 64 ? 384 : 0;
+  if (const char *env = getenv("CDGPU_MULTI_MIN")) multi_ok = multi_ok ? std::max(64, atoi(env)) : 0;
+  if (const char *env = getenv("CDGPU_COV_MULTI")) multi_ok = atoi(env) != 0 ? multi_ok : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C);
   cfg.blockDim = dim3(COV_T);

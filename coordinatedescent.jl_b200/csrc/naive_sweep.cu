@@ -689,7 +689,6 @@ __device__ void gram_engine(NCtx &c, double lam, long long maxPasses, unsigned l
 
 // The same phase with the chain engine spread over the whole cooperative grid (chain_engine.cuh: run_multi), for
 // active sets of many 32-entry blocks; called by ALL CTAs after the active Gram has been formed.
-constexpr int NV_MULTI_MIN = 160;
 constexpr int NV_MULTI_TEAM = 16; // CTAs that share the engine
 __device__ void gram_engine_multi(NCtx &c, double lam, long long maxPasses, unsigned long long pass_counter, int m0,
                                   const double *G, double *d0) {
@@ -885,7 +884,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
               __stcg(reinterpret_cast<unsigned *>(reinterpret_cast<int *>(hG0 + 72) + 2), 0u);
             }
             fast_grid_sync(c);
-            if (m_act >= NV_MULTI_MIN && a.multi_ok) {
+            if (a.multi_ok > 0 && m_act >= a.multi_ok) { // a.multi_ok: smallest list length for the team engine
               if (c.bid < NV_MULTI_TEAM) gram_engine_multi(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);
             } else if (c.bid == 0) {
               gram_engine(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);

@@ -307,9 +307,12 @@ def test_locpolyl1_wide_dense_active_sets(gpu, ref, form, randomize, monkeypatch
 
 @pytest.mark.parametrize("form", ["quad", "ls"])
 @pytest.mark.parametrize("randomize", [0, 1])
-def test_dense_active_set_retraces_oracle(gpu, ref, form, randomize):
+@pytest.mark.parametrize("engine", ["one_cta", "team"])
+def test_dense_active_set_retraces_oracle(gpu, ref, form, randomize, engine, monkeypatch):
     """Active sets of several 32-entry blocks (the blocked chain engine: panel updates, worker warps, drain,
-    a ragged last block): same passes / visits / list order as the oracle and the same iterate."""
+    a ragged last block): same passes / visits / list order as the oracle and the same iterate — on the single-CTA
+    engine and on the engine distributed over the cluster / the 16-CTA team (default only from 384 entries on)."""
+    monkeypatch.setenv("CDGPU_MULTI_MIN", "64" if engine == "team" else "100000")
     n, p, s = 300, 420, 30
     X, y, _ = gauss_problem(n, p, s, seed=91)
     A, b = X.T @ X / n, -X.T @ y / n
