@@ -127,7 +127,7 @@ __device__ __forceinline__ void st_async_16(uint32_t raddr, unsigned long long a
 template <bool PROF>
 __device__ __forceinline__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter, unsigned &round,
                                             long long &accepted, bool first_pass_of_kernel, int &nonapp_total,
-                                            long long *pf) {
+                                            long long *pf, int &m_bound) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -253,6 +253,7 @@ __device__ __forceinline__ double full_pass(Ctx &c, double lam, unsigned long lo
       a.act[sm->nact] = k;
       sm->nact += 1;
     }
+    if (!wmember) m_bound += 1; // every CTA: upper bound of the list length (dropzeros! can only shorten it)
     maxH = fmax(maxH, fabs(w.h));
     accepted += 1;
     cur = k;
@@ -546,6 +547,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   if (PROF && c.rank == 0 && tid < 8) a.prof[16 + tid] = 0;
   const long long t_start = PROF ? clock64() : 0;
   unsigned round = 0; // candidate-exchange rounds so far (selects slot parity and mbarrier phase)
+  int m_bound = *a.nact; // upper bound of the list length, the same in every CTA
   bool first_pass = true;
   unsigned long long pass_counter = 0;
   DevStats st;
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         const int m_old = c.sm->nact; // only meaningful on CTA 0
         const long long t0 = PROF ? clock64() : 0;
         const long long acc0 = st.accepted;
-        const double maxH = full_pass<PROF>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf);
+        const double maxH = full_pass<PROF>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf, m_bound);
         const long long t1 = PROF ? clock64() : 0;
         if (PROF) pf[0] += t1 - t0;
         if (PROF) pf[4] += st.accepted - acc0;
@@ -595,8 +597,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         }
       } else {
         const long long t0 = PROF ? clock64() : 0;
-        int m_all = 0; // list length, known to every CTA only when the distributed engine may be used
-        if (c.C > 1 && c.multi_ok) {
+        int m_all = 0; // list length, fetched from CTA 0 only when it may reach the distributed engine's size
+        if (c.C > 1 && c.multi_ok > 0 && m_bound >= c.multi_ok) {
           cluster.sync(); // CTA 0 has finished the list update
           m_all = *cluster.map_shared_rank(&c.sm->nact, 0);
         }
@@ -631,6 +633,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         st.accepted += b.accepted;
         st.maxH = b.maxH;
         conv = b.conv != 0;
+        m_bound = b.nact;
         // conv == 0 here means the pass budget ran out: the while condition ends the solve
       }
     }
@@ -638,6 +641,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
     if (c.rank == 0 && tid == 0) c.sm->bc.nact = c.sm->nact;
     cluster.sync();
     const int nnz = cluster.map_shared_rank(&c.sm->bc, 0)->nact;
+    m_bound = nnz;
     if (status) break;
     if (!a.accumulate) {
       if (c.rank == 0) {
