@@ -256,6 +256,7 @@ static int naive_check(cdgpu_handle *out, int loss_kind, const void *X, int64_t 
 
 API int cdgpu_naive_create(cdgpu_handle *out, int loss_kind, const double *X, int64_t n, int64_t p, int64_t ldx,
                            const double *y, const double *w, int device) {
+  return api_guard([&]() -> int {
   CD_TRY(naive_check(out, loss_kind, X, n, p, ldx, y, w));
   CD_TRY(cd_use_device(device));
   HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
@@ -283,10 +284,12 @@ API int cdgpu_naive_create(cdgpu_handle *out, int loss_kind, const double *X, in
   CD_TRY(naive_finish(h));
   *out = g.release();
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_naive_create_dev(cdgpu_handle *out, int loss_kind, const double *dX, int64_t n, int64_t p, int64_t ldx,
                                const double *dy, const double *dw, int device) {
+  return api_guard([&]() -> int {
   CD_TRY(naive_check(out, loss_kind, dX, n, p, ldx, dy, dw));
   CD_TRY(cd_use_device(device));
   HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
@@ -305,6 +308,7 @@ API int cdgpu_naive_create_dev(cdgpu_handle *out, int loss_kind, const double *d
   CD_TRY(naive_finish(h));
   *out = g.release();
   return CDGPU_OK;
+  });
 }
 
 static int quad_finish(cdgpu_handle_s *h, bool check_sym) {
@@ -325,6 +329,7 @@ static int quad_finish(cdgpu_handle_s *h, bool check_sym) {
 }
 
 API int cdgpu_quad_create(cdgpu_handle *out, const double *A, int64_t p, int64_t lda, const double *b, int device) {
+  return api_guard([&]() -> int {
   if (!out || !A || !b) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (p < 1 || lda < p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
@@ -349,10 +354,12 @@ API int cdgpu_quad_create(cdgpu_handle *out, const double *A, int64_t p, int64_t
   CD_TRY(quad_finish(h, true));
   *out = g.release();
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_quad_create_dev(cdgpu_handle *out, const double *dA, int64_t p, int64_t lda, const double *db,
                               int device) {
+  return api_guard([&]() -> int {
   if (!out || !dA || !db) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (p < 1 || lda < p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
@@ -372,6 +379,7 @@ API int cdgpu_quad_create_dev(cdgpu_handle *out, const double *dA, int64_t p, in
   CD_TRY(quad_finish(h, true));
   *out = g.release();
   return CDGPU_OK;
+  });
 }
 
 // A = X'X/n, b = -X'y/n on the device, wrapped as a QUAD handle
@@ -421,6 +429,7 @@ static int gram_build(cdgpu_handle *out, const double *dX, int64_t n_local, int6
 
 API int cdgpu_gram_create_dev(cdgpu_handle *out, const double *dX, int64_t n, int64_t p, int64_t ldx,
                               const double *dy, int device) {
+  return api_guard([&]() -> int {
   if (!out || !dX || !dy) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
@@ -429,20 +438,24 @@ API int cdgpu_gram_create_dev(cdgpu_handle *out, const double *dX, int64_t n, in
   CUDA_TRY(cudaDeviceSynchronize());
   tr.mark("use_device + device sync");
   return gram_build(out, dX, n, n, p, ldx, dy, device, nullptr, nullptr);
+  });
 }
 
 API int cdgpu_gram_create_sharded(cdgpu_handle *out, const double *dX_local, int64_t n_local, int64_t n_total,
                                   int64_t p, int64_t ldx, const double *dy_local, cdgpu_comm comm, int device) {
+  return api_guard([&]() -> int {
   if (!out || !dX_local || !dy_local) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (n_local < 1 || n_total < n_local || p < 1 || ldx < n_local) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
   CD_TRY(cd_use_device(device));
   CUDA_TRY(cudaDeviceSynchronize());
   return gram_build(out, dX_local, n_local, n_total, p, ldx, dy_local, device, comm, nullptr);
+  });
 }
 
 API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t p, int64_t ldx, const double *y,
                           int device) {
+  return api_guard([&]() -> int {
   if (!out || !X || !y) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
@@ -476,6 +489,7 @@ API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t
       cudaStreamSynchronize(cs);
       cudaStreamDestroy(cs);
     }
+    if (h->stream) cudaStreamSynchronize(h->stream); // queued SYRK launches may still read the staging buffers
     for (int i = 0; i < NCH; ++i)
       if (ev[i]) cudaEventDestroy(ev[i]);
     dfree(dXs);
@@ -542,6 +556,7 @@ API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t
   CD_TRY(quad_finish(h, false));
   *out = g.release();
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_dims(cdgpu_handle h, int64_t *n, int64_t *p, int *loss_kind) {
@@ -557,6 +572,7 @@ API int cdgpu_gram_ms(cdgpu_handle h, double *ms) {
   return CDGPU_OK;
 }
 API int cdgpu_quad_get(cdgpu_handle h, double *A_out, double *b_out) {
+  return api_guard([&]() -> int {
   if (!h || h->kind != CDGPU_LOSS_QUAD) return cdgpu_set_error(CDGPU_EARG, "not a CDQuadraticLoss handle");
   CUDA_TRY(cudaSetDevice(h->device));
   if (A_out)
@@ -564,6 +580,7 @@ API int cdgpu_quad_get(cdgpu_handle h, double *A_out, double *b_out) {
                           cudaMemcpyDeviceToHost));
   if (b_out) CUDA_TRY(cudaMemcpy(b_out, h->dy, h->p * sizeof(double), cudaMemcpyDeviceToHost));
   return CDGPU_OK;
+  });
 }
 
 // ---------------------------------------------------------------- solves --
@@ -834,6 +851,7 @@ static int lambda_max_dev(cdgpu_handle_s *h, const double *domega, double *out_h
 
 API int cdgpu_solve(cdgpu_handle h, double lambda0, const double *omega, const cdgpu_options *opt, double *nzval,
                     int64_t *nzval2ind, int64_t *nnz, cdgpu_stats *stats) {
+  return api_guard([&]() -> int {
   if (!h || !nzval || !nzval2ind || !nnz) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   CD_TRY(check_opts(opt));
   CUDA_TRY(cudaSetDevice(h->device));
@@ -870,11 +888,13 @@ API int cdgpu_solve(cdgpu_handle h, double lambda0, const double *omega, const c
     stats_to_abi(d, ms, stats);
   }
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_path(cdgpu_handle h, const double *lambda, int64_t m, const double *omega, const cdgpu_options *opt,
                    int64_t max_hat_s, int64_t capacity, int64_t *colptr, int64_t *rowval, double *nzval,
                    int64_t *m_done, cdgpu_stats *stats) {
+  return api_guard([&]() -> int {
   if (!h || !lambda || !colptr || !rowval || !nzval || !m_done) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (m < 0 || m > 0x7fffffff || capacity < 0) return cdgpu_set_error(CDGPU_EARG, "bad path length or capacity");
   CD_TRY(check_opts(opt));
@@ -938,6 +958,7 @@ API int cdgpu_path(cdgpu_handle h, const double *lambda, int64_t m, const double
   }
   *m_done = cols;
   return st;
+  });
 }
 
 // _findInitSigma! (utils.jl:60-77): the s columns most correlated with y (device: |X'y|), a tiny
@@ -1005,8 +1026,84 @@ static int screening_sigma(cdgpu_handle_s *h, int64_t sinit, double *sigma) {
   return CDGPU_OK;
 }
 
+// scaledLasso! with optionsCD.warmStart == false: every outer iteration is a cold coordinateDescent! (fill!(x,0) +
+// the numSteps continuation from lambda_max, coordinate_descent.jl:23-37 called from lasso.jl:132-133), so the sigma
+// loop cannot stay inside one launch: one launch per outer iteration, sigma from the device residual in between.
+static double host_std(const std::vector<double> &r) { // Statistics.std (corrected)
+  const size_t n = r.size();
+  double mean = 0.0, var = 0.0;
+  for (double v : r) mean += v;
+  mean /= (double)n;
+  for (double v : r) var += (v - mean) * (v - mean);
+  return sqrt(var / (double)(n - 1));
+}
+static int scaled_solve_cold(cdgpu_handle_s *h, double lambda, const double *domega, const cdgpu_iter_options *opt,
+                             double sigma0, double *nzval, int64_t *nzval2ind, int64_t *nnz, double *sigma_out,
+                             cdgpu_stats *stats) {
+  const size_t n = (size_t)h->n;
+  std::vector<double> r(n);
+  auto fetch_r = [&]() -> int {
+    CUDA_TRY(cudaMemcpyAsync(r.data(), h->dstate, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CDGPU_OK;
+  };
+  RunCfg cfg = {};
+  cfg.domega = domega;
+  cfg.accumulate = 1;
+  cfg.max_hat_s = -1;
+  double sigma = sigma0;
+  if (opt->initProcedure == CDGPU_INIT_WARMSTART) { // initialize!(f, x); sigma = std(f.r)   lasso.jl:124-126
+    cdgpu_options o0 = opt->optionsCD;
+    o0.maxIter = 0;
+    cfg.opt = &o0;
+    cfg.lambdas = &lambda;
+    cfg.nlambda = 1;
+    CD_TRY(run_sweeps(h, cfg));
+    CD_TRY(fetch_r());
+    sigma = host_std(r);
+  }
+  cfg.opt = &opt->optionsCD;
+  DevStats tot = {};
+  int outer = 0;
+  for (int64_t iter = 1; iter <= opt->maxIter; ++iter) {
+    outer = (int)iter;
+    CD_TRY(set_zero_iterate(h));
+    double lmax = 0.0;
+    CD_TRY(lambda_max_dev(h, domega, &lmax));
+    const std::vector<double> lams = continuation(lmax, lambda * sigma, opt->optionsCD.numSteps);
+    cfg.lambdas = lams.data();
+    cfg.nlambda = (int)lams.size();
+    CD_TRY(run_sweeps(h, cfg));
+    CD_TRY(flag_status(h, nullptr));
+    DevStats d;
+    CUDA_TRY(cudaMemcpy(&d, h->dstats, sizeof d, cudaMemcpyDeviceToHost));
+    tot.passes += d.passes;
+    tot.full_passes += d.full_passes;
+    tot.visits += d.visits;
+    tot.accepted += d.accepted;
+    tot.maxH = d.maxH;
+    tot.converged = d.converged;
+    CD_TRY(fetch_r());
+    double ss = 0.0;
+    for (double v : r) ss += v * v;
+    const double snew = sqrt(ss / (double)n); // lasso.jl:134
+    if (fabs(snew - sigma) / sigma < opt->optTol) break;
+    sigma = snew;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CD_TRY(download_iterate(h, nzval, nzval2ind, nnz));
+  tot.outer_iters = outer;
+  tot.sigma = sigma;
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (stats) stats_to_abi(tot, ms, stats);
+  if (sigma_out) *sigma_out = n > 1 ? host_std(r) : 0.0; // std(f.r)  lasso.jl:143
+  return CDGPU_OK;
+}
+
 API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, const cdgpu_iter_options *opt,
                            double *nzval, int64_t *nzval2ind, int64_t *nnz, double *sigma_out, cdgpu_stats *stats) {
+  return api_guard([&]() -> int {
   if (!h || !opt || !omega || !nzval || !nzval2ind || !nnz) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (h->kind != CDGPU_LOSS_LS)
     return cdgpu_set_error(CDGPU_EARG, "scaledLasso! needs a CDLeastSquaresLoss handle (lasso.jl:117)");
@@ -1022,6 +1119,8 @@ API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, c
   CD_TRY(rc);
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   CD_TRY(upload_iterate(h, nzval, nzval2ind, *nnz));
+  if (!opt->optionsCD.warmStart)
+    return scaled_solve_cold(h, lambda, domega, opt, sigma0, nzval, nzval2ind, nnz, sigma_out, stats);
   RunCfg cfg = {};
   cfg.opt = &opt->optionsCD;
   cfg.domega = domega;
@@ -1048,17 +1147,21 @@ API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, c
     *sigma_out = s[0];
   }
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_state(cdgpu_handle h, double *out) {
+  return api_guard([&]() -> int {
   if (!h || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   CUDA_TRY(cudaSetDevice(h->device));
   const size_t cnt = (size_t)(h->kind == CDGPU_LOSS_QUAD ? h->p : h->n);
   CUDA_TRY(cudaMemcpy(out, h->dstate, cnt * sizeof(double), cudaMemcpyDeviceToHost));
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_stdx(cdgpu_handle h, const double *w, double *out) {
+  return api_guard([&]() -> int {
   if (!h || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   CUDA_TRY(cudaSetDevice(h->device));
   if (h->kind == CDGPU_LOSS_QUAD) { // A = X'X/n  =>  _stdX!(X)_j = sqrt(A_jj)
@@ -1079,12 +1182,14 @@ API int cdgpu_stdx(cdgpu_handle h, const double *w, double *out) {
   CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return CDGPU_OK;
+  });
 }
 
 // refitLassoPath (lasso.jl:208-225): coefficients of the least-squares fit on the columns `support` (1-based, ns of
 // them) of the handle's design: X[:, S] \ y for a naive-form handle ([W]-weighted for CDWeightedLSLoss), the
 // equivalent A[S,S] \ (-b[S]) for a covariance-form handle.  Normal equations + Cholesky on the device.
 API int cdgpu_refit(cdgpu_handle h, const int64_t *support, int64_t ns, double *coef_out) {
+  return api_guard([&]() -> int {
   if (!h || (ns > 0 && (!support || !coef_out))) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (ns < 0 || ns > h->p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (ns == 0) return CDGPU_OK;
@@ -1108,13 +1213,16 @@ API int cdgpu_refit(cdgpu_handle h, const int64_t *support, int64_t ns, double *
   CUDA_TRY(cudaMemsetAsync(h->dflag, 0, sizeof(int), h->stream));
   if (flag) return cdgpu_set_error(CDGPU_EARG, "SingularException: the selected columns are not linearly independent");
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_lambda_max(cdgpu_handle h, const double *omega, double *out) {
+  return api_guard([&]() -> int {
   if (!h || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   CUDA_TRY(cudaSetDevice(h->device));
   int rc;
   const double *domega = upload_omega(h, omega, &rc);
   CD_TRY(rc);
   return lambda_max_dev(h, domega, out);
+  });
 }

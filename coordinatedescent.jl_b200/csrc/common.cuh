@@ -21,6 +21,21 @@ int cdgpu_set_error(int code, const char *fmt, ...);
     if (_rc) return _rc;   \
   } while (0)
 
+// No C++ exception crosses the C ABI (include/cdgpu.h): every entry point that can allocate runs inside this guard.
+#ifdef __cplusplus
+#include <new>
+template <class F>
+static inline int api_guard(F &&f) noexcept {
+  try {
+    return f();
+  } catch (const std::bad_alloc &) {
+    return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+  } catch (...) {
+    return cdgpu_set_error(CDGPU_ECUDA, "unexpected C++ exception inside libcdgpu");
+  }
+}
+#endif
+
 // ------------------------------------------------------------ device math --
 // ProximalBase.shrink: comparison based, NaN -> 0 (oracle/cdref.c: shrink)
 __device__ __forceinline__ double cd_shrink(double v, double c) { return v > c ? v - c : (v < -c ? v + c : 0.0); }

@@ -796,18 +796,19 @@ int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, in
 }
 
 int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
-  static bool attr_done = false;
+  static bool attr_done[64] = {false}; // function attributes are per device (context), not per process
+  const bool known_dev = h->device >= 0 && h->device < 64;
   auto fixed_for = [](int ecap) {
     return (sizeof(Smem) + 15) / 16 * 16 + chain::STAGE_DOUBLES * sizeof(double) + (size_t)ecap * (2 * sizeof(double) + sizeof(int) + 2 * sizeof(unsigned short));
   };
   const size_t fixed = fixed_for(COV_ACT_CAP);
   const size_t max_dyn = 227 * 1024;
-  if (!attr_done) {
+  if (!known_dev || !attr_done[h->device]) {
     CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
     CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
     CUDA_TRY(cudaFuncSetAttribute(cov_path_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_done = true;
+    if (known_dev) attr_done[h->device] = true;
   }
   // largest cluster the device will co-schedule (16 on B200 with the opt-in, else 8)
   static int dev_max_cluster[64] = {0}; // per device: the occupancy query is not free

@@ -1087,11 +1087,12 @@ int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a) {
 }
 
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
-  static bool attr_done = false;
+  static bool attr_done[64] = {false}; // function attributes are per device (context), not per process
   const size_t max_dyn = 227 * 1024;
-  if (!attr_done) {
+  const bool known = h->device >= 0 && h->device < 64;
+  if (!known || !attr_done[h->device]) {
     CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
-    attr_done = true;
+    if (known) attr_done[h->device] = true;
   }
   // shared memory: r (and w) + the state of the covariance-form active engine, whose capacity shrinks
   // (down to 0 = disabled, CTA 0 then runs active passes column by column) as n grows

@@ -56,6 +56,7 @@ struct cdgpu_comm_s {
 };
 
 API int cdgpu_comm_unique_id(void *id128) {
+  return api_guard([&]() -> int {
   if (!id128) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   CD_TRY(load_nccl());
   ncclUniqueId id;
@@ -63,9 +64,11 @@ API int cdgpu_comm_unique_id(void *id128) {
   if (r) return nccl_fail("ncclGetUniqueId", r);
   memcpy(id128, &id, sizeof id);
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_comm_init(cdgpu_comm *c, const void *id128, int rank, int nranks, int device) {
+  return api_guard([&]() -> int {
   if (!c || !id128) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (nranks < 1 || rank < 0 || rank >= nranks) return cdgpu_set_error(CDGPU_EARG, "bad rank / nranks");
   CD_TRY(load_nccl());
@@ -83,6 +86,7 @@ API int cdgpu_comm_init(cdgpu_comm *c, const void *id128, int rank, int nranks, 
   }
   *c = cc;
   return CDGPU_OK;
+  });
 }
 
 API int cdgpu_comm_destroy(cdgpu_comm c) {

@@ -1362,6 +1362,7 @@ static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, con
 API int cdgpu_vc_lvocv(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y, int degree,
                        const double *hArr, int64_t numH, int kernel_kind, double lambda0, const cdgpu_options *opt,
                        int64_t q_begin, int64_t q_end, int device, double *sqerr, cdgpu_stats *stats) {
+  return api_guard([&]() -> int {
   if (!X || !z || !y || !hArr || !opt || !sqerr) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   const int64_t m = numH * n;
   if (n < 2 || p < 1 || ldx < n || degree < 0 || numH < 0 || q_begin < 0 || q_end > m || q_begin > q_end)
@@ -1382,21 +1383,26 @@ API int cdgpu_vc_lvocv(const double *X, int64_t n, int64_t p, int64_t ldx, const
   if (q_begin == q_end) return CDGPU_OK;
   return vc_solve_moment(X, n, p, ldx, z, y, nullptr, m, q_begin, q_end, degree, kernel_kind, 0.0, lambda0, opt, device, nullptr,
                          nullptr, stats, hArr, sqerr);
+  });
 }
 API int cdgpu_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                        const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                        double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
                        cdgpu_stats *stats) {
+  return api_guard([&]() -> int {
   return vc_solve_impl(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt, device, out,
                        nullptr, stats);
+  });
 }
 API int cdgpu_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                              const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                              double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
                              double *outR, cdgpu_stats *stats) {
+  return api_guard([&]() -> int {
   if (!outR) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   return vc_solve_impl(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt, device, out,
                        outR, stats);
+  });
 }
 static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                          const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
