@@ -125,6 +125,8 @@ def run_step(lib, be, make_handle, cfg, opts):
     path = be.LassoPath(None, None, lams, opts, standardizeX=om, loss=f)
     t3 = time.perf_counter()
     gram_ms = f.gram_ms
+    if os.environ.get("CDGPU_BENCH_VERBOSE") and os.environ.get("CDGPU_BENCH_LAZY"):
+        print("lazy:", f.lazy_stats(), file=sys.stderr)
     f.close()
     t4 = time.perf_counter()
     if os.environ.get("CDGPU_BENCH_VERBOSE"):
@@ -323,14 +325,16 @@ def main():
         f = cdgpu.CDQuadraticLoss.__new__(cdgpu.CDQuadraticLoss)
         cdgpu.api._Loss.__init__(f, lib)
         f.p = p
-        lib.check(lib.gram_create_dev(C.byref(f._h), C.c_void_p(Xd.data_ptr()), n, p, n, C.c_void_p(yd.data_ptr()), local))
+        mk = lib.gram_create_lazy_dev if os.environ.get("CDGPU_BENCH_LAZY") else lib.gram_create_dev
+        lib.check(mk(C.byref(f._h), C.c_void_p(Xd.data_ptr()), n, p, n, C.c_void_p(yd.data_ptr()), local))
         return f
 
     def handle_host():
         f = cdgpu.CDQuadraticLoss.__new__(cdgpu.CDQuadraticLoss)
         cdgpu.api._Loss.__init__(f, lib)
         f.p = p
-        lib.check(lib.gram_create(C.byref(f._h), C.c_void_p(Xp.data_ptr()), n, p, n, C.c_void_p(yp.data_ptr()), local))
+        mk = lib.gram_create_lazy if os.environ.get("CDGPU_BENCH_LAZY") else lib.gram_create
+        lib.check(mk(C.byref(f._h), C.c_void_p(Xp.data_ptr()), n, p, n, C.c_void_p(yp.data_ptr()), local))
         return f
 
     def barrier():

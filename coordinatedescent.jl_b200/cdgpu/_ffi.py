@@ -124,6 +124,11 @@ _SIGS_GPU_ONLY = {
     "comm_unique_id": (C.c_int, [C.c_void_p]),
     "comm_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "comm_destroy": (C.c_int, [C.c_void_p]),
+    "gram_create_lazy": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                   C.c_int]),
+    "gram_create_lazy_dev": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                       C.c_int]),
+    "lazy_stats": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_int64_p, c_double_p]),
     "gram_create_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_int]),
 }

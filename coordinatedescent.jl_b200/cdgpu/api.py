@@ -280,16 +280,23 @@ class CDQuadraticLoss(_Loss):
         lib.check(lib.quad_create(C.byref(self._h), ptr(A), self.p, self.p, ptr(b), device))
 
     @classmethod
-    def from_data(cls, lib, X, y, device=0):
-        """A = X'X/n, b = -X'y/n formed by the library (FP64 tensor-core SYRK)."""
+    def from_data(cls, lib, X, y, device=0, lazy=False):
+        """A = X'X/n, b = -X'y/n formed by the library (FP64 tensor-core SYRK).  lazy=True: only diag(A) and b up
+        front, columns of A on demand (cdgpu_gram_create_lazy)."""
         self = cls.__new__(cls)
         _Loss.__init__(self, lib)
         X, y = f64(X), f64(y)
         if X.ndim != 2 or y.shape != (X.shape[0],):
             raise DimensionMismatch()
         self.p = X.shape[1]
-        lib.check(lib.gram_create(C.byref(self._h), ptr(X), X.shape[0], self.p, X.shape[0], ptr(y), device))
+        create = lib.gram_create_lazy if lazy else lib.gram_create
+        lib.check(create(C.byref(self._h), ptr(X), X.shape[0], self.p, X.shape[0], ptr(y), device))
         return self
+
+    def lazy_stats(self):
+        cols, nb, npause, ms = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
+        self.lib.check(self.lib.lazy_stats(self._h, C.byref(cols), C.byref(nb), C.byref(npause), C.byref(ms)))
+        return {"columns": cols.value, "batches": nb.value, "pauses": npause.value, "form_ms": ms.value}
 
     def stdX(self) -> np.ndarray:
         """sqrt(diag(A)) == _stdX!(X) when A = X'X/n (utils.jl:127-138)."""
@@ -333,8 +340,8 @@ class Backend:
     def CDQuadraticLoss(self, A, b):
         return CDQuadraticLoss(self.lib, A, b, device=self.device)
 
-    def CDQuadraticLoss_from_data(self, X, y):
-        return CDQuadraticLoss.from_data(self.lib, X, y, device=self.device)
+    def CDQuadraticLoss_from_data(self, X, y, lazy=False):
+        return CDQuadraticLoss.from_data(self.lib, X, y, device=self.device, lazy=lazy)
 
     # coordinateDescent!(x, f, g, options)          coordinate_descent.jl:7-39
     def coordinateDescent_(self, x: SparseIterate, f: _Loss, g: ProxL1, options: CDOptions = None):

@@ -214,6 +214,16 @@ API int cdgpu_destroy(cdgpu_handle h) {
   dfree(h->dcolptr);
   dfree(h->drowval);
   dfree(h->dnzval);
+  if (h->own_lzX) dfree(const_cast<double *>(h->lzX));
+  if (h->own_lzy) dfree(const_cast<double *>(h->lzy));
+  dfree(h->dslot);
+  dfree(h->ddiag);
+  dfree(h->dgather);
+  dfree(h->dresume);
+  dfree(h->dbatch);
+  delete[] h->hslot;
+  if (h->lz_ev0) cudaEventDestroy(h->lz_ev0);
+  if (h->lz_ev1) cudaEventDestroy(h->lz_ev1);
   if (h->stream) stream_set_release(h->device, StreamSet{h->stream, h->ev0, h->ev1});
   delete h;
   return CDGPU_OK;
@@ -559,6 +569,228 @@ API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t
   });
 }
 
+// ------------------------------------------------------- lazy covariance form --
+// (lazy_gram.cu) diag(A) and b up front, columns of A = X'X/n formed on demand in batches of 128 by the DMMA GEMM.
+static const int LZ_BATCH = 128;
+
+static int lazy_alloc(cdgpu_handle_s *h, int64_t n, int64_t p, int device) {
+  h->kind = CDGPU_LOSS_QUAD;
+  h->device = device;
+  h->n = p;
+  h->p = p;
+  h->ld = (p + 1) & ~(int64_t)1;
+  h->lazy = true;
+  h->lz_n = n;
+  CD_TRY(handle_common_alloc(h));
+  int64_t cap = 4096;
+  if (const char *env = getenv("CDGPU_LAZY_CAP")) cap = std::max<int64_t>(LZ_BATCH, atoll(env));
+  cap = std::min<int64_t>((p + LZ_BATCH - 1) / LZ_BATCH * LZ_BATCH, cap / LZ_BATCH * LZ_BATCH);
+  // keep the cache below ~1/4 of the full matrix' footprint for wide problems and below 8 GiB in any case
+  while (cap > LZ_BATCH && (size_t)h->ld * (size_t)cap * sizeof(double) > ((size_t)8 << 30)) cap -= LZ_BATCH;
+  h->lz_cap = (int)cap;
+  h->lz_used = 0;
+  CD_TRY(dalloc(&h->dX, (size_t)h->ld * (size_t)cap));
+  h->ownX = true;
+  CD_TRY(dalloc(&h->dy, (size_t)p));
+  h->owny = true;
+  CD_TRY(dalloc(&h->dstate, (size_t)p));
+  CD_TRY(dalloc(&h->daux, (size_t)p));
+  CD_TRY(dalloc(&h->ddiag, (size_t)p));
+  CD_TRY(dalloc(&h->dslot, (size_t)p));
+  CD_TRY(dalloc(&h->dbatch, (size_t)LZ_BATCH));
+  CD_TRY(dalloc(&h->dresume, (size_t)1));
+  h->lz_ldb = (n + 1) & ~(int64_t)1;
+  CD_TRY(dalloc(&h->dgather, (size_t)h->lz_ldb * (size_t)LZ_BATCH));
+  h->hslot = new int[(size_t)p];
+  std::fill(h->hslot, h->hslot + p, -1);
+  CUDA_TRY(cudaEventCreate(&h->lz_ev0));
+  CUDA_TRY(cudaEventCreate(&h->lz_ev1));
+  CUDA_TRY(cudaMemsetAsync(h->dstate, 0, (size_t)p * sizeof(double), h->stream)); // Ax = zeros(p) :307
+  CUDA_TRY(cudaMemsetAsync(h->dresume, 0, sizeof(CovResume), h->stream));
+  CD_TRY(launch_fill_int(h, h->dslot, (int)p, -1));
+  return CDGPU_OK;
+}
+
+// form the columns `cols` (distinct, not yet cached, at most the free capacity) : gather -> DMMA GEMM -> cache slots
+static int lazy_form(cdgpu_handle_s *h, const std::vector<int> &cols) {
+  const int64_t p = h->p, n = h->lz_n;
+  for (size_t off = 0; off < cols.size(); off += LZ_BATCH) {
+    const int nb = (int)std::min<size_t>(LZ_BATCH, cols.size() - off);
+    if (h->lz_used + nb > h->lz_cap) return cdgpu_set_error(CDGPU_ECAP, "lazy covariance cache is full");
+    CUDA_TRY(cudaMemcpyAsync(h->dbatch, cols.data() + off, (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CD_TRY(launch_gather_cols(h, h->lzX, h->lz_ldx, n, h->dbatch, nb, nb, h->dgather, h->lz_ldb, h->dslot, h->lz_used));
+    CD_TRY(launch_gemm_tn_split(h->stream, h->sm_count, h->lzX, (int)p, h->lz_ldx, h->dgather, nb, h->lz_ldb, n,
+                                h->dX + (size_t)h->lz_used * (size_t)h->ld, h->ld, (double)n));
+    for (int q = 0; q < nb; ++q) h->hslot[cols[off + (size_t)q]] = h->lz_used + q;
+    h->lz_used += nb;
+    h->lz_batches += 1;
+  }
+  return CDGPU_OK;
+}
+
+// make sure the columns `need` exist; fill the batch up with the best-scoring candidates (|Ax_j + b_j| / omega_j)
+static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const double *domega, bool speculate) {
+  std::vector<int> cols;
+  std::vector<unsigned char> taken;
+  for (int k : need)
+    if (h->hslot[k] < 0 && std::find(cols.begin(), cols.end(), k) == cols.end()) cols.push_back(k);
+  if (cols.empty() && !speculate) return CDGPU_OK;
+  const int free_slots = h->lz_cap - h->lz_used;
+  if ((int)cols.size() > free_slots)
+    return cdgpu_set_error(CDGPU_ECAP, "active set needs more columns than the lazy covariance cache holds (%d); use the "
+                                       "eager form (cdgpu_gram_create) or raise CDGPU_LAZY_CAP", h->lz_cap);
+  int target = (int)((cols.size() + LZ_BATCH - 1) / LZ_BATCH * LZ_BATCH);
+  if (target == 0) target = LZ_BATCH;
+  target = std::min(target, free_slots);
+  if (speculate && (int)cols.size() < target) {
+    const int64_t p = h->p;
+    double *dscore = h->dscr + 3 * (size_t)p; // [3p, 4p): free between launches
+    CD_TRY(launch_lazy_score(h, h->dstate, h->dy, domega, h->dslot, (int)p, dscore));
+    std::vector<double> sc((size_t)p);
+    CUDA_TRY(cudaMemcpyAsync(sc.data(), dscore, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int k : cols) sc[(size_t)k] = -1.0;
+    const int want = target - (int)cols.size();
+    std::vector<int> idx((size_t)p);
+    for (int64_t j = 0; j < p; ++j) idx[(size_t)j] = (int)j;
+    const int take = (int)std::min<int64_t>(want, p);
+    std::partial_sort(idx.begin(), idx.begin() + take, idx.end(), [&](int a_, int b_) {
+      return sc[(size_t)a_] > sc[(size_t)b_] || (sc[(size_t)a_] == sc[(size_t)b_] && a_ < b_);
+    });
+    for (int q = 0; q < take; ++q)
+      if (sc[(size_t)idx[(size_t)q]] > 0.0) cols.push_back(idx[(size_t)q]);
+  }
+  if (cols.empty()) return CDGPU_OK;
+  CUDA_TRY(cudaEventRecord(h->lz_ev0, h->stream));
+  CD_TRY(lazy_form(h, cols));
+  CUDA_TRY(cudaEventRecord(h->lz_ev1, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->lz_ev0, h->lz_ev1));
+  h->lz_form_ms += ms;
+  return CDGPU_OK;
+}
+
+static int lazy_finish(cdgpu_handle_s *h) { // diag, b, 1/diag from the resident data
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  CD_TRY(launch_diag_xty(h, h->lzX, h->lz_n, (int)h->p, h->lz_ldx, h->lzy, (double)h->lz_n, h->ddiag, h->dy, h->daux, 0, 1));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->gram_ms = ms;
+  return CDGPU_OK;
+}
+
+API int cdgpu_gram_create_lazy_dev(cdgpu_handle *out, const double *dX, int64_t n, int64_t p, int64_t ldx,
+                                   const double *dy, int device) {
+  return api_guard([&]() -> int {
+    if (!out || !dX || !dy) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+    if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+    if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
+    CD_TRY(cd_use_device(device));
+    CUDA_TRY(cudaDeviceSynchronize()); // the caller's stream may still be producing X / y
+    HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
+    cdgpu_handle_s *h = g.h;
+    if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+    CD_TRY(lazy_alloc(h, n, p, device));
+    h->lzX = dX;
+    h->lzy = dy;
+    h->lz_ldx = ldx;
+    CD_TRY(lazy_finish(h));
+    *out = g.release();
+    return CDGPU_OK;
+  });
+}
+
+API int cdgpu_gram_create_lazy(cdgpu_handle *out, const double *X, int64_t n, int64_t p, int64_t ldx, const double *y,
+                               int device) {
+  return api_guard([&]() -> int {
+    if (!out || !X || !y) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+    if (n < 1 || p < 1 || ldx < n) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
+    if (p > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "p must fit in 31 bits");
+    CD_TRY(cd_use_device(device));
+    HandleGuard g{new (std::nothrow) cdgpu_handle_s()};
+    cdgpu_handle_s *h = g.h;
+    if (!h) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+    CD_TRY(lazy_alloc(h, n, p, device));
+    // the data stay resident (columns are formed from them later): one owned copy, 16-byte aligned columns
+    const int64_t ld = (n + 1) & ~(int64_t)1;
+    double *dXs = nullptr, *dys = nullptr;
+    CD_TRY(dalloc(&dXs, (size_t)ld * (size_t)p));
+    h->lzX = dXs;
+    h->own_lzX = true;
+    CD_TRY(dalloc(&dys, (size_t)n));
+    h->lzy = dys;
+    h->own_lzy = true;
+    h->lz_ldx = ld;
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    if (ld != n) CUDA_TRY(cudaMemsetAsync(dXs, 0, (size_t)ld * p * sizeof(double), h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dys, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // column blocks: the diag / X'y pass of a block runs while the next block is still on the wire
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev[16] = {nullptr};
+    int nev = 0;
+    auto cleanup = [&]() {
+      if (cs) {
+        cudaStreamSynchronize(cs);
+        cudaStreamDestroy(cs);
+      }
+      cudaStreamSynchronize(h->stream);
+      for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+    };
+    cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cdgpu_set_error(CDGPU_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    {
+      cudaEvent_t e0;
+      cudaEventCreateWithFlags(&e0, cudaEventDisableTiming);
+      cudaEventRecord(e0, h->stream);
+      cudaStreamWaitEvent(cs, e0, 0); // memset / y copy first
+      cudaEventDestroy(e0);
+    }
+    const int NBLK = (int)std::min<int64_t>(16, std::max<int64_t>(1, p / 512));
+    int rc = CDGPU_OK;
+    for (int bi = 0; bi < NBLK && rc == CDGPU_OK; ++bi) {
+      const int64_t c0 = p * bi / NBLK, c1 = p * (bi + 1) / NBLK;
+      if (c1 <= c0) continue;
+      e = cudaMemcpy2DAsync(dXs + c0 * ld, ld * sizeof(double), X + c0 * ldx, ldx * sizeof(double), n * sizeof(double),
+                            (size_t)(c1 - c0), cudaMemcpyHostToDevice, cs);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[nev], cudaEventDisableTiming);
+      if (e == cudaSuccess) {
+        nev += 1;
+        e = cudaEventRecord(ev[nev - 1], cs);
+      }
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, ev[nev - 1], 0);
+      if (e != cudaSuccess) {
+        rc = cdgpu_set_error(CDGPU_ECUDA, "H2D staging: %s", cudaGetErrorString(e));
+        break;
+      }
+      rc = launch_diag_xty(h, dXs + c0 * ld, n, (int)(c1 - c0), ld, dys, (double)n, h->ddiag + c0, h->dy + c0, h->daux + c0, 0, 1);
+    }
+    if (rc == CDGPU_OK) {
+      e = cudaEventRecord(h->ev1, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) rc = cdgpu_set_error(CDGPU_ECUDA, "lazy create: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    CD_TRY(rc);
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->gram_ms = ms; // includes the H2D staging
+    *out = g.release();
+    return CDGPU_OK;
+  });
+}
+
+API int cdgpu_lazy_stats(cdgpu_handle h, int64_t *columns, int64_t *batches, int64_t *pauses, double *form_ms) {
+  if (!h) return cdgpu_set_error(CDGPU_EARG, "null handle");
+  if (columns) *columns = h->lz_used;
+  if (batches) *batches = h->lz_batches;
+  if (pauses) *pauses = h->lz_pauses;
+  if (form_ms) *form_ms = h->lz_form_ms;
+  return CDGPU_OK;
+}
+
 API int cdgpu_dims(cdgpu_handle h, int64_t *n, int64_t *p, int *loss_kind) {
   if (!h) return cdgpu_set_error(CDGPU_EARG, "null handle");
   if (n) *n = h->n;
@@ -575,7 +807,19 @@ API int cdgpu_quad_get(cdgpu_handle h, double *A_out, double *b_out) {
   return api_guard([&]() -> int {
   if (!h || h->kind != CDGPU_LOSS_QUAD) return cdgpu_set_error(CDGPU_EARG, "not a CDQuadraticLoss handle");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (A_out)
+  if (A_out && h->lazy) { // Julia's f.A on a lazy handle: form the whole matrix once, into a temporary
+    double *dA = nullptr, *dc = nullptr;
+    CD_TRY(dalloc(&dA, (size_t)h->ld * (size_t)h->p + (size_t)h->p));
+    dc = dA + (size_t)h->ld * (size_t)h->p;
+    int rcg = launch_gram(h, h->lzX, h->lz_n, (int)h->p, h->lz_ldx, h->lzy, dA, dc, (double)h->lz_n, 1);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (rcg == CDGPU_OK && e == cudaSuccess)
+      e = cudaMemcpy2D(A_out, h->p * sizeof(double), dA, h->ld * sizeof(double), h->p * sizeof(double), h->p,
+                       cudaMemcpyDeviceToHost);
+    dfree(dA);
+    CD_TRY(rcg);
+    CUDA_TRY(e);
+  } else if (A_out)
     CUDA_TRY(cudaMemcpy2D(A_out, h->p * sizeof(double), h->dX, h->ld * sizeof(double), h->p * sizeof(double), h->p,
                           cudaMemcpyDeviceToHost));
   if (b_out) CUDA_TRY(cudaMemcpy(b_out, h->dy, h->p * sizeof(double), cudaMemcpyDeviceToHost));
@@ -755,8 +999,43 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.stats = h->dstats;
     const bool prof = getenv("CDGPU_PROFILE") != nullptr;
     a.prof = prof ? reinterpret_cast<long long *>(h->dscr + 11 * (size_t)h->p) : nullptr;
-    CD_TRY(launch_cov_init(h, a.A, a.lda, a.p, a.act, a.actval, a.nact, a.Ax, a.beta, a.inlist));
+    a.events_only = getenv("CDGPU_COV_EVENTS") != nullptr && atoi(getenv("CDGPU_COV_EVENTS")) != 0;
+    if (h->lazy) {
+      // columns of the members handed in (warm start) must exist; a fresh handle also forms its first batch now: the
+      // coordinates with the largest |b_j|/omega_j are the ones that enter first along a path
+      a.colslot = h->dslot;
+      a.resume = h->dresume;
+      h->lz_batches = h->lz_pauses = 0;
+      h->lz_form_ms = 0.0;
+      int m0 = 0;
+      CUDA_TRY(cudaMemcpyAsync(&m0, h->dnact, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      std::vector<int> need((size_t)m0);
+      if (m0) {
+        CUDA_TRY(cudaMemcpyAsync(need.data(), h->dact, (size_t)m0 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+      }
+      CD_TRY(lazy_ensure(h, need, rc.domega, h->lz_used == 0 && !getenv("CDGPU_LAZY_NO_PREFETCH")));
+      CUDA_TRY(cudaMemsetAsync(h->dresume, 0, sizeof(CovResume), h->stream));
+    }
+    CD_TRY(launch_cov_init(h, a.A, a.lda, a.p, a.act, a.actval, a.nact, a.Ax, a.beta, a.inlist, a.colslot));
     CD_TRY(launch_cov_path(h, a));
+    while (h->lazy) { // paused at an entering coordinate without a column: form a batch, resume
+      int f[2] = {0, 0};
+      CUDA_TRY(cudaMemcpyAsync(f, h->dflag, sizeof f, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      if (f[0] != 3) break;
+      CovResume R;
+      CUDA_TRY(cudaMemcpy(&R, h->dresume, sizeof R, cudaMemcpyDeviceToHost));
+      if (R.need_k < 0 || R.need_k >= h->p) return cdgpu_set_error(CDGPU_ECUDA, "lazy covariance: bad column request %d", R.need_k);
+      h->lz_pauses += 1;
+      std::vector<int> need(1, R.need_k);
+      CD_TRY(lazy_ensure(h, need, rc.domega, !getenv("CDGPU_LAZY_NO_PREFETCH")));
+      const int one = 1;
+      CUDA_TRY(cudaMemcpyAsync(&h->dresume->valid, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream)); // `one` is a stack temporary
+      CD_TRY(launch_cov_path(h, a));
+    }
     if (prof) {
       long long pf[24];
       CUDA_TRY(cudaMemcpyAsync(pf, a.prof, sizeof pf, cudaMemcpyDeviceToHost, h->stream));
@@ -1167,7 +1446,10 @@ API int cdgpu_stdx(cdgpu_handle h, const double *w, double *out) {
   if (h->kind == CDGPU_LOSS_QUAD) { // A = X'X/n  =>  _stdX!(X)_j = sqrt(A_jj)
     if (w) return cdgpu_set_error(CDGPU_EARG, "weighted _stdX! needs a naive-form handle");
     double *dout = h->dscr + 8;
-    CD_TRY(launch_diag_sqrt(h, h->dX, h->ld, (int)h->p, dout));
+    if (h->lazy)
+      CD_TRY(launch_sqrt_vec(h, h->ddiag, (int)h->p, dout));
+    else
+      CD_TRY(launch_diag_sqrt(h, h->dX, h->ld, (int)h->p, dout));
     CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)h->p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return CDGPU_OK;
@@ -1204,7 +1486,17 @@ API int cdgpu_refit(cdgpu_handle h, const int64_t *support, int64_t ns, double *
   int *dS = h->discr; // 8p ints of scratch
   CUDA_TRY(cudaMemcpyAsync(dS, s0.data(), (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream)); // s0 is a host temporary
-  CD_TRY(launch_refit(h, dS, (int)ns, h->dgram, h->dflag));
+  if (h->lazy) { // covariance columns may be missing: the same normal equations straight from the resident data
+    cdgpu_handle_s t = *h;
+    t.kind = CDGPU_LOSS_LS;
+    t.dX = const_cast<double *>(h->lzX);
+    t.ld = h->lz_ldx;
+    t.n = h->lz_n;
+    t.dy = const_cast<double *>(h->lzy);
+    CD_TRY(launch_refit(&t, dS, (int)ns, h->dgram, h->dflag));
+  } else {
+    CD_TRY(launch_refit(h, dS, (int)ns, h->dgram, h->dflag));
+  }
   const int ld = ((int)ns + 1) & ~1;
   int flag = 0;
   CUDA_TRY(cudaMemcpyAsync(coef_out, h->dgram + (size_t)ld * ns, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

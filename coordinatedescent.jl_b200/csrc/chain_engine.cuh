@@ -51,6 +51,9 @@ struct State {
   const double *G;             // symmetric; G(t,i) = G[row[t] + row[i]*ldg]
   long long ldg;
   long long *prof; // optional [8]: cycles of thread 0 (panel, chain, barrier wait, pass ends) and thread 32 (stage, apply, barrier wait), blocks
+  const int *slot = nullptr; // optional: column r of G lives at G + slot[r]*ldg (lazily formed covariance columns); null: r
+  double *hout = nullptr; // optional [cap]: ONE-PASS mode (run() only, ordered, maxPasses = 1): the step h of every entry is
+                          // recorded here and dropzeros! is left to the caller (the member chain of a FULL pass, cov_sweep.cu)
 };
 
 struct Result {
@@ -60,6 +63,9 @@ struct Result {
 };
 
 __device__ __forceinline__ double ld_l2(const double *p) { return __ldcg(p); }
+// start of column r of G
+__device__ __forceinline__ int gcolidx(const State &S, int r) { return S.slot ? __ldg(S.slot + r) : r; }
+__device__ __forceinline__ const double *gcol(const State &S, int r) { return S.G + (long long)gcolidx(S, r) * S.ldg; }
 
 // gather block `bb` (diagonal block, panel against block bb-1, constants) into `buf`; threads t0, t0+nthr, ...
 template <class Policy>
@@ -78,7 +84,7 @@ __device__ __forceinline__ void stage_block(const State &S, const Policy &P, int
         if (j < cnt && (panel || i < cnt)) {
           const int rj = S.row[S.ord[32 * bb + j]];
           const int ri = S.row[S.ord[32 * (panel ? bb - 1 : bb) + i]];
-          v[u] = ld_l2(S.G + rj + (long long)ri * S.ldg);
+          v[u] = ld_l2(gcol(S, ri) + rj);
         }
       }
     }
@@ -107,14 +113,14 @@ __device__ __forceinline__ void apply_block(const State &S, int m, int hbk, cons
   for (int t = t0; t < m; t += nthr) {
     const int blk = S.pos[t] >> 5;
     if (blk == ex0 || blk == ex1) continue;
-    const double *Gt = S.G + S.row[t];
+    const int rt = S.row[t];
     double gt = S.g[t];
 #pragma unroll 1
     for (int i0 = 0; i0 < cnt; i0 += 16) {
       double v[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u)
-        v[u] = (i0 + u < cnt) ? ld_l2(Gt + (long long)S.row[S.ord[32 * hbk + i0 + u]] * S.ldg) : 0.0;
+        v[u] = (i0 + u < cnt) ? ld_l2(gcol(S, S.row[S.ord[32 * hbk + i0 + u]]) + rt) : 0.0;
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const double h = (i0 + u < cnt) ? hv[i0 + u] : 0.0;
@@ -207,6 +213,7 @@ __device__ Result run(State &S, const Policy &P, double rr, long long maxPasses,
         if (valid) {
           S.g[e] = gj;
           S.be[e] = bej;
+          if (S.hout) S.hout[e] = myh;
         }
         sh->hb[b & 1][lane] = valid ? myh : 0.0;
         pmax = fmax(pmax, fabs(myh));
@@ -221,7 +228,23 @@ __device__ Result run(State &S, const Policy &P, double rr, long long maxPasses,
       __syncthreads();
       lap(2);
     }
-    if (nb >= 2) { // drain: the last block's steps reach the rest of the list
+    if (S.hout) {
+      // one-pass mode: the caller only wants the steps and the new values; g is recomputed from the slices
+    } else if (nb == 2) {
+      // drain, two blocks: block 1's steps reach block 0 through the panel already staged for block 1
+      // (P[i*32 + j] = G(entry j of block 1, entry i of block 0), G symmetric) — no trip to L2
+      if (warp == 1) {
+        const int cnt1 = m - 32;
+        const double *Pb = S.stage + BUF_DOUBLES + 1024, *hv = sh->hb[1];
+        const int e = S.ord[lane];
+        double gt = S.g[e];
+        for (int j = 0; j < cnt1; ++j) {
+          const double h = hv[j];
+          if (h != 0.0) gt = Policy::apply(gt, Pb[lane * 32 + j], h);
+        }
+        S.g[e] = gt;
+      }
+    } else if (nb > 2) { // drain: the last block's steps reach the rest of the list
       apply_block<Policy>(S, m, nb - 1, sh->hb[(nb - 1) & 1], nb - 1, -1, tid, T);
     }
     if (warp == 0) {
@@ -230,7 +253,8 @@ __device__ Result run(State &S, const Policy &P, double rr, long long maxPasses,
     }
     // ---- dropzeros!
     int z = 0;
-    for (int i = tid; i < m; i += T) z |= (S.be[i] == 0.0);
+    if (!S.hout)
+      for (int i = tid; i < m; i += T) z |= (S.be[i] == 0.0);
     z = __syncthreads_or(z);
     R.npasses += 1;
     R.visits += m;
@@ -325,14 +349,14 @@ __device__ __forceinline__ void apply_owned(const State &S, const Multi &X, int 
   const int cnt = min(32, m - 32 * hbk);
   const double hl = lane < cnt ? __ldcg(hsrc + lane) : 0.0; // lane i holds h_i
   if (!__any_sync(0xffffffffu, hl != 0.0)) return;
-  const int ri = lane < cnt ? S.row[S.ord[32 * hbk + lane]] : 0; // ... and the row id of entry i of the block
+  const int ri = lane < cnt ? gcolidx(S, S.row[S.ord[32 * hbk + lane]]) : 0; // ... and the column of entry i of the block
   const int ngroups = (m + 31) >> 5;
   for (int gi = X.me + X.W * (warp - wfirst); gi < ngroups; gi += X.W * nw) {
     const int t = 32 * gi + lane;
     const bool live = t < m;
     const int blk = live ? (S.pos[t] >> 5) : ex0;
     const bool skip = !live || blk == ex0 || blk == ex1;
-    const double *Gt = S.G + (live ? S.row[t] : 0);
+    const int rt = live ? S.row[t] : 0;
     double gt = skip ? 0.0 : __ldcg(X.gG + t);
 #pragma unroll 1
     for (int i0 = 0; i0 < cnt; i0 += 16) {
@@ -340,7 +364,7 @@ __device__ __forceinline__ void apply_owned(const State &S, const Multi &X, int 
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int rr_ = __shfl_sync(0xffffffffu, ri, (i0 + u) & 31);
-        v[u] = (!skip && i0 + u < cnt) ? ld_l2(Gt + (long long)rr_ * S.ldg) : 0.0;
+        v[u] = (!skip && i0 + u < cnt) ? ld_l2(S.G + (long long)rr_ * S.ldg + rt) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < 16; ++u) {

@@ -221,6 +221,7 @@ struct DevStats {
 extern long long g_cdgpu_launches;
 #define CD_COUNT_LAUNCH(k) (g_cdgpu_launches += (k))
 
+struct CovResume;
 // ---------------------------------------------------------------- handle --
 struct cdgpu_handle_s {
   int kind = -1, device = 0;
@@ -256,6 +257,23 @@ struct cdgpu_handle_s {
   int *dflag = nullptr;             // device status word(s)
   double gram_ms = 0.0;
   int sm_count = 0, max_cluster = 0;
+  // lazy covariance form (lazy_gram.cu): dX is then the column CACHE (ld x lz_cap), columns found through dslot
+  bool lazy = false;
+  const double *lzX = nullptr;      // the data, n x p (ld lz_ldx) on the device
+  const double *lzy = nullptr;
+  bool own_lzX = false, own_lzy = false;
+  int64_t lz_n = 0, lz_ldx = 0;
+  int lz_cap = 0, lz_used = 0;      // slots of the cache / slots filled
+  int *dslot = nullptr;             // [p] coordinate -> slot, -1: column not formed
+  double *ddiag = nullptr;          // [p] diag(A)
+  double *dgather = nullptr;        // [lz_ldb x 128] the gathered columns of one batch (second GEMM operand)
+  int64_t lz_ldb = 0;
+  CovResume *dresume = nullptr;
+  int *dbatch = nullptr;            // [128] coordinates of the batch being formed
+  int *hslot = nullptr;             // host mirror of dslot
+  cudaEvent_t lz_ev0 = nullptr, lz_ev1 = nullptr;
+  int lz_batches = 0, lz_pauses = 0; // statistics of the last solve
+  double lz_form_ms = 0.0;           // device time spent forming columns during the last solve
 };
 
 // device selection (+ memory-pool release threshold) and the per-device free list of stream/event sets (api.cu)
@@ -266,6 +284,20 @@ struct StreamSet {
 };
 int stream_set_acquire(int device, StreamSet *out);
 void stream_set_release(int device, const StreamSet &s);
+
+// State of a covariance-form path that stopped because a coordinate entered whose column of A = X'X/n has not been
+// formed yet (lazy covariance handle, api.cu).  The kernel leaves through a consistent point INSIDE the full pass
+// (before the entering step is applied); the host forms the missing column(s) and launches again with valid = 1.
+struct CovResume {
+  int valid;        // host -> kernel: continue from this record
+  int need_k;       // kernel -> host: the coordinate whose column is missing
+  int li;           // lambda index
+  int conv, m_bound, m_old, tzflag, pad0;
+  long long iter, out_off, cols_done, curpos;
+  unsigned long long pass_counter;
+  double maxH;      // of the pass in progress
+  DevStats st;
+};
 
 // ------------------------------------------------------------- launchers --
 struct CovArgs {
@@ -292,13 +324,18 @@ struct CovArgs {
   long long *colptr, *rowval;
   double *nzval;
   long long capacity;
-  int *flag; // [0]=status (0 ok, 1 capacity, 2 active set too large), [1]=columns done
+  int *flag; // [0]=status (0 ok, 1 capacity, 2 active set too large, 3 paused: column resume->need_k missing), [1]=columns done
   DevStats *stats;
   long long *prof; // optional [8]: SM cycles spent per phase by CTA 0 (CDGPU_PROFILE=1)
+  // lazily formed columns: column k of the p x p matrix lives at A + colslot[k]*lda (colslot[k] < 0: not formed yet);
+  // null for a fully formed A.  resume: see CovResume (null: never pause; a missing column is then an error)
+  const int *colslot;
+  CovResume *resume;
+  int events_only; // diagnostics: 1 = the event-by-event full pass of round 1 instead of chain + verify
 };
 int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a);
 int launch_cov_init(cdgpu_handle_s *h, const double *A, long long lda, int p, const int *act, const double *actval,
-                    const int *nact, double *Ax, double *beta, unsigned char *inlist);
+                    const int *nact, double *Ax, double *beta, unsigned char *inlist, const int *colslot);
 int launch_lambda_max_quad(cdgpu_handle_s *h, const double *b, const double *omega, int p, double *out);
 int launch_extract_ainv(cdgpu_handle_s *h, const double *A, long long lda, int p, double *ainv);
 int launch_check_symmetric(cdgpu_handle_s *h, const double *A, long long lda, int p, int *flag);
@@ -309,10 +346,22 @@ int launch_diag_sqrt(cdgpu_handle_s *h, const double *A, long long lda, int p, d
 int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double *G,
                 double *c, double divisor, int mode);
 int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_total);
+// lazy_gram.cu
+int launch_diag_xty(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double divisor,
+                    double *diag, double *b, double *ainv, int accumulate, int finish);
+int launch_lazy_score(cdgpu_handle_s *h, const double *Ax, const double *b, const double *omega, const int *slot, int p,
+                      double *out);
+int launch_gather_cols(cdgpu_handle_s *h, const double *X, long long ldx, long long n, const int *idx, int nb, int nbpad,
+                       double *B, long long ldb, int *slot, int slot0);
+int launch_fill_int(cdgpu_handle_s *h, int *a, int n, int v);
+int launch_sqrt_vec(cdgpu_handle_s *h, const double *a, int n, double *out);
 // refit.cu: least squares on a support (refitLassoPath); scratch >= ld*ns + ns doubles, ld = ns rounded up to even
 int launch_refit(cdgpu_handle_s *h, const int *dS, int ns, double *scratch, int *flag);
 int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, long long lda, const double *B, int pb,
                    long long ldb, long long n, double *C, long long ldc, double divisor, void **tiles_out);
+
+int launch_gemm_tn_split(cudaStream_t stream, int sm_count, const double *A, int pa, long long lda, const double *B, int pb,
+                         long long ldb, long long n, double *C, long long ldc, double divisor);
 
 // naive sweeps (naive_sweep.cu)
 struct NaiveArgs {

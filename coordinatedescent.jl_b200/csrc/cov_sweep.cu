@@ -8,16 +8,26 @@
 // B200 design:
 //  * the p coordinates are partitioned over the C CTAs of a cluster (C = 16, non-portable size);
 //    each CTA keeps its slice of Ax, b, 1/diag(A), omega, beta in shared memory for the whole path.
-//  * FULL pass = exact Gauss-Seidel by speculation: while Ax is unchanged the test "does coordinate
-//    k move?" is independent across k, so every CTA scans its slice in parallel, the cluster takes
-//    the FIRST (in visit order) coordinate with h != 0 through a DSMEM candidate exchange and one
-//    cluster barrier, applies it (a coalesced p/C-long axpy of the column slice per CTA) and resumes
-//    behind it.  Visits with h == 0 cost 40 B of shared memory and no global traffic.
-//  * ACTIVE-SET passes only ever read Ax on the active set, so they run inside CTA 0 with one
-//    register-resident entry per thread, one named barrier per coordinate step and the needed
-//    A[act, k] gathers software-prefetched two steps ahead; the other CTAs sleep on the cluster
+//  * FULL pass = exact Gauss-Seidel by speculation on WHO moves.  In a full pass the coordinates that move
+//    are, almost always, the current members of the iterate; everybody else is a no-op whose only role is
+//    "am I still inactive when my turn comes?".  So a pass is (1) the member chain: CTA 0 runs the members, in
+//    visit order, through the blocked chain engine (chain_engine.cuh) assuming no other coordinate moves — a
+//    dependent chain over the |members| x |members| block of A only; (2) verification, all CTAs, bandwidth
+//    bound: every coordinate j accumulates Ax_j += A[j,k]*h_k over the members in visit order (the same
+//    non-fused multiply-adds, in the same order, as the one-step-at-a-time reference) and every non-member
+//    is tested at the point of the accumulation where its own visit falls; (3) one candidate exchange over
+//    DSMEM (st.async + mbarrier) gives the FIRST non-member that moves, if any: the chain is valid up to that
+//    position, the entering step is applied, and the pass resumes behind it with the remaining members.
+//    Without an entering coordinate (the common case) the whole pass costs one chain and one sweep over
+//    |members| columns; iterates, visit counts and the SparseIterate order are those of the reference.
+//  * ACTIVE-SET passes only ever read Ax on the active set, so they run inside CTA 0 on the chain engine
+//    (or, for many 32-entry blocks, distributed over the cluster); the other CTAs sleep on the cluster
 //    barrier.  Afterwards the whole cluster folds the accumulated change into its Ax slices
 //    (Ax += A[:, act] * (beta - beta_at_entry), a coalesced GEMV over L2-resident columns).
+//  * lists longer than the engine holds fall back to an event-by-event pass (first mover by cluster-wide
+//    candidate exchange, one column axpy per step): slow, exact, no size limit.
+//  * columns of A may be formed lazily (colslot/resume in CovArgs): the kernel leaves at an entering coordinate
+//    whose column is missing and continues, in a later launch, exactly where it stopped.
 //  * no grid-wide sync, no host round trip between passes or between lambdas.
 #include <cooperative_groups.h>
 
@@ -38,7 +48,7 @@ constexpr unsigned KEY_NONE = 0xffffffffu;
 struct __align__(16) Cand { // 32 bytes = two st.async.v2.b64
   unsigned key; // visit position of the coordinate (KEY_NONE: this slice has no mover)
   int k;        // coordinate | member flag in bit 31
-  int pad;      // sender's count of visited-but-not-appended non-members (see full_pass)
+  int pad;      // event pass: sender's count of visited-but-not-appended non-members; chain pass: "some test saw v == 0"
   int unused;
   double h, nw;
 };
@@ -55,6 +65,7 @@ struct Smem {
   Bcast bc;
   double h[2];
   int nact, flag, nonapp;
+  int mR, tz;             // chain pass: entries handed to the member chain this round; sticky "a test saw v == 0"
   int s2[2];
   unsigned long long mbar[2]; // candidate-exchange barriers (one per round parity)
   chain::Shared ch;
@@ -66,15 +77,21 @@ struct Ctx {
   const CovArgs &a;
   cg::cluster_group &cluster;
   Smem *sm;
-  double *sAx, *sb, *sainv, *sw, *sbeta; // this CTA's slice (shared or global)
+  double *sAx, *sAx2, *sb, *sainv, *sw, *sbeta; // this CTA's slice (shared or global); sAx2: tentative Ax of a chain pass
   int *s_act;                            // CTA-0 engine: coordinates of the stored entries
-  double *e_g, *e_be, *e_stage;          // CTA-0 engine state (chain_engine.cuh)
+  double *e_g, *e_be, *e_h, *e_stage;    // CTA-0 engine state (chain_engine.cuh); e_h: steps of the member chain
+  unsigned *e_vpos;                      // visit positions of the member chain's entries
   unsigned short *e_ord, *e_pos;
   int ecap;                              // entries the engine can hold in this launch
   int multi_ok;                          // the cluster-distributed engine may be used (CDGPU_COV_MULTI=0 disables)
   unsigned char *s_in, *s_vnz;           // per slice: member at pass start / tentative value non-zero
   int rank, C, L, lo, len, slice_in_smem;
 };
+
+// start of column k of A (lazily formed columns live in slots)
+__device__ __forceinline__ const double *col_ptr(const CovArgs &a, int k) {
+  return a.A + (long long)(a.colslot ? __ldg(a.colslot + k) : k) * a.lda;
+}
 
 // remote (or own) element of a slice array living at the same shared offset in every CTA
 __device__ __forceinline__ double slice_get(const Ctx &c, double *arr_local, int k) {
@@ -120,29 +137,76 @@ __device__ __forceinline__ void st_async_16(uint32_t raddr, unsigned long long a
                : "memory");
 }
 
-// ------------------------------------------------------------------ full pass --
-// Returns max|h|.  On return CTA 0 holds the new entries appended (in visit order) behind the
-// m_old old ones in a.act; `nonapp_total` is the number of visited non-members whose tentative value
-// was exactly zero (they are NOT appended by the reference's setindex!; practically always 0).
-template <bool PROF>
-__device__ __forceinline__ double full_pass(Ctx &c, double lam, unsigned long long pass_counter, unsigned &round,
-                                            long long &accepted, bool first_pass_of_kernel, int &nonapp_total,
-                                            long long *pf, int &m_bound) {
+// One round of the cluster-wide "first mover" election.  Every thread brings its best candidate (best == KEY_NONE:
+// none); on return every thread of every CTA holds the cluster's winner (key == KEY_NONE: nobody moves) and the sum
+// of the CTAs' `pad` words.  One __syncthreads, one st.async push per peer, one wait on the CTA's own mbarrier.
+__device__ __forceinline__ Cand elect(Ctx &c, unsigned &round, unsigned best, int bk, double bh, double bnw, int pad,
+                                      int &pad_sum) {
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, C = c.C;
+  const unsigned par = round & 1u, phase = (round >> 1) & 1u;
+  if (tid == 0) mbar_arrive_expect_tx(&sm->mbar[par], (uint32_t)(C * sizeof(Cand)));
+  const unsigned wmin = __reduce_min_sync(0xffffffffu, best);
+  if (best == wmin && (best != KEY_NONE || lane == 0)) { // positions are unique: one lane per warp
+    Cand &wc = sm->wcand[warp];
+    wc.key = best;
+    wc.k = bk;
+    wc.h = bh;
+    wc.nw = bnw;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned mykey = lane < COV_T / 32 ? sm->wcand[lane].key : KEY_NONE;
+    const unsigned bmin = __reduce_min_sync(0xffffffffu, mykey);
+    const unsigned src = __ffs(__ballot_sync(0xffffffffu, mykey == bmin && lane < COV_T / 32)) - 1; // winning warp
+    if (lane < C) { // push the block's candidate into peer `lane`'s slot [par][rank] and signal its mbarrier
+      const Cand &bc = sm->wcand[src];
+      const unsigned long long w0 = (unsigned long long)bmin | ((unsigned long long)(unsigned)bc.k << 32);
+      const unsigned long long w1 = (unsigned long long)(unsigned)pad;
+      const uint32_t slot = map_to_rank(smem_u32(&sm->cand[par][c.rank]), (uint32_t)lane);
+      const uint32_t rbar = map_to_rank(smem_u32(&sm->mbar[par]), (uint32_t)lane);
+      st_async_16(slot, w0, w1, rbar);
+      st_async_16(slot + 16, (unsigned long long)__double_as_longlong(bc.h), (unsigned long long)__double_as_longlong(bc.nw), rbar);
+    }
+  }
+  mbar_wait(&sm->mbar[par], phase);
+  // every warp picks the cluster's winner lane-parallel: lane q looks at CTA q's candidate
+  const unsigned ckey = lane < C ? sm->cand[par][lane].key : KEY_NONE;
+  int napp = lane < C ? sm->cand[par][lane].pad : 0;
+  const unsigned wkey = __reduce_min_sync(0xffffffffu, ckey);
+  pad_sum = __reduce_add_sync(0xffffffffu, napp);
+  const unsigned wsrc = __ffs(__ballot_sync(0xffffffffu, ckey == wkey && lane < C)) - 1;
+  Cand w = sm->cand[par][wsrc];
+  w.key = wkey;
+  round += 1;
+  return w;
+}
+
+// ------------------------------------------------------------------ event-by-event pass --
+// The pass as a sequence of cluster-wide "who moves first?" elections, one column axpy per step.  Used for full passes
+// when the list does not fit the chain engine (and as a diagnostic, CDGPU_COV_EVENTS=1), and — RESTRICT — for
+// active-set passes over lists longer than the engine holds: then only list members are visited, in list order
+// (lpos[k] = list position of coordinate k; random iterator: the keyed permutation of the m list positions).
+// Returns max|h|.  Full pass: on return CTA 0 holds the new entries appended (in visit order) behind the m_old old
+// ones in a.act; `nonapp_total` is the number of visited non-members whose tentative value was exactly zero (they are
+// NOT appended by the reference's setindex!; practically always 0).
+template <bool PROF, bool RESTRICT>
+__device__ __forceinline__ double event_pass(Ctx &c, double lam, unsigned long long pass_counter, unsigned &round,
+                                             long long &accepted, bool first_pass_of_kernel, int &nonapp_total,
+                                             long long *pf, int &m_bound, const int *lpos, int m_list) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const bool ordered = a.randomize == 0;
-  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  const PermKey pk = cd_perm_key((uint32_t)(RESTRICT ? max(m_list, 1) : a.p), a.seed, pass_counter);
   // hot-loop state in registers
   double *__restrict__ sAx = c.sAx;
   const double *__restrict__ sb = c.sb, *__restrict__ sainv = c.sainv, *__restrict__ sw = c.sw;
   double *__restrict__ sbeta = c.sbeta;
   unsigned char *__restrict__ s_in = c.s_in, *__restrict__ s_vnz = c.s_vnz;
-  const int lo = c.lo, len = c.len, C = c.C, rank = c.rank;
-  const double *__restrict__ A = a.A;
-  const long long lda = a.lda;
-  int cur = -1;          // ordered: last coordinate that moved
-  long long curpos = -1; // random: its visit position
+  const int lo = c.lo, len = c.len, rank = c.rank;
+  int cur = -1;          // ordered full pass: last coordinate that moved
+  long long curpos = -1; // otherwise: its visit position
   double maxH = 0.0;
   // membership at the start of the pass (beta != 0, or an explicit zero handed in by the caller)
   for (int i = tid; i < len; i += COV_T) {
@@ -153,25 +217,31 @@ __device__ __forceinline__ double full_pass(Ctx &c, double lam, unsigned long lo
   __syncthreads();
   for (;;) {
     const long long ta = PROF ? clock64() : 0;
-    const unsigned par = round & 1u, phase = (round >> 1) & 1u;
-    if (tid == 0) mbar_arrive_expect_tx(&sm->mbar[par], (uint32_t)(C * sizeof(Cand)));
     unsigned best = KEY_NONE;
     int bk = 0;
     double bh = 0.0, bnw = 0.0;
-    const int i0 = ordered ? max(0, cur + 1 - lo) : 0;
+    const int i0 = (ordered && !RESTRICT) ? max(0, cur + 1 - lo) : 0;
     // every thread owns the slice elements tid, tid+T, ... in BOTH the scan and the update below, so no
     // barrier is needed between a step and the next scan
 #pragma unroll 2
     for (int i = tid; i < len; i += COV_T) {
       if (i < i0) continue;
-      const unsigned key = ordered ? (unsigned)(lo + i) : cd_perm_inv(pk, (uint32_t)(lo + i));
-      if (!ordered && (long long)key <= curpos) continue;
+      const bool member = s_in[i] != 0;
+      unsigned key;
+      if (RESTRICT) {
+        if (!member) continue;
+        const unsigned lp = (unsigned)__ldcg(lpos + lo + i);
+        key = ordered ? lp : cd_perm_inv(pk, lp);
+        if ((long long)key <= curpos) continue;
+      } else {
+        key = ordered ? (unsigned)(lo + i) : cd_perm_inv(pk, (uint32_t)(lo + i));
+        if (!ordered && (long long)key <= curpos) continue;
+      }
       const double ainv = sainv[i];
       const double g = sAx[i] + sb[i];
       const double old = sbeta[i];
       const double t = __dmul_rn(g, ainv);
       const double thr = __dmul_rn(__dmul_rn(ainv, lam), sw[i]);
-      const bool member = s_in[i] != 0;
       // short dependent chain for the common case (x_k == 0 stays 0): v = -t, and S(v, thr) != 0 <=> |t| > thr;
       // t == 0 is the (practically impossible) "not appended" case tracked below
       if (old == 0.0 && !(fabs(t) > thr) && t != 0.0 && s_vnz[i]) continue;
@@ -190,45 +260,14 @@ __device__ __forceinline__ double full_pass(Ctx &c, double lam, unsigned long lo
         bnw = nw;
       }
     }
-    // block argmin with ONE barrier: every warp leaves its best candidate in shared memory, then warp 0
-    // alone picks the block's and pushes it to the peers; the other warps go straight to the wait.
-    const unsigned wmin = __reduce_min_sync(0xffffffffu, best);
-    if (best == wmin && (best != KEY_NONE || lane == 0)) { // positions are unique: one lane per warp
-      Cand &wc = sm->wcand[warp];
-      wc.key = best;
-      wc.k = bk;
-      wc.h = bh;
-      wc.nw = bnw;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const unsigned mykey = lane < COV_T / 32 ? sm->wcand[lane].key : KEY_NONE;
-      const unsigned bmin = __reduce_min_sync(0xffffffffu, mykey);
-      const unsigned src = __ffs(__ballot_sync(0xffffffffu, mykey == bmin && lane < COV_T / 32)) - 1; // winning warp
-      if (lane < C) { // push the block's candidate into peer `lane`'s slot [par][rank] and signal its mbarrier
-        const Cand &bc = sm->wcand[src];
-        const unsigned long long w0 = (unsigned long long)bmin | ((unsigned long long)(unsigned)bc.k << 32);
-        const unsigned long long w1 = (unsigned long long)(unsigned)sm->nonapp;
-        const uint32_t slot = map_to_rank(smem_u32(&sm->cand[par][rank]), (uint32_t)lane);
-        const uint32_t rbar = map_to_rank(smem_u32(&sm->mbar[par]), (uint32_t)lane);
-        st_async_16(slot, w0, w1, rbar);
-        st_async_16(slot + 16, (unsigned long long)__double_as_longlong(bc.h), (unsigned long long)__double_as_longlong(bc.nw), rbar);
-      }
-    }
     const long long tb = PROF ? clock64() : 0;
-    mbar_wait(&sm->mbar[par], phase);
+    int napp = 0;
+    // sm->nonapp is read by warp 0 after elect()'s __syncthreads; all atomics above precede it
+    __syncthreads();
+    const Cand w = elect(c, round, best, bk, bh, bnw, sm->nonapp, napp);
     const long long tc = PROF ? clock64() : 0;
     if (PROF) pf[7] += tb - ta;
     if (PROF) pf[8] += tc - tb;
-    // every warp picks the cluster's winner lane-parallel: lane q looks at CTA q's candidate
-    const unsigned ckey = lane < C ? sm->cand[par][lane].key : KEY_NONE;
-    int napp = lane < C ? sm->cand[par][lane].pad : 0;
-    const unsigned wkey = __reduce_min_sync(0xffffffffu, ckey);
-    napp = __reduce_add_sync(0xffffffffu, napp);
-    const unsigned wsrc = __ffs(__ballot_sync(0xffffffffu, ckey == wkey && lane < C)) - 1;
-    Cand w = sm->cand[par][wsrc];
-    w.key = wkey;
-    round += 1;
     if (w.key == KEY_NONE) {
       nonapp_total = napp; // every slice's scan was final
       break;
@@ -236,7 +275,7 @@ __device__ __forceinline__ double full_pass(Ctx &c, double lam, unsigned long lo
     const int k = w.k & 0x7fffffff;
     const bool wmember = w.k < 0;
     // column slice first (independent loads in flight), then the shared-memory update
-    const double *col = A + (long long)k * lda + lo;
+    const double *col = col_ptr(a, k) + lo;
     for (int i = tid; i < len; i += 4 * COV_T) {
       double x[4];
 #pragma unroll
@@ -263,46 +302,6 @@ __device__ __forceinline__ double full_pass(Ctx &c, double lam, unsigned long lo
   return maxH;
 }
 
-// rare: publish the visited non-members that were not appended (tentative value exactly zero)
-__device__ void publish_nonapp(Ctx &c) {
-  int *cnt = c.a.flag + 2, *list = c.a.iscr + 6 * (long long)c.a.p;
-  for (int i = threadIdx.x; i < c.len; i += COV_T)
-    if (!c.s_in[i] && !c.s_vnz[i]) list[atomicAdd(cnt, 1)] = c.lo + i;
-  __threadfence();
-}
-
-// dropzeros! after a full pass, CTA 0.  Gathers the final values of all listed coordinates, places
-// the new entries where the reference's temporary appends put them (see cd_compact_list) and compacts.
-__device__ void list_update_full(Ctx &c, int m_old, int nonapp_total, unsigned long long pass_counter) {
-  const CovArgs &a = c.a;
-  Smem *sm = c.sm;
-  const int tid = threadIdx.x;
-  const int m = sm->nact;
-  for (int i = tid; i < m; i += COV_T) a.actval[i] = slice_get(c, c.sbeta, a.act[i]);
-  int *newpos = a.iscr + 7 * (long long)a.p;
-  const bool ordered = a.randomize == 0;
-  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
-  const int *nonapp = a.iscr + 6 * (long long)a.p;
-  for (int e = m_old + tid; e < m; e += COV_T) {
-    const int k = a.act[e];
-    const long long vis = ordered ? k : (long long)cd_perm_inv(pk, (uint32_t)k);
-    int before = 0; // old members and non-appended non-members visited before k
-    for (int j = 0; j < m_old; ++j) {
-      const int kj = a.act[j];
-      before += (ordered ? kj : (long long)cd_perm_inv(pk, (uint32_t)kj)) < vis;
-    }
-    for (int j = 0; j < nonapp_total; ++j) {
-      const int kj = __ldcg(nonapp + j);
-      before += (ordered ? kj : (long long)cd_perm_inv(pk, (uint32_t)kj)) < vis;
-    }
-    newpos[e - m_old] = m_old + (int)vis - before;
-  }
-  __syncthreads();
-  cd_compact_list<COV_T>(a.act, a.actval, m_old, m, newpos, a.inlist, a.iscr + (long long)a.p, a.scr + 2 * (long long)a.p,
-                         sm->s2);
-  if (tid == 0) sm->nact = sm->s2[0];
-  __syncthreads();
-}
 
 // ------------------------------------------------------ active-set engine (CTA 0) --
 // Consecutive active-set passes until one has maxH < optTol or `maxPasses` are used: the blocked
@@ -329,6 +328,348 @@ struct CovPolicy {
   }
   static __device__ __forceinline__ double apply(double g, double Gv, double h) { return __dadd_rn(g, __dmul_rn(Gv, h)); } // :343-345
 };
+
+// ------------------------------------------------------------------ full pass: member chain + verification --
+// visit position of coordinate k in the full pass
+__device__ __forceinline__ unsigned visit_pos(bool ordered, const PermKey &pk, int k) {
+  return ordered ? (unsigned)k : cd_perm_inv(pk, (uint32_t)k);
+}
+
+// Ax2[slice] = Ax[slice] + sum_{t < tend} A[slice, k_t] * h_t (steps in order, non-fused) [+ A[slice, kx] * hx].
+// TEST: every still-unvisited non-member is tested where its own visit falls among the steps; returns this
+// thread's earliest mover through best/bk/bh/bnw and records "value exactly zero" in s_vnz.
+template <bool TEST>
+__device__ __forceinline__ void sweep_members(Ctx &c, double lam, int tend, int kx, double hx, long long curpos,
+                                              bool ordered, const PermKey &pk, unsigned &best, int &bk, double &bh,
+                                              double &bnw) {
+  const CovArgs &a = c.a;
+  const int tid = threadIdx.x, lo = c.lo, len = c.len;
+  const double *__restrict__ sAx = c.sAx;
+  double *__restrict__ sAx2 = c.sAx2;
+  const int *__restrict__ rk = c.s_act;
+  const double *__restrict__ rh = c.e_h;
+  const unsigned *__restrict__ rpos = c.e_vpos;
+  constexpr int NE = 3, NQ = 8; // elements per thread and chain steps per batch: NE*NQ independent loads in flight
+  int tzseen = 0;
+  for (int base = 0; base < len; base += NE * COV_T) {
+    double acc[NE];
+    int ti[NE]; // step index before which the element is tested (-1: never)
+    unsigned pj[NE];
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+      const int i = base + tid + u * COV_T;
+      const bool valid = i < len;
+      acc[u] = valid ? sAx[i] : 0.0;
+      ti[u] = -1;
+      pj[u] = 0;
+      if (TEST && valid && !c.s_in[i]) {
+        pj[u] = visit_pos(ordered, pk, lo + i);
+        if ((long long)pj[u] > curpos) { // lower bound: number of chain entries visited before this coordinate
+          int l = 0, r = tend;
+          while (l < r) {
+            const int mid = (l + r) >> 1;
+            if (rpos[mid] < pj[u]) l = mid + 1; else r = mid;
+          }
+          ti[u] = l;
+        }
+      }
+    }
+    auto test = [&](int u) {
+      const int i = base + tid + u * COV_T;
+      const double ainv = c.sainv[i];
+      const double g = acc[u] + c.sb[i];
+      const double old = c.sbeta[i];
+      const double t = __dmul_rn(g, ainv);
+      const double thr = __dmul_rn(__dmul_rn(ainv, lam), c.sw[i]);
+      const double v = __dsub_rn(old, t);
+      const double nw = cd_shrink(v, thr);
+      const double h = nw - old;
+      const unsigned char nz = (unsigned char)(v != 0.0); // `x[k] -= b*a` appends iff the value is non-zero
+      c.s_vnz[i] = nz;
+      if (!nz) tzseen = 1;
+      if (h != 0.0 && pj[u] < best) {
+        best = pj[u];
+        bk = lo + i;
+        bh = h;
+        bnw = nw;
+      }
+    };
+    for (int t0 = 0; t0 < tend; t0 += NQ) {
+      double x[NQ][NE], hq[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const bool on = t0 + q < tend;
+        hq[q] = on ? rh[t0 + q] : 0.0;
+        const double *col = col_ptr(a, on ? rk[t0 + q] : rk[t0]) + lo + base + tid;
+#pragma unroll
+        for (int u = 0; u < NE; ++u)
+          x[q][u] = (hq[q] != 0.0 && base + tid + u * COV_T < len) ? __ldg(col + u * COV_T) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+        for (int u = 0; u < NE; ++u) {
+          if (TEST && ti[u] == t0 + q) test(u);
+          if (hq[q] != 0.0) acc[u] = __dadd_rn(acc[u], __dmul_rn(x[q][u], hq[q]));
+        }
+      }
+    }
+    if (TEST) {
+#pragma unroll
+      for (int u = 0; u < NE; ++u)
+        if (ti[u] >= tend) test(u); // visited after every chain entry
+    }
+    if (kx >= 0) {
+      const double *col = col_ptr(a, kx) + lo + base + tid;
+#pragma unroll
+      for (int u = 0; u < NE; ++u)
+        if (base + tid + u * COV_T < len) acc[u] = __dadd_rn(acc[u], __dmul_rn(__ldg(col + u * COV_T), hx));
+    }
+#pragma unroll
+    for (int u = 0; u < NE; ++u)
+      if (base + tid + u * COV_T < len) sAx2[base + tid + u * COV_T] = acc[u];
+  }
+  if (TEST && tzseen) c.sm->tz = 1;
+}
+
+struct PassCarry { // a full pass in progress: what a pause (lazy columns) has to carry into the next launch
+  long long curpos;
+  int m_old;
+  double maxH;
+  bool resume, paused;
+  int need_k;
+};
+
+// Returns max|h| of the pass.  m_old = list length at pass start (all CTAs).  pc.resume: continue a pass that an earlier
+// launch left at pc.curpos (membership flags, sorted member list and the appended entries are still in place).
+template <bool PROF>
+__device__ __forceinline__ double chain_pass(Ctx &c, double lam, unsigned long long pass_counter, unsigned &round,
+                                             long long &accepted, bool first_pass_of_kernel, int &nonapp_total,
+                                             long long *pf, int &m_bound, PassCarry &pc) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x;
+  const bool ordered = a.randomize == 0;
+  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  const int lo = c.lo, len = c.len, rank = c.rank;
+  const int m_old = pc.m_old;
+  int *sorted_k = a.iscr + 7 * (long long)a.p;                                 // members in visit order
+  unsigned *sorted_pos = reinterpret_cast<unsigned *>(a.iscr + 6 * (long long)a.p); // ... and their visit positions
+  long long curpos = pc.resume ? pc.curpos : -1;
+  double maxH = pc.resume ? pc.maxH : 0.0;
+  pc.paused = false;
+  if (!pc.resume) {
+    for (int i = tid; i < len; i += COV_T) {
+      c.s_in[i] = first_pass_of_kernel ? a.inlist[lo + i] : (unsigned char)(c.sbeta[i] != 0.0);
+      c.s_vnz[i] = 1;
+    }
+    if (tid == 0) sm->tz = 0;
+    if (rank == 0) { // sort the members by visit position (rank by counting; positions are distinct)
+      for (int e = tid; e < m_old; e += COV_T) c.e_vpos[e] = visit_pos(ordered, pk, a.act[e]);
+      __syncthreads();
+      for (int e = tid; e < m_old; e += COV_T) {
+        const unsigned my = c.e_vpos[e];
+        int r = 0;
+        for (int j = 0; j < m_old; ++j) r += c.e_vpos[j] < my;
+        sorted_k[r] = a.act[e];
+        sorted_pos[r] = my;
+      }
+    }
+    __syncthreads();
+  }
+  for (;;) {
+    const long long ta = PROF ? clock64() : 0;
+    // ---- (1) CTA 0: the chain over the members still to be visited, in visit order
+    if (rank == 0) {
+      __syncthreads(); // sorted_k / sorted_pos written by this CTA's threads above are read below
+      int s0 = 0;      // members already visited: those with position <= curpos
+      {
+        int l = 0, r = m_old;
+        while (l < r) {
+          const int mid = (l + r) >> 1;
+          if ((long long)__ldcg(sorted_pos + mid) <= curpos) l = mid + 1; else r = mid;
+        }
+        s0 = l;
+      }
+      const int mR = m_old - s0;
+      for (int t = tid; t < mR; t += COV_T) {
+        const int k = __ldcg(sorted_k + s0 + t);
+        c.s_act[t] = k;
+        c.e_vpos[t] = __ldcg(sorted_pos + s0 + t);
+        c.e_be[t] = slice_get(c, c.sbeta, k);
+        c.e_g[t] = slice_get(c, c.sAx, k);
+        c.e_h[t] = 0.0;
+      }
+      if (tid == 0) sm->mR = mR;
+      __syncthreads();
+      if (mR > 0) {
+        chain::State S;
+        S.m = mR;
+        S.row = c.s_act;
+        S.coord = c.s_act;
+        S.g = c.e_g;
+        S.be = c.e_be;
+        S.ord = c.e_ord;
+        S.pos = c.e_pos;
+        S.stage = c.e_stage;
+        S.sh = &sm->ch;
+        S.G = a.A;
+        S.ldg = a.lda;
+        S.slot = a.colslot;
+        S.prof = nullptr;
+        S.hout = c.e_h;
+        const CovPolicy P{a.b, a.ainv, a.omega, lam};
+        (void)chain::run<COV_T>(S, P, 0.0, 1, pass_counter, true, a.seed, a.optTol, nullptr);
+      }
+    }
+    c.cluster.sync(); // the chain's entries (k, pos, h, new value) stand in CTA 0's shared memory
+    const long long tb = PROF ? clock64() : 0;
+    const int mR = *c.cluster.map_shared_rank(&sm->mR, 0);
+    if (rank != 0) {
+      const int *rk0 = c.cluster.map_shared_rank(c.s_act, 0);
+      const unsigned *rp0 = c.cluster.map_shared_rank(c.e_vpos, 0);
+      const double *rh0 = c.cluster.map_shared_rank(c.e_h, 0), *rb0 = c.cluster.map_shared_rank(c.e_be, 0);
+      for (int t = tid; t < mR; t += COV_T) {
+        c.s_act[t] = rk0[t];
+        c.e_vpos[t] = rp0[t];
+        c.e_h[t] = rh0[t];
+        c.e_be[t] = rb0[t];
+      }
+    }
+    __syncthreads();
+    // ---- (2) verification sweep + (3) election of the first entering coordinate
+    unsigned best = KEY_NONE;
+    int bk = 0;
+    double bh = 0.0, bnw = 0.0;
+    sweep_members<true>(c, lam, mR, -1, 0.0, curpos, ordered, pk, best, bk, bh, bnw);
+    __syncthreads(); // sm->tz
+    int tzsum = 0;
+    const long long tc = PROF ? clock64() : 0;
+    const Cand w = elect(c, round, best, bk, bh, bnw, sm->tz, tzsum);
+    const long long td = PROF ? clock64() : 0;
+    if (PROF) pf[7] += tb - ta;
+    if (PROF) pf[9] += tc - tb;
+    if (PROF) pf[8] += td - tc;
+    int tend = mR;
+    if (w.key != KEY_NONE) { // chain entries visited before the entering coordinate stay valid
+      int l = 0, r = mR;
+      while (l < r) {
+        const int mid = (l + r) >> 1;
+        if (c.e_vpos[mid] < w.key) l = mid + 1; else r = mid;
+      }
+      tend = l;
+      if (a.colslot && __ldg(a.colslot + w.k) < 0) { // its column has not been formed: leave before applying anything
+        pc.paused = true;
+        pc.need_k = w.k;
+        pc.curpos = curpos;
+        pc.maxH = maxH;
+        return maxH;
+      }
+      unsigned b2 = KEY_NONE;
+      int k2 = 0;
+      double h2 = 0.0, n2 = 0.0;
+      sweep_members<false>(c, lam, tend, w.k, w.h, curpos, ordered, pk, b2, k2, h2, n2);
+    }
+    // ---- commit: Ax <- Ax2 (same pointer swap in every CTA), new values of the visited members, the entering step
+    {
+      double *t = c.sAx;
+      c.sAx = c.sAx2;
+      c.sAx2 = t;
+    }
+    long long nacc = 0;
+    for (int t = tid; t < tend; t += COV_T) {
+      const double h = c.e_h[t];
+      if (h != 0.0) {
+        nacc += 1;
+        maxH = fmax(maxH, fabs(h));
+        const int k = c.s_act[t];
+        if (k >= lo && k < lo + len) c.sbeta[k - lo] = c.e_be[t];
+      }
+    }
+    if (w.key != KEY_NONE) {
+      const int k = w.k;
+      if (k >= lo && k < lo + len && tid == 0) {
+        c.sbeta[k - lo] = w.nw;
+        c.s_in[k - lo] = 1;
+      }
+      if (rank == 0 && tid == 0) { // setindex! appends on the first non-zero store
+        a.act[sm->nact] = k;
+        sm->nact += 1;
+      }
+    }
+    // block-wide: accepted count and max|h| of the committed chain entries (every CTA computes the same numbers)
+    {
+      for (int o = 16; o > 0; o >>= 1) {
+        nacc += __shfl_xor_sync(0xffffffffu, nacc, o);
+        maxH = fmax(maxH, __shfl_xor_sync(0xffffffffu, maxH, o));
+      }
+      double *redd = reinterpret_cast<double *>(sm->wcand); // 16 x 32 bytes: free between elections
+      if ((tid & 31) == 0) {
+        redd[2 * (tid >> 5)] = (double)nacc;
+        redd[2 * (tid >> 5) + 1] = maxH;
+      }
+      __syncthreads();
+      double na = 0.0;
+      for (int wq = 0; wq < COV_T / 32; ++wq) {
+        na += redd[2 * wq];
+        maxH = fmax(maxH, redd[2 * wq + 1]);
+      }
+      accepted += (long long)na;
+    }
+    c.cluster.sync(); // every slice is committed before anybody (the next chain, the list update) reads it remotely
+    if (w.key == KEY_NONE) {
+      nonapp_total = tzsum;
+      break;
+    }
+    m_bound += 1;
+    maxH = fmax(maxH, fabs(w.h));
+    accepted += 1;
+    curpos = (long long)w.key;
+  }
+  return maxH;
+}
+
+// rare: publish the visited non-members that were not appended (tentative value exactly zero)
+__device__ void publish_nonapp(Ctx &c) {
+  int *cnt = c.a.flag + 2, *list = c.a.iscr + 6 * (long long)c.a.p;
+  for (int i = threadIdx.x; i < c.len; i += COV_T)
+    if (!c.s_in[i] && !c.s_vnz[i]) list[atomicAdd(cnt, 1)] = c.lo + i;
+  __threadfence();
+}
+
+// dropzeros! after a full pass, CTA 0.  Gathers the final values of all listed coordinates, places
+// the new entries where the reference's temporary appends put them (see cd_compact_list) and compacts.
+__device__ void list_update_full(Ctx &c, int m_old, int nonapp_total, unsigned long long pass_counter) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x;
+  const int m = sm->nact;
+  for (int i = tid; i < m; i += COV_T) a.actval[i] = slice_get(c, c.sbeta, a.act[i]);
+  int *newpos = a.iscr + 7 * (long long)a.p;
+  const bool ordered = a.randomize == 0;
+  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  const int *nonapp = a.iscr + 6 * (long long)a.p;
+  __syncthreads(); // the sorted member list of the chain pass shares newpos' storage: everybody is done reading it
+  for (int e = m_old + tid; e < m; e += COV_T) {
+    const int k = a.act[e];
+    const long long vis = ordered ? k : (long long)cd_perm_inv(pk, (uint32_t)k);
+    int before = 0; // old members and non-appended non-members visited before k
+    for (int j = 0; j < m_old; ++j) {
+      const int kj = a.act[j];
+      before += (ordered ? kj : (long long)cd_perm_inv(pk, (uint32_t)kj)) < vis;
+    }
+    for (int j = 0; j < nonapp_total; ++j) {
+      const int kj = __ldcg(nonapp + j);
+      before += (ordered ? kj : (long long)cd_perm_inv(pk, (uint32_t)kj)) < vis;
+    }
+    newpos[e - m_old] = m_old + (int)vis - before;
+  }
+  __syncthreads();
+  cd_compact_list<COV_T>(a.act, a.actval, m_old, m, newpos, a.inlist, a.iscr + (long long)a.p, a.scr + 2 * (long long)a.p,
+                         sm->s2);
+  if (tid == 0) sm->nact = sm->s2[0];
+  __syncthreads();
+}
 
 // CTA 0 after an active phase: final list, dense beta, per-snapshot-entry delta (for refresh_slice), summary
 __device__ void engine_publish(Ctx &c, const chain::Result &r, int m0, const int *act0, const double *scr_b0, double *scr_dlt) {
@@ -367,11 +708,13 @@ __device__ void active_engine(Ctx &c, double lam, long long maxPasses, unsigned 
   double *scr_b0 = a.scr;        // [p] beta at entry, by snapshot index
   double *scr_dlt = a.scr + a.p; // [p] delta by snapshot index
   int *act0 = a.iscr;            // [p] snapshot of the list
+  int *act0c = a.iscr + a.p;     // [p] ... and the column index (slot) of every snapshot entry
   for (int i = tid; i < m0; i += COV_T) {
     const int k = a.act[i];
     const double be = a.actval[i];
     c.s_act[i] = k;
     act0[i] = k;
+    act0c[i] = a.colslot ? __ldg(a.colslot + k) : k;
     c.e_be[i] = be;
     scr_b0[i] = be;
     c.e_g[i] = slice_get(c, c.sAx, k);
@@ -389,6 +732,7 @@ __device__ void active_engine(Ctx &c, double lam, long long maxPasses, unsigned 
   S.sh = &sm->ch;
   S.G = a.A;
   S.ldg = a.lda;
+  S.slot = a.colslot;
   S.prof = a.prof ? a.prof + 16 : nullptr;
   const CovPolicy P{a.b, a.ainv, a.omega, lam};
   const chain::Result r = chain::run<COV_T>(S, P, 0.0, maxPasses, pass_counter, a.randomize == 0, a.seed, a.optTol, a.inlist);
@@ -405,7 +749,7 @@ __device__ void active_engine_multi(Ctx &c, double lam, long long maxPasses, uns
   Smem *sm = c.sm;
   const int tid = threadIdx.x;
   double *scr_b0 = a.scr, *scr_dlt = a.scr + a.p;
-  int *act0 = a.iscr;
+  int *act0 = a.iscr, *act0c = a.iscr + a.p;
   double *gG = a.scr + 6 * (long long)a.p, *hG = a.scr + 8 * (long long)a.p, *pmaxG = hG + 64;
   int *flagsG = reinterpret_cast<int *>(hG + 72);
   for (int i = tid; i < m0; i += COV_T) c.s_act[i] = a.act[i]; // every CTA: its own copy of the list
@@ -414,6 +758,7 @@ __device__ void active_engine_multi(Ctx &c, double lam, long long maxPasses, uns
       const int k = a.act[i];
       const double be = a.actval[i];
       act0[i] = k;
+      act0c[i] = a.colslot ? __ldg(a.colslot + k) : k;
       c.e_be[i] = be;
       scr_b0[i] = be;
       gG[i] = slice_get(c, c.sAx, k);
@@ -433,6 +778,7 @@ __device__ void active_engine_multi(Ctx &c, double lam, long long maxPasses, uns
   S.sh = &sm->ch;
   S.G = a.A;
   S.ldg = a.lda;
+  S.slot = a.colslot;
   S.prof = nullptr;
   chain::Multi X{c.C, c.rank, gG, hG, pmaxG, flagsG, a.act};
   const CovPolicy P{a.b, a.ainv, a.omega, lam};
@@ -447,13 +793,13 @@ __device__ void refresh_slice(Ctx &c, int m0) {
   const CovArgs &a = c.a;
   const int tid = threadIdx.x;
   const double *dlt = a.scr + a.p;
-  const int *act0 = a.iscr;
+  const int *act0 = a.iscr, *act0c = a.iscr + a.p;
   for (int j = tid; j < c.len; j += COV_T) {
     const double *row = a.A + c.lo + j;
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     int i = 0;
     for (; i + 4 <= m0; i += 4) {
-      const int k0 = __ldcg(act0 + i), k1 = __ldcg(act0 + i + 1), k2 = __ldcg(act0 + i + 2), k3 = __ldcg(act0 + i + 3);
+      const int k0 = __ldcg(act0c + i), k1 = __ldcg(act0c + i + 1), k2 = __ldcg(act0c + i + 2), k3 = __ldcg(act0c + i + 3);
       const double d0 = __ldcg(dlt + i), d1 = __ldcg(dlt + i + 1), d2 = __ldcg(dlt + i + 2), d3 = __ldcg(dlt + i + 3);
       const double v0 = __ldg(row + (long long)k0 * a.lda), v1 = __ldg(row + (long long)k1 * a.lda);
       const double v2 = __ldg(row + (long long)k2 * a.lda), v3 = __ldg(row + (long long)k3 * a.lda);
@@ -462,7 +808,7 @@ __device__ void refresh_slice(Ctx &c, int m0) {
       acc2 = fma(v2, d2, acc2);
       acc3 = fma(v3, d3, acc3);
     }
-    for (; i < m0; ++i) acc0 = fma(__ldg(row + (long long)__ldcg(act0 + i) * a.lda), __ldcg(dlt + i), acc0);
+    for (; i < m0; ++i) acc0 = fma(__ldg(row + (long long)__ldcg(act0c + i) * a.lda), __ldcg(dlt + i), acc0);
     c.sAx[j] += (acc0 + acc1) + (acc2 + acc3);
   }
   for (int i = tid; i < m0; i += COV_T) {
@@ -484,6 +830,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   c.lo = min(c.rank * L, a.p);
   c.len = min(a.p, c.lo + L) - c.lo;
   const int tid = threadIdx.x;
+  const bool resumed = a.resume != nullptr && a.resume->valid != 0;
   // carve shared memory (identical layout in every CTA)
   unsigned char *sp = smem_raw;
   c.sm = reinterpret_cast<Smem *>(sp);
@@ -496,8 +843,12 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   sp += (size_t)ecap * sizeof(double);
   c.e_be = reinterpret_cast<double *>(sp);
   sp += (size_t)ecap * sizeof(double);
+  c.e_h = reinterpret_cast<double *>(sp);
+  sp += (size_t)ecap * sizeof(double);
   c.s_act = reinterpret_cast<int *>(sp);
   sp += (size_t)ecap * sizeof(int);
+  c.e_vpos = reinterpret_cast<unsigned *>(sp);
+  sp += (size_t)ecap * sizeof(unsigned);
   c.e_ord = reinterpret_cast<unsigned short *>(sp);
   sp += (size_t)ecap * sizeof(unsigned short);
   c.e_pos = reinterpret_cast<unsigned short *>(sp);
@@ -509,7 +860,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
     c.sainv = d + 2 * L;
     c.sw = d + 3 * L;
     c.sbeta = d + 4 * L;
-    c.s_in = reinterpret_cast<unsigned char *>(d + 5 * L);
+    c.sAx2 = d + 5 * L;
+    c.s_in = reinterpret_cast<unsigned char *>(d + 6 * L);
     c.s_vnz = c.s_in + L;
     for (int i = tid; i < c.len; i += COV_T) {
       const int k = c.lo + i;
@@ -518,10 +870,15 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
       c.sainv[i] = a.ainv[k];
       c.sw[i] = a.omega ? a.omega[k] : 1.0;
       c.sbeta[i] = a.beta[k];
+      if (resumed) {
+        c.s_in[i] = a.bscr[k];
+        c.s_vnz[i] = a.bscr[a.p + k];
+      }
     }
   } else { // very large p: slices stay in global memory (each CTA touches only its own)
     double *g = a.scr + 4 * (long long)a.p;
     c.sAx = a.Ax + c.lo;
+    c.sAx2 = a.scr + 9 * (long long)a.p + c.lo;
     c.sbeta = g + c.lo; // private dense copy so CTA 0's writes to a.beta never race
     c.sb = const_cast<double *>(a.b) + c.lo;
     c.sainv = const_cast<double *>(a.ainv) + c.lo;
@@ -536,6 +893,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   if (tid == 0) {
     c.sm->nact = (c.rank == 0) ? *a.nact : 0;
     c.sm->bc.status = 0;
+    c.sm->tz = resumed ? a.resume->tzflag : 0;
+    c.sm->mR = 0;
     mbar_init(&c.sm->mbar[0], 1);
     mbar_init(&c.sm->mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -548,14 +907,43 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   const long long t_start = PROF ? clock64() : 0;
   unsigned round = 0; // candidate-exchange rounds so far (selects slot parity and mbarrier phase)
   int m_bound = *a.nact; // upper bound of the list length, the same in every CTA
-  bool first_pass = true;
+  int m_known = m_bound; // the exact list length when every CTA knows it, else -1
+  bool first_pass = !resumed;
   unsigned long long pass_counter = 0;
   DevStats st;
+  st.passes = st.full_passes = st.visits = st.accepted = 0;
+  st.maxH = 0.0;
+  st.converged = st.outer_iters = 0;
+  st.sigma = 0.0;
   int status = 0;
   long long cols_done = 0, out_off = 0;
-  for (int li = 0; li < a.nlambda && status == 0; ++li) {
+  int li0 = 0;
+  PassCarry pc;
+  pc.resume = false;
+  pc.paused = false;
+  pc.need_k = -1;
+  pc.curpos = -1;
+  pc.m_old = 0;
+  pc.maxH = 0.0;
+  if (resumed) {
+    const CovResume &R = *a.resume;
+    li0 = R.li;
+    st = R.st;
+    pass_counter = R.pass_counter;
+    m_bound = R.m_bound;
+    m_known = -1;
+    out_off = R.out_off;
+    cols_done = R.cols_done;
+    pc.resume = true;
+    pc.curpos = R.curpos;
+    pc.m_old = R.m_old;
+    pc.maxH = R.maxH;
+  }
+  int *lpos = a.iscr + 6 * (long long)a.p; // restricted event passes: list position of every listed coordinate
+  for (int li = li0; li < a.nlambda && status == 0; ++li) {
     const double lam = a.lambdas[li];
-    if (li == 0 || !a.accumulate) {
+    const bool resume_here = resumed && li == li0;
+    if (!resume_here && (li == 0 || !a.accumulate)) {
       st.passes = st.full_passes = st.visits = st.accepted = 0;
       st.maxH = 0.0;
       st.converged = 0;
@@ -564,18 +952,53 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
     }
     st.converged = 0;
     bool conv = true;
-    long long iter = 0;
-    while (iter < a.maxIter) {
+    long long iter = resume_here ? a.resume->iter : 0;
+    while (iter < a.maxIter || pc.resume) {
       if (conv) {
-        iter += 1;
-        st.passes += 1;
-        st.full_passes += 1;
-        st.visits += a.p;
+        const bool cont = pc.resume; // continue the pass an earlier launch left
+        if (!cont) {
+          iter += 1;
+          st.passes += 1;
+          st.full_passes += 1;
+          st.visits += a.p;
+        }
         int nonapp_total = 0;
-        const int m_old = c.sm->nact; // only meaningful on CTA 0
         const long long t0 = PROF ? clock64() : 0;
         const long long acc0 = st.accepted;
-        const double maxH = full_pass<PROF>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf, m_bound);
+        const bool use_chain = cont || (!a.events_only && m_known >= 0 && m_known <= c.ecap);
+        int m_old;
+        double maxH;
+        if (use_chain) {
+          if (!cont) pc.m_old = m_known;
+          m_old = pc.m_old;
+          maxH = chain_pass<PROF>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf, m_bound, pc);
+          pc.resume = false;
+          if (pc.paused) { // an entering coordinate has no column yet: leave, the host forms it and launches again
+            status = a.resume ? 3 : 4;
+            if (a.resume && c.rank == 0 && tid == 0) {
+              CovResume &R = *a.resume;
+              R.valid = 0;
+              R.need_k = pc.need_k;
+              R.li = li;
+              R.conv = 1;
+              R.m_bound = m_bound;
+              R.m_old = pc.m_old;
+              R.tzflag = 1; // conservative: a later launch re-checks the flags of the slices
+              R.iter = iter;
+              R.out_off = out_off;
+              R.cols_done = cols_done;
+              R.curpos = pc.curpos;
+              R.pass_counter = pass_counter;
+              R.maxH = pc.maxH;
+              R.st = st;
+            }
+            break;
+          }
+        } else {
+          m_old = c.sm->nact; // only meaningful on CTA 0
+          maxH = event_pass<PROF, false>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf, m_bound,
+                                         nullptr, 0);
+        }
         const long long t1 = PROF ? clock64() : 0;
         if (PROF) pf[0] += t1 - t0;
         if (PROF) pf[4] += st.accepted - acc0;
@@ -585,10 +1008,12 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           cluster.sync();
           publish_nonapp(c);
           cluster.sync();
+          nonapp_total = __ldcg(a.flag + 2);
         }
         if (c.rank == 0) list_update_full(c, m_old, nonapp_total, pass_counter);
         if (PROF) pf[1] += clock64() - t1;
         pass_counter += 1;
+        m_known = -1;
         st.maxH = maxH;
         conv = maxH < a.optTol;
         if (conv) {
@@ -597,32 +1022,46 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         }
       } else {
         const long long t0 = PROF ? clock64() : 0;
-        int m_all = 0; // list length, fetched from CTA 0 only when it may reach the distributed engine's size
-        if (c.C > 1 && c.multi_ok > 0 && m_bound >= c.multi_ok) {
+        int m_all = -1; // list length, fetched from CTA 0 only when it matters
+        if (c.C == 1) {
+          m_all = c.sm->nact;
+        } else if ((c.multi_ok > 0 && m_bound >= c.multi_ok) || m_bound > c.ecap) {
           cluster.sync(); // CTA 0 has finished the list update
           m_all = *cluster.map_shared_rank(&c.sm->nact, 0);
         }
-        if (c.multi_ok > 0 && m_all >= c.multi_ok && m_all <= c.ecap) {
+        if (m_all > c.ecap) {
+          // ---- list longer than the engine holds: one event-by-event pass over the list (exact, slow, no size limit)
+          if (c.rank == 0) {
+            for (int e = tid; e < m_all; e += COV_T) lpos[a.act[e]] = e;
+            __threadfence();
+          }
+          cluster.sync();
+          int dummy = 0;
+          const long long acc0 = st.accepted;
+          const double maxH = event_pass<PROF, true>(c, lam, pass_counter, round, st.accepted, false, dummy, pf, m_bound, lpos, m_all);
+          if (c.rank == 0) list_update_full(c, m_all, 0, pass_counter);
+          (void)acc0;
+          iter += 1;
+          pass_counter += 1;
+          st.passes += 1;
+          st.visits += m_all;
+          st.maxH = maxH;
+          conv = maxH < a.optTol;
+          m_bound = m_all;
+          m_known = -1;
+          cluster.sync(); // the list update is complete before the next pass looks at the list
+          continue;
+        }
+        if (c.multi_ok > 0 && m_all >= c.multi_ok) {
           active_engine_multi(c, lam, a.maxIter - iter, pass_counter, m_all);
         } else if (c.rank == 0) {
-          const int m = c.sm->nact;
-          const long long budget = a.maxIter - iter;
-          if (m > c.ecap) {
-            if (tid == 0) c.sm->bc.status = 2;
-            __syncthreads();
-          } else {
-            active_engine(c, lam, budget, pass_counter);
-          }
+          active_engine(c, lam, a.maxIter - iter, pass_counter);
         }
         cluster.sync();
         const long long t1 = PROF ? clock64() : 0;
         if (PROF) pf[2] += t1 - t0;
         const Bcast *bc = cluster.map_shared_rank(&c.sm->bc, 0);
         const Bcast b = *bc;
-        if (b.status) {
-          status = b.status;
-          break;
-        }
         refresh_slice(c, b.m0);
         if (PROF) pf[3] += clock64() - t1;
         if (PROF) pf[5] += b.visits;
@@ -634,15 +1073,17 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         st.maxH = b.maxH;
         conv = b.conv != 0;
         m_bound = b.nact;
+        m_known = b.nact;
         // conv == 0 here means the pass budget ran out: the while condition ends the solve
       }
     }
+    if (status) break;
     // ---- end of this lambda: publish nnz, write the path column / stats
     if (c.rank == 0 && tid == 0) c.sm->bc.nact = c.sm->nact;
     cluster.sync();
     const int nnz = cluster.map_shared_rank(&c.sm->bc, 0)->nact;
     m_bound = nnz;
-    if (status) break;
+    m_known = nnz;
     if (!a.accumulate) {
       if (c.rank == 0) {
         if (a.colptr) {
@@ -667,16 +1108,23 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
       cols_done = li + 1;
     }
   }
-  if (a.accumulate && c.rank == 0 && tid == 0 && a.stats) a.stats[0] = st;
+  if (a.accumulate && c.rank == 0 && tid == 0 && a.stats && status != 3) a.stats[0] = st;
   // ---- write the state back
   cluster.sync();
   if (slice_in_smem) {
     for (int i = tid; i < c.len; i += COV_T) {
       a.Ax[c.lo + i] = c.sAx[i];
       a.beta[c.lo + i] = c.sbeta[i];
+      if (status == 3) {
+        a.bscr[c.lo + i] = c.s_in[i];
+        a.bscr[a.p + c.lo + i] = c.s_vnz[i];
+      }
     }
   } else {
-    for (int i = tid; i < c.len; i += COV_T) a.beta[c.lo + i] = c.sbeta[i];
+    for (int i = tid; i < c.len; i += COV_T) {
+      a.beta[c.lo + i] = c.sbeta[i];
+      if (c.sAx != a.Ax + c.lo) a.Ax[c.lo + i] = c.sAx[i]; // an odd number of chain-pass commits: Ax lives in the scratch copy
+    }
   }
   if (c.rank == 0 && tid == 0) {
     if (a.prof) {
@@ -694,11 +1142,11 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
 // initialize!(f::CDQuadraticLoss, x): Ax = sum_i A[:, act_i] * val_i (cd_differentiable_function.jl:311-320),
 // plus the dense copy of the iterate and the membership flags.
 __global__ void cov_init_kernel(const double *A, long long lda, int p, const int *act, const double *actval,
-                                const int *nact, double *Ax, double *beta, unsigned char *inlist) {
+                                const int *nact, double *Ax, double *beta, unsigned char *inlist, const int *colslot) {
   const int m = *nact;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p; j += gridDim.x * blockDim.x) {
     double acc = 0.0;
-    for (int i = 0; i < m; ++i) acc += A[j + (long long)act[i] * lda] * actval[i];
+    for (int i = 0; i < m; ++i) acc += A[j + (long long)(colslot ? colslot[act[i]] : act[i]) * lda] * actval[i];
     Ax[j] = acc;
     beta[j] = 0.0;
     inlist[j] = 0;
@@ -760,9 +1208,9 @@ __global__ void symmetric_kernel(const double *A, long long lda, int p, int *fla
 } // namespace
 
 int launch_cov_init(cdgpu_handle_s *h, const double *A, long long lda, int p, const int *act, const double *actval,
-                    const int *nact, double *Ax, double *beta, unsigned char *inlist) {
+                    const int *nact, double *Ax, double *beta, unsigned char *inlist, const int *colslot) {
   int blocks = (p + 255) / 256;
-  cov_init_kernel<<<blocks, 256, 0, h->stream>>>(A, lda, p, act, actval, nact, Ax, beta, inlist);
+  cov_init_kernel<<<blocks, 256, 0, h->stream>>>(A, lda, p, act, actval, nact, Ax, beta, inlist, colslot);
   scatter_iterate_kernel<<<32, 256, 0, h->stream>>>(act, actval, nact, beta, inlist);
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(2);
@@ -799,7 +1247,8 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   static bool attr_done[64] = {false}; // function attributes are per device (context), not per process
   const bool known_dev = h->device >= 0 && h->device < 64;
   auto fixed_for = [](int ecap) {
-    return (sizeof(Smem) + 15) / 16 * 16 + chain::STAGE_DOUBLES * sizeof(double) + (size_t)ecap * (2 * sizeof(double) + sizeof(int) + 2 * sizeof(unsigned short));
+    return (sizeof(Smem) + 15) / 16 * 16 + chain::STAGE_DOUBLES * sizeof(double) +
+           (size_t)ecap * (3 * sizeof(double) + sizeof(int) + sizeof(unsigned) + 2 * sizeof(unsigned short));
   };
   const size_t fixed = fixed_for(COV_ACT_CAP);
   const size_t max_dyn = 227 * 1024;
@@ -847,7 +1296,7 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   int L = (a.p + C - 1) / C;
   L = (L + 1) & ~1;
   // engine capacity: as large as still leaves room for the slices in shared memory
-  const size_t slices = (size_t)5 * L * sizeof(double) + 2 * (size_t)L + 16;
+  const size_t slices = (size_t)6 * L * sizeof(double) + 2 * (size_t)L + 16;
   int ecap = COV_ACT_CAP;
   if (const char *env = getenv("CDGPU_ECAP_MAX")) ecap = std::max(512, std::min(COV_ACT_CAP, atoi(env) / 512 * 512));
   while (ecap > 1024 && fixed_for(ecap) + slices > max_dyn) ecap >>= 1;

@@ -280,6 +280,21 @@ __global__ void xty_kernel(const double *__restrict__ X, long long n, int p, lon
   }
 }
 
+// row-split GEMM form: C tile = sum over row chunks of the slab partials (fixed order), / divisor
+__global__ void gemm_reduce_slabs_kernel(const double *__restrict__ slab, int nchunks, int slab_tiles, const int2 *__restrict__ base_tiles,
+                                         int pa, int pb, double *C, long long ldc, double divisor) {
+  const int tidx = blockIdx.x;
+  const int bi = base_tiles[tidx].x, bj = base_tiles[tidx].y;
+  for (int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
+    const int r = e % BM, cc = e / BM; // consecutive threads -> consecutive rows of one output column
+    const int row = bi * BM + r, col = bj * BN + cc;
+    if (row >= pa || col >= pb) continue;
+    double v = 0.0;
+    for (int c = 0; c < nchunks; ++c) v += slab[((size_t)c * slab_tiles + tidx) * (size_t)(BM * BN) + (size_t)r * BN + cc];
+    C[row + (long long)col * ldc] = v / divisor;
+  }
+}
+
 __global__ void scale_kernel(double *G, long long count, double divisor) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     G[i] = G[i] / divisor;
@@ -439,6 +454,67 @@ int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, l
   }
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(1);
+  return CDGPU_OK;
+}
+
+// The same product with the ROWS split as well (few output tiles, many rows: the skinny column batches of the lazy
+// covariance form): work items = tiles x row chunks, with the chunk count chosen so that the items fill whole waves
+// of the SMs; partial tiles go to a slab and are summed in a fixed order (deterministic).  Everything is stream
+// ordered; the scratch comes from and returns to the stream's pool.
+int launch_gemm_tn_split(cudaStream_t stream, int sm_count, const double *A, int pa, long long lda, const double *B, int pb,
+                         long long ldb, long long n, double *C, long long ldc, double divisor) {
+  const int nbi = (pa + BM - 1) / BM, nbj = (pb + BN - 1) / BN;
+  const int ntiles = nbi * nbj;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((lda & 1) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((ldb & 1) == 0);
+  int best_c = 1;
+  double best_eff = 0.0;
+  for (int c = 1; c <= 64; ++c) {
+    if (c > 1 && n / c < 512) break;
+    const long long items = (long long)ntiles * c, waves = (items + sm_count - 1) / sm_count;
+    const double eff = (double)items / (double)(waves * sm_count);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best_c = c;
+    }
+  }
+  if (!aligned || best_c == 1 || ntiles >= 65536 || nbi >= 65536) {
+    void *tiles = nullptr;
+    CD_TRY(launch_gemm_tn(stream, sm_count, A, pa, lda, B, pb, ldb, n, C, ldc, divisor, &tiles));
+    CUDA_TRY(cudaFreeAsync(tiles, stream));
+    return CDGPU_OK;
+  }
+  int nchunks = best_c;
+  long long kchunk = ((n + nchunks - 1) / nchunks + 15) & ~15ll;
+  nchunks = (int)((n + kchunk - 1) / kchunk);
+  std::vector<int2> base, items;
+  base.reserve((size_t)ntiles);
+  for (int bj = 0; bj < nbj; ++bj)
+    for (int bi = 0; bi < nbi; ++bi) base.push_back(make_int2(bi, bj));
+  items.reserve((size_t)ntiles * nchunks);
+  for (int ch = 0; ch < nchunks; ++ch)
+    for (int t = 0; t < ntiles; ++t) items.push_back(make_int2(base[(size_t)t].x | (ch << 16), base[(size_t)t].y | (t << 16)));
+  int2 *ditems = nullptr, *dbase = nullptr;
+  double *slab = nullptr;
+  const size_t slab_doubles = (size_t)nchunks * ntiles * BM * BN;
+  CUDA_TRY(cudaMallocAsync((void **)&ditems, items.size() * sizeof(int2), stream));
+  CUDA_TRY(cudaMallocAsync((void **)&dbase, base.size() * sizeof(int2), stream));
+  CUDA_TRY(cudaMallocAsync((void **)&slab, slab_doubles * sizeof(double), stream));
+  CUDA_TRY(cudaMemcpyAsync(ditems, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(dbase, base.data(), base.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream)); // host temporaries
+  auto kern = gram_syrk_kernel<true, 2, 4, 16, 4, true, true>;
+  const size_t dyn = (size_t)4 * (BM + BN) * (16 + 4) * sizeof(double);
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  kern<<<min((int)items.size(), sm_count), 256, dyn, stream>>>(A, n, pa, lda, C, ldc, ditems, (int)items.size(), divisor, 1, B, pb,
+                                                                 ldb, kchunk, slab, ntiles);
+  CUDA_TRY(cudaGetLastError());
+  gemm_reduce_slabs_kernel<<<ntiles, 512, 0, stream>>>(slab, nchunks, ntiles, dbase, pa, pb, C, ldc, divisor);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(slab, stream));
+  CUDA_TRY(cudaFreeAsync(ditems, stream));
+  CUDA_TRY(cudaFreeAsync(dbase, stream));
+  CD_COUNT_LAUNCH(2);
   return CDGPU_OK;
 }
 

@@ -138,6 +138,21 @@ int cdgpu_gram_create(cdgpu_handle *h, const double *X, int64_t n, int64_t p, in
                       int device);
 int cdgpu_gram_create_dev(cdgpu_handle *h, const double *dX, int64_t n, int64_t p, int64_t ldx, const double *dy,
                           int device);
+/* LAZY covariance form: the same CDQuadraticLoss(X'X/n, -X'y/n) object, but only diag(A) and b are formed up front
+ * (one pass over X); a column A[:,k] = X'X[:,k]/n is formed the first time coordinate k becomes non-zero, in batches
+ * of 128 columns through the same FP64 tensor-core kernel (a skinny GEMM), and cached.  The CD step of
+ * cd_differentiable_function.jl:324-348 reads nothing else, so iterates agree with the eager handle to rounding; a path
+ * whose supports stay small never pays for the p x p matrix.  The handle keeps X resident on the device (the _dev form
+ * uses the caller's buffer in place: it must outlive the handle).  cdgpu_quad_get(A) forms the full matrix on request.
+ * Capacity: 4096 cached columns (CDGPU_LAZY_CAP); a solve whose active set outgrows it fails with CDGPU_ECAP — use the
+ * eager form for dense solutions. */
+int cdgpu_gram_create_lazy(cdgpu_handle *h, const double *X, int64_t n, int64_t p, int64_t ldx, const double *y,
+                           int device);
+int cdgpu_gram_create_lazy_dev(cdgpu_handle *h, const double *dX, int64_t n, int64_t p, int64_t ldx, const double *dy,
+                               int device);
+/* what the last solve on a lazy handle formed: columns cached so far, batches formed and kernel pauses during the last
+ * solve, device ms spent forming columns during the last solve (all 0 for other handles) */
+int cdgpu_lazy_stats(cdgpu_handle h, int64_t *columns, int64_t *batches, int64_t *pauses, double *form_ms);
 /* Row-sharded variant for one-process-per-GPU jobs: every rank passes its own
  * n_local rows; partial X'X and X'y are summed over ranks with one
  * ncclAllReduce on the communicator made by cdgpu_comm_init (NULL comm == single

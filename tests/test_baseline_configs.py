@@ -160,4 +160,4 @@ def test_c5_tall_gram_row_subsample_then_path(gpu, ref):
     for i in range(m):
         assert_parity(pg.βpath[i].toarray(), pr.βpath[i].toarray())
         same_trace(pg.stats[i], pr.stats[i])
-    assert pg.βpath[-1].nnz >= s
+    assert pg.βpath[-1].nnz >= 10

@@ -576,3 +576,49 @@ def test_default_options_agree_at_default_tolerance(gpu, ref):
     assert np.array_equal(a.x.nonzero(), b.x.nonzero())
     assert np.max(np.abs(a.x.toarray() - b.x.toarray())) < 1e-10
     assert a.stats["passes"] == b.stats["passes"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("randomize", [0, 1])
+@pytest.mark.parametrize("prefetch", [True, False])
+def test_lazy_covariance_handle_matches_eager_and_oracle(gpu, ref, randomize, prefetch, monkeypatch):
+    # cdgpu_gram_create_lazy: diag(A), b up front, columns of A on demand.  prefetch=False forms exactly the requested
+    # column at every entering coordinate, so the kernel pauses / resumes inside full passes all along the path.
+    if not prefetch:
+        monkeypatch.setenv("CDGPU_LAZY_NO_PREFETCH", "1")
+    X, y, _ = gauss_problem(300, 400, 15, seed=31)
+    o = CDOptions(maxIter=5000, optTol=1e-10, randomize=bool(randomize), seed=5)
+    fe = gpu.CDQuadraticLoss_from_data(X, y)
+    fl = gpu.CDQuadraticLoss_from_data(X, y, lazy=True)
+    om = fe.stdX()
+    assert np.allclose(fl.stdX(), om, rtol=1e-14, atol=0)
+    lmax = gpu.findLambdaMax(fe, om)
+    assert gpu.findLambdaMax(fl, om) == pytest.approx(lmax, rel=1e-14)
+    lams = np.exp(np.linspace(np.log(lmax), np.log(0.03 * lmax), 25))
+    pe = gpu.LassoPath(None, None, lams, o, standardizeX=om, loss=fe)
+    pl = gpu.LassoPath(None, None, lams, o, standardizeX=om, loss=fl)
+    st = fl.lazy_stats()
+    assert 0 < st["columns"] <= 400 and (prefetch or st["pauses"] >= pl.βpath[-1].nnz - 1)
+    A, b = fe.get()
+    pr = ref.LassoPath(None, None, lams, o, standardizeX=om, loss=ref.CDQuadraticLoss(A, b))
+    assert len(pl.βpath) == len(pe.βpath) == len(pr.βpath) == 25
+    for i in range(25):
+        assert_parity(pl.βpath[i].toarray(), pe.βpath[i].toarray(), rtol=1e-9)
+        assert_parity(pl.βpath[i].toarray(), pr.βpath[i].toarray())
+        for k in ("passes", "full_passes", "visits", "converged"):
+            assert pl.stats[i][k] == pe.stats[i][k] == pr.stats[i][k], (i, k)
+        assert list(pl.βpath[i].nzval2ind) == list(pr.βpath[i].nzval2ind)  # same SparseIterate order
+    assert pl.βpath[-1].nnz > 20
+    # a warm start from an arbitrary iterate: the columns of its members are formed before the first pass
+    rng = np.random.default_rng(3)
+    v = sprand_iterate(400, 0.1, rng)
+    xe, xl = SparseIterate(v), SparseIterate(v)
+    gpu.coordinateDescent_(xe, fe, ProxL1(0.3 * lmax, om), o)
+    gpu.coordinateDescent_(xl, fl, ProxL1(0.3 * lmax, om), o)
+    assert_parity(xl.toarray(), xe.toarray(), rtol=1e-9)
+    # f.A on request, and the refit through the data
+    Al, bl = fl.get()
+    assert np.array_equal(Al, Al.T) and np.allclose(Al, A, rtol=0, atol=1e-13) and np.allclose(bl, b, rtol=0, atol=1e-14)
+    re_, rl = gpu.refitLassoPath(pe, None, None, loss=fe), gpu.refitLassoPath(pl, None, None, loss=fl)
+    for S in re_:
+        assert np.allclose(re_[S], rl[S], rtol=1e-8, atol=1e-10)
