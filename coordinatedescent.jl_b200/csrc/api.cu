@@ -10,6 +10,7 @@
 #include <chrono>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -194,6 +195,8 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   CUDA_TRY(cudaMemsetAsync(h->dnact, 0, sizeof(int), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 8 * sizeof(int), h->stream));
   CD_TRY(device_sm_count(h->device, &h->sm_count));
+  CUDA_TRY(cudaEventCreate(&h->sw_ev0));
+  CUDA_TRY(cudaEventCreate(&h->sw_ev1));
   return CDGPU_OK;
 }
 
@@ -222,6 +225,8 @@ API int cdgpu_destroy(cdgpu_handle h) {
   dfree(h->dresume);
   dfree(h->dbatch);
   delete[] h->hslot;
+  if (h->sw_ev0) cudaEventDestroy(h->sw_ev0);
+  if (h->sw_ev1) cudaEventDestroy(h->sw_ev1);
   if (h->lz_ev0) cudaEventDestroy(h->lz_ev0);
   if (h->lz_ev1) cudaEventDestroy(h->lz_ev1);
   if (h->stream) stream_set_release(h->device, StreamSet{h->stream, h->ev0, h->ev1});
@@ -569,6 +574,86 @@ API int cdgpu_gram_create(cdgpu_handle *out, const double *X, int64_t n, int64_t
   });
 }
 
+// ------------------------------------------------------------ host -> device staging --
+// A Julia Matrix{Float64} is ordinary pageable memory: cudaMemcpy from it goes through the driver's own small staging
+// buffers on ONE thread (10-20 GB/s).  For large inputs the library stages by itself: two pinned buffers (kept for the
+// life of the process), several threads copy a block of columns into one while the DMA of the previous block runs
+// from the other.  Pinned / registered sources skip the staging and are copied directly.
+struct H2DStager {
+  std::mutex mu;
+  double *buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  size_t cap = 0; // doubles per buffer
+};
+static H2DStager g_stager;
+static bool host_is_pageable(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+// dst (device, column pitch ld_dst doubles) <- src (host, pitch ld_src): ncols columns of n doubles, in blocks of
+// columns; after_block(c0, c1) is called once the copy of columns [c0, c1) has been ENQUEUED on `cs` (the caller
+// orders its consumers behind it with an event).  nblocks_hint: blocks wanted by the caller (0: by size).
+template <class F>
+static int h2d_columns(double *dst, int64_t ld_dst, const double *src, int64_t ld_src, int64_t n, int64_t ncols,
+                       cudaStream_t cs, int nblocks_hint, F after_block) {
+  const size_t total = (size_t)n * (size_t)ncols * sizeof(double);
+  const bool stage = total >= ((size_t)32 << 20) && host_is_pageable(src) && !getenv("CDGPU_NO_STAGING");
+  int nthreads = (int)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency() / 2));
+  if (const char *env = getenv("CDGPU_H2D_THREADS")) nthreads = std::max(1, atoi(env));
+  if (!stage) {
+    const int nb = std::max(1, nblocks_hint);
+    for (int bi = 0; bi < nb; ++bi) {
+      const int64_t c0 = ncols * bi / nb, c1 = ncols * (bi + 1) / nb;
+      if (c1 <= c0) continue;
+      CUDA_TRY(cudaMemcpy2DAsync(dst + c0 * ld_dst, ld_dst * sizeof(double), src + c0 * ld_src, ld_src * sizeof(double),
+                                 (size_t)n * sizeof(double), (size_t)(c1 - c0), cudaMemcpyHostToDevice, cs));
+      CD_TRY(after_block(c0, c1));
+    }
+    return CDGPU_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_stager.mu);
+  const size_t want = ((size_t)64 << 20) / sizeof(double); // 64 MiB per buffer
+  if (g_stager.cap < want) {
+    for (int i = 0; i < 2; ++i) {
+      if (g_stager.buf[i]) cudaFreeHost(g_stager.buf[i]);
+      g_stager.buf[i] = nullptr;
+      CUDA_TRY(cudaHostAlloc((void **)&g_stager.buf[i], want * sizeof(double), cudaHostAllocPortable));
+      if (!g_stager.ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&g_stager.ev[i], cudaEventDisableTiming));
+    }
+    g_stager.cap = want;
+  }
+  int64_t cols_per = std::max<int64_t>(1, (int64_t)(g_stager.cap / (size_t)ld_dst));
+  if (nblocks_hint > 0) cols_per = std::min<int64_t>(cols_per, std::max<int64_t>(1, (ncols + nblocks_hint - 1) / nblocks_hint));
+  bool used[2] = {false, false};
+  int which = 0;
+  for (int64_t c0 = 0; c0 < ncols; c0 += cols_per, which ^= 1) {
+    const int64_t c1 = std::min<int64_t>(ncols, c0 + cols_per), nc = c1 - c0;
+    if (used[which]) CUDA_TRY(cudaEventSynchronize(g_stager.ev[which])); // its previous DMA has drained
+    double *pb = g_stager.buf[which];
+    auto work = [&](int t) {
+      for (int64_t c = c0 + t; c < c1; c += nthreads) {
+        memcpy(pb + (size_t)(c - c0) * (size_t)ld_dst, src + (size_t)c * (size_t)ld_src, (size_t)n * sizeof(double));
+        if (ld_dst > n) memset(pb + (size_t)(c - c0) * (size_t)ld_dst + n, 0, (size_t)(ld_dst - n) * sizeof(double));
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    CUDA_TRY(cudaMemcpyAsync(dst + c0 * ld_dst, pb, (size_t)nc * (size_t)ld_dst * sizeof(double), cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaEventRecord(g_stager.ev[which], cs));
+    used[which] = true;
+    CD_TRY(after_block(c0, c1));
+  }
+  for (int i = 0; i < 2; ++i)
+    if (used[i]) CUDA_TRY(cudaEventSynchronize(g_stager.ev[i])); // the pinned buffers are free again when we return
+  return CDGPU_OK;
+}
+
 // ------------------------------------------------------- lazy covariance form --
 // (lazy_gram.cu) diag(A) and b up front, columns of A = X'X/n formed on demand in batches of 128 by the DMMA GEMM.
 static const int LZ_BATCH = 128;
@@ -749,24 +834,17 @@ API int cdgpu_gram_create_lazy(cdgpu_handle *out, const double *X, int64_t n, in
       cudaEventDestroy(e0);
     }
     const int NBLK = (int)std::min<int64_t>(16, std::max<int64_t>(1, p / 512));
-    int rc = CDGPU_OK;
-    for (int bi = 0; bi < NBLK && rc == CDGPU_OK; ++bi) {
-      const int64_t c0 = p * bi / NBLK, c1 = p * (bi + 1) / NBLK;
-      if (c1 <= c0) continue;
-      e = cudaMemcpy2DAsync(dXs + c0 * ld, ld * sizeof(double), X + c0 * ldx, ldx * sizeof(double), n * sizeof(double),
-                            (size_t)(c1 - c0), cudaMemcpyHostToDevice, cs);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[nev], cudaEventDisableTiming);
-      if (e == cudaSuccess) {
+    int rc = h2d_columns(dXs, ld, X, ldx, n, p, cs, NBLK, [&](int64_t c0, int64_t c1) -> int {
+      if (nev >= 16) cudaEventDestroy(ev[--nev]); // more blocks than events (staging splits by size): recycle the last one
+      cudaError_t e2 = cudaEventCreateWithFlags(&ev[nev], cudaEventDisableTiming);
+      if (e2 == cudaSuccess) {
         nev += 1;
-        e = cudaEventRecord(ev[nev - 1], cs);
+        e2 = cudaEventRecord(ev[nev - 1], cs);
       }
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, ev[nev - 1], 0);
-      if (e != cudaSuccess) {
-        rc = cdgpu_set_error(CDGPU_ECUDA, "H2D staging: %s", cudaGetErrorString(e));
-        break;
-      }
-      rc = launch_diag_xty(h, dXs + c0 * ld, n, (int)(c1 - c0), ld, dys, (double)n, h->ddiag + c0, h->dy + c0, h->daux + c0, 0, 1);
-    }
+      if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(h->stream, ev[nev - 1], 0);
+      if (e2 != cudaSuccess) return cdgpu_set_error(CDGPU_ECUDA, "H2D staging: %s", cudaGetErrorString(e2));
+      return launch_diag_xty(h, dXs + c0 * ld, n, (int)(c1 - c0), ld, dys, (double)n, h->ddiag + c0, h->dy + c0, h->daux + c0, 0, 1);
+    });
     if (rc == CDGPU_OK) {
       e = cudaEventRecord(h->ev1, h->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -780,6 +858,20 @@ API int cdgpu_gram_create_lazy(cdgpu_handle *out, const double *X, int64_t n, in
     *out = g.release();
     return CDGPU_OK;
   });
+}
+
+API int cdgpu_sweep_ms(cdgpu_handle h, double *ms) {
+  if (!h || !ms) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (h->sweep_pending) {
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->sw_ev1));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->sw_ev0, h->sw_ev1));
+    h->sweep_ms = t;
+    h->sweep_pending = false;
+  }
+  *ms = h->sweep_ms;
+  return CDGPU_OK;
 }
 
 API int cdgpu_lazy_stats(cdgpu_handle h, int64_t *columns, int64_t *batches, int64_t *pauses, double *form_ms) {
@@ -1018,12 +1110,21 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
       CD_TRY(lazy_ensure(h, need, rc.domega, h->lz_used == 0 && !getenv("CDGPU_LAZY_NO_PREFETCH")));
       CUDA_TRY(cudaMemsetAsync(h->dresume, 0, sizeof(CovResume), h->stream));
     }
+    if (prof) CUDA_TRY(cudaMemsetAsync(a.prof, 0, 24 * sizeof(long long), h->stream));
+    h->sweep_ms = 0.0;
     CD_TRY(launch_cov_init(h, a.A, a.lda, a.p, a.act, a.actval, a.nact, a.Ax, a.beta, a.inlist, a.colslot));
+    CUDA_TRY(cudaEventRecord(h->sw_ev0, h->stream));
     CD_TRY(launch_cov_path(h, a));
+    CUDA_TRY(cudaEventRecord(h->sw_ev1, h->stream));
     while (h->lazy) { // paused at an entering coordinate without a column: form a batch, resume
       int f[2] = {0, 0};
       CUDA_TRY(cudaMemcpyAsync(f, h->dflag, sizeof f, cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream));
+      {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->sw_ev0, h->sw_ev1));
+        h->sweep_ms += ms;
+      }
       if (f[0] != 3) break;
       CovResume R;
       CUDA_TRY(cudaMemcpy(&R, h->dresume, sizeof R, cudaMemcpyDeviceToHost));
@@ -1034,8 +1135,11 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
       const int one = 1;
       CUDA_TRY(cudaMemcpyAsync(&h->dresume->valid, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream)); // `one` is a stack temporary
+      CUDA_TRY(cudaEventRecord(h->sw_ev0, h->stream));
       CD_TRY(launch_cov_path(h, a));
+      CUDA_TRY(cudaEventRecord(h->sw_ev1, h->stream));
     }
+    if (!h->lazy) h->sweep_pending = true; // eager: one launch, its time is read when somebody asks (no extra sync here)
     if (prof) {
       long long pf[24];
       CUDA_TRY(cudaMemcpyAsync(pf, a.prof, sizeof pf, cudaMemcpyDeviceToHost, h->stream));

@@ -274,6 +274,9 @@ struct cdgpu_handle_s {
   cudaEvent_t lz_ev0 = nullptr, lz_ev1 = nullptr;
   int lz_batches = 0, lz_pauses = 0; // statistics of the last solve
   double lz_form_ms = 0.0;           // device time spent forming columns during the last solve
+  double sweep_ms = 0.0;             // device time of the covariance sweep-kernel launches of the last solve
+  bool sweep_pending = false;
+  cudaEvent_t sw_ev0 = nullptr, sw_ev1 = nullptr;
 };
 
 // device selection (+ memory-pool release threshold) and the per-device free list of stream/event sets (api.cu)

@@ -337,19 +337,39 @@ __device__ __forceinline__ unsigned visit_pos(bool ordered, const PermKey &pk, i
 
 // Ax2[slice] = Ax[slice] + sum_{t < tend} A[slice, k_t] * h_t (steps in order, non-fused) [+ A[slice, kx] * hx].
 // TEST: every still-unvisited non-member is tested where its own visit falls among the steps; returns this
-// thread's earliest mover through best/bk/bh/bnw and records "value exactly zero" in s_vnz.
+// thread's earliest mover and records "value exactly zero" in s_vnz.  Not inlined, arguments by value: the sweep
+// gets the whole register file for its NE x NQ loads in flight (the path kernel itself sits at the 128-register cap).
+struct SweepIn {
+  const double *A;
+  long long lda;
+  const int *colslot;
+  const double *sAx, *sb, *sainv, *sw, *sbeta;
+  double *sAx2;
+  const int *rk;
+  const double *rh;
+  const unsigned *rpos;
+  unsigned char *s_in, *s_vnz;
+  int *tz;
+  int lo, len, tend, kx, ordered;
+  double lam, hx;
+  long long curpos;
+  PermKey pk;
+};
+struct SweepOut {
+  unsigned best;
+  int bk;
+  double bh, bnw;
+};
 template <bool TEST>
-__device__ __forceinline__ void sweep_members(Ctx &c, double lam, int tend, int kx, double hx, long long curpos,
-                                              bool ordered, const PermKey &pk, unsigned &best, int &bk, double &bh,
-                                              double &bnw) {
-  const CovArgs &a = c.a;
-  const int tid = threadIdx.x, lo = c.lo, len = c.len;
+__device__ __noinline__ SweepOut sweep_members(const SweepIn c) {
+  const int tid = threadIdx.x, lo = c.lo, len = c.len, tend = c.tend;
   const double *__restrict__ sAx = c.sAx;
   double *__restrict__ sAx2 = c.sAx2;
-  const int *__restrict__ rk = c.s_act;
-  const double *__restrict__ rh = c.e_h;
-  const unsigned *__restrict__ rpos = c.e_vpos;
-  constexpr int NE = 3, NQ = 8; // elements per thread and chain steps per batch: NE*NQ independent loads in flight
+  const int *__restrict__ rk = c.rk;
+  const double *__restrict__ rh = c.rh;
+  const unsigned *__restrict__ rpos = c.rpos;
+  SweepOut o{KEY_NONE, 0, 0.0, 0.0};
+  constexpr int NE = 3, NQ = 4; // elements per thread and chain steps per batch: NE*NQ independent loads in flight
   int tzseen = 0;
   for (int base = 0; base < len; base += NE * COV_T) {
     double acc[NE];
@@ -363,8 +383,8 @@ __device__ __forceinline__ void sweep_members(Ctx &c, double lam, int tend, int 
       ti[u] = -1;
       pj[u] = 0;
       if (TEST && valid && !c.s_in[i]) {
-        pj[u] = visit_pos(ordered, pk, lo + i);
-        if ((long long)pj[u] > curpos) { // lower bound: number of chain entries visited before this coordinate
+        pj[u] = visit_pos(c.ordered != 0, c.pk, lo + i);
+        if ((long long)pj[u] > c.curpos) { // lower bound: number of chain entries visited before this coordinate
           int l = 0, r = tend;
           while (l < r) {
             const int mid = (l + r) >> 1;
@@ -374,24 +394,27 @@ __device__ __forceinline__ void sweep_members(Ctx &c, double lam, int tend, int 
         }
       }
     }
+    double accv[NE]; // the running sum at the moment of the element's own visit (captured by a select: no divergence)
+#pragma unroll
+    for (int u = 0; u < NE; ++u) accv[u] = acc[u];
     auto test = [&](int u) {
       const int i = base + tid + u * COV_T;
       const double ainv = c.sainv[i];
-      const double g = acc[u] + c.sb[i];
+      const double g = accv[u] + c.sb[i];
       const double old = c.sbeta[i];
       const double t = __dmul_rn(g, ainv);
-      const double thr = __dmul_rn(__dmul_rn(ainv, lam), c.sw[i]);
+      const double thr = __dmul_rn(__dmul_rn(ainv, c.lam), c.sw[i]);
       const double v = __dsub_rn(old, t);
       const double nw = cd_shrink(v, thr);
       const double h = nw - old;
       const unsigned char nz = (unsigned char)(v != 0.0); // `x[k] -= b*a` appends iff the value is non-zero
       c.s_vnz[i] = nz;
       if (!nz) tzseen = 1;
-      if (h != 0.0 && pj[u] < best) {
-        best = pj[u];
-        bk = lo + i;
-        bh = h;
-        bnw = nw;
+      if (h != 0.0 && pj[u] < o.best) {
+        o.best = pj[u];
+        o.bk = lo + i;
+        o.bh = h;
+        o.bnw = nw;
       }
     };
     for (int t0 = 0; t0 < tend; t0 += NQ) {
@@ -400,7 +423,8 @@ __device__ __forceinline__ void sweep_members(Ctx &c, double lam, int tend, int 
       for (int q = 0; q < NQ; ++q) {
         const bool on = t0 + q < tend;
         hq[q] = on ? rh[t0 + q] : 0.0;
-        const double *col = col_ptr(a, on ? rk[t0 + q] : rk[t0]) + lo + base + tid;
+        const int k = on ? rk[t0 + q] : rk[t0];
+        const double *col = c.A + (long long)(c.colslot ? __ldg(c.colslot + k) : k) * c.lda + lo + base + tid;
 #pragma unroll
         for (int u = 0; u < NE; ++u)
           x[q][u] = (hq[q] != 0.0 && base + tid + u * COV_T < len) ? __ldg(col + u * COV_T) : 0.0;
@@ -409,27 +433,28 @@ __device__ __forceinline__ void sweep_members(Ctx &c, double lam, int tend, int 
       for (int q = 0; q < NQ; ++q) {
 #pragma unroll
         for (int u = 0; u < NE; ++u) {
-          if (TEST && ti[u] == t0 + q) test(u);
           if (hq[q] != 0.0) acc[u] = __dadd_rn(acc[u], __dmul_rn(x[q][u], hq[q]));
+          if (TEST) accv[u] = (t0 + q < ti[u]) ? acc[u] : accv[u]; // steps 0 .. ti-1 precede the visit
         }
       }
     }
     if (TEST) {
 #pragma unroll
       for (int u = 0; u < NE; ++u)
-        if (ti[u] >= tend) test(u); // visited after every chain entry
+        if (ti[u] >= 0) test(u); // uniform: every lane tests its elements once, after the sweep
     }
-    if (kx >= 0) {
-      const double *col = col_ptr(a, kx) + lo + base + tid;
+    if (c.kx >= 0) {
+      const double *col = c.A + (long long)(c.colslot ? __ldg(c.colslot + c.kx) : c.kx) * c.lda + lo + base + tid;
 #pragma unroll
       for (int u = 0; u < NE; ++u)
-        if (base + tid + u * COV_T < len) acc[u] = __dadd_rn(acc[u], __dmul_rn(__ldg(col + u * COV_T), hx));
+        if (base + tid + u * COV_T < len) acc[u] = __dadd_rn(acc[u], __dmul_rn(__ldg(col + u * COV_T), c.hx));
     }
 #pragma unroll
     for (int u = 0; u < NE; ++u)
       if (base + tid + u * COV_T < len) sAx2[base + tid + u * COV_T] = acc[u];
   }
-  if (TEST && tzseen) c.sm->tz = 1;
+  if (TEST && tzseen) *c.tz = 1;
+  return o;
 }
 
 struct PassCarry { // a full pass in progress: what a pause (lazy columns) has to carry into the next launch
@@ -538,14 +563,36 @@ __device__ __forceinline__ double chain_pass(Ctx &c, double lam, unsigned long l
     }
     __syncthreads();
     // ---- (2) verification sweep + (3) election of the first entering coordinate
-    unsigned best = KEY_NONE;
-    int bk = 0;
-    double bh = 0.0, bnw = 0.0;
-    sweep_members<true>(c, lam, mR, -1, 0.0, curpos, ordered, pk, best, bk, bh, bnw);
+    SweepIn si;
+    si.A = a.A;
+    si.lda = a.lda;
+    si.colslot = a.colslot;
+    si.sAx = c.sAx;
+    si.sb = c.sb;
+    si.sainv = c.sainv;
+    si.sw = c.sw;
+    si.sbeta = c.sbeta;
+    si.sAx2 = c.sAx2;
+    si.rk = c.s_act;
+    si.rh = c.e_h;
+    si.rpos = c.e_vpos;
+    si.s_in = c.s_in;
+    si.s_vnz = c.s_vnz;
+    si.tz = &sm->tz;
+    si.lo = lo;
+    si.len = len;
+    si.tend = mR;
+    si.kx = -1;
+    si.ordered = ordered ? 1 : 0;
+    si.lam = lam;
+    si.hx = 0.0;
+    si.curpos = curpos;
+    si.pk = pk;
+    const SweepOut so = sweep_members<true>(si);
     __syncthreads(); // sm->tz
     int tzsum = 0;
     const long long tc = PROF ? clock64() : 0;
-    const Cand w = elect(c, round, best, bk, bh, bnw, sm->tz, tzsum);
+    const Cand w = elect(c, round, so.best, so.bk, so.bh, so.bnw, sm->tz, tzsum);
     const long long td = PROF ? clock64() : 0;
     if (PROF) pf[7] += tb - ta;
     if (PROF) pf[9] += tc - tb;
@@ -565,10 +612,10 @@ __device__ __forceinline__ double chain_pass(Ctx &c, double lam, unsigned long l
         pc.maxH = maxH;
         return maxH;
       }
-      unsigned b2 = KEY_NONE;
-      int k2 = 0;
-      double h2 = 0.0, n2 = 0.0;
-      sweep_members<false>(c, lam, tend, w.k, w.h, curpos, ordered, pk, b2, k2, h2, n2);
+      si.tend = tend;
+      si.kx = w.k;
+      si.hx = w.h;
+      (void)sweep_members<false>(si);
     }
     // ---- commit: Ax <- Ax2 (same pointer swap in every CTA), new values of the visited members, the entering step
     {
@@ -903,7 +950,6 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   cluster.sync();
 
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (PROF && c.rank == 0 && tid < 8) a.prof[16 + tid] = 0;
   const long long t_start = PROF ? clock64() : 0;
   unsigned round = 0; // candidate-exchange rounds so far (selects slot parity and mbarrier phase)
   int m_bound = *a.nact; // upper bound of the list length, the same in every CTA
@@ -1129,7 +1175,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   if (c.rank == 0 && tid == 0) {
     if (a.prof) {
       pf[6] = clock64() - t_start;
-      for (int i = 0; i < 10; ++i) a.prof[i] = pf[i];
+      for (int i = 0; i < 10; ++i) a.prof[i] += pf[i]; // accumulated over the launches of one solve (host zeroes)
     }
     *a.nact = c.sm->nact;
     a.flag[0] = status;

@@ -153,6 +153,9 @@ int cdgpu_gram_create_lazy_dev(cdgpu_handle *h, const double *dX, int64_t n, int
 /* what the last solve on a lazy handle formed: columns cached so far, batches formed and kernel pauses during the last
  * solve, device ms spent forming columns during the last solve (all 0 for other handles) */
 int cdgpu_lazy_stats(cdgpu_handle h, int64_t *columns, int64_t *batches, int64_t *pauses, double *form_ms);
+/* device ms (CUDA events) spent inside the covariance-form sweep kernel during the last solve / path on a QUAD handle
+ * (all its launches; excludes forming columns on a lazy handle) */
+int cdgpu_sweep_ms(cdgpu_handle h, double *ms);
 /* Row-sharded variant for one-process-per-GPU jobs: every rank passes its own
  * n_local rows; partial X'X and X'y are summed over ranks with one
  * ncclAllReduce on the communicator made by cdgpu_comm_init (NULL comm == single
@@ -163,6 +166,12 @@ int cdgpu_comm_init(cdgpu_comm *c, const void *id128, int rank, int nranks, int 
 int cdgpu_comm_destroy(cdgpu_comm c);
 int cdgpu_gram_create_sharded(cdgpu_handle *h, const double *dX_local, int64_t n_local, int64_t n_total, int64_t p,
                               int64_t ldx, const double *dy_local, cdgpu_comm comm, int device);
+
+/* Synthetic design for benchmarks / multi-GPU tests: d_out[i + j*ld] (device memory, rows x cols) = a reproducible
+ * pseudo-normal value that depends only on (seed, row0 + i, col0 + j) — every row / column sharding of the same matrix
+ * over any number of GPUs sees identical data.  Blocking. */
+int cdgpu_synth_normal(double *d_out, int64_t rows, int64_t cols, int64_t ld, int64_t row0, int64_t col0, uint64_t seed,
+                       int device);
 
 int cdgpu_destroy(cdgpu_handle h);
 int cdgpu_dims(cdgpu_handle h, int64_t *n, int64_t *p, int *loss_kind);
