@@ -293,6 +293,12 @@ class CDQuadraticLoss(_Loss):
         lib.check(create(C.byref(self._h), ptr(X), X.shape[0], self.p, X.shape[0], ptr(y), device))
         return self
 
+    def sweep_stats(self):
+        """device ms inside the sweep kernel during the last solve / path, plus lazy_stats()."""
+        ms = C.c_double()
+        self.lib.check(self.lib.sweep_ms(self._h, C.byref(ms)))
+        return dict(self.lazy_stats(), sweep_ms=ms.value)
+
     def lazy_stats(self):
         cols, nb, npause, ms = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
         self.lib.check(self.lib.lazy_stats(self._h, C.byref(cols), C.byref(nb), C.byref(npause), C.byref(ms)))

@@ -337,8 +337,8 @@ __device__ __forceinline__ unsigned visit_pos(bool ordered, const PermKey &pk, i
 
 // Ax2[slice] = Ax[slice] + sum_{t < tend} A[slice, k_t] * h_t (steps in order, non-fused) [+ A[slice, kx] * hx].
 // TEST: every still-unvisited non-member is tested where its own visit falls among the steps; returns this
-// thread's earliest mover and records "value exactly zero" in s_vnz.  Not inlined, arguments by value: the sweep
-// gets the whole register file for its NE x NQ loads in flight (the path kernel itself sits at the 128-register cap).
+// thread's earliest mover and records "value exactly zero" in s_vnz.  Inlined so that the compiler keeps the address
+// spaces (shared-memory arrays as LDS, not generic loads competing with the column loads in the LSU queue).
 struct SweepIn {
   const double *A;
   long long lda;
@@ -361,7 +361,7 @@ struct SweepOut {
   double bh, bnw;
 };
 template <bool TEST>
-__device__ __noinline__ SweepOut sweep_members(const SweepIn c) {
+__device__ __forceinline__ SweepOut sweep_members(const SweepIn &c) {
   const int tid = threadIdx.x, lo = c.lo, len = c.len, tend = c.tend;
   const double *__restrict__ sAx = c.sAx;
   double *__restrict__ sAx2 = c.sAx2;

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--n", "400", "--p", "300", "--nlambda", "8", "--cpu-sample-p", "300"],
+                          "--n", "400", "--p", "300", "--nlambda", "8", "--ref-lambdas", "4"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
@@ -24,3 +24,14 @@ def test_reference_arm_prints_the_contract_line():
     cb, e2e = d["cpu_baseline"], d["e2e"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+    assert "proportional sample" in cb["sample"] and d["config"]["replicas"] == 1
+
+
+def test_reference_arm_models_n_replicas():
+    # --gpus N: the CPU job is N replicas too (N Gram samples back to back, N CD prefixes side by side)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                          "--n", "300", "--p", "200", "--nlambda", "6", "--ref-lambdas", "3"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["n_gpus"] == 2 and d["config"]["replicas"] == 2 and "2 replicas" in d["cpu_baseline"]["sample"]
