@@ -6,8 +6,17 @@
 # it keeps the package's types and exported functions and overrides the hot path
 # (coordinateDescent!, lasso, sqrtLasso, scaledLasso!, LassoPath, locpolyl1) with one ccall each.
 #
+# Two deliberate differences from the reference's loss objects:
+#  * COPY, NOT ALIAS.  The reference's losses alias the caller's arrays (locpolyl1 mutates `expandX` and `w` in place
+#    between solves, varying_coefficient_lasso.jl:54,63-65).  A device handle snapshots X / y / w / A / b at
+#    construction: after mutating them call `update!(f)` (or build a new loss).  The front-ends of this module never
+#    rely on aliasing.
+#  * The iterate is exchanged through ProximalBase's PUBLIC interface only (`fill!`, `setindex!`, `nnz`, the
+#    `nzval`/`nzval2ind` fields the reference itself reads in atom_iterator.jl:25,74): no assumption about the
+#    mutability of `SparseIterate` or about constructors the reference does not use.
+#
 #   using CoordinateDescentGPU            # instead of `using CoordinateDescent`
-#   f = CDQuadraticLoss(X'X/n, -X'y/n)    # or CDQuadraticLoss(X, y; from_data=true): Gram on the GPU
+#   f = CDQuadraticLoss(X'X/n, -X'y/n)    # or CDQuadraticLoss(X, y, Val(:data)) / Val(:lazy): covariance form on the GPU
 #   coordinateDescent!(x, f, ProxL1(λ, ω), CDOptions(; optTol=1e-8))
 #
 module CoordinateDescentGPU
@@ -22,7 +31,8 @@ export lasso, sqrtLasso, scaledLasso!, LassoPath, LassoSolution,
        CoordinateDifferentiableFunction,
        CDLeastSquaresLoss, CDWeightedLSLoss, CDQuadraticLoss, CDSqrtLassoLoss,
        coordinateDescent!,
-       GaussianKernel, SmoothingKernel, EpanechnikovKernel, evaluate, createKernel, locpolyl1
+       GaussianKernel, SmoothingKernel, EpanechnikovKernel, evaluate, createKernel, locpolyl1,
+       refitLassoPath, lvocv_locpolyl1, update!
 
 const libcdgpu = get(ENV, "LIBCDGPU", joinpath(@__DIR__, "..", "csrc", "libcdgpu.so"))
 
@@ -148,6 +158,37 @@ function CDQuadraticLoss(X::StridedMatrix{Float64}, y::AbstractVector{Float64}, 
     CDQuadraticLoss{Float64, Nothing, Nothing}(nothing, nothing, zeros(p), Handle(hp[]))
 end
 
+"""
+    CDQuadraticLoss(X, y, Val(:lazy))
+
+The same covariance-form loss without forming the p x p matrix: `diag(A)` and `b` up front, columns of `A = X'X/n` on
+demand as coordinates become non-zero (cdgpu_gram_create_lazy).  For paths whose supports stay small.
+"""
+function CDQuadraticLoss(X::StridedMatrix{Float64}, y::AbstractVector{Float64}, ::Val{:lazy}; device::Integer=0)
+    length(y) == size(X, 1) || throw(DimensionMismatch())
+    hp = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve X y check(ccall((:cdgpu_gram_create_lazy, libcdgpu), Cint,
+        (Ref{Ptr{Cvoid}}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Cint),
+        hp, X, size(X, 1), size(X, 2), stride(X, 2), y, device))
+    CDQuadraticLoss{Float64, Nothing, Nothing}(nothing, nothing, zeros(size(X, 2)), Handle(hp[]))
+end
+
+"""
+    update!(f)
+
+Re-upload the arrays a loss was built from after they were mutated in place (device handles copy, they do not alias).
+"""
+function update!(f::Union{CDLeastSquaresLoss, CDSqrtLassoLoss})
+    g = typeof(f).name.wrapper(f.y, f.X)
+    f.h.ptr, g.h.ptr = g.h.ptr, f.h.ptr      # the old handle is destroyed by g's finalizer
+    f
+end
+function update!(f::CDWeightedLSLoss)
+    g = CDWeightedLSLoss(f.y, f.X, f.w)
+    f.h.ptr, g.h.ptr = g.h.ptr, f.h.ptr
+    f
+end
+
 numCoordinates(f::CDQuadraticLoss) = length(f.Ax)
 numCoordinates(f::CoordinateDifferentiableFunction) = size(f.X, 2)
 state(f::CDQuadraticLoss) = f.Ax
@@ -155,11 +196,21 @@ state(f::CoordinateDifferentiableFunction) = f.r
 sync_state!(f) = (s = state(f); GC.@preserve s check(ccall((:cdgpu_state, libcdgpu), Cint, (Ptr{Cvoid}, Ptr{Float64}), f.h.ptr, s)); f)
 
 # ---------------------------------------------------------------- SparseIterate <-> (nzval, nzval2ind, nnz)
-function rebuild!(x::SparseIterate, nnz::Integer)
-    fill!(x.ind2nzval, 0)
-    x.nnz = nnz
-    @inbounds for i = 1:nnz
-        x.ind2nzval[x.nzval2ind[i]] = i
+# The triple crosses the ABI in caller-owned scratch copies; the iterate itself is only touched through
+# `fill!` (coordinate_descent.jl:25 does the same) and `setindex!`, which appends in the order given — the
+# insertion order pinned by test/atom_iterator.jl:13-28.  The library returns compacted lists (no explicit zeros).
+function export_iterate(x::SparseIterate{Float64})
+    p = length(x)
+    nzv = zeros(Float64, p); ind = zeros(Int64, p); m = nnz(x)
+    @inbounds for i = 1:m
+        nzv[i] = x.nzval[i]; ind[i] = x.nzval2ind[i]
+    end
+    nzv, ind, m
+end
+function import_iterate!(x::SparseIterate{Float64}, nzv::Vector{Float64}, ind::Vector{Int64}, m::Integer)
+    fill!(x, 0.0)
+    @inbounds for i = 1:m
+        x[ind[i]] = nzv[i]
     end
     x
 end
@@ -170,13 +221,14 @@ function coordinateDescent!(x::SparseIterate{Float64}, f::CoordinateDifferentiab
     ProximalBase.numCoordinates(x) == numCoordinates(f) || throw(DimensionMismatch())
     weighted = !isa(g, ProxL1{typeof(g.λ0), Nothing})
     weighted && (length(g.λ) == numCoordinates(f) || throw(DimensionMismatch()))
-    nnz = Ref{Int64}(x.nnz)
+    nzv, ind, m = export_iterate(x)
+    cnt = Ref{Int64}(m)
     st = Ref{cdgpu_stats}()
     ω = weighted ? convert(Vector{Float64}, g.λ) : Float64[]
-    GC.@preserve x ω check(ccall((:cdgpu_solve, libcdgpu), Cint,
+    GC.@preserve nzv ind ω check(ccall((:cdgpu_solve, libcdgpu), Cint,
         (Ptr{Cvoid}, Float64, Ptr{Float64}, Ref{cdgpu_options}, Ptr{Float64}, Ptr{Int64}, Ref{Int64}, Ref{cdgpu_stats}),
-        f.h.ptr, g.λ0, weighted ? pointer(ω) : C_NULL, Ref(c_opts(options)), x.nzval, x.nzval2ind, nnz, st))
-    rebuild!(x, nnz[])
+        f.h.ptr, g.λ0, weighted ? pointer(ω) : C_NULL, Ref(c_opts(options)), nzv, ind, cnt, st))
+    import_iterate!(x, nzv, ind, cnt[])
     sync_state!(f)          # f.r / f.Ax must reflect the final iterate (LassoSolution aliases f.r, lasso.jl:37)
     x
 end
@@ -220,12 +272,13 @@ end
 function scaledLasso!(x::SparseIterate{Float64}, X::AbstractMatrix{Float64}, y::AbstractVector{Float64}, λ::Float64,
                       ω::AbstractVector{Float64}, options::IterLassoOptions=IterLassoOptions())
     f = CDLeastSquaresLoss(y, X)
-    nnz = Ref{Int64}(x.nnz); σ = Ref{Float64}(0.0); st = Ref{cdgpu_stats}()
+    nzv, ind, m = export_iterate(x)
+    cnt = Ref{Int64}(m); σ = Ref{Float64}(0.0); st = Ref{cdgpu_stats}()
     ωv = convert(Vector{Float64}, ω)
-    GC.@preserve x ωv check(ccall((:cdgpu_scaled_solve, libcdgpu), Cint,
+    GC.@preserve nzv ind ωv check(ccall((:cdgpu_scaled_solve, libcdgpu), Cint,
         (Ptr{Cvoid}, Float64, Ptr{Float64}, Ref{cdgpu_iter_options}, Ptr{Float64}, Ptr{Int64}, Ref{Int64}, Ref{Float64}, Ref{cdgpu_stats}),
-        f.h.ptr, λ, ωv, Ref(c_opts(options)), x.nzval, x.nzval2ind, nnz, σ, st))
-    rebuild!(x, nnz[]); sync_state!(f)
+        f.h.ptr, λ, ωv, Ref(c_opts(options)), nzv, ind, cnt, σ, st))
+    import_iterate!(x, nzv, ind, cnt[]); sync_state!(f)
     g = ProxL1(λ * st[].sigma, ωv)
     LassoSolution{Float64, typeof(g)}(x, f.r, g, σ[])
 end
@@ -248,12 +301,11 @@ function LassoPath(X::StridedMatrix{Float64}, Y::StridedVector{Float64}, λpath:
     GC.@preserve λpath stdX colptr rowval nzval stats check(ccall((:cdgpu_path, libcdgpu), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ref{cdgpu_options}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ref{Int64}, Ptr{cdgpu_stats}),
         f.h.ptr, λpath, m, stdX, Ref(c_opts(options)), isinf(max_hat_s) ? -1 : Int64(max_hat_s), cap, colptr, rowval, nzval, done, stats))
-    βpath = Vector{SparseIterate{Float64}}(undef, done[])
+    βpath = Vector{SparseIterate{Float64,1}}(undef, done[])
     for i = 1:done[]
-        xi = SparseIterate(Float64, p)
+        xi = SparseIterate(Float64, p)                               # the constructor of lasso.jl:244
         rng = colptr[i]+1:colptr[i+1]
-        xi.nzval[1:length(rng)] = nzval[rng]; xi.nzval2ind[1:length(rng)] = rowval[rng]
-        βpath[i] = rebuild!(xi, length(rng))
+        βpath[i] = import_iterate!(xi, nzval[rng], rowval[rng], length(rng))
     end
     done[] < m && resize!(λpath, done[])                          # lasso.jl:253-256
     LassoPath{Float64}(copy(λpath), βpath)
@@ -315,7 +367,8 @@ function lvocv_locpolyl1(X::Matrix{Float64}, z::Vector{Float64}, y::Vector{Float
                          kernelType::Type{<:SmoothingKernel}, λ0::Float64, options::CDOptions=CDOptions(); device::Integer=0)
     n, p = size(X); numH = length(hArr)
     sqerr = zeros(Float64, n * numH)
-    kind = kernel_kind(createKernel(kernelType{Float64}, 1.0))
+    KT = kernelType isa UnionAll ? kernelType{Float64} : kernelType   # GaussianKernel or GaussianKernel{Float64}
+    kind = kernel_kind(createKernel(KT, 1.0))
     GC.@preserve X z y hArr sqerr check(ccall((:cdgpu_vc_lvocv, libcdgpu), Cint,
         (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Int64, Cint, Float64,
          Ref{cdgpu_options}, Int64, Int64, Cint, Ptr{Float64}, Ptr{Cvoid}),
