@@ -312,7 +312,8 @@ def sharded_metrics(be, args, rank, world, local, hbm):
             del Xf, yf
             rel = max(float(np.max(np.abs(As - A1)) / np.max(np.abs(A1))), float(np.max(np.abs(bs - b1)) / np.max(np.abs(b1))))
             out["gram_selfcheck"] = {"what": f"row-sharded Gram over {world} ranks (ncclAllReduce) vs the one-GPU Gram of the same keyed {nchk} x {pchk} rows",
-                                     "max_rel_diff": rel, "ok": bool(rel <= 1e-12), "symmetric": bool(np.array_equal(As, As.T))}
+                                     "max_rel_diff": rel, "symmetric": bool(np.array_equal(As, As.T)),
+                                     "ok": bool(rel <= 1e-12 and np.array_equal(As, As.T))}
     # ---- C5: tall lasso, rows sharded, strong scaling at fixed n
     free_b, _ = torch.cuda.mem_get_info()
     n, p, s = args.c5_rows, 2000, 20

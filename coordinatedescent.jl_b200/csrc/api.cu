@@ -202,6 +202,10 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
 
 API int cdgpu_destroy(cdgpu_handle h) {
   if (!h) return CDGPU_OK;
+  if (h->tall) {
+    cdgpu_destroy(h->tall);
+    h->tall = nullptr;
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->ownX) dfree(h->dX);
@@ -246,6 +250,7 @@ struct HandleGuard { // frees a half-built handle on an error return
   }
 };
 
+static int tall_attach(cdgpu_handle_s *h);
 static int naive_finish(cdgpu_handle_s *h) {
   // r = copy(y) (cd_differentiable_function.jl:54); column weights a_k = sum_i [w_i] X_ik^2
   CD_TRY(dalloc(&h->dstate, (size_t)h->n));
@@ -254,6 +259,9 @@ static int naive_finish(cdgpu_handle_s *h) {
   CD_TRY(launch_colsq(h, h->dX, h->ld, (int)h->n, (int)h->p, h->kind == CDGPU_LOSS_WLS ? h->dw : nullptr, h->daux,
                       false));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->kind != CDGPU_LOSS_SQRT && !getenv("CDGPU_NO_TALL") &&
+      (!naive_fits(h->n, h->kind == CDGPU_LOSS_WLS) || getenv("CDGPU_FORCE_TALL")))
+    CD_TRY(tall_attach(h));
   return CDGPU_OK;
 }
 
@@ -703,7 +711,7 @@ static int lazy_form(cdgpu_handle_s *h, const std::vector<int> &cols) {
     const int nb = (int)std::min<size_t>(LZ_BATCH, cols.size() - off);
     if (h->lz_used + nb > h->lz_cap) return cdgpu_set_error(CDGPU_ECAP, "lazy covariance cache is full");
     CUDA_TRY(cudaMemcpyAsync(h->dbatch, cols.data() + off, (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CD_TRY(launch_gather_cols(h, h->lzX, h->lz_ldx, n, h->dbatch, nb, nb, h->dgather, h->lz_ldb, h->dslot, h->lz_used));
+    CD_TRY(launch_gather_cols(h, h->lzX, h->lz_ldx, n, h->lzw, h->dbatch, nb, nb, h->dgather, h->lz_ldb, h->dslot, h->lz_used));
     CD_TRY(launch_gemm_tn_split(h->stream, h->sm_count, h->lzX, (int)p, h->lz_ldx, h->dgather, nb, h->lz_ldb, n,
                                 h->dX + (size_t)h->lz_used * (size_t)h->ld, h->ld, (double)n));
     for (int q = 0; q < nb; ++q) h->hslot[cols[off + (size_t)q]] = h->lz_used + q;
@@ -758,7 +766,7 @@ static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const do
 
 static int lazy_finish(cdgpu_handle_s *h) { // diag, b, 1/diag from the resident data
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  CD_TRY(launch_diag_xty(h, h->lzX, h->lz_n, (int)h->p, h->lz_ldx, h->lzy, (double)h->lz_n, h->ddiag, h->dy, h->daux, 0, 1));
+  CD_TRY(launch_diag_xty(h, h->lzX, h->lz_n, (int)h->p, h->lz_ldx, h->lzy, h->lzw, (double)h->lz_n, h->ddiag, h->dy, h->daux, 0, 1));
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   float ms = 0.f;
@@ -843,7 +851,7 @@ API int cdgpu_gram_create_lazy(cdgpu_handle *out, const double *X, int64_t n, in
       }
       if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(h->stream, ev[nev - 1], 0);
       if (e2 != cudaSuccess) return cdgpu_set_error(CDGPU_ECUDA, "H2D staging: %s", cudaGetErrorString(e2));
-      return launch_diag_xty(h, dXs + c0 * ld, n, (int)(c1 - c0), ld, dys, (double)n, h->ddiag + c0, h->dy + c0, h->daux + c0, 0, 1);
+      return launch_diag_xty(h, dXs + c0 * ld, n, (int)(c1 - c0), ld, dys, nullptr, (double)n, h->ddiag + c0, h->dy + c0, h->daux + c0, 0, 1);
     });
     if (rc == CDGPU_OK) {
       e = cudaEventRecord(h->ev1, h->stream);
@@ -858,6 +866,46 @@ API int cdgpu_gram_create_lazy(cdgpu_handle *out, const double *X, int64_t n, in
     *out = g.release();
     return CDGPU_OK;
   });
+}
+
+// ------------------------------------------------------------ tall naive-form problems --
+// The residual-form sweep kernel keeps r (and w) in shared memory, which bounds n (~28 000 rows, half with weights).
+// The reference's CDLeastSquaresLoss / CDWeightedLSLoss have no such bound (cd_differentiable_function.jl:43-194), so a
+// handle on a taller problem carries an inner LAZY covariance handle over the same device-resident X, y (w):
+// A = X'[W]X/n, b = -X'[W]y/n, the identical minimiser, columns of A formed only for coordinates that become non-zero.
+// Solves run there; f.r = y - X beta is formed afterwards from the active columns.  (CDSqrtLassoLoss has no such form
+// here: tall sqrt-lasso problems still answer CDGPU_ECAP.)
+static int tall_attach(cdgpu_handle_s *h) {
+  cdgpu_handle_s *t = new (std::nothrow) cdgpu_handle_s();
+  if (!t) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");
+  h->tall = t; // owned from here on (cdgpu_destroy(h) releases it, also on an error return below)
+  CD_TRY(lazy_alloc(t, h->n, h->p, h->device));
+  t->lzX = h->dX;
+  t->lzy = h->dy;
+  t->lzw = h->kind == CDGPU_LOSS_WLS ? h->dw : nullptr;
+  t->lz_ldx = h->ld;
+  CD_TRY(lazy_finish(t));
+  return CDGPU_OK;
+}
+// f.r = y - X beta for the inner handle's iterate (initialize!, cd_differentiable_function.jl:59-72)
+static int tall_residual(cdgpu_handle_s *h) {
+  cdgpu_handle_s *t = h->tall;
+  NaiveArgs a = {};
+  a.X = h->dX;
+  a.ldx = h->ld;
+  a.n = (int)h->n;
+  a.p = (int)h->p;
+  a.y = h->dy;
+  a.act = t->dact;
+  a.actval = t->dactval;
+  a.nact = t->dnact;
+  a.r = h->dstate;
+  a.beta = h->dbeta;
+  a.inlist = h->dinlist;
+  CUDA_TRY(cudaStreamSynchronize(t->stream));
+  CD_TRY(launch_naive_init(h, a));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return CDGPU_OK;
 }
 
 API int cdgpu_sweep_ms(cdgpu_handle h, double *ms) {
@@ -1238,6 +1286,10 @@ API int cdgpu_solve(cdgpu_handle h, double lambda0, const double *omega, const c
   if (!h || !nzval || !nzval2ind || !nnz) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   CD_TRY(check_opts(opt));
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->tall) { // tall LS / WLS: the inner covariance handle solves, then f.r is formed
+    CD_TRY(cdgpu_solve(h->tall, lambda0, omega, opt, nzval, nzval2ind, nnz, stats));
+    return tall_residual(h);
+  }
   int rc;
   const double *domega = upload_omega(h, omega, &rc);
   CD_TRY(rc);
@@ -1285,6 +1337,10 @@ API int cdgpu_path(cdgpu_handle h, const double *lambda, int64_t m, const double
   colptr[0] = 0;
   *m_done = 0;
   if (m == 0) return CDGPU_OK;
+  if (h->tall) {
+    CD_TRY(cdgpu_path(h->tall, lambda, m, omega, opt, max_hat_s, capacity, colptr, rowval, nzval, m_done, stats));
+    return tall_residual(h);
+  }
   if (!opt->warmStart) {
     // LassoPath with warmStart=false re-runs the internal continuation for every lambda
     // (coordinate_descent.jl:23-37): run it point by point.
@@ -1484,6 +1540,52 @@ static int scaled_solve_cold(cdgpu_handle_s *h, double lambda, const double *dom
   return CDGPU_OK;
 }
 
+// scaledLasso! (lasso.jl:107-144) on a tall LS handle: the inner covariance handle runs each coordinateDescent!, sigma is
+// re-estimated from the residual formed on the device (one launch per outer iteration instead of one for the loop)
+static int scaled_solve_tall(cdgpu_handle_s *h, double lambda, const double *omega, const cdgpu_iter_options *opt,
+                             double sigma0, double *nzval, int64_t *nzval2ind, int64_t *nnz, double *sigma_out,
+                             cdgpu_stats *stats) {
+  const size_t n = (size_t)h->n;
+  std::vector<double> r(n);
+  auto fetch_r = [&]() -> int {
+    CD_TRY(tall_residual(h));
+    CUDA_TRY(cudaMemcpy(r.data(), h->dstate, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return CDGPU_OK;
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  double sigma = sigma0;
+  if (opt->initProcedure == CDGPU_INIT_WARMSTART) { // initialize!(f, x); sigma = std(f.r)   lasso.jl:124-126
+    CD_TRY(upload_iterate(h->tall, nzval, nzval2ind, *nnz));
+    CD_TRY(fetch_r());
+    sigma = host_std(r);
+  }
+  cdgpu_stats tot = {}, st = {};
+  int outer = 0;
+  for (int64_t iter = 1; iter <= opt->maxIter; ++iter) {
+    outer = (int)iter;
+    CD_TRY(cdgpu_solve(h->tall, lambda * sigma, omega, &opt->optionsCD, nzval, nzval2ind, nnz, &st));
+    tot.passes += st.passes;
+    tot.full_passes += st.full_passes;
+    tot.visits += st.visits;
+    tot.accepted += st.accepted;
+    tot.maxH = st.maxH;
+    tot.converged = st.converged;
+    tot.device_ms += st.device_ms;
+    CD_TRY(fetch_r());
+    double ss = 0.0;
+    for (double v : r) ss += v * v;
+    const double snew = sqrt(ss / (double)n); // lasso.jl:134
+    if (fabs(snew - sigma) / sigma < opt->optTol) break;
+    sigma = snew;
+  }
+  tot.outer_iters = outer;
+  tot.sigma = sigma;
+  tot.device_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) *stats = tot;
+  if (sigma_out) *sigma_out = n > 1 ? host_std(r) : 0.0; // std(f.r)  lasso.jl:143
+  return CDGPU_OK;
+}
+
 API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, const cdgpu_iter_options *opt,
                            double *nzval, int64_t *nzval2ind, int64_t *nnz, double *sigma_out, cdgpu_stats *stats) {
   return api_guard([&]() -> int {
@@ -1497,6 +1599,7 @@ API int cdgpu_scaled_solve(cdgpu_handle h, double lambda, const double *omega, c
   CUDA_TRY(cudaSetDevice(h->device));
   double sigma0 = opt->sigma_init;
   if (opt->initProcedure == CDGPU_INIT_SCREENING) CD_TRY(screening_sigma(h, opt->sinit, &sigma0));
+  if (h->tall) return scaled_solve_tall(h, lambda, omega, opt, sigma0, nzval, nzval2ind, nnz, sigma_out, stats);
   int rc;
   const double *domega = upload_omega(h, omega, &rc);
   CD_TRY(rc);

@@ -261,6 +261,9 @@ struct cdgpu_handle_s {
   bool lazy = false;
   const double *lzX = nullptr;      // the data, n x p (ld lz_ldx) on the device
   const double *lzy = nullptr;
+  const double *lzw = nullptr;      // optional observation weights: A = X'WX/n, b = -X'Wy/n (tall CDWeightedLSLoss)
+  cdgpu_handle_s *tall = nullptr;   // naive LS/WLS handle too tall for the residual-in-shared-memory kernel: the solves run
+                                    // on this inner lazy covariance handle over the same X, y (w) — same minimiser
   bool own_lzX = false, own_lzy = false;
   int64_t lz_n = 0, lz_ldx = 0;
   int lz_cap = 0, lz_used = 0;      // slots of the cache / slots filled
@@ -350,12 +353,12 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
                 double *c, double divisor, int mode);
 int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_total);
 // lazy_gram.cu
-int launch_diag_xty(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double divisor,
-                    double *diag, double *b, double *ainv, int accumulate, int finish);
+int launch_diag_xty(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, const double *w,
+                    double divisor, double *diag, double *b, double *ainv, int accumulate, int finish);
 int launch_lazy_score(cdgpu_handle_s *h, const double *Ax, const double *b, const double *omega, const int *slot, int p,
                       double *out);
-int launch_gather_cols(cdgpu_handle_s *h, const double *X, long long ldx, long long n, const int *idx, int nb, int nbpad,
-                       double *B, long long ldb, int *slot, int slot0);
+int launch_gather_cols(cdgpu_handle_s *h, const double *X, long long ldx, long long n, const double *w, const int *idx, int nb,
+                       int nbpad, double *B, long long ldb, int *slot, int slot0);
 int launch_fill_int(cdgpu_handle_s *h, int *a, int n, int v);
 int launch_sqrt_vec(cdgpu_handle_s *h, const double *a, int n, double *out);
 // refit.cu: least squares on a support (refitLassoPath); scratch >= ld*ns + ns doubles, ld = ns rounded up to even
@@ -403,6 +406,7 @@ struct NaiveArgs {
   int multi_ok;    // grid-distributed chain engine for large active sets (CDGPU_NAIVE_MULTI=0 disables)
 };
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
+bool naive_fits(long long n, bool has_w);
 int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a); // r = y - X beta, beta dense, inlist
 int launch_colsq(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p, const double *w, double *out,
                  bool sqrt_over_n);

@@ -299,6 +299,24 @@ __global__ void scale_kernel(double *G, long long count, double divisor) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     G[i] = G[i] / divisor;
 }
+// after a multi-rank allreduce the two copies (i,j) / (j,i) of an entry may have been summed in different orders
+// (they sit in different chunks of the collective): the lower triangle is authoritative, as in the SYRK epilogue, so
+// issymmetric(A) (cd_differentiable_function.jl:306) holds bit for bit on every rank.  32 x 32 tiles through shared memory.
+__global__ void mirror_lower_kernel(double *G, long long ldg, int p) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.x, bj = blockIdx.y; // tile (rows bi, cols bj), bi >= bj: lower part
+  if (bj > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += blockDim.y) {
+    const int i = bi * 32 + tx, j = bj * 32 + r;
+    t[r][tx] = (i < p && j < p) ? G[i + (long long)j * ldg] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += blockDim.y) {
+    const int i = bj * 32 + tx, j = bi * 32 + r; // upper element (i, j) = lower element (j, i) = t[tx][r]
+    if (i < p && j < p && i < j) G[i + (long long)j * ldg] = t[tx][r];
+  }
+}
 
 } // namespace
 
@@ -524,6 +542,9 @@ int launch_scale_gram(cdgpu_handle_s *h, double *G, double *c, int p, double n_t
   const long long count = ldg * p + p;
   scale_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(G, count, n_total);
   CUDA_TRY(cudaGetLastError());
-  CD_COUNT_LAUNCH(1);
+  const int nb = (p + 31) / 32;
+  mirror_lower_kernel<<<dim3(nb, nb), dim3(32, 8), 0, h->stream>>>(G, ldg, p);
+  CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(2);
   return CDGPU_OK;
 }

@@ -17,13 +17,20 @@ namespace {
 
 // diag_j = sum_i X_ij^2 / n, b_j = -(X_j'y) / n, ainv_j = 1/diag_j: one warp per column, the column is read once
 __global__ void diag_xty_kernel(const double *__restrict__ X, long long n, int p, long long ldx,
-                                const double *__restrict__ y, double divisor, double *diag, double *b, double *ainv,
-                                int accumulate, int finish) {
+                                const double *__restrict__ y, const double *__restrict__ w, double divisor, double *diag,
+                                double *b, double *ainv, int accumulate, int finish) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < p; k += gridDim.x * wpb) {
     const double *col = X + (long long)k * ldx;
     double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
     long long i = lane;
+    if (w) {
+      for (; i < n; i += 32) {
+        const double x0 = __ldg(col + i), wx = __ldg(w + i) * x0;
+        s0 = fma(wx, x0, s0);
+        t0 = fma(wx, __ldg(y + i), t0);
+      }
+    }
     for (; i + 32 < n; i += 64) {
       const double x0 = __ldg(col + i), x1 = __ldg(col + i + 32);
       s0 = fma(x0, x0, s0);
@@ -65,14 +72,15 @@ __global__ void lazy_score_kernel(const double *Ax, const double *b, const doubl
 }
 
 // B[:, q] = X[:, idx[q]] (q < nb; columns beyond nb up to nbpad are zero-filled), and slot[idx[q]] = slot0 + q
-__global__ void gather_cols_kernel(const double *__restrict__ X, long long ldx, long long n, const int *__restrict__ idx,
-                                   int nb, int nbpad, double *B, long long ldb, int *slot, int slot0) {
+__global__ void gather_cols_kernel(const double *__restrict__ X, long long ldx, long long n, const double *__restrict__ w,
+                                   const int *__restrict__ idx, int nb, int nbpad, double *B, long long ldb, int *slot,
+                                   int slot0) {
   const int q = blockIdx.y;
   const bool live = q < nb;
   const double *src = X + (long long)(live ? idx[q] : 0) * ldx;
   double *dst = B + (long long)q * ldb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ldb; i += (long long)gridDim.x * blockDim.x)
-    dst[i] = (live && i < n) ? src[i] : 0.0;
+    dst[i] = (live && i < n) ? (w ? w[i] * src[i] : src[i]) : 0.0;
   if (live && blockIdx.x == 0 && threadIdx.x == 0) slot[idx[q]] = slot0 + q;
   (void)nbpad;
 }
@@ -86,9 +94,9 @@ __global__ void sqrt_vec_kernel(const double *a, int n, double *out) {
 
 } // namespace
 
-int launch_diag_xty(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, double divisor,
-                    double *diag, double *b, double *ainv, int accumulate, int finish) {
-  diag_xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, divisor, diag, b, ainv,
+int launch_diag_xty(cdgpu_handle_s *h, const double *X, long long n, int p, long long ldx, const double *y, const double *w,
+                    double divisor, double *diag, double *b, double *ainv, int accumulate, int finish) {
+  diag_xty_kernel<<<min((p + 7) / 8, h->sm_count * 8), 256, 0, h->stream>>>(X, n, p, ldx, y, w, divisor, diag, b, ainv,
                                                                             accumulate, finish);
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(1);
@@ -101,10 +109,10 @@ int launch_lazy_score(cdgpu_handle_s *h, const double *Ax, const double *b, cons
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
-int launch_gather_cols(cdgpu_handle_s *h, const double *X, long long ldx, long long n, const int *idx, int nb, int nbpad,
-                       double *B, long long ldb, int *slot, int slot0) {
+int launch_gather_cols(cdgpu_handle_s *h, const double *X, long long ldx, long long n, const double *w, const int *idx, int nb,
+                       int nbpad, double *B, long long ldb, int *slot, int slot0) {
   dim3 grid((unsigned)std::min<long long>((ldb + 255) / 256, 64), (unsigned)nbpad);
-  gather_cols_kernel<<<grid, 256, 0, h->stream>>>(X, ldx, n, idx, nb, nbpad, B, ldb, slot, slot0);
+  gather_cols_kernel<<<grid, 256, 0, h->stream>>>(X, ldx, n, w, idx, nb, nbpad, B, ldb, slot, slot0);
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;

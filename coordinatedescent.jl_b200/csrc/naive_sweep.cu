@@ -1086,6 +1086,12 @@ int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a) {
   return CDGPU_OK;
 }
 
+// does the residual (and w) of an n-row problem fit the naive kernel's shared memory?
+bool naive_fits(long long n, bool has_w) {
+  const size_t rbytes = (size_t)((n + 1) & ~1ll) * sizeof(double) * (has_w ? 2 : 1) + (sizeof(NSmem) + 15) / 16 * 16;
+  return rbytes <= (size_t)227 * 1024;
+}
+
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
   static bool attr_done[64] = {false}; // function attributes are per device (context), not per process
   const size_t max_dyn = 227 * 1024;
