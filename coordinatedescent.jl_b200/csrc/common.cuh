@@ -273,6 +273,16 @@ struct cdgpu_handle_s {
   int64_t lz_ldb = 0;
   CovResume *dresume = nullptr;
   int *dbatch = nullptr;            // [128] coordinates of the batch being formed
+  // speculative batch formed on a second stream WHILE the sweep kernel runs (the cluster kernel occupies 16 SMs)
+  cudaStream_t lz_stream2 = nullptr;
+  cudaEvent_t lz_spec_ev = nullptr;
+  double *dgather2 = nullptr;
+  int *dbatch2 = nullptr;
+  int spec_cols[128];               // host copy of the speculative batch
+  int spec_n = 0, spec_slot0 = 0;
+  bool spec_inflight = false;
+  int next_cand[256];               // runner-up candidates of the last scoring (best first)
+  int next_n = 0;
   int *hslot = nullptr;             // host mirror of dslot
   cudaEvent_t lz_ev0 = nullptr, lz_ev1 = nullptr;
   int lz_batches = 0, lz_pauses = 0; // statistics of the last solve
@@ -357,8 +367,9 @@ int launch_diag_xty(cdgpu_handle_s *h, const double *X, long long n, int p, long
                     double divisor, double *diag, double *b, double *ainv, int accumulate, int finish);
 int launch_lazy_score(cdgpu_handle_s *h, const double *Ax, const double *b, const double *omega, const int *slot, int p,
                       double *out);
-int launch_gather_cols(cdgpu_handle_s *h, const double *X, long long ldx, long long n, const double *w, const int *idx, int nb,
-                       int nbpad, double *B, long long ldb, int *slot, int slot0);
+int launch_gather_cols(cudaStream_t stream, const double *X, long long ldx, long long n, const double *w, const int *idx, int nb,
+                       int nbpad, double *B, long long ldb, int *slot, int slot0); // slot == null: no slot assignment
+int launch_assign_slots(cudaStream_t stream, const int *idx, int nb, int slot0, int *slot);
 int launch_fill_int(cdgpu_handle_s *h, int *a, int n, int v);
 int launch_sqrt_vec(cdgpu_handle_s *h, const double *a, int n, double *out);
 // refit.cu: least squares on a support (refitLassoPath); scratch >= ld*ns + ns doubles, ld = ns rounded up to even

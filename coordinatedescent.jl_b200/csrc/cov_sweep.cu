@@ -354,6 +354,7 @@ struct SweepIn {
   double lam, hx;
   long long curpos;
   PermKey pk;
+  long long *pfp; // optional profile slots [4]: set-up, sweep loop, tests, tail
 };
 struct SweepOut {
   unsigned best;
@@ -372,6 +373,7 @@ __device__ __forceinline__ SweepOut sweep_members(const SweepIn &c) {
   constexpr int NE = 3, NQ = 4; // elements per thread and chain steps per batch: NE*NQ independent loads in flight
   int tzseen = 0;
   for (int base = 0; base < len; base += NE * COV_T) {
+    const long long q0 = c.pfp ? clock64() : 0;
     double acc[NE];
     int ti[NE]; // step index before which the element is tested (-1: never)
     unsigned pj[NE];
@@ -417,6 +419,7 @@ __device__ __forceinline__ SweepOut sweep_members(const SweepIn &c) {
         o.bnw = nw;
       }
     };
+    const long long q1 = c.pfp ? clock64() : 0;
     for (int t0 = 0; t0 < tend; t0 += NQ) {
       double x[NQ][NE], hq[NQ];
 #pragma unroll
@@ -438,11 +441,13 @@ __device__ __forceinline__ SweepOut sweep_members(const SweepIn &c) {
         }
       }
     }
+    const long long q2 = c.pfp ? clock64() : 0;
     if (TEST) {
 #pragma unroll
       for (int u = 0; u < NE; ++u)
         if (ti[u] >= 0) test(u); // uniform: every lane tests its elements once, after the sweep
     }
+    const long long q3 = c.pfp ? clock64() : 0;
     if (c.kx >= 0) {
       const double *col = c.A + (long long)(c.colslot ? __ldg(c.colslot + c.kx) : c.kx) * c.lda + lo + base + tid;
 #pragma unroll
@@ -452,6 +457,12 @@ __device__ __forceinline__ SweepOut sweep_members(const SweepIn &c) {
 #pragma unroll
     for (int u = 0; u < NE; ++u)
       if (base + tid + u * COV_T < len) sAx2[base + tid + u * COV_T] = acc[u];
+    if (c.pfp && tid == 0) {
+      c.pfp[0] += q1 - q0;
+      c.pfp[1] += q2 - q1;
+      c.pfp[2] += q3 - q2;
+      c.pfp[3] += clock64() - q3;
+    }
   }
   if (TEST && tzseen) *c.tz = 1;
   return o;
@@ -588,6 +599,7 @@ __device__ __forceinline__ double chain_pass(Ctx &c, double lam, unsigned long l
     si.hx = 0.0;
     si.curpos = curpos;
     si.pk = pk;
+    si.pfp = (PROF && a.prof && rank == 0) ? a.prof + 10 : nullptr;
     const SweepOut so = sweep_members<true>(si);
     __syncthreads(); // sm->tz
     int tzsum = 0;

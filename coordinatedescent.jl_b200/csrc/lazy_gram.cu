@@ -81,10 +81,13 @@ __global__ void gather_cols_kernel(const double *__restrict__ X, long long ldx, 
   double *dst = B + (long long)q * ldb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ldb; i += (long long)gridDim.x * blockDim.x)
     dst[i] = (live && i < n) ? (w ? w[i] * src[i] : src[i]) : 0.0;
-  if (live && blockIdx.x == 0 && threadIdx.x == 0) slot[idx[q]] = slot0 + q;
+  if (slot && live && blockIdx.x == 0 && threadIdx.x == 0) slot[idx[q]] = slot0 + q;
   (void)nbpad;
 }
 
+__global__ void assign_slots_kernel(const int *idx, int nb, int slot0, int *slot) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nb; q += gridDim.x * blockDim.x) slot[idx[q]] = slot0 + q;
+}
 __global__ void fill_int_kernel(int *a, int n, int v) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = v;
 }
@@ -109,10 +112,16 @@ int launch_lazy_score(cdgpu_handle_s *h, const double *Ax, const double *b, cons
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
-int launch_gather_cols(cdgpu_handle_s *h, const double *X, long long ldx, long long n, const double *w, const int *idx, int nb,
+int launch_assign_slots(cudaStream_t stream, const int *idx, int nb, int slot0, int *slot) {
+  assign_slots_kernel<<<1, 128, 0, stream>>>(idx, nb, slot0, slot);
+  CUDA_TRY(cudaGetLastError());
+  CD_COUNT_LAUNCH(1);
+  return CDGPU_OK;
+}
+int launch_gather_cols(cudaStream_t stream, const double *X, long long ldx, long long n, const double *w, const int *idx, int nb,
                        int nbpad, double *B, long long ldb, int *slot, int slot0) {
   dim3 grid((unsigned)std::min<long long>((ldb + 255) / 256, 64), (unsigned)nbpad);
-  gather_cols_kernel<<<grid, 256, 0, h->stream>>>(X, ldx, n, w, idx, nb, nbpad, B, ldb, slot, slot0);
+  gather_cols_kernel<<<grid, 256, 0, stream>>>(X, ldx, n, w, idx, nb, nbpad, B, ldb, slot, slot0);
   CUDA_TRY(cudaGetLastError());
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;

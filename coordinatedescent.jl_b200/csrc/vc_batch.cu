@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 #define API extern "C" __attribute__((visibility("default")))
@@ -746,7 +748,10 @@ __global__ void __launch_bounds__(VCW * 32, 11) vc_cov_kernel(const VcCovArgs a)
     // slot-u entry, lane i's h is broadcast by one shuffle, every lane updates all its entries with the column of
     // the compact Gram that the cp.async ring brought to shared memory VC_RING-1 steps earlier (rows are read
     // through the lane's position -> snapshot-entry map).
-    auto phase_pass = [&](int m, const PermKey &pkm, int &accepted) -> double {
+    // MS = ceil(m / 32) slots per lane are live in the pass: the per-step work (gathers, multiply-adds) is instantiated
+    // for exactly that many, instead of the NU the widest possible list would need
+    auto phase_pass = [&](int m, const PermKey &pkm, int &accepted, auto ms_tag) -> double {
+      constexpr int MS = decltype(ms_tag)::value;
       unsigned *soff = reinterpret_cast<unsigned *>(stmpi); // byte offset of the column of visit position s in Gw
       int *slist = stmpi + ep;                              // list position i_ of visit position s
       for (int s_ = lane; s_ < m; s_ += 32) {
@@ -755,9 +760,9 @@ __global__ void __launch_bounds__(VCW * 32, 11) vc_cov_kernel(const VcCovArgs a)
         soff[s_] = (unsigned)(spos[sact[i_]] * ldw) * 8u;
       }
       __syncwarp();
-      int row[NU]; // snapshot entry (= row of the compact Gram) of this lane's visit positions
+      int row[MS]; // snapshot entry (= row of the compact Gram) of this lane's visit positions
 #pragma unroll
-      for (int u = 0; u < NU; ++u) {
+      for (int u = 0; u < MS; ++u) {
         const int s_ = lane + 32 * u;
         Ax[u] = be[u] = cc[u] = ai[u] = th[u] = 0.0;
         row[u] = 0;
@@ -788,16 +793,16 @@ __global__ void __launch_bounds__(VCW * 32, 11) vc_cov_kernel(const VcCovArgs a)
       for (int d = 0; d < VC_RING - 1; ++d) fetch(d);
       double maxH = 0.0;
 #pragma unroll
-      for (int u = 0; u < NU; ++u) {
+      for (int u = 0; u < MS; ++u) {
         const int cnt = min(32, m - 32 * u);
         for (int i = 0; i < cnt; ++i) { // visit position s_ = 32 u + i, ring stage i % VC_RING (32 % VC_RING == 0)
           const int s_ = 32 * u + i;
           asm volatile("cp.async.wait_group %0;" ::"n"(VC_RING - 2) : "memory"); // column of position s_ has landed
           __syncwarp();
           const double *col = ring + (i % VC_RING) * RS;
-          double gc[NU];
+          double gc[MS];
 #pragma unroll
-          for (int q = 0; q < NU; ++q) gc[q] = col[row[q]];
+          for (int q = 0; q < MS; ++q) gc[q] = col[row[q]];
           fetch(s_ + VC_RING - 1); // into the stage of position s_-1, which every lane read before the barrier above
           const double v = __dsub_rn(be[u], __dmul_rn(Ax[u] + cc[u], ai[u]));
           const double nwl = cd_shrink(v, th[u]);
@@ -805,7 +810,7 @@ __global__ void __launch_bounds__(VCW * 32, 11) vc_cov_kernel(const VcCovArgs a)
           if (lane == i) be[u] = nwl;
           // h == 0 adds an exact zero (the Gram entries are finite): no data-dependent branch on the chain
 #pragma unroll
-          for (int q = 0; q < NU; ++q) Ax[q] = __dadd_rn(Ax[q], __dmul_rn(gc[q], h));
+          for (int q = 0; q < MS; ++q) Ax[q] = __dadd_rn(Ax[q], __dmul_rn(gc[q], h));
           accepted += h != 0.0;
           maxH = fmax(maxH, fabs(h));
         }
@@ -813,7 +818,7 @@ __global__ void __launch_bounds__(VCW * 32, 11) vc_cov_kernel(const VcCovArgs a)
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
 #pragma unroll
-      for (int u = 0; u < NU; ++u) {
+      for (int u = 0; u < MS; ++u) {
         const int s_ = lane + 32 * u;
         if (s_ < m) {
           sAxE[row[u]] = Ax[u];
@@ -934,7 +939,19 @@ __global__ void __launch_bounds__(VCW * 32, 11) vc_cov_kernel(const VcCovArgs a)
         }
         const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), a.seed, pass_counter);
         int acc_pass = 0;
-        maxH = phase_pass(m, pkm, acc_pass);
+        {
+          const int ms = (m + 31) >> 5;
+          if (ms <= 1 || NU == 1)
+            maxH = phase_pass(m, pkm, acc_pass, std::integral_constant<int, 1>{});
+          else if (ms == 2 || NU == 2)
+            maxH = phase_pass(m, pkm, acc_pass, std::integral_constant<int, (NU < 2 ? NU : 2)>{});
+          else if (ms == 3 || NU == 3)
+            maxH = phase_pass(m, pkm, acc_pass, std::integral_constant<int, (NU < 3 ? NU : 3)>{});
+          else if (ms == 4 || NU == 4)
+            maxH = phase_pass(m, pkm, acc_pass, std::integral_constant<int, (NU < 4 ? NU : 4)>{});
+          else
+            maxH = phase_pass(m, pkm, acc_pass, std::integral_constant<int, NU>{});
+        }
         st.accepted += acc_pass;
         pc[1] += clock64() - tq;
         tq = clock64();
