@@ -21,8 +21,9 @@ N > 1   = one process per GPU.  The warm-started path of ONE problem is a sequen
 --impl reference = the reference's CPU implementation of the same step on the host cores: Gram by OpenBLAS (what
           Julia's X'X/n calls) with all threads + the C port of the reference's single-threaded CD loop
           (oracle/libcdref_fast.so).  Each step is a PROPORTIONAL sample of the C2 step: the first L lambdas of the
-          path at the full width p and the same fraction of the Gram's rows, so sample visits / sample time estimates
-          whole-step visits / whole-step time (the reference's cost per visit does not depend on lambda).
+          path at the full width p and the same fraction of the Gram's columns, so sample visits / sample time estimates
+          whole-step visits / whole-step time (the reference's cost per visit does not depend on lambda, the Gram's cost
+          is linear in the number of columns formed).
 """
 import argparse
 import ctypes as C
@@ -323,7 +324,9 @@ def sharded_metrics(be, args, rank, world, local, hbm):
     nl = hi - lo
     Xl, yl = keyed_rows(nl, p, lo, s, 555)
     torch.cuda.synchronize()
-    opts = CDOptions(randomize=False)
+    # optTol 1e-10 for this path: the Gram differs in the last bits with the number of ranks (summation order of the
+    # allreduce), and the supports of the 100 solutions should not depend on that
+    opts = CDOptions(randomize=False, optTol=1e-10, maxIter=20000)
     recs = []
     for rep in range(4):
         if world > 1:
@@ -344,7 +347,10 @@ def sharded_metrics(be, args, rank, world, local, hbm):
             recs.append((gms, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t2 - t0), path))
     gram_dev, gram_wall, path_wall, step_wall = mx(*[float(np.mean([r[i] for r in recs])) for i in range(4)])
     path = recs[-1][4]
-    supp = [tuple(sorted(int(k) for k in b.nonzero())) for b in path.βpath]
+    supp = []
+    for bcol in path.βpath:  # supports, ignoring coefficients below 1e-6 of the column's largest (not yet decided at optTol)
+        v = bcol.toarray()
+        supp.append(tuple(int(k) for k in np.flatnonzero(np.abs(v) > 1e-6 * max(np.max(np.abs(v)), 1e-300))))
     import hashlib
     sig = hashlib.sha256(repr(supp).encode()).hexdigest()[:16]
     flops = n * p * (p + 1) + 2 * n * p
@@ -357,7 +363,7 @@ def sharded_metrics(be, args, rank, world, local, hbm):
         "gram_tflops_aggregate": flops / (gram_dev * 1e-3) / 1e12, "visits": visits,
         "steps_per_sec": 1e3 / step_wall, "visits_per_sec": visits / (step_wall * 1e-3),
         "nnz_last": path.βpath[-1].nnz, "support_signature": sig,
-        "support_signature_note": "sha256 of the 100 support sets: must be the same string at every N",
+        "support_signature_note": "sha256 of the 100 support sets (|beta| > 1e-6 max|beta|, path at optTol 1e-10): the same string at every N",
         "nccl_ranks_in_data_plane_collective": world}
     del Xl, yl
     # ---- C4: 4096 independent local problems dealt round-robin over the ranks (no data-path collective, final all_gather)
@@ -399,16 +405,17 @@ def reference_setup(cfg):
     return ref
 
 
-def cpu_gram(X, y, n_rows, cores):
-    """A = X'X/n, b = -X'y/n on the first n_rows rows with numpy/OpenBLAS on `cores` threads; returns (A, b, seconds)."""
+def cpu_gram(X, y, cores, ncols=None):
+    """A[:, :ncols] = X'X[:, :ncols]/n, b = -X'y/n with numpy/OpenBLAS on `cores` threads (ncols = None: all of A, made
+    exactly symmetric); returns (A, b, seconds).  Cost is linear in ncols (flops and output bytes alike)."""
+    n, p = X.shape
     with host_threads(cores):
         t0 = time.perf_counter()
-        Xs = X[:n_rows]
-        A = Xs.T @ Xs
-        A /= n_rows
-        b = -(Xs.T @ y[:n_rows]) / n_rows
+        A = X.T @ (X if ncols is None else X[:, :ncols])
+        A /= n
+        b = -(X.T @ y) / n
         dt = time.perf_counter() - t0
-    if not np.array_equal(A, A.T):
+    if ncols is None and not np.array_equal(A, A.T):
         A = (A + A.T) * 0.5
     return np.asfortranarray(A), b, dt
 
@@ -427,7 +434,7 @@ def reference_main(args, cfg, base, workload):
     n, p = cfg["n"], cfg["p"]
     X, y = make_problem(n, p, cfg["s"], seed=123)
     opts = CDOptions(maxIter=cfg["maxIter"], optTol=cfg["optTol"], randomize=False, warmStart=True)
-    A, b, gram_full_s = cpu_gram(X, y, n, cores)  # setup: the matrix the CD sample runs on (timed once, reported)
+    A, b, gram_full_s = cpu_gram(X, y, cores)  # setup: the matrix the CD sample runs on (timed once, reported)
     L = max(1, min(args.ref_lambdas, cfg["nlambda"]))
     default_cfg = (n, p, cfg["nlambda"], cfg["s"]) == (C2["n"], C2["p"], C2["nlambda"], C2["s"])
 
@@ -456,12 +463,12 @@ def reference_main(args, cfg, base, workload):
             t.join()
         t1 = time.perf_counter()
         frac = vis[0] / v_total
-        rows = max(16, int(round(frac * n)))
+        cols = max(16, int(round(frac * p)))
         tg = 0.0
         for _ in range(N):
-            tg += cpu_gram(X, y, rows, cores)[2]
+            tg += cpu_gram(X, y, cores, ncols=cols)[2]
         t2 = time.perf_counter()
-        return sum(vis), t1 - t0, tg, t2 - t0, frac, rows
+        return sum(vis), t1 - t0, tg, t2 - t0, frac, cols
 
     for _ in range(min(args.warmup, 1)):
         step()
@@ -475,7 +482,7 @@ def reference_main(args, cfg, base, workload):
     val = tot_v / tt
     K = args.steps
     sample = (f"proportional sample of the C2 step per timed step: CD over the first {L} of {cfg['nlambda']} lambdas at the full width "
-              f"p={p} on the full-n Gram ({frac:.4f} of the path's {v_total} visits) + Gram of the first {rows} of {n} rows; "
+              f"p={p} on the full Gram ({frac:.4f} of the path's {v_total} visits) + the first {rows} of {p} columns of the Gram (all {n} rows); "
               f"Gram numpy/OpenBLAS on {cores} threads ({tg / K:.2f} s/step; the full Gram took {gram_full_s:.1f} s in setup), CD = C port "
               f"of the reference's single-threaded loop incl. its unconditional O(p) axpy per visit ({tc / K:.2f} s/step)"
               + (f"; N={N} replicas: {N} Gram samples back to back, {N} CD prefixes on {N} cores side by side" if N > 1 else "")
@@ -748,7 +755,7 @@ def cpu_leg(args, cfg, be, make_handle, opts):
     cores = os.cpu_count()
     X, y = make_problem(n, p, cfg["s"], seed=123)
     g = run_step(be, make_handle, cfg, opts, keep_path=True)
-    A, b, tg = cpu_gram(X, y, n, cores)
+    A, b, tg = cpu_gram(X, y, cores)
     L = args.cpu_lambdas if args.cpu_lambdas > 0 else cfg["nlambda"]
     t0 = time.perf_counter()
     f = ref.CDQuadraticLoss(A, b)

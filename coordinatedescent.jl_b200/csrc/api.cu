@@ -176,8 +176,8 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   };
   const size_t o_beta = take(p * sizeof(double)), o_act = take(p * sizeof(int)), o_actval = take(p * sizeof(double)),
                o_nact = take(sizeof(int)), o_inlist = take(p), o_omega = take(p * sizeof(double)),
-               o_scr = take((12 * p + 8 * (size_t)h->n + 64 + 4 * 2048 + 64) * sizeof(double)),
-               o_iscr = take((8 * p + 64) * sizeof(int)), o_bscr = take(2 * p + 64), o_flag = take(8 * sizeof(int));
+               o_scr = take((15 * p + 8 * (size_t)h->n + 64 + 4 * 2048 + 64) * sizeof(double)),
+               o_iscr = take((10 * p + 64) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(8 * sizeof(int));
   CD_TRY(dalloc(&h->dcommon, off));
   unsigned char *base = h->dcommon;
   h->dbeta = (double *)(base + o_beta);

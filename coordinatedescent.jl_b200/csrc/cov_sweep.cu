@@ -66,6 +66,8 @@ struct Smem {
   double h[2];
   int nact, flag, nonapp;
   int mR, tz;             // chain pass: entries handed to the member chain this round; sticky "a test saw v == 0"
+  int nd, nc;             // screening: entries of D (CTA 0); CURRENT rows of this CTA
+  double Dn2;             // screening: squared distance bound of this round (CTA 0)
   int s2[2];
   unsigned long long mbar[2]; // candidate-exchange barriers (one per round parity)
   chain::Shared ch;
@@ -688,6 +690,455 @@ __device__ __forceinline__ double chain_pass(Ctx &c, double lam, unsigned long l
   return maxH;
 }
 
+// ------------------------------------------------------------------ full pass with safe screening --
+// (round 2) The verification sweep above reads |members| x p/C doubles per CTA in every round, and so does the refresh
+// after an active phase: the part of the kernel that is bound by the cluster's path to L2.  Almost all of it only
+// confirms, again and again, that a far-from-threshold coordinate still does not move.  With
+//     S_j = sum_{k in D} A[j,k]^2        D = every coordinate whose beta changed since the last resync
+// Cauchy-Schwarz gives |Ax_j(now) - Ax_j(sync)| <= sqrt(S_j) * ||beta - beta_sync||_2 for ANY matrix A, so a
+// non-member row whose gradient at the last resync stays below its threshold by more than that bound provably does
+// not move and is not touched at all (STALE row: its stored Ax is the value at the last resync).  Rows that fail the
+// test are promoted to CURRENT: their Ax is brought up to date once (sum over D) and from then on they receive every
+// committed step in order, exactly as before, and are tested exactly where their visit falls.  Members are always
+// CURRENT.  When too many rows are CURRENT, and at the end of a launch, a RESYNC brings every row up to date with one
+// GEMV over the columns of D and restarts the bookkeeping.  Decisions are exact; the values of Ax differ from the
+// in-order accumulation only in rounding (as after a refresh).
+constexpr int SC_NCMAX = 384; // CURRENT rows per CTA that trigger a resync
+
+struct ScreenCtx {
+  double *sS, *sbsync;      // per slice: S_j; beta at the last resync
+  unsigned char *s_cur;     // per slice: row is CURRENT
+  unsigned short *cur_list; // [L] slice indices of the CURRENT rows
+  unsigned char *dflag;     // global [p]: coordinate is in D
+  int *dk;                  // global: coordinates of D
+  double *dsync, *dcur;     // global: beta at the last resync / beta now, per D entry
+};
+
+// value of a per-slice array element through the owner CTA
+__device__ __forceinline__ double slice_get_d(const Ctx &c, double *arr_local, int k) { return slice_get(c, arr_local, k); }
+
+// every row exact again; D = current members; S, flags and the CURRENT list rebuilt.  Cluster-collective.
+// Members = CTA 0's current list.
+__device__ void screen_resync(Ctx &c, ScreenCtx &sc, bool first) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x;
+  if (first)
+    for (int j = tid; j < c.len; j += COV_T) sc.dflag[c.lo + j] = 0;
+  __threadfence();
+  c.cluster.sync(); // CTA 0's list is final
+  const int m = *c.cluster.map_shared_rank(&sm->nact, 0);
+  // (1) CTA 0: current beta of every D entry
+  int nd = first ? 0 : *c.cluster.map_shared_rank(&sm->nd, 0);
+  if (c.rank == 0 && !first) {
+    for (int q = tid; q < nd; q += COV_T) sc.dcur[q] = slice_get(c, c.sbeta, sc.dk[q]);
+    __threadfence();
+  }
+  c.cluster.sync();
+  // (2) all: STALE rows += sum over D of A[j,k] (beta_k - beta_k_sync)
+  if (!first && nd > 0) {
+    for (int j = tid; j < c.len; j += COV_T) {
+      if (sc.s_cur[j]) continue;
+      double acc0 = 0.0, acc1 = 0.0;
+      int q = 0;
+      for (; q + 2 <= nd; q += 2) {
+        const int k0 = __ldcg(sc.dk + q), k1 = __ldcg(sc.dk + q + 1);
+        const double d0 = __ldcg(sc.dcur + q) - __ldcg(sc.dsync + q), d1 = __ldcg(sc.dcur + q + 1) - __ldcg(sc.dsync + q + 1);
+        const double v0 = d0 != 0.0 ? __ldg(col_ptr(a, k0) + c.lo + j) : 0.0;
+        const double v1 = d1 != 0.0 ? __ldg(col_ptr(a, k1) + c.lo + j) : 0.0;
+        acc0 = fma(v0, d0, acc0);
+        acc1 = fma(v1, d1, acc1);
+      }
+      for (; q < nd; ++q) {
+        const double d0 = __ldcg(sc.dcur + q) - __ldcg(sc.dsync + q);
+        if (d0 != 0.0) acc0 = fma(__ldg(col_ptr(a, __ldcg(sc.dk + q)) + c.lo + j), d0, acc0);
+      }
+      c.sAx[j] += acc0 + acc1;
+    }
+  }
+  c.cluster.sync(); // everybody is done with the old D
+  // (3) new bookkeeping: D = members, S_j over the members' columns, CURRENT = members
+  if (c.rank == 0) {
+    for (int q = tid; q < nd; q += COV_T) sc.dflag[sc.dk[q]] = 0;
+    __syncthreads();
+    for (int e = tid; e < m; e += COV_T) sc.dflag[a.act[e]] = 1;
+    for (int e = tid; e < m; e += COV_T) {
+      const int k = a.act[e];
+      sc.dk[e] = k;
+      sc.dsync[e] = slice_get(c, c.sbeta, k);
+    }
+    if (tid == 0) sm->nd = m;
+    __threadfence();
+  }
+  for (int j = tid; j < c.len; j += COV_T) {
+    sc.s_cur[j] = 0;
+    sc.sbsync[j] = c.sbeta[j];
+  }
+  if (tid == 0) sm->nc = 0;
+  c.cluster.sync();
+  for (int j = tid; j < c.len; j += COV_T) {
+    double s0 = 0.0, s1 = 0.0;
+    int e = 0;
+    for (; e + 2 <= m; e += 2) {
+      const double v0 = __ldg(col_ptr(a, __ldcg(sc.dk + e)) + c.lo + j), v1 = __ldg(col_ptr(a, __ldcg(sc.dk + e + 1)) + c.lo + j);
+      s0 = fma(v0, v0, s0);
+      s1 = fma(v1, v1, s1);
+    }
+    for (; e < m; ++e) {
+      const double v0 = __ldg(col_ptr(a, __ldcg(sc.dk + e)) + c.lo + j);
+      s0 = fma(v0, v0, s0);
+    }
+    sc.sS[j] = s0 + s1;
+  }
+  __syncthreads();
+  for (int e = tid; e < m; e += COV_T) { // members are CURRENT
+    const int k = __ldcg(sc.dk + e);
+    if (k >= c.lo && k < c.lo + c.len) {
+      sc.s_cur[k - c.lo] = 1;
+      sc.cur_list[atomicAdd(&sm->nc, 1)] = (unsigned short)(k - c.lo);
+    }
+  }
+  __syncthreads();
+}
+
+// after an active phase: the change of beta reaches the CURRENT rows only (everybody else is covered by the bound)
+__device__ void refresh_cur(Ctx &c, ScreenCtx &sc, int m0) {
+  const CovArgs &a = c.a;
+  const int tid = threadIdx.x;
+  const double *dlt = a.scr + a.p;
+  const int *act0 = a.iscr, *act0c = a.iscr + a.p;
+  const int nc = c.sm->nc;
+  for (int r = tid; r < nc; r += COV_T) {
+    const int j = sc.cur_list[r];
+    const double *row = a.A + c.lo + j;
+    double acc0 = 0.0, acc1 = 0.0;
+    int i = 0;
+    for (; i + 2 <= m0; i += 2) {
+      const double d0 = __ldcg(dlt + i), d1 = __ldcg(dlt + i + 1);
+      const double v0 = d0 != 0.0 ? __ldg(row + (long long)__ldcg(act0c + i) * a.lda) : 0.0;
+      const double v1 = d1 != 0.0 ? __ldg(row + (long long)__ldcg(act0c + i + 1) * a.lda) : 0.0;
+      acc0 = fma(v0, d0, acc0);
+      acc1 = fma(v1, d1, acc1);
+    }
+    for (; i < m0; ++i) {
+      const double d0 = __ldcg(dlt + i);
+      if (d0 != 0.0) acc0 = fma(__ldg(row + (long long)__ldcg(act0c + i) * a.lda), d0, acc0);
+    }
+    c.sAx[j] += acc0 + acc1;
+  }
+  for (int i = tid; i < m0; i += COV_T) {
+    const int k = __ldcg(act0 + i);
+    if (k >= c.lo && k < c.lo + c.len) c.sbeta[k - c.lo] = __ldcg(a.beta + k);
+  }
+  __syncthreads();
+}
+
+// The full pass of chain_pass with screened verification.  Same contract; additionally returns (through need_resync)
+// whether some CTA holds too many CURRENT rows.
+template <bool PROF>
+__device__ __forceinline__ double chain_pass_sc(Ctx &c, ScreenCtx &sc, double lam, unsigned long long pass_counter,
+                                                unsigned &round, long long &accepted, bool first_pass_of_kernel,
+                                                int &nonapp_total, long long *pf, int &m_bound, PassCarry &pc,
+                                                bool &need_resync) {
+  const CovArgs &a = c.a;
+  Smem *sm = c.sm;
+  const int tid = threadIdx.x;
+  const bool ordered = a.randomize == 0;
+  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  const int lo = c.lo, len = c.len, rank = c.rank;
+  const int m_old = pc.m_old;
+  int *sorted_k = a.iscr + 7 * (long long)a.p;
+  unsigned *sorted_pos = reinterpret_cast<unsigned *>(a.iscr + 6 * (long long)a.p);
+  long long curpos = pc.resume ? pc.curpos : -1;
+  double maxH = pc.resume ? pc.maxH : 0.0;
+  pc.paused = false;
+  need_resync = false;
+  if (!pc.resume) {
+    for (int i = tid; i < len; i += COV_T) {
+      c.s_in[i] = first_pass_of_kernel ? a.inlist[lo + i] : (unsigned char)(c.sbeta[i] != 0.0);
+      c.s_vnz[i] = 1;
+    }
+    if (tid == 0) sm->tz = 0;
+    if (rank == 0) {
+      for (int e = tid; e < m_old; e += COV_T) c.e_vpos[e] = visit_pos(ordered, pk, a.act[e]);
+      __syncthreads();
+      for (int e = tid; e < m_old; e += COV_T) {
+        const unsigned my = c.e_vpos[e];
+        int r = 0;
+        for (int j = 0; j < m_old; ++j) r += c.e_vpos[j] < my;
+        sorted_k[r] = a.act[e];
+        sorted_pos[r] = my;
+      }
+    }
+    __syncthreads();
+  }
+  int s0 = 0; // members already visited in this pass
+  if (pc.resume && rank == 0) {
+    int l = 0, r = m_old;
+    while (l < r) {
+      const int mid = (l + r) >> 1;
+      if ((long long)sorted_pos[mid] <= curpos) l = mid + 1; else r = mid;
+    }
+    s0 = l;
+  }
+  for (;;) {
+    const long long ta = PROF ? clock64() : 0;
+    // ---- (1) CTA 0: chain over the members still to be visited; the norm bound of this round
+    if (rank == 0) {
+      __syncthreads();
+      const int mR = m_old - s0;
+      for (int t = tid; t < mR; t += COV_T) {
+        const int k = sorted_k[s0 + t];
+        c.s_act[t] = k;
+        c.e_vpos[t] = sorted_pos[s0 + t];
+        c.e_be[t] = slice_get(c, c.sbeta, k);
+        c.e_g[t] = slice_get(c, c.sAx, k);
+        c.e_h[t] = 0.0;
+      }
+      if (tid == 0) sm->mR = mR;
+      // beta now of every D entry (for catch-ups) and the squared distance from the last resync
+      const int nd = sm->nd;
+      double part = 0.0;
+      for (int q = tid; q < nd; q += COV_T) {
+        const double cur = slice_get(c, c.sbeta, sc.dk[q]);
+        sc.dcur[q] = cur;
+        const double d = cur - sc.dsync[q];
+        part = fma(d, d, part);
+      }
+      __syncthreads();
+      if (mR > 0) {
+        chain::State S;
+        S.m = mR;
+        S.row = c.s_act;
+        S.coord = c.s_act;
+        S.g = c.e_g;
+        S.be = c.e_be;
+        S.ord = c.e_ord;
+        S.pos = c.e_pos;
+        S.stage = c.e_stage;
+        S.sh = &sm->ch;
+        S.G = a.A;
+        S.ldg = a.lda;
+        S.slot = a.colslot;
+        S.prof = nullptr;
+        S.hout = c.e_h;
+        const CovPolicy P{a.b, a.ainv, a.omega, lam};
+        (void)chain::run<COV_T>(S, P, 0.0, 1, pass_counter, true, a.seed, a.optTol, nullptr);
+      }
+      // entries that moved are further from (or closer to) beta_sync: take the larger of the two distances
+      for (int t = tid; t < mR; t += COV_T) {
+        const double h = c.e_h[t];
+        if (h != 0.0) {
+          const double bs = slice_get(c, sc.sbsync, c.s_act[t]);
+          const double dn = c.e_be[t] - bs, dold = (c.e_be[t] - h) - bs;
+          part += fmax(0.0, dn * dn - dold * dold);
+        }
+      }
+      part = warp_sum(part);
+      double *redd = reinterpret_cast<double *>(sm->wcand);
+      if ((tid & 31) == 0) redd[tid >> 5] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double tot = 0.0;
+        for (int wq = 0; wq < COV_T / 32; ++wq) tot += redd[wq];
+        sm->Dn2 = tot * (1.0 + 1e-9);
+      }
+      __threadfence();
+      __syncthreads();
+    }
+    c.cluster.sync();
+    const long long tb = PROF ? clock64() : 0;
+    const int mR = *c.cluster.map_shared_rank(&sm->mR, 0);
+    const int nd = *c.cluster.map_shared_rank(&sm->nd, 0);
+    const double Dn2 = *c.cluster.map_shared_rank(&sm->Dn2, 0);
+    if (rank != 0) {
+      const int *rk0 = c.cluster.map_shared_rank(c.s_act, 0);
+      const unsigned *rp0 = c.cluster.map_shared_rank(c.e_vpos, 0);
+      const double *rh0 = c.cluster.map_shared_rank(c.e_h, 0), *rb0 = c.cluster.map_shared_rank(c.e_be, 0);
+      for (int t = tid; t < mR; t += COV_T) {
+        c.s_act[t] = rk0[t];
+        c.e_vpos[t] = rp0[t];
+        c.e_h[t] = rh0[t];
+        c.e_be[t] = rb0[t];
+      }
+    }
+    __syncthreads();
+    // ---- (2a) STALE rows: safe-screening test; the few that fail are brought up to date and become CURRENT
+    for (int i = tid; i < len; i += COV_T) {
+      if (sc.s_cur[i] || c.s_in[i]) continue;
+      const unsigned pj = visit_pos(ordered, pk, lo + i);
+      if ((long long)pj <= curpos) continue;
+      const double g = c.sAx[i] + c.sb[i];
+      const double d = lam * c.sw[i] * (1.0 - 1e-9) - fabs(g);
+      if (d > 0.0 && d * d > sc.sS[i] * Dn2) continue; // provably below the threshold whenever its turn comes
+      double acc0 = 0.0;
+      for (int q = 0; q < nd; ++q) {
+        const double dd = __ldcg(sc.dcur + q) - __ldcg(sc.dsync + q);
+        if (dd != 0.0) acc0 = fma(__ldg(col_ptr(a, __ldcg(sc.dk + q)) + lo + i), dd, acc0);
+      }
+      c.sAx[i] += acc0;
+      sc.s_cur[i] = 1;
+      sc.cur_list[atomicAdd(&sm->nc, 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    // ---- (2b) CURRENT rows: the chain steps in visit order, exact test where the row's own visit falls
+    const int nc = sm->nc;
+    unsigned best = KEY_NONE;
+    int bk = 0;
+    double bh = 0.0, bnw = 0.0;
+    int tzseen = 0;
+    for (int r = tid; r < nc; r += COV_T) {
+      const int i = sc.cur_list[r];
+      double acc = c.sAx[i], accv = acc;
+      const bool testme = !c.s_in[i];
+      const unsigned pj = visit_pos(ordered, pk, lo + i);
+      const bool pend = testme && (long long)pj > curpos;
+      for (int t0 = 0; t0 < mR; t0 += 8) {
+        double x[8], hq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const bool on = t0 + q < mR;
+          hq[q] = on ? c.e_h[t0 + q] : 0.0;
+          x[q] = hq[q] != 0.0 ? __ldg(col_ptr(a, c.s_act[t0 + q]) + lo + i) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (hq[q] != 0.0) acc = __dadd_rn(acc, __dmul_rn(x[q], hq[q]));
+          if (t0 + q < mR && c.e_vpos[t0 + q] < pj) accv = acc; // steps visited before this row
+        }
+      }
+      c.sAx2[i] = acc;
+      if (pend) {
+        const double ainv = c.sainv[i];
+        const double g = accv + c.sb[i];
+        const double old = c.sbeta[i];
+        const double t = __dmul_rn(g, ainv);
+        const double thr = __dmul_rn(__dmul_rn(ainv, lam), c.sw[i]);
+        const double v = __dsub_rn(old, t);
+        const double nw = cd_shrink(v, thr);
+        const double h = nw - old;
+        const unsigned char nz = (unsigned char)(v != 0.0);
+        c.s_vnz[i] = nz;
+        if (!nz) tzseen = 1;
+        if (h != 0.0 && pj < best) {
+          best = pj;
+          bk = lo + i;
+          bh = h;
+          bnw = nw;
+        }
+      }
+    }
+    if (tzseen) sm->tz = 1;
+    __syncthreads();
+    int tzsum = 0;
+    const long long tc = PROF ? clock64() : 0;
+    const Cand w = elect(c, round, best, bk, bh, bnw, sm->tz | (nc > SC_NCMAX ? 0x10000 : 0), tzsum);
+    const long long td = PROF ? clock64() : 0;
+    if (PROF) pf[7] += tb - ta;
+    if (PROF) pf[9] += tc - tb;
+    if (PROF) pf[8] += td - tc;
+    if (tzsum >= 0x10000) need_resync = true;
+    tzsum &= 0xffff;
+    int tend = mR;
+    if (w.key != KEY_NONE) {
+      int l = 0, r = mR;
+      while (l < r) {
+        const int mid = (l + r) >> 1;
+        if (c.e_vpos[mid] < w.key) l = mid + 1; else r = mid;
+      }
+      tend = l;
+      if (a.colslot && __ldg(a.colslot + w.k) < 0) { // column not formed: leave before applying anything of this round
+        pc.paused = true;
+        pc.need_k = w.k;
+        pc.curpos = curpos;
+        pc.maxH = maxH;
+        return maxH;
+      }
+    }
+    // ---- commit on the CURRENT rows: all steps, or the steps before the entering coordinate plus its own
+    if (w.key == KEY_NONE) {
+      for (int r = tid; r < nc; r += COV_T) {
+        const int i = sc.cur_list[r];
+        c.sAx[i] = c.sAx2[i];
+      }
+    } else {
+      const double *colx = col_ptr(a, w.k) + lo;
+      for (int r = tid; r < nc; r += COV_T) {
+        const int i = sc.cur_list[r];
+        double acc = c.sAx[i];
+        for (int t = 0; t < tend; ++t) {
+          const double h = c.e_h[t];
+          if (h != 0.0) acc = __dadd_rn(acc, __dmul_rn(__ldg(col_ptr(a, c.s_act[t]) + lo + i), h));
+        }
+        c.sAx[i] = __dadd_rn(acc, __dmul_rn(__ldg(colx + i), w.h));
+      }
+      // the entering coordinate joins D: S of every row grows by its column (one coalesced read per entering step)
+      for (int i = tid; i < len; i += COV_T) {
+        const double v = __ldg(colx + i);
+        sc.sS[i] = fma(v, v, sc.sS[i]);
+      }
+    }
+    long long nacc = 0;
+    for (int t = tid; t < tend; t += COV_T) {
+      const double h = c.e_h[t];
+      if (h != 0.0) {
+        nacc += 1;
+        maxH = fmax(maxH, fabs(h));
+        const int k = c.s_act[t];
+        if (k >= lo && k < lo + len) c.sbeta[k - lo] = c.e_be[t];
+      }
+    }
+    if (w.key != KEY_NONE) {
+      const int k = w.k;
+      if (k >= lo && k < lo + len && tid == 0) {
+        c.sbeta[k - lo] = w.nw;
+        c.s_in[k - lo] = 1; // (its row was promoted to CURRENT by the screening test: it moved)
+      }
+      if (rank == 0 && tid == 0) {
+        a.act[sm->nact] = k;
+        sm->nact += 1;
+        if (!sc.dflag[k]) { // (a coordinate that left and comes back is still in D with its beta_sync)
+          sc.dflag[k] = 1;
+          sc.dk[sm->nd] = k; // beta_sync of a coordinate that was not a member is 0
+          sc.dsync[sm->nd] = 0.0;
+          sm->nd += 1;
+        }
+        __threadfence();
+      }
+    }
+    {
+      for (int o = 16; o > 0; o >>= 1) {
+        nacc += __shfl_xor_sync(0xffffffffu, nacc, o);
+        maxH = fmax(maxH, __shfl_xor_sync(0xffffffffu, maxH, o));
+      }
+      double *redd = reinterpret_cast<double *>(sm->wcand);
+      __syncthreads();
+      if ((tid & 31) == 0) {
+        redd[2 * (tid >> 5)] = (double)nacc;
+        redd[2 * (tid >> 5) + 1] = maxH;
+      }
+      __syncthreads();
+      double na = 0.0;
+      for (int wq = 0; wq < COV_T / 32; ++wq) {
+        na += redd[2 * wq];
+        maxH = fmax(maxH, redd[2 * wq + 1]);
+      }
+      accepted += (long long)na;
+    }
+    c.cluster.sync();
+    if (w.key == KEY_NONE) {
+      nonapp_total = tzsum;
+      break;
+    }
+    m_bound += 1;
+    maxH = fmax(maxH, fabs(w.h));
+    accepted += 1;
+    curpos = (long long)w.key;
+    s0 += tend;
+  }
+  return maxH;
+}
+
 // rare: publish the visited non-members that were not appended (tentative value exactly zero)
 __device__ void publish_nonapp(Ctx &c) {
   int *cnt = c.a.flag + 2, *list = c.a.iscr + 6 * (long long)c.a.p;
@@ -878,7 +1329,8 @@ __device__ void refresh_slice(Ctx &c, int m0) {
 }
 
 template <bool PROF>
-__global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int L, int slice_in_smem, int ecap, int multi_ok) {
+__global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int L, int slice_in_smem, int ecap, int multi_ok,
+                                                            int screen) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx c{a, cluster};
@@ -920,7 +1372,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
     c.sw = d + 3 * L;
     c.sbeta = d + 4 * L;
     c.sAx2 = d + 5 * L;
-    c.s_in = reinterpret_cast<unsigned char *>(d + 6 * L);
+    c.s_in = reinterpret_cast<unsigned char *>(d + (screen ? 8 : 6) * L);
     c.s_vnz = c.s_in + L;
     for (int i = tid; i < c.len; i += COV_T) {
       const int k = c.lo + i;
@@ -961,6 +1413,28 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   __syncthreads();
   cluster.sync();
 
+  ScreenCtx sc;
+  sc.sS = sc.sbsync = nullptr;
+  sc.s_cur = nullptr;
+  sc.cur_list = nullptr;
+  sc.dk = a.iscr + 8 * (long long)a.p;
+  sc.dsync = a.scr + 12 * (long long)a.p;
+  sc.dcur = a.scr + 13 * (long long)a.p;
+  sc.dflag = a.bscr + 2 * (long long)a.p;
+  if (screen) { // only with the slices in shared memory (launcher)
+    double *d = c.sAx;
+    sc.sS = d + 6 * L;
+    sc.sbsync = d + 7 * L;
+    sc.s_cur = c.s_vnz + L;
+    sc.cur_list = reinterpret_cast<unsigned short *>(sc.s_cur + L + (L & 1));
+    if (tid == 0) {
+      c.sm->nd = 0;
+      c.sm->nc = 0;
+      c.sm->Dn2 = 0.0;
+    }
+    __syncthreads();
+    screen_resync(c, sc, true);
+  }
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_start = PROF ? clock64() : 0;
   unsigned round = 0; // candidate-exchange rounds so far (selects slot parity and mbarrier phase)
@@ -1021,6 +1495,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           st.visits += a.p;
         }
         int nonapp_total = 0;
+        bool resync_after = false, reinit_after = false;
         const long long t0 = PROF ? clock64() : 0;
         const long long acc0 = st.accepted;
         const bool use_chain = cont || (!a.events_only && m_known >= 0 && m_known <= c.ecap);
@@ -1029,7 +1504,13 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         if (use_chain) {
           if (!cont) pc.m_old = m_known;
           m_old = pc.m_old;
-          maxH = chain_pass<PROF>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf, m_bound, pc);
+          bool need_resync = false;
+          if (screen)
+            maxH = chain_pass_sc<PROF>(c, sc, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf, m_bound, pc,
+                                       need_resync);
+          else
+            maxH = chain_pass<PROF>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf, m_bound, pc);
+          resync_after = need_resync;
           pc.resume = false;
           if (pc.paused) { // an entering coordinate has no column yet: leave, the host forms it and launches again
             status = a.resume ? 3 : 4;
@@ -1053,9 +1534,11 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
             break;
           }
         } else {
+          if (screen) screen_resync(c, sc, false); // the event pass keeps every row exact by itself
           m_old = c.sm->nact; // only meaningful on CTA 0
           maxH = event_pass<PROF, false>(c, lam, pass_counter, round, st.accepted, first_pass, nonapp_total, pf, m_bound,
                                          nullptr, 0);
+          reinit_after = screen != 0;
         }
         const long long t1 = PROF ? clock64() : 0;
         if (PROF) pf[0] += t1 - t0;
@@ -1069,6 +1552,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           nonapp_total = __ldcg(a.flag + 2);
         }
         if (c.rank == 0) list_update_full(c, m_old, nonapp_total, pass_counter);
+        if (reinit_after) screen_resync(c, sc, true);
+        else if (resync_after) screen_resync(c, sc, false);
         if (PROF) pf[1] += clock64() - t1;
         pass_counter += 1;
         m_known = -1;
@@ -1089,6 +1574,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         }
         if (m_all > c.ecap) {
           // ---- list longer than the engine holds: one event-by-event pass over the list (exact, slow, no size limit)
+          if (screen) screen_resync(c, sc, false);
           if (c.rank == 0) {
             for (int e = tid; e < m_all; e += COV_T) lpos[a.act[e]] = e;
             __threadfence();
@@ -1098,6 +1584,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           const long long acc0 = st.accepted;
           const double maxH = event_pass<PROF, true>(c, lam, pass_counter, round, st.accepted, false, dummy, pf, m_bound, lpos, m_all);
           if (c.rank == 0) list_update_full(c, m_all, 0, pass_counter);
+          if (screen) screen_resync(c, sc, true);
           (void)acc0;
           iter += 1;
           pass_counter += 1;
@@ -1120,7 +1607,10 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
         if (PROF) pf[2] += t1 - t0;
         const Bcast *bc = cluster.map_shared_rank(&c.sm->bc, 0);
         const Bcast b = *bc;
-        refresh_slice(c, b.m0);
+        if (screen)
+          refresh_cur(c, sc, b.m0);
+        else
+          refresh_slice(c, b.m0);
         if (PROF) pf[3] += clock64() - t1;
         if (PROF) pf[5] += b.visits;
         iter += b.npasses;
@@ -1168,6 +1658,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   }
   if (a.accumulate && c.rank == 0 && tid == 0 && a.stats && status != 3) a.stats[0] = st;
   // ---- write the state back
+  if (screen) screen_resync(c, sc, false); // every row of Ax exact again
   cluster.sync();
   if (slice_in_smem) {
     for (int i = tid; i < c.len; i += COV_T) {
@@ -1354,12 +1845,24 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   int L = (a.p + C - 1) / C;
   L = (L + 1) & ~1;
   // engine capacity: as large as still leaves room for the slices in shared memory
-  const size_t slices = (size_t)6 * L * sizeof(double) + 2 * (size_t)L + 16;
+  int screen = 0; // safe screening of the verification sweep (CDGPU_COV_SCREEN=1; being validated)
+  if (const char *env = getenv("CDGPU_COV_SCREEN")) screen = atoi(env) != 0;
+  if (L >= 65536 || a.events_only) screen = 0;
+  size_t slices = screen ? (size_t)8 * L * sizeof(double) + 5 * (size_t)L + 32 : (size_t)6 * L * sizeof(double) + 2 * (size_t)L + 16;
   int ecap = COV_ACT_CAP;
   if (const char *env = getenv("CDGPU_ECAP_MAX")) ecap = std::max(512, std::min(COV_ACT_CAP, atoi(env) / 512 * 512));
   while (ecap > 1024 && fixed_for(ecap) + slices > max_dyn) ecap >>= 1;
+  if (screen && fixed_for(ecap) + slices > max_dyn) { // no room for the screening arrays: plain verification
+    screen = 0;
+    slices = (size_t)6 * L * sizeof(double) + 2 * (size_t)L + 16;
+    ecap = COV_ACT_CAP;
+    while (ecap > 1024 && fixed_for(ecap) + slices > max_dyn) ecap >>= 1;
+  }
   int slice_in_smem = fixed_for(ecap) + slices <= max_dyn;
-  if (!slice_in_smem) ecap = COV_ACT_CAP;
+  if (!slice_in_smem) {
+    ecap = COV_ACT_CAP;
+    screen = 0;
+  }
   size_t dyn = slice_in_smem ? fixed_for(ecap) + slices : fixed_for(ecap);
   // the distributed engine needs 8p + 80 scratch doubles behind the slices; CDGPU_COV_MULTI=0 switches it off
   int multi_ok = a.p >= 64 ? 384 : 0;
@@ -1378,9 +1881,9 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (a.prof)
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<true>, a, L, slice_in_smem, ecap, multi_ok));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<true>, a, L, slice_in_smem, ecap, multi_ok, screen));
   else
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<false>, a, L, slice_in_smem, ecap, multi_ok));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, cov_path_kernel<false>, a, L, slice_in_smem, ecap, multi_ok, screen));
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
