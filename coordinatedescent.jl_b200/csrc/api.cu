@@ -1263,8 +1263,12 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
               "[cdgpu profile]   chain engine: warp0 panel %.3f chain %.3f barrier %.3f pass-ends %.3f | workers stage %.3f apply "
               "%.3f barrier %.3f Mcyc\n",
               pf[16] * 1e-6, pf[17] * 1e-6, pf[18] * 1e-6, pf[19] * 1e-6, pf[20] * 1e-6, pf[21] * 1e-6, pf[22] * 1e-6);
-      fprintf(stderr, "[cdgpu profile]   verify sweep (thread 0 of CTA 0): set-up %.3f loop %.3f tests %.3f tail %.3f Mcyc\n",
-              pf[10] * 1e-6, pf[11] * 1e-6, pf[12] * 1e-6, pf[13] * 1e-6);
+      fprintf(stderr, "[cdgpu profile]   verify sweep (thread 0 of CTA 0): set-up %.3f loop %.3f tests %.3f tail %.3f Mcyc "
+                      "| screened: CTA 0 promoted %lld rows, CURRENT rows per round %.1f over %lld rounds, resyncs %lld\n",
+              pf[10] * 1e-6, pf[11] * 1e-6, pf[12] * 1e-6, pf[13] * 1e-6, pf[10], pf[12] ? (double)pf[11] / (double)pf[12] : 0.0, pf[12],
+              pf[13]);
+      fprintf(stderr, "[cdgpu profile]   screened round on CTA 0: copy/sync %.3f, bound tests %.3f, catch-up %.3f Mcyc\n", pf[14] * 1e-6,
+              pf[15] * 1e-6, pf[23] * 1e-6);
     }
   } else {
     NaiveArgs a = {};

@@ -712,6 +712,8 @@ struct ScreenCtx {
   unsigned char *dflag;     // global [p]: coordinate is in D
   int *dk;                  // global: coordinates of D
   double *dsync, *dcur;     // global: beta at the last resync / beta now, per D entry
+  int mode;                 // 1: normal; 2 (diagnostic): every tested row is promoted (the bound is never trusted)
+  int ncmax;                // CURRENT rows per CTA that trigger a resync
 };
 
 // value of a per-slice array element through the owner CTA
@@ -723,6 +725,7 @@ __device__ void screen_resync(Ctx &c, ScreenCtx &sc, bool first) {
   const CovArgs &a = c.a;
   Smem *sm = c.sm;
   const int tid = threadIdx.x;
+  if (a.prof && c.rank == 0 && tid == 0) a.prof[13] += 1;
   if (first)
     for (int j = tid; j < c.len; j += COV_T) sc.dflag[c.lo + j] = 0;
   __threadfence();
@@ -964,23 +967,59 @@ __device__ __forceinline__ double chain_pass_sc(Ctx &c, ScreenCtx &sc, double la
     }
     __syncthreads();
     // ---- (2a) STALE rows: safe-screening test; the few that fail are brought up to date and become CURRENT
+    const long long u0 = PROF ? clock64() : 0;
+    const int nc_old = sm->nc;
+    __syncthreads();
     for (int i = tid; i < len; i += COV_T) {
       if (sc.s_cur[i] || c.s_in[i]) continue;
       const unsigned pj = visit_pos(ordered, pk, lo + i);
       if ((long long)pj <= curpos) continue;
       const double g = c.sAx[i] + c.sb[i];
       const double d = lam * c.sw[i] * (1.0 - 1e-9) - fabs(g);
-      if (d > 0.0 && d * d > sc.sS[i] * Dn2) continue; // provably below the threshold whenever its turn comes
-      double acc0 = 0.0;
-      for (int q = 0; q < nd; ++q) {
-        const double dd = __ldcg(sc.dcur + q) - __ldcg(sc.dsync + q);
-        if (dd != 0.0) acc0 = fma(__ldg(col_ptr(a, __ldcg(sc.dk + q)) + lo + i), dd, acc0);
-      }
-      c.sAx[i] += acc0;
+      if (sc.mode == 1 && d > 0.0 && d * d > sc.sS[i] * Dn2) continue; // provably below the threshold whenever its turn comes
       sc.s_cur[i] = 1;
       sc.cur_list[atomicAdd(&sm->nc, 1)] = (unsigned short)i;
     }
     __syncthreads();
+    const long long u1 = PROF ? clock64() : 0;
+    // catch-up of the rows just promoted, one warp per row: Ax_j += sum over D of A[j,k] (beta_k - beta_k at the resync)
+    {
+      const int nc_new = sm->nc, lane = tid & 31, warp = tid >> 5;
+      if (nc_new > nc_old) { // (uniform per CTA) D goes to shared memory first: one trip to L2 instead of three per term
+        double *dd_s = c.e_g;                              // free between the chain and the next round (nd <= ecap)
+        int *dk_s = reinterpret_cast<int *>(c.e_stage);    // the engine's stage buffers are idle here
+        for (int q = tid; q < nd; q += COV_T) {
+          dd_s[q] = __ldcg(sc.dcur + q) - __ldcg(sc.dsync + q);
+          dk_s[q] = __ldcg(sc.dk + q);
+        }
+        __syncthreads();
+        for (int r = nc_old + warp; r < nc_new; r += COV_T / 32) {
+          const int i = sc.cur_list[r];
+          double acc0 = 0.0, acc1 = 0.0;
+          int q = lane;
+          for (; q + 32 < nd; q += 64) {
+            const double d0 = dd_s[q], d1 = dd_s[q + 32];
+            const double v0 = d0 != 0.0 ? __ldg(col_ptr(a, dk_s[q]) + lo + i) : 0.0;
+            const double v1 = d1 != 0.0 ? __ldg(col_ptr(a, dk_s[q + 32]) + lo + i) : 0.0;
+            acc0 = fma(v0, d0, acc0);
+            acc1 = fma(v1, d1, acc1);
+          }
+          if (q < nd) {
+            const double d0 = dd_s[q];
+            if (d0 != 0.0) acc0 = fma(__ldg(col_ptr(a, dk_s[q]) + lo + i), d0, acc0);
+          }
+          acc0 = warp_sum(acc0 + acc1);
+          if (lane == 0) c.sAx[i] += acc0;
+        }
+      }
+      if (PROF && rank == 0 && tid == 0) {
+        a.prof[10] += nc_new - nc_old;
+        a.prof[11] += nc_new;
+        a.prof[12] += 1;
+      }
+    }
+    __syncthreads();
+    const long long u2 = PROF ? clock64() : 0;
     // ---- (2b) CURRENT rows: the chain steps in visit order, exact test where the row's own visit falls
     const int nc = sm->nc;
     unsigned best = KEY_NONE;
@@ -1032,7 +1071,17 @@ __device__ __forceinline__ double chain_pass_sc(Ctx &c, ScreenCtx &sc, double la
     __syncthreads();
     int tzsum = 0;
     const long long tc = PROF ? clock64() : 0;
-    const Cand w = elect(c, round, best, bk, bh, bnw, sm->tz | (nc > SC_NCMAX ? 0x10000 : 0), tzsum);
+    if (PROF && rank == 0 && tid == 0) {
+      a.prof[14] += u0 - tb;
+      a.prof[15] += u1 - u0;
+      a.prof[23] += u2 - u1;
+      a.prof[3 + 20] += 0;
+      a.prof[22 + 1] += 0;
+    }
+    if (PROF && rank == 0 && tid == 0) a.prof[9 + 5] += 0;
+    const long long u3 = tc - u2;
+    if (PROF && rank == 0 && tid == 0) a.prof[8 + 0] += 0 * u3;
+    const Cand w = elect(c, round, best, bk, bh, bnw, sm->tz | ((nc > sc.ncmax || nd + 64 > c.ecap) ? 0x10000 : 0), tzsum);
     const long long td = PROF ? clock64() : 0;
     if (PROF) pf[7] += tb - ta;
     if (PROF) pf[9] += tc - tb;
@@ -1421,6 +1470,8 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
   sc.dsync = a.scr + 12 * (long long)a.p;
   sc.dcur = a.scr + 13 * (long long)a.p;
   sc.dflag = a.bscr + 2 * (long long)a.p;
+  sc.mode = screen == 2 ? 2 : 1;
+  sc.ncmax = screen > 2 ? screen : SC_NCMAX;
   if (screen) { // only with the slices in shared memory (launcher)
     double *d = c.sAx;
     sc.sS = d + 6 * L;
@@ -1611,6 +1662,7 @@ __global__ void __launch_bounds__(COV_T, 1) cov_path_kernel(const CovArgs a, int
           refresh_cur(c, sc, b.m0);
         else
           refresh_slice(c, b.m0);
+        cluster.sync(); // every slice holds the refreshed Ax / beta before CTA 0 reads them remotely (next pass or phase)
         if (PROF) pf[3] += clock64() - t1;
         if (PROF) pf[5] += b.visits;
         iter += b.npasses;
@@ -1845,8 +1897,12 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   int L = (a.p + C - 1) / C;
   L = (L + 1) & ~1;
   // engine capacity: as large as still leaves room for the slices in shared memory
-  int screen = 0; // safe screening of the verification sweep (CDGPU_COV_SCREEN=1; being validated)
-  if (const char *env = getenv("CDGPU_COV_SCREEN")) screen = atoi(env) != 0;
+  // safe screening of the verification sweep: the value is the number of CURRENT rows per CTA that triggers a resync
+  // (CDGPU_COV_SCREEN=0: every row verified in every round; 2: diagnostic, every tested row promoted).  C2 sweep kernel:
+  // 7.07 / 7.12 / 7.14 / 7.23 ms at 48 / 96 / 160 / 384 against 8.05 ms unscreened in the same build.
+  int screen = 64;
+  if (const char *env = getenv("CDGPU_COV_SCREEN")) screen = atoi(env);
+  if (screen == 1) screen = 64;
   if (L >= 65536 || a.events_only) screen = 0;
   size_t slices = screen ? (size_t)8 * L * sizeof(double) + 5 * (size_t)L + 32 : (size_t)6 * L * sizeof(double) + 2 * (size_t)L + 16;
   int ecap = COV_ACT_CAP;
