@@ -210,6 +210,60 @@ def c3_metrics(be, local, hbm, reps=3):
                          "traffic": tr[0], "traffic_source": tr[1]}}
 
 
+def c1_metrics(be, ref, reps=3):
+    """C1 (configs[0]): cd_bench.jl-style lasso n=1000 p=5000, 10 true non-zeros, single lambda — the reference's own
+    CPU-runnable case.  Three lambdas (10 / ~230 / ~830 non-zeros).  Two device forms: the reference's residual form
+    (CDLeastSquaresLoss -> naive_path_kernel) and the covariance form on the same data (lazy covariance handle ->
+    cov_path_kernel, cold start from zero like `lasso`).  CPU column: the C port of the reference loop, one thread."""
+    from cdgpu import CDOptions, ProxL1, SparseIterate
+    n, p = 1000, 5000
+    X, y = make_problem(n, p, 10, 123)
+    opt = CDOptions(randomize=False)
+    out = []
+    fn = be.CDLeastSquaresLoss(y, X)
+    fr = ref.CDLeastSquaresLoss(y, X) if ref is not None else None
+    for lam in (math.sqrt(2 * math.log(p) / n), 0.05, 0.01):
+        row = {"lambda": lam}
+        runs = []
+        for i in range(reps + 1):
+            x = SparseIterate(p)
+            be.coordinateDescent_(x, fn, ProxL1(lam), opt)
+            if i:
+                runs.append(fn.last_stats["device_ms"])
+        st, bn = fn.last_stats, x.toarray()
+        row.update({"naive_device_ms": float(np.mean(runs)), "visits": st["visits"], "accepted": st["accepted"], "passes": st["passes"],
+                    "nnz": int(np.count_nonzero(bn)), "converged": bool(st["converged"])})
+        runs = []
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            fc = be.CDQuadraticLoss_from_data(X, y, lazy=True)  # includes H2D of X (40 MB) and the diag / b pass
+            x = SparseIterate(p)
+            be.coordinateDescent_(x, fc, ProxL1(lam), opt)
+            wall = time.perf_counter() - t0
+            stc, ls = fc.last_stats, fc.sweep_stats()
+            fc.close()
+            if i:
+                runs.append((stc["device_ms"], 1e3 * wall))
+        bc = x.toarray()
+        row.update({"cov_lazy_solve_device_ms": float(np.mean([r[0] for r in runs])),
+                    "cov_lazy_wall_ms_incl_create_and_h2d": float(np.mean([r[1] for r in runs])),
+                    "cov_lazy_columns": ls["columns"], "cov_lazy_pauses": ls["pauses"],
+                    "cov_vs_naive_same_support": bool(np.array_equal(bc != 0, bn != 0)),
+                    "cov_vs_naive_max_rel_diff": float(np.max(np.abs(bc - bn)) / max(np.max(np.abs(bn)), 1e-300))})
+        if fr is not None:
+            xr = SparseIterate(p)
+            t0 = time.perf_counter()
+            ref.coordinateDescent_(xr, fr, ProxL1(lam), opt)
+            row["cpu_port_1thread_ms"] = 1e3 * (time.perf_counter() - t0)
+            br = xr.toarray()
+            row["naive_vs_cpu_same_support"] = bool(np.array_equal(bn != 0, br != 0))
+            row["naive_vs_cpu_max_rel_diff"] = float(np.max(np.abs(bn - br)) / max(np.max(np.abs(br)), 1e-300))
+            row["naive_vs_cpu_same_trace"] = bool(fn.last_stats["visits"] == fr.last_stats["visits"] and fn.last_stats["passes"] == fr.last_stats["passes"])
+        out.append(row)
+    fn.close()
+    return {"workload": f"C1 lasso n={n} p={p}, 10 true non-zeros, single lambda, optTol 1e-7, ordered (X 40 MB: L2 resident)", "rows": out}
+
+
 def c4_data():
     n, p = 500, 50
     rng = np.random.default_rng(125)
@@ -736,7 +790,14 @@ def main():
         out["sharded"] = sharded
     if args.gpus == 1 and not args.no_secondary:
         sec = {}
-        for name, fn in (("c3_sqrt_lasso", lambda: c3_metrics(be, local, hbm)), ("c4_vc_lasso", lambda: c4_metrics(be, hbm))):
+        ref1 = None
+        if not args.no_cpu_baseline:
+            try:
+                ref1 = reference_setup(cfg)
+            except Exception:  # noqa: BLE001
+                ref1 = None
+        for name, fn in (("c1_lasso", lambda: c1_metrics(be, ref1)), ("c3_sqrt_lasso", lambda: c3_metrics(be, local, hbm)),
+                         ("c4_vc_lasso", lambda: c4_metrics(be, hbm))):
             try:
                 sec[name] = fn()
             except Exception as e:  # noqa: BLE001  (side measurements must never cost the headline line)

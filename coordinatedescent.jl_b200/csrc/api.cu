@@ -671,7 +671,8 @@ static int h2d_columns(double *dst, int64_t ld_dst, const double *src, int64_t l
 
 // ------------------------------------------------------- lazy covariance form --
 // (lazy_gram.cu) diag(A) and b up front, columns of A = X'X/n formed on demand in batches of 128 by the DMMA GEMM.
-static const int LZ_BATCH = 128;
+static const int LZ_BATCH = 128;  // columns per background batch (one 128-wide DMMA tile column)
+static const int LZ_NARROW = 32;  // columns per BLOCKING batch (128 x 32 tiles: a quarter of the tensor work, same X traffic)
 
 static int lazy_alloc(cdgpu_handle_s *h, int64_t n, int64_t p, int device) {
   h->kind = CDGPU_LOSS_QUAD;
@@ -743,8 +744,10 @@ static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const do
   if ((int)cols.size() > free_slots)
     return cdgpu_set_error(CDGPU_ECAP, "active set needs more columns than the lazy covariance cache holds (%d); use the "
                                        "eager form (cdgpu_gram_create) or raise CDGPU_LAZY_CAP", h->lz_cap);
-  int target = (int)((cols.size() + LZ_BATCH - 1) / LZ_BATCH * LZ_BATCH);
-  if (target == 0) target = LZ_BATCH;
+  // a blocking batch is narrow (the sweep kernel is waiting for it); the wide ones are formed in the background
+  const int width = getenv("CDGPU_LAZY_SPEC_OFF") ? LZ_BATCH : LZ_NARROW;
+  int target = (int)((cols.size() + width - 1) / width * width);
+  if (target == 0) target = width;
   target = std::min(target, free_slots);
   if (speculate && (int)cols.size() < target) {
     const int64_t p = h->p;
@@ -789,9 +792,7 @@ static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const do
 // (one 16-CTA cluster) runs on the main stream; the GEMM is sized for the remaining SMs.  The columns become visible to
 // the kernel only when the batch is committed (slot map written) at the next pause or at the end of the solve.
 static int lazy_spec_start(cdgpu_handle_s *h) {
-  // off by default: at BASELINE C2 the coordinate that forces the second batch is not among the 256 best-scoring
-  // ones at lambda_max, so the background batch only competes with the sweep kernel for L2 (measured: 12.77 -> 12.90 ms)
-  if (h->spec_inflight || h->next_n == 0 || !getenv("CDGPU_LAZY_SPEC")) return CDGPU_OK;
+  if (h->spec_inflight || h->next_n == 0 || getenv("CDGPU_LAZY_SPEC_OFF")) return CDGPU_OK;
   int nb = 0;
   for (int q = 0; q < h->next_n && nb < LZ_BATCH; ++q)
     if (h->hslot[h->next_cand[q]] < 0) h->spec_cols[nb++] = h->next_cand[q];

@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128;
+constexpr int BM = 128, BN_FULL = 128;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -44,15 +44,16 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 }
 
 // load one stage: rows (columns of X) [col0, col0+128) x k in [k0, k0+BK) into dst[128][LDK]
-template <bool ALIGNED16, int BK, int LDK, int GT>
+template <bool ALIGNED16, int BK, int LDK, int GT, int ROWS = 128>
 __device__ __forceinline__ void load_tile(double *dst, const double *X, long long ldx, long long n, int p, int col0,
                                           long long k0, int tid) {
   if (ALIGNED16) {
     constexpr int CPR = BK / 2; // 16-byte chunks per row
-    constexpr int ITERS = (128 * CPR) / GT;
+    constexpr int ITERS = (ROWS * CPR + GT - 1) / GT;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int idx = tid + it * GT;
+      if ((ROWS * CPR) % GT != 0 && idx >= ROWS * CPR) break;
       const int row = idx / CPR, ch = idx % CPR;
       const int col = col0 + row;
       const long long k = k0 + ch * 2;
@@ -62,10 +63,11 @@ __device__ __forceinline__ void load_tile(double *dst, const double *X, long lon
       cp_async16(dst + row * LDK + ch * 2, src, bytes);
     }
   } else {
-    constexpr int ITERS = (128 * BK) / GT;
+    constexpr int ITERS = (ROWS * BK + GT - 1) / GT;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int idx = tid + it * GT;
+      if ((ROWS * BK) % GT != 0 && idx >= ROWS * BK) break;
       const int row = idx / BK, ch = idx % BK;
       const int col = col0 + row;
       const long long k = k0 + ch;
@@ -80,7 +82,7 @@ __device__ __forceinline__ void load_tile(double *dst, const double *X, long lon
 // GEMM = false: SYRK on X (lower tiles, mirrored).  GEMM = true: C = X'B for a second K-contiguous operand
 // B (n x pb, ldb): every tile of the pa x pb rectangle, plain stores (used by the batched
 // varying-coefficient path, vc_batch.cu: all local Gram matrices in one FP64 tensor-core GEMM).
-template <bool ALIGNED16, int WM, int WN, int BK, int STAGES, bool PIPE, bool GEMM = false>
+template <bool ALIGNED16, int WM, int WN, int BK, int STAGES, bool PIPE, bool GEMM = false, int BN = 128>
 __global__ void __launch_bounds__(WM *WN * 32, 1)
     gram_syrk_kernel(const double *X, long long n, int p, long long ldx, double *G,
                      long long ldg, const int2 *__restrict__ tiles, int ntiles, double divisor, int mode,
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
       if (s < nK) {
         double *st = smem + s * STAGE_DOUBLES;
         load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, (long long)s * BK, tid);
-        load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, XB, ldB, n, pB, colB, (long long)s * BK, tid);
+        load_tile<ALIGNED16, BK, LDK, GT, BN>(st + BM * LDK, XB, ldB, n, pB, colB, (long long)s * BK, tid);
       }
       cp_commit();
     }
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
           if (kn < nK) {
             double *st = smem + (kn % STAGES) * STAGE_DOUBLES;
             load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, kn * BK, tid);
-            load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, XB, ldB, n, pB, colB, kn * BK, tid);
+            load_tile<ALIGNED16, BK, LDK, GT, BN>(st + BM * LDK, XB, ldB, n, pB, colB, kn * BK, tid);
           }
           cp_commit();
         }
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(WM *WN * 32, 1)
           if (kn < nK) {
             double *st = smem + (kn % STAGES) * STAGE_DOUBLES;
             load_tile<ALIGNED16, BK, LDK, GT>(st, X, ldx, n, p, colA, kn * BK, tid);
-            load_tile<ALIGNED16, BK, LDK, GT>(st + BM * LDK, XB, ldB, n, pB, colB, kn * BK, tid);
+            load_tile<ALIGNED16, BK, LDK, GT, BN>(st + BM * LDK, XB, ldB, n, pB, colB, kn * BK, tid);
           }
           cp_commit();
         }
@@ -250,12 +252,12 @@ __global__ void gram_reduce_slabs_kernel(const double *__restrict__ slab, int nc
                                          int p, double *G, long long ldg, double divisor, int mode) {
   const int tidx = blockIdx.x;
   const int bi = base_tiles[tidx].x, bj = base_tiles[tidx].y;
-  for (int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
-    const int r = e / BN, cc = e % BN;
-    const int row = bi * BM + r, col = bj * BN + cc;
+  for (int e = threadIdx.x; e < BM * BN_FULL; e += blockDim.x) {
+    const int r = e / BN_FULL, cc = e % BN_FULL;
+    const int row = bi * BM + r, col = bj * BN_FULL + cc;
     if (row >= p || col >= p || (bi == bj && row < col)) continue;
     double v = 0.0;
-    for (int c = 0; c < nchunks; ++c) v += slab[((size_t)c * slab_tiles + tidx) * (size_t)(BM * BN) + e];
+    for (int c = 0; c < nchunks; ++c) v += slab[((size_t)c * slab_tiles + tidx) * (size_t)(BM * BN_FULL) + e];
     if (mode == 1) v = v / divisor;
     G[row + (long long)col * ldg] = v;
     G[col + (long long)row * ldg] = v;
@@ -282,15 +284,15 @@ __global__ void xty_kernel(const double *__restrict__ X, long long n, int p, lon
 
 // row-split GEMM form: C tile = sum over row chunks of the slab partials (fixed order), / divisor
 __global__ void gemm_reduce_slabs_kernel(const double *__restrict__ slab, int nchunks, int slab_tiles, const int2 *__restrict__ base_tiles,
-                                         int pa, int pb, double *C, long long ldc, double divisor) {
+                                         int pa, int pb, double *C, long long ldc, double divisor, int bn) {
   const int tidx = blockIdx.x;
   const int bi = base_tiles[tidx].x, bj = base_tiles[tidx].y;
-  for (int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
+  for (int e = threadIdx.x; e < BM * bn; e += blockDim.x) {
     const int r = e % BM, cc = e / BM; // consecutive threads -> consecutive rows of one output column
-    const int row = bi * BM + r, col = bj * BN + cc;
+    const int row = bi * BM + r, col = bj * bn + cc;
     if (row >= pa || col >= pb) continue;
     double v = 0.0;
-    for (int c = 0; c < nchunks; ++c) v += slab[((size_t)c * slab_tiles + tidx) * (size_t)(BM * BN) + (size_t)r * BN + cc];
+    for (int c = 0; c < nchunks; ++c) v += slab[((size_t)c * slab_tiles + tidx) * (size_t)(BM * bn) + (size_t)r * bn + cc];
     C[row + (long long)col * ldc] = v / divisor;
   }
 }
@@ -376,7 +378,7 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
       for (int t = 0; t < ntiles; ++t) items.push_back(make_int2(base[t].x | (ch << 16), base[t].y | (t << 16)));
     int2 *ditems = nullptr, *dbase = nullptr;
     double *slab = nullptr;
-    const size_t slab_doubles = (size_t)nchunks * ntiles * BM * BN;
+    const size_t slab_doubles = (size_t)nchunks * ntiles * BM * BN_FULL;
     CUDA_TRY(cudaMallocAsync((void **)&ditems, items.size() * sizeof(int2), h->stream));
     CUDA_TRY(cudaMallocAsync((void **)&dbase, base.size() * sizeof(int2), h->stream));
     CUDA_TRY(cudaMallocAsync((void **)&slab, slab_doubles * sizeof(double), h->stream));
@@ -384,7 +386,7 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
     CUDA_TRY(cudaMemcpyAsync(dbase, base.data(), base.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream)); // host temporaries
     auto kern = gram_syrk_kernel<true, 2, 4, 16, 4, true>;
-    const size_t dyn = (size_t)4 * (BM + BN) * (16 + 4) * sizeof(double);
+    const size_t dyn = (size_t)4 * (BM + BN_FULL) * (16 + 4) * sizeof(double);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     kern<<<min((int)items.size(), h->sm_count), 256, dyn, h->stream>>>(X, n, p, ldx, G, ldg, ditems, (int)items.size(), divisor, mode,
                                                                       nullptr, 0, 0, kchunk, slab, ntiles);
@@ -408,7 +410,7 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
     CUDA_TRY(cudaGetLastError());
     return CDGPU_OK;
   };
-#define GRAM_DYN(BK, ST) ((size_t)(ST) * (BM + BN) * ((BK) + 4) * sizeof(double))
+#define GRAM_DYN(BK, ST) ((size_t)(ST) * (BM + BN_FULL) * ((BK) + 4) * sizeof(double))
   int rc;
   if (!aligned)
     rc = launch(gram_syrk_kernel<false, 2, 4, 16, 4, false>, 256, GRAM_DYN(16, 4));
@@ -443,7 +445,7 @@ int launch_gram(cdgpu_handle_s *h, const double *X, long long n, int p, long lon
 // has drained.
 int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, long long lda, const double *B, int pb,
                    long long ldb, long long n, double *C, long long ldc, double divisor, void **tiles_out) {
-  const int nbi = (pa + BM - 1) / BM, nbj = (pb + BN - 1) / BN;
+  const int nbi = (pa + BM - 1) / BM, nbj = (pb + BN_FULL - 1) / BN_FULL;
   std::vector<int2> tiles;
   tiles.reserve((size_t)nbi * nbj);
   // column panels of B outermost: the CTAs in flight share a few B panels and all of A through L2
@@ -460,7 +462,7 @@ int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, l
   const bool aligned = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((lda & 1) == 0) &&
                        ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((ldb & 1) == 0);
   const int grid = min(ntiles, sm_count);
-  const size_t dyn = (size_t)4 * (BM + BN) * (16 + 4) * sizeof(double);
+  const size_t dyn = (size_t)4 * (BM + BN_FULL) * (16 + 4) * sizeof(double);
   if (aligned) {
     auto kern = gram_syrk_kernel<true, 2, 4, 16, 4, true, true>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -481,10 +483,12 @@ int launch_gemm_tn(cudaStream_t stream, int sm_count, const double *A, int pa, l
 // ordered; the scratch comes from and returns to the stream's pool.
 int launch_gemm_tn_split(cudaStream_t stream, int sm_count, const double *A, int pa, long long lda, const double *B, int pb,
                          long long ldb, long long n, double *C, long long ldc, double divisor) {
-  const int nbi = (pa + BM - 1) / BM, nbj = (pb + BN - 1) / BN;
-  const int ntiles = nbi * nbj;
   const bool aligned = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((lda & 1) == 0) &&
                        ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((ldb & 1) == 0);
+  // narrow batches (<= 32 columns) use a 128 x 32 tile: a quarter of the DMMA work of the 128-wide tile for the same X traffic
+  const int bn = (pb <= 32 && aligned) ? 32 : BN_FULL;
+  const int nbi = (pa + BM - 1) / BM, nbj = (pb + bn - 1) / bn;
+  const int ntiles = nbi * nbj;
   int best_c = 1;
   double best_eff = 0.0;
   for (int c = 1; c <= 64; ++c) {
@@ -496,7 +500,7 @@ int launch_gemm_tn_split(cudaStream_t stream, int sm_count, const double *A, int
       best_c = c;
     }
   }
-  if (!aligned || best_c == 1 || ntiles >= 65536 || nbi >= 65536) {
+  if (!aligned || (best_c == 1 && bn == BN_FULL) || ntiles >= 65536 || nbi >= 65536) {
     void *tiles = nullptr;
     CD_TRY(launch_gemm_tn(stream, sm_count, A, pa, lda, B, pb, ldb, n, C, ldc, divisor, &tiles));
     CUDA_TRY(cudaFreeAsync(tiles, stream));
@@ -514,20 +518,27 @@ int launch_gemm_tn_split(cudaStream_t stream, int sm_count, const double *A, int
     for (int t = 0; t < ntiles; ++t) items.push_back(make_int2(base[(size_t)t].x | (ch << 16), base[(size_t)t].y | (t << 16)));
   int2 *ditems = nullptr, *dbase = nullptr;
   double *slab = nullptr;
-  const size_t slab_doubles = (size_t)nchunks * ntiles * BM * BN;
+  const size_t slab_doubles = (size_t)nchunks * ntiles * BM * bn;
   CUDA_TRY(cudaMallocAsync((void **)&ditems, items.size() * sizeof(int2), stream));
   CUDA_TRY(cudaMallocAsync((void **)&dbase, base.size() * sizeof(int2), stream));
   CUDA_TRY(cudaMallocAsync((void **)&slab, slab_doubles * sizeof(double), stream));
   CUDA_TRY(cudaMemcpyAsync(ditems, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
   CUDA_TRY(cudaMemcpyAsync(dbase, base.data(), base.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
   CUDA_TRY(cudaStreamSynchronize(stream)); // host temporaries
-  auto kern = gram_syrk_kernel<true, 2, 4, 16, 4, true, true>;
-  const size_t dyn = (size_t)4 * (BM + BN) * (16 + 4) * sizeof(double);
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  kern<<<min((int)items.size(), sm_count), 256, dyn, stream>>>(A, n, pa, lda, C, ldc, ditems, (int)items.size(), divisor, 1, B, pb,
-                                                                 ldb, kchunk, slab, ntiles);
+  const int grid = min((int)items.size(), sm_count);
+  if (bn == 32) {
+    auto kern = gram_syrk_kernel<true, 8, 1, 16, 4, true, true, 32>;
+    const size_t dyn = (size_t)4 * (BM + 32) * (16 + 4) * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<grid, 256, dyn, stream>>>(A, n, pa, lda, C, ldc, ditems, (int)items.size(), divisor, 1, B, pb, ldb, kchunk, slab, ntiles);
+  } else {
+    auto kern = gram_syrk_kernel<true, 2, 4, 16, 4, true, true>;
+    const size_t dyn = (size_t)4 * (BM + BN_FULL) * (16 + 4) * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<grid, 256, dyn, stream>>>(A, n, pa, lda, C, ldc, ditems, (int)items.size(), divisor, 1, B, pb, ldb, kchunk, slab, ntiles);
+  }
   CUDA_TRY(cudaGetLastError());
-  gemm_reduce_slabs_kernel<<<ntiles, 512, 0, stream>>>(slab, nchunks, ntiles, dbase, pa, pb, C, ldc, divisor);
+  gemm_reduce_slabs_kernel<<<ntiles, 512, 0, stream>>>(slab, nchunks, ntiles, dbase, pa, pb, C, ldc, divisor, bn);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaFreeAsync(slab, stream));
   CUDA_TRY(cudaFreeAsync(ditems, stream));
