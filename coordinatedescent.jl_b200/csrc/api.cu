@@ -733,6 +733,30 @@ static int lazy_form(cdgpu_handle_s *h, const std::vector<int> &cols) {
   return CDGPU_OK;
 }
 
+// The cache starts at 4096 slots (CDGPU_LAZY_CAP) and grows by doubling, up to all p columns, when a solve needs more:
+// a new buffer, one device-to-device copy of the filled slots (the kernel is paused / not running; a background batch
+// has been committed by the caller), the old buffer back to the pool.  Not enough memory for the next size: the cache
+// stays as it is and the caller reports CDGPU_ECAP.
+static int lazy_reserve(cdgpu_handle_s *h, int64_t slots) {
+  if (slots <= h->lz_cap) return CDGPU_OK;
+  const int64_t pmax = (h->p + LZ_BATCH - 1) / LZ_BATCH * LZ_BATCH;
+  int64_t cap = std::max<int64_t>(h->lz_cap, LZ_BATCH);
+  while (cap < slots) cap *= 2;
+  cap = std::min(cap, pmax);
+  if (cap <= h->lz_cap) return CDGPU_OK;
+  double *nb = nullptr;
+  if (dalloc(&nb, (size_t)h->ld * (size_t)cap) != CDGPU_OK) {
+    (void)cudaGetLastError();
+    return CDGPU_OK;
+  }
+  CUDA_TRY(cudaMemcpyAsync(nb, h->dX, (size_t)h->ld * (size_t)h->lz_used * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  dfree(h->dX);
+  h->dX = nb;
+  h->lz_cap = (int)cap;
+  return CDGPU_OK;
+}
+
 // make sure the columns `need` exist; fill the batch up with the best-scoring candidates (|Ax_j + b_j| / omega_j)
 static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const double *domega, bool speculate) {
   std::vector<int> cols;
@@ -740,14 +764,19 @@ static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const do
   for (int k : need)
     if (h->hslot[k] < 0 && std::find(cols.begin(), cols.end(), k) == cols.end()) cols.push_back(k);
   if (cols.empty() && (!speculate || h->lz_used > 0)) return CDGPU_OK; // nothing missing (a fresh handle still forms its first batch)
-  const int free_slots = h->lz_cap - h->lz_used;
-  if ((int)cols.size() > free_slots)
-    return cdgpu_set_error(CDGPU_ECAP, "active set needs more columns than the lazy covariance cache holds (%d); use the "
-                                       "eager form (cdgpu_gram_create) or raise CDGPU_LAZY_CAP", h->lz_cap);
-  // a blocking batch is narrow (the sweep kernel is waiting for it); the wide ones are formed in the background
-  const int width = getenv("CDGPU_LAZY_SPEC_OFF") ? LZ_BATCH : LZ_NARROW;
+  // a blocking batch is narrow (the sweep kernel is waiting for it); the wide ones are formed in the background.  A
+  // solve that keeps pausing is a dense one: from the third pause on the blocking batch doubles every time, so the
+  // number of pauses grows with the logarithm of the columns a solve touches and at most ~2x of them are formed.
+  int width = getenv("CDGPU_LAZY_SPEC_OFF") ? LZ_BATCH : LZ_NARROW;
+  if (h->lz_pauses > 2) width = (int)std::min<int64_t>((int64_t)width << std::min<int64_t>(h->lz_pauses - 2, 6), 2048);
   int target = (int)((cols.size() + width - 1) / width * width);
   if (target == 0) target = width;
+  target = (int)std::min<int64_t>(target, std::max<int64_t>((int64_t)cols.size(), h->p - h->lz_used));
+  CD_TRY(lazy_reserve(h, (int64_t)h->lz_used + target)); // grows the cache (up to all p columns) when it has to
+  const int free_slots = h->lz_cap - h->lz_used;
+  if ((int)cols.size() > free_slots)
+    return cdgpu_set_error(CDGPU_ECAP, "active set needs more columns than the lazy covariance cache can hold (%d of %lld)",
+                           h->lz_cap, (long long)h->p);
   target = std::min(target, free_slots);
   if (speculate && (int)cols.size() < target) {
     const int64_t p = h->p;
@@ -1213,6 +1242,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
         CUDA_TRY(cudaStreamSynchronize(h->stream));
       }
       CD_TRY(lazy_ensure(h, need, rc.domega, h->lz_used == 0 && !getenv("CDGPU_LAZY_NO_PREFETCH")));
+      a.A = h->dX; // the cache may have moved (lazy_reserve)
       CUDA_TRY(cudaMemsetAsync(h->dresume, 0, sizeof(CovResume), h->stream));
     }
     if (prof) CUDA_TRY(cudaMemsetAsync(a.prof, 0, 24 * sizeof(long long), h->stream));
@@ -1240,6 +1270,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
       std::vector<int> need(1, R.need_k);
       const bool missed = h->hslot[R.need_k] < 0; // speculation did not cover it: form a batch now, speculate again afterwards
       CD_TRY(lazy_ensure(h, need, rc.domega, !getenv("CDGPU_LAZY_NO_PREFETCH")));
+      a.A = h->dX; // the cache may have moved (lazy_reserve)
       const int one = 1;
       CUDA_TRY(cudaMemcpyAsync(&h->dresume->valid, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream)); // `one` is a stack temporary
