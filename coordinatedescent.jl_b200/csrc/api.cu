@@ -176,8 +176,8 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   };
   const size_t o_beta = take(p * sizeof(double)), o_act = take(p * sizeof(int)), o_actval = take(p * sizeof(double)),
                o_nact = take(sizeof(int)), o_inlist = take(p), o_omega = take(p * sizeof(double)),
-               o_scr = take((15 * p + 8 * (size_t)h->n + 64 + 4 * 2048 + 64) * sizeof(double)),
-               o_iscr = take((10 * p + 64) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(8 * sizeof(int));
+               o_scr = take((cd_scr_tail(p, (size_t)h->n) + 16 * p + 8) * sizeof(double)),
+               o_iscr = take((10 * p + 64) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(16 * sizeof(int));
   CD_TRY(dalloc(&h->dcommon, off));
   unsigned char *base = h->dcommon;
   h->dbeta = (double *)(base + o_beta);
@@ -193,7 +193,7 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   CUDA_TRY(cudaMemsetAsync(h->dbeta, 0, p * sizeof(double), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dinlist, 0, p, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dnact, 0, sizeof(int), h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 8 * sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 16 * sizeof(int), h->stream));
   CD_TRY(device_sm_count(h->device, &h->sm_count));
   CUDA_TRY(cudaEventCreate(&h->sw_ev0));
   CUDA_TRY(cudaEventCreate(&h->sw_ev1));
@@ -1188,7 +1188,8 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
   CUDA_TRY(cudaMemcpyAsync(h->dlam, rc.lambdas, (size_t)rc.nlambda * sizeof(double), cudaMemcpyHostToDevice,
                            h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dflag, 0, 4 * sizeof(int), h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->dflag + 4, 0xff, 4 * sizeof(int), h->stream)); // first-mover words
+  CUDA_TRY(cudaMemsetAsync(h->dflag + 4, 0xff, 8 * sizeof(int), h->stream)); // first-mover words
+  CUDA_TRY(cudaMemsetAsync(h->dflag + 12, 0, 4 * sizeof(int), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dstats, 0, (size_t)rc.nlambda * sizeof(DevStats), h->stream));
   if (rc.want_path) CUDA_TRY(cudaMemsetAsync(h->dcolptr, 0, ((size_t)rc.nlambda + 1) * sizeof(long long), h->stream));
   if (h->kind == CDGPU_LOSS_QUAD) {
@@ -1341,6 +1342,10 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.multi_ok = 384; // smallest active set handed to the 16-CTA team engine (below: chain-bound on one CTA anyway)
     if (const char *env = getenv("CDGPU_MULTI_MIN")) a.multi_ok = std::max(64, atoi(env));
     if (const char *env = getenv("CDGPU_NAIVE_MULTI")) a.multi_ok = atoi(env) != 0 ? a.multi_ok : 0;
+    a.pipeline = 1;
+    if (const char *env = getenv("CDGPU_NAIVE_PIPELINE")) a.pipeline = atoi(env) != 0;
+    a.plan = 1;
+    if (const char *env = getenv("CDGPU_NAIVE_PLAN")) a.plan = atoi(env) != 0;
     a.scaled = rc.scaled;
     a.outerMaxIter = rc.outerMaxIter;
     a.outerTol = rc.outerTol;
@@ -1355,8 +1360,8 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
       CUDA_TRY(cudaStreamSynchronize(h->stream));
       fprintf(stderr,
               "[cdgpu profile] naive path (CTA 0): total %.3f Mcyc | full-pass rounds %lld: column dots %.3f, grid.sync "
-              "%.3f, scan %.3f, apply %.3f | list update %.3f | active phase %.3f\n",
-              pf[6] * 1e-6, pf[7], pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6);
+              "%.3f, scan %.3f, apply %.3f | list update %.3f | active phase %.3f | member plan %.3f\n",
+              pf[6] * 1e-6, pf[7], pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6, pf[8] * 1e-6);
       fprintf(stderr,
               "[cdgpu profile]   chain engine: warp0 panel %.3f chain %.3f barrier %.3f pass-ends %.3f | workers stage %.3f apply "
               "%.3f barrier %.3f Mcyc\n",

@@ -48,6 +48,7 @@ struct NSmem {
   double bval[2], bval2[2];
   int nact, flag, nonapp;
   int s2[2];
+  unsigned warr; // warp arrivals at the warp-granular round barrier of the full pass (monotonic)
   chain::Shared ch;
 };
 
@@ -57,7 +58,7 @@ struct NCtx {
   NSmem *sm;
   double *r, *w; // shared
   double rr;     // ||r||^2 (every thread of every CTA holds the same value)
-  HEntry *hbuf;  // global, 2 * CH
+  HEntry *hbuf;  // global, 4 * CH (slot = round & 3)
   NBcast *bc;    // global
   // shared state of the covariance-form active engine (chain_engine.cuh), gcap entries (0: engine disabled)
   int *e_row, *e_coord;
@@ -65,7 +66,8 @@ struct NCtx {
   unsigned short *e_ord, *e_pos;
   int gcap;
   int CH, G, bid;
-  unsigned bar_target; // rounds of the full-pass barrier so far, times G
+  unsigned bar_target; // grid barriers so far, times G (every thread keeps the same value)
+  unsigned rnd;        // rounds of the full pass so far (slot of the first-mover word / result buffer = rnd & 3)
 };
 
 __device__ __forceinline__ double block_sum(NSmem *sm, double v, int slot) {
@@ -185,9 +187,9 @@ __device__ __forceinline__ double warp_col_dot(const NCtx &c, const double *col)
 // cg::grid_group::sync() over 148 CTAs.  The counter is zeroed at kernel start.
 __device__ __forceinline__ void fast_grid_sync(NCtx &c) {
   unsigned *ctr = reinterpret_cast<unsigned *>(c.a.flag + 7);
+  c.bar_target += (unsigned)c.G;
   __syncthreads();
   if (threadIdx.x == 0) {
-    c.bar_target += (unsigned)c.G;
     __threadfence();
     atomicAdd(ctr, 1u);
     unsigned v;
@@ -237,110 +239,310 @@ __device__ __forceinline__ void apply_step(NCtx &c, const double *col, double h)
   }
 }
 
+// r -= sum_t X[:, k_t] h_t over the planned members t in [t0, t1) (consecutive visit positions), element by element in
+// visit order with the same non-fused operations as one apply_step per member; ||r||^2 refreshed as apply_step does.
+__device__ void apply_planned(NCtx &c, int t0, int t1, double &maxH, long long &accepted) {
+  const NaiveArgs &a = c.a;
+  const int n = a.n, tid = threadIdx.x;
+  for (int i0 = tid; i0 < n; i0 += 2 * NV_T) {
+    const int i1 = i0 + NV_T;
+    double v0 = c.r[i0], v1 = i1 < n ? c.r[i1] : 0.0;
+    int t = t0;
+    for (; t + 4 <= t1; t += 4) { // 8 independent loads in flight, then the dependent updates in visit order
+      double x0[4], x1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double *col = a.X + (long long)c.e_coord[t + u] * a.ldx;
+        x0[u] = __ldg(col + i0);
+        x1[u] = i1 < n ? __ldg(col + i1) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double h = c.e_g[t + u];
+        v0 = __dsub_rn(v0, __dmul_rn(x0[u], h));
+        v1 = __dsub_rn(v1, __dmul_rn(x1[u], h));
+      }
+    }
+    for (; t < t1; ++t) {
+      const double *col = a.X + (long long)c.e_coord[t] * a.ldx;
+      const double h = c.e_g[t];
+      v0 = __dsub_rn(v0, __dmul_rn(__ldg(col + i0), h));
+      if (i1 < n) v1 = __dsub_rn(v1, __dmul_rn(__ldg(col + i1), h));
+    }
+    c.r[i0] = v0;
+    if (i1 < n) c.r[i1] = v1;
+  }
+  __syncthreads();
+  if (a.kind == CDGPU_LOSS_SQRT) { // same rows per thread and same summation order as apply_step
+    double acc = 0.0;
+    for (int i0 = tid; i0 < n; i0 += 8 * NV_T) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NV_T;
+        if (i < n) acc = fma(c.r[i], c.r[i], acc);
+      }
+    }
+    c.rr = block_sum(c.sm, acc, 0);
+    __syncthreads();
+  }
+  for (int t = t0; t < t1; ++t) {
+    const double h = c.e_g[t];
+    maxH = fmax(maxH, fabs(h));
+    accepted += h != 0.0;
+  }
+  if (c.bid == 0)
+    for (int t = t0 + tid; t < t1; t += NV_T)
+      if (c.e_g[t] != 0.0) __stcg(a.beta + c.e_coord[t], c.e_be[t]);
+}
+
+// plan arrays in global memory (CTA 0 writes, everybody copies them to shared memory)
+struct NPlan {
+  int *k, *pos;
+  double *h, *nw;
+};
+__device__ __forceinline__ NPlan plan_arrays(const NaiveArgs &a) {
+  NPlan P;
+  P.k = a.iscr + 8 * (long long)a.p;
+  P.pos = a.iscr + 9 * (long long)a.p;
+  P.h = a.scr + 8 + 9 * (long long)a.p + 32 + 2 * NV_GCAP_;
+  P.nw = P.h + NV_GCAP_;
+  return P;
+}
+
 // ------------------------------------------------------------------ full pass --
-__device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter, int &rp, int &round3,
-                            long long &accepted, long long *pf, int nact_hint) {
+// A ROUND evaluates a window of columns against the same r, then one grid barrier makes the first mover of the window
+// known to every CTA.  Rounds are numbered over the whole kernel (c.rnd); round s owns slot s & 3 of the result buffers
+// and of the first-mover words; every round has exactly one barrier (arrive_s after check_{s-1}).
+//  * CTA-per-column rounds (right behind a mover: movers cluster, lowest latency) use the CTA-wide barrier.
+//  * Warp-per-column rounds (streaming regime) are WARP-GRANULAR and SPLIT-PHASE: a warp that has finished its columns
+//    of round s arrives (shared counter; the last warp of the CTA arrives at the grid counter) and, once two rounds in a
+//    row were clean, goes straight on to the columns of round s+1 — evaluated against the same r on the assumption that
+//    round s is clean too — and only then waits for barrier s.  In the clean streaming regime no SM ever drains its
+//    memory pipeline at a barrier.  A mover in round s discards round s+1 (its barrier still runs, empty).
+//  * first-mover word of round s is reset by CTA 0 at check_{s+1}: everyone read it at check_s, i.e. before arriving at
+//    barrier s+1, and its next writers (round s+4) start behind barrier s+2, which CTA 0 joins after that reset.
+__device__ __forceinline__ void round_arrive_warp(NCtx &c) {
+  unsigned *ctr = reinterpret_cast<unsigned *>(c.a.flag + 7);
+  c.bar_target += (unsigned)c.G;
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    __threadfence(); // this warp's results of the round
+    const unsigned old = atomicAdd(&c.sm->warr, 1u);
+    if ((old % NV_W) == NV_W - 1) {
+      __threadfence();
+      atomicAdd(ctr, 1u);
+    }
+  }
+}
+__device__ __forceinline__ void round_wait_warp(NCtx &c) {
+  unsigned *ctr = reinterpret_cast<unsigned *>(c.a.flag + 7);
+  if ((threadIdx.x & 31) == 0) {
+    unsigned v;
+    int spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= c.bar_target) break;
+      if (++spins > 8) __nanosleep(128);
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void round_arrive_cta(NCtx &c) {
+  unsigned *ctr = reinterpret_cast<unsigned *>(c.a.flag + 7);
+  c.bar_target += (unsigned)c.G;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+  }
+}
+__device__ __forceinline__ void round_wait_cta(NCtx &c) {
+  unsigned *ctr = reinterpret_cast<unsigned *>(c.a.flag + 7);
+  if (threadIdx.x == 0) {
+    unsigned v;
+    int spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= c.bar_target) break;
+      if (++spins > 64) __nanosleep(256);
+    }
+  }
+  __syncthreads();
+}
+
+struct NWin {
+  int q0, qlen, W, slot;
+  bool cta;
+};
+
+// evaluate the columns of a window against the current r: tentative (h, new value) per position, first mover by atomicMin
+__device__ __forceinline__ void eval_window(NCtx &c, const NWin &wn, double lam, const PermKey &pk, bool ordered,
+                                            unsigned int *words, int *nonapp_flags) {
   const NaiveArgs &a = c.a;
   NSmem *sm = c.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  HEntry *hb = c.hbuf + (size_t)wn.slot * c.CH;
+  unsigned int *gmin = words + wn.slot;
+  int *nonapp_flag = nonapp_flags + wn.slot;
+  if (wn.cta) { // CTA-per-column mode
+    const int j = c.bid;
+    if (j < wn.qlen) {
+      const int k = ordered ? wn.q0 + j : (int)cd_perm(pk, (uint32_t)(wn.q0 + j));
+      const double *col = a.X + (long long)k * a.ldx;
+      double s = 0.0;
+      for (int t0 = tid; t0 < a.n; t0 += 8 * NV_T) {
+        double xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = (t0 + u * NV_T < a.n) ? __ldg(col + t0 + u * NV_T) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + u * NV_T;
+          if (t < a.n) s = fma(c.w ? xv[u] * c.w[t] : xv[u], c.r[t], s);
+        }
+      }
+      const double d = block_sum(sm, s, 1);
+      if (tid == 0) {
+        double nw, h;
+        bool tnz;
+        coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
+                     c.rr, nw, h, tnz);
+        const int app = (a.kind == CDGPU_LOSS_SQRT || tnz || __ldcg(a.inlist + k)) ? 1 : 0;
+        __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
+        __stcg(&hb[j].app, app);
+        if (!app) __stcg(nonapp_flag, 1);
+        if (h != 0.0) atomicMin(gmin, (unsigned int)j);
+      }
+    }
+    return;
+  }
+  // position j of the window belongs to CTA j % G, warp (j / G) % NV_W
+  for (int j = c.bid + c.G * warp; j < wn.qlen; j += c.G * NV_W) {
+    const int k = ordered ? wn.q0 + j : (int)cd_perm(pk, (uint32_t)(wn.q0 + j));
+    const double d = warp_col_dot(c, a.X + (long long)k * a.ldx);
+    if (lane == 0) {
+      double nw, h;
+      bool tnz;
+      coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
+                   c.rr, nw, h, tnz);
+      // sqrt-lasso never appends temporarily (x[k] = newVal, :278-283), so nothing to track there
+      const int app = (a.kind == CDGPU_LOSS_SQRT || tnz || __ldcg(a.inlist + k)) ? 1 : 0;
+      __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
+      __stcg(&hb[j].app, app);
+      if (!app) __stcg(nonapp_flag, 1);
+      if (h != 0.0) atomicMin(gmin, (unsigned int)j); // first position of the round that moves
+    }
+  }
+}
+
+// PLANNED MEMBERS (mP > 0): the members of the iterate almost always move in a full pass (an active phase only converges
+// to optTol), and each of them used to cost a round of its own: evaluation of the window behind it, grid barrier, apply.
+// With a plan (member_plan below: the members' steps, computed beforehand by one chain pass over the active Gram in
+// VISIT order on the assumption that no non-member moves) every CTA applies a member's step to its copy of r when the
+// sweep reaches its position — no barrier, consecutive members in one fused update — and windows hold non-members only
+// and never cross a planned position.  A non-member that does move voids the rest of the plan: the remaining members
+// are then evaluated like any other column.  c.e_coord / e_row / e_g / e_be (idle during a full pass) hold the plan:
+// coordinate, visit position, h, new value, in visit order.
+__device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter, long long &accepted, long long *pf,
+                            int nact_hint, int mP) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x;
   const bool ordered = a.randomize == 0;
   const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
-  int *nonapp_flag = a.flag + 2;              // set by any warp that produced a non-appended entry
-  unsigned int *gmin = reinterpret_cast<unsigned int *>(a.flag + 4); // 3 rotating words: first mover of a round
-  int *nonapp_list = a.iscr + 6 * (long long)a.p; // CTA 0
+  unsigned int *words = reinterpret_cast<unsigned int *>(a.flag + 8); // 4 rotating words: first mover of a round
+  int *nonapp_flags = a.flag + 12; // per slot: some warp produced a non-appended entry in that round (reset with the word)
+  int *nonapp_list = a.iscr + 6 * (long long)a.p;                     // CTA 0
   double maxH = 0.0;
-  if (c.bid == 0 && tid == 0) {
-    sm->nonapp = 0;
-    __stcg(nonapp_flag, 0);
-  }
+  if (c.bid == 0 && tid == 0) sm->nonapp = 0;
   // Window of columns evaluated in parallel against the same r.  A mover invalidates everything behind it,
   // so the window restarts small right behind a mover (those columns are L2-hot: a cheap re-evaluation)
   // and doubles after every clean round up to CH (streaming regime: one barrier per CH columns).
   // Right behind a mover the window is G columns, ONE PER CTA (16 warps share a column: lowest latency,
   // movers tend to cluster); a clean round then widens it to one column per warp, 2 per warp, ...
   const int Wwarp = min(c.CH, c.G * NV_W);
-  int W = nact_hint > 0 ? min(c.CH, c.G) : Wwarp;
-  int q0 = 0;
-  while (q0 < a.p) {
-    const int qlen = min(W, a.p - q0);
-    HEntry *hb = c.hbuf + (size_t)rp * c.CH;
-    const long long ta = clock64();
-    if (W <= c.G) { // CTA-per-column mode
-      const int j = c.bid;
-      if (j < qlen) {
-        const int k = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
-        const double *col = a.X + (long long)k * a.ldx;
-        double s = 0.0;
-        for (int t0 = tid; t0 < a.n; t0 += 8 * NV_T) {
-          double xv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) xv[u] = (t0 + u * NV_T < a.n) ? __ldg(col + t0 + u * NV_T) : 0.0;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int t = t0 + u * NV_T;
-            if (t < a.n) s = fma(c.w ? xv[u] * c.w[t] : xv[u], c.r[t], s);
-          }
-        }
-        const double d = block_sum(sm, s, 1);
-        if (tid == 0) {
-          double nw, h;
-          bool tnz;
-          coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
-                       c.rr, nw, h, tnz);
-          const int app = (a.kind == CDGPU_LOSS_SQRT || tnz || __ldcg(a.inlist + k)) ? 1 : 0;
-          __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
-          __stcg(&hb[j].app, app);
-          if (!app) __stcg(nonapp_flag, 1);
-          if (h != 0.0) atomicMin(gmin + round3, (unsigned int)j);
-        }
+  auto grow = [&](const NWin &w) { return w.cta ? Wwarp : min(c.CH, 2 * w.W); };
+  auto make = [&](int q0, int W) {
+    NWin w;
+    w.q0 = q0;
+    w.W = W;
+    w.qlen = min(W, a.p - q0);
+    w.cta = W <= c.G;
+    w.slot = (int)(c.rnd & 3u);
+    c.rnd += 1;
+    return w;
+  };
+  const bool pipeline = a.pipeline != 0;
+  int Wnext = (nact_hint > 0 && mP == 0) ? min(c.CH, c.G) : Wwarp;
+  int q0 = 0, streak = mP > 0 ? 2 : 0; // with a plan the sweep is expected to be clean: pipelined from the first window
+  int pi = 0;                          // next planned member
+  bool have_pend = false;
+  NWin pend = {}, spec = {};
+  for (;;) {
+    long long ta = clock64();
+    if (!have_pend) {
+      if (q0 >= a.p) break;
+      if (pi < mP && c.e_row[pi] == q0) { // a run of planned members at consecutive positions: one fused update of r
+        int pj = pi + 1;
+        while (pj < mP && c.e_row[pj] == q0 + (pj - pi)) ++pj;
+        apply_planned(c, pi, pj, maxH, accepted);
+        q0 += pj - pi;
+        pi = pj;
+        pf[3] += clock64() - ta;
+        continue;
       }
-    } else {
-    // position j of the window belongs to CTA j % G, warp (j / G) % NV_W
-    for (int j = c.bid + c.G * warp; j < qlen; j += c.G * NV_W) {
-      const int k = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
-      const double d = warp_col_dot(c, a.X + (long long)k * a.ldx);
-      if (lane == 0) {
-        double nw, h;
-        bool tnz;
-        coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), lam, a.omega ? __ldg(a.omega + k) : 1.0,
-                     c.rr, nw, h, tnz);
-        // sqrt-lasso never appends temporarily (x[k] = newVal, :278-283), so nothing to track there
-        const int app = (a.kind == CDGPU_LOSS_SQRT || tnz || __ldcg(a.inlist + k)) ? 1 : 0;
-        __stcg(reinterpret_cast<double2 *>(hb + j), make_double2(h, nw));
-        __stcg(&hb[j].app, app);
-        if (!app) __stcg(nonapp_flag, 1);
-        if (h != 0.0) atomicMin(gmin + round3, (unsigned int)j); // first position of the round that moves
-      }
+      pend = make(q0, Wnext);
+      if (pi < mP) pend.qlen = min(pend.qlen, c.e_row[pi] - q0);
+      eval_window(c, pend, lam, pk, ordered, words, nonapp_flags);
+      if (pend.cta) round_arrive_cta(c); else round_arrive_warp(c);
+      have_pend = true;
     }
+    // the next window, on the assumption that `pend` turns out clean: evaluated while barrier `pend` completes
+    bool have_spec = false;
+    if (pipeline && streak >= 2 && !pend.cta && pend.q0 + pend.qlen < a.p && !(pi < mP && c.e_row[pi] == pend.q0 + pend.qlen)) {
+      spec = make(pend.q0 + pend.qlen, grow(pend));
+      if (pi < mP) spec.qlen = min(spec.qlen, c.e_row[pi] - spec.q0);
+      eval_window(c, spec, lam, pk, ordered, words, nonapp_flags);
+      have_spec = true;
     }
     const long long tb = clock64();
-    fast_grid_sync(c);
+    if (pend.cta) round_wait_cta(c); else round_wait_warp(c);
     const long long tc = clock64();
     pf[0] += tb - ta;
     pf[1] += tc - tb;
     pf[7] += 1;
-    const unsigned int jmin = __ldcg(gmin + round3);
-    // the word used two rounds from now was last read before this barrier: reset it
-    if (c.bid == 0 && tid == 0) __stcg(gmin + (round3 + 2) % 3, 0xffffffffu);
-    round3 = (round3 + 1) % 3;
-    rp ^= 1;
-    if (c.bid == 0 && __ldcg(nonapp_flag)) { // rare: remember the finalised non-appended coordinates
-      const int jend = jmin == 0xffffffffu ? qlen : (int)jmin;
+    const HEntry *hb = c.hbuf + (size_t)pend.slot * c.CH;
+    const unsigned int jmin = __ldcg(words + pend.slot);
+    if (c.bid == 0 && tid == 0) { // the previous round's word and flag
+      __stcg(words + ((pend.slot + 3) & 3), 0xffffffffu);
+      __stcg(nonapp_flags + ((pend.slot + 3) & 3), 0);
+    }
+    if (c.bid == 0 && __ldcg(nonapp_flags + pend.slot)) { // rare: remember the finalised non-appended coordinates
+      __syncthreads();
+      const int jend = jmin == 0xffffffffu ? pend.qlen : (int)jmin;
       for (int j = tid; j < jend; j += NV_T)
         if (__ldcg(&hb[j].app) == 0)
-          nonapp_list[atomicAdd(&sm->nonapp, 1)] = ordered ? q0 + j : (int)cd_perm(pk, (uint32_t)(q0 + j));
+          nonapp_list[atomicAdd(&sm->nonapp, 1)] = ordered ? pend.q0 + j : (int)cd_perm(pk, (uint32_t)(pend.q0 + j));
       __syncthreads();
     }
     const long long td = clock64();
     pf[2] += td - tc;
     if (jmin == 0xffffffffu) { // clean round: every position of the window is final
-      q0 += qlen;
-      W = W <= c.G ? Wwarp : min(c.CH, 2 * W);
+      q0 = pend.q0 + pend.qlen;
+      Wnext = grow(pend);
+      streak += 1;
+      if (have_spec) {
+        round_arrive_warp(c); // arrive_{s+1} only now: the grid counter is shared by consecutive barriers
+        pend = spec;
+        Wnext = grow(pend);
+      } else {
+        have_pend = false;
+      }
       continue;
     }
-    const int k = ordered ? q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(q0 + jmin));
+    const int k = ordered ? pend.q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(pend.q0 + jmin));
     const double2 e = __ldcg(reinterpret_cast<const double2 *>(hb + jmin));
     const double h = e.x, nw = e.y;
+    if (!pend.cta) __syncthreads(); // warp-granular round: the other warps may still be reading r
     if (c.bid == 0 && tid == 0) {
       __stcg(a.beta + k, nw);
       if (!a.inlist[k]) { // setindex! appends on the first non-zero store
@@ -352,10 +554,22 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     apply_step(c, a.X + (long long)k * a.ldx, h);
     maxH = fmax(maxH, fabs(h));
     accepted += 1;
-    q0 += (int)jmin + 1;
-    W = min(c.CH, c.G);
+    q0 = pend.q0 + (int)jmin + 1;
+    Wnext = min(c.CH, c.G);
+    streak = 0;
+    have_pend = false;
+    mP = 0; // a non-member moved: the rest of the plan is void
+    if (have_spec) { // the discarded round still has its barrier (nothing is read from it)
+      round_arrive_cta(c);
+      round_wait_cta(c);
+      if (c.bid == 0 && tid == 0) {
+        __stcg(words + ((spec.slot + 3) & 3), 0xffffffffu);
+        __stcg(nonapp_flags + ((spec.slot + 3) & 3), 0);
+      }
+    }
     pf[3] += clock64() - td;
   }
+  __syncthreads(); // warps of a warp-granular round leave together
   return maxH;
 }
 
@@ -501,6 +715,7 @@ __device__ void active_phase(NCtx &c, double lam, long long maxPasses, unsigned 
 // finally r -= X_A (beta - beta_at_entry) is applied once.  Same iterates as the reference up to
 // rounding (d maintained incrementally instead of re-reduced); same visit order and list semantics.
 constexpr int NV_GCAP = NV_GCAP_; // largest active set handled this way (G scratch = 32 MB)
+constexpr int NV_PLAN_MAX = 512;  // largest list whose steps are planned ahead of a full pass (member_plan)
 
 __device__ __forceinline__ void nbar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
 
@@ -641,6 +856,69 @@ struct SqrtPolicy { // :259-283 with s, ||r+||^2 from d, ||r||^2, a
   }
   static __device__ __forceinline__ double apply(double d, double Gv, double h) { return __dsub_rn(d, __dmul_rn(Gv, h)); }
 };
+
+// CTA 0, before a full pass: the steps the m members will take when the pass reaches them, by ONE chain pass over the
+// active Gram G = X_A'[W]X_A and d = X_A'(w.r) (just formed by the grid) in the VISIT order of the full pass, on the
+// assumption that no non-member moves (full_pass drops the rest of the plan when one does).  Plan -> global memory.
+__device__ void member_plan(NCtx &c, double lam, unsigned long long pass_counter, int m, const double *G, const double *d0) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x;
+  const bool ordered = a.randomize == 0;
+  const PermKey pk = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+  const NPlan PL = plan_arrays(a);
+  int *vis = c.e_coord; // visit position by list index (temporary)
+  for (int i = tid; i < m; i += NV_T) {
+    const int k = a.act[i];
+    vis[i] = ordered ? k : (int)cd_perm_inv(pk, (uint32_t)k);
+  }
+  __syncthreads();
+  for (int i = tid; i < m; i += NV_T) {
+    const int my = vis[i];
+    int t = 0;
+    for (int j = 0; j < m; ++j) t += vis[j] < my;
+    c.e_row[t] = i; // t-th visited member = list entry i = row i of G
+    PL.pos[t] = my;
+  }
+  __syncthreads();
+  for (int t = tid; t < m; t += NV_T) {
+    const int i = c.e_row[t];
+    c.e_be[t] = a.actval[i];
+    c.e_g[t] = __ldcg(d0 + i);
+  }
+  __syncthreads();
+  for (int t = tid; t < m; t += NV_T) {
+    const int k = a.act[c.e_row[t]];
+    c.e_coord[t] = k;
+    PL.k[t] = k;
+  }
+  __syncthreads();
+  chain::State S;
+  S.m = m;
+  S.row = c.e_row;
+  S.coord = c.e_coord;
+  S.g = c.e_g;
+  S.be = c.e_be;
+  S.ord = c.e_ord;
+  S.pos = c.e_pos;
+  S.stage = c.e_stage;
+  S.sh = &sm->ch;
+  S.G = G;
+  S.ldg = m;
+  S.prof = nullptr;
+  S.hout = PL.h;
+  if (a.kind == CDGPU_LOSS_SQRT) {
+    const SqrtPolicy P{a.colsq, a.omega, lam};
+    (void)chain::run<NV_T>(S, P, c.rr, 1, pass_counter, true, a.seed, a.optTol, nullptr);
+  } else {
+    const LsPolicy P{a.colsq, a.omega, lam, (double)a.n};
+    (void)chain::run<NV_T>(S, P, 0.0, 1, pass_counter, true, a.seed, a.optTol, nullptr);
+  }
+  __syncthreads();
+  for (int t = tid; t < m; t += NV_T) PL.nw[t] = c.e_be[t];
+  __threadfence();
+  __syncthreads();
+}
 
 // CTA 0: the active-set passes as the blocked warp-level chain over (d, beta) of the m0 stored entries
 __device__ void gram_engine(NCtx &c, double lam, long long maxPasses, unsigned long long pass_counter, int m0,
@@ -814,6 +1092,8 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   }
   if (tid == 0) c.sm->nact = *a.nact;
   c.bar_target = 0;
+  c.rnd = 0;
+  if (tid == 0) c.sm->warr = 0;
   if (c.bid == 0 && tid == 0) __stcg(reinterpret_cast<unsigned *>(a.flag + 7), 0u);
   __syncthreads();
   grid.sync(); // the round-barrier counter is zero before anyone arrives
@@ -822,8 +1102,8 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (a.prof && c.bid == 0 && tid < 8) a.prof[16 + tid] = 0;
   const long long t_start = clock64();
-  int rp = 0, round3 = 0;
   int nact_hint = *a.nact; // every CTA's view of the list length (refreshed whenever CTA 0 publishes it)
+  bool hint_stale = false; // a full pass has run since the last refresh
   unsigned long long pass_counter = 0;
   DevStats st;
   st.passes = st.full_passes = st.visits = st.accepted = 0;
@@ -854,7 +1134,34 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           st.full_passes += 1;
           st.visits += a.p;
           const int m_old = c.sm->nact; // CTA 0
-          const double maxH = full_pass(c, lam, pass_counter, rp, round3, st.accepted, pf, nact_hint);
+          int mP = 0;
+          if (a.plan && a.gram && c.gcap > 0) {
+            const long long tp0 = clock64();
+            if (hint_stale) { // the list may have changed in the full pass that ended the previous solve
+              fast_grid_sync(c);
+              nact_hint = __ldcg(&bc->nact);
+              hint_stale = false;
+            }
+            if (nact_hint >= 1 && nact_hint <= min(c.gcap, NV_PLAN_MAX)) {
+              double *Gs = a.gram, *ds = a.gram + (long long)NV_GCAP * NV_GCAP;
+              build_active_gram(c, nact_hint, Gs, ds);
+              fast_grid_sync(c);
+              if (c.bid == 0) member_plan(c, lam, pass_counter, nact_hint, Gs, ds);
+              fast_grid_sync(c);
+              mP = nact_hint;
+              const NPlan PL = plan_arrays(a);
+              for (int t = tid; t < mP; t += NV_T) {
+                c.e_coord[t] = __ldcg(PL.k + t);
+                c.e_row[t] = __ldcg(PL.pos + t);
+                c.e_g[t] = __ldcg(PL.h + t);
+                c.e_be[t] = __ldcg(PL.nw + t);
+              }
+              __syncthreads();
+            }
+            pf[8] += clock64() - tp0;
+          }
+          const double maxH = full_pass(c, lam, pass_counter, st.accepted, pf, nact_hint, mP);
+          hint_stale = true;
           const long long t1 = clock64();
           if (c.bid == 0) {
             list_update_full(c, m_old, pass_counter);
@@ -876,6 +1183,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           fast_grid_sync(c); // CTA 0 has published the list length
           const int m_act = __ldcg(&bc->nact);
           nact_hint = m_act;
+          hint_stale = false;
           if (m_act >= 1 && m_act <= c.gcap && a.gram) {
             double *Gs = a.gram, *ds = a.gram + (long long)NV_GCAP * NV_GCAP;
             build_active_gram(c, m_act, Gs, ds);
@@ -908,6 +1216,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           st.maxH = __ldcg(&bc->maxH);
           conv = __ldcg(&bc->conv) != 0;
           nact_hint = __ldcg(&bc->nact);
+          hint_stale = false;
           fast_grid_sync(c); // bc may be rewritten only after everyone has read it
         }
       }
@@ -927,6 +1236,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
     fast_grid_sync(c);
     const int nnz = __ldcg(&bc->nact);
     nact_hint = nnz;
+    hint_stale = false;
     if (!a.accumulate) {
       if (a.colptr && out_off + nnz > a.capacity) status = 1;
       if (c.bid == 0 && status == 0) {
@@ -1134,9 +1444,9 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
     long long v = atoll(env);
     if (v >= 1) CH = min(v, (long long)a.p);
   }
-  // hbuf + broadcast block live behind the 8p+8n scratch doubles: carve from the tail of iscr/scr
-  // scratch doubles: [0,8) misc | hbuf 2*CH entries of 32 B <= 8p | bc 16 | compaction staging p
-  HEntry *hbuf = reinterpret_cast<HEntry *>(a.scr + 8);
+  // scratch doubles: [0,8) misc | (8p free) | bc 16 | compaction staging p | ... | tail: the 4 result buffers of the
+  // full-pass rounds, 4 * CH entries of 32 B <= 16p doubles (handle_common_alloc)
+  HEntry *hbuf = reinterpret_cast<HEntry *>(a.scr + cd_scr_tail((size_t)a.p, (size_t)a.n));
   NBcast *bc = reinterpret_cast<NBcast *>(a.scr + 8 + 8 * (long long)a.p);
   int ch = (int)CH;
   void *args[] = {(void *)&a, (void *)&ch, (void *)&hbuf, (void *)&bc, (void *)&gcap};
