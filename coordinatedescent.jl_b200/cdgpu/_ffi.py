@@ -129,6 +129,7 @@ _SIGS_GPU_ONLY = {
     "gram_create_lazy_dev": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                        C.c_int]),
     "lazy_stats": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_int64_p, c_double_p]),
+    "lazy_form_columns": (C.c_int, [C.c_void_p, c_int64_p]),
     "sweep_ms": (C.c_int, [C.c_void_p, c_double_p]),
     "synth_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int]),
     "gram_create_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,

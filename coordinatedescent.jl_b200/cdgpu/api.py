@@ -302,7 +302,10 @@ class CDQuadraticLoss(_Loss):
     def lazy_stats(self):
         cols, nb, npause, ms = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
         self.lib.check(self.lib.lazy_stats(self._h, C.byref(cols), C.byref(nb), C.byref(npause), C.byref(ms)))
-        return {"columns": cols.value, "batches": nb.value, "pauses": npause.value, "form_ms": ms.value}
+        fc = C.c_int64()
+        self.lib.check(self.lib.lazy_form_columns(self._h, C.byref(fc)))
+        return {"columns": cols.value, "batches": nb.value, "pauses": npause.value, "form_ms": ms.value,
+                "form_columns": fc.value}
 
     def stdX(self) -> np.ndarray:
         """sqrt(diag(A)) == _stdX!(X) when A = X'X/n (utils.jl:127-138)."""

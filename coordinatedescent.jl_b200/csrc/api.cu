@@ -814,6 +814,7 @@ static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const do
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, h->lz_ev0, h->lz_ev1));
   h->lz_form_ms += ms;
+  h->lz_form_cols += (long long)cols.size();
   return CDGPU_OK;
 }
 
@@ -1013,6 +1014,12 @@ API int cdgpu_lazy_stats(cdgpu_handle h, int64_t *columns, int64_t *batches, int
   if (batches) *batches = h->lz_batches;
   if (pauses) *pauses = h->lz_pauses;
   if (form_ms) *form_ms = h->lz_form_ms;
+  return CDGPU_OK;
+}
+
+API int cdgpu_lazy_form_columns(cdgpu_handle h, int64_t *columns) {
+  if (!h || !columns) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  *columns = h->lz_form_cols;
   return CDGPU_OK;
 }
 
@@ -1234,6 +1241,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
       CD_TRY(lazy_spec_commit(h)); // left in flight by the previous solve
       h->lz_batches = h->lz_pauses = 0;
       h->lz_form_ms = 0.0;
+      h->lz_form_cols = 0;
       int m0 = 0;
       CUDA_TRY(cudaMemcpyAsync(&m0, h->dnact, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream));

@@ -175,7 +175,9 @@ __device__ Result run(State &S, const Policy &P, double rr, long long maxPasses,
         const bool valid = lane < cnt;
         const int e = valid ? S.ord[32 * b + lane] : 0;
         double gj = valid ? S.g[e] : 0.0, bej = valid ? S.be[e] : 0.0;
-        const double c0 = buf[2048 + lane], c1 = buf[2048 + 32 + lane], c2 = buf[2048 + 64 + lane];
+        // lanes past the end of the list step on benign constants (their results are never used; garbage could send
+        // every step of the warp through a policy's slow path)
+        const double c0 = valid ? buf[2048 + lane] : 1.0, c1 = valid ? buf[2048 + 32 + lane] : 1.0, c2 = valid ? buf[2048 + 64 + lane] : 1.0;
         if (b > 0) { // steps of the previous block, in order
           const double *hp = sh->hb[(b - 1) & 1], *Pb = buf + 1024;
 #pragma unroll 1
@@ -411,7 +413,9 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
         const bool valid = lane < cnt;
         const int e = valid ? S.ord[32 * b + lane] : 0;
         double gj = valid ? __ldcg(X.gG + e) : 0.0, bej = valid ? S.be[e] : 0.0;
-        const double c0 = buf[2048 + lane], c1 = buf[2048 + 32 + lane], c2 = buf[2048 + 64 + lane];
+        // lanes past the end of the list step on benign constants (their results are never used; garbage could send
+        // every step of the warp through a policy's slow path)
+        const double c0 = valid ? buf[2048 + lane] : 1.0, c1 = valid ? buf[2048 + 32 + lane] : 1.0, c2 = valid ? buf[2048 + 64 + lane] : 1.0;
         if (b > 0) { // steps of the previous block, in order
           const double *hp = sh->hb[(b - 1) & 1], *Pb = buf + 1024;
 #pragma unroll 8

@@ -286,6 +286,7 @@ struct cdgpu_handle_s {
   int *hslot = nullptr;             // host mirror of dslot
   cudaEvent_t lz_ev0 = nullptr, lz_ev1 = nullptr;
   int lz_batches = 0, lz_pauses = 0; // statistics of the last solve
+  long long lz_form_cols = 0;        // columns formed by the blocking (timed) batches of the last solve
   double lz_form_ms = 0.0;           // device time spent forming columns during the last solve
   double sweep_ms = 0.0;             // device time of the covariance sweep-kernel launches of the last solve
   bool sweep_pending = false;

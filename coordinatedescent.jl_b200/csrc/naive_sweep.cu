@@ -819,12 +819,22 @@ struct LsPolicy { // cd_differentiable_function.jl:101-104 / :184-187
   double lam, nd;
   __device__ __forceinline__ void load_consts(int k, double &c0, double &c1, double &c2) const {
     c0 = __ldg(colsq + k);
-    c1 = 0.0;
+    c1 = 1.0 / c0;
     c2 = __dmul_rn(__dmul_rn(nd / c0, lam), omega ? __ldg(omega + k) : 1.0);
   }
-  __device__ __forceinline__ void step(double d, double be, double aa, double, double th, double, double &nw, double &h,
+  // d / aa with the reciprocal known: one Newton correction of the product gives the correctly rounded quotient (the
+  // sequence a division expands to, minus the reciprocal: ~25 instead of ~120 cycles on the dependent chain); operands
+  // outside its safe range (tiny / huge quotients, non-finite values, a zero column) take the plain division
+  static __device__ __forceinline__ double quot(double d, double aa, double inv) {
+    const double q0 = d * inv;
+    const double e = fma(-q0, aa, d);
+    const double q1 = fma(e, inv, q0);
+    const double aq = fabs(q1);
+    return (aq < 1e280 && (aq > 1e-280 || d == 0.0)) ? q1 : d / aa;
+  }
+  __device__ __forceinline__ void step(double d, double be, double aa, double inv, double th, double, double &nw, double &h,
                                        double &dr) const {
-    const double v = __dadd_rn(be, d / aa);
+    const double v = __dadd_rn(be, quot(d, aa, inv));
     nw = cd_shrink(v, th);
     h = nw - be;
     dr = 0.0;

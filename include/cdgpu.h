@@ -153,6 +153,9 @@ int cdgpu_gram_create_lazy_dev(cdgpu_handle *h, const double *dX, int64_t n, int
 /* what the last solve on a lazy handle formed: columns cached so far, batches formed and kernel pauses during the last
  * solve, device ms spent forming columns during the last solve (all 0 for other handles) */
 int cdgpu_lazy_stats(cdgpu_handle h, int64_t *columns, int64_t *batches, int64_t *pauses, double *form_ms);
+/* columns formed by the BLOCKING batches of the last solve, i.e. the ones form_ms of cdgpu_lazy_stats times (batches
+ * formed in the background, while the sweep kernel runs, are not timed) */
+int cdgpu_lazy_form_columns(cdgpu_handle h, int64_t *columns);
 /* device ms (CUDA events) spent inside the covariance-form sweep kernel during the last solve / path on a QUAD handle
  * (all its launches; excludes forming columns on a lazy handle) */
 int cdgpu_sweep_ms(cdgpu_handle h, double *ms);
