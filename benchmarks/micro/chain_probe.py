@@ -19,9 +19,12 @@ X = rng.standard_normal((p, n)).T
 beta = rng.standard_normal(s) * (1.0 + rng.random(s))
 y = X[:, :s] @ beta + rng.standard_normal(n)
 lam = float(sys.argv[1]) if len(sys.argv) > 1 else 0.01
-be = cdgpu.default()
+# CDGPU_PROBE_LIB=coordinatedescent.jl_b200/csrc/prof/libcdgpu.so: the diagnostics build (make -C csrc prof) with the
+# chain engines' own cycle counters
+be = cdgpu.Backend(cdgpu.Lib(os.path.abspath(os.environ["CDGPU_PROBE_LIB"]), "cdgpu")) if os.environ.get("CDGPU_PROBE_LIB") else cdgpu.default()
+forms = os.environ.get("CDGPU_PROBE_FORMS", "cov,naive").split(",")
 opt = CDOptions(maxIter=2000, optTol=1e-7, randomize=False)
-for form in ("cov", "naive"):
+for form in forms:
     f = be.CDQuadraticLoss_from_data(X, y) if form == "cov" else be.CDLeastSquaresLoss(y, X)
     for rep in range(2):
         x = SparseIterate(p)

@@ -176,8 +176,8 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   };
   const size_t o_beta = take(p * sizeof(double)), o_act = take(p * sizeof(int)), o_actval = take(p * sizeof(double)),
                o_nact = take(sizeof(int)), o_inlist = take(p), o_omega = take(p * sizeof(double)),
-               o_scr = take((cd_scr_tail(p, (size_t)h->n) + 16 * p + 8) * sizeof(double)),
-               o_iscr = take((10 * p + 64) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(16 * sizeof(int));
+               o_scr = take((cd_scr_tail(p, (size_t)h->n) + 16 * p + 8 + 32) * sizeof(double)),
+               o_iscr = take((10 * p + 64 + 3 * 512 + 8) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(16 * sizeof(int));
   CD_TRY(dalloc(&h->dcommon, off));
   unsigned char *base = h->dcommon;
   h->dbeta = (double *)(base + o_beta);
@@ -1345,8 +1345,11 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.capacity = rc.capacity;
     a.flag = h->dflag;
     a.stats = h->dstats;
-    if (!h->dgram && !getenv("CDGPU_NAIVE_NO_GRAM_ENGINE")) CD_TRY(dalloc(&h->dgram, (size_t)2048 * 2048 + 2048));
+    const size_t gcap = cd_gram_cap((size_t)h->p);
+    if (!h->dgram && !getenv("CDGPU_NAIVE_NO_GRAM_ENGINE")) CD_TRY(dalloc(&h->dgram, gcap * gcap + gcap));
     a.gram = getenv("CDGPU_NAIVE_NO_GRAM_ENGINE") ? nullptr : h->dgram;
+    a.gram_cap = (int)gcap;
+    if (const char *env = getenv("CDGPU_NAIVE_GCAP")) a.gram_cap = std::max(256, std::min((int)gcap, atoi(env))); // diagnostics
     a.multi_ok = 384; // smallest active set handed to the 16-CTA team engine (below: chain-bound on one CTA anyway)
     if (const char *env = getenv("CDGPU_MULTI_MIN")) a.multi_ok = std::max(64, atoi(env));
     if (const char *env = getenv("CDGPU_NAIVE_MULTI")) a.multi_ok = atoi(env) != 0 ? a.multi_ok : 0;
@@ -1359,7 +1362,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.outerTol = rc.outerTol;
     a.sigma0 = rc.sigma0;
     const bool prof = getenv("CDGPU_PROFILE") != nullptr;
-    a.prof = prof ? reinterpret_cast<long long *>(h->dscr + 11 * (size_t)h->p) : nullptr;
+    a.prof = prof ? reinterpret_cast<long long *>(h->dscr + cd_scr_tail((size_t)h->p, (size_t)h->n) + 16 * (size_t)h->p + 8) : nullptr; // 32 doubles behind the round buffers
     CD_TRY(launch_naive_init(h, a));
     CD_TRY(launch_naive_path(h, a));
     if (prof) {
@@ -1368,12 +1371,14 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
       CUDA_TRY(cudaStreamSynchronize(h->stream));
       fprintf(stderr,
               "[cdgpu profile] naive path (CTA 0): total %.3f Mcyc | full-pass rounds %lld: column dots %.3f, grid.sync "
-              "%.3f, scan %.3f, apply %.3f | list update %.3f | active phase %.3f | member plan %.3f\n",
-              pf[6] * 1e-6, pf[7], pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6, pf[8] * 1e-6);
+              "%.3f, scan %.3f, apply %.3f | list update %.3f | active phase %.3f (forming the active Gram %.3f) | member plan %.3f\n",
+              pf[6] * 1e-6, pf[7], pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6, pf[9] * 1e-6,
+              pf[8] * 1e-6);
       fprintf(stderr,
               "[cdgpu profile]   chain engine: warp0 panel %.3f chain %.3f barrier %.3f pass-ends %.3f | workers stage %.3f apply "
-              "%.3f barrier %.3f Mcyc\n",
-              pf[16] * 1e-6, pf[17] * 1e-6, pf[18] * 1e-6, pf[19] * 1e-6, pf[20] * 1e-6, pf[21] * 1e-6, pf[22] * 1e-6);
+              "%.3f barrier %.3f | team engine (counters with -DCDGPU_CHAIN_PROF): apply on CTA 1 %.3f; whole call %.3f, of which publish %.3f Mcyc\n",
+              pf[16] * 1e-6, pf[17] * 1e-6, pf[18] * 1e-6, pf[19] * 1e-6, pf[20] * 1e-6, pf[21] * 1e-6, pf[22] * 1e-6, pf[23] * 1e-6,
+              pf[10] * 1e-6, pf[11] * 1e-6);
     }
   }
   return CDGPU_OK;
@@ -1801,7 +1806,10 @@ API int cdgpu_refit(cdgpu_handle h, const int64_t *support, int64_t ns, double *
     if (support[i] < 1 || support[i] > h->p) return cdgpu_set_error(CDGPU_EDIM, "BoundsError: support index out of range");
     s0[(size_t)i] = (int)(support[i] - 1);
   }
-  if (!h->dgram) CD_TRY(dalloc(&h->dgram, (size_t)2048 * 2048 + 2048));
+  if (!h->dgram) {
+    const size_t gcap = cd_gram_cap((size_t)h->p);
+    CD_TRY(dalloc(&h->dgram, gcap * gcap + gcap));
+  }
   int *dS = h->discr; // 8p ints of scratch
   CUDA_TRY(cudaMemcpyAsync(dS, s0.data(), (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream)); // s0 is a host temporary

@@ -390,6 +390,23 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
   int m = S.m;
   Result R{0, 0, 0, 0.0, 0, m};
   Shared *sh = S.sh;
+  // optional cycle counters (S.prof): thread 0 of CTA 0 [0..3] = panel, chain, team barrier, pass ends; thread 32 of
+  // CTA 0 [4..6] = staging, apply, team barrier; thread 0 of CTA 1 [7] = apply
+  // (compiled in with -DCDGPU_CHAIN_PROF only: the counters cost the naive kernel registers it does not have)
+#ifdef CDGPU_CHAIN_PROF
+  long long pc[4] = {0, 0, 0, 0};
+  const bool prof = S.prof != nullptr && ((chainCTA && (tid == 0 || tid == 32)) || (X.me == 1 && tid == 0));
+  long long tp = prof ? clock64() : 0;
+  auto lap = [&](int slot) {
+    if (prof) {
+      const long long t = clock64();
+      pc[slot] += t - tp;
+      tp = t;
+    }
+  };
+#else
+  auto lap = [](int) {};
+#endif
   for (long long pass = 0; pass < maxPasses; ++pass) {
     const int m_pass = m;
     const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), seed, pass_counter + pass);
@@ -406,6 +423,7 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
     }
     double pmax = 0.0;
     long long acc = 0;
+    lap(3);
     for (int b = 0; b < nb; ++b) {
       if (chainCTA && warp == 0) {
         double *buf = S.stage + (b & 1) * BUF_DOUBLES;
@@ -424,6 +442,7 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
             if (h != 0.0) gj = Policy::apply(gj, Pb[i * 32 + lane], h);
           }
         }
+        lap(0);
         double myh = 0.0;
         double drow = buf[lane];
         for (int i = 0; i < cnt; ++i) {
@@ -450,11 +469,15 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
         sh->hb[b & 1][lane] = hv;
         __stcg(X.hG + (b & 1) * 32 + lane, hv);
         pmax = fmax(pmax, fabs(myh));
+        lap(1);
       } else {
         if (chainCTA && b + 1 < nb) stage_block(S, P, m, b + 1, S.stage + ((b + 1) & 1) * BUF_DOUBLES, tid - 32, T - 32);
+        lap(0);
         if (b >= 1) apply_owned<T, Policy>(S, X, m, b - 1, X.hG + ((b - 1) & 1) * 32, b - 1, b, chainCTA ? 1 : 0);
+        lap(1);
       }
       sync();
+      lap(2);
     }
     // drain: the last block's steps reach the rest of the list (CTA 0's warp 0 joins in)
     if (nb >= 2) apply_owned<T, Policy>(S, X, m, nb - 1, X.hG + ((nb - 1) & 1) * 32, nb - 1, -1, 0);
@@ -537,6 +560,17 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
       break;
     }
   }
+  lap(3);
+#ifdef CDGPU_CHAIN_PROF
+  if (prof) {
+    if (X.me == 1) {
+      S.prof[7] += pc[1];
+    } else {
+      const int o = tid == 0 ? 0 : 4;
+      for (int i = 0; i < (tid == 0 ? 4 : 3); ++i) S.prof[o + i] += pc[i];
+    }
+  }
+#endif
   if (chainCTA) {
     __syncthreads();
     if (tid == 0) sh->hb[0][0] = (double)R.accepted;

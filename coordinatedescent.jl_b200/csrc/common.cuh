@@ -414,13 +414,16 @@ struct NaiveArgs {
   long long outerMaxIter;
   double outerTol, sigma0;
   long long *prof; // optional [10]: SM cycles per phase on CTA 0 (CDGPU_PROFILE=1)
-  double *gram;    // scratch for the covariance-form active engine: 2048*2048 + 2048 doubles (or null)
+  double *gram;    // scratch for the covariance-form active engine: gram_cap^2 + gram_cap doubles (or null)
+  int gram_cap;    // largest active set the scratch holds (cd_gram_cap(p))
   int multi_ok;    // grid-distributed chain engine for large active sets (CDGPU_NAIVE_MULTI=0 disables)
   int pipeline;    // split-phase rounds of the full pass (CDGPU_NAIVE_PIPELINE=0 disables)
   int plan;        // members' steps of a full pass planned by one chain pass (CDGPU_NAIVE_PLAN=0 disables)
 };
 // offset (doubles, even) of the tail of a handle's scratch: 16p doubles for the result buffers of the full-pass rounds
-inline size_t cd_scr_tail(size_t p, size_t n) { return (15 * p + 8 * n + 64 + 4 * 2048 + 64 + 1) & ~(size_t)1; }
+constexpr int CD_GCAP = 4096; // largest active set of a naive handle that runs on the chain engines (Gram scratch 134 MB)
+inline size_t cd_gram_cap(size_t p) { return p < 2048 ? 2048 : (p < (size_t)CD_GCAP ? p : (size_t)CD_GCAP); }
+inline size_t cd_scr_tail(size_t p, size_t n) { return (15 * p + 8 * n + 64 + 4 * (size_t)CD_GCAP + 64 + 1) & ~(size_t)1; }
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
 bool naive_fits(long long n, bool has_w);
 int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a); // r = y - X beta, beta dense, inlist

@@ -28,7 +28,7 @@ namespace {
 
 constexpr int NV_T = 512;
 constexpr int NV_W = NV_T / 32;
-constexpr int NV_GCAP_ = 2048; // == NV_GCAP below
+constexpr int NV_GCAP_ = CD_GCAP; // == NV_GCAP below: stride of the per-entry scratch arrays in global memory
 
 struct __align__(16) HEntry {
   double h, nw;
@@ -297,13 +297,14 @@ __device__ void apply_planned(NCtx &c, int t0, int t1, double &maxH, long long &
 
 // plan arrays in global memory (CTA 0 writes, everybody copies them to shared memory)
 struct NPlan {
-  int *k, *pos;
+  int *k, *pos, *row; // coordinate, visit position, list index (= row of the active Gram) of the t-th visited member
   double *h, *nw;
 };
 __device__ __forceinline__ NPlan plan_arrays(const NaiveArgs &a) {
   NPlan P;
-  P.k = a.iscr + 8 * (long long)a.p;
-  P.pos = a.iscr + 9 * (long long)a.p;
+  P.k = a.iscr + 10 * (long long)a.p + 64; // 3 x NV_PLAN_MAX ints behind the sweep's scratch ints (handle_common_alloc)
+  P.pos = P.k + 512;
+  P.row = P.pos + 512;
   P.h = a.scr + 8 + 9 * (long long)a.p + 32 + 2 * NV_GCAP_;
   P.nw = P.h + NV_GCAP_;
   return P;
@@ -369,6 +370,12 @@ __device__ __forceinline__ void round_wait_cta(NCtx &c) {
   }
   __syncthreads();
 }
+
+constexpr int NV_PLAN_MAX = 512;  // largest list whose steps are planned ahead of a full pass (member_plan)
+constexpr int NV_REPLAN_MIN = 8;  // a non-member moved: the remaining members are planned again when at least this many are left
+constexpr int NV_REPLAN_MAX = 8;  // ... at most this often per pass (each costs two grid barriers and a chain over the rest)
+static_assert(NV_PLAN_MAX <= NV_T, "replan_members handles one entry per thread");
+__device__ void replan_members(NCtx &c, double lam, int t0, int t1);
 
 struct NWin {
   int q0, qlen, W, slot;
@@ -474,7 +481,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
   const bool pipeline = a.pipeline != 0;
   int Wnext = (nact_hint > 0 && mP == 0) ? min(c.CH, c.G) : Wwarp;
   int q0 = 0, streak = mP > 0 ? 2 : 0; // with a plan the sweep is expected to be clean: pipelined from the first window
-  int pi = 0;                          // next planned member
+  int pi = 0, replans = 0;             // next planned member; plans redone in this pass
   bool have_pend = false;
   NWin pend = {}, spec = {};
   for (;;) {
@@ -558,7 +565,6 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     Wnext = min(c.CH, c.G);
     streak = 0;
     have_pend = false;
-    mP = 0; // a non-member moved: the rest of the plan is void
     if (have_spec) { // the discarded round still has its barrier (nothing is read from it)
       round_arrive_cta(c);
       round_wait_cta(c);
@@ -568,6 +574,20 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
       }
     }
     pf[3] += clock64() - td;
+    // a non-member moved: the steps planned for the members still to come are void.  With enough of them left they are
+    // planned again against the new r (fresh d = X_k'(w.r), the same active Gram); otherwise they become ordinary columns.
+    if (mP > 0) {
+      const long long tr0 = clock64();
+      if (mP - pi >= NV_REPLAN_MIN && replans < NV_REPLAN_MAX) {
+        replan_members(c, lam, pi, mP);
+        replans += 1;
+        Wnext = Wwarp;
+        streak = 2;
+      } else {
+        mP = 0;
+      }
+      pf[8] += clock64() - tr0;
+    }
   }
   __syncthreads(); // warps of a warp-granular round leave together
   return maxH;
@@ -714,8 +734,7 @@ __device__ void active_phase(NCtx &c, double lam, long long maxPasses, unsigned 
 // step and the G column gathers prefetched two steps ahead (no O(n) work per step at all), and
 // finally r -= X_A (beta - beta_at_entry) is applied once.  Same iterates as the reference up to
 // rounding (d maintained incrementally instead of re-reduced); same visit order and list semantics.
-constexpr int NV_GCAP = NV_GCAP_; // largest active set handled this way (G scratch = 32 MB)
-constexpr int NV_PLAN_MAX = 512;  // largest list whose steps are planned ahead of a full pass (member_plan)
+constexpr int NV_GCAP = NV_GCAP_; // largest active set handled this way (G scratch = gram_cap^2 doubles: 134 MB at 4096)
 
 __device__ __forceinline__ void nbar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
 
@@ -889,6 +908,7 @@ __device__ void member_plan(NCtx &c, double lam, unsigned long long pass_counter
     for (int j = 0; j < m; ++j) t += vis[j] < my;
     c.e_row[t] = i; // t-th visited member = list entry i = row i of G
     PL.pos[t] = my;
+    PL.row[t] = i;
   }
   __syncthreads();
   for (int t = tid; t < m; t += NV_T) {
@@ -926,7 +946,82 @@ __device__ void member_plan(NCtx &c, double lam, unsigned long long pass_counter
   }
   __syncthreads();
   for (int t = tid; t < m; t += NV_T) PL.nw[t] = c.e_be[t];
+  if (tid == 0) PL.row[512] = m; // leading dimension of G, for replan_members
   __threadfence();
+  __syncthreads();
+}
+
+// Every CTA, in the middle of a planned full pass, after a non-member has moved: the steps of the planned members
+// [t0, t1) still to come are computed again.  d = X_k'(w.r) fresh against the current r (one warp per member, all CTAs),
+// then CTA 0 runs the chain over them in visit order on the active Gram formed for this pass (the new coordinate has
+// been visited already and takes no further part), and everybody reloads that part of the plan.
+__device__ void replan_members(NCtx &c, double lam, int t0, int t1) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const NPlan PL = plan_arrays(a);
+  const double *G = a.gram;
+  double *ds = a.gram + (long long)a.gram_cap * a.gram_cap;
+  const int mlist = (int)__ldcg(reinterpret_cast<const int *>(PL.row + 512)); // list length the Gram was formed for
+  {
+    const int gw = c.bid * NV_W + (tid >> 5), nw = c.G * NV_W;
+    for (int t = t0 + gw; t < t1; t += nw) {
+      const double v = warp_col_dot(c, a.X + (long long)c.e_coord[t] * a.ldx);
+      if (lane == 0) __stcg(ds + t, v);
+    }
+  }
+  fast_grid_sync(c);
+  if (c.bid == 0) {
+    const int m = t1 - t0; // <= NV_PLAN_MAX <= NV_T: one entry per thread
+    int k = 0, row = 0;
+    double be = 0.0, g = 0.0;
+    if (tid < m) {
+      k = c.e_coord[t0 + tid];
+      row = __ldcg(PL.row + t0 + tid);
+      be = a.actval[row]; // the members still to come have not changed in this pass
+      g = __ldcg(ds + t0 + tid);
+    }
+    __syncthreads();
+    if (tid < m) {
+      c.e_coord[tid] = k;
+      c.e_row[tid] = row;
+      c.e_be[tid] = be;
+      c.e_g[tid] = g;
+    }
+    __syncthreads();
+    chain::State S;
+    S.m = m;
+    S.row = c.e_row;
+    S.coord = c.e_coord;
+    S.g = c.e_g;
+    S.be = c.e_be;
+    S.ord = c.e_ord;
+    S.pos = c.e_pos;
+    S.stage = c.e_stage;
+    S.sh = &sm->ch;
+    S.G = G;
+    S.ldg = mlist;
+    S.prof = nullptr;
+    S.hout = PL.h + t0;
+    if (a.kind == CDGPU_LOSS_SQRT) {
+      const SqrtPolicy P{a.colsq, a.omega, lam};
+      (void)chain::run<NV_T>(S, P, c.rr, 1, 0, true, a.seed, a.optTol, nullptr);
+    } else {
+      const LsPolicy P{a.colsq, a.omega, lam, (double)a.n};
+      (void)chain::run<NV_T>(S, P, 0.0, 1, 0, true, a.seed, a.optTol, nullptr);
+    }
+    __syncthreads();
+    if (tid < m) PL.nw[t0 + tid] = c.e_be[tid];
+    __threadfence();
+    __syncthreads();
+  }
+  fast_grid_sync(c);
+  for (int t = t0 + tid; t < t1; t += NV_T) {
+    c.e_coord[t] = __ldcg(PL.k + t);
+    c.e_row[t] = __ldcg(PL.pos + t);
+    c.e_g[t] = __ldcg(PL.h + t);
+    c.e_be[t] = __ldcg(PL.nw + t);
+  }
   __syncthreads();
 }
 
@@ -1013,7 +1108,7 @@ __device__ void gram_engine_multi(NCtx &c, double lam, long long maxPasses, unsi
   S.sh = &sm->ch;
   S.G = G;
   S.ldg = m0;
-  S.prof = nullptr;
+  S.prof = a.prof ? a.prof + 16 : nullptr;
   // team = the first W CTAs of the cooperative grid (all co-resident), with its own barrier: one atomic arrive and
   // an acquire-poll on a counter in global memory — a 16-CTA barrier costs a fraction of grid.sync() over 148
   const int W = min(c.G, NV_MULTI_TEAM);
@@ -1043,7 +1138,9 @@ __device__ void gram_engine_multi(NCtx &c, double lam, long long maxPasses, unsi
     r = chain::run_multi<NV_T>(S, X, P, sync, 0.0, maxPasses, pass_counter, ordered, a.seed, a.optTol, a.inlist);
   }
   if (c.bid != 0) return;
+  const long long tpub = clock64();
   gram_publish(c, r, m0, act0, scr_b0, scr_dlt);
+  if (a.prof && tid == 0) a.prof[11] += clock64() - tpub;
 }
 
 __device__ double shared_std(NCtx &c) { // Statistics.std(r), corrected, two-pass
@@ -1110,7 +1207,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   c.rr = shared_sumsq(c);
 
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (a.prof && c.bid == 0 && tid < 8) a.prof[16 + tid] = 0;
+  if (a.prof && c.bid == 0 && tid < 14) a.prof[10 + tid] = 0;
   const long long t_start = clock64();
   int nact_hint = *a.nact; // every CTA's view of the list length (refreshed whenever CTA 0 publishes it)
   bool hint_stale = false; // a full pass has run since the last refresh
@@ -1153,7 +1250,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
               hint_stale = false;
             }
             if (nact_hint >= 1 && nact_hint <= min(c.gcap, NV_PLAN_MAX)) {
-              double *Gs = a.gram, *ds = a.gram + (long long)NV_GCAP * NV_GCAP;
+              double *Gs = a.gram, *ds = a.gram + (long long)a.gram_cap * a.gram_cap;
               build_active_gram(c, nact_hint, Gs, ds);
               fast_grid_sync(c);
               if (c.bid == 0) member_plan(c, lam, pass_counter, nact_hint, Gs, ds);
@@ -1195,15 +1292,19 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           nact_hint = m_act;
           hint_stale = false;
           if (m_act >= 1 && m_act <= c.gcap && a.gram) {
-            double *Gs = a.gram, *ds = a.gram + (long long)NV_GCAP * NV_GCAP;
+            double *Gs = a.gram, *ds = a.gram + (long long)a.gram_cap * a.gram_cap;
+            const long long tg0 = clock64();
             build_active_gram(c, m_act, Gs, ds);
+            pf[9] += clock64() - tg0;
             if (c.bid == 0 && tid == 0) { // team-barrier counter of gram_engine_multi (behind hG, pmaxG, 2 flags)
               double *hG0 = a.scr + 8 + 9 * (long long)a.p + 32 + 4 * NV_GCAP + 8;
               __stcg(reinterpret_cast<unsigned *>(reinterpret_cast<int *>(hG0 + 72) + 2), 0u);
             }
             fast_grid_sync(c);
+            const long long tg2 = clock64();
             if (a.multi_ok > 0 && m_act >= a.multi_ok) { // a.multi_ok: smallest list length for the team engine
               if (c.bid < NV_MULTI_TEAM) gram_engine_multi(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);
+              if (a.prof && c.bid == 0 && tid == 0) a.prof[10] += clock64() - tg2;
             } else if (c.bid == 0) {
               gram_engine(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);
             }
@@ -1427,7 +1528,7 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
     return gcap ? chain::STAGE_DOUBLES * sizeof(double) + (size_t)gcap * (2 * sizeof(double) + 2 * sizeof(int) + 2 * sizeof(unsigned short))
                 : (size_t)0;
   };
-  int gcap = a.gram ? NV_GCAP : 0;
+  int gcap = a.gram ? a.gram_cap : 0;
   while (gcap >= 256 && rbytes + engine_bytes(gcap) > max_dyn) gcap >>= 1;
   if (gcap < 256) gcap = 0;
   const size_t dyn = rbytes + engine_bytes(gcap);

@@ -196,6 +196,27 @@ def test_front_ends(gpu, ref):
     assert gpu.lasso(X, y, lam).x.nnz == 0
 
 
+@pytest.mark.parametrize("randomize", [False, True])
+def test_naive_path_plans_and_replans_members(gpu, ref, randomize):
+    """LassoPath in the reference's naive form (lasso.jl:229-260): every lambda starts with a full pass over a warm list
+    (members' steps planned by one chain pass, naive_sweep.cu: member_plan) into which new coordinates enter (the rest of
+    the plan is redone: replan_members).  Scattered true support, so members and entering coordinates interleave."""
+    n, p, s = 500, 3000, 40
+    rng = np.random.default_rng(77)
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    supp = rng.choice(p, s, replace=False)
+    y = X[:, supp] @ (rng.standard_normal(s) * 2.0) + 3.0 * rng.standard_normal(n)
+    lmax = np.max(np.abs(X.T @ y / n))
+    lams = list(np.exp(np.linspace(np.log(0.95 * lmax), np.log(0.03 * lmax), 30)))
+    o = CDOptions(randomize=randomize, **TIGHT)
+    pa = gpu.LassoPath(X, y, lams, o, standardizeX=False)
+    pb = ref.LassoPath(X, y, lams, o, standardizeX=False)
+    assert max(b.nnz for b in pb.βpath) >= 100
+    for i in range(len(lams)):
+        assert_parity(pa.βpath[i].toarray(), pb.βpath[i].toarray())
+        assert (pa.stats[i]["passes"], pa.stats[i]["visits"]) == (pb.stats[i]["passes"], pb.stats[i]["visits"]), i
+
+
 @pytest.mark.parametrize("init", ["InitStd", "WarmStart", "Screening"])
 def test_scaled_lasso_parity(gpu, ref, init):
     n, p, s = 600, 400, 15
