@@ -18,6 +18,8 @@ struct Pol { // covariance-form update with unit consts
     c1 = __ldg(ainv + k);
     c2 = __dmul_rn(c1, lam);
   }
+  static constexpr bool FAST_V = true;
+  __device__ __forceinline__ double enter(double g, double be, double c0, double c1) const { return __dsub_rn(be, __dmul_rn(g + c0, c1)); }
   __device__ __forceinline__ void step(double g, double be, double c0, double c1, double c2, double, double &nw, double &h,
                                        double &dr) const {
     const double v = __dsub_rn(be, __dmul_rn(g + c0, c1));

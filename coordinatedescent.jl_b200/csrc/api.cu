@@ -177,7 +177,8 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   const size_t o_beta = take(p * sizeof(double)), o_act = take(p * sizeof(int)), o_actval = take(p * sizeof(double)),
                o_nact = take(sizeof(int)), o_inlist = take(p), o_omega = take(p * sizeof(double)),
                o_scr = take((cd_scr_tail(p, (size_t)h->n) + 16 * p + 8 + 32) * sizeof(double)),
-               o_iscr = take((10 * p + 64 + 3 * 512 + 8) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(16 * sizeof(int));
+               o_iscr = take((10 * p + 64 + 3 * 512 + 8) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(16 * sizeof(int)),
+               o_chain = take(CD_MULTI_SCR_BYTES);
   CD_TRY(dalloc(&h->dcommon, off));
   unsigned char *base = h->dcommon;
   h->dbeta = (double *)(base + o_beta);
@@ -190,6 +191,7 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   h->discr = (int *)(base + o_iscr);
   h->dbscr = base + o_bscr;
   h->dflag = (int *)(base + o_flag);
+  h->dchain = (double *)(base + o_chain);
   CUDA_TRY(cudaMemsetAsync(h->dbeta, 0, p * sizeof(double), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dinlist, 0, p, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dnact, 0, sizeof(int), h->stream));
@@ -1216,6 +1218,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.scr = h->dscr;
     a.iscr = h->discr;
     a.bscr = h->dbscr;
+    a.chain_scr = h->dchain;
     a.lambdas = h->dlam;
     a.nlambda = rc.nlambda;
     a.accumulate = rc.accumulate;
@@ -1331,6 +1334,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.scr = h->dscr;
     a.iscr = h->discr;
     a.bscr = h->dbscr;
+    a.chain_scr = h->dchain;
     a.lambdas = h->dlam;
     a.nlambda = rc.nlambda;
     a.accumulate = rc.accumulate;
@@ -1375,8 +1379,8 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
               pf[6] * 1e-6, pf[7], pf[0] * 1e-6, pf[1] * 1e-6, pf[2] * 1e-6, pf[3] * 1e-6, pf[4] * 1e-6, pf[5] * 1e-6, pf[9] * 1e-6,
               pf[8] * 1e-6);
       fprintf(stderr,
-              "[cdgpu profile]   chain engine: warp0 panel %.3f chain %.3f barrier %.3f pass-ends %.3f | workers stage %.3f apply "
-              "%.3f barrier %.3f | team engine (counters with -DCDGPU_CHAIN_PROF): apply on CTA 1 %.3f; whole call %.3f, of which publish %.3f Mcyc\n",
+              "[cdgpu profile]   chain engine: warp0 panel %.3f chain %.3f barrier %.3f pass-ends %.3f | workers stage %.3f apply (team: "
+              "warp 0 waiting for owners) %.3f barrier %.3f | team engine (counters with -DCDGPU_CHAIN_PROF): apply on CTA 1 %.3f; whole call %.3f, of which publish %.3f Mcyc\n",
               pf[16] * 1e-6, pf[17] * 1e-6, pf[18] * 1e-6, pf[19] * 1e-6, pf[20] * 1e-6, pf[21] * 1e-6, pf[22] * 1e-6, pf[23] * 1e-6,
               pf[10] * 1e-6, pf[11] * 1e-6);
     }

@@ -131,6 +131,87 @@ __device__ __forceinline__ void apply_block(const State &S, int m, int hbk, cons
   }
 }
 
+// The 32 dependent steps of one block on warp 0 (lane j owns entry j of the block; D = the staged 32x32 diagonal block,
+// D[i*32 + j] = G(entry j, entry i)).  Policies with FAST_V (soft-threshold steps: LS / WLS / quadratic) carry, next to
+// the gradient g_j, the argument of the shrinkage v_j = be_j -+ g_j/a_jj itself: it is formed once per block exactly as
+// step() forms it, and a step h on entry i moves it by one fused multiply-add with the pre-scaled row D[j,i]/a_jj, so
+// that the dependent path of a step is FMA -> compare/select -> subtract -> shuffle (~60 cycles) instead of
+// multiply, add, quotient (3 FMAs + range test), add, shrink, subtract, shuffle (~150).  g_j receives the same
+// unfused updates as before, off the dependent path; v_j is re-derived from it at the next block, so the two never
+// drift apart by more than the 32 roundings of a block.
+template <class Policy>
+__device__ __forceinline__ void chain_steps(const Policy &P, const double *buf, int cnt, int lane, double &gj, double &bej,
+                                            double c0, double c1, double c2, double &rr, double &myh, long long &acc) {
+  double drow = buf[lane];
+  if constexpr (Policy::FAST_V) {
+    double v = P.enter(gj, bej, c0, c1);
+    double ds = lane > 0 || cnt != 32 ? __dmul_rn(drow, c1) : 0.0; // (full block: lane 0 is frozen from the start)
+    // nw = shrink(v, c2), h = nw - be with both branches evaluated ahead of the comparisons
+    auto prox = [&](double vv, double &nw, double &hi) {
+      const double up = __dsub_rn(vv, c2), dn = __dadd_rn(vv, c2); // (intrinsics: kept as two adds next to the compares)
+      const double hup = __dsub_rn(up, bej), hdn = __dsub_rn(dn, bej);
+      const bool gt = vv > c2, lt = vv < -c2;
+      nw = gt ? up : (lt ? dn : 0.0);
+      hi = gt ? hup : (lt ? hdn : -bej);
+    };
+    if (cnt == 32) {
+      // full block, straight-line: constant shared-memory offsets and shuffle lanes; lane i's v is frozen from its own
+      // step on (lanes <= i multiply the step by a zero row), so that its step is read off v once more after the loop
+      // instead of being captured by four selects in every step
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const double dnext = buf[((i + 1) & 31) * 32 + lane];
+        double nw, hi;
+        prox(v, nw, hi);
+        const double h = __shfl_sync(0xffffffffu, hi, i);
+        v = fma(-ds, h, v);
+        gj = Policy::apply(gj, drow, h); // h == 0: the product is +-0 and g keeps its value
+        drow = dnext;
+        ds = lane > i + 1 ? __dmul_rn(dnext, c1) : 0.0; // a zero row freezes v (the select is off the dependent path)
+      }
+      double nw;
+      prox(v, nw, myh);
+      bej = nw;
+      acc += __popc(__ballot_sync(0xffffffffu, myh != 0.0));
+    } else {
+      int nacc = 0;
+      for (int i = 0; i < cnt; ++i) {
+        const double dnext = buf[((i + 1) & 31) * 32 + lane];
+        double nw, hi;
+        prox(v, nw, hi);
+        const double h = __shfl_sync(0xffffffffu, hi, i);
+        v = fma(-ds, h, v); // (lane i itself: its v is not read again in this block)
+        if (lane == i) {
+          bej = nw;
+          myh = hi;
+        }
+        gj = Policy::apply(gj, drow, h);
+        nacc += h != 0.0;
+        drow = dnext;
+        ds = __dmul_rn(dnext, c1);
+      }
+      acc += nacc;
+    }
+  } else {
+    for (int i = 0; i < cnt; ++i) {
+      const double dnext = buf[((i + 1) & 31) * 32 + lane];
+      double nw, hi, dr;
+      P.step(gj, bej, c0, c1, c2, rr, nw, hi, dr);
+      const double h = __shfl_sync(0xffffffffu, hi, i);
+      if (lane == i) {
+        bej = nw;
+        myh = hi;
+      }
+      if (h != 0.0) {
+        gj = Policy::apply(gj, drow, h);
+        if (Policy::HAS_RR) rr += __shfl_sync(0xffffffffu, dr, i);
+        acc += 1;
+      }
+      drow = dnext;
+    }
+  }
+}
+
 // Runs consecutive active-set passes until one has max|h| < optTol or maxPasses are used.
 // Block-collective over T threads (T >= 64, multiple of 32); S.m entries are loaded in S.g/be/row/coord.
 template <int T, class Policy>
@@ -195,23 +276,7 @@ __device__ Result run(State &S, const Policy &P, double rr, long long maxPasses,
         }
         lap(0);
         double myh = 0.0;
-        double drow = buf[lane];
-        for (int i = 0; i < (CHAIN_PROBE_BIT(2) ? 0 : cnt); ++i) {
-          const double dnext = buf[((i + 1) & 31) * 32 + lane];
-          double nw, hi, dr;
-          P.step(gj, bej, c0, c1, c2, rr, nw, hi, dr);
-          const double h = __shfl_sync(0xffffffffu, hi, i);
-          if (lane == i) {
-            bej = nw;
-            myh = hi;
-          }
-          if (h != 0.0) {
-            gj = Policy::apply(gj, drow, h);
-            if (Policy::HAS_RR) rr += __shfl_sync(0xffffffffu, dr, i);
-            acc += 1;
-          }
-          drow = dnext;
-        }
+        chain_steps(P, buf, CHAIN_PROBE_BIT(2) ? 0 : cnt, lane, gj, bej, c0, c1, c2, rr, myh, acc);
         if (valid) {
           S.g[e] = gj;
           S.be[e] = bej;
@@ -326,56 +391,70 @@ __device__ Result run(State &S, const Policy &P, double rr, long long maxPasses,
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// The same engine spread over W CTAs (a thread-block cluster, or the cooperative grid), for active sets of many
+// The same engine spread over W >= 2 CTAs (a thread-block cluster, or the cooperative grid), for active sets of many
 // blocks: with ONE CTA the 32 steps of a block reach the other m - 64 entries through a single SM's L2 port
 // (~12 k cycles per block at m = 800, measured), which is what bounds dense active sets.  Here g lives in global
-// memory (L2), CTA 0 keeps the chain (warp 0) and the staging (warps 1..15), and EVERY CTA applies the previous
-// block's steps to the 32-entry groups it owns (group % W); one barrier of the whole team per block hands over g
-// of the next block and h of the finished one.  Same step order per entry as run(): bit-identical iterates.
+// memory (L2).  CTA 0 keeps the chain (warp 0) and the staging (warps 1..15) and nothing else.  The 32-entry groups of
+// the list are dealt to the warps of the other CTAs (group gi: CTA 1 + gi % (W-1), warp gi / (W-1)); an owner applies the
+// steps of block b to its groups as soon as they are published.  Inside a pass there is NO team barrier, only two kinds
+// of flags in global memory:
+//   hseq        (release by the chain warp) = number of blocks whose steps h are in hpass[] — owners poll it;
+//   gdone[gi]   (release by the owner)      = number of blocks whose steps have reached group gi — before block b the
+//               chain warp polls the flags of the groups its 32 entries live in (ordered visits: ONE group), and needs
+//               them only up to block b-2 (block b-1 arrives through the staged panel), so the owners have the whole
+//               chain of block b-1 to get there and their L2 round trips are off the dependent path.
+// One team barrier per pass (drain complete, max|h| and the list state published).  Every entry still receives the
+// steps in visit order: same iterates as run().
 struct Multi {
   int W, me;      // CTAs in the team, this CTA's index (0 runs the chain)
   double *gG;     // [m] g by entry (global)
-  double *hG;     // [2][32] steps of the last two blocks (global)
+  double *hG;     // [64] unused by the flag pipeline (kept: callers lay pmaxG / flagsG out behind it)
   double *pmaxG;  // [1]
   int *flagsG;    // [0] new m, [1] list changed
   int *rowG;      // [m] row ids of the list (global; rewritten by CTA 0 when the list is compacted)
+  double *hpass;  // [m] steps of the current pass by visit position (global)
+  unsigned *seq;  // [32 + ceil(m/32)] hseq at [0], gdone[gi] at [32 + gi] (global)
 };
 
-// apply block hbk's steps to the entries of the 32-entry groups owned by this CTA, skipping blocks ex0 / ex1.
-// Warps wfirst.. of the CTA take the owned groups round-robin; lane = entry within the group.
-template <int T, class Policy>
-__device__ __forceinline__ void apply_owned(const State &S, const Multi &X, int m, int hbk, const double *hsrc, int ex0,
-                                            int ex1, int wfirst) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = T / 32 - wfirst;
-  if (warp < wfirst) return;
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// one owner warp: the steps of block hbk (h_i on lane i, read from hsrc) reach the entries of group gi, except those
+// that live in block hbk itself or in block hbk+1 (the chain warp applies the panel to them).  lane = entry in the group.
+template <class Policy>
+__device__ __forceinline__ void apply_group(const State &S, const Multi &X, int m, int hbk, const double *hsrc, int gi) {
+  const int lane = threadIdx.x & 31;
   const int cnt = min(32, m - 32 * hbk);
   const double hl = lane < cnt ? __ldcg(hsrc + lane) : 0.0; // lane i holds h_i
   if (!__any_sync(0xffffffffu, hl != 0.0)) return;
   const int ri = lane < cnt ? gcolidx(S, S.row[S.ord[32 * hbk + lane]]) : 0; // ... and the column of entry i of the block
-  const int ngroups = (m + 31) >> 5;
-  for (int gi = X.me + X.W * (warp - wfirst); gi < ngroups; gi += X.W * nw) {
-    const int t = 32 * gi + lane;
-    const bool live = t < m;
-    const int blk = live ? (S.pos[t] >> 5) : ex0;
-    const bool skip = !live || blk == ex0 || blk == ex1;
-    const int rt = live ? S.row[t] : 0;
-    double gt = skip ? 0.0 : __ldcg(X.gG + t);
+  const int t = 32 * gi + lane;
+  const bool live = t < m;
+  const int blk = live ? (S.pos[t] >> 5) : hbk;
+  const bool skip = !live || blk == hbk || blk == hbk + 1;
+  const int rt = live ? S.row[t] : 0;
+  double gt = skip ? 0.0 : __ldcg(X.gG + t);
 #pragma unroll 1
-    for (int i0 = 0; i0 < cnt; i0 += 16) {
-      double v[16];
+  for (int i0 = 0; i0 < cnt; i0 += 16) {
+    double v[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int rr_ = __shfl_sync(0xffffffffu, ri, (i0 + u) & 31);
-        v[u] = (!skip && i0 + u < cnt) ? ld_l2(S.G + (long long)rr_ * S.ldg + rt) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const double h = __shfl_sync(0xffffffffu, hl, (i0 + u) & 31);
-        if (i0 + u < cnt && h != 0.0) gt = Policy::apply(gt, v[u], h);
-      }
+    for (int u = 0; u < 16; ++u) {
+      const int rr_ = __shfl_sync(0xffffffffu, ri, (i0 + u) & 31);
+      v[u] = (!skip && i0 + u < cnt) ? ld_l2(S.G + (long long)rr_ * S.ldg + rt) : 0.0;
     }
-    if (!skip) __stcg(X.gG + t, gt);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const double h = __shfl_sync(0xffffffffu, hl, (i0 + u) & 31);
+      if (i0 + u < cnt && h != 0.0) gt = Policy::apply(gt, v[u], h);
+    }
   }
+  if (!skip) __stcg(X.gG + t, gt);
 }
 
 // Team-collective: every thread of every CTA of the team calls it with the same arguments (S.row/ord/pos are
@@ -390,11 +469,11 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
   int m = S.m;
   Result R{0, 0, 0, 0.0, 0, m};
   Shared *sh = S.sh;
-  // optional cycle counters (S.prof): thread 0 of CTA 0 [0..3] = panel, chain, team barrier, pass ends; thread 32 of
-  // CTA 0 [4..6] = staging, apply, team barrier; thread 0 of CTA 1 [7] = apply
+  // optional cycle counters (S.prof): thread 0 of CTA 0 [0..3] = panel, chain, CTA barrier, pass ends, [5] = wait for the
+  // owners' flags; thread 32 of CTA 0 [4], [6] = staging, CTA barrier; thread 0 of CTA 1 [7] = apply
   // (compiled in with -DCDGPU_CHAIN_PROF only: the counters cost the naive kernel registers it does not have)
 #ifdef CDGPU_CHAIN_PROF
-  long long pc[4] = {0, 0, 0, 0};
+  long long pc[5] = {0, 0, 0, 0, 0};
   const bool prof = S.prof != nullptr && ((chainCTA && (tid == 0 || tid == 32)) || (X.me == 1 && tid == 0));
   long long tp = prof ? clock64() : 0;
   auto lap = [&](int slot) {
@@ -407,6 +486,13 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
 #else
   auto lap = [](int) {};
 #endif
+  const int NW = T / 32;
+  // flags start from zero: one team barrier per call
+  if (chainCTA)
+    for (int i = tid; i < 32 + ((m + 31) >> 5); i += T) X.seq[i] = 0u;
+  __threadfence();
+  sync();
+  unsigned base = 0; // blocks of the passes before this one
   for (long long pass = 0; pass < maxPasses; ++pass) {
     const int m_pass = m;
     const PermKey pkm = cd_perm_key((uint32_t)max(m, 1), seed, pass_counter + pass);
@@ -417,70 +503,93 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
     }
     __syncthreads();
     const int nb = (m + 31) >> 5;
+    double pmax = 0.0;
+    long long acc = 0;
     if (chainCTA) {
       stage_block(S, P, m, 0, S.stage, tid, T);
       __syncthreads();
-    }
-    double pmax = 0.0;
-    long long acc = 0;
-    lap(3);
-    for (int b = 0; b < nb; ++b) {
-      if (chainCTA && warp == 0) {
-        double *buf = S.stage + (b & 1) * BUF_DOUBLES;
-        const int cnt = min(32, m - 32 * b);
-        const bool valid = lane < cnt;
-        const int e = valid ? S.ord[32 * b + lane] : 0;
-        double gj = valid ? __ldcg(X.gG + e) : 0.0, bej = valid ? S.be[e] : 0.0;
-        // lanes past the end of the list step on benign constants (their results are never used; garbage could send
-        // every step of the warp through a policy's slow path)
-        const double c0 = valid ? buf[2048 + lane] : 1.0, c1 = valid ? buf[2048 + 32 + lane] : 1.0, c2 = valid ? buf[2048 + 64 + lane] : 1.0;
-        if (b > 0) { // steps of the previous block, in order
-          const double *hp = sh->hb[(b - 1) & 1], *Pb = buf + 1024;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const double h = hp[i];
-            if (h != 0.0) gj = Policy::apply(gj, Pb[i * 32 + lane], h);
+      lap(3);
+      for (int b = 0; b < nb; ++b) {
+        if (warp == 0) {
+          double *buf = S.stage + (b & 1) * BUF_DOUBLES;
+          const int cnt = min(32, m - 32 * b);
+          const bool valid = lane < cnt;
+          const int e = valid ? S.ord[32 * b + lane] : 0;
+          if (b >= 2 && valid) { // the steps of blocks <= b-2 have reached this lane's entry (earlier passes: team barrier)
+            const unsigned need = base + (unsigned)(b - 1);
+            const unsigned *f = X.seq + 32 + (e >> 5);
+            while (ld_acquire_u32(f) < need) {
+            }
           }
-        }
-        lap(0);
-        double myh = 0.0;
-        double drow = buf[lane];
-        for (int i = 0; i < cnt; ++i) {
-          const double dnext = buf[((i + 1) & 31) * 32 + lane];
-          double nw, hi, dr;
-          P.step(gj, bej, c0, c1, c2, rr, nw, hi, dr);
-          const double h = __shfl_sync(0xffffffffu, hi, i);
-          if (lane == i) {
-            bej = nw;
-            myh = hi;
+          __syncwarp();
+          lap(4);
+          double gj = valid ? __ldcg(X.gG + e) : 0.0, bej = valid ? S.be[e] : 0.0;
+          // lanes past the end of the list step on benign constants (their results are never used; garbage could send
+          // every step of the warp through a policy's slow path)
+          const double c0 = valid ? buf[2048 + lane] : 1.0, c1 = valid ? buf[2048 + 32 + lane] : 1.0, c2 = valid ? buf[2048 + 64 + lane] : 1.0;
+          if (b > 0) { // steps of the previous block, in order
+            const double *hp = sh->hb[(b - 1) & 1], *Pb = buf + 1024;
+            // operands first, then the 32 dependent updates (a zero step leaves gj as it is: the skipped product is +-0)
+#pragma unroll
+            for (int i0 = 0; i0 < 32; i0 += 16) {
+              double pv[16], hv[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                pv[u] = Pb[(i0 + u) * 32 + lane];
+                hv[u] = hp[i0 + u];
+              }
+#pragma unroll
+              for (int u = 0; u < 16; ++u) gj = Policy::apply(gj, pv[u], hv[u]);
+            }
           }
-          if (h != 0.0) {
-            gj = Policy::apply(gj, drow, h);
-            if (Policy::HAS_RR) rr += __shfl_sync(0xffffffffu, dr, i);
-            acc += 1;
+          lap(0);
+          double myh = 0.0;
+          chain_steps(P, buf, cnt, lane, gj, bej, c0, c1, c2, rr, myh, acc);
+          if (valid) {
+            __stcg(X.gG + e, gj);
+            S.be[e] = bej;
           }
-          drow = dnext;
+          const double hv = valid ? myh : 0.0;
+          sh->hb[b & 1][lane] = hv;
+          __stcg(X.hpass + 32 * b + lane, hv);
+          pmax = fmax(pmax, fabs(myh));
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence();
+            st_release_u32(X.seq, base + (unsigned)b + 1u);
+          }
+          lap(1);
+        } else {
+          if (b + 1 < nb) stage_block(S, P, m, b + 1, S.stage + ((b + 1) & 1) * BUF_DOUBLES, tid - 32, T - 32);
+          lap(0);
         }
-        if (valid) {
-          __stcg(X.gG + e, gj);
-          S.be[e] = bej;
-        }
-        const double hv = valid ? myh : 0.0;
-        sh->hb[b & 1][lane] = hv;
-        __stcg(X.hG + (b & 1) * 32 + lane, hv);
-        pmax = fmax(pmax, fabs(myh));
-        lap(1);
-      } else {
-        if (chainCTA && b + 1 < nb) stage_block(S, P, m, b + 1, S.stage + ((b + 1) & 1) * BUF_DOUBLES, tid - 32, T - 32);
-        lap(0);
-        if (b >= 1) apply_owned<T, Policy>(S, X, m, b - 1, X.hG + ((b - 1) & 1) * 32, b - 1, b, chainCTA ? 1 : 0);
-        lap(1);
+        __syncthreads(); // the next block is staged, hb[b & 1] is visible to the next panel
+        lap(2);
       }
-      sync();
-      lap(2);
+    } else {
+      // owner warps: groups (me-1) + (W-1)*warp, + (W-1)*NW, ... ; block by block as the steps are published
+      const int g0 = (X.me - 1) + (X.W - 1) * warp, gstep = (X.W - 1) * NW;
+      const int ngroups = nb;
+      if (g0 < ngroups) {
+        for (int b = 0; b < nb; ++b) {
+          const unsigned need = base + (unsigned)b + 1u;
+          while (ld_acquire_u32(X.seq) < need) {
+          }
+          __syncwarp();
+          lap(0);
+          for (int gi = g0; gi < ngroups; gi += gstep) {
+            apply_group<Policy>(S, X, m, b, X.hpass + 32 * b, gi);
+            __syncwarp();
+            if (lane == 0) {
+              __threadfence();
+              st_release_u32(X.seq + 32 + gi, need);
+            }
+          }
+          lap(1);
+        }
+      }
     }
-    // drain: the last block's steps reach the rest of the list (CTA 0's warp 0 joins in)
-    if (nb >= 2) apply_owned<T, Policy>(S, X, m, nb - 1, X.hG + ((nb - 1) & 1) * 32, nb - 1, -1, 0);
+    base += (unsigned)nb;
     // ---- end of the pass on CTA 0: max|h|, dropzeros!
     if (chainCTA) {
       if (warp == 0) {
@@ -567,7 +676,9 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
       S.prof[7] += pc[1];
     } else {
       const int o = tid == 0 ? 0 : 4;
-      for (int i = 0; i < (tid == 0 ? 4 : 3); ++i) S.prof[o + i] += pc[i];
+      for (int i = 0; i < (tid == 0 ? 4 : 3); ++i)
+        if (tid == 0 || i != 1) S.prof[o + i] += pc[i];
+      if (tid == 0) S.prof[5] += pc[4]; // the chain warp's wait for the owners' flags
     }
   }
 #endif

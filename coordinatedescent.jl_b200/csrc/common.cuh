@@ -255,6 +255,7 @@ struct cdgpu_handle_s {
   double *dnzval = nullptr;
   int64_t outcap = 0, outcols = 0;
   int *dflag = nullptr;             // device status word(s)
+  double *dchain = nullptr;         // scratch of the team chain engine (chain_engine.cuh: Multi::hpass, Multi::seq)
   double gram_ms = 0.0;
   int sm_count = 0, max_cluster = 0;
   // lazy covariance form (lazy_gram.cu): dX is then the column CACHE (ld x lz_cap), columns found through dslot
@@ -349,6 +350,7 @@ struct CovArgs {
   const int *colslot;
   CovResume *resume;
   int events_only; // diagnostics: 1 = the event-by-event full pass of round 1 instead of chain + verify
+  double *chain_scr; // CD_MULTI_SCR_BYTES of global scratch for the team chain engine
 };
 int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a);
 int launch_cov_init(cdgpu_handle_s *h, const double *A, long long lda, int p, const int *act, const double *actval,
@@ -419,9 +421,12 @@ struct NaiveArgs {
   int multi_ok;    // grid-distributed chain engine for large active sets (CDGPU_NAIVE_MULTI=0 disables)
   int pipeline;    // split-phase rounds of the full pass (CDGPU_NAIVE_PIPELINE=0 disables)
   int plan;        // members' steps of a full pass planned by one chain pass (CDGPU_NAIVE_PLAN=0 disables)
+  double *chain_scr; // CD_MULTI_SCR_BYTES of global scratch for the team chain engine
 };
 // offset (doubles, even) of the tail of a handle's scratch: 16p doubles for the result buffers of the full-pass rounds
 constexpr int CD_GCAP = 4096; // largest active set of a naive handle that runs on the chain engines (Gram scratch 134 MB)
+// global scratch of the team chain engine (chain_engine.cuh: Multi::hpass [CD_GCAP doubles], Multi::seq [32 + CD_GCAP/32 words])
+constexpr size_t CD_MULTI_SCR_BYTES = (size_t)CD_GCAP * sizeof(double) + (32 + CD_GCAP / 32) * sizeof(unsigned);
 inline size_t cd_gram_cap(size_t p) { return p < 2048 ? 2048 : (p < (size_t)CD_GCAP ? p : (size_t)CD_GCAP); }
 inline size_t cd_scr_tail(size_t p, size_t n) { return (15 * p + 8 * n + 64 + 4 * (size_t)CD_GCAP + 64 + 1) & ~(size_t)1; }
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);

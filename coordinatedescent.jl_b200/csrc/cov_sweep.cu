@@ -311,6 +311,11 @@ __device__ __forceinline__ double event_pass(Ctx &c, double lam, unsigned long l
 // gathered from the L2-resident columns of A.
 struct CovPolicy {
   static constexpr bool HAS_RR = false;
+  static constexpr bool FAST_V = true; // chain_engine.cuh: chain_steps
+  // argument of the shrinkage, as step() forms it
+  __device__ __forceinline__ double enter(double g, double be, double c0, double c1) const {
+    return __dsub_rn(be, __dmul_rn(g + c0, c1));
+  }
   const double *b, *ainv, *omega;
   double lam;
   __device__ __forceinline__ void load_consts(int k, double &c0, double &c1, double &c2) const {
@@ -1339,7 +1344,7 @@ __device__ void active_engine_multi(Ctx &c, double lam, long long maxPasses, uns
   S.ldg = a.lda;
   S.slot = a.colslot;
   S.prof = nullptr;
-  chain::Multi X{c.C, c.rank, gG, hG, pmaxG, flagsG, a.act};
+  chain::Multi X{c.C, c.rank, gG, hG, pmaxG, flagsG, a.act, a.chain_scr, reinterpret_cast<unsigned *>(a.chain_scr + CD_GCAP)};
   const CovPolicy P{a.b, a.ainv, a.omega, lam};
   cg::cluster_group &cl = c.cluster;
   const chain::Result r = chain::run_multi<COV_T>(S, X, P, [&cl]() { cl.sync(); }, 0.0, maxPasses, pass_counter,
@@ -1921,7 +1926,7 @@ int launch_cov_path(cdgpu_handle_s *h, const CovArgs &a) {
   }
   size_t dyn = slice_in_smem ? fixed_for(ecap) + slices : fixed_for(ecap);
   // the distributed engine needs 8p + 80 scratch doubles behind the slices; CDGPU_COV_MULTI=0 switches it off
-  int multi_ok = a.p >= 64 ? 384 : 0;
+  int multi_ok = (a.p >= 64 && C >= 2) ? 384 : 0; // run_multi: the chain CTA plus at least one owner CTA
   if (const char *env = getenv("CDGPU_MULTI_MIN")) multi_ok = multi_ok ? std::max(64, atoi(env)) : 0;
   if (const char *env = getenv("CDGPU_COV_MULTI")) multi_ok = atoi(env) != 0 ? multi_ok : 0;
   cudaLaunchConfig_t cfg = {};

@@ -834,6 +834,7 @@ __device__ void gram_publish(NCtx &c, const chain::Result &r, int m0, const int 
 // closed-form updates on d_t = X_t'(w.r) for the chain engine (chain_engine.cuh)
 struct LsPolicy { // cd_differentiable_function.jl:101-104 / :184-187
   static constexpr bool HAS_RR = false;
+  static constexpr bool FAST_V = true; // chain_engine.cuh: chain_steps
   const double *colsq, *omega;
   double lam, nd;
   __device__ __forceinline__ void load_consts(int k, double &c0, double &c1, double &c2) const {
@@ -851,6 +852,8 @@ struct LsPolicy { // cd_differentiable_function.jl:101-104 / :184-187
     const double aq = fabs(q1);
     return (aq < 1e280 && (aq > 1e-280 || d == 0.0)) ? q1 : d / aa;
   }
+  // argument of the shrinkage, as step() forms it
+  __device__ __forceinline__ double enter(double d, double be, double aa, double inv) const { return __dadd_rn(be, quot(d, aa, inv)); }
   __device__ __forceinline__ void step(double d, double be, double aa, double inv, double th, double, double &nw, double &h,
                                        double &dr) const {
     const double v = __dadd_rn(be, quot(d, aa, inv));
@@ -862,6 +865,8 @@ struct LsPolicy { // cd_differentiable_function.jl:101-104 / :184-187
 };
 struct SqrtPolicy { // :259-283 with s, ||r+||^2 from d, ||r||^2, a
   static constexpr bool HAS_RR = true;
+  static constexpr bool FAST_V = false; // the threshold moves with ||r||^2: every step is evaluated in full
+  __device__ __forceinline__ double enter(double, double, double, double) const { return 0.0; }
   const double *colsq, *omega;
   double lam;
   __device__ __forceinline__ void load_consts(int k, double &c0, double &c1, double &c2) const {
@@ -1112,7 +1117,7 @@ __device__ void gram_engine_multi(NCtx &c, double lam, long long maxPasses, unsi
   // team = the first W CTAs of the cooperative grid (all co-resident), with its own barrier: one atomic arrive and
   // an acquire-poll on a counter in global memory — a 16-CTA barrier costs a fraction of grid.sync() over 148
   const int W = min(c.G, NV_MULTI_TEAM);
-  chain::Multi X{W, c.bid, d0, hG, pmaxG, flagsG, rowG}; // g = X_A'(w.r), already in global memory
+  chain::Multi X{W, c.bid, d0, hG, pmaxG, flagsG, rowG, a.chain_scr, reinterpret_cast<unsigned *>(a.chain_scr + CD_GCAP)}; // g = X_A'(w.r), already in global memory
   unsigned *ctr = reinterpret_cast<unsigned *>(flagsG + 2);
   unsigned target = 0;
   auto sync = [ctr, &target, W]() {
@@ -1302,7 +1307,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
             }
             fast_grid_sync(c);
             const long long tg2 = clock64();
-            if (a.multi_ok > 0 && m_act >= a.multi_ok) { // a.multi_ok: smallest list length for the team engine
+            if (a.multi_ok > 0 && m_act >= a.multi_ok && c.G >= 2) { // a.multi_ok: smallest list length for the team engine (chain CTA + owners)
               if (c.bid < NV_MULTI_TEAM) gram_engine_multi(c, lam, a.maxIter - iter, pass_counter, m_act, Gs, ds);
               if (a.prof && c.bid == 0 && tid == 0) a.prof[10] += clock64() - tg2;
             } else if (c.bid == 0) {
