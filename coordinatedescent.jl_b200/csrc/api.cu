@@ -1370,7 +1370,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     CD_TRY(launch_naive_init(h, a));
     CD_TRY(launch_naive_path(h, a));
     if (prof) {
-      long long pf[24];
+      long long pf[32];
       CUDA_TRY(cudaMemcpyAsync(pf, a.prof, sizeof pf, cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(cudaStreamSynchronize(h->stream));
       fprintf(stderr,
@@ -1383,6 +1383,10 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
               "warp 0 waiting for owners) %.3f barrier %.3f | team engine (counters with -DCDGPU_CHAIN_PROF): apply on CTA 1 %.3f; whole call %.3f, of which publish %.3f Mcyc\n",
               pf[16] * 1e-6, pf[17] * 1e-6, pf[18] * 1e-6, pf[19] * 1e-6, pf[20] * 1e-6, pf[21] * 1e-6, pf[22] * 1e-6, pf[23] * 1e-6,
               pf[10] * 1e-6, pf[11] * 1e-6);
+      fprintf(stderr,
+              "[cdgpu profile]   owner warp (CTA 1, thread 0; -DCDGPU_CHAIN_PROF): wait g %.3f, wait h %.3f, 32 updates %.3f, tagged store %.3f, "
+              "prefetch %.3f Mcyc\n",
+              pf[24] * 1e-6, pf[25] * 1e-6, pf[26] * 1e-6, pf[27] * 1e-6, pf[28] * 1e-6);
     }
   }
   return CDGPU_OK;

@@ -77,21 +77,22 @@ __device__ __forceinline__ void stage_block(const State &S, const Policy &P, int
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
       const int idx = base + u * nthr;
-      v[u] = 0.0;
-      if (idx < total) {
-        const int i = (idx >> 5) & 31, j = idx & 31;
-        const bool panel = idx >= 1024;
-        if (j < cnt && (panel || i < cnt)) {
-          const int rj = S.row[S.ord[32 * bb + j]];
-          const int ri = S.row[S.ord[32 * (panel ? bb - 1 : bb) + i]];
-          v[u] = ld_l2(gcol(S, ri) + rj);
-        }
-      }
+      // every load is issued unconditionally on a clamped (valid) address and masked when it is stored: a predicated
+      // load makes the compiler wait for it as soon as the predicate register is needed again, which serialises the batch
+      const int idc = min(idx, total - 1);
+      const int i = (idc >> 5) & 31, j = idc & 31;
+      const bool panel = idc >= 1024;
+      const int rj = S.row[S.ord[32 * bb + min(j, cnt - 1)]];
+      const int ri = S.row[S.ord[32 * (panel ? bb - 1 : bb) + (panel ? i : min(i, cnt - 1))]];
+      v[u] = ld_l2(gcol(S, ri) + rj);
     }
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
       const int idx = base + u * nthr;
-      if (idx < total) buf[idx] = v[u];
+      if (idx < total) {
+        const int i = (idx >> 5) & 31, j = idx & 31;
+        buf[idx] = (j < cnt && (idx >= 1024 || i < cnt)) ? v[u] : 0.0;
+      }
     }
   }
   for (int j = t0; j < cnt; j += nthr) {
@@ -120,7 +121,7 @@ __device__ __forceinline__ void apply_block(const State &S, int m, int hbk, cons
       double v[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u)
-        v[u] = (i0 + u < cnt) ? ld_l2(gcol(S, S.row[S.ord[32 * hbk + i0 + u]]) + rt) : 0.0;
+        v[u] = ld_l2(gcol(S, S.row[S.ord[32 * hbk + min(i0 + u, cnt - 1)]]) + rt); // unconditional (see stage_block); h = 0 past the end
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const double h = (i0 + u < cnt) ? hv[i0 + u] : 0.0;
@@ -393,68 +394,146 @@ __device__ Result run(State &S, const Policy &P, double rr, long long maxPasses,
 // ------------------------------------------------------------------------------------------------------------
 // The same engine spread over W >= 2 CTAs (a thread-block cluster, or the cooperative grid), for active sets of many
 // blocks: with ONE CTA the 32 steps of a block reach the other m - 64 entries through a single SM's L2 port
-// (~12 k cycles per block at m = 800, measured), which is what bounds dense active sets.  Here g lives in global
-// memory (L2).  CTA 0 keeps the chain (warp 0) and the staging (warps 1..15) and nothing else.  The 32-entry groups of
-// the list are dealt to the warps of the other CTAs (group gi: CTA 1 + gi % (W-1), warp gi / (W-1)); an owner applies the
-// steps of block b to its groups as soon as they are published.  Inside a pass there is NO team barrier, only two kinds
-// of flags in global memory:
-//   hseq        (release by the chain warp) = number of blocks whose steps h are in hpass[] — owners poll it;
-//   gdone[gi]   (release by the owner)      = number of blocks whose steps have reached group gi — before block b the
-//               chain warp polls the flags of the groups its 32 entries live in (ordered visits: ONE group), and needs
-//               them only up to block b-2 (block b-1 arrives through the staged panel), so the owners have the whole
-//               chain of block b-1 to get there and their L2 round trips are off the dependent path.
-// One team barrier per pass (drain complete, max|h| and the list state published).  Every entry still receives the
-// steps in visit order: same iterates as run().
+// (~12 k cycles per block at m = 800, measured), which is what bounds dense active sets.  CTA 0 keeps the chain
+// (warp 0) and the staging (warps 1..15) and nothing else.  The 32-entry groups of the list are dealt to the warps of
+// the other CTAs (group gi: CTA 1 + gi % (W-1), warp gi / (W-1)); an owner applies the steps of block b to its groups as
+// soon as they are published.  Inside a pass there is NO barrier and NO fence between the CTAs: g and h travel through
+// global memory (L2) as TAGGED values — 16 bytes {low word, tag, high word, tag}, each 8-byte half written and read
+// atomically, the tag = number of blocks (counted over all passes of the call) whose steps the value contains — and
+// every reader knows the tag it needs, so it simply re-reads until both halves carry it:
+//   h of block b            tag base+b+1, written by the chain warp, awaited by every owner;
+//   g of an entry, owners   an owner applying block b reads tag base+b and writes base+b+1; it leaves the entries of
+//                           blocks b and b+1 alone (block b+1 gets the steps through the staged panel);
+//   g of an entry, chain    before block b the chain warp needs tag >= base+b-1 (the owners have the whole chain of
+//                           block b-1 to get there: their L2 round trips are off the dependent path) and writes base+b+1.
+// One team barrier per pass (max|h| and the list state published).  Every entry still receives the steps in visit
+// order: same iterates as run().
 struct Multi {
   int W, me;      // CTAs in the team, this CTA's index (0 runs the chain)
-  double *gG;     // [m] g by entry (global)
-  double *hG;     // [64] unused by the flag pipeline (kept: callers lay pmaxG / flagsG out behind it)
+  double *gG;     // [m] g by entry (global): input and output of the call
+  double *hG;     // [64] unused by the tagged pipeline (kept: callers lay pmaxG / flagsG out behind it)
   double *pmaxG;  // [1]
   int *flagsG;    // [0] new m, [1] list changed
   int *rowG;      // [m] row ids of the list (global; rewritten by CTA 0 when the list is compacted)
-  double *hpass;  // [m] steps of the current pass by visit position (global)
-  unsigned *seq;  // [32 + ceil(m/32)] hseq at [0], gdone[gi] at [32 + gi] (global)
+  uint4 *gT;      // [m] tagged g by entry (global)
+  uint4 *hT;      // [ceil32(m)] tagged steps of the current pass by visit position (global)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void tag_store(uint4 *p, double x, unsigned tag) {
+  const unsigned lo = (unsigned)__double2loint(x), hi = (unsigned)__double2hiint(x);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
 }
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// re-read until both halves carry the same tag >= need
+__device__ __forceinline__ double tag_wait(const uint4 *p, unsigned need) {
+  unsigned lo, t0, hi, t1;
+  do {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(p) : "memory");
+  } while (t0 != t1 || (int)(t0 - need) < 0);
+  return __hiloint2double((int)hi, (int)lo);
 }
 
-// one owner warp: the steps of block hbk (h_i on lane i, read from hsrc) reach the entries of group gi, except those
-// that live in block hbk itself or in block hbk+1 (the chain warp applies the panel to them).  lane = entry in the group.
-template <class Policy>
-__device__ __forceinline__ void apply_group(const State &S, const Multi &X, int m, int hbk, const double *hsrc, int gi) {
-  const int lane = threadIdx.x & 31;
-  const int cnt = min(32, m - 32 * hbk);
-  const double hl = lane < cnt ? __ldcg(hsrc + lane) : 0.0; // lane i holds h_i
-  if (!__any_sync(0xffffffffu, hl != 0.0)) return;
-  const int ri = lane < cnt ? gcolidx(S, S.row[S.ord[32 * hbk + lane]]) : 0; // ... and the column of entry i of the block
-  const int t = 32 * gi + lane;
-  const bool live = t < m;
-  const int blk = live ? (S.pos[t] >> 5) : hbk;
-  const bool skip = !live || blk == hbk || blk == hbk + 1;
-  const int rt = live ? S.row[t] : 0;
-  double gt = skip ? 0.0 : __ldcg(X.gG + t);
+// One pass of an owner warp (every warp of the CTAs 1..W-1): its groups are (me-1) + (W-1)*warp, + (W-1)*NW, ...;
+// block by block as the steps are published.  A warp with ONE group (the usual case) that has a 32x32 tile of the CTA's
+// idle stage area (warps 0..3) fetches its G entries for the next block into that tile while the chain of that block
+// runs, so that between "h is published" and "g is handed on" there is one L2 read and 32 dependent updates.
+#ifdef CDGPU_CHAIN_PROF
+#define OWNER_LAP(slot)                                    \
+  do {                                                     \
+    if (prof_apply && tid == 0) {                          \
+      const long long t_ = clock64();                      \
+      if ((slot) >= 0) prof_apply[(slot)] += t_ - tlap;    \
+      tlap = t_;                                           \
+    }                                                      \
+  } while (0)
+#else
+#define OWNER_LAP(slot) \
+  do {                  \
+  } while (0)
+#endif
+template <int T, class Policy>
+__device__ __forceinline__ void owner_pass(const State &S, const Multi &X, int m, int nb, unsigned base, long long *prof_apply) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = T / 32;
+  const int g0 = (X.me - 1) + (X.W - 1) * warp, gstep = (X.W - 1) * NW;
+  if (g0 >= nb) return;
+  long long tacc = 0;
+#ifdef CDGPU_CHAIN_PROF
+  long long tlap = 0; // prof_apply[1..5]: wait for g, wait for h, 32 updates, tagged store, prefetch of the next block
+#endif
+  const bool tiled = g0 + gstep >= nb && warp < STAGE_DOUBLES / 1024;
+  double *tile = S.stage + 1024 * warp; // [i*32 + lane] = G(entry t1, entry i of the block)
+  const int t1 = 32 * g0 + lane;
+  const bool live1 = t1 < m;
+  const int blk1 = live1 ? (S.pos[t1] >> 5) : -1, rt1 = live1 ? S.row[t1] : 0;
+  auto prefetch = [&](int b) {
+    const int cnt = min(32, m - 32 * b);
+    const int ri = lane < cnt ? gcolidx(S, S.row[S.ord[32 * b + lane]]) : 0;
+    const bool skip = !live1 || blk1 == b || blk1 == b + 1;
 #pragma unroll 1
-  for (int i0 = 0; i0 < cnt; i0 += 16) {
-    double v[16];
+    for (int i0 = 0; i0 < 32; i0 += 16) {
+      double v[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int rr_ = __shfl_sync(0xffffffffu, ri, (i0 + u) & 31);
-      v[u] = (!skip && i0 + u < cnt) ? ld_l2(S.G + (long long)rr_ * S.ldg + rt) : 0.0;
+      for (int u = 0; u < 16; ++u) { // unconditional loads on valid addresses (ri = 0 past the block, rt1 = 0 past the list)
+        const int rr_ = __shfl_sync(0xffffffffu, ri, i0 + u);
+        v[u] = ld_l2(S.G + (long long)rr_ * S.ldg + rt1);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) tile[(i0 + u) * 32 + lane] = (!skip && i0 + u < cnt) ? v[u] : 0.0;
     }
+  };
+  if (tiled) prefetch(0);
+  for (int b = 0; b < nb; ++b) {
+    const unsigned tagb = base + (unsigned)b; // what the entries carry before this block; + 1 afterwards
+    if (tiled) {
+      const bool skip = !live1 || blk1 == b || blk1 == b + 1;
+      OWNER_LAP(-1);
+      double gt = skip ? 0.0 : tag_wait(X.gT + t1, tagb);          // own last write, or the chain warp's (block b-1)
+      OWNER_LAP(1);
+      const double hl = tag_wait(X.hT + 32 * b + lane, tagb + 1u); // lane i holds h_i
+      __syncwarp();
+      OWNER_LAP(2);
+      const long long tp0 = prof_apply ? clock64() : 0;
+#pragma unroll 8
+      for (int u = 0; u < 32; ++u) gt = Policy::apply(gt, tile[u * 32 + lane], __shfl_sync(0xffffffffu, hl, u)); // (skip: tile = 0)
+      OWNER_LAP(3);
+      if (!skip) tag_store(X.gT + t1, gt, tagb + 1u);
+      OWNER_LAP(4);
+      if (b + 1 < nb) prefetch(b + 1);
+      OWNER_LAP(5);
+      if (prof_apply) tacc += clock64() - tp0;
+    } else {
+      const double hl = tag_wait(X.hT + 32 * b + lane, tagb + 1u);
+      const long long tp0 = prof_apply ? clock64() : 0;
+      const int cnt = min(32, m - 32 * b);
+      const int ri = lane < cnt ? gcolidx(S, S.row[S.ord[32 * b + lane]]) : 0;
+      for (int gi = g0; gi < nb; gi += gstep) {
+        const int t = 32 * gi + lane;
+        const bool live = t < m;
+        const int blk = live ? (S.pos[t] >> 5) : b;
+        const bool skip = !live || blk == b || blk == b + 1;
+        const int rt = live ? S.row[t] : 0;
+        double gt = skip ? 0.0 : tag_wait(X.gT + t, tagb);
+        __syncwarp();
+#pragma unroll 1
+        for (int i0 = 0; i0 < cnt; i0 += 16) {
+          double v[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const double h = __shfl_sync(0xffffffffu, hl, (i0 + u) & 31);
-      if (i0 + u < cnt && h != 0.0) gt = Policy::apply(gt, v[u], h);
+          for (int u = 0; u < 16; ++u) {
+            const int rr_ = __shfl_sync(0xffffffffu, ri, (i0 + u) & 31);
+            v[u] = ld_l2(S.G + (long long)rr_ * S.ldg + rt); // unconditional, valid address (see stage_block)
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const double h = __shfl_sync(0xffffffffu, hl, (i0 + u) & 31); // (0 past the end of the block)
+            gt = Policy::apply(gt, v[u], h);
+          }
+        }
+        if (!skip) tag_store(X.gT + t, gt, tagb + 1u);
+      }
+      if (prof_apply) tacc += clock64() - tp0;
     }
   }
-  if (!skip) __stcg(X.gG + t, gt);
+  if (prof_apply && tid == 0) *prof_apply += tacc;
 }
 
 // Team-collective: every thread of every CTA of the team calls it with the same arguments (S.row/ord/pos are
@@ -483,13 +562,16 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
       tp = t;
     }
   };
+  long long *prof_apply = (S.prof != nullptr && X.me == 1) ? S.prof + 7 : nullptr; // thread 0 of CTA 1: cycles applying
 #else
   auto lap = [](int) {};
+  long long *prof_apply = nullptr;
 #endif
-  const int NW = T / 32;
-  // flags start from zero: one team barrier per call
-  if (chainCTA)
-    for (int i = tid; i < 32 + ((m + 31) >> 5); i += T) X.seq[i] = 0u;
+  // tagged copies of g (tag 0); one team barrier per call
+  for (int i = X.me * T + tid; i < ((m + 31) & ~31); i += X.W * T) {
+    if (i < m) tag_store(X.gT + i, __ldcg(X.gG + i), 0u);
+    tag_store(X.hT + i, 0.0, 0u); // (tags left by an earlier call must not pass for this call's)
+  }
   __threadfence();
   sync();
   unsigned base = 0; // blocks of the passes before this one
@@ -515,15 +597,10 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
           const int cnt = min(32, m - 32 * b);
           const bool valid = lane < cnt;
           const int e = valid ? S.ord[32 * b + lane] : 0;
-          if (b >= 2 && valid) { // the steps of blocks <= b-2 have reached this lane's entry (earlier passes: team barrier)
-            const unsigned need = base + (unsigned)(b - 1);
-            const unsigned *f = X.seq + 32 + (e >> 5);
-            while (ld_acquire_u32(f) < need) {
-            }
-          }
+          // g with the steps of every block <= b-2 of this pass (and of all earlier passes) applied
+          double gj = valid ? tag_wait(X.gT + e, base + (unsigned)max(b - 1, 0)) : 0.0, bej = valid ? S.be[e] : 0.0;
           __syncwarp();
           lap(4);
-          double gj = valid ? __ldcg(X.gG + e) : 0.0, bej = valid ? S.be[e] : 0.0;
           // lanes past the end of the list step on benign constants (their results are never used; garbage could send
           // every step of the warp through a policy's slow path)
           const double c0 = valid ? buf[2048 + lane] : 1.0, c1 = valid ? buf[2048 + 32 + lane] : 1.0, c2 = valid ? buf[2048 + 64 + lane] : 1.0;
@@ -545,19 +622,14 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
           lap(0);
           double myh = 0.0;
           chain_steps(P, buf, cnt, lane, gj, bej, c0, c1, c2, rr, myh, acc);
+          const double hv = valid ? myh : 0.0;
+          tag_store(X.hT + 32 * b + lane, hv, base + (unsigned)b + 1u); // all 32 lanes: owners wait on every lane's tag
           if (valid) {
-            __stcg(X.gG + e, gj);
+            tag_store(X.gT + e, gj, base + (unsigned)b + 1u);
             S.be[e] = bej;
           }
-          const double hv = valid ? myh : 0.0;
           sh->hb[b & 1][lane] = hv;
-          __stcg(X.hpass + 32 * b + lane, hv);
           pmax = fmax(pmax, fabs(myh));
-          __syncwarp();
-          if (lane == 0) {
-            __threadfence();
-            st_release_u32(X.seq, base + (unsigned)b + 1u);
-          }
           lap(1);
         } else {
           if (b + 1 < nb) stage_block(S, P, m, b + 1, S.stage + ((b + 1) & 1) * BUF_DOUBLES, tid - 32, T - 32);
@@ -567,27 +639,7 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
         lap(2);
       }
     } else {
-      // owner warps: groups (me-1) + (W-1)*warp, + (W-1)*NW, ... ; block by block as the steps are published
-      const int g0 = (X.me - 1) + (X.W - 1) * warp, gstep = (X.W - 1) * NW;
-      const int ngroups = nb;
-      if (g0 < ngroups) {
-        for (int b = 0; b < nb; ++b) {
-          const unsigned need = base + (unsigned)b + 1u;
-          while (ld_acquire_u32(X.seq) < need) {
-          }
-          __syncwarp();
-          lap(0);
-          for (int gi = g0; gi < ngroups; gi += gstep) {
-            apply_group<Policy>(S, X, m, b, X.hpass + 32 * b, gi);
-            __syncwarp();
-            if (lane == 0) {
-              __threadfence();
-              st_release_u32(X.seq + 32 + gi, need);
-            }
-          }
-          lap(1);
-        }
-      }
+      owner_pass<T, Policy>(S, X, m, nb, base, prof_apply);
     }
     base += (unsigned)nb;
     // ---- end of the pass on CTA 0: max|h|, dropzeros!
@@ -630,9 +682,9 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
         const int mn = sh->newm;
         double *tmpd = S.stage;
         int *tmpi = reinterpret_cast<int *>(S.stage);
-        for (int i = tid; i < mn; i += T) tmpd[i] = __ldcg(X.gG + idx[i]);
+        for (int i = tid; i < mn; i += T) tmpd[i] = tag_wait(X.gT + idx[i], base); // (every entry ends a pass with tag base)
         __syncthreads();
-        for (int i = tid; i < mn; i += T) __stcg(X.gG + i, tmpd[i]);
+        for (int i = tid; i < mn; i += T) tag_store(X.gT + i, tmpd[i], base);
         __syncthreads();
         for (int i = tid; i < mn; i += T) tmpd[i] = S.be[idx[i]];
         __syncthreads();
@@ -673,7 +725,6 @@ __device__ Result run_multi(State &S, const Multi &X, const Policy &P, Sync sync
 #ifdef CDGPU_CHAIN_PROF
   if (prof) {
     if (X.me == 1) {
-      S.prof[7] += pc[1];
     } else {
       const int o = tid == 0 ? 0 : 4;
       for (int i = 0; i < (tid == 0 ? 4 : 3); ++i)

@@ -1344,7 +1344,7 @@ __device__ void active_engine_multi(Ctx &c, double lam, long long maxPasses, uns
   S.ldg = a.lda;
   S.slot = a.colslot;
   S.prof = nullptr;
-  chain::Multi X{c.C, c.rank, gG, hG, pmaxG, flagsG, a.act, a.chain_scr, reinterpret_cast<unsigned *>(a.chain_scr + CD_GCAP)};
+  chain::Multi X{c.C, c.rank, gG, hG, pmaxG, flagsG, a.act, reinterpret_cast<uint4 *>(a.chain_scr), reinterpret_cast<uint4 *>(a.chain_scr) + CD_GCAP};
   const CovPolicy P{a.b, a.ainv, a.omega, lam};
   cg::cluster_group &cl = c.cluster;
   const chain::Result r = chain::run_multi<COV_T>(S, X, P, [&cl]() { cl.sync(); }, 0.0, maxPasses, pass_counter,

@@ -1117,7 +1117,7 @@ __device__ void gram_engine_multi(NCtx &c, double lam, long long maxPasses, unsi
   // team = the first W CTAs of the cooperative grid (all co-resident), with its own barrier: one atomic arrive and
   // an acquire-poll on a counter in global memory — a 16-CTA barrier costs a fraction of grid.sync() over 148
   const int W = min(c.G, NV_MULTI_TEAM);
-  chain::Multi X{W, c.bid, d0, hG, pmaxG, flagsG, rowG, a.chain_scr, reinterpret_cast<unsigned *>(a.chain_scr + CD_GCAP)}; // g = X_A'(w.r), already in global memory
+  chain::Multi X{W, c.bid, d0, hG, pmaxG, flagsG, rowG, reinterpret_cast<uint4 *>(a.chain_scr), reinterpret_cast<uint4 *>(a.chain_scr) + CD_GCAP}; // g = X_A'(w.r), already in global memory
   unsigned *ctr = reinterpret_cast<unsigned *>(flagsG + 2);
   unsigned target = 0;
   auto sync = [ctr, &target, W]() {
@@ -1212,7 +1212,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   c.rr = shared_sumsq(c);
 
   long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (a.prof && c.bid == 0 && tid < 14) a.prof[10 + tid] = 0;
+  if (a.prof && c.bid == 0 && tid < 22) a.prof[10 + tid] = 0;
   const long long t_start = clock64();
   int nact_hint = *a.nact; // every CTA's view of the list length (refreshed whenever CTA 0 publishes it)
   bool hint_stale = false; // a full pass has run since the last refresh
