@@ -1361,6 +1361,8 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     if (const char *env = getenv("CDGPU_NAIVE_PIPELINE")) a.pipeline = atoi(env) != 0;
     a.plan = 1;
     if (const char *env = getenv("CDGPU_NAIVE_PLAN")) a.plan = atoi(env) != 0;
+    a.replan = 0; // only in builds with -DCDGPU_WITH_REPLAN (naive_sweep.cu: full_pass)
+    if (const char *env = getenv("CDGPU_NAIVE_REPLAN")) a.replan = atoi(env) != 0;
     a.scaled = rc.scaled;
     a.outerMaxIter = rc.outerMaxIter;
     a.outerTol = rc.outerTol;

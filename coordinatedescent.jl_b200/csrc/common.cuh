@@ -422,6 +422,7 @@ struct NaiveArgs {
   int pipeline;    // split-phase rounds of the full pass (CDGPU_NAIVE_PIPELINE=0 disables)
   int plan;        // members' steps of a full pass planned by one chain pass (CDGPU_NAIVE_PLAN=0 disables)
   double *chain_scr; // CD_MULTI_SCR_BYTES of global scratch for the team chain engine
+  int replan;      // members still to come are planned again after an entering coordinate moved (-DCDGPU_WITH_REPLAN builds, CDGPU_NAIVE_REPLAN=1)
 };
 // offset (doubles, even) of the tail of a handle's scratch: 16p doubles for the result buffers of the full-pass rounds
 constexpr int CD_GCAP = 4096; // largest active set of a naive handle that runs on the chain engines (Gram scratch 134 MB)

@@ -129,8 +129,14 @@ __device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
   return v;
 }
 
-// one warp: d = sum_i X[i,k] r_i [w_i].  16-byte loads, 8 independent loads (4 KB) in flight per
-// warp so 16 warps keep ~64 KB per SM outstanding (HBM latency x bandwidth / 148 SMs ~ 35 KB).
+// one warp: d = sum_i X[i,k] r_i [w_i].  16-byte streaming loads, software pipelined in half-batches of four (2 KB per
+// warp): the next four loads are issued before the last four are consumed, so a warp has 2-4 KB in flight at every
+// moment whatever order the compiler gives the instructions (left alone it splits a batch of eight loads around the
+// first multiply-adds and the warp drains to zero loads in flight between batches: the streaming rounds of a full
+// pass ran 10 % slower after an unrelated change elsewhere in the kernel).  The tail (< 8 elements per lane) is one
+// batch of clamped loads, masked.  Summation order as in the plain loop: full batches alternate (s0,s1)/(s2,s3) over
+// u = 0..7, the tail adds to (s0,s1).  (Not a function call: a call in this kernel makes r a generic pointer and
+// costs every phase 60 %, measured.)
 template <bool HASW>
 __device__ __forceinline__ double warp_col_dot_t(const NCtx &c, const double *col) {
   const int n = c.a.n, lane = threadIdx.x & 31;
@@ -141,15 +147,12 @@ __device__ __forceinline__ double warp_col_dot_t(const NCtx &c, const double *co
     const double2 *w2 = reinterpret_cast<const double2 *>(c.w);
     const int np = n >> 1;
     int i = lane;
-    for (; i + 7 * 32 < np; i += 8 * 32) {
-      double2 x[8];
+    auto consume4 = [&](double2(&x)[4], int at) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = ldg_stream2(c2 + i + 32 * u);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const double2 rv = r2[i + 32 * u];
+      for (int u = 0; u < 4; ++u) {
+        const double2 rv = r2[at + 32 * u];
         if (HASW) {
-          const double2 wv = w2[i + 32 * u];
+          const double2 wv = w2[at + 32 * u];
           x[u].x *= wv.x;
           x[u].y *= wv.y;
         }
@@ -161,16 +164,42 @@ __device__ __forceinline__ double warp_col_dot_t(const NCtx &c, const double *co
           s1 = fma(x[u].y, rv.y, s1);
         }
       }
-    }
-    for (; i < np; i += 32) {
-      double2 xv = ldg_stream2(c2 + i);
-      const double2 rv = r2[i];
-      if (HASW) {
-        xv.x *= w2[i].x;
-        xv.y *= w2[i].y;
+    };
+    if (i + 7 * 32 < np) {
+      double2 xa[4], xb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xa[u] = ldg_stream2(c2 + i + 32 * u);
+      for (;;) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xb[u] = ldg_stream2(c2 + i + 128 + 32 * u);
+        consume4(xa, i);
+        const bool more = i + 256 + 7 * 32 < np;
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) xa[u] = ldg_stream2(c2 + i + 256 + 32 * u);
+        }
+        consume4(xb, i + 128);
+        i += 256;
+        if (!more) break;
       }
-      s0 = fma(xv.x, rv.x, s0);
-      s1 = fma(xv.y, rv.y, s1);
+    }
+    if (i < np) { // tail: at most 7 elements per lane
+      double2 xt[7];
+#pragma unroll
+      for (int u = 0; u < 7; ++u) xt[u] = ldg_stream2(c2 + min(i + 32 * u, np - 1));
+#pragma unroll
+      for (int u = 0; u < 7; ++u) {
+        const int j = i + 32 * u;
+        if (j < np) {
+          const double2 rv = r2[j];
+          if (HASW) {
+            xt[u].x *= w2[j].x;
+            xt[u].y *= w2[j].y;
+          }
+          s0 = fma(xt[u].x, rv.x, s0);
+          s1 = fma(xt[u].y, rv.y, s1);
+        }
+      }
     }
     if ((n & 1) && lane == 0) s2 = fma(HASW ? col[n - 1] * c.w[n - 1] : col[n - 1], c.r[n - 1], s2);
   } else {
@@ -481,7 +510,10 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
   const bool pipeline = a.pipeline != 0;
   int Wnext = (nact_hint > 0 && mP == 0) ? min(c.CH, c.G) : Wwarp;
   int q0 = 0, streak = mP > 0 ? 2 : 0; // with a plan the sweep is expected to be clean: pipelined from the first window
-  int pi = 0, replans = 0;             // next planned member; plans redone in this pass
+  int pi = 0;                          // next planned member
+#ifdef CDGPU_WITH_REPLAN
+  int replans = 0;                     // plans redone in this pass
+#endif
   bool have_pend = false;
   NWin pend = {}, spec = {};
   for (;;) {
@@ -576,18 +608,20 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     pf[3] += clock64() - td;
     // a non-member moved: the steps planned for the members still to come are void.  With enough of them left they are
     // planned again against the new r (fresh d = X_k'(w.r), the same active Gram); otherwise they become ordinary columns.
-    if (mP > 0) {
+    // (Compiled in with -DCDGPU_WITH_REPLAN and switched on by CDGPU_NAIVE_REPLAN=1 only: measured on B200 the two grid
+    // barriers + chain of a re-plan cost more than the rounds they save — C1 lambda=0.05 8.3 ms with, 6.9 ms without — and
+    // the inlined call in this loop costs the streaming rounds of every pass 7 % through register allocation alone.)
+#ifdef CDGPU_WITH_REPLAN
+    if (mP > 0 && a.replan && mP - pi >= NV_REPLAN_MIN && replans < NV_REPLAN_MAX) {
       const long long tr0 = clock64();
-      if (mP - pi >= NV_REPLAN_MIN && replans < NV_REPLAN_MAX) {
-        replan_members(c, lam, pi, mP);
-        replans += 1;
-        Wnext = Wwarp;
-        streak = 2;
-      } else {
-        mP = 0;
-      }
+      replan_members(c, lam, pi, mP);
+      replans += 1;
+      Wnext = Wwarp;
+      streak = 2;
       pf[8] += clock64() - tr0;
-    }
+    } else
+#endif
+      mP = 0;
   }
   __syncthreads(); // warps of a warp-granular round leave together
   return maxH;
