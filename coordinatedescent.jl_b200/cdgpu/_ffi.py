@@ -113,6 +113,9 @@ _SIGS = {
     "vc_solve_refit": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Options),
                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vc_solve_chain": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Options),
+                                 C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "refit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "vc_lvocv": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                            C.c_int, C.c_double, C.POINTER(Options), C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),

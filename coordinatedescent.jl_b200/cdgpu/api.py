@@ -474,7 +474,11 @@ class Backend:
         return out
 
     # locpolyl1(X, z, y, zgrid, degree, kernel, λ0, refit, options)  varying_coefficient_lasso.jl:30-79
-    def locpolyl1(self, X, z, y, zgrid, degree, kernel, λ0, refit=False, options: CDOptions = None, shard=None):
+    def locpolyl1(self, X, z, y, zgrid, degree, kernel, λ0, refit=False, options: CDOptions = None, shard=None, chain=None):
+        """`chain`: grid points per warm-started run.  None / 1: the library's default (device: every grid point from
+        zero, all of them concurrently; CPU oracle: the reference's chain over the grid points it is given); k: runs of
+        k consecutive grid points, each point from its predecessor's iterate; `len(zgrid)`: the reference's loop
+        exactly (varying_coefficient_lasso.jl:56,68), as one sequential chain."""
         options = options or CDOptions()
         X, z, y, zgrid = f64(X), f64(z), f64(y), f64(zgrid)
         n, p = X.shape
@@ -485,6 +489,13 @@ class Backend:
         out = np.zeros((ep, m), order="F")
         stats = (_ffi.Stats * m)()
         o = options.c()
+        if chain is not None and int(chain) != 1:
+            outR = np.zeros((ep, m), order="F") if refit else None
+            self.lib.check(self.lib.vc_solve_chain(ptr(X), n, p, n, ptr(z), ptr(y), ptr(zgrid), m, lo, hi, int(degree),
+                                                   kernel.kind, float(kernel.h), float(λ0), C.byref(o), int(chain),
+                                                   self.device, ptr(out), ptr(outR), C.cast(stats, C.c_void_p)))
+            self.last_vc_stats = [stats[i].as_dict() for i in range(lo, hi)]
+            return out, outR
         if not refit:
             self.lib.check(self.lib.vc_solve(ptr(X), n, p, n, ptr(z), ptr(y), ptr(zgrid), m, lo, hi, int(degree),
                                              kernel.kind, float(kernel.h), float(λ0), C.byref(o), self.device, ptr(out),

@@ -535,7 +535,8 @@ const void *vc_cov_pick_lvo(int nu);  // vc_cov_lvo.cu
 static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                            const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                            double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
-                           double *outR, cdgpu_stats *stats, const double *harr = nullptr, double *lvo_err = nullptr) {
+                           double *outR, cdgpu_stats *stats, const double *harr = nullptr, double *lvo_err = nullptr,
+                           int64_t chain = 1) {
   // harr != null: the problems are those of lvocv_locpolyl1 (m = numH * n, zgrid unused, out/outR null, one squared
   // prediction error per problem into lvo_err)
   const int64_t ep = p * (degree + 1), mloc = m_end - m_begin, P2 = p * (p + 1) / 2, PA = P2 + p + 2;
@@ -545,6 +546,12 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, mloc));
   chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (int64_t)((1ll << 30) / ((long long)ldz * nq * 8))));
   if (const char *env = getenv("CDGPU_VC_CHUNK")) chunk = std::max<int64_t>(1, std::min<int64_t>(chunk, atoll(env))); // tests: force several chunks
+  // chains of warm-started grid points never straddle two chunks (one kernel launch each)
+  chain = std::max<int64_t>(1, std::min<int64_t>(chain, mloc));
+  if (chain > chunk)
+    return cdgpu_set_error(CDGPU_ECAP, "chain of %lld grid points exceeds the %lld whose moment blocks fit one chunk", (long long)chain,
+                           (long long)chunk);
+  chunk = chunk / chain * chain;
   cudaStream_t s = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr, eg = nullptr;
   double *dX = nullptr, *dz = nullptr, *dy = nullptr, *dgz = nullptr, *dout = nullptr, *dZ = nullptr, *dV = nullptr, *dC = nullptr;
@@ -668,6 +675,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
     a.lvo_err = derr;
     a.prof = dprof;
     a.gscr = dG;
+    a.chain = (int)chain;
     const int64_t ctas = std::min<int64_t>((mc + VCW - 1) / VCW, (int64_t)occ * sms);
     void *kargs[] = {(void *)&a};
     VM_TRY(cudaLaunchKernel(kfn, dim3((unsigned)ctas), dim3(VCW * 32), kargs, dyn, s));
@@ -720,7 +728,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
 static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                          const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                          double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out, double *outR,
-                         cdgpu_stats *stats);
+                         cdgpu_stats *stats, int64_t chain = 1);
 // lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): numH * n leave-one-out local scaled-lasso problems, all in
 // one batch; problems [q_begin, q_end) of the (bandwidth-major) list are solved (sharding hook), MSE[h] is summed on
 // the host in observation order from the per-problem squared errors.
@@ -769,11 +777,21 @@ API int cdgpu_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx,
                        outR, stats);
   });
 }
+API int cdgpu_vc_solve_chain(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                             const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                             double bandwidth, double lambda0, const cdgpu_options *opt, int64_t chain, int device,
+                             double *out, double *outR, cdgpu_stats *stats) {
+  return api_guard([&]() -> int {
+  return vc_solve_impl(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt, device, out,
+                       outR, stats, chain);
+  });
+}
 static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                          const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                          double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out, double *outR,
-                         cdgpu_stats *stats) {
+                         cdgpu_stats *stats, int64_t chain) {
   if (!X || !z || !y || !zgrid || !opt || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  if (chain < 1) return cdgpu_set_error(CDGPU_EARG, "chain must be at least 1");
   if (n < 1 || p < 1 || ldx < n || degree < 0 || m < 0 || m_begin < 0 || m_end > m || m_begin > m_end)
     return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (kernel_kind != CDGPU_KERNEL_GAUSSIAN && kernel_kind != CDGPU_KERNEL_EPANECHNIKOV)
@@ -796,7 +814,10 @@ static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, con
     const char *form = getenv("CDGPU_VC_FORM");
     if (ep <= 256 && (outR || !(form && strcmp(form, "naive") == 0)))
       return vc_solve_moment(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt,
-                             device, out, outR, stats);
+                             device, out, outR, stats, nullptr, nullptr, chain);
+    if (chain > 1)
+      return cdgpu_set_error(CDGPU_ECAP, "chained grid points need the moment form: p*(degree+1) = %lld exceeds 256 (or CDGPU_VC_FORM=naive)",
+                             (long long)ep);
     if (outR)
       return cdgpu_set_error(CDGPU_ECAP, "refit on the device needs the moment form: p*(degree+1) = %lld exceeds 256",
                              (long long)ep);

@@ -42,6 +42,10 @@ struct VcCovArgs {
   double *lvo_err;     // squared prediction error per problem
   unsigned long long *prof; // optional [8]: summed warp cycles: full passes, active chain, list compaction, phase open, phase close, total
   double *gscr; // per-warp scratch for the compact active Gram: (grid * VCW) x MC x MC doubles, MC = ep rounded up to even
+  // grid points per work item, >= 1: a warp solves `chain` consecutive grid points one after the other, each from the
+  // previous one's iterate (values AND list order: the reference's loop, varying_coefficient_lasso.jl:56,68, is
+  // chain = m); 1: every grid point from zero
+  int chain;
 };
 
 constexpr int VCW = 1;      // warps (local problems) per CTA (one: shared memory then packs 11 problems per SM)
@@ -86,11 +90,17 @@ __global__ void __launch_bounds__(VCW * 32, VC_RING > 4 ? 9 : 11) vc_cov_kernel(
     ttri[u] = tj[u] * (tj[u] + 1) / 2;
   }
 
+  double be[NU]; // the iterate in coordinate layout: carried from one grid point of a chain to the next
+  int nact = 0;
   for (;;) {
-    int g = 0;
-    if (lane == 0) g = a.g0 + atomicAdd(a.counter, 1);
-    g = __shfl_sync(0xffffffffu, g, 0);
-    if (g >= a.g1) break;
+    int wi = 0;
+    if (lane == 0) wi = atomicAdd(a.counter, 1);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    const long long gfirst = (long long)a.g0 + (long long)wi * a.chain;
+    if (gfirst >= a.g1) break;
+    const int glast = (int)min((long long)a.g1, gfirst + a.chain);
+    for (int g = (int)gfirst; g < glast; ++g) {
+    const bool cold = g == (int)gfirst;
     const double *Cg = a.C + (long long)(g - a.g0) * nq * a.ldc;
     // element (k1, k2) of A_g through the moment blocks
     auto moment = [&](int k1, int k2) -> double {
@@ -100,11 +110,12 @@ __global__ void __launch_bounds__(VCW * 32, VC_RING > 4 ? 9 : 11) vc_cov_kernel(
     };
     // state: COORDINATE layout outside a phase (slot u <-> coordinate lane + 32u), ENTRY layout inside one
     // (slot u <-> snapshot entry lane + 32u of the phase's active list)
-    double Ax[NU], be[NU], cc[NU], ai[NU], th[NU];
+    double Ax[NU], cc[NU], ai[NU], th[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const int t = lane + 32 * u;
-      Ax[u] = be[u] = cc[u] = th[u] = 0.0;
+      Ax[u] = cc[u] = th[u] = 0.0;
+      if (cold) be[u] = 0.0;
       ai[u] = 0.0;
       if (t < ep) {
         const double att = __ldg(Cg + (long long)(2 * tl[u]) * a.ldc + ttri[u] + tj[u]);
@@ -116,8 +127,10 @@ __global__ void __launch_bounds__(VCW * 32, VC_RING > 4 ? 9 : 11) vc_cov_kernel(
         sth[t] = th[u];
       }
     }
-    for (int k = lane; k < ep; k += 32) sin[k] = 0;
-    int nact = 0;
+    if (cold) {
+      for (int k = lane; k < ep; k += 32) sin[k] = 0;
+      nact = 0;
+    }
     __syncwarp();
 
     // coordinate layout: Ax[u] += A_g[t_u, k] * h for the mover k = (kj, kl)
@@ -133,6 +146,11 @@ __global__ void __launch_bounds__(VCW * 32, VC_RING > 4 ? 9 : 11) vc_cov_kernel(
 #pragma unroll
       for (int u = 0; u < NU; ++u) Ax[u] = __dadd_rn(Ax[u], __dmul_rn(gv[u], h));
     };
+
+    // warm start inside a chain: (A x) of this grid point's Gram at the carried iterate, stored entries in list order
+    // (what initialize! does for the reference's loss, cd_differentiable_function.jl:135-148)
+    if (!cold)
+      for (int i = 0; i < nact; ++i) apply(sact[i], sval[i]);
 
     // ---- phases of consecutive active-set passes.  Active-set passes only need (A x) on the active set, so a
     // phase (a) gathers the compact m0 x m0 block A_g[act0, act0] once into this warp's scratch (L2 resident,
@@ -620,7 +638,12 @@ __global__ void __launch_bounds__(VCW * 32, VC_RING > 4 ? 9 : 11) vc_cov_kernel(
     }
     if (lane == 0 && a.stats) a.stats[g] = st;
     __syncwarp();
+    const bool keep_list = g + 1 < glast; // the next grid point of the chain starts from this list
     if (LVO || a.outR) {
+      if (keep_list) { // the refit reuses sact / sin / sval
+        for (int i = lane; i < nact; i += 32) stmpi[i] = sact[i];
+        __syncwarp();
+      }
       // ---- refit (varying_coefficient_lasso.jl:71-76): A_g[S,S] x = -b_g[S] on the expanded coordinates S of every
       // group with a non-zero coefficient; both sides come from the moment blocks
       const int ms = selected_groups();
@@ -649,7 +672,22 @@ __global__ void __launch_bounds__(VCW * 32, VC_RING > 4 ? 9 : 11) vc_cov_kernel(
         }
       }
       __syncwarp();
+      if (keep_list) {
+        for (int k2 = lane; k2 < ep; k2 += 32) sin[k2] = 0;
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+          if (lane + 32 * u < ep) sbeta[lane + 32 * u] = be[u];
+        __syncwarp();
+        for (int i = lane; i < nact; i += 32) {
+          const int k2 = stmpi[i];
+          sact[i] = k2;
+          sin[k2] = 1;
+          sval[i] = sbeta[k2];
+        }
+        __syncwarp();
+      }
     }
+    } // grid points of the chain
   }
 }
 

@@ -995,6 +995,23 @@ API int cdref_vc_solve(const double *X, int64_t n, int64_t p, int64_t ldx, const
                               device, out, NULL, stats);
 }
 
+/* the chain cut into runs of `chain` grid points (include/cdgpu.h: cdgpu_vc_solve_chain): every run is the
+ * reference's loop on its own grid points, the first one from zero */
+API int cdref_vc_solve_chain(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                             const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                             double bandwidth, double lambda0, const cdgpu_options *opt, int64_t chain, int device,
+                             double *out, double *outR, cdgpu_stats *stats) {
+  if (chain < 1) return fail(CDGPU_EARG, "chain must be at least 1");
+  if (m_begin < 0 || m_end > m || m_begin > m_end) return fail(CDGPU_EDIM, "DimensionMismatch");
+  for (int64_t b0 = m_begin; b0 < m_end; b0 += chain) {
+    const int64_t b1 = b0 + chain < m_end ? b0 + chain : m_end;
+    int rc = cdref_vc_solve_refit(X, n, p, ldx, z, y, zgrid, m, b0, b1, degree, kernel_kind, bandwidth, lambda0, opt, device,
+                                  out, outR, stats);
+    if (rc) return rc;
+  }
+  return CDGPU_OK;
+}
+
 /* refitLassoPath (lasso.jl:208-225) for one support: X[:, S] \ y by the normal equations and LU (the reference's
  * `\` on a tall matrix is a QR least squares: same solution up to conditioning). */
 API int cdref_refit(cdgpu_handle f, const int64_t *support, int64_t ns, double *coef_out) {

@@ -326,6 +326,43 @@ def test_locpolyl1_wide_dense_active_sets(gpu, ref, form, randomize, monkeypatch
     assert all(s["converged"] == 1 for s in gpu.last_vc_stats)
 
 
+@pytest.mark.parametrize("randomize", [0, 1])
+@pytest.mark.parametrize("refit", [False, True])
+def test_locpolyl1_chain_is_the_reference_loop(gpu, ref, refit, randomize):
+    """The reference creates `beta` once and every grid point's coordinateDescent! starts from its predecessor's
+    solution, values and list order (varying_coefficient_lasso.jl:56,68).  cdgpu_vc_solve_chain with chain = m walks the
+    grid the same way on one warp: per grid point the same supports, coefficients, passes and visits as the CPU path at a
+    LOOSE tolerance (where a cold start would stop somewhere else); chain = 4 equals the reference run on every block of
+    four grid points on its own; the refit (which borrows the list's storage on the device) does not disturb the chain."""
+    rng = np.random.default_rng(86)
+    n, p, degree, m = 280, 14, 1, 12
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    Y = X[:, 0] * np.sin(3 * Z) + X[:, 1] * np.cos(2 * Z) + X[:, 2] * Z + 0.1 * rng.standard_normal(n)
+    zgrid = np.linspace(0.1, 0.9, m)
+    o = CDOptions(randomize=randomize, seed=5, maxIter=20000, optTol=1e-5)
+    og, ogR = gpu.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.01, refit, o, chain=m)
+    sg = gpu.last_vc_stats
+    orf, orR = ref.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.01, refit, o)
+    sr = ref.last_vc_stats
+    assert np.count_nonzero(orf) > 3 * m
+    assert np.array_equal(og != 0, orf != 0)
+    assert np.max(np.abs(og - orf)) <= 1e-9 * np.max(np.abs(orf))
+    assert [(a["passes"], a["visits"]) for a in sg] == [(b["passes"], b["visits"]) for b in sr]
+    # warm starts are what make the later grid points cheap: the cold batch needs more passes at this tolerance
+    gpu.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.01, False, o)
+    assert sum(a["passes"] for a in gpu.last_vc_stats[1:]) > sum(b["passes"] for b in sr[1:])
+    if refit:
+        assert np.array_equal(ogR != 0, orR != 0) and np.allclose(ogR, orR, rtol=1e-6, atol=1e-9)
+    o4, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.01, refit, o, chain=4)
+    s4 = gpu.last_vc_stats
+    for b0 in range(0, m, 4):
+        ob, _ = ref.locpolyl1(X, Z, Y, zgrid[b0:b0 + 4], degree, GaussianKernel(0.2), 0.01, refit, o)
+        assert np.array_equal(o4[:, b0:b0 + 4] != 0, ob != 0)
+        assert np.max(np.abs(o4[:, b0:b0 + 4] - ob)) <= 1e-9 * np.max(np.abs(ob))
+        assert [(a["passes"], a["visits"]) for a in s4[b0:b0 + 4]] == [(b["passes"], b["visits"]) for b in ref.last_vc_stats]
+
+
 @pytest.mark.parametrize("form", ["quad", "ls"])
 @pytest.mark.parametrize("randomize", [0, 1])
 @pytest.mark.parametrize("engine", ["one_cta", "team"])
