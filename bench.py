@@ -275,6 +275,7 @@ def c4_data():
 
 
 C4_OPTTOL = 1e-9  # batch (cold starts) and the reference's warm-start chain agree to 1e-6 at this tolerance (tests/test_baseline_configs.py)
+C4_CHAIN = 2      # grid points per warm-started run (cdgpu_vc_solve_chain): 2048 runs still fill the GPU, every second point starts warm
 
 
 def c4_metrics(be, hbm, reps=3):
@@ -284,10 +285,14 @@ def c4_metrics(be, hbm, reps=3):
     X, Z, Y = c4_data()
     zgrid = np.linspace(0.01, 0.99, m)
     opt = CDOptions(randomize=False, optTol=C4_OPTTOL)
-    runs = []
+    runs, cold = [], []
+    for i in range(reps + 1):  # the batch with every grid point started from zero, for comparison
+        out_cold, _ = be.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.01, False, opt)
+        if i:
+            cold.append(be.last_vc_stats[0]["device_ms"])
     for i in range(reps + 1):
         t0 = time.perf_counter()
-        be.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.01, False, opt)
+        out_chain, _ = be.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.01, False, opt, chain=C4_CHAIN)
         wall = time.perf_counter() - t0
         if i:
             runs.append((be.last_vc_stats[0]["device_ms"], wall, be.last_vc_stats))
@@ -298,9 +303,12 @@ def c4_metrics(be, hbm, reps=3):
     ep = p * (degree + 1)
     alg = 8 * n * (p + 2) * m + 8 * n * visits  # 8n(p+2) per local problem + 8n per visit
     tr = NCU_TRAFFIC.get("vc_cov_kernel_c4", (None, None))
-    return {"workload": f"C4 locpolyl1: {m} grid points, n={n} p={p} degree={degree} (ep={ep}), Gaussian h=0.2, lambda0=0.01, optTol={C4_OPTTOL}",
+    return {"workload": f"C4 locpolyl1: {m} grid points, n={n} p={p} degree={degree} (ep={ep}), Gaussian h=0.2, lambda0=0.01, optTol={C4_OPTTOL}, "
+                        f"warm-start chain cut into runs of {C4_CHAIN} grid points",
             "kernels": "vc_build_z/v + gram_syrk_kernel<GEMM> (all local Grams as one DMMA GEMM) + vc_cov_kernel",
             "device_ms": dev, "device_ms_runs": [r[0] for r in runs], "wall_ms_incl_h2d_d2h": 1e3 * wall,
+            "cold_batch_device_ms": float(np.mean(cold)), "cold_batch_device_ms_runs": cold,
+            "max_rel_diff_chain_vs_cold_batch": float(np.max(np.abs(out_chain - out_cold)) / np.max(np.abs(out_cold))),
             "problems_per_sec": m / (dev * 1e-3), "problems_per_sec_e2e": m / wall, "visits": visits,
             "all_converged": all(s["converged"] for s in stats),
             "roofline": {"bound": "hbm", "achieved": alg / (dev * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
@@ -432,15 +440,15 @@ def sharded_metrics(be, args, rank, world, local, hbm):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if world > 1:
-            full = locpolyl1_sharded(be, Xc, Zc, Yc, zgrid, 2, GaussianKernel(0.2), 0.01, opt)
+            full = locpolyl1_sharded(be, Xc, Zc, Yc, zgrid, 2, GaussianKernel(0.2), 0.01, opt, chain=C4_CHAIN)
         else:
-            full, _ = be.locpolyl1(Xc, Zc, Yc, zgrid, 2, GaussianKernel(0.2), 0.01, False, opt)
+            full, _ = be.locpolyl1(Xc, Zc, Yc, zgrid, 2, GaussianKernel(0.2), 0.01, False, opt, chain=C4_CHAIN)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         if rep:
             recs.append((be.last_vc_stats[0]["device_ms"], 1e3 * wall))
     dev, wall = mx(float(np.mean([r[0] for r in recs])), float(np.mean([r[1] for r in recs])))
-    out["c4_vc_lasso"] = {"workload": f"C4 locpolyl1 {m} grid points (n=500 p=50 degree=2) dealt round-robin over {world} GPU(s); optTol={C4_OPTTOL}",
+    out["c4_vc_lasso"] = {"workload": f"C4 locpolyl1 {m} grid points (n=500 p=50 degree=2) in warm-started runs of {C4_CHAIN}, the runs dealt round-robin over {world} GPU(s); optTol={C4_OPTTOL}",
                           "scaling": "strong", "device_ms": dev, "wall_ms_incl_copies_and_gather": wall,
                           "problems_per_sec": m / (dev * 1e-3), "problems_per_sec_e2e": m / (wall * 1e-3),
                           "coef_checksum": float(np.sum(np.abs(full))), "nnz": int(np.count_nonzero(full)),

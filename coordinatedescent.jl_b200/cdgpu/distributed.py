@@ -23,29 +23,41 @@ def shard_range(m: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def locpolyl1_sharded(be: Backend, X, z, y, zgrid, degree, kernel, λ0, options=None, group=None, interleave=True):
+def locpolyl1_sharded(be: Backend, X, z, y, zgrid, degree, kernel, λ0, options=None, group=None, interleave=True, chain=1):
     """locpolyl1 with the grid points split over the ranks of `group`; every rank returns the full
     ep x m matrix (all_gather of the owned columns).  No data-path collective: the local problems are
     independent.  `interleave=True` deals the grid points round-robin (rank r owns zgrid[r::world]):
     neighbouring grid points cost about the same number of passes, so the ranks finish together;
-    `interleave=False` gives every rank one contiguous block ([m_begin, m_end) of the C ABI)."""
+    `interleave=False` gives every rank one contiguous block ([m_begin, m_end) of the C ABI).  `chain` > 1: the units
+    dealt are runs of `chain` consecutive grid points, each run warm-started point to point (cdgpu_vc_solve_chain), so
+    the result does not depend on the number of ranks."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     zgrid = f64(zgrid)
     m = zgrid.size
+    chain = max(1, int(chain))
+
+    def owned(r):  # grid points of rank r when runs of `chain` points are dealt round-robin
+        runs = np.arange(r, -(-m // chain), world)
+        idx = (runs[:, None] * chain + np.arange(chain)[None, :]).ravel()
+        return idx[idx < m]
+
     if interleave:
-        mine_idx = np.arange(rank, m, world)
-        out, _ = be.locpolyl1(X, z, y, np.ascontiguousarray(zgrid[mine_idx]), degree, kernel, λ0, False, options)
+        mine_idx = owned(rank)
+        out, _ = be.locpolyl1(X, z, y, np.ascontiguousarray(zgrid[mine_idx]), degree, kernel, λ0, False, options,
+                              chain=chain if chain > 1 else None)
         cols = out
     else:
+        if chain > 1:
+            raise ValueError("chain > 1 needs interleave=True (runs are the units dealt)")
         lo, hi = shard_range(m, rank, world)
         out, _ = be.locpolyl1(X, z, y, zgrid, degree, kernel, λ0, False, options, shard=(lo, hi))
         cols = out[:, lo:hi]
     ep = out.shape[0]
     # gather variable-sized column blocks: pad to the largest block
-    width = -(-m // world)
+    width = max(owned(r).size for r in range(world)) if interleave else -(-m // world)
     mine = torch.zeros(width * ep, dtype=torch.float64)
     mine[: cols.shape[1] * ep] = torch.from_numpy(np.ascontiguousarray(cols.T).ravel())
     backend = dist.get_backend(group)
@@ -56,7 +68,7 @@ def locpolyl1_sharded(be: Backend, X, z, y, zgrid, degree, kernel, λ0, options=
     full = np.zeros((ep, m), order="F")
     for r, t in enumerate(parts):
         if interleave:
-            idx = np.arange(r, m, world)
+            idx = owned(r)
             full[:, idx] = t.cpu().numpy()[: idx.size * ep].reshape(idx.size, ep).T
         else:
             a, b = shard_range(m, r, world)

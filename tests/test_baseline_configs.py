@@ -127,7 +127,8 @@ def test_c4_locpolyl1_batch_matches_the_chained_reference(gpu, ref):
     m = 4096
     zgrid = np.linspace(0.01, 0.99, m)
     out, _ = gpu.locpolyl1(X, Z, Y, zgrid, 2, GaussianKernel(0.2), 0.01, False, C4_OPT)
-    assert all(s["converged"] for s in gpu.last_vc_stats)
+    gpu_cold_stats = gpu.last_vc_stats
+    assert all(s["converged"] for s in gpu_cold_stats)
     sub = np.ascontiguousarray(zgrid[::32])
     outr, _ = ref.locpolyl1(X, Z, Y, sub, 2, GaussianKernel(0.2), 0.01, False, C4_OPT)
     g = out[:, ::32]
@@ -137,6 +138,16 @@ def test_c4_locpolyl1_batch_matches_the_chained_reference(gpu, ref):
     for j in (0, 31, 77, 127):
         o1, _ = ref.locpolyl1(X, Z, Y, sub[j:j + 1], 2, GaussianKernel(0.2), 0.01, False, C4_OPT)
         assert np.array_equal(g[:, j] != 0, o1[:, 0] != 0) and np.max(np.abs(g[:, j] - o1[:, 0])) <= 1e-9 * np.max(np.abs(o1))
+    # the bench's C4 leg: the chain cut into runs of two grid points (cdgpu_vc_solve_chain).  The first 64 grid points
+    # against the oracle running the same 32 runs: same supports, passes and visits; the whole grid against the cold batch
+    oc, _ = gpu.locpolyl1(X, Z, Y, zgrid, 2, GaussianKernel(0.2), 0.01, False, C4_OPT, chain=2)
+    sc = gpu.last_vc_stats
+    assert all(s["converged"] for s in sc)
+    assert np.array_equal(oc != 0, out != 0) and np.max(np.abs(oc - out)) <= 1e-6 * np.max(np.abs(out))
+    orc, _ = ref.locpolyl1(X, Z, Y, zgrid[:64], 2, GaussianKernel(0.2), 0.01, False, C4_OPT, chain=2)
+    assert np.array_equal(oc[:, :64] != 0, orc != 0) and np.max(np.abs(oc[:, :64] - orc)) <= 1e-9 * np.max(np.abs(orc))
+    assert [(a["passes"], a["visits"]) for a in sc[:64]] == [(b["passes"], b["visits"]) for b in ref.last_vc_stats]
+    assert sum(a["passes"] for a in sc) < 0.75 * sum(a["passes"] for a in gpu_cold_stats)
 
 
 def test_c5_tall_gram_row_subsample_then_path(gpu, ref):

@@ -48,6 +48,12 @@ def _worker(rank, world, port, q):
     oc = CDOptions(randomize=False, warmStart=False, optTol=1e-10, maxIter=20000)
     mse_sharded = lvocv_locpolyl1_sharded(ref, X[:60], Z[:60], Y[:60], degree, hs, GaussianKernel, 0.3, oc)
     mse_whole = ref.lvocv_locpolyl1(X[:60], Z[:60], Y[:60], degree, hs, GaussianKernel, 0.3, oc)
+    # runs of two warm-started grid points (cdgpu_vc_solve_chain) dealt over the ranks: the same runs as in one process,
+    # so the result is identical even at a loose tolerance (9 grid points: the last run has one)
+    ol = CDOptions(randomize=False, optTol=1e-4, maxIter=20000)
+    chained = locpolyl1_sharded(ref, X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.02, ol, chain=2)
+    chained_whole, _ = ref.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.02, False, ol, chain=2)
+    assert np.array_equal(chained, chained_whole)
     err = max(float(np.max(np.abs(full - whole))), float(np.max(np.abs(blocks - whole))),
               float(np.max(np.abs(mse_sharded - mse_whole) / mse_whole)))
     q.put((rank, err, int(np.count_nonzero(whole))))
