@@ -177,8 +177,8 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   const size_t o_beta = take(p * sizeof(double)), o_act = take(p * sizeof(int)), o_actval = take(p * sizeof(double)),
                o_nact = take(sizeof(int)), o_inlist = take(p), o_omega = take(p * sizeof(double)),
                o_scr = take((cd_scr_tail(p, (size_t)h->n) + 16 * p + 8 + 32) * sizeof(double)),
-               o_iscr = take((10 * p + 64 + 3 * 512 + 8) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(16 * sizeof(int)),
-               o_chain = take(CD_MULTI_SCR_BYTES);
+               o_iscr = take((10 * p + 64 + 4 * 512 + 32) * sizeof(int)), o_bscr = take(4 * p + 64), o_flag = take(16 * sizeof(int)),
+               o_chain = take(CD_MULTI_SCR_BYTES), o_rsnap = take(2 * (size_t)(h->n > 0 ? h->n : 0) * sizeof(double) + 16);
   CD_TRY(dalloc(&h->dcommon, off));
   unsigned char *base = h->dcommon;
   h->dbeta = (double *)(base + o_beta);
@@ -192,6 +192,7 @@ static int handle_common_alloc(cdgpu_handle_s *h) {
   h->dbscr = base + o_bscr;
   h->dflag = (int *)(base + o_flag);
   h->dchain = (double *)(base + o_chain);
+  h->drsnap = (double *)(base + o_rsnap);
   CUDA_TRY(cudaMemsetAsync(h->dbeta, 0, p * sizeof(double), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dinlist, 0, p, h->stream));
   CUDA_TRY(cudaMemsetAsync(h->dnact, 0, sizeof(int), h->stream));
@@ -1361,6 +1362,9 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     if (const char *env = getenv("CDGPU_NAIVE_PIPELINE")) a.pipeline = atoi(env) != 0;
     a.plan = 1;
     if (const char *env = getenv("CDGPU_NAIVE_PLAN")) a.plan = atoi(env) != 0;
+    a.rsnap = h->drsnap;
+    a.dense = 1;
+    if (const char *env = getenv("CDGPU_NAIVE_DENSE")) a.dense = atoi(env) != 0;
     a.replan = 0; // only in builds with -DCDGPU_WITH_REPLAN (naive_sweep.cu: full_pass)
     if (const char *env = getenv("CDGPU_NAIVE_REPLAN")) a.replan = atoi(env) != 0;
     a.scaled = rc.scaled;

@@ -255,6 +255,7 @@ struct cdgpu_handle_s {
   double *dnzval = nullptr;
   int64_t outcap = 0, outcols = 0;
   int *dflag = nullptr;             // device status word(s)
+  double *drsnap = nullptr;         // NaiveArgs::rsnap
   double *dchain = nullptr;         // scratch of the team chain engine (chain_engine.cuh: Multi::hpass, Multi::seq)
   double gram_ms = 0.0;
   int sm_count = 0, max_cluster = 0;
@@ -422,6 +423,8 @@ struct NaiveArgs {
   int pipeline;    // split-phase rounds of the full pass (CDGPU_NAIVE_PIPELINE=0 disables)
   int plan;        // members' steps of a full pass planned by one chain pass (CDGPU_NAIVE_PLAN=0 disables)
   double *chain_scr; // CD_MULTI_SCR_BYTES of global scratch for the team chain engine
+  double *rsnap;   // 2n doubles: r at the start of a planned super-window of the full pass (two buffers)
+  int dense;       // dense mode of the full pass: segments planned over members + candidates (CDGPU_NAIVE_DENSE=0 disables)
   int replan;      // members still to come are planned again after an entering coordinate moved (-DCDGPU_WITH_REPLAN builds, CDGPU_NAIVE_REPLAN=1)
 };
 // offset (doubles, even) of the tail of a handle's scratch: 16p doubles for the result buffers of the full-pass rounds

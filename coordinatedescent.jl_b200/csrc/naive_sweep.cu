@@ -268,9 +268,10 @@ __device__ __forceinline__ void apply_step(NCtx &c, const double *col, double h)
   }
 }
 
-// r -= sum_t X[:, k_t] h_t over the planned members t in [t0, t1) (consecutive visit positions), element by element in
-// visit order with the same non-fused operations as one apply_step per member; ||r||^2 refreshed as apply_step does.
-__device__ void apply_planned(NCtx &c, int t0, int t1, double &maxH, long long &accepted) {
+// r -= sum_t X[:, k_t] h_t over the planned entries t in [t0, t1) (increasing visit positions), element by element in
+// visit order with the same non-fused operations as one apply_step per entry; ||r||^2 refreshed as apply_step does.
+// Touches this CTA's r only: the iterate and the list are written by commit_planned once the steps are final.
+__device__ void apply_planned_r(NCtx &c, int t0, int t1) {
   const NaiveArgs &a = c.a;
   const int n = a.n, tid = threadIdx.x;
   for (int i0 = tid; i0 < n; i0 += 2 * NV_T) {
@@ -314,26 +315,43 @@ __device__ void apply_planned(NCtx &c, int t0, int t1, double &maxH, long long &
     c.rr = block_sum(c.sm, acc, 0);
     __syncthreads();
   }
+}
+// the planned entries [t0, t1) are final: statistics (every CTA), the dense iterate and the list (CTA 0)
+__device__ void commit_planned(NCtx &c, int t0, int t1, double &maxH, long long &accepted) {
+  const NaiveArgs &a = c.a;
+  const int tid = threadIdx.x;
   for (int t = t0; t < t1; ++t) {
     const double h = c.e_g[t];
     maxH = fmax(maxH, fabs(h));
     accepted += h != 0.0;
   }
-  if (c.bid == 0)
+  if (c.bid == 0) {
     for (int t = t0 + tid; t < t1; t += NV_T)
       if (c.e_g[t] != 0.0) __stcg(a.beta + c.e_coord[t], c.e_be[t]);
+    if (tid == 0) // dense mode plans candidates too: a non-member that moves is appended (setindex!), in visit order
+      for (int t = t0; t < t1; ++t) {
+        const int k = c.e_coord[t];
+        if (c.e_g[t] != 0.0 && !a.inlist[k]) {
+          __stcg(a.inlist + k, (unsigned char)1);
+          a.act[c.sm->nact] = k;
+          c.sm->nact += 1;
+        }
+      }
+  }
 }
 
 // plan arrays in global memory (CTA 0 writes, everybody copies them to shared memory)
 struct NPlan {
   int *k, *pos, *row; // coordinate, visit position, list index (= row of the active Gram) of the t-th visited member
-  double *h, *nw;
+  int *ext;           // dense mode: the coordinates planned for a segment of a full pass (members + candidates), NV_PLAN_MAX
+  double *h, *nw;     // (row[512] = leading dimension of G, row[513] = entries in ext, row[514] = ext was truncated)
 };
 __device__ __forceinline__ NPlan plan_arrays(const NaiveArgs &a) {
   NPlan P;
   P.k = a.iscr + 10 * (long long)a.p + 64; // 3 x NV_PLAN_MAX ints behind the sweep's scratch ints (handle_common_alloc)
   P.pos = P.k + 512;
   P.row = P.pos + 512;
+  P.ext = P.row + 520;
   P.h = a.scr + 8 + 9 * (long long)a.p + 32 + 2 * NV_GCAP_;
   P.nw = P.h + NV_GCAP_;
   return P;
@@ -413,14 +431,14 @@ struct NWin {
 
 // evaluate the columns of a window against the current r: tentative (h, new value) per position, first mover by atomicMin
 __device__ __forceinline__ void eval_window(NCtx &c, const NWin &wn, double lam, const PermKey &pk, bool ordered,
-                                            unsigned int *words, int *nonapp_flags) {
+                                            unsigned int *words, int *nonapp_flags, int ja, int jb, bool warp_mode) {
   const NaiveArgs &a = c.a;
   NSmem *sm = c.sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   HEntry *hb = c.hbuf + (size_t)wn.slot * c.CH;
   unsigned int *gmin = words + wn.slot;
   int *nonapp_flag = nonapp_flags + wn.slot;
-  if (wn.cta) { // CTA-per-column mode
+  if (wn.cta && !warp_mode) { // CTA-per-column mode
     const int j = c.bid;
     if (j < wn.qlen) {
       const int k = ordered ? wn.q0 + j : (int)cd_perm(pk, (uint32_t)(wn.q0 + j));
@@ -451,8 +469,9 @@ __device__ __forceinline__ void eval_window(NCtx &c, const NWin &wn, double lam,
     }
     return;
   }
-  // position j of the window belongs to CTA j % G, warp (j / G) % NV_W
-  for (int j = c.bid + c.G * warp; j < wn.qlen; j += c.G * NV_W) {
+  // position j of the window belongs to CTA j % G, warp (j / G) % NV_W; [ja, jb): the part of the window evaluated now
+  const int stride = c.G * NV_W, jw = c.bid + c.G * warp;
+  for (int j = ja <= jw ? jw : jw + (ja - jw + stride - 1) / stride * stride; j < jb; j += stride) {
     const int k = ordered ? wn.q0 + j : (int)cd_perm(pk, (uint32_t)(wn.q0 + j));
     const double d = warp_col_dot(c, a.X + (long long)k * a.ldx);
     if (lane == 0) {
@@ -478,8 +497,19 @@ __device__ __forceinline__ void eval_window(NCtx &c, const NWin &wn, double lam,
 // and never cross a planned position.  A non-member that does move voids the rest of the plan: the remaining members
 // are then evaluated like any other column.  c.e_coord / e_row / e_g / e_be (idle during a full pass) hold the plan:
 // coordinate, visit position, h, new value, in visit order.
+// DENSE MODE (mover-dense passes: cold starts, small penalties).  A pass is cut into SEGMENTS.  Before a segment the grid
+// evaluates every remaining column once against the current r (dense_prescan) and the plan holds, next to the members,
+// the CANDIDATES: non-members that would move at 0.9 lambda; one chain pass over the Gram of members + candidates gives
+// all their steps (a candidate that does not move after all gets h = 0 and is not appended).  The segment ends — and the
+// rest of the pass is planned again from the position reached (`q_resume` < p) — when a coordinate outside the plan moves
+// and enough of the plan is left, or when a truncated plan (more than NV_PLAN_MAX entries) is used up.  Same iterates
+// and list order as the one-round-per-mover pass: planned or not, every coordinate is updated at its visit position
+// with the step the sequential algorithm takes there.
+constexpr int NV_DENSE_MIN_LEFT = 12; // planned entries left that make a new plan cheaper than a round each
+constexpr int NV_DENSE_EVENTS = 4;    // ... or this many unplanned movers since the segment started
 __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter, long long &accepted, long long *pf,
-                            int nact_hint, int mP) {
+                            int nact_hint, int mP, int q_start, bool dense, bool truncated, int &q_resume, int &events,
+                            int &plan_used, int &plan_moved) {
   const NaiveArgs &a = c.a;
   NSmem *sm = c.sm;
   const int tid = threadIdx.x;
@@ -509,8 +539,13 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
   };
   const bool pipeline = a.pipeline != 0;
   int Wnext = (nact_hint > 0 && mP == 0) ? min(c.CH, c.G) : Wwarp;
-  int q0 = 0, streak = mP > 0 ? 2 : 0; // with a plan the sweep is expected to be clean: pipelined from the first window
+  int q0 = q_start, streak = mP > 0 ? 2 : 0; // with a plan the sweep is expected to be clean: pipelined from the first window
   int pi = 0;                          // next planned member
+  int seg_events = 0;                  // unplanned movers of this segment
+  bool sw = false;                     // `pend` is a planned super-window: entries [pi, sw_pj) applied to r, not yet committed
+  int sw_pj = 0;
+  double *sw_snap = nullptr, sw_rr = 0.0; // r and ||r||^2 at its start
+  q_resume = a.p;
 #ifdef CDGPU_WITH_REPLAN
   int replans = 0;                     // plans redone in this pass
 #endif
@@ -520,27 +555,59 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     long long ta = clock64();
     if (!have_pend) {
       if (q0 >= a.p) break;
-      if (pi < mP && c.e_row[pi] == q0) { // a run of planned members at consecutive positions: one fused update of r
-        int pj = pi + 1;
-        while (pj < mP && c.e_row[pj] == q0 + (pj - pi)) ++pj;
-        apply_planned(c, pi, pj, maxH, accepted);
-        q0 += pj - pi;
-        pi = pj;
-        pf[3] += clock64() - ta;
-        continue;
+      if (dense && truncated && mP > 0 && pi == mP) { // the plan stopped at NV_PLAN_MAX entries: plan the rest
+        q_resume = q0;
+        break;
       }
-      pend = make(q0, Wnext);
-      if (pi < mP) pend.qlen = min(pend.qlen, c.e_row[pi] - q0);
-      eval_window(c, pend, lam, pk, ordered, words, nonapp_flags);
-      if (pend.cta) round_arrive_cta(c); else round_arrive_warp(c);
-      have_pend = true;
+      if (pi < mP) {
+        // PLANNED SUPER-WINDOW: up to CH positions, planned and not, in ONE round.  Every CTA walks the window in visit
+        // order on its own copy of r: the columns of a gap between planned positions are evaluated (one warp each)
+        // against r as it stands there, then the planned run behind the gap is applied — no grid barrier per gap,
+        // only two CTA barriers.  The iterate and the list are written once the round is known to be clean
+        // (commit_planned); if an unplanned coordinate of the window does move, r is restored from the snapshot CTA 0
+        // took at the start (global memory, two buffers) and the planned steps before the mover are replayed: the same
+        // operations in the same order, so r is bit for bit what the one-round-per-mover pass has there.
+        pend = make(q0, c.CH);
+        pend.cta = true; // CTA-wide barrier, no speculative next window
+        HEntry *hbw = c.hbuf + (size_t)pend.slot * c.CH;
+        sw_snap = a.rsnap + (size_t)(pend.slot & 1) * a.n;
+        sw_rr = c.rr;
+        if (c.bid == 0)
+          for (int i = tid; i < a.n; i += NV_T) __stcg(sw_snap + i, c.r[i]);
+        int pj = pi, ja = 0;
+        while (ja < pend.qlen) {
+          const int jb = (pj < mP && c.e_row[pj] - q0 < pend.qlen) ? c.e_row[pj] - q0 : pend.qlen;
+          if (jb > ja) eval_window(c, pend, lam, pk, ordered, words, nonapp_flags, ja, jb, true);
+          if (jb < pend.qlen) { // the run of planned entries at consecutive positions starting at jb
+            int pk2 = pj + 1;
+            while (pk2 < mP && c.e_row[pk2] == c.e_row[pj] + (pk2 - pj) && c.e_row[pk2] - q0 < pend.qlen) ++pk2;
+            if (c.bid == 0)
+              for (int t = pj + tid; t < pk2; t += NV_T) __stcg(&hbw[c.e_row[t] - q0].app, 1); // (not a window entry)
+            __syncthreads(); // every warp has finished reading r for the gap
+            apply_planned_r(c, pj, pk2);
+            ja = jb + (pk2 - pj);
+            pj = pk2;
+          } else {
+            ja = jb;
+          }
+        }
+        sw_pj = pj;
+        sw = true;
+        round_arrive_cta(c);
+        have_pend = true;
+      } else {
+        pend = make(q0, Wnext);
+        eval_window(c, pend, lam, pk, ordered, words, nonapp_flags, 0, pend.qlen, false);
+        if (pend.cta) round_arrive_cta(c); else round_arrive_warp(c);
+        sw = false;
+        have_pend = true;
+      }
     }
     // the next window, on the assumption that `pend` turns out clean: evaluated while barrier `pend` completes
     bool have_spec = false;
-    if (pipeline && streak >= 2 && !pend.cta && pend.q0 + pend.qlen < a.p && !(pi < mP && c.e_row[pi] == pend.q0 + pend.qlen)) {
+    if (pipeline && streak >= 2 && !pend.cta && pend.q0 + pend.qlen < a.p && pi >= mP) {
       spec = make(pend.q0 + pend.qlen, grow(pend));
-      if (pi < mP) spec.qlen = min(spec.qlen, c.e_row[pi] - spec.q0);
-      eval_window(c, spec, lam, pk, ordered, words, nonapp_flags);
+      eval_window(c, spec, lam, pk, ordered, words, nonapp_flags, 0, spec.qlen, false);
       have_spec = true;
     }
     const long long tb = clock64();
@@ -566,6 +633,13 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     const long long td = clock64();
     pf[2] += td - tc;
     if (jmin == 0xffffffffu) { // clean round: every position of the window is final
+      if (sw) {
+        commit_planned(c, pi, sw_pj, maxH, accepted);
+        for (int t = pi; t < sw_pj; ++t) plan_moved += c.e_g[t] != 0.0;
+        plan_used += sw_pj - pi;
+        pi = sw_pj;
+        sw = false;
+      }
       q0 = pend.q0 + pend.qlen;
       Wnext = grow(pend);
       streak += 1;
@@ -581,6 +655,22 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     const int k = ordered ? pend.q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(pend.q0 + jmin));
     const double2 e = __ldcg(reinterpret_cast<const double2 *>(hb + jmin));
     const double h = e.x, nw = e.y;
+    if (sw) { // an unplanned coordinate of a super-window moved: the planned entries before it stand, the rest is undone
+      int pc = pi;
+      while (pc < sw_pj && c.e_row[pc] < pend.q0 + (int)jmin) ++pc;
+      if (pc < sw_pj) {
+        __syncthreads();
+        for (int i = tid; i < a.n; i += NV_T) c.r[i] = __ldcg(sw_snap + i);
+        c.rr = sw_rr;
+        __syncthreads();
+        if (pc > pi) apply_planned_r(c, pi, pc);
+      }
+      commit_planned(c, pi, pc, maxH, accepted);
+      for (int t = pi; t < pc; ++t) plan_moved += c.e_g[t] != 0.0;
+      plan_used += pc - pi;
+      pi = pc;
+      sw = false;
+    }
     if (!pend.cta) __syncthreads(); // warp-granular round: the other warps may still be reading r
     if (c.bid == 0 && tid == 0) {
       __stcg(a.beta + k, nw);
@@ -621,10 +711,70 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
       pf[8] += clock64() - tr0;
     } else
 #endif
+    {
+      seg_events += 1;
+      events += 1;
+      if (dense && a.p - q0 >= 64 && (mP - pi >= NV_DENSE_MIN_LEFT || seg_events >= NV_DENSE_EVENTS)) {
+        q_resume = q0; // a new segment: plan the rest of the pass against the current r
+        break;
+      }
       mP = 0;
+    }
   }
   __syncthreads(); // warps of a warp-granular round leave together
   return maxH;
+}
+
+// dense mode, every CTA: bscr[q] for the visit positions q >= q0 of the pass: 1 = the coordinate is listed, 2 = a
+// non-member that would move against the CURRENT r at 0.9 lambda (a candidate), 0 = neither
+__device__ void dense_prescan(NCtx &c, double lam, const PermKey &pk, bool ordered, int q0) {
+  const NaiveArgs &a = c.a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = q0 + c.bid + c.G * warp; q < a.p; q += c.G * NV_W) {
+    const int k = ordered ? q : (int)cd_perm(pk, (uint32_t)q);
+    unsigned char f = 1;
+    if (!__ldcg(a.inlist + k)) {
+      const double d = warp_col_dot(c, a.X + (long long)k * a.ldx);
+      double nw, h;
+      bool tnz;
+      coord_update(a.kind, a.n, d, __ldg(a.colsq + k), __ldcg(a.beta + k), 0.9 * lam, a.omega ? __ldg(a.omega + k) : 1.0, c.rr,
+                   nw, h, tnz);
+      f = h != 0.0 ? 2 : 0;
+    }
+    if (lane == 0) __stcg(a.bscr + q, f);
+  }
+}
+
+// dense mode, CTA 0: the flagged positions from q0 on, in visit order, become the plan's coordinate list (at most `cap`)
+__device__ void dense_select(NCtx &c, const PermKey &pk, bool ordered, int q0, int cap) {
+  const NaiveArgs &a = c.a;
+  NSmem *sm = c.sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const NPlan PL = plan_arrays(a);
+  int cnt = 0;
+  for (int base = q0; base < a.p && cnt <= cap; base += NV_T) {
+    const int q = base + tid;
+    const bool f = q < a.p && __ldcg(a.bscr + q) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) sm->redu[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w2 = 0; w2 < NV_W; ++w2) {
+      const int v = (int)sm->redu[w2];
+      if (w2 < warp) off += v;
+      tot += v;
+    }
+    const int pos = cnt + off + __popc(bal & ((1u << lane) - 1u));
+    if (f && pos < cap) PL.ext[pos] = ordered ? q : (int)cd_perm(pk, (uint32_t)q);
+    cnt += tot;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    PL.row[513] = min(cnt, cap);
+    PL.row[514] = cnt > cap ? 1 : 0;
+  }
+  __threadfence();
+  __syncthreads();
 }
 
 // dropzeros! after a full pass on CTA 0: new entries go where the reference's temporary appends put
@@ -773,7 +923,7 @@ constexpr int NV_GCAP = NV_GCAP_; // largest active set handled this way (G scra
 __device__ __forceinline__ void nbar(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
 
 // all CTAs: G[i + j*m] = sum_t w_t X[t,act_i] X[t,act_j] (both triangles), d[i] = sum_t w_t r_t X[t,act_i]
-__device__ void build_active_gram(NCtx &c, int m, double *G, double *d) {
+__device__ void build_active_gram(NCtx &c, int m, double *G, double *d, const int *lst) {
   const NaiveArgs &a = c.a;
   const int lane = threadIdx.x & 31, n = a.n;
   const long long gw = (long long)c.bid * NV_W + (threadIdx.x >> 5), nw = (long long)c.G * NV_W;
@@ -781,7 +931,7 @@ __device__ void build_active_gram(NCtx &c, int m, double *G, double *d) {
   for (long long idx = gw; idx < npair + m; idx += nw) {
     if (idx >= npair) { // d entry
       const int i = (int)(idx - npair);
-      const double v = warp_col_dot(c, a.X + (long long)__ldcg(a.act + i) * a.ldx);
+      const double v = warp_col_dot(c, a.X + (long long)__ldcg(lst + i) * a.ldx);
       if (lane == 0) __stcg(d + i, v);
       continue;
     }
@@ -790,7 +940,7 @@ __device__ void build_active_gram(NCtx &c, int m, double *G, double *d) {
     while ((long long)i * (i + 1) / 2 > idx) --i;
     while ((long long)(i + 1) * (i + 2) / 2 <= idx) ++i;
     const int j = (int)(idx - (long long)i * (i + 1) / 2);
-    const double *ci = a.X + (long long)__ldcg(a.act + i) * a.ldx, *cj = a.X + (long long)__ldcg(a.act + j) * a.ldx;
+    const double *ci = a.X + (long long)__ldcg(lst + i) * a.ldx, *cj = a.X + (long long)__ldcg(lst + j) * a.ldx;
     double s0 = 0.0, s1 = 0.0;
     if (c.w) {
       int t = lane;
@@ -928,7 +1078,8 @@ struct SqrtPolicy { // :259-283 with s, ||r+||^2 from d, ||r||^2, a
 // CTA 0, before a full pass: the steps the m members will take when the pass reaches them, by ONE chain pass over the
 // active Gram G = X_A'[W]X_A and d = X_A'(w.r) (just formed by the grid) in the VISIT order of the full pass, on the
 // assumption that no non-member moves (full_pass drops the rest of the plan when one does).  Plan -> global memory.
-__device__ void member_plan(NCtx &c, double lam, unsigned long long pass_counter, int m, const double *G, const double *d0) {
+__device__ void member_plan(NCtx &c, double lam, unsigned long long pass_counter, int m, const double *G, const double *d0,
+                            const int *lst) {
   const NaiveArgs &a = c.a;
   NSmem *sm = c.sm;
   const int tid = threadIdx.x;
@@ -937,7 +1088,7 @@ __device__ void member_plan(NCtx &c, double lam, unsigned long long pass_counter
   const NPlan PL = plan_arrays(a);
   int *vis = c.e_coord; // visit position by list index (temporary)
   for (int i = tid; i < m; i += NV_T) {
-    const int k = a.act[i];
+    const int k = __ldcg(lst + i);
     vis[i] = ordered ? k : (int)cd_perm_inv(pk, (uint32_t)k);
   }
   __syncthreads();
@@ -952,12 +1103,12 @@ __device__ void member_plan(NCtx &c, double lam, unsigned long long pass_counter
   __syncthreads();
   for (int t = tid; t < m; t += NV_T) {
     const int i = c.e_row[t];
-    c.e_be[t] = a.actval[i];
+    c.e_be[t] = __ldcg(a.beta + __ldcg(lst + i)); // (the dense iterate is current; candidates: 0)
     c.e_g[t] = __ldcg(d0 + i);
   }
   __syncthreads();
   for (int t = tid; t < m; t += NV_T) {
-    const int k = a.act[c.e_row[t]];
+    const int k = __ldcg(lst + c.e_row[t]);
     c.e_coord[t] = k;
     PL.k[t] = k;
   }
@@ -1249,6 +1400,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
   if (a.prof && c.bid == 0 && tid < 22) a.prof[10 + tid] = 0;
   const long long t_start = clock64();
   int nact_hint = *a.nact; // every CTA's view of the list length (refreshed whenever CTA 0 publishes it)
+  int last_events = 0;     // unplanned movers of the last full pass (dense mode of the next one)
   bool hint_stale = false; // a full pass has run since the last refresh
   unsigned long long pass_counter = 0;
   DevStats st;
@@ -1280,33 +1432,71 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           st.full_passes += 1;
           st.visits += a.p;
           const int m_old = c.sm->nact; // CTA 0
-          int mP = 0;
-          if (a.plan && a.gram && c.gcap > 0) {
-            const long long tp0 = clock64();
-            if (hint_stale) { // the list may have changed in the full pass that ended the previous solve
-              fast_grid_sync(c);
-              nact_hint = __ldcg(&bc->nact);
-              hint_stale = false;
-            }
-            if (nact_hint >= 1 && nact_hint <= min(c.gcap, NV_PLAN_MAX)) {
-              double *Gs = a.gram, *ds = a.gram + (long long)a.gram_cap * a.gram_cap;
-              build_active_gram(c, nact_hint, Gs, ds);
-              fast_grid_sync(c);
-              if (c.bid == 0) member_plan(c, lam, pass_counter, nact_hint, Gs, ds);
-              fast_grid_sync(c);
-              mP = nact_hint;
-              const NPlan PL = plan_arrays(a);
-              for (int t = tid; t < mP; t += NV_T) {
-                c.e_coord[t] = __ldcg(PL.k + t);
-                c.e_row[t] = __ldcg(PL.pos + t);
-                c.e_g[t] = __ldcg(PL.h + t);
-                c.e_be[t] = __ldcg(PL.nw + t);
-              }
-              __syncthreads();
-            }
-            pf[8] += clock64() - tp0;
+          // dense mode (full_pass): when a pre-scan of the remaining columns is cheap (X stays in L2) or the last full
+          // pass had many unplanned movers
+          if (hint_stale && a.plan && a.gram && c.gcap > 0) { // the list may have changed in the full pass that ended the previous solve
+            fast_grid_sync(c);
+            nact_hint = __ldcg(&bc->nact);
+            hint_stale = false;
           }
-          const double maxH = full_pass(c, lam, pass_counter, st.accepted, pf, nact_hint, mP);
+          // X in L2 (a pre-scan costs about one round): an empty list (cold start: nothing else can be planned) or 8
+          // unplanned movers in the last full pass; X streamed from HBM: when those movers' rounds (~6 us each) cost
+          // more than twice the extra pass over X
+          const bool x_in_l2 = (long long)a.n * a.p * 8 <= (64ll << 20);
+          const bool dense = a.dense && a.plan && a.gram && c.gcap > 0 &&
+                             (x_in_l2 ? (nact_hint == 0 || last_events >= 8)
+                                      : (double)last_events * 3.0 > (double)a.n * (double)a.p * 1.6e-6);
+          const PermKey pk_pass = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
+          double maxH = 0.0;
+          int q_start = 0, events_pass = 0;
+          // entries per plan: a cold start begins small (against r = y almost every coordinate looks like a mover, and the
+          // first large steps change that), then the size follows how much of the last plan actually moved
+          int cap = nact_hint == 0 ? 32 : min(c.gcap, NV_PLAN_MAX);
+          for (;;) { // segments of the pass (one, unless dense mode plans again)
+            int mP = 0;
+            bool truncated = false;
+            if (a.plan && a.gram && c.gcap > 0) {
+              const long long tp0 = clock64();
+              double *Gs = a.gram, *ds = a.gram + (long long)a.gram_cap * a.gram_cap;
+              const NPlan PL = plan_arrays(a);
+              const int *lst = nullptr;
+              int mE = 0;
+              if (dense) {
+                dense_prescan(c, lam, pk_pass, a.randomize == 0, q_start);
+                fast_grid_sync(c);
+                if (c.bid == 0) dense_select(c, pk_pass, a.randomize == 0, q_start, cap);
+                fast_grid_sync(c);
+                mE = __ldcg(PL.row + 513);
+                truncated = __ldcg(PL.row + 514) != 0;
+                lst = PL.ext;
+              } else if (q_start == 0 && nact_hint >= 1 && nact_hint <= min(c.gcap, NV_PLAN_MAX)) {
+                mE = nact_hint;
+                lst = a.act;
+              }
+              if (mE >= 1) {
+                build_active_gram(c, mE, Gs, ds, lst);
+                fast_grid_sync(c);
+                if (c.bid == 0) member_plan(c, lam, pass_counter, mE, Gs, ds, lst);
+                fast_grid_sync(c);
+                mP = mE;
+                for (int t = tid; t < mP; t += NV_T) {
+                  c.e_coord[t] = __ldcg(PL.k + t);
+                  c.e_row[t] = __ldcg(PL.pos + t);
+                  c.e_g[t] = __ldcg(PL.h + t);
+                  c.e_be[t] = __ldcg(PL.nw + t);
+                }
+                __syncthreads();
+              }
+              pf[8] += clock64() - tp0;
+            }
+            int q_resume = a.p, used = 0, moved = 0;
+            maxH = fmax(maxH, full_pass(c, lam, pass_counter, st.accepted, pf, nact_hint, mP, q_start, dense, truncated, q_resume,
+                                        events_pass, used, moved));
+            if (q_resume >= a.p) break;
+            q_start = q_resume;
+            if (used > 0) cap = 2 * moved >= used ? min(min(c.gcap, NV_PLAN_MAX), 2 * cap) : (4 * moved < used ? max(32, cap / 2) : cap);
+          }
+          last_events = events_pass;
           hint_stale = true;
           const long long t1 = clock64();
           if (c.bid == 0) {
@@ -1333,7 +1523,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
           if (m_act >= 1 && m_act <= c.gcap && a.gram) {
             double *Gs = a.gram, *ds = a.gram + (long long)a.gram_cap * a.gram_cap;
             const long long tg0 = clock64();
-            build_active_gram(c, m_act, Gs, ds);
+            build_active_gram(c, m_act, Gs, ds, a.act);
             pf[9] += clock64() - tg0;
             if (c.bid == 0 && tid == 0) { // team-barrier counter of gram_engine_multi (behind hG, pmaxG, 2 flags)
               double *hG0 = a.scr + 8 + 9 * (long long)a.p + 32 + 4 * NV_GCAP + 8;
