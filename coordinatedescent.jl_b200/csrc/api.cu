@@ -1355,7 +1355,7 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     a.gram = getenv("CDGPU_NAIVE_NO_GRAM_ENGINE") ? nullptr : h->dgram;
     a.gram_cap = (int)gcap;
     if (const char *env = getenv("CDGPU_NAIVE_GCAP")) a.gram_cap = std::max(256, std::min((int)gcap, atoi(env))); // diagnostics
-    a.multi_ok = 384; // smallest active set handed to the 16-CTA team engine (below: chain-bound on one CTA anyway)
+    a.multi_ok = 192; // smallest active set handed to the 16-CTA team engine (C1 lambda=0.05, 230 entries: 5.9 -> 5.45 ms against 384)
     if (const char *env = getenv("CDGPU_MULTI_MIN")) a.multi_ok = std::max(64, atoi(env));
     if (const char *env = getenv("CDGPU_NAIVE_MULTI")) a.multi_ok = atoi(env) != 0 ? a.multi_ok : 0;
     a.pipeline = 1;

@@ -125,7 +125,12 @@ __device__ __forceinline__ void coord_update(int kind, int n, double d, double a
 // streaming 16-byte load that does not pollute L1 (each column is read once per visit)
 __device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
   double2 v;
+  // (a weak load, not .nc: the warp barriers that pin the issue order in warp_col_dot_t do not order read-only loads)
+#ifdef CDGPU_STREAM_NC
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+#else
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+#endif
   return v;
 }
 
@@ -133,9 +138,10 @@ __device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
 // warp): the next four loads are issued before the last four are consumed, so a warp has 2-4 KB in flight at every
 // moment whatever order the compiler gives the instructions (left alone it splits a batch of eight loads around the
 // first multiply-adds and the warp drains to zero loads in flight between batches: the streaming rounds of a full
-// pass ran 10 % slower after an unrelated change elsewhere in the kernel).  The tail (< 8 elements per lane) is one
-// batch of clamped loads, masked.  Summation order as in the plain loop: full batches alternate (s0,s1)/(s2,s3) over
-// u = 0..7, the tail adds to (s0,s1).  (Not a function call: a call in this kernel makes r a generic pointer and
+// pass ran 10 % slower after an unrelated change elsewhere in the kernel); a warp barrier behind each group of loads
+// pins that order for the assembler (weak loads: read-only ones may cross it).  The tail (<= 8 elements per lane) is
+// one batch of clamped loads, masked.  Summation order: full batches alternate (s0,s1)/(s2,s3) over u = 0..7, the tail
+// adds to (s0,s1).  (Not a function call: a call in this kernel makes r a generic pointer and
 // costs every phase 60 %, measured.)
 template <bool HASW>
 __device__ __forceinline__ double warp_col_dot_t(const NCtx &c, const double *col) {
@@ -165,30 +171,33 @@ __device__ __forceinline__ double warp_col_dot_t(const NCtx &c, const double *co
         }
       }
     };
-    if (i + 7 * 32 < np) {
+    const int nb = np >> 8; // batches of 256 double2 that every lane takes in full (warp-uniform: the barriers below)
+    if (nb > 0) {
       double2 xa[4], xb[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) xa[u] = ldg_stream2(c2 + i + 32 * u);
-      for (;;) {
+      for (int bt = 0; bt < nb; ++bt) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) xb[u] = ldg_stream2(c2 + i + 128 + 32 * u);
+        __syncwarp(); // scheduling fence: the four loads above are issued before anything below
         consume4(xa, i);
-        const bool more = i + 256 + 7 * 32 < np;
-        if (more) {
+        // the first half of the next batch; behind the last batch the same addresses once more (an L1/L2 hit, never
+        // used): a conditional load would be a predicated load into temporaries that are copied at once — a stall for
+        // the full memory latency right behind the issue
+        const int nx = bt + 1 < nb ? i + 256 : i;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) xa[u] = ldg_stream2(c2 + i + 256 + 32 * u);
-        }
+        for (int u = 0; u < 4; ++u) xa[u] = ldg_stream2(c2 + nx + 32 * u);
+        __syncwarp();
         consume4(xb, i + 128);
         i += 256;
-        if (!more) break;
       }
     }
-    if (i < np) { // tail: at most 7 elements per lane
-      double2 xt[7];
+    if (i < np) { // tail: at most 8 elements per lane
+      double2 xt[8];
 #pragma unroll
-      for (int u = 0; u < 7; ++u) xt[u] = ldg_stream2(c2 + min(i + 32 * u, np - 1));
+      for (int u = 0; u < 8; ++u) xt[u] = ldg_stream2(c2 + min(i + 32 * u, np - 1));
 #pragma unroll
-      for (int u = 0; u < 7; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int j = i + 32 * u;
         if (j < np) {
           const double2 rv = r2[j];
@@ -507,6 +516,10 @@ __device__ __forceinline__ void eval_window(NCtx &c, const NWin &wn, double lam,
 // with the step the sequential algorithm takes there.
 constexpr int NV_DENSE_MIN_LEFT = 12; // planned entries left that make a new plan cheaper than a round each
 constexpr int NV_DENSE_EVENTS = 4;    // ... or this many unplanned movers since the segment started
+// (DENSE is a template parameter of the path kernel: problems whose X stays in L2 get the instance with dense mode and
+// super-windows; everything else gets the instance without that code — merely compiling it into the kernel cost the
+// HBM-bound streaming rounds 10 %, at C3 1.44 -> 1.59 ms, through register allocation.)
+template <bool DENSE>
 __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter, long long &accepted, long long *pf,
                             int nact_hint, int mP, int q_start, bool dense, bool truncated, int &q_resume, int &events,
                             int &plan_used, int &plan_moved) {
@@ -555,12 +568,32 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     long long ta = clock64();
     if (!have_pend) {
       if (q0 >= a.p) break;
-      if (dense && truncated && mP > 0 && pi == mP) { // the plan stopped at NV_PLAN_MAX entries: plan the rest
+      if (DENSE && dense && truncated && mP > 0 && pi == mP) { // the plan stopped at `cap` entries: plan the rest
         q_resume = q0;
         break;
       }
-      if (pi < mP) {
-        // PLANNED SUPER-WINDOW: up to CH positions, planned and not, in ONE round.  Every CTA walks the window in visit
+      // a super-window pays when at least 8 planned entries lie among the next CH positions: every gap then saves a
+      // grid barrier; a sparser plan keeps the pipelined windows
+      constexpr int sw_min = 8;
+      int planned_near = 0;
+      if (DENSE)
+        for (int t = pi; t < mP && planned_near < sw_min && c.e_row[t] < q0 + c.CH; ++t) planned_near += 1;
+      if (pi < mP && planned_near < sw_min && c.e_row[pi] == q0) {
+        // sparse plan (a few members in a long streaming pass): a run of planned entries at consecutive positions is
+        // one fused update of r between two ordinary windows
+        int pj = pi + 1;
+        while (pj < mP && c.e_row[pj] == q0 + (pj - pi)) ++pj;
+        apply_planned_r(c, pi, pj);
+        commit_planned(c, pi, pj, maxH, accepted);
+        for (int t = pi; t < pj; ++t) plan_moved += c.e_g[t] != 0.0;
+        plan_used += pj - pi;
+        q0 += pj - pi;
+        pi = pj;
+        pf[3] += clock64() - ta;
+        continue;
+      }
+      if (DENSE && pi < mP && planned_near >= sw_min) {
+        // PLANNED SUPER-WINDOW (dense plan): up to CH positions, planned and not, in ONE round.  Every CTA walks the window in visit
         // order on its own copy of r: the columns of a gap between planned positions are evaluated (one warp each)
         // against r as it stands there, then the planned run behind the gap is applied — no grid barrier per gap,
         // only two CTA barriers.  The iterate and the list are written once the round is known to be clean
@@ -597,6 +630,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
         have_pend = true;
       } else {
         pend = make(q0, Wnext);
+        if (pi < mP) pend.qlen = min(pend.qlen, c.e_row[pi] - q0); // windows never cross a planned position
         eval_window(c, pend, lam, pk, ordered, words, nonapp_flags, 0, pend.qlen, false);
         if (pend.cta) round_arrive_cta(c); else round_arrive_warp(c);
         sw = false;
@@ -605,8 +639,9 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     }
     // the next window, on the assumption that `pend` turns out clean: evaluated while barrier `pend` completes
     bool have_spec = false;
-    if (pipeline && streak >= 2 && !pend.cta && pend.q0 + pend.qlen < a.p && pi >= mP) {
+    if (pipeline && streak >= 2 && !pend.cta && pend.q0 + pend.qlen < a.p && !(pi < mP && c.e_row[pi] == pend.q0 + pend.qlen)) {
       spec = make(pend.q0 + pend.qlen, grow(pend));
+      if (pi < mP) spec.qlen = min(spec.qlen, c.e_row[pi] - spec.q0);
       eval_window(c, spec, lam, pk, ordered, words, nonapp_flags, 0, spec.qlen, false);
       have_spec = true;
     }
@@ -633,7 +668,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     const long long td = clock64();
     pf[2] += td - tc;
     if (jmin == 0xffffffffu) { // clean round: every position of the window is final
-      if (sw) {
+      if (DENSE && sw) {
         commit_planned(c, pi, sw_pj, maxH, accepted);
         for (int t = pi; t < sw_pj; ++t) plan_moved += c.e_g[t] != 0.0;
         plan_used += sw_pj - pi;
@@ -655,7 +690,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     const int k = ordered ? pend.q0 + (int)jmin : (int)cd_perm(pk, (uint32_t)(pend.q0 + jmin));
     const double2 e = __ldcg(reinterpret_cast<const double2 *>(hb + jmin));
     const double h = e.x, nw = e.y;
-    if (sw) { // an unplanned coordinate of a super-window moved: the planned entries before it stand, the rest is undone
+    if (DENSE && sw) { // an unplanned coordinate of a super-window moved: the planned entries before it stand, the rest is undone
       int pc = pi;
       while (pc < sw_pj && c.e_row[pc] < pend.q0 + (int)jmin) ++pc;
       if (pc < sw_pj) {
@@ -714,7 +749,7 @@ __device__ double full_pass(NCtx &c, double lam, unsigned long long pass_counter
     {
       seg_events += 1;
       events += 1;
-      if (dense && a.p - q0 >= 64 && (mP - pi >= NV_DENSE_MIN_LEFT || seg_events >= NV_DENSE_EVENTS)) {
+      if (DENSE && dense && a.p - q0 >= 64 && (mP - pi >= NV_DENSE_MIN_LEFT || seg_events >= NV_DENSE_EVENTS)) {
         q_resume = q0; // a new segment: plan the rest of the pass against the current r
         break;
       }
@@ -1353,6 +1388,7 @@ __device__ double shared_sumsq(NCtx &c) {
   return v;
 }
 
+template <bool DENSE>
 __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, int CH, HEntry *hbuf, NBcast *bc, int gcap) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1439,29 +1475,32 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
             nact_hint = __ldcg(&bc->nact);
             hint_stale = false;
           }
-          // X in L2 (a pre-scan costs about one round): an empty list (cold start: nothing else can be planned) or 8
-          // unplanned movers in the last full pass; X streamed from HBM: when those movers' rounds (~6 us each) cost
-          // more than twice the extra pass over X
-          const bool x_in_l2 = (long long)a.n * a.p * 8 <= (64ll << 20);
-          const bool dense = a.dense && a.plan && a.gram && c.gcap > 0 &&
-                             (x_in_l2 ? (nact_hint == 0 || last_events >= 8)
-                                      : (double)last_events * 3.0 > (double)a.n * (double)a.p * 1.6e-6);
+          // DENSE instance (X in L2: a pre-scan costs about one round): an empty list (cold start: nothing else can be
+          // planned) or 8 unplanned movers in the last full pass
+          // (lists longer than one plan are left to the ordinary pass: a 512 x 512 Gram per chunk costs what it saves)
+          const bool dense = DENSE && a.dense && a.plan && a.gram && c.gcap > 0 && nact_hint <= min(c.gcap, NV_PLAN_MAX) &&
+                             (nact_hint == 0 || last_events >= 8);
           const PermKey pk_pass = cd_perm_key((uint32_t)a.p, a.seed, pass_counter);
           double maxH = 0.0;
           int q_start = 0, events_pass = 0;
           // entries per plan: a cold start begins small (against r = y almost every coordinate looks like a mover, and the
           // first large steps change that), then the size follows how much of the last plan actually moved
           int cap = nact_hint == 0 ? 32 : min(c.gcap, NV_PLAN_MAX);
+          int segs = 0;
           for (;;) { // segments of the pass (one, unless dense mode plans again)
             int mP = 0;
             bool truncated = false;
+            // at most 6 planned segments per pass (32 + 64 + ... + 512 entries cover a thousand movers): a pass with more
+            // movers than that (C1 at lambda = 0.01: a cold pass with 2000) is cheaper one round per mover from there on
+            const bool dense_now = dense && segs < 6;
+            segs += 1;
             if (a.plan && a.gram && c.gcap > 0) {
               const long long tp0 = clock64();
               double *Gs = a.gram, *ds = a.gram + (long long)a.gram_cap * a.gram_cap;
               const NPlan PL = plan_arrays(a);
               const int *lst = nullptr;
               int mE = 0;
-              if (dense) {
+              if (DENSE && dense_now) {
                 dense_prescan(c, lam, pk_pass, a.randomize == 0, q_start);
                 fast_grid_sync(c);
                 if (c.bid == 0) dense_select(c, pk_pass, a.randomize == 0, q_start, cap);
@@ -1490,7 +1529,7 @@ __global__ void __launch_bounds__(NV_T, 1) naive_path_kernel(const NaiveArgs a, 
               pf[8] += clock64() - tp0;
             }
             int q_resume = a.p, used = 0, moved = 0;
-            maxH = fmax(maxH, full_pass(c, lam, pass_counter, st.accepted, pf, nact_hint, mP, q_start, dense, truncated, q_resume,
+            maxH = fmax(maxH, full_pass<DENSE>(c, lam, pass_counter, st.accepted, pf, nact_hint, mP, q_start, dense_now, truncated, q_resume,
                                         events_pass, used, moved));
             if (q_resume >= a.p) break;
             q_start = q_resume;
@@ -1747,7 +1786,8 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
   const size_t max_dyn = 227 * 1024;
   const bool known = h->device >= 0 && h->device < 64;
   if (!known || !attr_done[h->device]) {
-    CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
     if (known) attr_done[h->device] = true;
   }
   // shared memory: r (and w) + the state of the covariance-form active engine, whose capacity shrinks
@@ -1773,7 +1813,10 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
     if (v >= 1 && v <= h->sm_count) G = v;
   }
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, naive_path_kernel, NV_T, dyn));
+  // the instance with dense mode and super-windows for problems whose X stays in L2 (see full_pass)
+  const bool dense_kernel = a.dense && (long long)a.n * a.p * 8 <= (64ll << 20);
+  const void *kfn = dense_kernel ? (const void *)naive_path_kernel<true> : (const void *)naive_path_kernel<false>;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, NV_T, dyn));
   if (occ < 1) return cdgpu_set_error(CDGPU_ECUDA, "naive sweep kernel does not fit on an SM");
   G = max(1, min(G, occ * h->sm_count));
   // chunk: up to 8 columns per warp per round, at most ~48 MB of columns so a re-evaluation hits L2
@@ -1790,7 +1833,7 @@ int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
   NBcast *bc = reinterpret_cast<NBcast *>(a.scr + 8 + 8 * (long long)a.p);
   int ch = (int)CH;
   void *args[] = {(void *)&a, (void *)&ch, (void *)&hbuf, (void *)&bc, (void *)&gcap};
-  CUDA_TRY(cudaLaunchCooperativeKernel((void *)naive_path_kernel, dim3(G), dim3(NV_T), args, dyn, h->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(G), dim3(NV_T), args, dyn, h->stream));
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
 }
