@@ -47,7 +47,7 @@ C2_VISITS = 3990575
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures under profiles/
 NCU_TRAFFIC = {
     "gram_syrk_kernel": (30.228562e9 + 3.203871e9, "profiles/r1d_kernels_ncu.txt"),
-    "naive_path_kernel_c3": (6.059584e9 + 0.009213e9, "profiles/r1d_kernels_ncu.txt"),
+    "naive_path_kernel_c3": (6.542697e9 + 0.010799e9, "profiles/r5_naive_path_ncu.txt"),
 }
 try:
     NCU_TRAFFIC.update({k: tuple(v) for k, v in json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).items()})

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """One launch of each hot kernel at its BASELINE.json size, for `ncu --set full` (see profiles/README.md):
 C2 Gram (gram_syrk_kernel) + covariance path (cov_path_kernel), C3 sqrt-lasso (naive_path_kernel),
-C4 varying-coefficient lasso (gram_syrk_kernel<GEMM> + vc_cov_kernel)."""
+C4 varying-coefficient lasso (gram_syrk_kernel<GEMM> + vc_cov_kernel); `c1`: the dense active-set case (C1 at lambda = 0.01:
+the team chain engine inside naive_path_kernel)."""
 import ctypes as C
 import math
 import os
@@ -59,6 +60,16 @@ if "c3" in which:
     print("c3:", f.last_stats)
     f.close()
     del Xd, yd
+if "c1" in which:  # C1 at lambda = 0.01: 828 active entries, 1317 passes -> the team chain engine inside naive_path_kernel
+    rng = np.random.default_rng(123)
+    n, p, s = 1000, 5000, 10
+    X = rng.standard_normal((p, n)).T
+    y = X[:, :s] @ (rng.standard_normal(s) * (1.0 + rng.random(s))) + rng.standard_normal(n)
+    f = be.CDLeastSquaresLoss(y, X)
+    x = SparseIterate(p)
+    be.coordinateDescent_(x, f, ProxL1(0.01), CDOptions(maxIter=2000, optTol=1e-7, randomize=False))
+    print("c1:", f.last_stats)
+    f.close()
 if "c4" in which:
     n, p, degree, m = 500, 50, 2, 4096
     rng = np.random.default_rng(125)
