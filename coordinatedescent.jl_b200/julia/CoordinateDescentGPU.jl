@@ -328,9 +328,22 @@ kernel_kind(::EpanechnikovKernel) = Cint(1)
 # locpolyl1 (varying_coefficient_lasso.jl:30-79): all grid points in one batched call; with refit=true the weighted
 # normal equations on the selected groups (:71-76) are formed from the same moment blocks and solved on the device
 function locpolyl1(X::Matrix{Float64}, z::Vector{Float64}, y::Vector{Float64}, zgrid::Vector{Float64}, degree::Int64,
-                   kernel::SmoothingKernel{Float64}, λ0::Float64, refit::Bool, options::CDOptions=CDOptions(); device::Integer=0)
+                   kernel::SmoothingKernel{Float64}, λ0::Float64, refit::Bool, options::CDOptions=CDOptions(); device::Integer=0,
+                   chain::Integer=1)
+    # chain: grid points per warm-started run (cdgpu_vc_solve_chain).  1: every grid point from zero, all of them concurrently
+    # (the default); length(zgrid): the reference's loop exactly (`beta` carried from grid point to grid point,
+    # varying_coefficient_lasso.jl:56,68) as one sequential chain on the device; k: runs of k grid points.
     n, p = size(X); ep = p * (degree + 1); m = length(zgrid)
     out = zeros(Float64, ep, m)
+    if chain != 1
+        outR = refit ? zeros(Float64, ep, m) : nothing
+        GC.@preserve X z y zgrid out outR check(ccall((:cdgpu_vc_solve_chain, libcdgpu), Cint,
+            (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint, Cint, Float64, Float64,
+             Ref{cdgpu_options}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+            X, n, p, n, z, y, zgrid, m, 0, m, degree, kernel_kind(kernel), kernel.h, λ0, Ref(c_opts(options)), chain, device, out,
+            refit ? pointer(outR) : Ptr{Float64}(C_NULL), C_NULL))
+        return sparse(out), (refit ? sparse(outR) : spzeros(Float64, ep, m))
+    end
     if !refit
         GC.@preserve X z y zgrid out check(ccall((:cdgpu_vc_solve, libcdgpu), Cint,
             (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint, Cint, Float64, Float64,

@@ -199,8 +199,9 @@ def test_front_ends(gpu, ref):
 @pytest.mark.parametrize("randomize", [False, True])
 def test_naive_path_plans_and_replans_members(gpu, ref, randomize):
     """LassoPath in the reference's naive form (lasso.jl:229-260): every lambda starts with a full pass over a warm list
-    (members' steps planned by one chain pass, naive_sweep.cu: member_plan) into which new coordinates enter (the rest of
-    the plan is redone: replan_members).  Scattered true support, so members and entering coordinates interleave."""
+    (members' steps planned by one chain pass, naive_sweep.cu: member_plan) into which new coordinates enter (dense mode:
+    candidates planned next to the members, super-windows, snapshot + replay when an unplanned coordinate moves).
+    Scattered true support, so members and entering coordinates interleave."""
     n, p, s = 500, 3000, 40
     rng = np.random.default_rng(77)
     X = np.asfortranarray(rng.standard_normal((n, p)))
