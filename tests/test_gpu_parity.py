@@ -541,6 +541,13 @@ def test_errors_match_reference(gpu):
         gpu.coordinateDescent_(SparseIterate(5), f, ProxL1(0.1, np.ones(4)))
     with pytest.raises(cdgpu.ArgumentError):
         gpu.scaledLasso_(SparseIterate(5), X, y, 0.1, np.ones(5), IterLassoOptions(initProcedure="Nope"))
+    z = np.linspace(0.0, 1.0, 20)
+    with pytest.raises(cdgpu.ArgumentError):  # cdgpu_vc_solve_chain: runs of at least one grid point
+        gpu.locpolyl1(X, z, y, np.array([0.3, 0.6]), 1, GaussianKernel(0.3), 0.1, False, CDOptions(), chain=0)
+    # a chain longer than the grid is the whole grid; a single grid point is a chain of one
+    a, _ = gpu.locpolyl1(X, z, y, np.array([0.3, 0.6]), 1, GaussianKernel(0.3), 0.1, False, CDOptions(randomize=False), chain=7)
+    b, _ = gpu.locpolyl1(X, z, y, np.array([0.3, 0.6]), 1, GaussianKernel(0.3), 0.1, False, CDOptions(randomize=False), chain=2)
+    assert np.array_equal(a, b)
 
 
 # ---------------------------------------------------------------------------- edge cases
