@@ -1813,7 +1813,8 @@ API int cdgpu_refit(cdgpu_handle h, const int64_t *support, int64_t ns, double *
   if (!h || (ns > 0 && (!support || !coef_out))) return cdgpu_set_error(CDGPU_EARG, "null pointer");
   if (ns < 0 || ns > h->p) return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
   if (ns == 0) return CDGPU_OK;
-  if (ns > 2048) return cdgpu_set_error(CDGPU_ECAP, "refit handles supports of at most 2048 columns");
+  if (ns > (int64_t)cd_gram_cap((size_t)h->p))
+    return cdgpu_set_error(CDGPU_ECAP, "refit handles supports of at most %d columns", (int)cd_gram_cap((size_t)h->p));
   CUDA_TRY(cudaSetDevice(h->device));
   std::vector<int> s0((size_t)ns);
   for (int64_t i = 0; i < ns; ++i) {

@@ -431,7 +431,7 @@ struct NaiveArgs {
 constexpr int CD_GCAP = 4096; // largest active set of a naive handle that runs on the chain engines (Gram scratch 134 MB)
 // global scratch of the team chain engine (chain_engine.cuh: Multi::gT, Multi::hT: CD_GCAP tagged values of 16 bytes each)
 constexpr size_t CD_MULTI_SCR_BYTES = (size_t)2 * CD_GCAP * 16;
-inline size_t cd_gram_cap(size_t p) { return p < 2048 ? 2048 : (p < (size_t)CD_GCAP ? p : (size_t)CD_GCAP); }
+inline size_t cd_gram_cap(size_t p) { return p < 2048 ? 2048 : (p < (size_t)CD_GCAP ? ((p + 1) & ~(size_t)1) : (size_t)CD_GCAP); } // even
 inline size_t cd_scr_tail(size_t p, size_t n) { return (15 * p + 8 * n + 64 + 4 * (size_t)CD_GCAP + 64 + 1) & ~(size_t)1; }
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
 bool naive_fits(long long n, bool has_w);

@@ -2,7 +2,7 @@
 // The normal equations on the support come from the handle's own device data: X_S'[W]X_S, X_S'[W]y by one warp per
 // pair of columns (naive-form handles), or A[S,S], -b[S] gathered from the covariance-form handle; one CTA then
 // solves the ns x ns system by a left-looking Cholesky in global scratch (columns contiguous: coalesced) and two
-// triangular sweeps.  ns <= 2048.
+// triangular sweeps.  ns <= CD_GCAP = 4096 (the scratch of the handle's active Gram, common.cuh: cd_gram_cap).
 #include <algorithm>
 
 #include "common.cuh"
@@ -61,7 +61,7 @@ __global__ void refit_gram_quad_kernel(const double *__restrict__ A, long long l
 
 // one CTA: Cholesky (lower, in place) + L y = rhs + L' x = y; flag[0] = 1 when not positive definite
 __global__ void __launch_bounds__(RF_T, 1) refit_solve_kernel(double *M, int ld, int ns, double *rhs, int *flag) {
-  __shared__ double lrow[2048];
+  __shared__ double lrow[CD_GCAP]; // row j of L while column j is formed (32 KB)
   __shared__ double red[RF_T / 32];
   __shared__ double sdiag;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

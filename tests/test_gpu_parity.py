@@ -470,6 +470,18 @@ def test_refit_next_tier(gpu, ref):
         fd = gpu.CDLeastSquaresLoss(y, Xd)
         coef = np.zeros(4)
         gpu.lib.check(gpu.lib.refit(fd._h, cdgpu._ffi.ptr(np.array([1, 2, 3, 4], dtype=np.int64)), 4, cdgpu._ffi.ptr(coef)))
+    # a support beyond the first 2048 columns of scratch (round 1's limit; now the handle's Gram scratch: 4096), odd width
+    rng = np.random.default_rng(93)
+    nb, pb, nsb = 2700, 2601, 2301
+    Xb = np.asfortranarray(rng.standard_normal((nb, pb)))
+    yb = rng.standard_normal(nb)
+    fb = gpu.CDLeastSquaresLoss(yb, Xb)
+    Sb = np.sort(rng.choice(pb, nsb, replace=False))
+    coef = np.zeros(nsb)
+    gpu.lib.check(gpu.lib.refit(fb._h, cdgpu._ffi.ptr((Sb + 1).astype(np.int64)), nsb, cdgpu._ffi.ptr(coef)))
+    fb.close()
+    want = np.linalg.lstsq(Xb[:, Sb], yb, rcond=None)[0]
+    assert np.max(np.abs(coef - want)) <= 1e-9 * np.max(np.abs(want))
     # locpolyl1(refit=true): refitted coefficients solve the weighted normal equations on the selected groups
     rng = np.random.default_rng(92)
     Xs = np.asfortranarray(rng.standard_normal((200, 6)))
