@@ -66,6 +66,21 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+_STATS_NAMES = tuple(k for k, _ in Stats._fields_)
+_STATS_DTYPE = np.dtype([("passes", "<i8"), ("full_passes", "<i8"), ("visits", "<i8"), ("accepted", "<i8"), ("maxH", "<f8"),
+                         ("converged", "<i4"), ("outer_iters", "<i4"), ("sigma", "<f8"), ("device_ms", "<f8")])
+assert _STATS_DTYPE.itemsize == C.sizeof(Stats)
+
+
+def stats_dicts(arr, count):
+    """The first `count` entries of a ctypes array of Stats as dicts (one pass through numpy instead of a getattr per
+    field: a 100-lambda path has 900 of them)."""
+    if count <= 0:
+        return []
+    rows = np.frombuffer(arr, dtype=_STATS_DTYPE, count=count).tolist()
+    return [dict(zip(_STATS_NAMES, r)) for r in rows]
+
+
 class DimensionMismatch(ValueError):
     """Julia's DimensionMismatch (CDGPU_EDIM)."""
 

@@ -444,13 +444,13 @@ class Backend:
         o = options.c()
         self.lib.check(self.lib.path(f._h, ptr(lam), m, ptr(stdX), C.byref(o), mhs, cap, ptr(colptr), ptr(rowval),
                                      ptr(nzval), C.byref(done), C.cast(stats, C.c_void_p)))
-        βpath = []
-        for i in range(done.value):
-            a, b = colptr[i], colptr[i + 1]
-            βpath.append(SparseIterate(p, _triple=(nzval[a:b].copy(), rowval[a:b].copy())))
+        nd = done.value
+        tot = int(colptr[nd])
+        vals, inds, cp = nzval[:tot].copy(), rowval[:tot].copy(), colptr[: nd + 1].tolist()  # columns are views of one copy
+        βpath = [SparseIterate(p, _triple=(vals[cp[i]:cp[i + 1]], inds[cp[i]:cp[i + 1]])) for i in range(nd)]
         if own:
             f.close()
-        return LassoPath(lam[: done.value].copy(), βpath, [stats[i].as_dict() for i in range(done.value)])
+        return LassoPath(lam[: done.value].copy(), βpath, _ffi.stats_dicts(stats, done.value))
 
     # refitLassoPath(path, X, Y)                        lasso.jl:208-225
     def refitLassoPath(self, path: LassoPath, X, Y, loss=None):
