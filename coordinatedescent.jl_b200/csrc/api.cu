@@ -620,7 +620,7 @@ static int h2d_columns(double *dst, int64_t ld_dst, const double *src, int64_t l
                        cudaStream_t cs, int nblocks_hint, F after_block) {
   const size_t total = (size_t)n * (size_t)ncols * sizeof(double);
   const bool stage = total >= ((size_t)32 << 20) && host_is_pageable(src) && !getenv("CDGPU_NO_STAGING");
-  int nthreads = (int)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency() / 2));
+  int nthreads = (int)std::min<unsigned>(16, std::max<unsigned>(1, std::thread::hardware_concurrency() - 1));
   if (const char *env = getenv("CDGPU_H2D_THREADS")) nthreads = std::max(1, atoi(env));
   if (!stage) {
     const int nb = std::max(1, nblocks_hint);
@@ -652,7 +652,16 @@ static int h2d_columns(double *dst, int64_t ld_dst, const double *src, int64_t l
     const int64_t c1 = std::min<int64_t>(ncols, c0 + cols_per), nc = c1 - c0;
     if (used[which]) CUDA_TRY(cudaEventSynchronize(g_stager.ev[which])); // its previous DMA has drained
     double *pb = g_stager.buf[which];
+    const bool contiguous = ld_dst == n && ld_src == n; // one run of bytes: each thread copies one large piece (the C
+                                                        // library then uses streaming stores: no read-for-ownership)
     auto work = [&](int t) {
+      if (contiguous) {
+        const size_t bytes = (size_t)nc * (size_t)n * sizeof(double);
+        const size_t per = ((bytes + (size_t)nthreads - 1) / (size_t)nthreads + 4095) & ~(size_t)4095;
+        const size_t b0 = std::min(bytes, per * (size_t)t), b1 = std::min(bytes, b0 + per);
+        if (b1 > b0) memcpy(reinterpret_cast<char *>(pb) + b0, reinterpret_cast<const char *>(src + (size_t)c0 * (size_t)ld_src) + b0, b1 - b0);
+        return;
+      }
       for (int64_t c = c0 + t; c < c1; c += nthreads) {
         memcpy(pb + (size_t)(c - c0) * (size_t)ld_dst, src + (size_t)c * (size_t)ld_src, (size_t)n * sizeof(double));
         if (ld_dst > n) memset(pb + (size_t)(c - c0) * (size_t)ld_dst + n, 0, (size_t)(ld_dst - n) * sizeof(double));
