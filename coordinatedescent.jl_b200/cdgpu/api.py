@@ -475,10 +475,11 @@ class Backend:
 
     # locpolyl1(X, z, y, zgrid, degree, kernel, λ0, refit, options)  varying_coefficient_lasso.jl:30-79
     def locpolyl1(self, X, z, y, zgrid, degree, kernel, λ0, refit=False, options: CDOptions = None, shard=None, chain=None):
-        """`chain`: grid points per warm-started run.  None / 1: the library's default (device: every grid point from
-        zero, all of them concurrently; CPU oracle: the reference's chain over the grid points it is given); k: runs of
-        k consecutive grid points, each point from its predecessor's iterate; `len(zgrid)`: the reference's loop
-        exactly (varying_coefficient_lasso.jl:56,68), as one sequential chain."""
+        """`chain`: grid points per warm-started run.  None: the library's default (device: every grid point from zero,
+        all of them concurrently; CPU oracle: the reference's chain over the grid points it is given); 1: every grid
+        point from zero on either library; k: runs of k consecutive grid points, each point from its predecessor's
+        iterate; `len(zgrid)`: the reference's loop exactly (varying_coefficient_lasso.jl:56,68), as one sequential
+        chain."""
         options = options or CDOptions()
         X, z, y, zgrid = f64(X), f64(z), f64(y), f64(zgrid)
         n, p = X.shape
@@ -489,7 +490,7 @@ class Backend:
         out = np.zeros((ep, m), order="F")
         stats = (_ffi.Stats * m)()
         o = options.c()
-        if chain is not None and int(chain) != 1:
+        if chain is not None:
             outR = np.zeros((ep, m), order="F") if refit else None
             self.lib.check(self.lib.vc_solve_chain(ptr(X), n, p, n, ptr(z), ptr(y), ptr(zgrid), m, lo, hi, int(degree),
                                                    kernel.kind, float(kernel.h), float(λ0), C.byref(o), int(chain),

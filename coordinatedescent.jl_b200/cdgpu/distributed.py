@@ -47,7 +47,7 @@ def locpolyl1_sharded(be: Backend, X, z, y, zgrid, degree, kernel, λ0, options=
     if interleave:
         mine_idx = owned(rank)
         out, _ = be.locpolyl1(X, z, y, np.ascontiguousarray(zgrid[mine_idx]), degree, kernel, λ0, False, options,
-                              chain=chain if chain > 1 else None)
+                              chain=chain if chain > 1 else None)  # (None: the library's default)
         cols = out
     else:
         if chain > 1:

@@ -246,6 +246,36 @@ def test_lvocv_oracle_prefers_the_true_bandwidth_and_chain_cut_agree(ref):
     assert cut[0] < 0.5 * cut[1]
 
 
+def test_locpolyl1_chain_runs_in_the_oracle(ref):
+    """cdref_vc_solve_chain: the reference's warm-start chain (varying_coefficient_lasso.jl:56,68) cut into runs of k
+    grid points.  k = m is the plain oracle call; a run equals the plain call on its own grid points; warm starts change
+    the pass counts of a run's later points but, at a tight tolerance, not the solution."""
+    from cdgpu import CDOptions, GaussianKernel
+    rng = np.random.default_rng(97)
+    n, p, m = 120, 6, 7
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    Y = X[:, 0] * np.sin(4 * Z) + X[:, 1] * Z + 0.1 * rng.standard_normal(n)
+    zgrid = np.linspace(0.15, 0.85, m)
+    loose = CDOptions(randomize=False, maxIter=20000, optTol=1e-4)
+    whole, _ = ref.locpolyl1(X, Z, Y, zgrid, 1, GaussianKernel(0.25), 0.02, False, loose)
+    sw = ref.last_vc_stats
+    chained, _ = ref.locpolyl1(X, Z, Y, zgrid, 1, GaussianKernel(0.25), 0.02, False, loose, chain=m)
+    assert np.array_equal(whole, chained) and [s["passes"] for s in sw] == [s["passes"] for s in ref.last_vc_stats]
+    runs, _ = ref.locpolyl1(X, Z, Y, zgrid, 1, GaussianKernel(0.25), 0.02, False, loose, chain=3)
+    sr = ref.last_vc_stats
+    for b0 in range(0, m, 3):
+        own, _ = ref.locpolyl1(X, Z, Y, zgrid[b0:b0 + 3], 1, GaussianKernel(0.25), 0.02, False, loose)
+        assert np.array_equal(runs[:, b0:b0 + 3], own)
+        assert [s["passes"] for s in sr[b0:b0 + 3]] == [s["passes"] for s in ref.last_vc_stats]
+    tight = CDOptions(randomize=False, maxIter=200000, optTol=1e-12)
+    a, _ = ref.locpolyl1(X, Z, Y, zgrid, 1, GaussianKernel(0.25), 0.02, False, tight, chain=1)
+    b, _ = ref.locpolyl1(X, Z, Y, zgrid, 1, GaussianKernel(0.25), 0.02, False, tight, chain=m)
+    assert np.array_equal(a != 0, b != 0) and np.max(np.abs(a - b)) <= 1e-8 * np.max(np.abs(b))
+    with pytest.raises(ValueError):
+        ref.locpolyl1(X, Z, Y, zgrid, 1, GaussianKernel(0.25), 0.02, False, loose, chain=0)
+
+
 def test_oracle_refits_match_numpy(ref):
     """refitLassoPath (lasso.jl:208-225, test/lasso.jl:236-241) and locpolyl1(refit=true)
     (varying_coefficient_lasso.jl:71-76) in the oracle against numpy's own least squares."""
