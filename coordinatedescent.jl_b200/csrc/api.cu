@@ -802,18 +802,16 @@ static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const do
     std::vector<int> idx((size_t)p);
     for (int64_t j = 0; j < p; ++j) idx[(size_t)j] = (int)j;
     const int take = (int)std::min<int64_t>(want, p);
-    std::partial_sort(idx.begin(), idx.begin() + take, idx.end(), [&](int a_, int b_) {
-      return sc[(size_t)a_] > sc[(size_t)b_] || (sc[(size_t)a_] == sc[(size_t)b_] && a_ < b_);
-    });
+    // the next-best candidates are formed speculatively while the sweep kernel runs (lazy_spec_start): one selection of
+    // the take + more best (a strict total order: score, then index), linear in p, then a sort of those few
+    const int more = (int)std::min<int64_t>(LZ_BATCH, p - take);
+    auto better = [&](int a_, int b_) { return sc[(size_t)a_] > sc[(size_t)b_] || (sc[(size_t)a_] == sc[(size_t)b_] && a_ < b_); };
+    if (take + more < p) std::nth_element(idx.begin(), idx.begin() + (take + more), idx.end(), better);
+    std::sort(idx.begin(), idx.begin() + (take + more), better);
     for (int q = 0; q < take; ++q)
       if (sc[(size_t)idx[(size_t)q]] > 0.0) cols.push_back(idx[(size_t)q]);
-    // the next-best candidates: formed speculatively while the sweep kernel runs (lazy_spec_start)
-    const int more = (int)std::min<int64_t>(LZ_BATCH, p - take);
     h->next_n = 0;
     if (more > 0) {
-      std::partial_sort(idx.begin() + take, idx.begin() + take + more, idx.end(), [&](int a_, int b_) {
-        return sc[(size_t)a_] > sc[(size_t)b_] || (sc[(size_t)a_] == sc[(size_t)b_] && a_ < b_);
-      });
       for (int q = 0; q < more; ++q)
         if (sc[(size_t)idx[(size_t)(take + q)]] > 0.0) h->next_cand[h->next_n++] = idx[(size_t)(take + q)];
     }
