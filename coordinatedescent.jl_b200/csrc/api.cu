@@ -1244,6 +1244,14 @@ static int run_sweeps(cdgpu_handle_s *h, const RunCfg &rc) {
     const bool prof = getenv("CDGPU_PROFILE") != nullptr;
     a.prof = prof ? reinterpret_cast<long long *>(h->dscr + 11 * (size_t)h->p) : nullptr;
     a.events_only = getenv("CDGPU_COV_EVENTS") != nullptr && atoi(getenv("CDGPU_COV_EVENTS")) != 0;
+    if (!h->lazy && getenv("CDGPU_IDENTITY_SLOT")) { // diagnostics: an eager handle through the column-slot indirection
+      std::vector<int> id((size_t)h->p);
+      for (int64_t j = 0; j < h->p; ++j) id[(size_t)j] = (int)j;
+      int *dslot_id = h->discr + 9 * (size_t)h->p; // [9p, 10p): free between launches
+      CUDA_TRY(cudaMemcpyAsync(dslot_id, id.data(), (size_t)h->p * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      a.colslot = dslot_id;
+    }
     if (h->lazy) {
       // columns of the members handed in (warm start) must exist; a fresh handle also forms its first batch now: the
       // coordinates with the largest |b_j|/omega_j are the ones that enter first along a path
