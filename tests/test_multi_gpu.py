@@ -54,6 +54,12 @@ def _main():
     full = locpolyl1_sharded(be, Xs, Z, Y, zgrid, 1, GaussianKernel(0.2), 0.02, o)
     whole, _ = be.locpolyl1(Xs, Z, Y, zgrid, 1, GaussianKernel(0.2), 0.02, False, o)
     assert np.array_equal(full, whole)
+    # the warm-start chain in runs of two grid points (cdgpu_vc_solve_chain): the runs are the units dealt over the ranks,
+    # so the sharded result is the one-GPU result bit for bit even at a loose tolerance (33 grid points: the last run has one)
+    ol = CDOptions(randomize=False, optTol=1e-4, maxIter=20000)
+    full2 = locpolyl1_sharded(be, Xs, Z, Y, zgrid, 1, GaussianKernel(0.2), 0.02, ol, chain=2)
+    whole2, _ = be.locpolyl1(Xs, Z, Y, zgrid, 1, GaussianKernel(0.2), 0.02, False, ol, chain=2)
+    assert np.array_equal(full2, whole2)
     comm.close()
     dist.barrier()
     if rank == 0:
