@@ -781,6 +781,8 @@ static int lazy_ensure(cdgpu_handle_s *h, const std::vector<int> &need, const do
   // number of pauses grows with the logarithm of the columns a solve touches and at most ~2x of them are formed.
   int width = getenv("CDGPU_LAZY_SPEC_OFF") ? LZ_BATCH : LZ_NARROW;
   if (h->lz_pauses > 2) width = (int)std::min<int64_t>((int64_t)width << std::min<int64_t>(h->lz_pauses - 2, 6), 2048);
+  if (h->lz_used == 0)
+    if (const char *env = getenv("CDGPU_LAZY_FIRST")) width = std::max(LZ_NARROW, atoi(env) / LZ_NARROW * LZ_NARROW); // diagnostics
   int target = (int)((cols.size() + width - 1) / width * width);
   if (target == 0) target = width;
   target = (int)std::min<int64_t>(target, std::max<int64_t>((int64_t)cols.size(), h->p - h->lz_used));
