@@ -842,7 +842,9 @@ static int lazy_spec_start(cdgpu_handle_s *h) {
   if (nb == 0 || h->lz_used + nb > h->lz_cap) return CDGPU_OK;
   CUDA_TRY(cudaMemcpyAsync(h->dbatch2, h->spec_cols, (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, h->lz_stream2));
   CD_TRY(launch_gather_cols(h->lz_stream2, h->lzX, h->lz_ldx, h->lz_n, h->lzw, h->dbatch2, nb, nb, h->dgather2, h->lz_ldb, nullptr, 0));
-  CD_TRY(launch_gemm_tn_split(h->lz_stream2, std::max(8, h->sm_count - 16), h->lzX, (int)h->p, h->lz_ldx, h->dgather2, nb, h->lz_ldb,
+  int spec_sms = std::max(8, h->sm_count - 16);
+  if (const char *env = getenv("CDGPU_LAZY_SPEC_SMS")) spec_sms = std::max(8, std::min(spec_sms, atoi(env))); // diagnostics
+  CD_TRY(launch_gemm_tn_split(h->lz_stream2, spec_sms, h->lzX, (int)h->p, h->lz_ldx, h->dgather2, nb, h->lz_ldb,
                               h->lz_n, h->dX + (size_t)h->lz_used * (size_t)h->ld, h->ld, (double)h->lz_n));
   CUDA_TRY(cudaEventRecord(h->lz_spec_ev, h->lz_stream2));
   h->spec_n = nb;
