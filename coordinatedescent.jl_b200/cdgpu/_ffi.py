@@ -149,6 +149,10 @@ _SIGS_GPU_ONLY = {
     "lazy_stats": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_int64_p, c_double_p]),
     "lazy_form_columns": (C.c_int, [C.c_void_p, c_int64_p]),
     "sweep_ms": (C.c_int, [C.c_void_p, c_double_p]),
+    "vc_solve_csc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                               C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Options),
+                               C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
     "synth_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int]),
     "gram_create_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_int]),

@@ -474,8 +474,11 @@ class Backend:
         return out
 
     # locpolyl1(X, z, y, zgrid, degree, kernel, λ0, refit, options)  varying_coefficient_lasso.jl:30-79
-    def locpolyl1(self, X, z, y, zgrid, degree, kernel, λ0, refit=False, options: CDOptions = None, shard=None, chain=None):
-        """`chain`: grid points per warm-started run.  None: the library's default (device: every grid point from zero,
+    def locpolyl1(self, X, z, y, zgrid, degree, kernel, λ0, refit=False, options: CDOptions = None, shard=None, chain=None,
+                  sparse=False):
+        """`sparse=True`: the results come back as the reference's SparseMatrixCSC (`spzeros(ep, m)`, :46-47), compacted on
+        the device (`cdgpu_vc_solve_csc`), as `(colptr, rowval, nzval)` triples with 0-based offsets and 1-based rows;
+        the second triple is None without refit.  `chain`: grid points per warm-started run.  None: the library's default (device: every grid point from zero,
         all of them concurrently; CPU oracle: the reference's chain over the grid points it is given); 1: every grid
         point from zero on either library; k: runs of k consecutive grid points, each point from its predecessor's
         iterate; `len(zgrid)`: the reference's loop exactly (varying_coefficient_lasso.jl:56,68), as one sequential
@@ -490,6 +493,25 @@ class Backend:
         out = np.zeros((ep, m), order="F")
         stats = (_ffi.Stats * m)()
         o = options.c()
+        if sparse:
+            cap = max(1, min(ep * (hi - lo), 64 * (hi - lo)))
+            while True:
+                cp, rv, nz = np.zeros(m + 1, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap)
+                cpR, rvR, nzR = (np.zeros(m + 1, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap)) if refit \
+                    else (None, None, None)
+                rc = self.lib.vc_solve_csc(ptr(X), n, p, n, ptr(z), ptr(y), ptr(zgrid), m, lo, hi, int(degree), kernel.kind,
+                                           float(kernel.h), float(λ0), C.byref(o), 1 if chain is None else int(chain),
+                                           self.device, cap, ptr(cp), ptr(rv), ptr(nz), ptr(cpR), ptr(rvR), ptr(nzR),
+                                           C.cast(stats, C.c_void_p))
+                need = max(int(cp[m]), int(cpR[m]) if refit else 0)
+                if rc == _ffi.ECAP and need > cap:  # the library reports the entries it needs: one retry
+                    cap = need
+                    continue
+                self.lib.check(rc)
+                break
+            self.last_vc_stats = [stats[i].as_dict() for i in range(lo, hi)]
+            tri = (cp, rv[:cp[m]].copy(), nz[:cp[m]].copy())
+            return tri, ((cpR, rvR[:cpR[m]].copy(), nzR[:cpR[m]].copy()) if refit else None)
         if chain is not None:
             outR = np.zeros((ep, m), order="F") if refit else None
             self.lib.check(self.lib.vc_solve_chain(ptr(X), n, p, n, ptr(z), ptr(y), ptr(zgrid), m, lo, hi, int(degree),

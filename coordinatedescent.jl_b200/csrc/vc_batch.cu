@@ -526,7 +526,100 @@ __global__ void vc_build_v_kernel(const double *__restrict__ z, const double *__
   }
 }
 
+// ---- locpolyl1's SparseMatrixCSC result formed on the device (varying_coefficient_lasso.jl:46-47 spzeros(ep, m), :69
+// out[:, i] = beta, :76): one warp per grid point counts, then writes, the stored entries of its column in row order
+__global__ void vc_csc_count_kernel(const double *__restrict__ out, int ep, int g0, int g1, long long *cnt) {
+  const int g = g0 + (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (g >= g1) return;
+  const double *col = out + (long long)g * ep;
+  int c = 0;
+  for (int i = lane; i < ep; i += 32) c += col[i] != 0.0;
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) cnt[g - g0] = c;
+}
+__global__ void vc_csc_fill_kernel(const double *__restrict__ out, int ep, int g0, int g1, const long long *__restrict__ off,
+                                   long long *rowval, double *nzval) {
+  const int g = g0 + (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (g >= g1) return;
+  const double *col = out + (long long)g * ep;
+  long long o = off[g - g0];
+  for (int i0 = 0; i0 < ep; i0 += 32) {
+    const int i = i0 + lane;
+    const double v = i < ep ? col[i] : 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, v != 0.0);
+    if (v != 0.0) {
+      const long long at = o + __popc(bal & ((1u << lane) - 1u));
+      rowval[at] = i + 1;
+      nzval[at] = v;
+    }
+    o += __popc(bal);
+  }
+}
+
 } // namespace
+
+// caller-side description of the CSC outputs of cdgpu_vc_solve_csc (R: the refit matrix, colptrR null without refit)
+struct VcCsc {
+  int64_t capacity;
+  int64_t *colptr, *rowval;
+  double *nzval;
+  int64_t *colptrR, *rowvalR;
+  double *nzvalR;
+};
+// dense ep x m result on the device -> CSC in the caller's arrays; only colptr and the stored entries are copied to the host.
+// Columns outside [m_begin, m_end) are empty.  CDGPU_ECAP (colptr[m] = entries needed) when capacity is too small.
+static int vc_emit_csc(cudaStream_t s, const double *dout, int64_t ep, int64_t m, int64_t m_begin, int64_t m_end, int64_t capacity,
+                       int64_t *colptr, int64_t *rowval, double *nzval) {
+  const int64_t mloc = m_end - m_begin;
+  long long *dcnt = nullptr, *drow = nullptr;
+  double *dval = nullptr;
+  int rc = CDGPU_OK;
+  auto fail = [&](cudaError_t e, const char *what) {
+    rc = cdgpu_set_error(e == cudaErrorMemoryAllocation ? CDGPU_ENOMEM : CDGPU_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  };
+  std::vector<long long> cnt((size_t)mloc);
+  cudaError_t e = cudaMallocAsync((void **)&dcnt, (size_t)mloc * sizeof(long long), s);
+  const unsigned blocks = (unsigned)((mloc * 32 + 255) / 256);
+  if (e != cudaSuccess) fail(e, "cudaMallocAsync(csc counts)");
+  if (!rc) {
+    vc_csc_count_kernel<<<blocks, 256, 0, s>>>(dout, (int)ep, (int)m_begin, (int)m_end, dcnt);
+    CD_COUNT_LAUNCH(1);
+    e = cudaMemcpyAsync(cnt.data(), dcnt, (size_t)mloc * sizeof(long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) fail(e, "csc count");
+  }
+  int64_t tot = 0;
+  if (!rc) {
+    for (int64_t g = 0; g <= m_begin; ++g) colptr[g] = 0;
+    for (int64_t g = 0; g < mloc; ++g) {
+      const long long c = cnt[(size_t)g];
+      cnt[(size_t)g] = tot; // exclusive offsets for the fill
+      tot += c;
+      colptr[m_begin + g + 1] = tot;
+    }
+    for (int64_t g = m_end + 1; g <= m; ++g) colptr[g] = tot;
+    if (tot > capacity)
+      rc = cdgpu_set_error(CDGPU_ECAP, "CSC output needs %lld entries, capacity is %lld", (long long)tot, (long long)capacity);
+  }
+  if (!rc && tot > 0) {
+    e = cudaMallocAsync((void **)&drow, (size_t)tot * sizeof(long long), s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dval, (size_t)tot * sizeof(double), s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dcnt, cnt.data(), (size_t)mloc * sizeof(long long), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) fail(e, "csc staging");
+    if (!rc) {
+      vc_csc_fill_kernel<<<blocks, 256, 0, s>>>(dout, (int)ep, (int)m_begin, (int)m_end, dcnt, drow, dval);
+      CD_COUNT_LAUNCH(1);
+      static_assert(sizeof(long long) == sizeof(int64_t), "rowval is copied as int64_t");
+      e = cudaMemcpyAsync(rowval, drow, (size_t)tot * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(nzval, dval, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) fail(e, "csc fill");
+    }
+  }
+  for (void *ptr : {(void *)dcnt, (void *)drow, (void *)dval})
+    if (ptr) cudaFreeAsync(ptr, s);
+  return rc;
+}
 
 // host driver of the moment form; grid points are processed in chunks so the moment blocks stay <= ~1 GiB
 const void *vc_cov_pick_std(int nu); // vc_cov_std.cu
@@ -536,7 +629,9 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
                            const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                            double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out,
                            double *outR, cdgpu_stats *stats, const double *harr = nullptr, double *lvo_err = nullptr,
-                           int64_t chain = 1) {
+                           int64_t chain = 1, const VcCsc *csc = nullptr) {
+  // csc != null: out / outR are null and the results leave the device as CSC (cdgpu_vc_solve_csc)
+  const bool wantR = outR || (csc && csc->colptrR);
   // harr != null: the problems are those of lvocv_locpolyl1 (m = numH * n, zgrid unused, out/outR null, one squared
   // prediction error per problem into lvo_err)
   const int64_t ep = p * (degree + 1), mloc = m_end - m_begin, P2 = p * (p + 1) / 2, PA = P2 + p + 2;
@@ -595,7 +690,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   VM_TRY(cudaMallocAsync((void **)&dz, (size_t)n * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dy, (size_t)n * sizeof(double), s));
   if (!harr) VM_TRY(cudaMallocAsync((void **)&dgz, (size_t)m * sizeof(double), s));
-  if (out) VM_TRY(cudaMallocAsync((void **)&dout, (size_t)ep * m * sizeof(double), s));
+  if (out || csc) VM_TRY(cudaMallocAsync((void **)&dout, (size_t)ep * m * sizeof(double), s));
   if (harr) {
     const int64_t numH = m / n;
     VM_TRY(cudaMallocAsync((void **)&dharr, (size_t)numH * sizeof(double), s));
@@ -603,7 +698,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
     VM_TRY(cudaMemcpyAsync(dharr, harr, (size_t)numH * sizeof(double), cudaMemcpyHostToDevice, s));
   }
   VM_TRY(cudaMallocAsync((void **)&dst, (size_t)m * sizeof(DevStats), s));
-  if (outR) VM_TRY(cudaMallocAsync((void **)&doutR, (size_t)ep * m * sizeof(double), s));
+  if (wantR) VM_TRY(cudaMallocAsync((void **)&doutR, (size_t)ep * m * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dZ, (size_t)ldz * PA * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dV, (size_t)ldz * nq * chunk * sizeof(double), s));
   VM_TRY(cudaMallocAsync((void **)&dC, (size_t)ldc * nq * chunk * sizeof(double), s));
@@ -689,6 +784,14 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   if (outR)
     VM_TRY(cudaMemcpyAsync(outR + m_begin * ep, doutR + m_begin * ep, (size_t)mloc * ep * sizeof(double), cudaMemcpyDeviceToHost, s));
   VM_TRY(cudaStreamSynchronize(s));
+  if (csc) {
+    rc = vc_emit_csc(s, dout, ep, m, m_begin, m_end, csc->capacity, csc->colptr, csc->rowval, csc->nzval);
+    if (!rc && csc->colptrR) rc = vc_emit_csc(s, doutR, ep, m, m_begin, m_end, csc->capacity, csc->colptrR, csc->rowvalR, csc->nzvalR);
+    if (rc) {
+      cleanup();
+      return rc;
+    }
+  }
   if (stats) {
     float ms = 0.f;
     VM_TRY(cudaEventElapsedTime(&ms, e0, e1));
@@ -728,7 +831,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
 static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                          const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                          double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out, double *outR,
-                         cdgpu_stats *stats, int64_t chain = 1);
+                         cdgpu_stats *stats, int64_t chain = 1, const VcCsc *csc = nullptr);
 // lvocv_locpolyl1 (varying_coefficient_lasso.jl:81-137): numH * n leave-one-out local scaled-lasso problems, all in
 // one batch; problems [q_begin, q_end) of the (bandwidth-major) list are solved (sharding hook), MSE[h] is summed on
 // the host in observation order from the per-problem squared errors.
@@ -786,11 +889,25 @@ API int cdgpu_vc_solve_chain(const double *X, int64_t n, int64_t p, int64_t ldx,
                        outR, stats, chain);
   });
 }
+API int cdgpu_vc_solve_csc(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                           const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                           double bandwidth, double lambda0, const cdgpu_options *opt, int64_t chain, int device,
+                           int64_t capacity, int64_t *colptr, int64_t *rowval, double *nzval, int64_t *colptrR,
+                           int64_t *rowvalR, double *nzvalR, cdgpu_stats *stats) {
+  return api_guard([&]() -> int {
+  if (!colptr || capacity < 0 || (capacity > 0 && (!rowval || !nzval)) || (colptrR && capacity > 0 && (!rowvalR || !nzvalR)))
+    return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  const VcCsc csc = {capacity, colptr, rowval, nzval, colptrR, rowvalR, nzvalR};
+  return vc_solve_impl(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt, device, nullptr,
+                       nullptr, stats, chain, &csc);
+  });
+}
 static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                          const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                          double bandwidth, double lambda0, const cdgpu_options *opt, int device, double *out, double *outR,
-                         cdgpu_stats *stats, int64_t chain) {
-  if (!X || !z || !y || !zgrid || !opt || !out) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+                         cdgpu_stats *stats, int64_t chain, const VcCsc *csc) {
+  if (!X || !z || !y || !zgrid || !opt || (!out && !csc)) return cdgpu_set_error(CDGPU_EARG, "null pointer");
+  const bool wantR = outR || (csc && csc->colptrR);
   if (chain < 1) return cdgpu_set_error(CDGPU_EARG, "chain must be at least 1");
   if (n < 1 || p < 1 || ldx < n || degree < 0 || m < 0 || m_begin < 0 || m_end > m || m_begin > m_end)
     return cdgpu_set_error(CDGPU_EDIM, "DimensionMismatch");
@@ -807,18 +924,25 @@ static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, con
   if (device < 0 || device >= ndev) return cdgpu_set_error(CDGPU_EARG, "device out of range");
   CD_TRY(cd_use_device(device));
   const int64_t mloc = m_end - m_begin;
-  if (mloc == 0) return CDGPU_OK;
+  if (mloc == 0) {
+    if (csc) {
+      for (int64_t g = 0; g <= m; ++g) csc->colptr[g] = 0;
+      if (csc->colptrR)
+        for (int64_t g = 0; g <= m; ++g) csc->colptrR[g] = 0;
+    }
+    return CDGPU_OK;
+  }
   {
     // moment (covariance) form unless the expanded problem is too wide for the warp kernel's registers;
     // CDGPU_VC_FORM=naive keeps the residual-form kernels below
     const char *form = getenv("CDGPU_VC_FORM");
-    if (ep <= 256 && (outR || !(form && strcmp(form, "naive") == 0)))
+    if (ep <= 256 && (wantR || !(form && strcmp(form, "naive") == 0)))
       return vc_solve_moment(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt,
-                             device, out, outR, stats, nullptr, nullptr, chain);
+                             device, out, outR, stats, nullptr, nullptr, chain, csc);
     if (chain > 1)
       return cdgpu_set_error(CDGPU_ECAP, "chained grid points need the moment form: p*(degree+1) = %lld exceeds 256 (or CDGPU_VC_FORM=naive)",
                              (long long)ep);
-    if (outR)
+    if (wantR)
       return cdgpu_set_error(CDGPU_ECAP, "refit on the device needs the moment form: p*(degree+1) = %lld exceeds 256",
                              (long long)ep);
   }
@@ -915,9 +1039,17 @@ static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, con
   CD_COUNT_LAUNCH(1);
   VC_TRY(cudaGetLastError());
   VC_TRY(cudaEventRecord(e1, s));
-  VC_TRY(cudaMemcpyAsync(out + m_begin * ep, dout + m_begin * ep, (size_t)mloc * ep * sizeof(double),
-                         cudaMemcpyDeviceToHost, s));
+  if (out)
+    VC_TRY(cudaMemcpyAsync(out + m_begin * ep, dout + m_begin * ep, (size_t)mloc * ep * sizeof(double),
+                           cudaMemcpyDeviceToHost, s));
   VC_TRY(cudaStreamSynchronize(s));
+  if (csc) {
+    rc = vc_emit_csc(s, dout, ep, m, m_begin, m_end, csc->capacity, csc->colptr, csc->rowval, csc->nzval);
+    if (rc) {
+      cleanup();
+      return rc;
+    }
+  }
   if (stats) {
     float ms = 0.f;
     VC_TRY(cudaEventElapsedTime(&ms, e0, e1));

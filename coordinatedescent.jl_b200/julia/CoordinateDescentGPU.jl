@@ -329,11 +329,36 @@ kernel_kind(::EpanechnikovKernel) = Cint(1)
 # normal equations on the selected groups (:71-76) are formed from the same moment blocks and solved on the device
 function locpolyl1(X::Matrix{Float64}, z::Vector{Float64}, y::Vector{Float64}, zgrid::Vector{Float64}, degree::Int64,
                    kernel::SmoothingKernel{Float64}, λ0::Float64, refit::Bool, options::CDOptions=CDOptions(); device::Integer=0,
-                   chain::Integer=1)
+                   chain::Integer=1, sparse_output::Bool=true)
     # chain: grid points per warm-started run (cdgpu_vc_solve_chain).  1: every grid point from zero, all of them concurrently
     # (the default); length(zgrid): the reference's loop exactly (`beta` carried from grid point to grid point,
     # varying_coefficient_lasso.jl:56,68) as one sequential chain on the device; k: runs of k grid points.
     n, p = size(X); ep = p * (degree + 1); m = length(zgrid)
+    if sparse_output
+        # SparseMatrixCSC built from the device-side compaction (cdgpu_vc_solve_csc): only colptr and the stored entries
+        # cross the ABI.  One retry when the first guess of the capacity is too small (colptr[m+1] then holds the need).
+        cap = max(1, min(ep * m, 64 * m))
+        while true
+            cp = zeros(Int64, m + 1); rv = zeros(Int64, cap); nz = zeros(Float64, cap)
+            cpR = zeros(Int64, m + 1); rvR = zeros(Int64, refit ? cap : 0); nzR = zeros(Float64, refit ? cap : 0)
+            rc = GC.@preserve X z y zgrid cp rv nz cpR rvR nzR ccall((:cdgpu_vc_solve_csc, libcdgpu), Cint,
+                (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint, Cint, Float64,
+                 Float64, Ref{cdgpu_options}, Int64, Cint, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64},
+                 Ptr{Float64}, Ptr{Cvoid}),
+                X, n, p, n, z, y, zgrid, m, 0, m, degree, kernel_kind(kernel), kernel.h, λ0, Ref(c_opts(options)), chain, device, cap,
+                cp, rv, nz, refit ? pointer(cpR) : Ptr{Int64}(C_NULL), refit ? pointer(rvR) : Ptr{Int64}(C_NULL),
+                refit ? pointer(nzR) : Ptr{Float64}(C_NULL), C_NULL)
+            need = max(cp[m+1], cpR[m+1])
+            if rc == 7 && need > cap   # CDGPU_ECAP
+                cap = need
+                continue
+            end
+            check(rc)
+            out = SparseMatrixCSC(ep, m, cp .+ 1, rv[1:cp[m+1]], nz[1:cp[m+1]])
+            outR = refit ? SparseMatrixCSC(ep, m, cpR .+ 1, rvR[1:cpR[m+1]], nzR[1:cpR[m+1]]) : spzeros(Float64, ep, m)
+            return out, outR
+        end
+    end
     out = zeros(Float64, ep, m)
     if chain != 1
         outR = refit ? zeros(Float64, ep, m) : nothing

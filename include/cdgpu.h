@@ -250,6 +250,18 @@ int cdgpu_vc_solve_chain(const double *X, int64_t n, int64_t p, int64_t ldx, con
                          double bandwidth, double lambda0, const cdgpu_options *opt, int64_t chain, int device,
                          double *out, double *outR, cdgpu_stats *stats);
 
+/* locpolyl1's results as the reference returns them: SparseMatrixCSC (varying_coefficient_lasso.jl:46-47 `spzeros(ep, m)`,
+ * :69 `out[:, i] = beta`, :76 `outR[...]`).  Same solve as cdgpu_vc_solve_chain (chain = 1: every grid point from zero); the
+ * stored entries (value != 0) are compacted on the device and only colptr and those entries cross the ABI instead of the
+ * dense ep x m matrix.  colptr[m+1] 0-based offsets, rowval 1-based rows in increasing order, nzval; columns outside
+ * [m_begin, m_end) are empty.  rowval / nzval (and rowvalR / nzvalR) are caller-allocated with `capacity` entries each;
+ * CDGPU_ECAP when a matrix has more, with colptr[m] (colptrR[m]) = the entries it needs.  colptrR NULL: no refit. */
+int cdgpu_vc_solve_csc(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
+                       const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
+                       double bandwidth, double lambda0, const cdgpu_options *opt, int64_t chain, int device,
+                       int64_t capacity, int64_t *colptr, int64_t *rowval, double *nzval, int64_t *colptrR,
+                       int64_t *rowvalR, double *nzvalR, cdgpu_stats *stats);
+
 /* refitLassoPath(path, X, Y) (lasso.jl:208-225), one support at a time: the least-squares coefficients on the
  * columns `support` (1-based indices, ns of them) of the handle's design — X[:, S] \ y for a naive-form handle
  * (w-weighted for CDWeightedLSLoss), A[S,S] \ (-b[S]) for a covariance-form handle.  Normal equations and Cholesky

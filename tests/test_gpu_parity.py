@@ -364,6 +364,69 @@ def test_locpolyl1_chain_is_the_reference_loop(gpu, ref, refit, randomize):
         assert [(a["passes"], a["visits"]) for a in s4[b0:b0 + 4]] == [(b["passes"], b["visits"]) for b in ref.last_vc_stats]
 
 
+def _csc_to_dense(tri, ep, m):
+    cp, rv, nz = tri
+    out = np.zeros((ep, m), order="F")
+    assert cp[0] == 0 and np.all(np.diff(cp) >= 0) and cp[m] == rv.size == nz.size
+    for g in range(m):
+        rows = rv[cp[g]:cp[g + 1]]
+        assert np.all(np.diff(rows) > 0) and (rows.size == 0 or (rows[0] >= 1 and rows[-1] <= ep))
+        out[rows - 1, g] = nz[cp[g]:cp[g + 1]]
+    return out
+
+
+@pytest.mark.parametrize("form", ["moment", "naive"])
+@pytest.mark.parametrize("refit", [False, True])
+def test_locpolyl1_csc_output_equals_dense(gpu, ref, form, refit, monkeypatch):
+    """locpolyl1 returns SparseMatrixCSC (varying_coefficient_lasso.jl:46-47,69,76).  cdgpu_vc_solve_csc compacts the
+    columns on the device: the CSC triple expands to exactly the dense result of cdgpu_vc_solve / _refit / _chain (bit for
+    bit, same stored pattern as `sparse(out)`), agrees with the oracle, leaves the columns outside a shard empty, and a
+    capacity that is too small comes back as CDGPU_ECAP carrying the entries needed (the mirror retries once)."""
+    if form == "naive":
+        if refit:
+            pytest.skip("device refit needs the moment form")
+        monkeypatch.setenv("CDGPU_VC_FORM", "naive")
+    rng = np.random.default_rng(93)
+    n, p, degree, m = 260, 40, 1, 37
+    ep = p * (degree + 1)
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    Y = X[:, 0] * np.sin(3 * Z) + X[:, 1] * np.cos(2 * Z) + X[:, 2] * Z + 0.1 * rng.standard_normal(n)
+    zgrid = np.linspace(0.05, 0.95, m)
+    o = CDOptions(maxIter=20000, optTol=1e-9)
+    k = GaussianKernel(0.15)
+    od, odR = gpu.locpolyl1(X, Z, Y, zgrid, degree, k, 0.02, refit, o)
+    tri, triR = gpu.locpolyl1(X, Z, Y, zgrid, degree, k, 0.02, refit, o, sparse=True)
+    assert 0 < tri[0][m] < ep * m // 2
+    assert np.array_equal(_csc_to_dense(tri, ep, m), od)
+    orf, orR = ref.locpolyl1(X, Z, Y, zgrid, degree, k, 0.02, refit, o, chain=1)
+    assert np.array_equal(od != 0, orf != 0)
+    if refit:
+        assert np.array_equal(_csc_to_dense(triR, ep, m), odR, equal_nan=True)
+        assert np.array_equal(odR != 0, orR != 0)
+    else:
+        assert triR is None
+    # a shard: only its columns are stored
+    tri_s, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, k, 0.02, refit, o, shard=(5, 19), sparse=True)
+    ds = _csc_to_dense(tri_s, ep, m)
+    assert np.array_equal(ds[:, 5:19], od[:, 5:19]) and not ds[:, :5].any() and not ds[:, 19:].any()
+    tri_e, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, k, 0.02, refit, o, shard=(7, 7), sparse=True)
+    assert tri_e[0][m] == 0
+    if form == "moment":  # the chained solve through the same exit
+        oc, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, k, 0.02, False, o, chain=m)
+        tri_c, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, k, 0.02, False, o, chain=m, sparse=True)
+        assert np.array_equal(_csc_to_dense(tri_c, ep, m), oc)
+    # capacity too small: ECAP with the entries needed in colptr[m]
+    import ctypes as C
+    from cdgpu import _ffi
+    cp = np.zeros(m + 1, dtype=np.int64)
+    rv, nz = np.zeros(3, dtype=np.int64), np.zeros(3)
+    oc_ = o.c()
+    rc = gpu.lib.vc_solve_csc(_ffi.ptr(X), n, p, n, _ffi.ptr(Z), _ffi.ptr(Y), _ffi.ptr(zgrid), m, 0, m, degree, k.kind, k.h, 0.02,
+                              C.byref(oc_), 1, gpu.device, 3, _ffi.ptr(cp), _ffi.ptr(rv), _ffi.ptr(nz), None, None, None, None)
+    assert rc == _ffi.ECAP and cp[m] == tri[0][m]
+
+
 @pytest.mark.parametrize("form", ["quad", "ls"])
 @pytest.mark.parametrize("randomize", [0, 1])
 @pytest.mark.parametrize("engine", ["one_cta", "team"])
