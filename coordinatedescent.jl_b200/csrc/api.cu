@@ -224,6 +224,7 @@ API int cdgpu_destroy(cdgpu_handle h) {
   dfree(h->dcolptr);
   dfree(h->drowval);
   dfree(h->dnzval);
+  dfree(h->dtall);
   if (h->own_lzX) dfree(const_cast<double *>(h->lzX));
   if (h->own_lzy) dfree(const_cast<double *>(h->lzy));
   dfree(h->dslot);
@@ -973,8 +974,8 @@ API int cdgpu_gram_create_lazy(cdgpu_handle *out, const double *X, int64_t n, in
 // The reference's CDLeastSquaresLoss / CDWeightedLSLoss have no such bound (cd_differentiable_function.jl:43-194), so a
 // handle on a taller problem carries an inner LAZY covariance handle over the same device-resident X, y (w):
 // A = X'[W]X/n, b = -X'[W]y/n, the identical minimiser, columns of A formed only for coordinates that become non-zero.
-// Solves run there; f.r = y - X beta is formed afterwards from the active columns.  (CDSqrtLassoLoss has no such form
-// here: tall sqrt-lasso problems still answer CDGPU_ECAP.)
+// Solves run there; f.r = y - X beta is formed afterwards from the active columns.  (CDSqrtLassoLoss has no such form:
+// tall sqrt-lasso problems run the residual form with the rows dealt over the grid, tall_sweep.cu.)
 static int tall_attach(cdgpu_handle_s *h) {
   cdgpu_handle_s *t = new (std::nothrow) cdgpu_handle_s();
   if (!t) return cdgpu_set_error(CDGPU_ENOMEM, "out of host memory");

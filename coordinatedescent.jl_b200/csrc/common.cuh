@@ -257,6 +257,7 @@ struct cdgpu_handle_s {
   int *dflag = nullptr;             // device status word(s)
   double *drsnap = nullptr;         // NaiveArgs::rsnap
   double *dchain = nullptr;         // scratch of the team chain engine (chain_engine.cuh: Multi::hpass, Multi::seq)
+  double *dtall = nullptr;          // per-CTA partial sums of the row-distributed sqrt-lasso sweep (tall_sweep.cu)
   double gram_ms = 0.0;
   int sm_count = 0, max_cluster = 0;
   // lazy covariance form (lazy_gram.cu): dX is then the column CACHE (ld x lz_cap), columns found through dslot
@@ -434,6 +435,7 @@ constexpr size_t CD_MULTI_SCR_BYTES = (size_t)2 * CD_GCAP * 16;
 inline size_t cd_gram_cap(size_t p) { return p < 2048 ? 2048 : (p < (size_t)CD_GCAP ? ((p + 1) & ~(size_t)1) : (size_t)CD_GCAP); } // even
 inline size_t cd_scr_tail(size_t p, size_t n) { return (15 * p + 8 * n + 64 + 4 * (size_t)CD_GCAP + 64 + 1) & ~(size_t)1; }
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a);
+int launch_tall_sqrt(cdgpu_handle_s *h, const NaiveArgs &a); // tall_sweep.cu: rows dealt over the grid (n of any size)
 bool naive_fits(long long n, bool has_w);
 int launch_naive_init(cdgpu_handle_s *h, const NaiveArgs &a); // r = y - X beta, beta dense, inlist
 int launch_colsq(cdgpu_handle_s *h, const double *X, long long ldx, int n, int p, const double *w, double *out,

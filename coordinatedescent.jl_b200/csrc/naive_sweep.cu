@@ -1784,6 +1784,9 @@ bool naive_fits(long long n, bool has_w) {
 int launch_naive_path(cdgpu_handle_s *h, const NaiveArgs &a) {
   static bool attr_done[64] = {false}; // function attributes are per device (context), not per process
   const size_t max_dyn = 227 * 1024;
+  // tall sqrt-lasso problems (r does not fit one CTA's shared memory): rows dealt over the grid, tall_sweep.cu
+  if (a.kind == CDGPU_LOSS_SQRT && !a.scaled && (!naive_fits(a.n, false) || getenv("CDGPU_FORCE_TALL")))
+    return launch_tall_sqrt(h, a);
   const bool known = h->device >= 0 && h->device < 64;
   if (!known || !attr_done[h->device]) {
     CUDA_TRY(cudaFuncSetAttribute(naive_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));

@@ -1,0 +1,296 @@
+// Residual-form sweeps of CDSqrtLassoLoss for TALL problems (cd_differentiable_function.jl:197-291 under the driver of
+// coordinate_descent.jl:7-110): n beyond what one CTA's shared memory holds (naive_sweep.cu keeps a copy of r per CTA,
+// n <= ~28 000).  The reference has no such bound; the covariance form that carries tall LS / WLS problems (api.cu:
+// tall_attach) does not apply to the sqrt-lasso step, which needs ||r|| at every visit.
+//
+// Layout: the ROWS are dealt over the CTAs of one cooperative grid (one CTA per SM); CTA g keeps rows
+// [g L, (g+1) L) of r in its shared memory for the whole call (L = ceil(n / G); in global memory beyond ~25 000 rows per
+// CTA, i.e. n > 3.7 M).  A visit of coordinate k needs s0 = X_k' r and ||r||^2:
+//   s = s0 + x_k a_k,  rsqr+ = ||r||^2 + x_k (2 s0 + x_k a_k)      (a_k = X_k' X_k, the partial residual never formed)
+// then the closed form of :277-283 and r -= X_k h.  Every CTA holds a slice partial of s0 and of ||r||^2; one grid barrier
+// makes them visible, every CTA adds the G partials in the same order and takes the same decision (no broadcast).
+// A WINDOW of 16 consecutive positions of the pass is evaluated per barrier (one warp per coordinate on the slice): the
+// coordinates that do not move (almost all of a full pass) cost no barrier of their own; the first one that moves is
+// applied and the window restarts behind it, so the visit sequence is the reference's.  Barriers per pass =
+// ceil(len / 16) + moves.  The iterate (list, values, dense copy, membership) is written by CTA 0 only; the others read
+// x_k before the window's barrier and the list after the barrier that ends a pass.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+namespace cg = cooperative_groups;
+
+namespace {
+constexpr int TS_T = 512, TS_W = TS_T / 32, TS_PART = TS_W + 1; // doubles per CTA and buffer: 16 dots + the slice's ||r||^2
+constexpr int TS_HDR = 96;                                      // shared doubles ahead of the r slice
+
+__device__ __forceinline__ void ts_grid_sync(unsigned *ctr, unsigned &target, unsigned G) {
+  target += G;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+    }
+  }
+  __syncthreads();
+}
+
+// descendCoordinate!(f::CDSqrtLassoLoss, ...) :242-291 from s0 = X_k' r, a = X_k' X_k, rr = ||r||^2, old = x_k
+__device__ __forceinline__ double ts_step(double s0, double a, double old, double l, double rr) {
+  const double s = old != 0.0 ? fma(old, a, s0) : s0;
+  const double rsq = old != 0.0 ? rr + old * fma(old, a, 2.0 * s0) : rr;
+  const double t = l * sqrt(rsq);
+  if (fabs(s) <= t) return 0.0;
+  const double q = l / sqrt(1.0 - l * l / a) * sqrt(rsq - s * s / a);
+  return s > t ? (s - q) / a : (s + q) / a;
+}
+
+__global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, double *part, int L, int r_in_smem) {
+  extern __shared__ __align__(16) double ts_sm[];
+  double *red = ts_sm;          // [0, TS_PART): sums over the CTAs of the window's dots and of ||r||^2
+  double *wred = ts_sm + 32;    // [32, 48): per-warp partials of a block reduction
+  double *sxk = ts_sm + 48;     // [48, 64): x_k of the window's coordinates
+  int *sk = reinterpret_cast<int *>(ts_sm + 64); // [64, 72): the window's coordinates
+  double *slice_rr = ts_sm + 80; // this CTA's sum of r_i^2
+  const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row0 = (long long)bid * L;
+  const int len = (int)max(0ll, min((long long)L, (long long)a.n - row0));
+  double *r = r_in_smem ? ts_sm + TS_HDR : a.r + row0;
+  unsigned *ctr = reinterpret_cast<unsigned *>(a.flag + 7);
+  unsigned target = 0;
+  if (bid == 0 && tid == 0) __stcg(ctr, 0u);
+  if (r_in_smem)
+    for (int i = tid; i < len; i += TS_T) r[i] = a.r[row0 + i];
+  __syncthreads();
+  cg::this_grid().sync(); // the barrier counter is zero before anyone arrives
+
+  // block sum of v -> *slice_rr (all threads may read it after the call)
+  auto block_sum_to = [&](double v, double *dst) {
+    v = warp_sum(v);
+    if (lane == 0) wred[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      double t = lane < TS_W ? wred[lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) *dst = t;
+    }
+    __syncthreads();
+  };
+  {
+    double acc = 0.0;
+    for (int i = tid; i < len; i += TS_T) acc = fma(r[i], r[i], acc);
+    block_sum_to(acc, slice_rr);
+  }
+
+  int nact = *a.nact; // every CTA's view of the list length (refreshed behind the barrier that ends a pass)
+  int buf = 0;
+  unsigned long long pass_counter = 0;
+  DevStats st;
+  st.passes = st.full_passes = st.visits = st.accepted = 0;
+  st.maxH = 0.0;
+  st.converged = 0;
+  st.outer_iters = 0;
+  st.sigma = 0.0;
+  int status = 0;
+  long long cols_done = 0, out_off = 0;
+  const bool ordered = a.randomize == 0;
+
+  for (int li = 0; li < a.nlambda && status == 0; ++li) {
+    if (li > 0 && !a.accumulate) {
+      st.passes = st.full_passes = st.visits = st.accepted = 0;
+      st.maxH = 0.0;
+    }
+    const double lam = a.lambdas[li];
+    // ---- _coordinateDescent! (coordinate_descent.jl:65-92)
+    st.converged = 0;
+    bool conv = true;
+    for (long long iter = 1; iter <= a.maxIter; ++iter) {
+      const bool full = conv;
+      const int seqlen = full ? a.p : nact;
+      const PermKey pk = cd_perm_key((uint32_t)max(seqlen, 1), a.seed, pass_counter);
+      pass_counter += 1;
+      st.passes += 1;
+      if (full) st.full_passes += 1;
+      double maxH = 0.0;
+      int nlist = nact; // CTA 0, thread 0: the list grows during a full pass
+      // ---- _cdPass! (:94-110), a window of TS_W positions per barrier
+      int i0 = 0;
+      while (i0 < seqlen) {
+        const int wn = min(TS_W, seqlen - i0);
+        if (tid < wn) {
+          const int pos = ordered ? i0 + tid : (int)cd_perm(pk, (uint32_t)(i0 + tid));
+          const int k = full ? pos : __ldcg(a.act + pos);
+          sk[tid] = k;
+          sxk[tid] = __ldcg(a.beta + k); // read before the barrier: CTA 0 writes x_k only behind it
+        }
+        __syncthreads();
+        double *mine = part + ((long long)buf * G + bid) * TS_PART;
+        if (warp < wn) {
+          const double *col = a.X + (long long)sk[warp] * a.ldx + row0;
+          double acc0 = 0.0, acc1 = 0.0;
+          int i = lane;
+          for (; i + 32 < len; i += 64) {
+            acc0 = fma(__ldg(col + i), r[i], acc0);
+            acc1 = fma(__ldg(col + i + 32), r[i + 32], acc1);
+          }
+          if (i < len) acc0 = fma(__ldg(col + i), r[i], acc0);
+          const double d = warp_sum(acc0 + acc1);
+          if (lane == 0) __stcg(mine + warp, d);
+        }
+        if (tid == 0) __stcg(mine + TS_W, *slice_rr);
+        ts_grid_sync(ctr, target, (unsigned)G);
+        // sums over the CTAs, the same order everywhere: value v by warp v (and warp 0 also the ||r||^2 slot)
+        for (int v = warp; v < TS_PART; v += TS_W) {
+          if (v < wn || v == TS_W) {
+            const double *src = part + (long long)buf * G * TS_PART + v;
+            double t = 0.0;
+            for (int g = lane; g < G; g += 32) t += __ldcg(src + (long long)g * TS_PART);
+            t = warp_sum(t);
+            if (lane == 0) red[v] = t;
+          }
+        }
+        buf ^= 1;
+        __syncthreads();
+        // every thread walks the window: the first coordinate that moves ends it
+        const double rr = red[TS_W];
+        int moved = -1;
+        double hmv = 0.0, nwv = 0.0;
+        for (int w = 0; w < wn; ++w) {
+          const int k = sk[w];
+          const double old = sxk[w];
+          const double l = a.omega ? lam * __ldg(a.omega + k) : lam;
+          const double nw = ts_step(red[w], __ldg(a.colsq + k), old, l, rr);
+          const double h = nw - old;
+          st.visits += 1;
+          if (fabs(h) > maxH) maxH = fabs(h);
+          if (h != 0.0) {
+            st.accepted += 1;
+            moved = w;
+            hmv = h;
+            nwv = nw;
+            break;
+          }
+        }
+        if (moved >= 0) {
+          const int k = sk[moved];
+          const double *col = a.X + (long long)k * a.ldx + row0;
+          double acc = 0.0;
+          for (int i = tid; i < len; i += TS_T) {
+            const double v = fma(-__ldg(col + i), hmv, r[i]);
+            r[i] = v;
+            acc = fma(v, v, acc);
+          }
+          if (bid == 0 && tid == 0) { // x[k] = newVal: appended on the first non-zero store (setindex!)
+            __stcg(a.beta + k, nwv);
+            if (nwv != 0.0 && !a.inlist[k]) {
+              a.inlist[k] = 1;
+              a.act[nlist] = k;
+              nlist += 1;
+            }
+          }
+          block_sum_to(acc, slice_rr); // (its barriers also order the window's shared arrays against the next fill)
+          i0 += moved + 1;
+        } else {
+          __syncthreads();
+          i0 += wn;
+        }
+      }
+      // ---- dropzeros!(x) on CTA 0 (the last stored entry moves into a hole), then everyone learns the new list
+      if (bid == 0) {
+        __syncthreads();
+        if (tid == 0) sk[0] = nlist;
+        __syncthreads();
+        const int m = sk[0];
+        for (int i = tid; i < m; i += TS_T) a.actval[i] = __ldcg(a.beta + a.act[i]);
+        __syncthreads();
+        if (tid == 0) {
+          int mm = m, i = 0;
+          while (i < mm) {
+            if (a.actval[i] == 0.0) {
+              a.inlist[a.act[i]] = 0;
+              if (i != mm - 1) {
+                a.actval[i] = a.actval[mm - 1];
+                a.act[i] = a.act[mm - 1];
+              }
+              mm -= 1;
+            } else {
+              i += 1;
+            }
+          }
+          *a.nact = mm;
+        }
+      }
+      ts_grid_sync(ctr, target, (unsigned)G);
+      nact = __ldcg(a.nact);
+      st.maxH = maxH;
+      const bool prev = conv;
+      conv = maxH < a.optTol;
+      if (prev && conv) {
+        st.converged = 1;
+        break;
+      }
+    }
+    // ---- end of this lambda
+    const int nnz = nact;
+    if (!a.accumulate) {
+      if (a.colptr && out_off + nnz > a.capacity) status = 1;
+      if (bid == 0 && status == 0) {
+        if (a.colptr) {
+          for (int i = tid; i < nnz; i += TS_T) {
+            a.rowval[out_off + i] = (long long)a.act[i] + 1;
+            a.nzval[out_off + i] = a.actval[i];
+          }
+          if (tid == 0) a.colptr[li + 1] = out_off + nnz;
+        }
+        if (tid == 0 && a.stats) a.stats[li] = st;
+      }
+      out_off += nnz;
+      if (status == 0) cols_done = li + 1;
+      if (a.max_hat_s >= 0 && nnz > a.max_hat_s) break;
+    } else {
+      cols_done = li + 1;
+    }
+  }
+  if (r_in_smem)
+    for (int i = tid; i < len; i += TS_T) a.r[row0 + i] = r[i];
+  if (bid == 0 && tid == 0) {
+    if (a.accumulate && a.stats) a.stats[0] = st;
+    a.flag[0] = status;
+    a.flag[1] = (int)cols_done;
+  }
+}
+} // namespace
+
+// tall CDSqrtLassoLoss handles (and any sqrt-lasso handle under CDGPU_FORCE_TALL=1): same contract as launch_naive_path
+int launch_tall_sqrt(cdgpu_handle_s *h, const NaiveArgs &a) {
+  if (a.kind != CDGPU_LOSS_SQRT || a.scaled)
+    return cdgpu_set_error(CDGPU_EARG, "the row-distributed sweep is the sqrt-lasso one");
+  static bool attr_done[64] = {false};
+  const size_t max_dyn = 227 * 1024;
+  const bool known = h->device >= 0 && h->device < 64;
+  if (!known || !attr_done[h->device]) {
+    CUDA_TRY(cudaFuncSetAttribute(tall_sqrt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    if (known) attr_done[h->device] = true;
+  }
+  int G = h->sm_count;
+  if (const char *env = getenv("CDGPU_TALL_GRID")) G = std::max(1, std::min(G, atoi(env)));
+  G = (int)std::min<long long>(G, ((long long)a.n + 63) / 64); // at least 64 rows per CTA
+  const int L = (int)((((long long)a.n + G - 1) / G + 1) & ~1ll);
+  size_t dyn = (size_t)(TS_HDR + L) * sizeof(double);
+  int r_in_smem = 1;
+  if (dyn > max_dyn || getenv("CDGPU_TALL_R_GLOBAL")) {
+    r_in_smem = 0;
+    dyn = (size_t)TS_HDR * sizeof(double);
+  }
+  const size_t part_doubles = (size_t)2 * h->sm_count * TS_PART;
+  if (!h->dtall) CUDA_TRY(cudaMalloc((void **)&h->dtall, part_doubles * sizeof(double)));
+  double *part = h->dtall;
+  int Larg = L;
+  void *args[] = {(void *)&a, (void *)&part, (void *)&Larg, (void *)&r_in_smem};
+  CUDA_TRY(cudaLaunchCooperativeKernel(tall_sqrt_kernel, dim3(G), dim3(TS_T), args, dyn, h->stream));
+  CD_COUNT_LAUNCH(1);
+  return CDGPU_OK;
+}

@@ -803,3 +803,70 @@ def test_tall_naive_problem_solves_through_the_lazy_covariance_form(gpu, ref, ki
         s1, s2 = gpu.scaledLasso_(x1, X, y, 0.05, om, io), ref.scaledLasso_(x2, X, y, 0.05, om, io)
         assert_parity(x1.toarray(), x2.toarray())
         assert s1.stats["outer_iters"] == s2.stats["outer_iters"] and s1.σ == pytest.approx(s2.σ, rel=1e-8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("randomize", [0, 1])
+@pytest.mark.parametrize("grid", [None, 3])
+def test_row_distributed_sqrt_lasso_retraces_oracle(gpu, ref, randomize, grid, monkeypatch):
+    """tall_sweep.cu (the residual form with the rows dealt over the grid) forced on a small problem: same passes, visits
+    and accepted steps as the oracle, warm and cold (the internal continuation of coordinate_descent.jl:28-36), ordered
+    and random visits, a λ path through the same launch, weighted penalty; `grid=3` leaves 100 rows per CTA."""
+    monkeypatch.setenv("CDGPU_FORCE_TALL", "1")
+    if grid:
+        monkeypatch.setenv("CDGPU_TALL_GRID", str(grid))
+    rng = np.random.default_rng(77)
+    n, p, s = 300, 700, 10
+    X, y, _ = gauss_problem(n, p, s, seed=78)
+    om = 0.5 + rng.random(p)
+    lam = 3.2
+    for warm in (True, False):
+        o = CDOptions(randomize=randomize, seed=9, warmStart=warm, numSteps=7, **TIGHT)
+        outs = []
+        for be in (gpu, ref):
+            f = be.CDSqrtLassoLoss(y, X)
+            x = SparseIterate(sprand_iterate(p, 0.02, np.random.default_rng(3)))
+            be.coordinateDescent_(x, f, ProxL1(lam, om), o)
+            assert f.last_stats["converged"] == 1
+            outs.append((x.toarray(), f.r, f.last_stats, x.nzval2ind[:x.nnz].copy()))
+        (bg, rg, sg, ig), (br, rr, sr, ir) = outs
+        assert np.count_nonzero(br) >= 3
+        assert_parity(bg, br, sqrt_objective(X, y, bg, lam, om), sqrt_objective(X, y, br, lam, om))
+        # (`accepted` counts h != 0, which near the fixed point is decided by the last bit of a sum taken in another order)
+        assert (sg["passes"], sg["full_passes"], sg["visits"]) == (sr["passes"], sr["full_passes"], sr["visits"])
+        assert abs(sg["accepted"] - sr["accepted"]) <= 0.02 * sr["accepted"]
+        assert list(ig) == list(ir)  # the list order (dropzeros!) too
+        assert np.allclose(rg, y - X @ bg, atol=1e-10)
+    # maxIter cuts the loop at the same place
+    o = CDOptions(randomize=randomize, seed=4, maxIter=3, optTol=1e-12)
+    xs = []
+    for be in (gpu, ref):
+        f = be.CDSqrtLassoLoss(y, X)
+        x = SparseIterate(p)
+        be.coordinateDescent_(x, f, ProxL1(lam, om), o)
+        assert f.last_stats["converged"] == 0 and f.last_stats["passes"] == 3
+        xs.append(x.toarray())
+    assert np.allclose(xs[0], xs[1], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_tall_sqrt_lasso_problem(gpu, ref):
+    """CDSqrtLassoLoss on n = 60 000 rows (r1 / r2: CDGPU_ECAP beyond ~28 000): the rows are dealt over the SMs, each CTA
+    keeps its slice of r in shared memory (tall_sweep.cu).  Same supports, coefficients, passes and visits as the oracle;
+    sqrtLasso front-end on the same data."""
+    n, p, s = 60000, 300, 10
+    X, y, _ = gauss_problem(n, p, s, seed=43)
+    o = CDOptions(maxIter=5000, optTol=1e-11, randomize=False)
+    fg, fr = gpu.CDSqrtLassoLoss(y, X), ref.CDSqrtLassoLoss(y, X)
+    om = fg.stdX()
+    lam = 1.1 * np.sqrt(2 * np.log(p))
+    xg, xr = SparseIterate(p), SparseIterate(p)
+    gpu.coordinateDescent_(xg, fg, ProxL1(lam, om), o)
+    ref.coordinateDescent_(xr, fr, ProxL1(lam, om), o)
+    assert 3 <= np.count_nonzero(xr.toarray()) <= 40
+    assert_parity(xg.toarray(), xr.toarray())
+    assert fg.last_stats["passes"] == fr.last_stats["passes"] and fg.last_stats["visits"] == fr.last_stats["visits"]
+    assert np.allclose(fg.r, y - X @ xg.toarray(), rtol=0, atol=1e-9)
+    sg, sr = gpu.sqrtLasso(X, y, lam, None, o), ref.sqrtLasso(X, y, lam, None, o)
+    assert_parity(sg.x.toarray(), sr.x.toarray())
+    assert sg.σ == pytest.approx(sr.σ, rel=1e-9)
