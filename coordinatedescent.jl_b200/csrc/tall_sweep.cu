@@ -9,19 +9,51 @@
 //   s = s0 + x_k a_k,  rsqr+ = ||r||^2 + x_k (2 s0 + x_k a_k)      (a_k = X_k' X_k, the partial residual never formed)
 // then the closed form of :277-283 and r -= X_k h.  Every CTA holds a slice partial of s0 and of ||r||^2; one grid barrier
 // makes them visible, every CTA adds the G partials in the same order and takes the same decision (no broadcast).
-// A WINDOW of 16 consecutive positions of the pass is evaluated per barrier (one warp per coordinate on the slice): the
-// coordinates that do not move (almost all of a full pass) cost no barrier of their own; the first one that moves is
-// applied and the window restarts behind it, so the visit sequence is the reference's.  Barriers per pass =
-// ceil(len / 16) + moves.  The iterate (list, values, dense copy, membership) is written by CTA 0 only; the others read
-// x_k before the window's barrier and the list after the barrier that ends a pass.
+// In a full pass a WINDOW of 64 consecutive positions is evaluated per barrier (four columns per warp against one read of
+// the slice): the coordinates that do not move (almost all of a full pass) cost no barrier of their own; the first one
+// that moves is applied and the window restarts behind it, so the visit sequence is the reference's.  Barriers per full
+// pass = ceil(p / 64) + moves; a pass over the stored entries takes one barrier per visit (the whole CTA on one column).
+// The iterate (list, values, dense copy, membership) is written by CTA 0 only; the others read x_k before the window's
+// barrier and the list after the barrier that ends a pass.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
 namespace cg = cooperative_groups;
 
 namespace {
-constexpr int TS_T = 512, TS_W = TS_T / 32, TS_PART = TS_W + 1; // doubles per CTA and buffer: 16 dots + the slice's ||r||^2
-constexpr int TS_HDR = 96;                                      // shared doubles ahead of the r slice
+constexpr int TS_T = 512, TS_NW = TS_T / 32;
+constexpr int TS_W = 64, TS_PART = TS_W + 1; // positions per window; doubles per CTA and buffer: the dots + the slice's ||r||^2
+constexpr int TS_HDR = 448;                  // shared doubles ahead of the r slice
+
+__device__ __forceinline__ double2 ts_ld2(const double2 *p) { // X is read once per visit: keep it out of L1
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+// one warp: NC column dots against the same slice of r (16-byte loads, r read once for the NC columns)
+template <int NC>
+__device__ __forceinline__ void ts_warp_dots(const double *const *col, const double *r, int len, int lane, double *out) {
+  double acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+  const int pairs = len >> 1;
+  const double2 *r2 = reinterpret_cast<const double2 *>(r);
+#pragma unroll 2
+  for (int j = lane; j < pairs; j += 32) {
+    const double2 rv = r2[j];
+    double2 xv[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) xv[c] = ts_ld2(reinterpret_cast<const double2 *>(col[c]) + j);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = fma(xv[c].y, rv.y, fma(xv[c].x, rv.x, acc[c]));
+  }
+  if ((len & 1) && lane == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = fma(__ldg(col[c] + len - 1), r[len - 1], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) out[c] = warp_sum(acc[c]);
+}
 
 __device__ __forceinline__ void ts_grid_sync(unsigned *ctr, unsigned &target, unsigned G) {
   target += G;
@@ -39,10 +71,11 @@ __device__ __forceinline__ void ts_grid_sync(unsigned *ctr, unsigned &target, un
 }
 
 // descendCoordinate!(f::CDSqrtLassoLoss, ...) :242-291 from s0 = X_k' r, a = X_k' X_k, rr = ||r||^2, old = x_k
-__device__ __forceinline__ double ts_step(double s0, double a, double old, double l, double rr) {
+// (srr = sqrt(rr), shared by the coordinates of a window that are zero)
+__device__ __forceinline__ double ts_step(double s0, double a, double old, double l, double rr, double srr) {
   const double s = old != 0.0 ? fma(old, a, s0) : s0;
   const double rsq = old != 0.0 ? rr + old * fma(old, a, 2.0 * s0) : rr;
-  const double t = l * sqrt(rsq);
+  const double t = l * (old != 0.0 ? sqrt(rsq) : srr);
   if (fabs(s) <= t) return 0.0;
   const double q = l / sqrt(1.0 - l * l / a) * sqrt(rsq - s * s / a);
   return s > t ? (s - q) / a : (s + q) / a;
@@ -50,15 +83,21 @@ __device__ __forceinline__ double ts_step(double s0, double a, double old, doubl
 
 __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, double *part, int L, int r_in_smem) {
   extern __shared__ __align__(16) double ts_sm[];
-  double *red = ts_sm;          // [0, TS_PART): sums over the CTAs of the window's dots and of ||r||^2
-  double *wred = ts_sm + 32;    // [32, 48): per-warp partials of a block reduction
-  double *sxk = ts_sm + 48;     // [48, 64): x_k of the window's coordinates
-  int *sk = reinterpret_cast<int *>(ts_sm + 64); // [64, 72): the window's coordinates
-  double *slice_rr = ts_sm + 80; // this CTA's sum of r_i^2
+  double *red = ts_sm;           // [0, TS_PART): sums over the CTAs of the window's dots and of ||r||^2
+  double *wred = ts_sm + 72;     // [72, 88): per-warp partials of a block reduction
+  double *sxk = ts_sm + 88;      // [88, 152): x_k of the window's coordinates
+  int *sk = reinterpret_cast<int *>(ts_sm + 152); // [152, 184): the window's coordinates
+  double *slice_rr = ts_sm + 184; // this CTA's sum of r_i^2
+  double *tmp1 = ts_sm + 185;
+  int *smv = reinterpret_cast<int *>(ts_sm + 186); // first mover of the window, per warp of deciders
+  double *scol = ts_sm + 192, *slam = ts_sm + 256, *sh = ts_sm + 320, *snw = ts_sm + 384; // a_k, omega_k, h, new x_k
   const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long row0 = (long long)bid * L;
   const int len = (int)max(0ll, min((long long)L, (long long)a.n - row0));
   double *r = r_in_smem ? ts_sm + TS_HDR : a.r + row0;
+  // 16-byte loads of the column slices (row0 is even): X 16-byte aligned with an even leading dimension
+  const bool vec = (a.ldx & 1) == 0 && (reinterpret_cast<unsigned long long>(a.X) & 15) == 0 &&
+                   (reinterpret_cast<unsigned long long>(a.r) & 15) == 0;
   unsigned *ctr = reinterpret_cast<unsigned *>(a.flag + 7);
   unsigned target = 0;
   if (bid == 0 && tid == 0) __stcg(ctr, 0u);
@@ -73,7 +112,7 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
     if (lane == 0) wred[warp] = v;
     __syncthreads();
     if (warp == 0) {
-      double t = lane < TS_W ? wred[lane] : 0.0;
+      double t = lane < TS_NW ? wred[lane] : 0.0;
       t = warp_sum(t);
       if (lane == 0) *dst = t;
     }
@@ -117,71 +156,156 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
       double maxH = 0.0;
       int nlist = nact; // CTA 0, thread 0: the list grows during a full pass
       // ---- _cdPass! (:94-110), a window of TS_W positions per barrier
-      int i0 = 0;
+      int i0 = 0, wcap = TS_W;
       while (i0 < seqlen) {
-        const int wn = min(TS_W, seqlen - i0);
-        if (tid < wn) {
-          const int pos = ordered ? i0 + tid : (int)cd_perm(pk, (uint32_t)(i0 + tid));
-          const int k = full ? pos : __ldcg(a.act + pos);
-          sk[tid] = k;
-          sxk[tid] = __ldcg(a.beta + k); // read before the barrier: CTA 0 writes x_k only behind it
+        // a sparse pass moves at almost every visit: one position per barrier, the whole CTA on its column;
+        // a full pass moves rarely: up to TS_W positions per barrier, up to four columns per warp.  What lies behind a
+        // mover in its window was read for nothing, so a window ends at the first stored entry (x_k != 0: it will move)
+        // and is narrower (wcap) right after a coordinate has entered
+        int wn = full ? min(wcap, seqlen - i0) : 1;
+        if (tid < 64) {
+          double xk = 0.0;
+          if (tid < wn) {
+            const int pos = ordered ? i0 + tid : (int)cd_perm(pk, (uint32_t)(i0 + tid));
+            const int k = full ? pos : __ldcg(a.act + pos);
+            sk[tid] = k;
+            xk = __ldcg(a.beta + k); // read before the barrier: CTA 0 writes x_k only behind it
+            sxk[tid] = xk;
+            scol[tid] = __ldg(a.colsq + k);
+            slam[tid] = a.omega ? __ldg(a.omega + k) : 1.0;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, xk != 0.0);
+          if (lane == 0) smv[2 + warp] = bal ? __ffs(bal) + 32 * warp : 1 << 20;
         }
         __syncthreads();
+        wn = min(wn, min(smv[2], smv[3]));
         double *mine = part + ((long long)buf * G + bid) * TS_PART;
-        if (warp < wn) {
-          const double *col = a.X + (long long)sk[warp] * a.ldx + row0;
+        if (wn == 1) {
+          const double *col = a.X + (long long)sk[0] * a.ldx + row0;
           double acc0 = 0.0, acc1 = 0.0;
-          int i = lane;
-          for (; i + 32 < len; i += 64) {
-            acc0 = fma(__ldg(col + i), r[i], acc0);
-            acc1 = fma(__ldg(col + i + 32), r[i + 32], acc1);
+          if (vec) {
+            const int pairs = len >> 1;
+            const double2 *c2 = reinterpret_cast<const double2 *>(col), *r2 = reinterpret_cast<const double2 *>(r);
+            int j = tid;
+            for (; j + TS_T < pairs; j += 2 * TS_T) {
+              const double2 x0 = ts_ld2(c2 + j), x1 = ts_ld2(c2 + j + TS_T), r0 = r2[j], r1 = r2[j + TS_T];
+              acc0 = fma(x0.y, r0.y, fma(x0.x, r0.x, acc0));
+              acc1 = fma(x1.y, r1.y, fma(x1.x, r1.x, acc1));
+            }
+            if (j < pairs) {
+              const double2 x0 = ts_ld2(c2 + j), r0 = r2[j];
+              acc0 = fma(x0.y, r0.y, fma(x0.x, r0.x, acc0));
+            }
+            if ((len & 1) && tid == 0) acc1 = fma(__ldg(col + len - 1), r[len - 1], acc1);
+          } else {
+            for (int i = tid; i < len; i += TS_T) acc0 = fma(__ldg(col + i), r[i], acc0);
           }
-          if (i < len) acc0 = fma(__ldg(col + i), r[i], acc0);
-          const double d = warp_sum(acc0 + acc1);
-          if (lane == 0) __stcg(mine + warp, d);
+          block_sum_to(acc0 + acc1, tmp1);
+          if (tid == 0) __stcg(mine, *tmp1);
+        } else if (warp < wn) {
+          const int nc = (wn - warp + TS_NW - 1) / TS_NW; // positions warp, warp + 16, ...
+          const double *col[4];
+          double d[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) col[c] = a.X + (long long)sk[min(warp + c * TS_NW, wn - 1)] * a.ldx + row0;
+          if (vec) {
+            if (nc == 4) ts_warp_dots<4>(col, r, len, lane, d);
+            else if (nc == 3) ts_warp_dots<3>(col, r, len, lane, d);
+            else if (nc == 2) ts_warp_dots<2>(col, r, len, lane, d);
+            else ts_warp_dots<1>(col, r, len, lane, d);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              double acc = 0.0;
+              if (c < nc)
+                for (int i = lane; i < len; i += 32) acc = fma(__ldg(col[c] + i), r[i], acc);
+              d[c] = warp_sum(acc);
+            }
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < nc) __stcg(mine + warp + c * TS_NW, d[c]);
+          }
         }
         if (tid == 0) __stcg(mine + TS_W, *slice_rr);
         ts_grid_sync(ctr, target, (unsigned)G);
-        // sums over the CTAs, the same order everywhere: value v by warp v (and warp 0 also the ||r||^2 slot)
-        for (int v = warp; v < TS_PART; v += TS_W) {
-          if (v < wn || v == TS_W) {
-            const double *src = part + (long long)buf * G * TS_PART + v;
-            double t = 0.0;
-            for (int g = lane; g < G; g += 32) t += __ldcg(src + (long long)g * TS_PART);
-            t = warp_sum(t);
-            if (lane == 0) red[v] = t;
+        // sums over the CTAs, the same order everywhere: values v = warp, warp + 16, ... (warp 0 also the ||r||^2 slot)
+        {
+          double t[5];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const int v = warp + c * TS_NW;
+            t[c] = 0.0;
+            if (v < TS_PART && (v < wn || v == TS_W)) {
+              const double *src = part + (long long)buf * G * TS_PART + v;
+              for (int g = lane; g < G; g += 32) t[c] += __ldcg(src + (long long)g * TS_PART);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const int v = warp + c * TS_NW;
+            if (v < TS_PART && (v < wn || v == TS_W)) {
+              const double tv = warp_sum(t[c]);
+              if (lane == 0) red[v] = tv;
+            }
           }
         }
         buf ^= 1;
         __syncthreads();
-        // every thread walks the window: the first coordinate that moves ends it
+        // the coordinates ahead of the first one that moves leave r as it is, so every position of the window is decided
+        // on its own (thread w: position w) and the first mover ends the window
         const double rr = red[TS_W];
-        int moved = -1;
-        double hmv = 0.0, nwv = 0.0;
-        for (int w = 0; w < wn; ++w) {
-          const int k = sk[w];
-          const double old = sxk[w];
-          const double l = a.omega ? lam * __ldg(a.omega + k) : lam;
-          const double nw = ts_step(red[w], __ldg(a.colsq + k), old, l, rr);
-          const double h = nw - old;
-          st.visits += 1;
-          if (fabs(h) > maxH) maxH = fabs(h);
-          if (h != 0.0) {
-            st.accepted += 1;
-            moved = w;
-            hmv = h;
-            nwv = nw;
-            break;
+        if (tid < 64) {
+          double nw = 0.0, h = 0.0;
+          if (tid < wn) {
+            nw = ts_step(red[tid], scol[tid], sxk[tid], slam[tid] * lam, rr, sqrt(rr));
+            h = nw - sxk[tid];
+            sh[tid] = h;
+            snw[tid] = nw;
           }
+          const unsigned bal = __ballot_sync(0xffffffffu, h != 0.0);
+          if (lane == 0) smv[warp] = bal ? __ffs(bal) - 1 + 32 * warp : -1;
+        }
+        __syncthreads();
+        const int moved = smv[0] >= 0 ? smv[0] : smv[1];
+        double hmv = 0.0, nwv = 0.0;
+        if (moved >= 0) {
+          hmv = sh[moved];
+          nwv = snw[moved];
+          st.visits += moved + 1;
+          st.accepted += 1;
+          if (fabs(hmv) > maxH) maxH = fabs(hmv);
+        } else {
+          st.visits += wn;
         }
         if (moved >= 0) {
           const int k = sk[moved];
           const double *col = a.X + (long long)k * a.ldx + row0;
           double acc = 0.0;
-          for (int i = tid; i < len; i += TS_T) {
-            const double v = fma(-__ldg(col + i), hmv, r[i]);
-            r[i] = v;
-            acc = fma(v, v, acc);
+          if (vec) {
+            const int pairs = len >> 1;
+            const double2 *c2 = reinterpret_cast<const double2 *>(col);
+            double2 *r2 = reinterpret_cast<double2 *>(r);
+            for (int j = tid; j < pairs; j += TS_T) {
+              const double2 x = ts_ld2(c2 + j);
+              double2 v = r2[j];
+              v.x = fma(-x.x, hmv, v.x);
+              v.y = fma(-x.y, hmv, v.y);
+              r2[j] = v;
+              acc = fma(v.y, v.y, fma(v.x, v.x, acc));
+            }
+            if ((len & 1) && tid == 0) {
+              const double v = fma(-__ldg(col + len - 1), hmv, r[len - 1]);
+              r[len - 1] = v;
+              acc = fma(v, v, acc);
+            }
+          } else {
+            for (int i = tid; i < len; i += TS_T) {
+              const double v = fma(-__ldg(col + i), hmv, r[i]);
+              r[i] = v;
+              acc = fma(v, v, acc);
+            }
           }
           if (bid == 0 && tid == 0) { // x[k] = newVal: appended on the first non-zero store (setindex!)
             __stcg(a.beta + k, nwv);
@@ -193,9 +317,11 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
           }
           block_sum_to(acc, slice_rr); // (its barriers also order the window's shared arrays against the next fill)
           i0 += moved + 1;
+          if (sxk[moved] == 0.0) wcap = TS_NW; // an entering coordinate: others tend to follow closely
         } else {
           __syncthreads();
           i0 += wn;
+          wcap = min(TS_W, 2 * wcap);
         }
       }
       // ---- dropzeros!(x) on CTA 0 (the last stored entry moves into a hole), then everyone learns the new list
