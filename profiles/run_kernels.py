@@ -46,6 +46,21 @@ if "c2" in which:
     print("c2: gram %.2f ms, path %.2f ms, visits %d" % (f.gram_ms, path.stats[0]["device_ms"], sum(s["visits"] for s in path.stats)))
     f.close()
     del Xd, yd
+if "tall" in which:  # tall sqrt-lasso: the row-distributed sweep of tall_sweep.cu
+    n, p, s = 1000000, 500, 10
+    Xd = randn_cols(p, n)
+    yd = Xd[:s].T @ (1.0 + torch.rand(s, device="cuda", dtype=torch.float64, generator=g)) + torch.randn(n, device="cuda", dtype=torch.float64, generator=g)
+    torch.cuda.synchronize()
+    f = cdgpu.CDSqrtLassoLoss.__new__(cdgpu.CDSqrtLassoLoss)
+    cdgpu.api._Loss.__init__(f, lib)
+    f.n, f.p = n, p
+    lib.check(lib.naive_create_dev(C.byref(f._h), cdgpu._ffi.LOSS_SQRT, C.c_void_p(Xd.data_ptr()), n, p, n, C.c_void_p(yd.data_ptr()), None, 0))
+    om = f.stdX()
+    x = SparseIterate(p)
+    be.coordinateDescent_(x, f, ProxL1(1.1 * math.sqrt(2 * math.log(p)), om), CDOptions(randomize=False))
+    print("tall:", f.last_stats)
+    f.close()
+    del Xd, yd
 if "c3" in which:
     n, p, s = 5000, 50000, 20
     Xd = randn_cols(p, n)
