@@ -48,6 +48,7 @@ C2_VISITS = 3990575
 NCU_TRAFFIC = {
     "gram_syrk_kernel": (30.228562e9 + 3.203871e9, "profiles/r1d_kernels_ncu.txt"),
     "naive_path_kernel_c3": (6.542697e9 + 0.010799e9, "profiles/r5_naive_path_ncu.txt"),
+    "tall_sqrt_kernel": (9.675816e9 + 0.003752e9, "profiles/r7_tall_sqrt_ncu.txt (same n, p; profiles/run_kernels.py tall)"),
 }
 try:
     NCU_TRAFFIC.update({k: tuple(v) for k, v in json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).items()})
@@ -203,6 +204,52 @@ def c3_metrics(be, local, hbm, reps=3):
     tr = NCU_TRAFFIC.get("naive_path_kernel_c3", (None, None))
     return {"workload": f"C3 sqrt-lasso n={n} p={p} lambda={lam:.3f}, naive form, X 2.0 GB resident in HBM, one launch per solve",
             "kernel": "naive_path_kernel", "device_ms": ms, "device_ms_runs": [r["device_ms"] for r in runs],
+            "visits": st["visits"], "passes": st["passes"], "full_passes": st["full_passes"], "nnz": st["nnz"],
+            "converged": bool(st["converged"]), "visits_per_sec": st["visits"] / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                         "bytes_per_visit": 8 * n, "bytes_per_launch": 8 * n * st["visits"], "launch_ms": ms,
+                         "traffic": tr[0], "traffic_source": tr[1]}}
+
+
+def tall_sqrt_metrics(be, local, hbm, reps=3):
+    """Tall sqrt-lasso (n = 10^6, p = 500: X 4 GB resident in HBM): CDSqrtLassoLoss beyond one CTA's shared memory, the
+    row-distributed sweep of csrc/tall_sweep.cu.  Same timing as c3_metrics."""
+    import torch
+
+    import cdgpu
+    from cdgpu import CDOptions, ProxL1, SparseIterate
+    lib = be.lib
+    n, p, s = 1000000, 500, 10
+    g = torch.Generator(device="cuda")
+    g.manual_seed(125)
+    Xd = torch.empty((p, n), device="cuda", dtype=torch.float64)
+    for j0 in range(0, p, 50):
+        Xd[j0:j0 + 50].normal_(generator=g)
+    beta = 1.0 + torch.rand(s, device="cuda", dtype=torch.float64, generator=g)
+    yd = Xd[:s].T @ beta + torch.randn(n, device="cuda", dtype=torch.float64, generator=g)
+    torch.cuda.synchronize()
+    f = cdgpu.CDSqrtLassoLoss.__new__(cdgpu.CDSqrtLassoLoss)
+    cdgpu.api._Loss.__init__(f, lib)
+    f.n, f.p = n, p
+    lib.check(lib.naive_create_dev(C.byref(f._h), cdgpu._ffi.LOSS_SQRT, C.c_void_p(Xd.data_ptr()), n, p, n,
+                                   C.c_void_p(yd.data_ptr()), None, local))
+    om = f.stdX()
+    lam = 1.1 * math.sqrt(2 * math.log(p))
+    runs = []
+    for i in range(reps + 1):
+        x = SparseIterate(p)
+        be.coordinateDescent_(x, f, ProxL1(lam, om), CDOptions(randomize=False))
+        if i:
+            runs.append(dict(f.last_stats, nnz=x.nnz))
+    f.close()
+    del Xd, yd
+    ms = float(np.mean([r["device_ms"] for r in runs]))
+    st = runs[-1]
+    gbs = 8 * n * st["visits"] / (ms * 1e-3) / 1e9
+    tr = NCU_TRAFFIC.get("tall_sqrt_kernel", (None, None))
+    return {"workload": f"tall sqrt-lasso n={n} p={p} lambda={lam:.3f} (omega = stdX), residual form with the rows dealt over the "
+                        "SMs, X 4.0 GB resident in HBM, one launch per solve",
+            "kernel": "tall_sqrt_kernel", "device_ms": ms, "device_ms_runs": [r["device_ms"] for r in runs],
             "visits": st["visits"], "passes": st["passes"], "full_passes": st["full_passes"], "nnz": st["nnz"],
             "converged": bool(st["converged"]), "visits_per_sec": st["visits"] / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
@@ -809,7 +856,8 @@ def main():
             except Exception:  # noqa: BLE001
                 ref1 = None
         for name, fn in (("c1_lasso", lambda: c1_metrics(be, ref1)), ("c3_sqrt_lasso", lambda: c3_metrics(be, local, hbm)),
-                         ("c4_vc_lasso", lambda: c4_metrics(be, hbm))):
+                         ("c4_vc_lasso", lambda: c4_metrics(be, hbm)),
+                         ("tall_sqrt_lasso", lambda: tall_sqrt_metrics(be, local, hbm))):
             try:
                 sec[name] = fn()
             except Exception as e:  # noqa: BLE001  (side measurements must never cost the headline line)
