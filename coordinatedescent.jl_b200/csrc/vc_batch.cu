@@ -5,7 +5,7 @@
 //   sd_k = sqrt(sum_i w_i eX_ik^2 / n) (utils.jl:140-151),
 // solved by the reference's CD loop on CDWeightedLSLoss (cd_differentiable_function.jl:165-194).
 //
-// B200 design.  DEFAULT (ep <= 256): the MOMENT FORM further down — all local Gram matrices of all grid points are
+// B200 design.  DEFAULT (ep <= 256; up to 512 for refit / chains / lvocv): the MOMENT FORM further down — all local Gram matrices of all grid points are
 // one FP64 tensor-core GEMM (Z'V, gram_dmma.cu) and each local lasso is a covariance-form CD solved by ONE WARP
 // (vc_cov_kernel), with the refit (cdgpu_vc_solve_refit) and the leave-one-out scaled-lasso problems of
 // lvocv_locpolyl1 (cdgpu_vc_lvocv) in the same kernel.  RESIDUAL FORM (CDGPU_VC_FORM=naive, or ep > 256), first
@@ -716,7 +716,7 @@ static int vc_solve_moment(const double *X, int64_t n, int64_t p, int64_t ldx, c
   const int nu = (int)((ep + 31) / 32);
   const int ring = 4; // columns of the compact Gram in flight per warp (see vc_cov_kernel.cuh)
   const void *kfn = harr ? vc_cov_pick_lvo(nu) : vc_cov_pick_std(nu);
-  const size_t wsz = vc_cov_warp_bytes((int)ep, nu <= 6 ? std::max(nu, 1) : 8, ring);
+  const size_t wsz = vc_cov_warp_bytes((int)ep, vc_cov_inst(nu), ring);
   const size_t dyn = VCW * wsz;
   VM_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   int occ = 0;
@@ -848,7 +848,8 @@ API int cdgpu_vc_lvocv(const double *X, int64_t n, int64_t p, int64_t ldx, const
   if (opt->maxIter < 0 || opt->randomize < 0 || opt->randomize > 1) return cdgpu_set_error(CDGPU_EARG, "bad options");
   const int64_t ep = p * (degree + 1);
   if (n > 0x7fffffff || ep > 0x7fffffff || m > 0x7fffffff) return cdgpu_set_error(CDGPU_EDIM, "sizes must fit in 31 bits");
-  if (ep > 256) return cdgpu_set_error(CDGPU_ECAP, "lvocv needs the moment form: p*(degree+1) = %lld exceeds 256", (long long)ep);
+  if (ep > VC_COV_MAX_EP)
+    return cdgpu_set_error(CDGPU_ECAP, "lvocv needs the moment form: p*(degree+1) = %lld exceeds %d", (long long)ep, VC_COV_MAX_EP);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -936,15 +937,17 @@ static int vc_solve_impl(const double *X, int64_t n, int64_t p, int64_t ldx, con
     // moment (covariance) form unless the expanded problem is too wide for the warp kernel's registers;
     // CDGPU_VC_FORM=naive keeps the residual-form kernels below
     const char *form = getenv("CDGPU_VC_FORM");
-    if (ep <= 256 && (wantR || !(form && strcmp(form, "naive") == 0)))
+    // (256 < ep <= 512: the 12- and 16-slot instances of the moment kernel spill registers, so the plain solve keeps the
+    // residual form there and only what needs the moment form - refit, chained grid points - takes them)
+    if ((ep <= 256 && (wantR || !(form && strcmp(form, "naive") == 0))) || (ep <= VC_COV_MAX_EP && (wantR || chain > 1)))
       return vc_solve_moment(X, n, p, ldx, z, y, zgrid, m, m_begin, m_end, degree, kernel_kind, bandwidth, lambda0, opt,
                              device, out, outR, stats, nullptr, nullptr, chain, csc);
     if (chain > 1)
-      return cdgpu_set_error(CDGPU_ECAP, "chained grid points need the moment form: p*(degree+1) = %lld exceeds 256 (or CDGPU_VC_FORM=naive)",
-                             (long long)ep);
+      return cdgpu_set_error(CDGPU_ECAP, "chained grid points need the moment form: p*(degree+1) = %lld exceeds %d",
+                             (long long)ep, VC_COV_MAX_EP);
     if (wantR)
-      return cdgpu_set_error(CDGPU_ECAP, "refit on the device needs the moment form: p*(degree+1) = %lld exceeds 256",
-                             (long long)ep);
+      return cdgpu_set_error(CDGPU_ECAP, "refit on the device needs the moment form: p*(degree+1) = %lld exceeds %d",
+                             (long long)ep, VC_COV_MAX_EP);
   }
   int nr = n <= 128 ? 4 : (n <= 256 ? 8 : (n <= 512 ? 16 : 0)); // 0: CTA-per-problem kernel
   if (const char *env = getenv("CDGPU_VC_THREADS")) nr = atoi(env) == 32 ? nr : 0;

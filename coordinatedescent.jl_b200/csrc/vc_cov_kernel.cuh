@@ -57,6 +57,10 @@ __host__ __device__ inline size_t vc_cov_warp_bytes(int ep, int nu, int ring) { 
   return ((size_t)(ring * RS + 8 * ep) * sizeof(double) + (size_t)(6 * ep + 4) * sizeof(int) + (size_t)ep + 15) / 16 * 16;
 }
 
+// slots per lane of the kernel instance that serves nu = ceil(ep / 32) (VC_DEFINE_PICK below)
+__host__ __device__ inline int vc_cov_inst(int nu) { return nu <= 6 ? (nu < 1 ? 1 : nu) : (nu <= 8 ? 8 : (nu <= 12 ? 12 : 16)); }
+constexpr int VC_COV_MAX_EP = 512; // widest expanded problem of the moment form (16 slots per lane)
+
 template <int OFF>
 __device__ __forceinline__ void vc_cp16(unsigned dst, const char *src) {
   asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%2], 16;" ::"r"(dst), "l"(src), "n"(OFF) : "memory");
@@ -703,5 +707,7 @@ __global__ void __launch_bounds__(VCW * 32, VC_RING > 4 ? 9 : 11) vc_cov_kernel(
            : nu == 4 ? (const void *)vc_cov_kernel<4, LV, RG>              \
            : nu == 5 ? (const void *)vc_cov_kernel<5, LV, RG>              \
            : nu == 6 ? (const void *)vc_cov_kernel<6, LV, RG>              \
-                     : (const void *)vc_cov_kernel<8, LV, RG>;             \
+           : nu <= 8 ? (const void *)vc_cov_kernel<8, LV, RG>              \
+           : nu <= 12 ? (const void *)vc_cov_kernel<12, LV, RG>            \
+                      : (const void *)vc_cov_kernel<16, LV, RG>;           \
   }

@@ -244,7 +244,7 @@ int cdgpu_vc_solve_refit(const double *X, int64_t n, int64_t p, int64_t ldx, con
  * [m_begin, m_end) are cut into runs of `chain` consecutive points; a run is solved by one warp, point after point,
  * each from the previous one's iterate; the first point of a run starts from zero.  chain = m_end - m_begin is the
  * reference's loop exactly (one sequential chain: same iterates, passes and visits as the CPU path); chain = 1 is
- * cdgpu_vc_solve / cdgpu_vc_solve_refit.  outR may be NULL (no refit).  CDGPU_ECAP when p*(degree+1) > 256. */
+ * cdgpu_vc_solve / cdgpu_vc_solve_refit.  outR may be NULL (no refit).  CDGPU_ECAP when p*(degree+1) > 512. */
 int cdgpu_vc_solve_chain(const double *X, int64_t n, int64_t p, int64_t ldx, const double *z, const double *y,
                          const double *zgrid, int64_t m, int64_t m_begin, int64_t m_end, int degree, int kernel_kind,
                          double bandwidth, double lambda0, const cdgpu_options *opt, int64_t chain, int device,

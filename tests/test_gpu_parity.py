@@ -286,10 +286,11 @@ def test_locpolyl1_parity(gpu, ref, kernel, degree, form, monkeypatch):
     assert np.array_equal(a[:, :12], og[:, :12]) and np.array_equal(b[:, 12:], og[:, 12:])
 
 
-@pytest.mark.parametrize("p,degree", [(28, 2), (100, 1), (64, 3)])
+@pytest.mark.parametrize("p,degree", [(28, 2), (100, 1), (64, 3), (120, 2), (128, 3)])
 def test_locpolyl1_moment_form_lane_slot_counts(gpu, ref, p, degree, monkeypatch):
-    """ep = 84, 200, 256: three, seven (kernel instance 8) and eight coordinates per lane; the grid is also cut into
-    chunks of two problems (CDGPU_VC_CHUNK) to cover the chunked driver."""
+    """ep = 84, 200, 256: three, seven (kernel instance 8) and eight coordinates per lane; ep = 360, 512 (r1 / r2:
+    CDGPU_ECAP for the device refit above 256): the 12- and 16-slot instances; the grid is also cut into chunks of two
+    problems (CDGPU_VC_CHUNK) to cover the chunked driver."""
     monkeypatch.setenv("CDGPU_VC_CHUNK", "2")
     rng = np.random.default_rng(84)
     n = 300
@@ -870,3 +871,31 @@ def test_tall_sqrt_lasso_problem(gpu, ref):
     sg, sr = gpu.sqrtLasso(X, y, lam, None, o), ref.sqrtLasso(X, y, lam, None, o)
     assert_parity(sg.x.toarray(), sr.x.toarray())
     assert sg.σ == pytest.approx(sr.σ, rel=1e-9)
+
+
+@pytest.mark.gpu
+def test_wide_local_problems_chain_and_lvocv(gpu, ref):
+    """ep = 300 > 256 (r1 / r2: CDGPU_ECAP): the reference's warm-start chain (cdgpu_vc_solve_chain, chain = m) and
+    lvocv_locpolyl1 run on the 12-slot instance of the moment kernel: same passes / visits per grid point as the CPU
+    loop, same leave-one-out errors."""
+    rng = np.random.default_rng(96)
+    n, p, degree, m = 200, 150, 1, 6
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = rng.random(n)
+    Y = X[:, 0] * np.sin(3 * Z) + X[:, 1] * np.cos(2 * Z) + X[:, 2] * Z + 0.1 * rng.standard_normal(n)
+    zgrid = np.linspace(0.2, 0.8, m)
+    o = CDOptions(randomize=0, maxIter=20000, optTol=1e-6)
+    og, _ = gpu.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.05, False, o, chain=m)
+    sg = gpu.last_vc_stats
+    orf, _ = ref.locpolyl1(X, Z, Y, zgrid, degree, GaussianKernel(0.2), 0.05, False, o)
+    sr = ref.last_vc_stats
+    assert np.count_nonzero(orf) > 2 * m
+    assert np.array_equal(og != 0, orf != 0) and np.max(np.abs(og - orf)) <= 1e-9 * np.max(np.abs(orf))
+    assert [(a["passes"], a["visits"]) for a in sg] == [(b["passes"], b["visits"]) for b in sr]
+    n2 = 40
+    o2 = CDOptions(randomize=0, warmStart=False, **TIGHT)
+    h = np.array([0.3])
+    mg = gpu.lvocv_locpolyl1(X[:n2], Z[:n2], Y[:n2], degree, h, GaussianKernel, 0.5, o2)
+    sq_g = gpu.last_lvocv_sqerr.copy()
+    mr = ref.lvocv_locpolyl1(X[:n2], Z[:n2], Y[:n2], degree, h, GaussianKernel, 0.5, o2)
+    assert np.allclose(sq_g, ref.last_lvocv_sqerr, rtol=1e-6, atol=1e-12) and np.allclose(mg, mr, rtol=1e-8)
