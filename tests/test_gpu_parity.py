@@ -838,6 +838,20 @@ def test_row_distributed_sqrt_lasso_retraces_oracle(gpu, ref, randomize, grid, m
         assert abs(sg["accepted"] - sr["accepted"]) <= 0.02 * sr["accepted"]
         assert list(ig) == list(ir)  # the list order (dropzeros!) too
         assert np.allclose(rg, y - X @ bg, atol=1e-10)
+    # a warm-started λ path through the same launch (CSC output and per-λ statistics written by the kernel), max_hat_s
+    lams = np.array([6.0, 4.5, 3.2, 2.4])
+    o = CDOptions(randomize=randomize, seed=9, **TIGHT)
+    paths = []
+    for be in (gpu, ref):
+        f = be.CDSqrtLassoLoss(y, X)
+        paths.append(be.LassoPath(None, None, lams, o, standardizeX=om, loss=f))
+        paths.append(be.LassoPath(None, None, lams, o, standardizeX=om, loss=f, max_hat_s=4))
+    pg, pgs, pr, prs = paths
+    assert len(pg.βpath) == len(pr.βpath) == 4 and len(pgs.βpath) == len(prs.βpath) < 4
+    for i in range(4):
+        assert_parity(pg.βpath[i].toarray(), pr.βpath[i].toarray())
+        assert (pg.stats[i]["passes"], pg.stats[i]["visits"]) == (pr.stats[i]["passes"], pr.stats[i]["visits"])
+    assert pg.βpath[-1].nnz > pg.βpath[0].nnz
     # maxIter cuts the loop at the same place
     o = CDOptions(randomize=randomize, seed=4, maxIter=3, optTol=1e-12)
     xs = []
