@@ -22,8 +22,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 constexpr int TS_T = 512, TS_NW = TS_T / 32;
-constexpr int TS_W = 64, TS_PART = TS_W + 1; // positions per window; doubles per CTA and buffer: the dots + the slice's ||r||^2
-constexpr int TS_HDR = 448;                  // shared doubles ahead of the r slice
+constexpr int TS_W = 256, TS_PART = TS_W + 1; // most positions per window; doubles per CTA and buffer: the dots + the slice's ||r||^2
+constexpr int TS_HDR = 1700;                  // shared doubles ahead of the r slice
 
 __device__ __forceinline__ double2 ts_ld2(const double2 *p) { // X is read once per visit: keep it out of L1
   double2 v;
@@ -81,16 +81,15 @@ __device__ __forceinline__ double ts_step(double s0, double a, double old, doubl
   return s > t ? (s - q) / a : (s + q) / a;
 }
 
-__global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, double *part, int L, int r_in_smem) {
+__global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, double *part, int L, int r_in_smem, int wmax) {
   extern __shared__ __align__(16) double ts_sm[];
   double *red = ts_sm;           // [0, TS_PART): sums over the CTAs of the window's dots and of ||r||^2
-  double *wred = ts_sm + 72;     // [72, 88): per-warp partials of a block reduction
-  double *sxk = ts_sm + 88;      // [88, 152): x_k of the window's coordinates
-  int *sk = reinterpret_cast<int *>(ts_sm + 152); // [152, 184): the window's coordinates
-  double *slice_rr = ts_sm + 184; // this CTA's sum of r_i^2
-  double *tmp1 = ts_sm + 185;
-  int *smv = reinterpret_cast<int *>(ts_sm + 186); // first mover of the window, per warp of deciders
-  double *scol = ts_sm + 192, *slam = ts_sm + 256, *sh = ts_sm + 320, *snw = ts_sm + 384; // a_k, omega_k, h, new x_k
+  double *wred = ts_sm + 264;    // [264, 280): per-warp partials of a block reduction
+  double *slice_rr = ts_sm + 280; // this CTA's sum of r_i^2
+  double *tmp1 = ts_sm + 281;
+  int *smv = reinterpret_cast<int *>(ts_sm + 282); // [282, 290): per warp of deciders, first mover [0, 8) / first stored entry [8, 16)
+  int *sk = reinterpret_cast<int *>(ts_sm + 290);  // [290, 418): the window's coordinates
+  double *sxk = ts_sm + 418, *scol = ts_sm + 674, *slam = ts_sm + 930, *sh = ts_sm + 1186, *snw = ts_sm + 1442; // x_k, a_k, omega_k, h, new x_k
   const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long row0 = (long long)bid * L;
   const int len = (int)max(0ll, min((long long)L, (long long)a.n - row0));
@@ -156,14 +155,14 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
       double maxH = 0.0;
       int nlist = nact; // CTA 0, thread 0: the list grows during a full pass
       // ---- _cdPass! (:94-110), a window of TS_W positions per barrier
-      int i0 = 0, wcap = TS_W;
+      int i0 = 0, wcap = wmax;
       while (i0 < seqlen) {
         // a sparse pass moves at almost every visit: one position per barrier, the whole CTA on its column;
         // a full pass moves rarely: up to TS_W positions per barrier, up to four columns per warp.  What lies behind a
         // mover in its window was read for nothing, so a window ends at the first stored entry (x_k != 0: it will move)
         // and is narrower (wcap) right after a coordinate has entered
         int wn = full ? min(wcap, seqlen - i0) : 1;
-        if (tid < 64) {
+        if (tid < TS_W) {
           double xk = 0.0;
           if (tid < wn) {
             const int pos = ordered ? i0 + tid : (int)cd_perm(pk, (uint32_t)(i0 + tid));
@@ -175,10 +174,11 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
             slam[tid] = a.omega ? __ldg(a.omega + k) : 1.0;
           }
           const unsigned bal = __ballot_sync(0xffffffffu, xk != 0.0);
-          if (lane == 0) smv[2 + warp] = bal ? __ffs(bal) + 32 * warp : 1 << 20;
+          if (lane == 0) smv[8 + warp] = bal ? __ffs(bal) + 32 * warp : 1 << 20;
         }
         __syncthreads();
-        wn = min(wn, min(smv[2], smv[3]));
+#pragma unroll
+        for (int q = 0; q < TS_W / 32; ++q) wn = min(wn, smv[8 + q]);
         double *mine = part + ((long long)buf * G + bid) * TS_PART;
         if (wn == 1) {
           const double *col = a.X + (long long)sk[0] * a.ldx + row0;
@@ -203,39 +203,42 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
           block_sum_to(acc0 + acc1, tmp1);
           if (tid == 0) __stcg(mine, *tmp1);
         } else if (warp < wn) {
-          const int nc = (wn - warp + TS_NW - 1) / TS_NW; // positions warp, warp + 16, ...
-          const double *col[4];
-          double d[4];
+          const int nc = (wn - warp + TS_NW - 1) / TS_NW; // positions warp, warp + 16, ...: four at a time
+          for (int c0 = 0; c0 < nc; c0 += 4) {
+            const int n4 = min(4, nc - c0);
+            const double *col[4];
+            double d[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) col[c] = a.X + (long long)sk[min(warp + c * TS_NW, wn - 1)] * a.ldx + row0;
-          if (vec) {
-            if (nc == 4) ts_warp_dots<4>(col, r, len, lane, d);
-            else if (nc == 3) ts_warp_dots<3>(col, r, len, lane, d);
-            else if (nc == 2) ts_warp_dots<2>(col, r, len, lane, d);
-            else ts_warp_dots<1>(col, r, len, lane, d);
-          } else {
+            for (int c = 0; c < 4; ++c) col[c] = a.X + (long long)sk[min(warp + (c0 + c) * TS_NW, wn - 1)] * a.ldx + row0;
+            if (vec) {
+              if (n4 == 4) ts_warp_dots<4>(col, r, len, lane, d);
+              else if (n4 == 3) ts_warp_dots<3>(col, r, len, lane, d);
+              else if (n4 == 2) ts_warp_dots<2>(col, r, len, lane, d);
+              else ts_warp_dots<1>(col, r, len, lane, d);
+            } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              double acc = 0.0;
-              if (c < nc)
-                for (int i = lane; i < len; i += 32) acc = fma(__ldg(col[c] + i), r[i], acc);
-              d[c] = warp_sum(acc);
+              for (int c = 0; c < 4; ++c) {
+                double acc = 0.0;
+                if (c < n4)
+                  for (int i = lane; i < len; i += 32) acc = fma(__ldg(col[c] + i), r[i], acc);
+                d[c] = warp_sum(acc);
+              }
             }
-          }
-          if (lane == 0) {
+            if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (c < nc) __stcg(mine + warp + c * TS_NW, d[c]);
+              for (int c = 0; c < 4; ++c)
+                if (c < n4) __stcg(mine + warp + (c0 + c) * TS_NW, d[c]);
+            }
           }
         }
         if (tid == 0) __stcg(mine + TS_W, *slice_rr);
         ts_grid_sync(ctr, target, (unsigned)G);
         // sums over the CTAs, the same order everywhere: values v = warp, warp + 16, ... (warp 0 also the ||r||^2 slot)
-        {
-          double t[5];
+        for (int c0 = 0; c0 <= TS_W / TS_NW; c0 += 4) {
+          double t[4];
 #pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            const int v = warp + c * TS_NW;
+          for (int c = 0; c < 4; ++c) {
+            const int v = warp + (c0 + c) * TS_NW;
             t[c] = 0.0;
             if (v < TS_PART && (v < wn || v == TS_W)) {
               const double *src = part + (long long)buf * G * TS_PART + v;
@@ -243,20 +246,21 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
             }
           }
 #pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            const int v = warp + c * TS_NW;
+          for (int c = 0; c < 4; ++c) {
+            const int v = warp + (c0 + c) * TS_NW;
             if (v < TS_PART && (v < wn || v == TS_W)) {
               const double tv = warp_sum(t[c]);
               if (lane == 0) red[v] = tv;
             }
           }
+          if (c0 * TS_NW >= wn && c0 + 4 <= TS_W / TS_NW) c0 = TS_W / TS_NW - 4; // nothing left but the ||r||^2 slot
         }
         buf ^= 1;
         __syncthreads();
         // the coordinates ahead of the first one that moves leave r as it is, so every position of the window is decided
         // on its own (thread w: position w) and the first mover ends the window
         const double rr = red[TS_W];
-        if (tid < 64) {
+        if (tid < TS_W) {
           double nw = 0.0, h = 0.0;
           if (tid < wn) {
             nw = ts_step(red[tid], scol[tid], sxk[tid], slam[tid] * lam, rr, sqrt(rr));
@@ -268,7 +272,9 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
           if (lane == 0) smv[warp] = bal ? __ffs(bal) - 1 + 32 * warp : -1;
         }
         __syncthreads();
-        const int moved = smv[0] >= 0 ? smv[0] : smv[1];
+        int moved = -1;
+#pragma unroll
+        for (int q = TS_W / 32 - 1; q >= 0; --q) moved = smv[q] >= 0 ? smv[q] : moved;
         double hmv = 0.0, nwv = 0.0;
         if (moved >= 0) {
           hmv = sh[moved];
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
         } else {
           __syncthreads();
           i0 += wn;
-          wcap = min(TS_W, 2 * wcap);
+          wcap = min(wmax, 2 * wcap);
         }
       }
       // ---- dropzeros!(x) on CTA 0 (the last stored entry moves into a hole), then everyone learns the new list
@@ -415,7 +421,10 @@ int launch_tall_sqrt(cdgpu_handle_s *h, const NaiveArgs &a) {
   if (!h->dtall) CUDA_TRY(cudaMalloc((void **)&h->dtall, part_doubles * sizeof(double)));
   double *part = h->dtall;
   int Larg = L;
-  void *args[] = {(void *)&a, (void *)&part, (void *)&Larg, (void *)&r_in_smem};
+  // positions per window of a full pass: about 400 MB of columns per barrier, 64..256
+  int wmax = (int)std::min<long long>(TS_W, std::max<long long>(64, (400000000ll / (8ll * a.n) + 63) / 64 * 64));
+  if (const char *env = getenv("CDGPU_TALL_WINDOW")) wmax = std::max(1, std::min(TS_W, atoi(env)));
+  void *args[] = {(void *)&a, (void *)&part, (void *)&Larg, (void *)&r_in_smem, (void *)&wmax};
   CUDA_TRY(cudaLaunchCooperativeKernel(tall_sqrt_kernel, dim3(G), dim3(TS_T), args, dyn, h->stream));
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
