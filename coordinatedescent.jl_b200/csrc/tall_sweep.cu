@@ -23,7 +23,9 @@ namespace cg = cooperative_groups;
 namespace {
 constexpr int TS_T = 512, TS_NW = TS_T / 32;
 constexpr int TS_W = 256, TS_PART = TS_W + 1; // most positions per window; doubles per CTA and buffer: the dots + the slice's ||r||^2
-constexpr int TS_HDR = 1700;                  // shared doubles ahead of the r slice
+constexpr int TS_HDR = 2930;                  // shared doubles ahead of the r slice
+constexpr int TS_GM = 32;                     // longest list whose passes run on its Gram (one lane per entry)
+constexpr int TS_GPART = 532;                 // doubles per CTA: 32*31/2 pair dots + 32 dots with r + ... + the slice's ||r||^2 (last)
 
 __device__ __forceinline__ double2 ts_ld2(const double2 *p) { // X is read once per visit: keep it out of L1
   double2 v;
@@ -81,7 +83,7 @@ __device__ __forceinline__ double ts_step(double s0, double a, double old, doubl
   return s > t ? (s - q) / a : (s + q) / a;
 }
 
-__global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, double *part, int L, int r_in_smem, int wmax) {
+__global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, double *part, int L, int r_in_smem, int wmax, double *gpart) {
   extern __shared__ __align__(16) double ts_sm[];
   double *red = ts_sm;           // [0, TS_PART): sums over the CTAs of the window's dots and of ||r||^2
   double *wred = ts_sm + 264;    // [264, 280): per-warp partials of a block reduction
@@ -89,6 +91,11 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
   double *tmp1 = ts_sm + 281;
   int *smv = reinterpret_cast<int *>(ts_sm + 282); // [282, 290): per warp of deciders, first mover [0, 8) / first stored entry [8, 16)
   int *sk = reinterpret_cast<int *>(ts_sm + 290);  // [290, 418): the window's coordinates
+  // passes over the stored entries on the Gram of the list
+  double *Gs = ts_sm + 1700, *ds = ts_sm + 2724, *bs = ts_sm + 2756, *b0 = ts_sm + 2788, *acol = ts_sm + 2820, *lamv = ts_sm + 2852;
+  int *ord = reinterpret_cast<int *>(ts_sm + 2884), *crd = reinterpret_cast<int *>(ts_sm + 2900);
+  double *res = ts_sm + 2916; // maxH, ||r||^2, visits
+  int *resi = reinterpret_cast<int *>(ts_sm + 2920); // list length, passes, converged, accepted
   double *sxk = ts_sm + 418, *scol = ts_sm + 674, *slam = ts_sm + 930, *sh = ts_sm + 1186, *snw = ts_sm + 1442; // x_k, a_k, omega_k, h, new x_k
   const int G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long row0 = (long long)bid * L;
@@ -146,6 +153,170 @@ __global__ void __launch_bounds__(TS_T, 1) tall_sqrt_kernel(const NaiveArgs a, d
     st.converged = 0;
     bool conv = true;
     for (long long iter = 1; iter <= a.maxIter; ++iter) {
+      if (!conv && gpart && nact >= 1 && nact <= TS_GM) {
+        // ---- the passes over the stored entries (until one of them converges) on the Gram of the list: with
+        // G = X_A' X_A and d = X_A' r a visit is s0 = d_g, and a step h of entry g is d -= h G[:, g],
+        // ||r||^2 += h (h a_g - 2 s0); r itself is brought up to date once at the end.  Two grid barriers for the whole
+        // phase instead of one per visit; every CTA runs the same chain on the same sums (warp 0, one lane per entry).
+        const int m0 = nact, npair = m0 * (m0 - 1) / 2, nval = npair + m0;
+        if (tid < m0) {
+          const int k = __ldcg(a.act + tid);
+          crd[tid] = k;
+          const double b = __ldcg(a.beta + k);
+          b0[tid] = b;
+          bs[tid] = b;
+          acol[tid] = __ldg(a.colsq + k);
+          lamv[tid] = a.omega ? __ldg(a.omega + k) : 1.0;
+          ord[tid] = tid;
+        }
+        __syncthreads();
+        double *gmine = gpart + (long long)bid * TS_GPART;
+        for (int q = warp; q < nval; q += TS_NW) {
+          int i = 0, j;
+          const double *y;
+          if (q < npair) { // pair (i, j), i < j
+            int rem = q;
+            while (rem >= m0 - 1 - i) {
+              rem -= m0 - 1 - i;
+              i += 1;
+            }
+            j = i + 1 + rem;
+            y = a.X + (long long)crd[j] * a.ldx + row0;
+          } else {
+            i = q - npair;
+            y = r;
+          }
+          const double *x = a.X + (long long)crd[i] * a.ldx + row0;
+          double acc0 = 0.0, acc1 = 0.0;
+          int t = lane;
+          for (; t + 32 < len; t += 64) {
+            acc0 = fma(__ldg(x + t), y[t], acc0);
+            acc1 = fma(__ldg(x + t + 32), y[t + 32], acc1);
+          }
+          if (t < len) acc0 = fma(__ldg(x + t), y[t], acc0);
+          const double v = warp_sum(acc0 + acc1);
+          if (lane == 0) __stcg(gmine + q, v);
+        }
+        if (tid == 0) __stcg(gmine + TS_GPART - 1, *slice_rr);
+        ts_grid_sync(ctr, target, (unsigned)G);
+        for (int q = warp; q <= nval; q += TS_NW) {
+          const double *src = gpart + (q < nval ? q : TS_GPART - 1);
+          double t = 0.0;
+          for (int g = lane; g < G; g += 32) t += __ldcg(src + (long long)g * TS_GPART);
+          t = warp_sum(t);
+          if (lane == 0) {
+            if (q < npair) {
+              int i = 0, rem = q;
+              while (rem >= m0 - 1 - i) {
+                rem -= m0 - 1 - i;
+                i += 1;
+              }
+              const int j = i + 1 + rem;
+              Gs[i * TS_GM + j] = t;
+              Gs[j * TS_GM + i] = t;
+            } else if (q < nval) {
+              ds[q - npair] = t;
+            } else {
+              res[1] = t;
+            }
+          }
+        }
+        if (tid < m0) Gs[tid * TS_GM + tid] = acol[tid];
+        __syncthreads();
+        if (warp == 0) {
+          const bool on = lane < m0;
+          double d = on ? ds[lane] : 0.0, be = on ? bs[lane] : 0.0;
+          const double ac = on ? acol[lane] : 1.0, lm = on ? lamv[lane] * lam : 0.0;
+          double rr = res[1], maxH = 0.0;
+          int mcur = m0, acc = 0;
+          long long np = 0, vis = 0;
+          const long long left = a.maxIter - iter + 1;
+          bool cv = false;
+          while (np < left) {
+            const PermKey pk = cd_perm_key((uint32_t)max(mcur, 1), a.seed, pass_counter + (unsigned long long)np);
+            maxH = 0.0;
+            for (int i = 0; i < mcur; ++i) {
+              const int g = ord[ordered ? i : (int)cd_perm(pk, (uint32_t)i)];
+              const double s0 = __shfl_sync(0xffffffffu, d, g), old = __shfl_sync(0xffffffffu, be, g);
+              const double ag = __shfl_sync(0xffffffffu, ac, g), lg = __shfl_sync(0xffffffffu, lm, g);
+              const double nw = ts_step(s0, ag, old, lg, rr, sqrt(rr));
+              const double h = nw - old;
+              if (fabs(h) > maxH) maxH = fabs(h);
+              if (h != 0.0) {
+                acc += 1;
+                if (on) d = fma(-h, Gs[lane * TS_GM + g], d);
+                rr = fma(h, fma(h, ag, -2.0 * s0), rr);
+                if (lane == g) be = nw;
+              }
+            }
+            vis += mcur;
+            np += 1;
+            if (on) bs[lane] = be;
+            __syncwarp();
+            if (lane == 0) { // dropzeros!: the last stored entry moves into a hole
+              int i = 0, mm = mcur;
+              while (i < mm) {
+                if (bs[ord[i]] == 0.0) {
+                  if (i != mm - 1) ord[i] = ord[mm - 1];
+                  mm -= 1;
+                } else {
+                  i += 1;
+                }
+              }
+              resi[0] = mm;
+            }
+            __syncwarp();
+            mcur = resi[0];
+            cv = maxH < a.optTol;
+            if (cv) break;
+          }
+          if (lane == 0) {
+            res[0] = maxH;
+            res[2] = (double)vis;
+            resi[1] = (int)np;
+            resi[2] = cv ? 1 : 0;
+            resi[3] = acc;
+          }
+        }
+        __syncthreads();
+        const int mcur = resi[0], np = resi[1];
+        { // r -= X_A (x - x at entry), ||r||^2 of the slice afresh (a thread owns the same rows for every column)
+          for (int g = 0; g < m0; ++g) {
+            const double dlt = bs[g] - b0[g];
+            if (dlt == 0.0) continue;
+            const double *col = a.X + (long long)crd[g] * a.ldx + row0;
+            for (int i = tid; i < len; i += TS_T) r[i] = fma(-__ldg(col + i), dlt, r[i]);
+          }
+          double acc = 0.0;
+          for (int i = tid; i < len; i += TS_T) acc = fma(r[i], r[i], acc);
+          block_sum_to(acc, slice_rr);
+        }
+        if (bid == 0) {
+          if (tid < m0) {
+            __stcg(a.beta + crd[tid], bs[tid]);
+            a.inlist[crd[tid]] = 0;
+          }
+          __syncthreads();
+          if (tid < mcur) {
+            const int g = ord[tid];
+            a.act[tid] = crd[g];
+            a.actval[tid] = bs[g];
+            a.inlist[crd[g]] = 1;
+          }
+          if (tid == 0) *a.nact = mcur;
+        }
+        ts_grid_sync(ctr, target, (unsigned)G);
+        nact = mcur;
+        st.passes += np;
+        st.visits += (long long)res[2];
+        st.accepted += resi[3];
+        st.maxH = res[0];
+        pass_counter += (unsigned long long)np;
+        conv = resi[2] != 0;
+        iter += np - 1;
+        __syncthreads(); // the phase's shared results are read; the next pass may refill the header
+        continue;
+      }
       const bool full = conv;
       const int seqlen = full ? a.p : nact;
       const PermKey pk = cd_perm_key((uint32_t)max(seqlen, 1), a.seed, pass_counter);
@@ -417,14 +588,17 @@ int launch_tall_sqrt(cdgpu_handle_s *h, const NaiveArgs &a) {
     r_in_smem = 0;
     dyn = (size_t)TS_HDR * sizeof(double);
   }
-  const size_t part_doubles = (size_t)2 * h->sm_count * TS_PART;
+  const size_t part_doubles = (size_t)2 * h->sm_count * TS_PART + (size_t)h->sm_count * TS_GPART;
   if (!h->dtall) CUDA_TRY(cudaMalloc((void **)&h->dtall, part_doubles * sizeof(double)));
   double *part = h->dtall;
   int Larg = L;
   // positions per window of a full pass: about 400 MB of columns per barrier, 64..256
   int wmax = (int)std::min<long long>(TS_W, std::max<long long>(64, (400000000ll / (8ll * a.n) + 63) / 64 * 64));
   if (const char *env = getenv("CDGPU_TALL_WINDOW")) wmax = std::max(1, std::min(TS_W, atoi(env)));
-  void *args[] = {(void *)&a, (void *)&part, (void *)&Larg, (void *)&r_in_smem, (void *)&wmax};
+  double *gpart = part + (size_t)2 * h->sm_count * TS_PART;
+  if (const char *env = getenv("CDGPU_TALL_GRAM"))
+    if (atoi(env) == 0) gpart = nullptr; // passes over the stored entries visit by visit
+  void *args[] = {(void *)&a, (void *)&part, (void *)&Larg, (void *)&r_in_smem, (void *)&wmax, (void *)&gpart};
   CUDA_TRY(cudaLaunchCooperativeKernel(tall_sqrt_kernel, dim3(G), dim3(TS_T), args, dyn, h->stream));
   CD_COUNT_LAUNCH(1);
   return CDGPU_OK;
