@@ -48,7 +48,7 @@ C2_VISITS = 3990575
 NCU_TRAFFIC = {
     "gram_syrk_kernel": (30.228562e9 + 3.203871e9, "profiles/r1d_kernels_ncu.txt"),
     "naive_path_kernel_c3": (6.542697e9 + 0.010799e9, "profiles/r5_naive_path_ncu.txt"),
-    "tall_sqrt_kernel": (9.675816e9 + 0.003752e9, "profiles/r7_tall_sqrt_ncu.txt (same n, p; profiles/run_kernels.py tall)"),
+    "tall_sqrt_kernel": (9.621257e9 + 0.005187e9, "profiles/r8_tall_sqrt_ncu.txt (same n, p; profiles/run_kernels.py tall)"),
 }
 try:
     NCU_TRAFFIC.update({k: tuple(v) for k, v in json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).items()})

@@ -812,10 +812,13 @@ def test_tall_naive_problem_solves_through_the_lazy_covariance_form(gpu, ref, ki
 def test_row_distributed_sqrt_lasso_retraces_oracle(gpu, ref, randomize, grid, monkeypatch):
     """tall_sweep.cu (the residual form with the rows dealt over the grid) forced on a small problem: same passes, visits
     and accepted steps as the oracle, warm and cold (the internal continuation of coordinate_descent.jl:28-36), ordered
-    and random visits, a λ path through the same launch, weighted penalty; `grid=3` leaves 100 rows per CTA."""
+    and random visits, a λ path through the same launch, weighted penalty; `grid=3` leaves 100 rows per CTA and also covers the visit-by-visit form of the
+    stored-entry passes and a window width that is not a multiple of the warp count."""
     monkeypatch.setenv("CDGPU_FORCE_TALL", "1")
     if grid:
         monkeypatch.setenv("CDGPU_TALL_GRID", str(grid))
+        monkeypatch.setenv("CDGPU_TALL_GRAM", "0")  # passes over the stored entries visit by visit (default: on the list's Gram)
+        monkeypatch.setenv("CDGPU_TALL_WINDOW", "48")
     rng = np.random.default_rng(77)
     n, p, s = 300, 700, 10
     X, y, _ = gauss_problem(n, p, s, seed=78)
