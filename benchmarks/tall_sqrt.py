@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Tall sqrt-lasso (CDSqrtLassoLoss, n beyond one CTA's shared memory): the row-distributed residual-form sweep of
 tall_sweep.cu against the CPU oracle port on the same data.  One JSON line.
-Usage: python benchmarks/tall_sqrt.py [n] [p] [--cpu]"""
+Usage: python benchmarks/tall_sqrt.py [n] [p] [s] [--cpu]      (s: non-zeros of the generating model)"""
 import json
 import os
 import sys
@@ -27,7 +27,7 @@ def main():
     p = int(args[1]) if len(args) > 1 else 1000
     rng = np.random.default_rng(11)
     X = np.asfortranarray(rng.standard_normal((p, n)).T)
-    s = 10
+    s = int(args[2]) if len(args) > 2 else 10
     y = X[:, :s] @ (1.0 + rng.random(s)) + rng.standard_normal(n)
     lam = 1.1 * np.sqrt(2 * np.log(p))
     opt = CDOptions(maxIter=2000, optTol=1e-7, randomize=False)
